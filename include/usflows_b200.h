@@ -1,0 +1,177 @@
+/* usflows_b200 -- C ABI of the B200 (sm_100a) flow-evaluation library  (libusflows_b200.so)
+ *
+ * Drop-in boundary for the hot path of aai-institute/USFlows: the per-layer forward (sample) and
+ * backward (log_prob) passes of a `Flow`/`USFlow` layer stack and the base-distribution log-density.
+ * The reference is pure Python/PyTorch and has no FFI of its own; each entry point below names the
+ * reference call site(s) (file:line under /root/reference/src/usflows) whose arithmetic it replaces.
+ * The Python host package `usflows_b200` binds these symbols with ctypes.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless the name ends in `_host`; buffers are caller-owned
+ *  - matrices are row-major; `ld*` are leading dimensions in ELEMENTS
+ *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream)
+ *  - every function returns USF_OK (0) or a negative USF_ERR_* code; the message is in usf_last_error()
+ *  - no CPU fallback exists: without a CUDA device every compute entry point returns USF_ERR_CUDA
+ */
+#ifndef USFLOWS_B200_H
+#define USFLOWS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define USF_ABI_VERSION 1
+
+#define USF_OK 0
+#define USF_ERR_INVALID (-1)     /* bad argument (shape, alignment, null pointer) */
+#define USF_ERR_CUDA (-2)        /* CUDA runtime / driver error, no device, launch failure */
+#define USF_ERR_UNSUPPORTED (-3) /* valid request this build cannot serve */
+#define USF_ERR_INFEASIBLE (-4)  /* a layer is not invertible (zero on diag(U) or in scale) */
+
+/* contraction engines (usf_linear_args.engine) */
+#define USF_ENGINE_SIMT 0      /* fp32 FFMA, CUDA cores; any shape / alignment                         */
+#define USF_ENGINE_TC_3XTF32 1 /* tcgen05 kind::tf32, 3-term split (hi*hi + lo*hi + hi*lo): ~fp32 accuracy */
+#define USF_ENGINE_TC_TF32 2   /* tcgen05 kind::tf32, single pass                                      */
+#define USF_ENGINE_TC_BF16 3   /* tcgen05 kind::f16 (bf16 operands), fp32 accumulate                   */
+
+/* base distributions (distributions.py:199-238) */
+#define USF_BASE_LAPLACE 0
+#define USF_BASE_NORMAL 1
+
+const char* usf_last_error(void);
+int usf_abi_version(void);
+/* device properties of the current CUDA device; any pointer may be NULL */
+int usf_device_info(int* sm_count, int* cc_major, int* cc_minor, int64_t* l2_bytes);
+
+/* ------------------------------------------------------------------------------------------------
+ * usf_linear: out[M,N] = epilogue( A[M,K] . W[N,K]^T )
+ *   v = acc + bias[n]; if relu: v = max(v,0); if resid: v = resid[m,n] + resid_sign * v;
+ *   if colscale: v *= colscale[n]; if postsub: v -= postsub[n]; stored to every non-NULL output plane.
+ * Replaces: F.linear in BlockAffineTransform.forward/backward (transforms.py:934, 960-961),
+ *           LUTransform.forward/backward (:1255, :1267-1268), pyro.nn.DenseNN's Linear+ReLU stack,
+ *           the masked residual add/sub of MaskedCoupling.forward/backward (:284-290, :301-306) and
+ *           ScaleTransform.forward (:105-114) when fused as `colscale`.
+ * Operand planes by engine:
+ *   SIMT      a (fp32) [+ a_lo added to it], w (fp32) [+ w_lo]; trans_w=1 reads w as [K,N]
+ *   TC_3XTF32 a, a_lo, w, w_lo: fp32 storage holding tf32-representable values (x = hi + lo)
+ *   TC_TF32   a, w fp32 (low 13 mantissa bits ignored by the tensor core)
+ *   TC_BF16   a, w bf16
+ * tcgen05 engines need 16-byte aligned operand pointers and lda/ldw multiples of 4 (8 for bf16).
+ */
+typedef struct usf_linear_args {
+  int64_t M;
+  int32_t N;
+  int32_t K;
+  int32_t engine;
+  int32_t trans_w;
+  const void* a;
+  const void* a_lo;
+  int64_t lda;
+  const void* w;
+  const void* w_lo;
+  int64_t ldw;
+  const float* bias;
+  int32_t relu;
+  float resid_sign;
+  const float* resid;
+  const float* resid_lo;
+  int64_t ldr;
+  const float* colscale;
+  const float* postsub;
+  float* out_f32;
+  int64_t ld_f32;
+  float* out_hi;
+  float* out_lo;
+  int64_t ld_split;
+  void* out_bf16;
+  int64_t ld_bf16;
+} usf_linear_args;
+
+int usf_linear(const usf_linear_args* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * elementwise / reduction kernels over [N_rows, d] activations (HBM-bound, 128-bit accesses)
+ */
+
+/* out = ((x / div[j]) * mul[j]) - sub[j]  (each vector optional), written to any of the planes.
+ * Replaces ScaleTransform.backward (transforms.py:116-125), ScaleTransform.forward (:105-114), the
+ * `y - b` of BlockAffineTransform.backward (:959) for the first layer, and the fp32 -> operand-format
+ * conversion of user input. */
+int usf_ingest(const float* x, int64_t ldx, int64_t rows, int32_t d, const float* div, const float* mul,
+               const float* sub, float* out_f32, int64_t ld_f32, float* out_hi, float* out_lo,
+               int64_t ld_split, void* out_bf16, int64_t ld_bf16, void* stream);
+
+/* out[r] = sum_j logpdf_base(z[r,j]; loc[j], scale[j]) + add_const  (z = z_hi [+ z_lo]).
+ * Replaces DistributionModule.log_prob (distributions.py:150-151; torch Laplace/Normal.log_prob +
+ * Independent sum) and the `+ log_det` of Flow.log_prob (flows.py:234-245). */
+int usf_base_logprob(const float* z, const float* z_lo, int64_t ldz, int64_t rows, int32_t d,
+                     const float* loc, const float* scale, int32_t base_kind, float add_const,
+                     float* out, void* stream);
+
+/* z[r,j] = loc[j] + scale[j] * eps with eps ~ Laplace(0,1) or N(0,1) from Philox4x32-10(seed, offset).
+ * Replaces DistributionModule.sample (distributions.py:147-148) in Flow.sample (flows.py:258). */
+int usf_base_sample(int64_t rows, int32_t d, const float* loc, const float* scale, int32_t base_kind,
+                    uint64_t seed, uint64_t offset, float* out_f32, int64_t ld_f32, float* out_hi,
+                    float* out_lo, int64_t ld_split, void* out_bf16, int64_t ld_bf16, void* stream);
+
+/* y = x >= 0 ? x : slope * x ; optional per-row count of negative inputs (for log|det J| = log(slope)*count).
+ * Replaces LeakyReLUTransform.forward/backward (transforms.py:434-454). */
+int usf_leaky_relu(const float* x, int64_t ldx, int64_t rows, int32_t d, float slope, float* y,
+                   int64_t ldy, float* neg_count, void* stream);
+
+/* y[r,j] = x[r,perm[j]].  Replaces Permute._call/_inverse (transforms.py:213-232). */
+int usf_permute(const float* x, int64_t ldx, int64_t rows, int32_t d, const int32_t* perm, float* y,
+                int64_t ldy, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * weight preparation (runs once per weight version; all matrices [d,d] fp32 with leading dim ld)
+ */
+
+/* L = tril(L_raw,-1) + I  and  U = triu(U_raw)  (transforms.py:1271-1279); either output may be NULL.
+ * `transpose_u` writes U^T instead (operand layout for L @ U as A . B^T). */
+int usf_lu_assemble(const float* L_raw, const float* U_raw, int32_t d, int64_t ld_raw, float* L, float* U,
+                    int64_t ld_out, int32_t transpose_u, void* stream);
+
+/* out[0] = sum_i log|U_raw[i,i]| (transforms.py:1303-1320), out[1] = number of zero diagonal entries
+ * (LUTransform.is_feasible, :1347-1349).  `out` is 2 floats on the device. */
+int usf_lu_logabsdet(const float* U_raw, int32_t d, int64_t ld, float* out, void* stream);
+
+/* out[0] = sum log|v_j| , out[1] = number of zeros (ScaleTransform.log_abs_det_jacobian / is_feasible,
+ * transforms.py:135-152). */
+int usf_vec_logabs(const float* v, int64_t n, float* out, void* stream);
+
+/* X = T^-1 for a triangular T (lower != 0: lower triangular, else upper); unit_diag != 0 takes the
+ * diagonal as 1.  Replaces torch.inverse(self.L) / torch.inverse(self.U) (transforms.py:1264-1265,
+ * 1291-1292).  `work` is a device scratch of usf_tri_inverse_work_floats(d) floats. */
+int64_t usf_tri_inverse_work_floats(int32_t d);
+int usf_tri_inverse(const float* T, int32_t d, int64_t ldt, int32_t lower, int32_t unit_diag, float* X,
+                    int64_t ldx, float* work, void* stream);
+
+/* out[c,r] = in[r,c] */
+int usf_transpose(const float* in, int32_t rows, int32_t cols, int64_t ld_in, float* out, int64_t ld_out,
+                  void* stream);
+
+/* out[r,c] = in[r,c] * rowf[r] * colf[c]   (either factor vector optional) -- folds the coupling mask
+ * into the conditioner's first / last Linear (transforms.py:284-289). */
+int usf_scale_rows_cols(const float* in, int32_t rows, int32_t cols, int64_t ld_in, const float* rowf,
+                        const float* colf, float* out, int64_t ld_out, void* stream);
+
+/* tf32 split planes / bf16 copy of an fp32 matrix (operand formats of the tcgen05 engines) */
+int usf_split_tf32(const float* in, int64_t rows, int32_t cols, int64_t ld_in, float* hi, float* lo,
+                   int64_t ld_out, void* stream);
+int usf_to_bf16(const float* in, int64_t rows, int32_t cols, int64_t ld_in, void* out, int64_t ld_out,
+                void* stream);
+
+/* W <- W @ (I - 2 v v^T / v.v) in place (one Householder reflection, transforms.py:795-809);
+ * `work` = d floats. */
+int usf_householder_right(float* W, int32_t d, int64_t ld, const float* v, float* work, void* stream);
+
+/* out[j] = softplus(in[j])  (distributions.py:211-215, base scale parameterisation) */
+int usf_softplus(const float* in, int64_t n, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* USFLOWS_B200_H */

@@ -1,0 +1,177 @@
+"""TEST-ONLY stand-in for the C ABI: emulates every `usflows_b200.ops` entry point with torch CPU ops so the
+host logic (layer planning, fusion, plane bookkeeping, weight-preparation order, caching, state-dict
+compatibility) can be tested without a GPU.  Installed by the `fake_ops` fixture through monkeypatching;
+never importable from the product package."""
+import torch
+
+from usflows_b200 import ops as real_ops
+from usflows_b200.ops import Act, ENGINE_SIMT, ENGINE_TC_3XTF32, ENGINE_TC_BF16, ENGINE_TC_TF32
+
+CALLS = []
+
+
+def tf32_round(x: torch.Tensor) -> torch.Tensor:
+    i = x.contiguous().view(torch.int32)
+    i = (i + 0x1000) & ~0x1FFF
+    return i.view(torch.float32)
+
+
+def _store(out: Act, v: torch.Tensor):
+    if out.f32 is not None:
+        out.f32.copy_(v)
+    if out.hi is not None:
+        h = tf32_round(v)
+        out.hi.copy_(h)
+        out.lo.copy_(tf32_round(v - h))
+    if out.bf16 is not None:
+        out.bf16.copy_(v.to(torch.bfloat16))
+
+
+def linear(engine, a, w, w_lo, N, K, *, bias=None, relu=False, resid=None, resid_sign=1.0, colscale=None,
+           postsub=None, out=None, trans_w=False):
+    CALLS.append(("linear", engine, a.rows, N, K))
+    if engine == ENGINE_TC_BF16:
+        A = a.bf16.float()
+        W = w.float()
+    elif engine == ENGINE_TC_3XTF32:
+        assert a.hi is not None and a.lo is not None and w_lo is not None
+        A, W = a.hi + a.lo, w + w_lo
+    elif engine == ENGINE_TC_TF32:
+        A = a.f32 if a.f32 is not None else a.hi
+        W = w
+    else:
+        A = a.f32 if a.f32 is not None else a.hi + a.lo
+        W = w if w_lo is None else w + w_lo
+    assert A.shape == (a.rows, K), (A.shape, a.rows, K)
+    v = A @ (W if trans_w else W.T)
+    assert v.shape[1] == N
+    if bias is not None:
+        v = v + bias
+    if relu:
+        v = torch.relu(v)
+    if resid is not None:
+        r, rl = resid.resid_planes()
+        r = r if rl is None else r + rl
+        v = r + resid_sign * v
+    if colscale is not None:
+        v = v * colscale
+    if postsub is not None:
+        v = v - postsub
+    _store(out, v)
+
+
+def ingest(x, out, *, div=None, mul=None, sub=None):
+    CALLS.append(("ingest",))
+    v = x
+    if div is not None:
+        v = v / div
+    if mul is not None:
+        v = v * mul
+    if sub is not None:
+        v = v - sub
+    _store(out, v)
+
+
+def base_logprob(z, loc, scale, kind, add_const, out):
+    CALLS.append(("base_logprob",))
+    p, pl = z.resid_planes()
+    v = p if pl is None else p + pl
+    if kind == real_ops.BASE_LAPLACE:
+        lp = -torch.log(2 * scale) - (v - loc).abs() / scale
+    else:
+        lp = -((v - loc) ** 2) / (2 * scale ** 2) - scale.log() - 0.9189385332046727
+    out.copy_(lp.sum(-1) + add_const)
+
+
+def base_sample(out, loc, scale, kind, seed, offset):
+    g = torch.Generator().manual_seed((seed + offset) % (2 ** 63))
+    if kind == real_ops.BASE_LAPLACE:
+        u = torch.rand(out.rows, out.width, generator=g) * 2 - 1
+        e = -u.sign() * torch.log1p(-u.abs())
+    else:
+        e = torch.randn(out.rows, out.width, generator=g)
+    _store(out, loc + scale * e)
+
+
+def leaky_relu(x, slope, y, neg_count=None):
+    y.copy_(torch.where(x >= 0, x, x * slope))
+    if neg_count is not None:
+        neg_count.copy_((x < 0).float().sum(-1))
+
+
+def permute(x, perm_i32, y):
+    y.copy_(x.index_select(-1, perm_i32.long()))
+
+
+def lu_assemble(L_raw, U_raw, L=None, U=None, transpose_u=False):
+    if L is not None:
+        L.copy_(L_raw.tril(-1) + torch.eye(L_raw.shape[0]))
+    if U is not None:
+        U.copy_(U_raw.triu().T if transpose_u else U_raw.triu())
+
+
+def lu_logabsdet(U_raw, out2):
+    d = U_raw.diag()
+    out2[0] = d.abs().log().double().sum().float()
+    out2[1] = float((d == 0).sum())
+
+
+def vec_logabs(v, out2):
+    out2[0] = v.abs().log().double().sum().float()
+    out2[1] = float((v == 0).sum())
+
+
+def tri_inverse(T, lower, unit_diag, X):
+    Tm = T.tril() if lower else T.triu()
+    if unit_diag:
+        Tm = Tm - torch.diag(Tm.diag()) + torch.eye(T.shape[0])
+    X.copy_(torch.inverse(Tm.double()).float())
+
+
+def transpose(a, out):
+    out.copy_(a.T)
+
+
+def scale_rows_cols(a, out, rowf=None, colf=None):
+    v = a
+    if rowf is not None:
+        v = v * rowf[:, None]
+    if colf is not None:
+        v = v * colf[None, :]
+    out.copy_(v)
+
+
+def split_tf32(a, hi, lo):
+    h = tf32_round(a)
+    hi.copy_(h)
+    if lo is not None:
+        lo.copy_(tf32_round(a - h))
+
+
+def to_bf16(a, out):
+    out.copy_(a.to(torch.bfloat16))
+
+
+def householder_right(W, v, work):
+    W.copy_(W - torch.outer(W @ v, v) * (2.0 / torch.dot(v, v)))
+
+
+def softplus(a, out):
+    out.copy_(torch.nn.functional.softplus(a))
+
+
+def matmul_f32(a, b, out, bias=None):
+    v = a @ b
+    out.copy_(v if bias is None else v + bias)
+
+
+def require_cuda(t, name="tensor", dtype=torch.float32):
+    return t
+
+
+def install(monkeypatch):
+    CALLS.clear()
+    for name in ["linear", "ingest", "base_logprob", "base_sample", "leaky_relu", "permute", "lu_assemble",
+                 "lu_logabsdet", "vec_logabs", "tri_inverse", "transpose", "scale_rows_cols", "split_tf32", "to_bf16",
+                 "householder_right", "softplus", "matmul_f32", "require_cuda"]:
+        monkeypatch.setattr(real_ops, name, globals()[name])

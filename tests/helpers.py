@@ -1,0 +1,45 @@
+"""Shared test helpers: golden-fixture loading and construction of product flows from an oracle spec."""
+import json
+import os
+
+import numpy as np
+import torch
+
+from oracle import flow_oracle as O
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+SMALL_CASES = ["c1_d2_laplace", "d2_refinit", "d6_hh_normal", "d5_noconj", "d32_h64", "d100_h50_hh"]
+LARGE_CASES = ["c2_d784", "c4_d3072_b2"]
+
+
+def load_case(name):
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    spec = json.loads(bytes(z["spec"]).decode())
+    params = {k[len("param:"):]: torch.from_numpy(z[k]) for k in z.files if k.startswith("param:")}
+    if not params:
+        params = O.random_params(spec, int(z["seed"]))
+    arrays = {k: torch.from_numpy(np.asarray(z[k])) for k in z.files
+              if not k.startswith("param:") and k not in ("spec", "seed", "truth64_from_reference")}
+    return spec, params, arrays
+
+
+def build_flow(spec, params, device="cuda", precision=None):
+    """usflows_b200.USFlow with the reference state-dict loaded."""
+    import usflows_b200 as U
+    d = spec["in_dims"][0]
+    base_cls = U.Laplace if spec.get("base", "laplace") == "laplace" else U.Normal
+    flow = U.USFlow(
+        base_distribution=base_cls(torch.zeros(d), torch.ones(d)), in_dims=list(spec["in_dims"]),
+        coupling_blocks=spec["coupling_blocks"], conditioner_cls=U.DenseNN,
+        conditioner_args=dict(input_dim=d, hidden_dims=list(spec["hidden_dims"]), param_dims=[d]),
+        prior_scale=1.0, lu_transform=spec.get("lu_transform", 1), householder=spec.get("householder", 1),
+        affine_conjugation=spec.get("affine_conjugation", False), precision=precision)
+    res = flow.load_state_dict(params, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    return flow.to(device)
+
+
+def rel_err(a, b):
+    """max |a - b| / max(max |b|, 1): norm-wise relative error used for every parity statement."""
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp(min=1.0))

@@ -1,0 +1,121 @@
+"""Host-side logic (planning, fusion, plane bookkeeping, weight-prep order, caching, state-dict layout) tested on
+CPU against the golden fixtures, with the C ABI replaced by a torch emulation (tests/fake_backend.py)."""
+import pytest
+import torch
+
+import fake_backend
+from helpers import LARGE_CASES, SMALL_CASES, build_flow, load_case, rel_err
+
+
+@pytest.fixture
+def fake_ops(monkeypatch):
+    fake_backend.install(monkeypatch)
+    return fake_backend
+
+
+@pytest.mark.parametrize("mode", ["fp32_simt", "fp32", "tf32"])
+@pytest.mark.parametrize("name", SMALL_CASES + ["c2_d784"])
+def test_flow_program_matches_reference(fake_ops, name, mode):
+    spec, params, arr = load_case(name)
+    flow = build_flow(spec, params, device="cpu", precision=mode)
+    lp = flow.log_prob(arr["x"])
+    z = flow.backward(arr["x"])
+    y = flow._forward(arr["z0"])
+    tol = 2e-5 if mode != "tf32" else 1e-4       # the emulated tf32 engine multiplies in fp32
+    assert rel_err(lp, arr["lp32"]) < tol
+    assert rel_err(z, arr["z32"]) < 5e-5
+    assert rel_err(y, arr["y32"]) < 5e-5
+
+
+def test_bf16_mode_runs_with_its_own_bound(fake_ops):
+    spec, params, arr = load_case("d32_h64")
+    flow = build_flow(spec, params, device="cpu", precision="bf16")
+    assert rel_err(flow.log_prob(arr["x"]), arr["lp32"]) < 5e-2
+
+
+def test_kernel_count_per_log_prob(fake_ops):
+    """one ingest + 5B+1 contractions + one base-density reduction for a conjugated USFlow (B blocks)."""
+    spec, params, arr = load_case("d32_h64")
+    flow = build_flow(spec, params, device="cpu", precision="fp32")
+    flow.log_prob(arr["x"])               # includes weight preparation
+    fake_backend.CALLS.clear()
+    flow.log_prob(arr["x"])               # steady state: prepared weights are cached
+    kinds = [c[0] for c in fake_backend.CALLS]
+    B = spec["coupling_blocks"]
+    assert kinds.count("ingest") == 1 and kinds.count("base_logprob") == 1
+    assert kinds.count("linear") == 5 * B + 1
+
+
+def test_prepared_weights_follow_weight_version(fake_ops):
+    spec, params, arr = load_case("d6_hh_normal")
+    flow = build_flow(spec, params, device="cpu", precision="fp32_simt")
+    lp0 = flow.log_prob(arr["x"])
+    with torch.no_grad():
+        flow.layers[-1].scale.mul_(2.0)
+    lp1 = flow.log_prob(arr["x"])
+    assert not torch.allclose(lp0, lp1)
+
+
+def test_state_dict_layout_matches_reference():
+    spec, params, _ = load_case("d6_hh_normal")
+    flow = build_flow(spec, params, device="cpu")
+    assert set(flow.state_dict().keys()) == set(params.keys())
+    for k, v in flow.state_dict().items():
+        assert v.shape == params[k].shape, k
+    # InverseTransform aliases block parameters (same storage), as in the reference
+    sd = flow.state_dict()
+    a = sd["trainable_layers.0.block_transform.transforms.0.L_raw"]
+    b = sd["trainable_layers.2.transform.block_transform.transforms.0.L_raw"]
+    assert a.data_ptr() == b.data_ptr()
+
+
+def test_layer_stack_and_masks():
+    import usflows_b200 as U
+    spec, params, _ = load_case("d5_noconj")
+    flow = build_flow(spec, params, device="cpu")
+    names = [type(l).__name__ for l in flow.layers]
+    assert names == ["BlockAffineTransform", "MaskedCoupling"] * 3 + ["BlockAffineTransform", "ScaleTransform"]
+    assert torch.equal(U.USFlow.create_checkerboard_mask([4]), torch.tensor([[0., 1., 0., 1.]]))
+    assert torch.equal(U.USFlow.create_checkerboard_mask([2, 2]), torch.tensor([[[0., 1.], [1., 0.]]]))
+    assert torch.equal(U.USFlow.create_channel_mask([2, 2]), torch.tensor([[[0., 0.], [1., 1.]]]))
+
+
+def test_cpu_tensor_is_rejected_without_fake_backend():
+    spec, params, arr = load_case("d5_noconj")
+    flow = build_flow(spec, params, device="cpu")
+    with pytest.raises(RuntimeError, match="CUDA"):
+        flow.log_prob(arr["x"])
+
+
+def test_individual_layers(fake_ops):
+    """known-answer tests of the reference (tests/veriflow/transforms_test.py:5-67) through the engine."""
+    import usflows_b200 as U
+    dim = 10
+    t = U.ScaleTransform([dim])
+    with torch.no_grad():
+        t.scale.copy_(torch.ones(dim) * 2)
+    x = torch.ones(1, dim)
+    y = t(x)
+    assert (y == 2 * x).all() and (t.backward(y) == x).all()
+    assert abs(float(t.log_abs_det_jacobian(x, y)) - dim * float(torch.log(torch.tensor(2.0)))) < 1e-6
+
+    t = U.LUTransform(dim)
+    with torch.no_grad():
+        t.L_raw.copy_(torch.tril(torch.ones(dim, dim)))
+        t.U_raw.copy_(torch.eye(dim))
+        t.bias_vector.copy_(torch.zeros(dim))
+    y = t(x)
+    assert (y == (torch.arange(dim) + 1.0)).all() and (t.backward(y) == x).all()
+    assert float(t.log_abs_det_jacobian(x, y)) == 0
+
+    t = U.LeakyReLUTransform()
+    x = torch.tensor([[1.0, -1.0] * 5])
+    y = t(x)
+    assert (y == x * torch.tensor([1.0, 0.01] * 5)).all()
+    assert torch.allclose(t.backward(y), x)
+    assert abs(float(t.log_abs_det_jacobian(x, y)) - 5 * float(torch.log(torch.tensor(0.01)))) < 1e-5
+
+    t = U.Permute(torch.arange(dim))
+    x = torch.arange(dim, dtype=torch.float32).reshape(1, dim)
+    assert (t(x) == x).all() and (t.backward(x) == x).all()
+    assert float(t.log_abs_det_jacobian(x, x)) == 0

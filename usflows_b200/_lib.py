@@ -1,0 +1,99 @@
+"""ctypes binding of libusflows_b200.so -- the only route from the Python host code to the CUDA kernels.
+
+There is no fallback: if the library is missing it is (re)built with nvcc when possible, otherwise importing
+the compute path raises.  Every wrapper raises RuntimeError with `usf_last_error()` on a non-zero status.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import shutil
+
+from . import build as _build
+
+_lib = None
+
+c_f32p = C.c_void_p  # device pointers travel as integers
+c_i64 = C.c_int64
+c_i32 = C.c_int32
+
+
+class LinearArgs(C.Structure):
+    """Mirror of `usf_linear_args` (include/usflows_b200.h)."""
+
+    _fields_ = [
+        ("M", C.c_int64), ("N", C.c_int32), ("K", C.c_int32), ("engine", C.c_int32), ("trans_w", C.c_int32),
+        ("a", C.c_void_p), ("a_lo", C.c_void_p), ("lda", C.c_int64),
+        ("w", C.c_void_p), ("w_lo", C.c_void_p), ("ldw", C.c_int64),
+        ("bias", C.c_void_p), ("relu", C.c_int32), ("resid_sign", C.c_float),
+        ("resid", C.c_void_p), ("resid_lo", C.c_void_p), ("ldr", C.c_int64),
+        ("colscale", C.c_void_p), ("postsub", C.c_void_p),
+        ("out_f32", C.c_void_p), ("ld_f32", C.c_int64),
+        ("out_hi", C.c_void_p), ("out_lo", C.c_void_p), ("ld_split", C.c_int64),
+        ("out_bf16", C.c_void_p), ("ld_bf16", C.c_int64),
+    ]
+
+
+ENGINE_SIMT, ENGINE_TC_3XTF32, ENGINE_TC_TF32, ENGINE_TC_BF16 = 0, 1, 2, 3
+BASE_LAPLACE, BASE_NORMAL = 0, 1
+
+_P, _I64, _I32, _F, _U64 = C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_uint64
+
+# name -> (restype, argtypes); must list every symbol declared in include/usflows_b200.h
+SIGNATURES = {
+    "usf_last_error": (C.c_char_p, []),
+    "usf_abi_version": (C.c_int, []),
+    "usf_device_info": (C.c_int, [C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int64)]),
+    "usf_linear": (C.c_int, [C.POINTER(LinearArgs), _P]),
+    "usf_ingest": (C.c_int, [_P, _I64, _I64, _I32, _P, _P, _P, _P, _I64, _P, _P, _I64, _P, _I64, _P]),
+    "usf_base_logprob": (C.c_int, [_P, _P, _I64, _I64, _I32, _P, _P, _I32, _F, _P, _P]),
+    "usf_base_sample": (C.c_int, [_I64, _I32, _P, _P, _I32, _U64, _U64, _P, _I64, _P, _P, _I64, _P, _I64, _P]),
+    "usf_leaky_relu": (C.c_int, [_P, _I64, _I64, _I32, _F, _P, _I64, _P, _P]),
+    "usf_permute": (C.c_int, [_P, _I64, _I64, _I32, _P, _P, _I64, _P]),
+    "usf_lu_assemble": (C.c_int, [_P, _P, _I32, _I64, _P, _P, _I64, _I32, _P]),
+    "usf_lu_logabsdet": (C.c_int, [_P, _I32, _I64, _P, _P]),
+    "usf_vec_logabs": (C.c_int, [_P, _I64, _P, _P]),
+    "usf_tri_inverse_work_floats": (C.c_int64, [_I32]),
+    "usf_tri_inverse": (C.c_int, [_P, _I32, _I64, _I32, _I32, _P, _I64, _P, _P]),
+    "usf_transpose": (C.c_int, [_P, _I32, _I32, _I64, _P, _I64, _P]),
+    "usf_scale_rows_cols": (C.c_int, [_P, _I32, _I32, _I64, _P, _P, _P, _I64, _P]),
+    "usf_split_tf32": (C.c_int, [_P, _I64, _I32, _I64, _P, _P, _I64, _P]),
+    "usf_to_bf16": (C.c_int, [_P, _I64, _I32, _I64, _P, _I64, _P]),
+    "usf_householder_right": (C.c_int, [_P, _I32, _I64, _P, _P, _P]),
+    "usf_softplus": (C.c_int, [_P, _I64, _P, _P]),
+    "usf_debug_set_block_n": (C.c_int, [C.c_int]),
+}
+
+
+def library_path() -> str:
+    return _build.LIB
+
+
+def load():
+    """Load (building first if the sources changed and nvcc exists).  Raises if impossible."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if _build.needs_build():
+        nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+        if os.path.exists(nvcc) or shutil.which("nvcc"):
+            _build.build()
+        elif not os.path.exists(_build.LIB):
+            raise RuntimeError(
+                "usflows_b200: libusflows_b200.so is not built and nvcc is unavailable; run "
+                "`python -m usflows_b200.build` (there is no CPU fallback)")
+    lib = C.CDLL(_build.LIB)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the ABI and this table disagree
+        fn.restype = res
+        fn.argtypes = args
+    if lib.usf_abi_version() != 1:
+        raise RuntimeError("usflows_b200: ABI version mismatch between _lib.py and the shared library")
+    _lib = lib
+    return lib
+
+
+def check(status: int) -> None:
+    if status != 0:
+        msg = load().usf_last_error().decode(errors="replace")
+        raise RuntimeError(f"usflows_b200 [{status}]: {msg}")

@@ -1,0 +1,274 @@
+// C ABI of libusflows_b200.so (see include/usflows_b200.h for the contract of every entry point).
+#include "common.cuh"
+#include "elementwise.cuh"
+#include "gemm_simt.cuh"
+#include "gemm_tc.cuh"
+#include "prep.cuh"
+
+namespace usf {
+
+thread_local char g_err[512] = "";
+int g_force_block_n = 0;
+
+int num_sms() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
+PFN_encodeTiled get_encode_tiled() {
+  static PFN_encodeTiled fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+
+int make_epilogue(const usf_linear_args* a, Epilogue* ep) {
+  USF_REQUIRE(a->out_f32 || a->out_hi || a->out_bf16, "usf_linear needs at least one output plane");
+  USF_REQUIRE((a->out_hi == nullptr) == (a->out_lo == nullptr), "out_hi and out_lo come as a pair");
+  USF_REQUIRE(!a->resid_lo || a->resid, "resid_lo without resid");
+  ep->bias = a->bias;
+  ep->resid_hi = a->resid;
+  ep->resid_lo = a->resid_lo;
+  ep->colscale = a->colscale;
+  ep->postsub = a->postsub;
+  ep->out_f32 = a->out_f32;
+  ep->out_hi = a->out_hi;
+  ep->out_lo = a->out_lo;
+  ep->out_bf16 = reinterpret_cast<__nv_bfloat16*>(a->out_bf16);
+  ep->ldr = a->ldr;
+  ep->ld_f32 = a->ld_f32;
+  ep->ld_split = a->ld_split;
+  ep->ld_bf16 = a->ld_bf16;
+  ep->resid_sign = a->resid_sign;
+  ep->relu = a->relu;
+  bool ok = true;
+  if (a->bias) ok = ok && aligned16(a->bias);
+  if (a->colscale) ok = ok && aligned16(a->colscale);
+  if (a->postsub) ok = ok && aligned16(a->postsub);
+  if (a->resid) ok = ok && aligned16(a->resid) && a->ldr % 4 == 0;
+  if (a->resid_lo) ok = ok && aligned16(a->resid_lo);
+  if (a->out_f32) ok = ok && aligned16(a->out_f32) && a->ld_f32 % 4 == 0;
+  if (a->out_hi) ok = ok && aligned16(a->out_hi) && aligned16(a->out_lo) && a->ld_split % 4 == 0;
+  if (a->out_bf16) ok = ok && aligned16(a->out_bf16) && a->ld_bf16 % 8 == 0;
+  ep->vec_ok = ok ? 1 : 0;
+  return USF_OK;
+}
+
+static inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+}  // namespace usf
+
+using namespace usf;
+
+extern "C" {
+
+const char* usf_last_error(void) { return g_err; }
+int usf_abi_version(void) { return USF_ABI_VERSION; }
+
+int usf_device_info(int* sm_count, int* cc_major, int* cc_minor, int64_t* l2_bytes) {
+  int dev = 0;
+  USF_CUDA_OK(cudaGetDevice(&dev));
+  int v = 0;
+  if (sm_count) { USF_CUDA_OK(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev)); *sm_count = v; }
+  if (cc_major) { USF_CUDA_OK(cudaDeviceGetAttribute(&v, cudaDevAttrComputeCapabilityMajor, dev)); *cc_major = v; }
+  if (cc_minor) { USF_CUDA_OK(cudaDeviceGetAttribute(&v, cudaDevAttrComputeCapabilityMinor, dev)); *cc_minor = v; }
+  if (l2_bytes) { USF_CUDA_OK(cudaDeviceGetAttribute(&v, cudaDevAttrL2CacheSize, dev)); *l2_bytes = v; }
+  return USF_OK;
+}
+
+int usf_debug_set_block_n(int bn) {  // test hook: force the tcgen05 tile width (0 = automatic)
+  g_force_block_n = bn;
+  return USF_OK;
+}
+
+int usf_linear(const usf_linear_args* a, void* stream) {
+  USF_REQUIRE(a != nullptr, "null args");
+  USF_REQUIRE(a->M >= 0 && a->N >= 0 && a->K >= 0, "negative extent");
+  USF_REQUIRE(a->a && a->w, "null operand");
+  Epilogue ep;
+  int rc = make_epilogue(a, &ep);
+  if (rc) return rc;
+  switch (a->engine) {
+    case USF_ENGINE_SIMT: return launch_gemm_simt(a, ep, S(stream));
+    case USF_ENGINE_TC_3XTF32:
+    case USF_ENGINE_TC_TF32:
+    case USF_ENGINE_TC_BF16: return launch_gemm_tc(a, ep, S(stream));
+  }
+  return fail(USF_ERR_INVALID, "unknown engine%s%s");
+}
+
+int usf_ingest(const float* x, int64_t ldx, int64_t rows, int32_t d, const float* dv, const float* mul,
+               const float* sub, float* out_f32, int64_t ld_f32, float* out_hi, float* out_lo, int64_t ld_split,
+               void* out_bf16, int64_t ld_bf16, void* stream) {
+  USF_REQUIRE(x && rows >= 0 && d > 0, "bad input");
+  USF_REQUIRE((out_hi == nullptr) == (out_lo == nullptr), "out_hi and out_lo come as a pair");
+  if (rows == 0) return USF_OK;
+  OutPlanes o{out_f32, out_hi, out_lo, reinterpret_cast<__nv_bfloat16*>(out_bf16), ld_f32, ld_split, ld_bf16};
+  const bool vec = planes_vec_ok(o) && aligned16(x) && ldx % 4 == 0 && d % 4 == 0 && (!dv || aligned16(dv)) &&
+                   (!mul || aligned16(mul)) && (!sub || aligned16(sub)) && (!out_bf16 || d % 8 == 0 || true);
+  if (vec)
+    ingest_kernel<true><<<ew_grid(rows * (d / 4), 256), 256, 0, S(stream)>>>(x, ldx, rows, d, dv, mul, sub, o);
+  else
+    ingest_kernel<false><<<ew_grid(rows * d, 256), 256, 0, S(stream)>>>(x, ldx, rows, d, dv, mul, sub, o);
+  USF_CUDA_OK(cudaGetLastError());
+  return USF_OK;
+}
+
+int usf_base_logprob(const float* z, const float* z_lo, int64_t ldz, int64_t rows, int32_t d, const float* loc,
+                     const float* scale, int32_t base_kind, float add_const, float* out, void* stream) {
+  USF_REQUIRE(z && loc && scale && out && d > 0 && rows >= 0, "bad input");
+  USF_REQUIRE(base_kind == USF_BASE_LAPLACE || base_kind == USF_BASE_NORMAL, "unknown base distribution");
+  if (rows == 0) return USF_OK;
+  const bool vec = aligned16(z) && (!z_lo || aligned16(z_lo)) && ldz % 4 == 0 && d % 4 == 0 && aligned16(loc) && aligned16(scale);
+  const int grid = ew_grid(rows * 32, BLP_THREADS);
+  if (vec)
+    base_logprob_kernel<true><<<grid, BLP_THREADS, 0, S(stream)>>>(z, z_lo, ldz, rows, d, loc, scale, base_kind, add_const, out);
+  else
+    base_logprob_kernel<false><<<grid, BLP_THREADS, 0, S(stream)>>>(z, z_lo, ldz, rows, d, loc, scale, base_kind, add_const, out);
+  USF_CUDA_OK(cudaGetLastError());
+  return USF_OK;
+}
+
+int usf_base_sample(int64_t rows, int32_t d, const float* loc, const float* scale, int32_t base_kind, uint64_t seed,
+                    uint64_t offset, float* out_f32, int64_t ld_f32, float* out_hi, float* out_lo, int64_t ld_split,
+                    void* out_bf16, int64_t ld_bf16, void* stream) {
+  USF_REQUIRE(loc && scale && d > 0 && rows >= 0, "bad input");
+  USF_REQUIRE(base_kind == USF_BASE_LAPLACE || base_kind == USF_BASE_NORMAL, "unknown base distribution");
+  USF_REQUIRE((out_hi == nullptr) == (out_lo == nullptr), "out_hi and out_lo come as a pair");
+  if (rows == 0) return USF_OK;
+  OutPlanes o{out_f32, out_hi, out_lo, reinterpret_cast<__nv_bfloat16*>(out_bf16), ld_f32, ld_split, ld_bf16};
+  const int vec = planes_vec_ok(o) ? 1 : 0;
+  base_sample_kernel<<<ew_grid(rows * ((d + 3) / 4), 256), 256, 0, S(stream)>>>(rows, d, loc, scale, base_kind, seed, offset, o, vec);
+  USF_CUDA_OK(cudaGetLastError());
+  return USF_OK;
+}
+
+int usf_leaky_relu(const float* x, int64_t ldx, int64_t rows, int32_t d, float slope, float* y, int64_t ldy,
+                   float* neg_count, void* stream) {
+  USF_REQUIRE(x && y && d > 0 && rows >= 0, "bad input");
+  if (rows == 0) return USF_OK;
+  leaky_relu_kernel<<<ew_grid(rows * 32, 256), 256, 0, S(stream)>>>(x, ldx, rows, d, slope, y, ldy, neg_count);
+  USF_CUDA_OK(cudaGetLastError());
+  return USF_OK;
+}
+
+int usf_permute(const float* x, int64_t ldx, int64_t rows, int32_t d, const int32_t* perm, float* y, int64_t ldy,
+                void* stream) {
+  USF_REQUIRE(x && y && perm && d > 0 && rows >= 0, "bad input");
+  USF_REQUIRE(x != y, "permute cannot run in place");
+  if (rows == 0) return USF_OK;
+  permute_kernel<<<ew_grid(rows * d, 256), 256, 0, S(stream)>>>(x, ldx, rows, d, perm, y, ldy);
+  USF_CUDA_OK(cudaGetLastError());
+  return USF_OK;
+}
+
+int usf_lu_assemble(const float* L_raw, const float* U_raw, int32_t d, int64_t ld_raw, float* L, float* U,
+                    int64_t ld_out, int32_t transpose_u, void* stream) {
+  USF_REQUIRE(d > 0 && (L || U), "bad input");
+  USF_REQUIRE((!L || L_raw) && (!U || U_raw), "missing raw matrix");
+  lu_assemble_kernel<<<ew_grid((long long)d * d, 256), 256, 0, S(stream)>>>(L_raw, U_raw, d, ld_raw, L, U, ld_out, transpose_u);
+  USF_CUDA_OK(cudaGetLastError());
+  return USF_OK;
+}
+
+int usf_lu_logabsdet(const float* U_raw, int32_t d, int64_t ld, float* out, void* stream) {
+  USF_REQUIRE(U_raw && out && d > 0, "bad input");
+  logabs_kernel<<<1, 1024, 0, S(stream)>>>(U_raw, d, ld + 1, out);
+  USF_CUDA_OK(cudaGetLastError());
+  return USF_OK;
+}
+
+int usf_vec_logabs(const float* v, int64_t n, float* out, void* stream) {
+  USF_REQUIRE(v && out && n > 0, "bad input");
+  logabs_kernel<<<1, 1024, 0, S(stream)>>>(v, n, 1, out);
+  USF_CUDA_OK(cudaGetLastError());
+  return USF_OK;
+}
+
+int64_t usf_tri_inverse_work_floats(int32_t d) {
+  const int64_t nb = (d + TI_NB - 1) / TI_NB;
+  return nb * TI_NB * TI_NB + 2LL * d * d;
+}
+
+int usf_transpose(const float* in, int32_t rows, int32_t cols, int64_t ld_in, float* out, int64_t ld_out, void* stream) {
+  USF_REQUIRE(in && out && rows > 0 && cols > 0 && in != out, "bad input");
+  dim3 grid((cols + 31) / 32, (rows + 31) / 32);
+  transpose_kernel<<<grid, 256, 0, S(stream)>>>(in, rows, cols, ld_in, out, ld_out);
+  USF_CUDA_OK(cudaGetLastError());
+  return USF_OK;
+}
+
+int usf_tri_inverse(const float* T, int32_t d, int64_t ldt, int32_t lower, int32_t unit_diag, float* X, int64_t ldx,
+                    float* work, void* stream) {
+  USF_REQUIRE(T && X && work && d > 0 && T != X, "bad input");
+  const int nb = (d + TI_NB - 1) / TI_NB;
+  float* dinv = work;
+  if (lower) {
+    tri_diag_inverse_kernel<<<nb, TI_NB, 0, S(stream)>>>(T, d, ldt, unit_diag, dinv);
+    tri_panel_sweep_kernel<<<nb, 256, 0, S(stream)>>>(T, d, ldt, dinv, X, ldx);
+    USF_CUDA_OK(cudaGetLastError());
+    return USF_OK;
+  }
+  float* Tt = work + (int64_t)nb * TI_NB * TI_NB;
+  float* Xt = Tt + (int64_t)d * d;
+  int rc = usf_transpose(T, d, d, ldt, Tt, d, stream);
+  if (rc) return rc;
+  tri_diag_inverse_kernel<<<nb, TI_NB, 0, S(stream)>>>(Tt, d, d, unit_diag, dinv);
+  tri_panel_sweep_kernel<<<nb, 256, 0, S(stream)>>>(Tt, d, d, dinv, Xt, d);
+  USF_CUDA_OK(cudaGetLastError());
+  return usf_transpose(Xt, d, d, d, X, ldx, stream);
+}
+
+int usf_scale_rows_cols(const float* in, int32_t rows, int32_t cols, int64_t ld_in, const float* rowf,
+                        const float* colf, float* out, int64_t ld_out, void* stream) {
+  USF_REQUIRE(in && out && rows > 0 && cols > 0, "bad input");
+  scale_rows_cols_kernel<<<ew_grid((long long)rows * cols, 256), 256, 0, S(stream)>>>(in, rows, cols, ld_in, rowf, colf, out, ld_out);
+  USF_CUDA_OK(cudaGetLastError());
+  return USF_OK;
+}
+
+int usf_split_tf32(const float* in, int64_t rows, int32_t cols, int64_t ld_in, float* hi, float* lo, int64_t ld_out,
+                   void* stream) {
+  USF_REQUIRE(in && hi && rows > 0 && cols > 0, "bad input");
+  split_tf32_kernel<<<ew_grid(rows * cols, 256), 256, 0, S(stream)>>>(in, rows, cols, ld_in, hi, lo, ld_out);
+  USF_CUDA_OK(cudaGetLastError());
+  return USF_OK;
+}
+
+int usf_to_bf16(const float* in, int64_t rows, int32_t cols, int64_t ld_in, void* out, int64_t ld_out, void* stream) {
+  USF_REQUIRE(in && out && rows > 0 && cols > 0, "bad input");
+  to_bf16_kernel<<<ew_grid(rows * cols, 256), 256, 0, S(stream)>>>(in, rows, cols, ld_in, reinterpret_cast<__nv_bfloat16*>(out), ld_out);
+  USF_CUDA_OK(cudaGetLastError());
+  return USF_OK;
+}
+
+int usf_householder_right(float* W, int32_t d, int64_t ld, const float* v, float* work, void* stream) {
+  USF_REQUIRE(W && v && work && d > 0, "bad input");
+  householder_matvec_kernel<<<(d + 7) / 8, 256, 0, S(stream)>>>(W, d, ld, v, work);
+  householder_rank1_kernel<<<ew_grid((long long)d * d, 256), 256, 0, S(stream)>>>(W, d, ld, v, work);
+  USF_CUDA_OK(cudaGetLastError());
+  return USF_OK;
+}
+
+int usf_softplus(const float* in, int64_t n, float* out, void* stream) {
+  USF_REQUIRE(in && out && n > 0, "bad input");
+  softplus_kernel<<<ew_grid(n, 256), 256, 0, S(stream)>>>(in, n, out);
+  USF_CUDA_OK(cudaGetLastError());
+  return USF_OK;
+}
+
+}  // extern "C"

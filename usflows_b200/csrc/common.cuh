@@ -1,0 +1,167 @@
+// Shared helpers for the usflows_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/usflows_b200.h"
+
+namespace usf {
+
+// ---------------------------------------------------------------------------------------------
+// error reporting (thread-local message, returned through usf_last_error())
+// ---------------------------------------------------------------------------------------------
+extern thread_local char g_err[512];
+
+inline int fail(int code, const char* fmt, const char* a = "", const char* b = "") {
+  snprintf(g_err, sizeof(g_err), fmt, a, b);
+  return code;
+}
+
+#define USF_CUDA_OK(expr)                                                                         \
+  do {                                                                                            \
+    cudaError_t _e = (expr);                                                                      \
+    if (_e != cudaSuccess) {                                                                      \
+      snprintf(usf::g_err, sizeof(usf::g_err), "%s failed: %s (%s:%d)", #expr,                    \
+               cudaGetErrorString(_e), __FILE__, __LINE__);                                       \
+      return USF_ERR_CUDA;                                                                        \
+    }                                                                                             \
+  } while (0)
+
+#define USF_REQUIRE(cond, msg)                                                                    \
+  do {                                                                                            \
+    if (!(cond)) {                                                                                \
+      snprintf(usf::g_err, sizeof(usf::g_err), "invalid argument: %s [%s] (%s:%d)", msg, #cond,   \
+               __FILE__, __LINE__);                                                               \
+      return USF_ERR_INVALID;                                                                     \
+    }                                                                                             \
+  } while (0)
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+int num_sms();  // cached cudaDevAttrMultiProcessorCount of the current device
+
+// ---------------------------------------------------------------------------------------------
+// fused epilogue shared by the tcgen05 and the SIMT contraction kernels
+//   v = acc (+ bias[n]) ; relu ; v = resid[m,n] + sign * v ; v *= colscale[n] ; v -= postsub[n]
+//   then written to any of: fp32 plane, tf32 hi/lo split planes, bf16 plane.
+// ---------------------------------------------------------------------------------------------
+struct Epilogue {
+  const float* bias;
+  const float* resid_hi;
+  const float* resid_lo;
+  const float* colscale;
+  const float* postsub;
+  float* out_f32;
+  float* out_hi;
+  float* out_lo;
+  __nv_bfloat16* out_bf16;
+  long long ldr, ld_f32, ld_split, ld_bf16;
+  float resid_sign;
+  int relu;
+  int vec_ok;  // every pointer 16-byte aligned and every ld a multiple of 4 (8 for bf16)
+};
+
+__device__ __forceinline__ float tf32_round(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+__device__ __forceinline__ float epi_value(const Epilogue& ep, float v, long long m, int n) {
+  if (ep.bias) v += __ldg(ep.bias + n);
+  if (ep.relu) v = fmaxf(v, 0.f);
+  if (ep.resid_hi) {
+    float r = ep.resid_hi[m * ep.ldr + n];
+    if (ep.resid_lo) r += ep.resid_lo[m * ep.ldr + n];
+    v = fmaf(ep.resid_sign, v, r);
+  }
+  if (ep.colscale) v *= __ldg(ep.colscale + n);
+  if (ep.postsub) v -= __ldg(ep.postsub + n);
+  return v;
+}
+
+__device__ __forceinline__ void epi_store1(const Epilogue& ep, float v, long long m, int n) {
+  if (ep.out_f32) ep.out_f32[m * ep.ld_f32 + n] = v;
+  if (ep.out_hi) {
+    float hi = tf32_round(v);
+    ep.out_hi[m * ep.ld_split + n] = hi;
+    ep.out_lo[m * ep.ld_split + n] = tf32_round(v - hi);
+  }
+  if (ep.out_bf16) ep.out_bf16[m * ep.ld_bf16 + n] = __float2bfloat16_rn(v);
+}
+
+// four consecutive columns n..n+3 of row m (n % 4 == 0, all in range, ep.vec_ok)
+__device__ __forceinline__ void epi_apply4(const Epilogue& ep, float (&v)[4], long long m, int n) {
+  if (ep.bias) {
+    float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + n));
+    v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
+  }
+  if (ep.relu) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = fmaxf(v[i], 0.f);
+  }
+  if (ep.resid_hi) {
+    float4 r = *reinterpret_cast<const float4*>(ep.resid_hi + m * ep.ldr + n);
+    if (ep.resid_lo) {
+      float4 l = *reinterpret_cast<const float4*>(ep.resid_lo + m * ep.ldr + n);
+      r.x += l.x; r.y += l.y; r.z += l.z; r.w += l.w;
+    }
+    v[0] = fmaf(ep.resid_sign, v[0], r.x); v[1] = fmaf(ep.resid_sign, v[1], r.y);
+    v[2] = fmaf(ep.resid_sign, v[2], r.z); v[3] = fmaf(ep.resid_sign, v[3], r.w);
+  }
+  if (ep.colscale) {
+    float4 s = __ldg(reinterpret_cast<const float4*>(ep.colscale + n));
+    v[0] *= s.x; v[1] *= s.y; v[2] *= s.z; v[3] *= s.w;
+  }
+  if (ep.postsub) {
+    float4 s = __ldg(reinterpret_cast<const float4*>(ep.postsub + n));
+    v[0] -= s.x; v[1] -= s.y; v[2] -= s.z; v[3] -= s.w;
+  }
+  if (ep.out_f32) *reinterpret_cast<float4*>(ep.out_f32 + m * ep.ld_f32 + n) = make_float4(v[0], v[1], v[2], v[3]);
+  if (ep.out_hi) {
+    float h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { h[i] = tf32_round(v[i]); l[i] = tf32_round(v[i] - h[i]); }
+    *reinterpret_cast<float4*>(ep.out_hi + m * ep.ld_split + n) = make_float4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<float4*>(ep.out_lo + m * ep.ld_split + n) = make_float4(l[0], l[1], l[2], l[3]);
+  }
+  if (ep.out_bf16) {
+    __nv_bfloat162 p0 = __floats2bfloat162_rn(v[0], v[1]);
+    __nv_bfloat162 p1 = __floats2bfloat162_rn(v[2], v[3]);
+    uint2 u;
+    u.x = *reinterpret_cast<uint32_t*>(&p0);
+    u.y = *reinterpret_cast<uint32_t*>(&p1);
+    *reinterpret_cast<uint2*>(ep.out_bf16 + m * ep.ld_bf16 + n) = u;
+  }
+}
+
+// NC consecutive columns starting at n0 of row m, with range checks on N
+template <int NC>
+__device__ __forceinline__ void epi_row_chunk(const Epilogue& ep, float (&v)[NC], long long m, int n0, int N) {
+  if (ep.vec_ok) {
+#pragma unroll
+    for (int j = 0; j < NC; j += 4) {
+      int n = n0 + j;
+      if (n + 3 < N) {
+        float t[4] = {v[j], v[j + 1], v[j + 2], v[j + 3]};
+        epi_apply4(ep, t, m, n);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (n + i < N) epi_store1(ep, epi_value(ep, v[j + i], m, n + i), m, n + i);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < NC; ++j)
+      if (n0 + j < N) epi_store1(ep, epi_value(ep, v[j], m, n0 + j), m, n0 + j);
+  }
+}
+
+int make_epilogue(const usf_linear_args* a, Epilogue* ep);  // validates pointers / strides
+
+}  // namespace usf

@@ -1,0 +1,133 @@
+// fp32 CUDA-core contraction: out = epilogue(A[M,K] . W[N,K]^T), any shape / alignment.
+// Used for tiny or unaligned problems (d = 2 ... ), for weight preparation with transposed operands,
+// and as the fp32 cross-check of the tcgen05 engines.  64x64x16 tiles, 256 threads, 4x4 per thread,
+// register-staged double buffering.
+#pragma once
+#include "common.cuh"
+
+namespace usf {
+
+constexpr int SG_BM = 64, SG_BN = 64, SG_BK = 16, SG_THREADS = 256;
+
+template <bool TRANS_W>
+__global__ void __launch_bounds__(SG_THREADS)
+gemm_simt_kernel(const float* __restrict__ A, const float* __restrict__ A_lo, long long lda,
+                 const float* __restrict__ W, const float* __restrict__ W_lo, long long ldw,
+                 long long M, int N, int K, Epilogue ep) {
+  __shared__ float sA[2][SG_BK][SG_BM + 4];
+  __shared__ float sW[2][SG_BK][SG_BN + 4];
+
+  const int tid = threadIdx.x;
+  const long long m0 = (long long)blockIdx.x * SG_BM;
+  const int n0 = blockIdx.y * SG_BN;
+  const int tx = tid % 16, ty = tid / 16;  // 16 x 16 threads, each a 4x4 micro tile
+
+  // loader mapping: A tile 64 rows x 16 k -> each thread 4 consecutive k of one row
+  const int la_row = tid / 4, la_k = (tid % 4) * 4;
+  // W tile: [N,K] layout -> same mapping; [K,N] layout -> each thread 4 consecutive n of one k
+  const int lw_row = TRANS_W ? tid / 16 : tid / 4;        // k index (trans) or n index
+  const int lw_col = TRANS_W ? (tid % 16) * 4 : (tid % 4) * 4;
+
+  float ra[4], rw[4];
+  auto load_tiles = [&](int k0) {
+    const long long gm = m0 + la_row;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int gk = k0 + la_k + i;
+      float v = 0.f;
+      if (gm < M && gk < K) {
+        v = A[gm * lda + gk];
+        if (A_lo) v += A_lo[gm * lda + gk];
+      }
+      ra[i] = v;
+    }
+    if (TRANS_W) {
+      const int gk = k0 + lw_row;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int gn = n0 + lw_col + i;
+        float v = 0.f;
+        if (gn < N && gk < K) {
+          v = W[(long long)gk * ldw + gn];
+          if (W_lo) v += W_lo[(long long)gk * ldw + gn];
+        }
+        rw[i] = v;
+      }
+    } else {
+      const int gn = n0 + lw_row;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int gk = k0 + lw_col + i;
+        float v = 0.f;
+        if (gn < N && gk < K) {
+          v = W[(long long)gn * ldw + gk];
+          if (W_lo) v += W_lo[(long long)gn * ldw + gk];
+        }
+        rw[i] = v;
+      }
+    }
+  };
+  auto store_tiles = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) sA[buf][la_k + i][la_row] = ra[i];
+    if (TRANS_W) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) sW[buf][lw_row][lw_col + i] = rw[i];
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) sW[buf][lw_col + i][lw_row] = rw[i];
+    }
+  };
+
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  const int nk = (K + SG_BK - 1) / SG_BK;
+  load_tiles(0);
+  store_tiles(0);
+  __syncthreads();
+  for (int kb = 0; kb < nk; ++kb) {
+    const int buf = kb & 1;
+    if (kb + 1 < nk) load_tiles((kb + 1) * SG_BK);
+#pragma unroll
+    for (int k = 0; k < SG_BK; ++k) {
+      float a[4], w[4];
+      *reinterpret_cast<float4*>(a) = *reinterpret_cast<const float4*>(&sA[buf][k][ty * 4]);
+      *reinterpret_cast<float4*>(w) = *reinterpret_cast<const float4*>(&sW[buf][k][tx * 4]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
+    }
+    if (kb + 1 < nk) store_tiles(buf ^ 1);
+    __syncthreads();
+  }
+
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const long long m = m0 + ty * 4 + i;
+    if (m < M) epi_row_chunk<4>(ep, acc[i], m, n0 + tx * 4, N);
+  }
+}
+
+inline int launch_gemm_simt(const usf_linear_args* a, const Epilogue& ep, cudaStream_t st) {
+  if (a->M == 0 || a->N == 0) return USF_OK;
+  USF_REQUIRE((a->M + SG_BM - 1) / SG_BM <= 0x7fffffffLL && (a->N + SG_BN - 1) / SG_BN <= 65535,
+              "SIMT engine: problem too large for one launch");
+  dim3 grid((unsigned)((a->M + SG_BM - 1) / SG_BM), (a->N + SG_BN - 1) / SG_BN);
+  if (a->trans_w)
+    gemm_simt_kernel<true><<<grid, SG_THREADS, 0, st>>>(
+        (const float*)a->a, (const float*)a->a_lo, a->lda, (const float*)a->w, (const float*)a->w_lo, a->ldw,
+        a->M, a->N, a->K, ep);
+  else
+    gemm_simt_kernel<false><<<grid, SG_THREADS, 0, st>>>(
+        (const float*)a->a, (const float*)a->a_lo, a->lda, (const float*)a->w, (const float*)a->w_lo, a->ldw,
+        a->M, a->N, a->K, ep);
+  USF_CUDA_OK(cudaGetLastError());
+  return USF_OK;
+}
+
+}  // namespace usf

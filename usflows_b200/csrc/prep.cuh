@@ -1,0 +1,262 @@
+// Weight-preparation kernels: run once per weight version (the reference redoes this work on every call,
+// transforms.py:1264-1293, 1457-1476).  fp32 throughout; reductions accumulate in fp64.
+#pragma once
+#include "common.cuh"
+
+namespace usf {
+
+// L = tril(L_raw,-1) + I ; U = triu(U_raw) (optionally transposed)
+__global__ void __launch_bounds__(256)
+lu_assemble_kernel(const float* __restrict__ L_raw, const float* __restrict__ U_raw, int d, long long ld_raw,
+                   float* __restrict__ L, float* __restrict__ U, long long ld_out, int transpose_u) {
+  const long long total = (long long)d * d;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / d), c = (int)(i % d);
+    if (L) L[(long long)r * ld_out + c] = c < r ? L_raw[(long long)r * ld_raw + c] : (c == r ? 1.f : 0.f);
+    if (U) {
+      const float u = c >= r ? U_raw[(long long)r * ld_raw + c] : 0.f;
+      if (transpose_u) U[(long long)c * ld_out + r] = u;
+      else U[(long long)r * ld_out + c] = u;
+    }
+  }
+}
+
+// out[0] = sum log|v[i*stride]| (fp64 accumulation), out[1] = #zeros ; single block
+__global__ void __launch_bounds__(1024)
+logabs_kernel(const float* __restrict__ v, long long n, long long stride, float* __restrict__ out) {
+  __shared__ double ssum[32];
+  __shared__ int szero[32];
+  double acc = 0.0;
+  int zeros = 0;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+    const float x = v[i * stride];
+    if (x == 0.f) ++zeros;
+    acc += (double)logf(fabsf(x));
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    zeros += __shfl_xor_sync(0xffffffffu, zeros, o);
+  }
+  if ((threadIdx.x & 31) == 0) { ssum[threadIdx.x >> 5] = acc; szero[threadIdx.x >> 5] = zeros; }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    acc = threadIdx.x < (blockDim.x >> 5) ? ssum[threadIdx.x] : 0.0;
+    zeros = threadIdx.x < (blockDim.x >> 5) ? szero[threadIdx.x] : 0;
+    for (int o = 16; o > 0; o >>= 1) {
+      acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      zeros += __shfl_xor_sync(0xffffffffu, zeros, o);
+    }
+    if (threadIdx.x == 0) { out[0] = (float)acc; out[1] = (float)zeros; }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+transpose_kernel(const float* __restrict__ in, int rows, int cols, long long ld_in, float* __restrict__ out, long long ld_out) {
+  __shared__ float tile[32][33];
+  const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (int i = ty; i < 32; i += 8) {
+    const int r = by + i, c = bx + tx;
+    tile[i][tx] = (r < rows && c < cols) ? in[(long long)r * ld_in + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int r = bx + i, c = by + tx;  // out is [cols, rows]
+    if (r < cols && c < rows) out[(long long)r * ld_out + c] = tile[tx][i];
+  }
+}
+
+__global__ void __launch_bounds__(256)
+scale_rows_cols_kernel(const float* __restrict__ in, int rows, int cols, long long ld_in, const float* __restrict__ rowf,
+                       const float* __restrict__ colf, float* __restrict__ out, long long ld_out) {
+  const long long total = (long long)rows * cols;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / cols), c = (int)(i % cols);
+    float v = in[(long long)r * ld_in + c];
+    if (rowf) v *= rowf[r];
+    if (colf) v *= colf[c];
+    out[(long long)r * ld_out + c] = v;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+split_tf32_kernel(const float* __restrict__ in, long long rows, int cols, long long ld_in, float* __restrict__ hi,
+                  float* __restrict__ lo, long long ld_out) {
+  const long long total = rows * cols;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cols;
+    const int c = (int)(i - r * cols);
+    const float v = in[r * ld_in + c];
+    const float h = tf32_round(v);
+    hi[r * ld_out + c] = h;
+    if (lo) lo[r * ld_out + c] = tf32_round(v - h);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+to_bf16_kernel(const float* __restrict__ in, long long rows, int cols, long long ld_in, __nv_bfloat16* __restrict__ out,
+               long long ld_out) {
+  const long long total = rows * cols;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cols;
+    const int c = (int)(i - r * cols);
+    out[r * ld_out + c] = __float2bfloat16_rn(in[r * ld_in + c]);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+softplus_kernel(const float* __restrict__ in, long long n, float* __restrict__ out) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float x = in[i];
+    out[i] = x > 20.f ? x : log1pf(expf(x));  // torch softplus (beta=1, threshold=20)
+  }
+}
+
+// ---- Householder: W <- W - (2 / v.v) (W v) v^T -------------------------------------------------------
+// step 1: work[r] = (W[r,:] . v) * 2 / (v.v)   (one warp per row)
+__global__ void __launch_bounds__(256)
+householder_matvec_kernel(const float* __restrict__ W, int d, long long ld, const float* __restrict__ v, float* __restrict__ work) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r = blockIdx.x * 8 + warp;
+  if (r >= d) return;
+  float dot = 0.f, vv = 0.f;
+  for (int j = lane; j < d; j += 32) {
+    const float x = v[j];
+    dot = fmaf(W[(long long)r * ld + j], x, dot);
+    vv = fmaf(x, x, vv);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    dot += __shfl_xor_sync(0xffffffffu, dot, o);
+    vv += __shfl_xor_sync(0xffffffffu, vv, o);
+  }
+  if (lane == 0) work[r] = 2.f * dot / vv;
+}
+// step 2: W[r,c] -= work[r] * v[c]
+__global__ void __launch_bounds__(256)
+householder_rank1_kernel(float* __restrict__ W, int d, long long ld, const float* __restrict__ v, const float* __restrict__ work) {
+  const long long total = (long long)d * d;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / d), c = (int)(i % d);
+    W[(long long)r * ld + c] = fmaf(-work[r], v[c], W[(long long)r * ld + c]);
+  }
+}
+
+// ---- triangular inverse (lower triangular, optional unit diagonal) -----------------------------------
+// Blocked forward substitution with NB = 64:  X[I,J] = Tinv_II (delta_IJ I - sum_{J<=K<I} T[I,K] X[K,J]).
+// Kernel 1 inverts the 64x64 diagonal blocks in shared memory (one CTA per block);
+// kernel 2 gives every CTA one 64-column panel J of X and sweeps block rows I = J .. nb-1.
+// An upper-triangular inverse is taken as the transpose of the lower-triangular inverse of T^T (host side).
+constexpr int TI_NB = 64;
+
+// Dinv[b] (64x64, row-major, ld 64) = inverse of the b-th diagonal block of T; blocks past d are identity-padded
+__global__ void __launch_bounds__(TI_NB)
+tri_diag_inverse_kernel(const float* __restrict__ T, int d, long long ldt, int unit_diag, float* __restrict__ Dinv) {
+  __shared__ float sT[TI_NB][TI_NB + 1];
+  __shared__ float sX[TI_NB][TI_NB + 1];
+  const int b = blockIdx.x, j = threadIdx.x, base = b * TI_NB;
+  for (int r = 0; r < TI_NB; ++r) {
+    const int gr = base + r, gc = base + j;
+    float v = (r == j) ? 1.f : 0.f;
+    if (gr < d && gc < d && j <= r) {
+      v = T[(long long)gr * ldt + gc];
+      if (r == j && unit_diag) v = 1.f;
+    }
+    sT[r][j] = v;
+  }
+  __syncthreads();
+  // thread j solves T x = e_j (column j of the inverse), forward substitution
+  for (int i = 0; i < TI_NB; ++i) {
+    float s = (i == j) ? 1.f : 0.f;
+    if (i > j) {
+      for (int k = j; k < i; ++k) s = fmaf(-sT[i][k], sX[k][j], s);
+    }
+    sX[i][j] = (i < j) ? 0.f : s / sT[i][i];
+  }
+  __syncthreads();
+  for (int r = 0; r < TI_NB; ++r) Dinv[((long long)b * TI_NB + r) * TI_NB + j] = sX[r][j];
+}
+
+// 256 threads, each a 4x4 micro tile of the 64x64 accumulator
+__global__ void __launch_bounds__(256)
+tri_panel_sweep_kernel(const float* __restrict__ T, int d, long long ldt, const float* __restrict__ Dinv,
+                       float* X, long long ldx) {
+  __shared__ float sA[TI_NB][TI_NB + 4];   // T[I,K] tile, stored transposed: sA[k][i]
+  __shared__ float sB[TI_NB][TI_NB + 4];   // X[K,J] tile: sB[k][j]
+  const int nb = (d + TI_NB - 1) / TI_NB;
+  const int J = blockIdx.x;
+  const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
+
+  for (int I = J; I < nb; ++I) {
+    float acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+    for (int K = J; K < I; ++K) {
+      for (int e = tid; e < TI_NB * TI_NB; e += 256) {
+        const int r = e / TI_NB, c = e % TI_NB;
+        const int gi = I * TI_NB + r, gk = K * TI_NB + c;
+        sA[c][r] = (gi < d && gk < d) ? T[(long long)gi * ldt + gk] : 0.f;
+        const int gk2 = K * TI_NB + r, gj = J * TI_NB + c;
+        sB[r][c] = (gk2 < d && gj < d) ? X[(long long)gk2 * ldx + gj] : 0.f;
+      }
+      __syncthreads();
+#pragma unroll 8
+      for (int k = 0; k < TI_NB; ++k) {
+        float a[4], b[4];
+        *reinterpret_cast<float4*>(a) = *reinterpret_cast<const float4*>(&sA[k][ty * 4]);
+        *reinterpret_cast<float4*>(b) = *reinterpret_cast<const float4*>(&sB[k][tx * 4]);
+#pragma unroll
+        for (int p = 0; p < 4; ++p)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) acc[p][q] = fmaf(a[p], b[q], acc[p][q]);
+      }
+      __syncthreads();
+    }
+    // R = delta_IJ I - acc  -> sB ; Dinv_I -> sA (transposed) ; X[I,J] = Dinv_I . R
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int r = ty * 4 + p, c = tx * 4 + q;
+        sB[r][c] = ((I == J && r == c) ? 1.f : 0.f) - acc[p][q];
+      }
+    for (int e = tid; e < TI_NB * TI_NB; e += 256) {
+      const int r = e / TI_NB, c = e % TI_NB;
+      sA[c][r] = Dinv[((long long)I * TI_NB + r) * TI_NB + c];
+    }
+    __syncthreads();
+    float out[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) out[a][b] = 0.f;
+#pragma unroll 8
+    for (int k = 0; k < TI_NB; ++k) {
+      float a[4], b[4];
+      *reinterpret_cast<float4*>(a) = *reinterpret_cast<const float4*>(&sA[k][ty * 4]);
+      *reinterpret_cast<float4*>(b) = *reinterpret_cast<const float4*>(&sB[k][tx * 4]);
+#pragma unroll
+      for (int p = 0; p < 4; ++p)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) out[p][q] = fmaf(a[p], b[q], out[p][q]);
+    }
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int gi = I * TI_NB + ty * 4 + p, gj = J * TI_NB + tx * 4 + q;
+        if (gi < d && gj < d) X[(long long)gi * ldx + gj] = out[p][q];
+      }
+    __threadfence_block();
+    __syncthreads();  // X[I,J] visible to the whole CTA before it is re-read as a K block
+  }
+  // blocks above the diagonal panel start are zero
+  for (int I = 0; I < J; ++I)
+    for (int e = tid; e < TI_NB * TI_NB; e += 256) {
+      const int gi = I * TI_NB + e / TI_NB, gj = J * TI_NB + e % TI_NB;
+      if (gi < d && gj < d) X[(long long)gi * ldx + gj] = 0.f;
+    }
+}
+
+}  // namespace usf

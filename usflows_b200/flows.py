@@ -1,0 +1,227 @@
+"""`Flow` and `USFlow` -- drop-in mirrors of the reference's model API (src/usflows/flows.py:22-605).
+
+Same constructor signatures, attributes (`layers`, `trainable_layers`, `base_distribution`, `device`,
+`export`), state-dict layout and methods (`log_prob`, `sample`, `_forward`, `backward`, `forward`, `to`,
+`is_feasible`, `add_jitter`, `log_prior`).  Evaluation runs through `engine.Program`: fused sm_100a kernels
+behind the C ABI, prepared weights cached per weight version, the total log|det J| (a model constant for
+every USFlow layer) computed once per weight version.  CUDA tensors only.
+"""
+from __future__ import annotations
+
+import math
+from typing import Any, Dict, Iterable, List, Literal, Optional, Type
+
+import torch
+
+from . import engine, ops
+from .distributions import DistributionModule, Independent
+from .transforms import (BaseTransform, BlockAffineTransform, HouseholderTransform, InverseTransform, LUTransform,
+                         MaskedCoupling, ScaleTransform, SequentialAffineTransform)
+
+
+class Flow(torch.nn.Module):
+    """Base flow: a list of bijective layers over a base distribution (flows.py:22-292)."""
+
+    export_modes = Literal["log_prob", "sample", "forward", "backward"]
+    export: str = "log_prob"
+    device = "cpu"
+
+    def __init__(self, base_distribution, layers, soft_training: bool = False, training_noise_prior=None,
+                 device: str = "cpu", precision: Optional[str] = None, *args, **kwargs) -> None:
+        super().__init__(*args, **kwargs)
+        if soft_training:
+            # reference flows.py:559-565 passes a context to the conditioner, which pyro's DenseNN rejects
+            raise NotImplementedError("usflows_b200: soft_training (context-conditioned conditioners) is not built")
+        self.soft_training = soft_training
+        self.training_noise_prior = training_noise_prior
+        self.layers = layers
+        self.trainable_layers = torch.nn.ModuleList([l for l in layers if isinstance(l, torch.nn.Module)])
+        self.base_distribution = base_distribution
+        self.precision = precision
+        self.to(device)
+        self.device = device
+        batch_shape = self.base_distribution.batch_shape
+        if len(batch_shape) > 0:                                   # flows.py:97-101
+            self.base_distribution = Independent(self.base_distribution, len(batch_shape))
+        self._programs: Dict[str, Any] = {}
+
+    # -- reference API ---------------------------------------------------------------------------
+    def forward(self, x: torch.Tensor):
+        """Export-mode dispatch (flows.py:30-43)."""
+        if self.export == "log_prob":
+            return self.log_prob(x)
+        if self.export == "sample":
+            return self.sample()
+        if self.export == "forward":
+            return self._forward(x)
+        if self.export == "backward":
+            return self.backward(x)
+        raise ValueError(f"Unknown export mode {self.export}")
+
+    def _forward(self, x: torch.Tensor) -> torch.Tensor:
+        """latent -> data through every layer's `forward` (flows.py:45-55)."""
+        return self._run("forward", x)
+
+    def backward(self, x: torch.Tensor) -> torch.Tensor:
+        """data -> latent through every layer's `backward` in reverse order (flows.py:57-67)."""
+        return self._run("backward", x)
+
+    def log_prob(self, x: torch.Tensor, context: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """log p(x) = base.log_prob(z) - sum_k log|det J_k|  (flows.py:225-245)."""
+        if context is not None:
+            raise NotImplementedError("usflows_b200: context-conditioned evaluation is not built")
+        prog, ladj = self._program("backward")
+        base = self._base_module()
+        loc, scale = base._prepared()
+        x2, batch_shape = engine._flatten_rows(x, len(self._event_shape()))
+        out = torch.empty(x2.shape[0], dtype=torch.float32, device=x2.device)
+        d = x2.shape[1]
+
+        def sink(z_chunk, r0, r1):
+            ops.base_logprob(ops.Act(r1 - r0, d, f32=z_chunk), loc, scale, base.base_kind, -ladj, out[r0:r1])
+
+        with torch.no_grad():
+            prog.run(x2, self.precision, sink=sink)
+        return out.reshape(batch_shape)
+
+    def sample(self, sample_shape: Iterable[int] = None, context: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Draw from the base and push through the layers (flows.py:247-265)."""
+        if context is not None:
+            raise NotImplementedError("usflows_b200: context-conditioned evaluation is not built")
+        if sample_shape is None:
+            sample_shape = [1]
+        shape = [int(s) for s in sample_shape]
+        z = self.base_distribution.sample(shape)
+        ev = len(self._event_shape())
+        y = self._run("forward", z.reshape(-1, *z.shape[z.dim() - ev:]))
+        return y.reshape(*shape, *y.shape[1:])
+
+    def to(self, device):
+        self.device = device
+        self.trainable_layers = torch.nn.ModuleList([l.to(device) for l in self.trainable_layers])
+        for l in self.layers:                                    # plain-attribute tensors (masks)
+            if isinstance(l, BaseTransform):
+                l.to(device)
+        self._distribution_to(device)
+        self._programs = {}
+        return super().to(device)
+
+    def is_feasible(self) -> bool:
+        return all(l.is_feasible() for l in self.layers if isinstance(l, BaseTransform))
+
+    def add_jitter(self, jitter: float = 1e-6) -> None:
+        for l in self.layers:
+            if isinstance(l, BaseTransform) and not l.is_feasible():
+                l.add_jitter(jitter)
+
+    def log_prior(self):
+        return 0
+
+    def _distribution_to(self, device) -> None:
+        pass
+
+    # -- engine glue -----------------------------------------------------------------------------
+    def _base_module(self) -> DistributionModule:
+        b = self.base_distribution
+        return b.base_dist if isinstance(b, Independent) else b
+
+    def _event_shape(self):
+        return self.base_distribution.event_shape
+
+    def _weights_key(self):
+        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+
+    def _program(self, direction: str):
+        """(Program, total forward log|det J|) for the current weight version."""
+        key = self._weights_key()
+        hit = self._programs.get(direction)
+        if hit is None or hit[0] != key:
+            prog = engine.Program(self.layers, direction)
+            ladj, n_bad = engine.total_ladj(self.layers)
+            hit = (key, prog, ladj, n_bad)
+            self._programs[direction] = hit
+        return hit[1], hit[2]
+
+    def _run(self, direction: str, x: torch.Tensor) -> torch.Tensor:
+        prog, _ = self._program(direction)
+        x2, batch_shape = engine._flatten_rows(x, len(self._event_shape()))
+        with torch.no_grad():
+            y = prog.run(x2, self.precision)
+        return y.reshape(*batch_shape, *self._event_shape())
+
+
+class USFlow(Flow):
+    """Uniformly scaling flow: [BlockAffine(LU..[, Householder]) -> additive MaskedCoupling
+    [-> BlockAffine^-1]] x coupling_blocks -> BlockAffine(LU) -> Scale  (flows.py:380-491)."""
+
+    MASKTYPE = Literal["checkerboard", "channel"]
+
+    def __init__(self, base_distribution, in_dims: List[int], coupling_blocks: int,
+                 conditioner_cls: Type[torch.nn.Module], conditioner_args: Dict[str, Any], soft_training=False,
+                 prior_scale: Optional[float] = None, training_noise_prior=None, affine_conjugation: bool = False,
+                 nonlinearity: Optional[torch.nn.Module] = None, lu_transform: int = 1, householder: int = 1,
+                 masktype: str = "checkerboard", *args, **kwargs):
+        self.coupling_blocks = coupling_blocks
+        self.in_dims = in_dims
+        self.conditioner_cls = conditioner_cls
+        self.conditioner_args = conditioner_args
+        self.prior_scale = prior_scale
+        if masktype == "checkerboard":
+            self.mask_Generator = USFlow.create_checkerboard_mask
+        elif masktype == "channel":
+            self.mask_Generator = USFlow.create_channel_mask
+        else:
+            raise ValueError(f"Unknown mask type {masktype}")
+        if lu_transform < 0:
+            raise ValueError("Number of LU transforms must be non-negative")
+        if householder < 0:
+            raise ValueError("Number of Householder vectors transforms must be non-negative")
+        self.lu_transform = lu_transform
+        self.householder = householder
+
+        layers = []
+        mask = self.mask_Generator(in_dims)
+        for _ in range(coupling_blocks):
+            affine_layers = [LUTransform(in_dims[0], prior_scale) for _ in range(lu_transform)]
+            if householder > 0:
+                affine_layers.append(HouseholderTransform(dim=in_dims[0], nvs=householder))
+            block_affine_layer = None
+            if affine_layers:
+                block_affine_layer = BlockAffineTransform(in_dims, SequentialAffineTransform(affine_layers))
+                layers.append(block_affine_layer)
+            layers.append(MaskedCoupling(mask, conditioner_cls(**conditioner_args)))
+            if affine_conjugation and block_affine_layer is not None:
+                layers.append(InverseTransform(block_affine_layer))   # shares parameters (flows.py:469-470)
+            mask = 1 - mask
+        layers.append(BlockAffineTransform(in_dims, LUTransform(in_dims[0], prior_scale)))
+        layers.append(ScaleTransform(in_dims))
+        super().__init__(base_distribution, layers, soft_training=soft_training,
+                         training_noise_prior=training_noise_prior, *args, **kwargs)
+
+    @classmethod
+    def create_checkerboard_mask(cls, in_dims, invert: bool = False) -> torch.Tensor:
+        """(sum of index coordinates) mod 2, float32, shape (1, *in_dims)  (flows.py:494-514)."""
+        axes = [torch.arange(d, dtype=torch.int32) for d in in_dims]
+        idx = torch.stack(torch.meshgrid(*axes, indexing="ij"))
+        mask = torch.fmod(idx.sum(dim=0), 2).to(torch.float32).view(1, *in_dims)
+        return 1 - mask if invert else mask
+
+    @classmethod
+    def create_channel_mask(cls, in_dims, invert: bool = False) -> torch.Tensor:
+        """(first index coordinate) mod 2  (flows.py:516-536)."""
+        axes = [torch.arange(d, dtype=torch.int32) for d in in_dims]
+        idx = torch.stack(torch.meshgrid(*axes, indexing="ij"))
+        mask = torch.fmod(idx[0], 2).to(torch.float32).view(1, *in_dims)
+        return 1 - mask if invert else mask
+
+    def log_prior(self):
+        """Sum of the top-level layers' log_prior -- identically 0 in the reference because
+        BlockAffineTransform does not forward to its LU layer (flows.py:538-549)."""
+        if self.prior_scale is not None:
+            return sum(l.log_prior() for l in self.layers)
+        return 0
+
+    def load_state_dict(self, state_dict, strict: bool = True, **kw):
+        """Accepts reference checkpoints: InverseTransform layers alias block i's parameters and appear a
+        second time under `trainable_layers.{i+2}.transform...` -- both copies are accepted."""
+        return super().load_state_dict(state_dict, strict=strict, **kw)

@@ -1,0 +1,179 @@
+"""Typed Python wrappers over the C ABI: torch CUDA tensors in, kernels launched on the current stream.
+
+torch is used here for device memory and stream handles only.  Non-CUDA tensors raise: there is no CPU
+path in this package (the CPU oracle lives in oracle/ and is test infrastructure).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import (BASE_LAPLACE, BASE_NORMAL, ENGINE_SIMT, ENGINE_TC_3XTF32, ENGINE_TC_BF16,  # noqa: F401
+                   ENGINE_TC_TF32, LinearArgs, check)
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def require_cuda(t: torch.Tensor, name: str = "tensor", dtype=torch.float32) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError(f"usflows_b200: {name} must be a CUDA tensor (no CPU fallback exists)")
+    if dtype is not None and t.dtype != dtype:
+        raise RuntimeError(f"usflows_b200: {name} must have dtype {dtype}, got {t.dtype}")
+    return t
+
+
+def _ld(t: torch.Tensor) -> int:
+    """Leading dimension of a 2-D row-major view (last dim contiguous)."""
+    if t.dim() == 1:
+        return t.shape[0]
+    assert t.dim() == 2 and (t.stride(1) == 1 or t.shape[1] == 1), "row-major 2-D view expected"
+    return t.stride(0) if t.shape[0] > 1 else max(t.stride(0), t.shape[1])
+
+
+def pad4(n: int, mult: int = 8) -> int:
+    return (n + mult - 1) // mult * mult
+
+
+@dataclass
+class Act:
+    """One activation matrix [rows, width] in up to three storage planes (views into workspaces)."""
+
+    rows: int
+    width: int
+    f32: Optional[torch.Tensor] = None      # full fp32 values
+    hi: Optional[torch.Tensor] = None       # tf32-representable high part  (value = hi + lo)
+    lo: Optional[torch.Tensor] = None
+    bf16: Optional[torch.Tensor] = None
+
+    def resid_planes(self):
+        if self.f32 is not None:
+            return self.f32, None
+        if self.hi is not None:
+            return self.hi, self.lo
+        raise RuntimeError("activation has no fp32-accurate plane to use as a residual")
+
+
+def linear(engine: int, a: Act, w, w_lo, N: int, K: int, *, bias=None, relu=False, resid: Optional[Act] = None,
+           resid_sign: float = 1.0, colscale=None, postsub=None, out: Act, trans_w: bool = False) -> None:
+    """out = epilogue(a . w^T); see usf_linear in include/usflows_b200.h."""
+    args = LinearArgs()
+    args.M, args.N, args.K = a.rows, N, K
+    args.engine, args.trans_w = engine, int(trans_w)
+    if engine == ENGINE_TC_BF16:
+        args.a, args.a_lo, args.lda = _ptr(a.bf16), None, _ld(a.bf16)
+    elif engine == ENGINE_TC_3XTF32:
+        args.a, args.a_lo, args.lda = _ptr(a.hi), _ptr(a.lo), _ld(a.hi)
+    elif a.f32 is not None:
+        args.a, args.a_lo, args.lda = _ptr(a.f32), None, _ld(a.f32)
+    else:  # SIMT / TF32 reading split planes (SIMT adds lo; TF32 uses the hi plane)
+        args.a, args.a_lo, args.lda = _ptr(a.hi), (_ptr(a.lo) if engine == ENGINE_SIMT else None), _ld(a.hi)
+    args.w, args.w_lo, args.ldw = _ptr(w), _ptr(w_lo), _ld(w)
+    args.bias, args.relu, args.resid_sign = _ptr(bias), int(relu), float(resid_sign)
+    if resid is not None:
+        r, rl = resid.resid_planes()
+        args.resid, args.resid_lo, args.ldr = _ptr(r), _ptr(rl), _ld(r)
+    args.colscale, args.postsub = _ptr(colscale), _ptr(postsub)
+    if out.f32 is not None:
+        args.out_f32, args.ld_f32 = _ptr(out.f32), _ld(out.f32)
+    if out.hi is not None:
+        args.out_hi, args.out_lo, args.ld_split = _ptr(out.hi), _ptr(out.lo), _ld(out.hi)
+    if out.bf16 is not None:
+        args.out_bf16, args.ld_bf16 = _ptr(out.bf16), _ld(out.bf16)
+    check(_lib.load().usf_linear(C.byref(args), _stream()))
+
+
+def ingest(x: torch.Tensor, out: Act, *, div=None, mul=None, sub=None) -> None:
+    rows, d = x.shape
+    check(_lib.load().usf_ingest(
+        _ptr(x), _ld(x), rows, d, _ptr(div), _ptr(mul), _ptr(sub),
+        _ptr(out.f32), _ld(out.f32) if out.f32 is not None else 0,
+        _ptr(out.hi), _ptr(out.lo), _ld(out.hi) if out.hi is not None else 0,
+        _ptr(out.bf16), _ld(out.bf16) if out.bf16 is not None else 0, _stream()))
+
+
+def base_logprob(z: Act, loc, scale, kind: int, add_const: float, out: torch.Tensor) -> None:
+    p, pl = z.resid_planes()
+    check(_lib.load().usf_base_logprob(_ptr(p), _ptr(pl), _ld(p), z.rows, z.width, _ptr(loc), _ptr(scale), kind,
+                                       float(add_const), _ptr(out), _stream()))
+
+
+def base_sample(out: Act, loc, scale, kind: int, seed: int, offset: int) -> None:
+    check(_lib.load().usf_base_sample(
+        out.rows, out.width, _ptr(loc), _ptr(scale), kind, seed & (2**64 - 1), offset & (2**64 - 1),
+        _ptr(out.f32), _ld(out.f32) if out.f32 is not None else 0,
+        _ptr(out.hi), _ptr(out.lo), _ld(out.hi) if out.hi is not None else 0,
+        _ptr(out.bf16), _ld(out.bf16) if out.bf16 is not None else 0, _stream()))
+
+
+def leaky_relu(x: torch.Tensor, slope: float, y: torch.Tensor, neg_count: Optional[torch.Tensor] = None) -> None:
+    rows, d = x.shape
+    check(_lib.load().usf_leaky_relu(_ptr(x), _ld(x), rows, d, float(slope), _ptr(y), _ld(y), _ptr(neg_count), _stream()))
+
+
+def permute(x: torch.Tensor, perm_i32: torch.Tensor, y: torch.Tensor) -> None:
+    rows, d = x.shape
+    check(_lib.load().usf_permute(_ptr(x), _ld(x), rows, d, _ptr(perm_i32), _ptr(y), _ld(y), _stream()))
+
+
+# ---- weight preparation --------------------------------------------------------------------------
+def lu_assemble(L_raw, U_raw, L=None, U=None, transpose_u=False) -> None:
+    d = (L_raw if L_raw is not None else U_raw).shape[0]
+    ref = L if L is not None else U
+    check(_lib.load().usf_lu_assemble(_ptr(L_raw), _ptr(U_raw), d, _ld(L_raw if L_raw is not None else U_raw),
+                                      _ptr(L), _ptr(U), _ld(ref), int(transpose_u), _stream()))
+
+
+def lu_logabsdet(U_raw, out2) -> None:
+    check(_lib.load().usf_lu_logabsdet(_ptr(U_raw), U_raw.shape[0], _ld(U_raw), _ptr(out2), _stream()))
+
+
+def vec_logabs(v, out2) -> None:
+    check(_lib.load().usf_vec_logabs(_ptr(v), v.numel(), _ptr(out2), _stream()))
+
+
+def tri_inverse(T, lower: bool, unit_diag: bool, X) -> None:
+    d = T.shape[0]
+    n = _lib.load().usf_tri_inverse_work_floats(d)
+    work = torch.empty(n, dtype=torch.float32, device=T.device)
+    check(_lib.load().usf_tri_inverse(_ptr(T), d, _ld(T), int(lower), int(unit_diag), _ptr(X), _ld(X), _ptr(work), _stream()))
+
+
+def transpose(a, out) -> None:
+    check(_lib.load().usf_transpose(_ptr(a), a.shape[0], a.shape[1], _ld(a), _ptr(out), _ld(out), _stream()))
+
+
+def scale_rows_cols(a, out, rowf=None, colf=None) -> None:
+    check(_lib.load().usf_scale_rows_cols(_ptr(a), a.shape[0], a.shape[1], _ld(a), _ptr(rowf), _ptr(colf), _ptr(out), _ld(out), _stream()))
+
+
+def split_tf32(a, hi, lo) -> None:
+    check(_lib.load().usf_split_tf32(_ptr(a), a.shape[0], a.shape[1], _ld(a), _ptr(hi), _ptr(lo), _ld(hi), _stream()))
+
+
+def to_bf16(a, out) -> None:
+    check(_lib.load().usf_to_bf16(_ptr(a), a.shape[0], a.shape[1], _ld(a), _ptr(out), _ld(out), _stream()))
+
+
+def householder_right(W, v, work) -> None:
+    check(_lib.load().usf_householder_right(_ptr(W), W.shape[0], _ld(W), _ptr(v), _ptr(work), _stream()))
+
+
+def softplus(a, out) -> None:
+    check(_lib.load().usf_softplus(_ptr(a), a.numel(), _ptr(out), _stream()))
+
+
+def matmul_f32(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, bias=None) -> None:
+    """out = a @ b (+ bias) in fp32 on CUDA cores (weight preparation); b is [K, N] row-major."""
+    M, K = a.shape
+    N = b.shape[1]
+    linear(ENGINE_SIMT, Act(M, K, f32=a), b, None, N, K, bias=bias, out=Act(M, N, f32=out), trans_w=True)

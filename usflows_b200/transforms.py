@@ -1,0 +1,487 @@
+"""Transform layers of the flow stack -- drop-in mirrors of the reference's `src/usflows/transforms.py`.
+
+Same class names, constructor arguments, parameter names/shapes (state-dict compatible) and method surface
+(`forward`, `backward`, `log_abs_det_jacobian`, `is_feasible`, `add_jitter`, `log_prior`, `sign`, `simplify`,
+`matrix`/`bias`/`inverse_matrix`).  The arithmetic runs in the sm_100a kernels of libusflows_b200.so:
+weight-side work (L@U, triangular inverses, Householder products, log-dets) is computed once per weight
+version by the preparation kernels and cached; batch-side work goes through `engine.run_layers`.
+There is no CPU path: calling a layer with a non-CUDA tensor raises.
+
+Direction convention (as in the reference): `forward` = sampling direction (latent -> data),
+`backward` = density direction (data -> latent).
+"""
+from __future__ import annotations
+
+import math
+from typing import Iterable, List, Optional
+
+import torch
+from torch import nn
+from torch.nn import init
+
+from . import ops
+
+
+def _versions(params) -> tuple:
+    return tuple((p.data_ptr(), p._version) for p in params)
+
+
+class BaseTransform(nn.Module):
+    """Contract of every layer (reference transforms.py:23-69)."""
+
+    bijective = True
+
+    def is_feasible(self) -> bool:
+        return True
+
+    def add_jitter(self, jitter: float = 1e-6) -> None:
+        pass
+
+    def jitter(self, jitter: float = 1e-6) -> None:  # the reference's abstract name (transforms.py:37-39)
+        self.add_jitter(jitter)
+
+    def forward(self, x: torch.Tensor, context: Optional[torch.Tensor] = None) -> torch.Tensor:
+        from . import engine
+        return engine.run_layers([self], "forward", x)
+
+    def backward(self, y: torch.Tensor, context: Optional[torch.Tensor] = None) -> torch.Tensor:
+        from . import engine
+        return engine.run_layers([self], "backward", y)
+
+    def _call(self, x):
+        return self.forward(x)
+
+    def _inverse(self, y):
+        return self.backward(y)
+
+    def log_abs_det_jacobian(self, x, y, context=None):
+        raise NotImplementedError
+
+    def log_prior(self):
+        """Uniform (pseudo-)prior (transforms.py:62-64)."""
+        return 0.0
+
+    def simplify(self):
+        return self
+
+    def sign(self):
+        return 1
+
+    # engine hooks -------------------------------------------------------------------------------
+    def _ladj_device(self) -> Optional[torch.Tensor]:
+        """Device tensor [2] = (forward log|det J|, #infeasible entries), or None when identically 0."""
+        return None
+
+
+# ------------------------------------------------------------------------------------------------
+class ScaleTransform(BaseTransform):
+    """y = scale * x  (transforms.py:73-171)."""
+
+    def __init__(self, in_dims, prior_scale: float = 1.0):
+        super().__init__()
+        self.in_dims = in_dims
+        self.prior_scale = prior_scale
+        self.dim = math.prod(in_dims) if isinstance(in_dims, Iterable) else in_dims
+        self.scale = nn.Parameter(torch.empty(in_dims))
+        self.init_params()
+
+    def init_params(self):
+        bound = 1 / math.sqrt(self.dim) if self.dim > 0 else 0
+        init.uniform_(self.scale, -bound, bound)            # transforms.py:99-103
+
+    def log_abs_det_jacobian(self, x=None, y=None, context=None):
+        return self._ladj_device()[0]                          # sum log|scale| (:135-144)
+
+    def _ladj_device(self):
+        key = _versions([self.scale])
+        if getattr(self, "_ladj_key", None) != key:
+            ops.require_cuda(self.scale, "ScaleTransform.scale")
+            out = torch.empty(2, dtype=torch.float32, device=self.scale.device)
+            ops.vec_logabs(self.scale.detach().reshape(-1), out)
+            self._ladj_cache, self._ladj_key = out, key
+        return self._ladj_cache
+
+    def sign(self) -> int:
+        return 1 if int((self.scale < 0).sum()) % 2 == 0 else -1
+
+    def is_feasible(self) -> bool:
+        return bool((self.scale != 0).all())
+
+    def add_jitter(self, jitter: float = 1e-6) -> None:
+        # the reference's version references a non-existent attribute (transforms.py:154-157); fixed here
+        with torch.no_grad():
+            self.scale.add_(torch.randn_like(self.scale) * jitter)
+
+    def log_prior(self):
+        return 0
+
+
+class Permute(BaseTransform):
+    """y = x[..., permutation]  (transforms.py:174-251)."""
+
+    volume_preserving = True
+
+    def __init__(self, permutation: torch.Tensor, *, dim: int = -1, cache_size: int = 1):
+        super().__init__()
+        if dim >= 0:
+            raise ValueError("'dim' keyword argument must be negative")
+        self.permutation = permutation
+        self.dim = dim
+
+    @property
+    def inv_permutation(self):
+        result = torch.empty_like(self.permutation, dtype=torch.long)
+        result[self.permutation] = torch.arange(self.permutation.size(0), dtype=torch.long,
+                                                device=self.permutation.device)
+        return result
+
+    def log_abs_det_jacobian(self, x, y, context=None):
+        return torch.zeros(x.size()[:-1], dtype=x.dtype, device=x.device)
+
+    def to(self, device):
+        self.permutation = self.permutation.to(device)
+        return super().to(device)
+
+
+class LeakyReLUTransform(BaseTransform):
+    """y = leaky_relu(x, alpha)  (transforms.py:417-474).
+
+    `log_abs_det_jacobian` is per row: log(alpha) * #{x_j < 0}.  The reference sums log(y/x) over the whole
+    tensor including the batch axis (NaN at x = 0, transforms.py:474); on an unbatched vector -- the only
+    case the reference tests -- both agree.
+    """
+
+    def __init__(self, alpha: float = 0.01):
+        if alpha == 0:
+            raise ValueError("alpha must be positive")
+        super().__init__()
+        self.alpha = alpha
+
+    def log_abs_det_jacobian(self, x, y, context=None):
+        from . import engine
+        return engine.leaky_relu_ladj(x, self.alpha)
+
+
+# ------------------------------------------------------------------------------------------------
+class AffineTransform(BaseTransform):
+    """y = A x + b with getters for A, b, A^-1 (transforms.py:697-750).  Subclasses fill `_prepare`."""
+
+    def __init__(self, dim: int):
+        super().__init__()
+        self.dim = dim
+        self.input_shape = dim
+
+    def _prep_params(self) -> List[torch.Tensor]:
+        return list(self.parameters())
+
+    def _prepared(self) -> dict:
+        """dict(matrix [d,d], inverse_matrix [d,d], bias [d], ladj [2]) for the current weight version."""
+        key = _versions(self._prep_params())
+        if getattr(self, "_prep_key", None) != key:
+            for p in self._prep_params():
+                ops.require_cuda(p, f"{type(self).__name__} parameter")
+            with torch.no_grad():
+                self._prep_cache = self._prepare()
+            self._prep_key = key
+        return self._prep_cache
+
+    def _prepare(self) -> dict:
+        raise NotImplementedError
+
+    def matrix(self) -> torch.Tensor:
+        return self._prepared()["matrix"]
+
+    def inverse_matrix(self) -> torch.Tensor:
+        return self._prepared()["inverse_matrix"]
+
+    def bias(self) -> torch.Tensor:
+        return self._prepared()["bias"]
+
+    def log_abs_det_jacobian(self, x=None, y=None, context=None):
+        return self._prepared()["ladj"][0]
+
+    def _ladj_device(self):
+        return self._prepared()["ladj"]
+
+    def simplify(self):
+        return self
+
+
+class LUTransform(AffineTransform):
+    """y = (L U) x + b with L unit lower, U upper triangular (transforms.py:1178-1379)."""
+
+    volume_preserving = False
+
+    def __init__(self, dim: int, prior_scale: float = 1.0):
+        super().__init__(dim)
+        self.L_raw = nn.Parameter(torch.empty(dim, dim))
+        self.U_raw = nn.Parameter(torch.empty(dim, dim))
+        self.bias_vector = nn.Parameter(torch.empty(dim))
+        self.prior_scale = prior_scale
+        self.init_params()
+        self.L_mask = torch.tril(torch.ones(dim, dim), diagonal=-1)
+        self.U_mask = torch.triu(torch.ones(dim, dim), diagonal=0)
+        self.L_raw.register_hook(lambda grad: grad * self.L_mask.to(grad.device))   # transforms.py:1212-1213
+        self.U_raw.register_hook(lambda grad: grad * self.U_mask.to(grad.device))
+
+    def init_params(self):
+        """Same init distributions as transforms.py:1215-1240."""
+        init.kaiming_uniform_(self.L_raw, nonlinearity="relu")
+        with torch.no_grad():
+            self.L_raw.copy_(self.L_raw.tril(diagonal=-1).fill_diagonal_(1))
+        init.kaiming_uniform_(self.U_raw, nonlinearity="relu")
+        with torch.no_grad():
+            self.U_raw.fill_diagonal_(0)
+            d = self.dim
+            sign = -torch.ones(d) + 2 * torch.bernoulli(0.5 * torch.ones(d))
+            scale = self.prior_scale * torch.ones(d) * 1 / d if self.prior_scale is not None else torch.ones(d)
+            self.U_raw += sign * torch.normal(torch.zeros(d), scale).exp().diag()
+            self.U_raw.copy_(self.U_raw.triu())
+        bound = 1 / math.sqrt(self.dim) if self.dim > 0 else 0
+        init.uniform_(self.bias_vector, -bound, bound)
+
+    def _prepare(self) -> dict:
+        d, dev = self.dim, self.L_raw.device
+        new = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)  # noqa: E731
+        L, U = new(d, d), new(d, d)
+        ops.lu_assemble(self.L_raw.detach(), self.U_raw.detach(), L, U)       # :1271-1279
+        W = new(d, d)
+        ops.matmul_f32(L, U, W)                                                # matrix = L @ U (:1281-1283)
+        Linv, Uinv = new(d, d), new(d, d)
+        ops.tri_inverse(L, True, True, Linv)                                   # inverse(L), inverse(U)
+        ops.tri_inverse(U, False, False, Uinv)                                 #   (:1291-1292)
+        Winv = new(d, d)
+        ops.matmul_f32(Uinv, Linv, Winv)                                       # U^-1 @ L^-1 (:1293)
+        ladj = new(2)
+        ops.lu_logabsdet(self.U_raw.detach(), ladj)                            # sum log|diag U| (:1303-1320)
+        return dict(matrix=W, inverse_matrix=Winv, bias=self.bias_vector.detach(), ladj=ladj,
+                    L=L, U=U, L_inv=Linv, U_inv=Uinv)
+
+    @property
+    def L(self) -> torch.Tensor:
+        return self._prepared()["L"]
+
+    @property
+    def U(self) -> torch.Tensor:
+        return self._prepared()["U"]
+
+    def sign(self):
+        return self.U_raw.diag().prod().sign()
+
+    def to(self, device):
+        self.L_mask = self.L_mask.to(device)
+        self.U_mask = self.U_mask.to(device)
+        self.device = device
+        return super().to(device)
+
+    def is_feasible(self) -> bool:
+        return bool((self.U_raw.diag() != 0).all())
+
+    def add_jitter(self, jitter: float = 1e-6) -> None:
+        with torch.no_grad():
+            self.U_raw.diagonal().add_(torch.randn(self.dim, device=self.U_raw.device) * jitter)
+
+    def log_prior(self):
+        x = self.U_raw.diag().abs().log()
+        return -(x * x).sum() / (2 * self.prior_scale ** 2) - x.sum()
+
+
+class HouseholderTransform(AffineTransform):
+    """y = H x, H = w_0 prod_k (I - 2 v_k v_k^T / v_k.v_k)  (transforms.py:752-872); log|det| = 0."""
+
+    ladj = 0
+
+    def __init__(self, dim: int, nvs: int = 1, device="cpu"):
+        super().__init__(dim)
+        self.nvs = nvs
+        indices = torch.randperm(dim)
+        w = torch.zeros((dim, dim))
+        w[torch.arange(dim), indices] = 1.0
+        self.vk_householder = nn.Parameter(0.2 * torch.randn(nvs, dim))
+        self.w_0 = nn.Parameter(w, requires_grad=False)
+        self.to(device)
+
+    def _prepare(self) -> dict:
+        d, dev = self.dim, self.w_0.device
+        W = self.w_0.detach().clone()
+        work = torch.empty(d, dtype=torch.float32, device=dev)
+        for k in range(self.nvs):
+            ops.householder_right(W, self.vk_householder.detach()[k].contiguous(), work)  # :795-809
+        Wt = torch.empty(d, d, dtype=torch.float32, device=dev)
+        ops.transpose(W, Wt)                                                               # :864-868
+        return dict(matrix=W, inverse_matrix=Wt, bias=torch.zeros(d, dtype=torch.float32, device=dev),
+                    ladj=torch.zeros(2, dtype=torch.float32, device=dev))
+
+
+class SequentialAffineTransform(AffineTransform):
+    """Composition of affine maps as one matrix + bias (transforms.py:1381-1486)."""
+
+    def __init__(self, transforms: Iterable[AffineTransform]):
+        transforms = list(transforms)
+        dim = transforms[0].dim
+        if any(t.dim != dim for t in transforms):
+            raise ValueError("All transforms must have the same dimension")
+        super().__init__(dim)
+        self.transforms = nn.ModuleList(transforms)
+
+    def _prepare(self) -> dict:
+        parts = [t._prepared() for t in self.transforms]
+        d, dev = self.dim, parts[0]["matrix"].device
+        new = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)  # noqa: E731
+        # matrix: I @ A_1 @ A_2 ... (:1457-1462); inverse: I @ A_n^-1 @ ... @ A_1^-1 (:1464-1469)
+        M = parts[0]["matrix"]
+        for p in parts[1:]:
+            out = new(d, d)
+            ops.matmul_f32(M, p["matrix"], out)
+            M = out
+        Minv = parts[-1]["inverse_matrix"]
+        for p in parts[-2::-1]:
+            out = new(d, d)
+            ops.matmul_f32(Minv, p["inverse_matrix"], out)
+            Minv = out
+        # bias: b = 0; b = b @ A_k + b_k (:1471-1476)
+        b = parts[0]["bias"]
+        for p in parts[1:]:
+            out = new(1, d)
+            ops.matmul_f32(b.reshape(1, d), p["matrix"], out, bias=p["bias"])
+            b = out.reshape(d)
+        ladj = torch.stack([p["ladj"] for p in parts]).sum(0)                  # :1429-1446
+        return dict(matrix=M, inverse_matrix=Minv, bias=b, ladj=ladj)
+
+    def is_feasible(self) -> bool:
+        return all(t.is_feasible() for t in self.transforms)
+
+    def add_jitter(self, jitter: float = 1e-6) -> None:
+        for t in self.transforms:
+            t.add_jitter(jitter)
+
+    def sign(self):
+        return math.prod([t.sign() for t in self.transforms])
+
+    def to(self, device):
+        for t in self.transforms:
+            t.to(device)
+        self.device = device
+        return super().to(device)
+
+
+class BlockAffineTransform(BaseTransform):
+    """Applies an AffineTransform over `in_dims[0]` (transforms.py:874-1029).  Flat inputs (1-D `in_dims`)
+    are supported; the 1x1-convolution modes of image-shaped `in_dims` are not built yet."""
+
+    def __init__(self, in_dims: Iterable[int], block_transform: AffineTransform):
+        super().__init__()
+        self.in_dims = list(in_dims)
+        if block_transform.dim != self.in_dims[0]:
+            raise ValueError("block_transform dim must match input dim")
+        self.block_size = self.in_dims[0]
+        self.input_rank = len(self.in_dims) - 1
+        self.n_blocks = math.prod(self.in_dims[1:])
+        if self.input_rank != 0:
+            raise NotImplementedError("usflows_b200: only flat in_dims=[d] is implemented (SURVEY 8f, next-3)")
+        self.block_transform = block_transform
+
+    def log_abs_det_jacobian(self, x=None, y=None, context=None):
+        return self.block_transform.log_abs_det_jacobian(x, y, context) * self.n_blocks
+
+    def _ladj_device(self):
+        return self.block_transform._ladj_device() * torch.tensor(
+            [float(self.n_blocks), 1.0], device=self.block_transform._ladj_device().device)
+
+    def sign(self):
+        return self.block_transform.sign() ** self.n_blocks
+
+    def is_feasible(self) -> bool:
+        return self.block_transform.is_feasible()
+
+    def add_jitter(self, jitter: float = 1e-6) -> None:
+        self.block_transform.add_jitter(jitter)
+
+    def to(self, device):
+        self.block_transform.to(device)
+        return super().to(device)
+
+
+class InverseTransform(BaseTransform):
+    """Swaps forward/backward of the wrapped transform and negates its log-det (transforms.py:349-414)."""
+
+    def __init__(self, transform: BaseTransform):
+        super().__init__()
+        self.transform = transform
+        self.bijective = transform.bijective
+
+    def log_abs_det_jacobian(self, x=None, y=None, context=None):
+        return -self.transform.log_abs_det_jacobian(x, y, context)
+
+    def _ladj_device(self):
+        inner = self.transform._ladj_device()
+        if inner is None:
+            return None
+        return inner * torch.tensor([-1.0, 1.0], device=inner.device)
+
+    def sign(self):
+        return self.transform.sign()
+
+    def is_feasible(self) -> bool:
+        return self.transform.is_feasible()
+
+    def add_jitter(self, jitter: float = 1e-6) -> None:
+        self.transform.add_jitter(jitter)
+
+    def simplify(self):
+        return InverseTransform(self.transform.simplify())
+
+
+class MaskedCoupling(BaseTransform):
+    """y = x + (1 - mask) * conditioner(x * mask)  (additive coupling, transforms.py:254-347); log|det| = 0.
+
+    The conditioner must be a `usflows_b200.nn.DenseNN` (Linear/ReLU stack): its GEMMs, the masking and the
+    residual add/sub run fused in the contraction kernels' epilogues."""
+
+    def __init__(self, mask: torch.Tensor, conditioner: nn.Module):
+        super().__init__()
+        self.mask = mask
+        self.conditioner = conditioner
+        self.input_shape = mask.shape
+
+    def log_abs_det_jacobian(self, x=None, y=None, context=None):
+        return 0.0
+
+    def sign(self):
+        return 1.0
+
+    def to(self, device):
+        self.mask = self.mask.to(device)
+        return super().to(device)
+
+    def _prepared(self) -> dict:
+        """Mask folded into the first / last Linear: (x*m) W1^T = x (W1 diag(m))^T and
+        (1-m) * (h W3^T + b3) = h (diag(1-m) W3)^T + (1-m) b3 -- exact, multiplying by 0/1."""
+        lin = list(self.conditioner.layers)
+        params = [p for layer in lin for p in (layer.weight, layer.bias)]
+        key = _versions(params) + (self.mask.data_ptr(),)
+        if getattr(self, "_prep_key", None) != key:
+            for p in params:
+                ops.require_cuda(p, "conditioner parameter")
+            dev = params[0].device
+            m = self.mask.to(dev).reshape(-1).to(torch.float32).contiguous()
+            inv = (1 - m).contiguous()
+            with torch.no_grad():
+                ws = [l.weight.detach() for l in lin]
+                bs = [l.bias.detach() for l in lin]
+                w_first = torch.empty_like(ws[0])
+                ops.scale_rows_cols(ws[0], w_first, colf=m)
+                if len(lin) == 1:
+                    tmp = torch.empty_like(w_first)
+                    ops.scale_rows_cols(w_first, tmp, rowf=inv)
+                    ws = [tmp]
+                else:
+                    w_last = torch.empty_like(ws[-1])
+                    ops.scale_rows_cols(ws[-1], w_last, rowf=inv)
+                    ws = [w_first] + ws[1:-1] + [w_last]
+                b_last = torch.empty_like(bs[-1])
+                ops.scale_rows_cols(bs[-1].reshape(1, -1), b_last.reshape(1, -1), colf=inv)
+                bs = bs[:-1] + [b_last]
+            self._prep_cache = dict(weights=ws, biases=bs)
+            self._prep_key = key
+        return self._prep_cache
