@@ -1,0 +1,311 @@
+#!/usr/bin/env python
+"""Benchmark of the USFlows hot path on B200:  `log_prob` throughput (samples/s) of a flat USFlow.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c4|c5|c1] [--precision fp32|tf32|bf16]
+    python bench.py --impl reference ...      # the reference algorithm's CPU path (oracle port) on host cores
+
+Contract (one JSON line on stdout, printed by rank 0): metric/value/unit/n_gpus/steps/warmup/ms_per_step/
+higher_is_better/scaling/vs_baseline/dtype/data/config + roofline, cpu_baseline, e2e, clocks, gpu_launches.
+
+A "step" is one `log_prob` pass over one batch of synthetic rows per GPU (weak scaling: every rank evaluates
+its own `rows` rows, no data-path collective).  `value` is measured with the batch resident in HBM; `e2e` goes
+through `Flow.log_prob_host` with pinned HOST buffers (H2D of the batch and D2H of the log-probs inside the
+timed region).  Workloads follow BASELINE.json / SURVEY 8d:
+  c2: d=784,  B=4, MLP [1024,1024], Laplace base, 65536 rows   <- the configuration the metric is quoted on
+  c4: d=3072, B=8, MLP [1024,1024], Normal base,  32768 rows
+  c5: d=3072, B=4, MLP [1024,1024], Laplace base, 32768 rows
+  c1: d=2,    B=10, MLP [32,32],    Laplace base, 1048576 rows
+Inputs are larger than L2 (c2: 205 MB per batch vs 126 MB), so no explicit L2 flush is needed between steps.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    "c2": dict(spec=dict(in_dims=[784], coupling_blocks=4, hidden_dims=[1024, 1024], affine_conjugation=True,
+                         lu_transform=1, householder=0, base="laplace"), rows=65536, cpu_rows=8192,
+               name="C2 MNIST-shaped 784-D USFlow (B=4, MLP 1024x1024, Laplace) batch log_prob"),
+    "c4": dict(spec=dict(in_dims=[3072], coupling_blocks=8, hidden_dims=[1024, 1024], affine_conjugation=True,
+                         lu_transform=1, householder=0, base="normal"), rows=32768, cpu_rows=1024,
+               name="C4 CIFAR-shaped 3072-D USFlow (B=8, MLP 1024x1024, Normal) batch log_prob"),
+    "c5": dict(spec=dict(in_dims=[3072], coupling_blocks=4, hidden_dims=[1024, 1024], affine_conjugation=True,
+                         lu_transform=1, householder=0, base="laplace"), rows=32768, cpu_rows=2048,
+               name="C5 3072-D USFlow (B=4, MLP 1024x1024, Laplace) batch log_prob"),
+    "c1": dict(spec=dict(in_dims=[2], coupling_blocks=10, hidden_dims=[32, 32], affine_conjugation=True,
+                         lu_transform=1, householder=0, base="laplace"), rows=1 << 20, cpu_rows=65536,
+               name="C1 2-D USFlow (B=10, MLP 32x32, Laplace) batch log_prob"),
+}
+
+
+def algorithmic_flops_per_sample(spec) -> float:
+    """(2B+1) * 2 d^2 + B * 2 (d H + H^2 + H d) with conjugation (B+1 affine layers without)."""
+    d, B = spec["in_dims"][0], spec["coupling_blocks"]
+    dims = [d] + list(spec["hidden_dims"]) + [d]
+    mlp = sum(2 * dims[i] * dims[i + 1] for i in range(len(dims) - 1))
+    n_aff = 2 * B + 1 if spec.get("affine_conjugation") else B + 1
+    return n_aff * 2 * d * d + B * mlp
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f), "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, smax, reasons, power = [], None, set(), []
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax = float(f[2]); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "power_w_max": max(power) if power else None, "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_run(wl, steps: int, warmup: int, rows: int):
+    """The reference algorithm's own CPU path (oracle port = same ATen ops in the same order, including the
+    per-call weight re-preparation) on all host cores.  Returns (as-is samples/s, amortised samples/s, cores)."""
+    import torch
+    from oracle import flow_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    spec = wl["spec"]
+    params = O.random_params(spec, 0)
+    g = torch.Generator().manual_seed(1)
+    x = torch.rand(rows, spec["in_dims"][0], generator=g)
+    with torch.no_grad():
+        for _ in range(warmup):
+            O.flow_log_prob(x, spec, params)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            O.flow_log_prob(x, spec, params)
+        t_asis = (time.perf_counter() - t0) / steps
+        _, prepared = O.flow_log_prob_amortised(x, spec, params)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            O.flow_log_prob_amortised(x, spec, params, prepared=prepared)
+        t_am = (time.perf_counter() - t0) / steps
+    return rows / t_asis, rows / t_am, cores, t_asis
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="usflows_b200", choices=["usflows_b200", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "fp32_simt", "tf32", "bf16"])
+    ap.add_argument("--rows", type=int, default=0, help="rows per GPU per step (default: the workload's)")
+    ap.add_argument("--chunk-rows", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-modes", action="store_true", help="skip the extra tf32 / bf16 mode measurements")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    wl = WORKLOADS[args.workload]
+    spec = wl["spec"]
+    d = spec["in_dims"][0]
+    flops_per_sample = algorithmic_flops_per_sample(spec)
+
+    base_line = dict(metric="log_prob_samples_per_sec", unit="samples/s", n_gpus=args.gpus, steps=args.steps,
+                     warmup=args.warmup, higher_is_better=True, scaling="weak", vs_baseline=None,
+                     data="synthetic")
+
+    # ---------------------------------------------------------------- reference arm (CPU, rank 0 only)
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        rows = args.rows or wl["cpu_rows"]
+        v_asis, v_am, cores, t = cpu_reference_run(wl, max(1, args.steps), max(1, min(args.warmup, 1)), rows)
+        line = dict(base_line, impl="reference", value=v_asis, ms_per_step=t * 1e3, dtype="f32",
+                    config=dict(workload=wl["name"], rows_per_step=rows, d=d, hidden=spec["hidden_dims"],
+                                coupling_blocks=spec["coupling_blocks"], engine="torch CPU (oracle port of the reference)"),
+                    cpu_baseline=dict(value=v_asis, unit="samples/s", cores=cores, kind="port",
+                                      sample=f"{rows} rows x {max(1, args.steps)} steps of the same workload; "
+                                             f"as-is (per-call weight re-preparation, as the reference does); "
+                                             f"amortised = {v_am:.1f} samples/s", amortised_value=v_am),
+                    e2e=dict(value=v_asis, unit="samples/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+        print(json.dumps(line), flush=True)
+        return
+
+    # ---------------------------------------------------------------- B200 arm
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    import usflows_b200 as U
+    from usflows_b200 import engine, ops
+    from oracle import flow_oracle as O      # parameters only (deterministic synthetic model); timed code is ours
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import build_flow
+
+    if args.chunk_rows:
+        U.set_chunk_rows(args.chunk_rows)
+    rows = args.rows or wl["rows"]
+    params = O.random_params(spec, 0)
+    flow = build_flow(spec, params, device=dev, precision=args.precision)
+    g = torch.Generator().manual_seed(1 + rank)
+    x_host = torch.rand(rows, d, generator=g).pin_memory()
+    x = x_host.to(dev)
+    out_host = torch.empty(rows, dtype=torch.float32).pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms) / steps
+
+    # preparation (once per weight version) timed separately
+    t0 = time.perf_counter()
+    lp = flow.log_prob(x[:256])
+    torch.cuda.synchronize()
+    prep_ms = (time.perf_counter() - t0) * 1e3
+
+    step = lambda: flow.log_prob(x)                    # noqa: E731
+    for _ in range(args.warmup):
+        step()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ops.LAUNCHES = 0
+    ms_step = timed(step, args.steps)
+    launches = ops.LAUNCHES
+    value = world * rows / (ms_step * 1e-3)
+
+    # end to end: pinned host rows in, host log-probs out, copies inside the timed region
+    e2e_step = lambda: flow.log_prob_host(x_host, out_host)   # noqa: E731
+    for _ in range(max(1, args.warmup // 2)):
+        e2e_step()
+    ms_e2e = timed(e2e_step, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # kernel-class breakdown of one step (events around every launch; after the timed region)
+    breakdown = engine.profile_step(lambda: flow.log_prob(x))
+    gemm_ms = sum(v for k, v in breakdown.items() if k.startswith("linear"))
+    peaks, peak_kind = measured_peaks()
+    achieved_tf = rows * flops_per_sample / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+    peak_tf = peaks["bf16_tflops_sustained"]
+    n_gemm = sum(1 for k in breakdown.get("_names", []) if k.startswith("linear")) or 1
+
+    extra_modes = {}
+    if not args.no_modes and rank == 0 and world == 1:
+        for mode in ("tf32", "bf16"):
+            if mode == args.precision:
+                continue
+            f2 = build_flow(spec, params, device=dev, precision=mode)
+            f2.log_prob(x[:256])
+            for _ in range(2):
+                f2.log_prob(x)
+            ms = timed(lambda: f2.log_prob(x), max(3, args.steps // 2))
+            ref = lp.double().cpu()
+            err = float(((f2.log_prob(x[:256]).double().cpu() - ref).abs() / ref.abs().clamp(min=1)).max())
+            extra_modes[mode] = dict(value=rows / (ms * 1e-3), ms_per_step=ms,
+                                     tflops=rows * flops_per_sample / (ms * 1e-3) / 1e12,
+                                     max_rel_diff_vs_fp32_mode=err)
+            del f2
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        v_asis, v_am, cores, _ = cpu_reference_run(wl, 3, 1, wl["cpu_rows"])
+        cpu = dict(value=v_asis, unit="samples/s", cores=cores, kind="port",
+                   sample=f"{wl['cpu_rows']} rows x 3 steps of the same workload through the oracle port of the "
+                          f"reference (torch CPU, per-call weight re-preparation as the reference does)",
+                   amortised_value=v_am)
+
+    line = dict(
+        base_line, impl="usflows_b200", value=value, ms_per_step=ms_step,
+        dtype={"fp32": "f32 (tf32x3 split on tcgen05, fp32 accumulate)", "fp32_simt": "f32", "tf32": "tf32",
+               "bf16": "bf16"}[args.precision],
+        config=dict(workload=wl["name"], rows_per_gpu_per_step=rows, d=d, hidden=spec["hidden_dims"],
+                    coupling_blocks=spec["coupling_blocks"], precision=args.precision,
+                    chunk_rows=engine._default_chunk_rows, l2="inputs larger than L2, no flush",
+                    flops_per_sample=flops_per_sample, prep_ms_once_per_weight_version=prep_ms),
+        roofline=dict(bound="tensor", achieved=achieved_tf, peak=peak_tf, unit="TFLOP/s",
+                      frac=achieved_tf / peak_tf, traffic=None, peak_source=f"bf16_tflops_sustained ({peak_kind})",
+                      kernel="tc::gemm_tc_kernel (all launches of one step)", kernel_ms_per_step=gemm_ms,
+                      launches_per_step=n_gemm,
+                      note="algorithmic fp32 FLOPs; the fp32 mode spends 3 tf32 MMAs (= 6 bf16-equivalents) per "
+                           "algorithmic MAC, so its ceiling is 1/6 of this peak",
+                      frac_of_mode_ceiling=(achieved_tf / (peak_tf / 6.0)) if args.precision == "fp32" else None),
+        cpu_baseline=cpu,
+        e2e=dict(value=world * rows / (ms_e2e * 1e-3), unit="samples/s", ms_per_step=ms_e2e,
+                 h2d_bytes_per_step=rows * d * 4, d2h_bytes_per_step=rows * 4),
+        gpu_launches=launches, clocks=clocks, modes=extra_modes,
+        breakdown_ms={k: v for k, v in breakdown.items() if not k.startswith("_")})
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -91,6 +91,13 @@ typedef struct usf_linear_args {
 
 int usf_linear(const usf_linear_args* args, void* stream);
 
+/* TC_3XTF32 accuracy knob: number of 32-element K-slabs accumulated in TMEM before the partial tile is
+ * added into fp32 registers with round-to-nearest (the tensor core truncates when it accumulates; long
+ * chains carry a systematic toward-zero bias).  0 = accumulate the whole K in TMEM.  Default 2. */
+int usf_set_accum_chunk(int k_slabs);
+/* test hook: force the tcgen05 tile width BLOCK_N (0 = automatic) */
+int usf_debug_set_block_n(int block_n);
+
 /* ------------------------------------------------------------------------------------------------
  * elementwise / reduction kernels over [N_rows, d] activations (HBM-bound, 128-bit accesses)
  */

@@ -331,7 +331,7 @@ def base_log_prob(z: Tensor, spec: dict, params) -> Tensor:
     else:
         var = s ** 2
         lp = -((z - loc) ** 2) / (2 * var) - s.log() - math.log(math.sqrt(2 * math.pi))
-    return lp.reshape(z.shape[0], -1).sum(-1) if loc.dim() >= 1 else lp
+    return lp.sum(dim=tuple(range(z.dim() - loc.dim(), z.dim()))) if loc.dim() >= 1 else lp
 
 
 def base_sample_from_uniform(u: Tensor, spec: dict, params) -> Tensor:

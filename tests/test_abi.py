@@ -1,0 +1,62 @@
+"""The C-ABI library builds for sm_100a, loads, and exports every symbol include/usflows_b200.h declares
+(no compute calls: this runs without a GPU)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    with open(os.path.join(ROOT, "include", "usflows_b200.h")) as f:
+        text = f.read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(usf_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_are_exported_and_bound():
+    from usflows_b200 import _lib
+    lib = _lib.load()
+    declared = _declared_symbols()
+    assert len(declared) >= 20
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+        assert name in _lib.SIGNATURES, f"{name} has no ctypes signature in _lib.py"
+    assert lib.usf_abi_version() == 1
+
+
+def test_linear_args_layout_matches_header():
+    """ctypes mirror vs the C struct: field order and count."""
+    from usflows_b200 import _lib
+    with open(os.path.join(ROOT, "include", "usflows_b200.h")) as f:
+        text = f.read()
+    body = re.search(r"typedef struct usf_linear_args \{(.*?)\} usf_linear_args;", text, flags=re.S).group(1)
+    fields = re.findall(r"\b([A-Za-z_0-9]+);", body)
+    assert fields == [f[0] for f in _lib.LinearArgs._fields_]
+    assert ctypes.sizeof(_lib.LinearArgs) == 8 + 4 * 4 + 6 * 8 + 8 + 4 + 4 + 3 * 8 + 2 * 8 + 2 * 8 + 3 * 8 + 2 * 8
+
+
+def test_invalid_arguments_fail_loudly_without_gpu():
+    from usflows_b200 import _lib
+    lib = _lib.load()
+    rc = lib.usf_linear(None, None)
+    assert rc == -1 and b"null args" in lib.usf_last_error()
+    with pytest.raises(RuntimeError, match="usflows_b200"):
+        _lib.check(rc)
+
+
+def test_sass_contains_blackwell_tensor_and_tma_instructions():
+    """tcgen05.mma -> UTC*MMA, TMA -> UTMALDG, tcgen05.ld -> LDTM (B200_PROFILING.md)."""
+    import shutil
+    import subprocess
+    from usflows_b200 import _lib
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    _lib.load()
+    sass = subprocess.run([cuobjdump, "-sass", _lib.library_path()], capture_output=True, text=True).stdout
+    for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM"):
+        assert mnemonic in sass, mnemonic
+    assert "sm_100a" in sass

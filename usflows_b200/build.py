@@ -21,8 +21,8 @@ INCLUDE = os.path.join(os.path.dirname(PKG), "include")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
-    "-O3", "-std=c++17", "-lineinfo", "-shared", "-Xcompiler", "-fPIC",
-    "--expt-relaxed-constexpr", "-Xptxas", "-v", "--cudart", "shared",
+    "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
+    "--expt-relaxed-constexpr", "-Xptxas", "-v",
 ]
 
 
@@ -53,12 +53,28 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     os.makedirs(LIBDIR, exist_ok=True)
-    cmd = [nvcc] + NVCC_FLAGS + ["-I", INCLUDE, "-o", LIB, os.path.join(CSRC, "capi.cu")]
-    proc = subprocess.run(cmd, capture_output=True, text=True)
-    log = proc.stdout + proc.stderr
+    units = sorted(f for f in os.listdir(CSRC) if f.endswith(".cu"))
+    objs = [os.path.join(LIBDIR, u[:-3] + ".o") for u in units]
+
+    def compile_one(pair):
+        src, obj = pair
+        cmd = [nvcc] + NVCC_FLAGS + ["-I", INCLUDE, "-c", "-o", obj, os.path.join(CSRC, src)]
+        proc = subprocess.run(cmd, capture_output=True, text=True)
+        return " ".join(cmd) + "\n" + proc.stdout + proc.stderr, proc.returncode
+
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=len(units)) as pool:      # translation units compile in parallel
+        results = list(pool.map(compile_one, zip(units, objs)))
+    log = "\n".join(r[0] for r in results)
+    rc = max(r[1] for r in results)
+    if rc == 0:
+        cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "--cudart", "shared", "-o", LIB] + objs
+        proc = subprocess.run(cmd, capture_output=True, text=True)
+        log += "\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr
+        rc = proc.returncode
     with open(os.path.join(LIBDIR, "build.log"), "w") as f:
-        f.write(" ".join(cmd) + "\n" + log)
-    if proc.returncode != 0:
+        f.write(log)
+    if rc != 0:
         raise RuntimeError("nvcc failed:\n" + log[-8000:])
     if verbose:
         print(log)

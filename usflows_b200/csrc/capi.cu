@@ -9,6 +9,7 @@ namespace usf {
 
 thread_local char g_err[512] = "";
 int g_force_block_n = 0;
+int g_chunk_slabs = 2;
 
 int num_sms() {
   static int cached[64] = {0};
@@ -92,6 +93,12 @@ int usf_device_info(int* sm_count, int* cc_major, int* cc_minor, int64_t* l2_byt
 
 int usf_debug_set_block_n(int bn) {  // test hook: force the tcgen05 tile width (0 = automatic)
   g_force_block_n = bn;
+  return USF_OK;
+}
+
+int usf_set_accum_chunk(int k_slabs) {  // 3xTF32 mode: K-slabs (32 elements each) per accumulation chain; 0 = whole K
+  USF_REQUIRE(k_slabs >= 0, "negative chunk");
+  g_chunk_slabs = k_slabs;
   return USF_OK;
 }
 

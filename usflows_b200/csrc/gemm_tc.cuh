@@ -8,9 +8,16 @@
 //     tile i+1
 //   * NTERMS = 3 is the fp32-accurate mode: A = A_hi + A_lo, W = W_hi + W_lo with every plane exactly
 //     representable in tf32; D = A_hi.W_hi + A_lo.W_hi + A_hi.W_lo accumulated in fp32 (error ~2^-21)
+//   * the tensor core adds into its fp32 accumulator with truncation, so a long K chain carries a
+//     systematic toward-zero bias (~0.2 ulp per MMA step, measured: 5e-6 relative at K=1024 x 3 terms,
+//     coherent across layers).  The fp32 mode therefore closes the TMEM accumulator every
+//     `chunk_slabs` K-slabs and the epilogue warps add the partial tile into fp32 registers with
+//     round-to-nearest (two TMEM accumulators ping-pong between the MMA issuer and the epilogue)
 //   * persistent CTAs (grid = min(tiles, SMs)), warp-specialised: warp 0 TMA producer, warp 1 MMA
-//     issuer + TMEM owner, warps 2..5 epilogue (tcgen05.ld 32x32b -> registers -> fused epilogue ->
-//     global stores)
+//     issuer + TMEM owner, warps 4..11 epilogue (tcgen05.ld 32x32b -> registers -> fused epilogue ->
+//     global stores; warp w owns TMEM lane quarter w % 4 and one half of the tile's columns); the
+//     epilogue warpgroups take the register file with setmaxnreg (232 regs: up to 128 fp32 partial sums
+//     per thread stay in registers)
 #pragma once
 #include "common.cuh"
 
@@ -25,8 +32,11 @@ namespace tc {
 constexpr int BLOCK_M = 128;
 constexpr int SLAB_BYTES = 128;  // K extent of one stage in bytes (= swizzle span)
 constexpr int UMMA_K_BYTES = 32;
-constexpr int NUM_THREADS = 192;
-constexpr int NUM_EPI_WARPS = 4;
+constexpr int NUM_THREADS = 384;   // warpgroup 0: TMA producer, MMA issuer, 2 idle warps; warpgroups 1-2: epilogue
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int FIRST_EPI_WARP = 4;
+constexpr int REGS_NON_EPI = 48;   // setmaxnreg budget after role dispatch: 128*48 + 256*232 = 65536
+constexpr int REGS_EPI = 232;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -143,6 +153,7 @@ template <int BLOCK_N, int NTERMS, bool BF16>
 struct Config {
   static_assert(BLOCK_N % 16 == 0 && BLOCK_N >= 16 && BLOCK_N <= 256, "UMMA N for M=128");
   static_assert(NTERMS == 1 || NTERMS == 3, "1 = single pass, 3 = tf32 split");
+  static constexpr int kBlockN = BLOCK_N;
   static constexpr int NPLANES = NTERMS == 3 ? 2 : 1;
   static constexpr int A_TILE = BLOCK_M * SLAB_BYTES;
   static constexpr int B_TILE = BLOCK_N * SLAB_BYTES;
@@ -156,16 +167,75 @@ struct Config {
   static constexpr int TMEM_COLS = 2 * ACC_STRIDE;  // power of two >= 64
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
   static constexpr int ELEMS_PER_SLAB = SLAB_BYTES / (BF16 ? 2 : 4);
+  static constexpr int HALF0 = ((BLOCK_N / 16 + 1) / 2) * 16;  // columns owned by epilogue warps 4..7
+  static constexpr int HALF1 = BLOCK_N - HALF0;                // ... and by warps 8..11 (may be 0)
   // instruction descriptor: D=f32, A/B = tf32 (2) or bf16 (1), both K-major, N>>3, M>>4
   static constexpr uint32_t IDESC = (1u << 4) | ((BF16 ? 1u : 2u) << 7) | ((BF16 ? 1u : 2u) << 10) |
                                     ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
 };
 
+// One epilogue warp: owns TMEM lanes [32*quarter, 32*quarter+32) and columns [col0, col0+COLS) of every tile.
+// Partial accumulators (one per K chunk) are summed in fp32 registers (round-to-nearest), then the fused
+// epilogue runs on the register tile.  tfull0/tempty0 are the addresses of barrier 0 of each pair (8 B apart).
+template <class C, int COLS>
+__device__ __forceinline__ void epilogue_loop(int col0, int quarter, int lane, uint32_t tmem_base, uint32_t tfull0,
+                                              uint32_t tempty0, long long n_tiles, int n_blocks, int k_slabs,
+                                              int chunk_slabs, long long M, int N, const Epilogue& ep) {
+  constexpr int BLOCK_N = C::kBlockN;
+  int acc = 0;
+  uint32_t acc_phase = 0;
+  const int n_chunks = (k_slabs + chunk_slabs - 1) / chunk_slabs;
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const long long m_idx = (tile / n_blocks) * BLOCK_M;
+    const int n_idx = (int)(tile % n_blocks) * BLOCK_N;
+    const long long row = m_idx + quarter * 32 + lane;
+    if (COLS == 0) {  // nothing to own (BLOCK_N == 16): still take part in the barrier protocol
+      for (int c = 0; c < n_chunks; ++c) {
+        mbar_wait(tfull0 + 8u * acc, acc_phase);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty0 + 8u * acc);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+      continue;
+    }
+    float master[COLS > 0 ? COLS : 1];
+    for (int c = 0; c < n_chunks; ++c) {
+      mbar_wait(tfull0 + 8u * acc, acc_phase);
+      tcgen05_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * C::ACC_STRIDE + col0;
+#pragma unroll
+      for (int j = 0; j < COLS; j += 16) {
+        float v[16];
+        tmem_ld16(taddr + j, v);
+        tmem_ld_wait();
+        if (c == 0) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) master[j + i] = v[i];
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) master[j + i] += v[i];
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty0 + 8u * acc);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if (row < M) {
+#pragma unroll
+      for (int j = 0; j < COLS; j += 16) {
+        if (n_idx + col0 + j < N)
+          epi_row_chunk<16>(ep, *reinterpret_cast<float(*)[16]>(&master[j]), row, n_idx + col0 + j, N);
+      }
+    }
+  }
+}
+
 template <int BLOCK_N, int NTERMS, bool BF16>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_a_lo,
                const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_w_lo,
-               long long M, int N, int K, Epilogue ep) {
+               long long M, int N, int K, int chunk_slabs, Epilogue ep) {
   using C = Config<BLOCK_N, NTERMS, BF16>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -183,6 +253,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   const long long m_blocks = (M + BLOCK_M - 1) / BLOCK_M;
   const long long n_tiles = m_blocks * n_blocks;
   const int k_slabs = (K + C::ELEMS_PER_SLAB - 1) / C::ELEMS_PER_SLAB;
+  if (chunk_slabs <= 0 || chunk_slabs > k_slabs) chunk_slabs = k_slabs;  // slabs per TMEM accumulation chain
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tm_a);
@@ -204,6 +275,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
+  if (warp < FIRST_EPI_WARP) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_NON_EPI));
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
@@ -235,69 +308,49 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     int acc = 0;
     uint32_t acc_phase = 0;
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      mbar_wait(tempty_bar(acc), acc_phase ^ 1);  // epilogue has drained this accumulator
-      tcgen05_fence_after();
-      const uint32_t tmem_d = tmem_base + acc * C::ACC_STRIDE;
-      for (int ks = 0; ks < k_slabs; ++ks) {
-        mbar_wait(full_bar(stage), phase);
+      for (int ks0 = 0; ks0 < k_slabs; ks0 += chunk_slabs) {
+        const int ks1 = ks0 + chunk_slabs < k_slabs ? ks0 + chunk_slabs : k_slabs;
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1);  // epilogue has drained this accumulator
         tcgen05_fence_after();
-        if (lane == 0) {
-          const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
-          const uint32_t sb = sa + C::NPLANES * C::A_TILE;
-          const uint64_t da_hi = make_smem_desc(sa), db_hi = make_smem_desc(sb);
+        const uint32_t tmem_d = tmem_base + acc * C::ACC_STRIDE;
+        for (int ks = ks0; ks < ks1; ++ks) {
+          mbar_wait(full_bar(stage), phase);
+          tcgen05_fence_after();
+          if (lane == 0) {
+            const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
+            const uint32_t sb = sa + C::NPLANES * C::A_TILE;
+            const uint64_t da_hi = make_smem_desc(sa), db_hi = make_smem_desc(sb);
+            if (NTERMS == 3) {  // small terms first: they meet the accumulator while it is smallest
+              const uint64_t da_lo = make_smem_desc(sa + C::A_TILE), db_lo = make_smem_desc(sb + C::B_TILE_PAD);
 #pragma unroll
-          for (int k = 0; k < SLAB_BYTES / UMMA_K_BYTES; ++k) {
-            const uint64_t koff = (uint64_t)((k * UMMA_K_BYTES) >> 4);
-            umma<BF16>(da_hi + koff, db_hi + koff, tmem_d, C::IDESC, (ks > 0 || k > 0) ? 1u : 0u);
-          }
-          if (NTERMS == 3) {
-            const uint64_t da_lo = make_smem_desc(sa + C::A_TILE), db_lo = make_smem_desc(sb + C::B_TILE_PAD);
+              for (int k = 0; k < SLAB_BYTES / UMMA_K_BYTES; ++k) {
+                const uint64_t koff = (uint64_t)((k * UMMA_K_BYTES) >> 4);
+                umma<BF16>(da_lo + koff, db_hi + koff, tmem_d, C::IDESC, (ks > ks0 || k > 0) ? 1u : 0u);
+                umma<BF16>(da_hi + koff, db_lo + koff, tmem_d, C::IDESC, 1u);
+              }
+            }
 #pragma unroll
             for (int k = 0; k < SLAB_BYTES / UMMA_K_BYTES; ++k) {
               const uint64_t koff = (uint64_t)((k * UMMA_K_BYTES) >> 4);
-              umma<BF16>(da_lo + koff, db_hi + koff, tmem_d, C::IDESC, 1u);
-              umma<BF16>(da_hi + koff, db_lo + koff, tmem_d, C::IDESC, 1u);
+              umma<BF16>(da_hi + koff, db_hi + koff, tmem_d, C::IDESC, (NTERMS == 3 || ks > ks0 || k > 0) ? 1u : 0u);
             }
+            umma_commit(empty_bar(stage));                  // smem slot free once these MMAs retire
+            if (ks == ks1 - 1) umma_commit(tfull_bar(acc));  // this accumulation chain is complete
           }
-          umma_commit(empty_bar(stage));                       // smem slot free once these MMAs retire
-          if (ks == k_slabs - 1) umma_commit(tfull_bar(acc));  // accumulator complete
+          __syncwarp();
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
-        __syncwarp();
-        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+  }
   } else {
-    // ===================== epilogue warps (TMEM lane quarter = warp % 4) =====================
-    const int quarter = warp & 3;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      const long long m_idx = (tile / n_blocks) * BLOCK_M;
-      const int n_idx = (int)(tile % n_blocks) * BLOCK_N;
-      mbar_wait(tfull_bar(acc), acc_phase);
-      tcgen05_fence_after();
-      const long long row = m_idx + quarter * 32 + lane;
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * C::ACC_STRIDE;
-#pragma unroll 1
-      for (int c = 0; c + 32 <= BLOCK_N; c += 32) {
-        float v[32];
-        tmem_ld32(taddr + c, v);
-        tmem_ld_wait();
-        if (row < M && n_idx + c < N) epi_row_chunk<32>(ep, v, row, n_idx + c, N);
-      }
-      if (BLOCK_N % 32 != 0) {
-        constexpr int c = BLOCK_N / 32 * 32;
-        float v[16];
-        tmem_ld16(taddr + c, v);
-        tmem_ld_wait();
-        if (row < M && n_idx + c < N) epi_row_chunk<16>(ep, v, row, n_idx + c, N);
-      }
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-    }
+    // ===================== epilogue warps (TMEM lane quarter = warp % 4; column half = (warp-4)/4) ======
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_EPI));
+    if (warp < FIRST_EPI_WARP + 4) epilogue_loop<C, C::HALF0>(0, warp & 3, lane, tmem_base, tfull_bar(0), tempty_bar(0), n_tiles, n_blocks,
+                                             k_slabs, chunk_slabs, M, N, ep);
+    else          epilogue_loop<C, C::HALF1>(C::HALF0, warp & 3, lane, tmem_base, tfull_bar(0), tempty_bar(0), n_tiles,
+                                             n_blocks, k_slabs, chunk_slabs, M, N, ep);
   }
 
   tcgen05_fence_before();
@@ -311,6 +364,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
 }  // namespace tc
 
 // host side ---------------------------------------------------------------------------------------
+extern int g_chunk_slabs;  // K-slabs per TMEM accumulation chain in the 3xTF32 mode (usf_set_accum_chunk)
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -360,7 +414,8 @@ int launch_gemm_tc_cfg(const usf_linear_args* a, const Epilogue& ep, cudaStream_
   }
   const long long tiles = ((a->M + tc::BLOCK_M - 1) / tc::BLOCK_M) * ((a->N + BLOCK_N - 1) / BLOCK_N);
   const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
-  kern<<<grid, tc::NUM_THREADS, C::SMEM_BYTES, st>>>(ma, mal, mw, mwl, a->M, a->N, a->K, ep);
+  kern<<<grid, tc::NUM_THREADS, C::SMEM_BYTES, st>>>(ma, mal, mw, mwl, a->M, a->N, a->K,
+                                                       NTERMS == 3 ? g_chunk_slabs : 0, ep);
   USF_CUDA_OK(cudaGetLastError());
   return USF_OK;
 }
@@ -368,7 +423,7 @@ int launch_gemm_tc_cfg(const usf_linear_args* a, const Epilogue& ep, cudaStream_
 // BLOCK_N choice: the widest tile that wastes the least of N (wide tiles halve the shared-memory
 // operand traffic per MMA cycle: 64 + 8192/N bytes per cycle for tf32)
 inline int pick_block_n(int N) {
-  static const int cands[] = {256, 224, 208, 192, 160, 128, 96, 64, 32};
+  static const int cands[] = {256, 208, 128, 64, 32};
   int best = 256;
   double best_cost = 1e30;
   for (int bn : cands) {
@@ -385,17 +440,18 @@ template <int NTERMS, bool BF16>
 int launch_gemm_tc_terms(const usf_linear_args* a, const Epilogue& ep, cudaStream_t st, int bn) {
   switch (bn) {
     case 256: return launch_gemm_tc_cfg<256, NTERMS, BF16>(a, ep, st);
-    case 224: return launch_gemm_tc_cfg<224, NTERMS, BF16>(a, ep, st);
     case 208: return launch_gemm_tc_cfg<208, NTERMS, BF16>(a, ep, st);
-    case 192: return launch_gemm_tc_cfg<192, NTERMS, BF16>(a, ep, st);
-    case 160: return launch_gemm_tc_cfg<160, NTERMS, BF16>(a, ep, st);
     case 128: return launch_gemm_tc_cfg<128, NTERMS, BF16>(a, ep, st);
-    case 96: return launch_gemm_tc_cfg<96, NTERMS, BF16>(a, ep, st);
     case 64: return launch_gemm_tc_cfg<64, NTERMS, BF16>(a, ep, st);
     case 32: return launch_gemm_tc_cfg<32, NTERMS, BF16>(a, ep, st);
   }
-  return fail(USF_ERR_INVALID, "unsupported BLOCK_N%s%s");
+  return fail(USF_ERR_INVALID, "unsupported BLOCK_N (built: 256, 208, 128, 64, 32)%s%s");
 }
+
+// one translation unit per engine (gemm_tc_inst_*.cu) so the variants compile in parallel
+int launch_gemm_tc_3xtf32(const usf_linear_args* a, const Epilogue& ep, cudaStream_t st, int bn);
+int launch_gemm_tc_tf32(const usf_linear_args* a, const Epilogue& ep, cudaStream_t st, int bn);
+int launch_gemm_tc_bf16(const usf_linear_args* a, const Epilogue& ep, cudaStream_t st, int bn);
 
 extern int g_force_block_n;  // test hook (usf_debug_set_block_n)
 
@@ -411,10 +467,10 @@ inline int launch_gemm_tc(const usf_linear_args* a, const Epilogue& ep, cudaStre
   const int bn = g_force_block_n > 0 ? g_force_block_n : pick_block_n(a->N);
   if (a->engine == USF_ENGINE_TC_3XTF32) {
     USF_REQUIRE(a->a_lo && a->w_lo && aligned16(a->a_lo) && aligned16(a->w_lo), "3xTF32 needs a_lo and w_lo planes");
-    return launch_gemm_tc_terms<3, false>(a, ep, st, bn);
+    return launch_gemm_tc_3xtf32(a, ep, st, bn);
   }
-  if (a->engine == USF_ENGINE_TC_TF32) return launch_gemm_tc_terms<1, false>(a, ep, st, bn);
-  return launch_gemm_tc_terms<1, true>(a, ep, st, bn);
+  if (a->engine == USF_ENGINE_TC_TF32) return launch_gemm_tc_tf32(a, ep, st, bn);
+  return launch_gemm_tc_bf16(a, ep, st, bn);
 }
 
 }  // namespace usf
