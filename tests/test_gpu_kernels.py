@@ -1,0 +1,155 @@
+"""Unit tests of individual C-ABI kernels against fp64 torch-CPU arithmetic (run with -m gpu on the B200)."""
+import pytest
+import torch
+
+from helpers import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _planes(t, kind):
+    from usflows_b200 import ops
+    from usflows_b200.ops import Act
+    M, K = t.shape
+    ld = ops.pad4(K)
+    dev = "cuda"
+    if kind == "bf16":
+        b = torch.zeros(M, ld, dtype=torch.bfloat16, device=dev)[:, :K]
+        b.copy_(t)
+        return Act(M, K, bf16=b), b.float().cpu()
+    f = torch.zeros(M, ld, device=dev)[:, :K]
+    f.copy_(t)
+    if kind == "split":
+        hi, lo = torch.zeros(2, M, ld, device=dev)[:, :, :K]
+        ops.split_tf32(f, hi, lo)
+        return Act(M, K, hi=hi, lo=lo), (hi.double() + lo.double()).cpu()
+    return Act(M, K, f32=f), t
+
+
+ENGINES = [("simt", 0, "f32", 3e-6), ("3xtf32", 1, "split", 3e-6), ("tf32", 2, "f32", 2e-3), ("bf16", 3, "bf16", 3e-6)]
+
+
+@pytest.mark.parametrize("eng_name,eng,fmt,tol", ENGINES)
+@pytest.mark.parametrize("M,N,K", [(1, 40, 40), (128, 128, 32), (300, 784, 1024), (1000, 1024, 784), (257, 3072, 520),
+                                   (513, 100, 50), (64, 33, 47)])
+def test_linear_all_engines_full_epilogue(eng_name, eng, fmt, tol, M, N, K):
+    from usflows_b200 import ops
+    from usflows_b200.ops import Act
+    if eng != 0 and min(N, K) < 32:
+        pytest.skip("tcgen05 engines are used for N, K >= 32")
+    g = torch.Generator().manual_seed(M * 7 + N)
+    a = torch.randn(M, K, generator=g)
+    w = torch.randn(N, K, generator=g) / K ** 0.5
+    bias, colscale, postsub = (torch.randn(N, generator=g) for _ in range(3))
+    resid = torch.randn(M, N, generator=g)
+    act, a_used = _planes(a, fmt)
+    wact, w_used = _planes(w, fmt)
+    racc, r_used = _planes(resid, "split" if fmt == "split" else "f32")
+    w_hi = wact.bf16 if fmt == "bf16" else (wact.hi if fmt == "split" else wact.f32)
+    out = Act(M, N, f32=torch.zeros(M, ops.pad4(N), device="cuda")[:, :N],
+              hi=torch.zeros(M, ops.pad4(N), device="cuda")[:, :N], lo=torch.zeros(M, ops.pad4(N), device="cuda")[:, :N],
+              bf16=torch.zeros(M, ops.pad4(N), device="cuda", dtype=torch.bfloat16)[:, :N])
+    ops.linear(eng, act, w_hi, wact.lo, N, K, bias=bias.cuda(), relu=True, resid=racc, resid_sign=-1.0,
+               colscale=colscale.cuda(), postsub=postsub.cuda(), out=out)
+    ref = torch.relu(a_used.double() @ w_used.double().T + bias.double())
+    ref = (r_used.double() - ref) * colscale.double() - postsub.double()
+    assert rel_err(out.f32, ref) <= tol
+    assert rel_err(out.hi.double() + out.lo.double(), out.f32) <= 1e-6          # split planes reconstruct the value
+    assert rel_err(out.bf16.float(), out.f32) <= 1e-2
+
+
+@pytest.mark.parametrize("bn", [32, 64, 128, 208, 256])
+@pytest.mark.parametrize("chunk", [0, 1, 3])
+def test_tile_widths_and_accumulation_chunks(bn, chunk):
+    from usflows_b200 import _lib, ops
+    from usflows_b200.ops import Act
+    M, N, K = 400, 600, 500
+    g = torch.Generator().manual_seed(bn + chunk)
+    a, w = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) / K ** 0.5
+    act, a_used = _planes(a, "split")
+    wact, w_used = _planes(w, "split")
+    out = Act(M, N, f32=torch.zeros(M, ops.pad4(N), device="cuda")[:, :N])
+    lib = _lib.load()
+    lib.usf_debug_set_block_n(bn)
+    lib.usf_set_accum_chunk(chunk)
+    try:
+        ops.linear(1, act, wact.hi, wact.lo, N, K, out=out)
+        torch.cuda.synchronize()
+    finally:
+        lib.usf_debug_set_block_n(0)
+        lib.usf_set_accum_chunk(2)
+    assert rel_err(out.f32, a_used.double() @ w_used.double().T) <= (3e-6 if chunk else 2e-5)
+
+
+def test_simt_transposed_weight_and_unaligned():
+    from usflows_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    a, b = torch.randn(37, 53, generator=g), torch.randn(53, 29, generator=g)
+    out = torch.empty(37, 29, device="cuda")
+    ops.matmul_f32(a.cuda(), b.cuda(), out)
+    assert rel_err(out, a.double() @ b.double()) <= 2e-6
+
+
+def test_ingest_and_base_logprob():
+    from usflows_b200 import ops
+    from usflows_b200.ops import Act
+    g = torch.Generator().manual_seed(1)
+    for rows, d in [(7, 5), (300, 784), (129, 3072)]:
+        x = torch.rand(rows, d, generator=g)
+        div, sub = torch.rand(d, generator=g) + 0.5, torch.randn(d, generator=g)
+        out = Act(rows, d, f32=torch.empty(rows, d, device="cuda"),
+                  hi=torch.zeros(rows, ops.pad4(d), device="cuda")[:, :d], lo=torch.zeros(rows, ops.pad4(d), device="cuda")[:, :d])
+        ops.ingest(x.cuda(), out, div=div.cuda(), sub=sub.cuda())
+        ref = x / div - sub
+        assert torch.equal(out.f32.cpu(), ref)                                   # same fp32 ops, bit exact
+        assert rel_err(out.hi.double() + out.lo.double(), ref) <= 3e-7
+        loc, scale = torch.randn(d, generator=g), torch.rand(d, generator=g) + 0.5
+        res = torch.empty(rows, device="cuda")
+        for kind, dist in ((ops.BASE_LAPLACE, torch.distributions.Laplace), (ops.BASE_NORMAL, torch.distributions.Normal)):
+            ops.base_logprob(Act(rows, d, f32=out.f32), loc.cuda(), scale.cuda(), kind, 1.25, res)
+            want = dist(loc.double(), scale.double()).log_prob(ref.double()).sum(-1) + 1.25
+            assert rel_err(res, want) <= 2e-6
+
+
+@pytest.mark.parametrize("d", [1, 5, 64, 100, 784, 1500])
+def test_triangular_inverse_and_lu_prep(d):
+    from usflows_b200 import ops
+    g = torch.Generator().manual_seed(d)
+    L_raw = torch.randn(d, d, generator=g) * (0.6 / d ** 0.5)
+    U_raw = torch.randn(d, d, generator=g) * (0.6 / d ** 0.5)
+    U_raw = U_raw.triu(1) + torch.diag(torch.sign(torch.randn(d, generator=g)) * torch.exp(torch.randn(d, generator=g) * 0.1))
+    L, U = torch.empty(d, d, device="cuda"), torch.empty(d, d, device="cuda")
+    ops.lu_assemble(L_raw.cuda(), U_raw.cuda(), L, U)
+    assert torch.equal(L.cpu(), L_raw.tril(-1) + torch.eye(d)) and torch.equal(U.cpu(), U_raw.triu())
+    X = torch.empty(d, d, device="cuda")
+    ops.tri_inverse(L, True, True, X)
+    assert rel_err(X, torch.inverse(L.double().cpu())) <= 2e-6
+    ops.tri_inverse(U, False, False, X)
+    assert rel_err(X, torch.inverse(U.double().cpu())) <= 2e-6
+    out2 = torch.empty(2, device="cuda")
+    ops.lu_logabsdet(U_raw.cuda(), out2)
+    assert abs(float(out2[0]) - float(U_raw.diag().abs().log().double().sum())) <= 1e-5 * max(1.0, d ** 0.5)
+    assert float(out2[1]) == 0
+
+
+def test_householder_and_transpose():
+    from usflows_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    d = 130
+    W = torch.randn(d, d, generator=g)
+    v = torch.randn(d, generator=g)
+    Wd = W.cuda().clone()
+    ops.householder_right(Wd, v.cuda(), torch.empty(d, device="cuda"))
+    ref = W.double() @ (torch.eye(d, dtype=torch.float64) - 2 * torch.outer(v.double(), v.double()) / v.double().dot(v.double()))
+    assert rel_err(Wd, ref) <= 2e-6
+    Wt = torch.empty(d, d, device="cuda")
+    ops.transpose(Wd, Wt)
+    assert torch.equal(Wt.cpu(), Wd.cpu().T)
+
+
+def test_errors_are_loud():
+    from usflows_b200 import ops
+    from usflows_b200.ops import Act
+    with pytest.raises(RuntimeError, match="usflows_b200"):
+        a = Act(4, 40, f32=torch.zeros(4, 41, device="cuda")[:, 1:])      # misaligned operand for a tcgen05 engine
+        ops.linear(2, a, torch.zeros(40, 40, device="cuda"), None, 40, 40, out=Act(4, 40, f32=torch.zeros(4, 40, device="cuda")))

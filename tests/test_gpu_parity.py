@@ -1,0 +1,192 @@
+"""Parity of the CUDA path (through the C ABI) against the reference outputs held in tests/golden/ and
+against the CPU oracle on seeded inputs.  Run on the B200 box:  python -m pytest tests -m gpu -x -q
+
+Tolerances (norm-wise: max|a-b| / max(max|b|, 1), see helpers.rel_err):
+  fp32 mode (tcgen05 3xTF32 + fp32 promotion)  log_prob <= 1e-5 ; latents / samples <= 3e-5
+       -- the reference's own fp32 result sits 1e-6 (log_prob) / 1e-5 (latents) from the fp64 evaluation of
+          the same weights (tests/golden/report.json), so tighter agreement between two fp32 paths is noise
+  fp32_simt mode (FFMA)                         same bounds
+  tf32 mode                                     log_prob <= 2e-2, latents <= 3e-2   (own bound)
+  bf16 mode                                     log_prob <= 5e-2, latents <= 2e-1   (own bound)
+"""
+import math
+
+import pytest
+import torch
+
+from helpers import LARGE_CASES, SMALL_CASES, build_flow, load_case, rel_err
+from oracle import flow_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TOL = {  # mode: (log_prob, latent/sample)
+    "fp32": (1e-5, 3e-5),
+    "fp32_simt": (1e-5, 3e-5),
+    "tf32": (2e-2, 3e-2),
+    "bf16": (5e-2, 2e-1),
+}
+
+
+@pytest.mark.parametrize("mode", list(TOL))
+@pytest.mark.parametrize("name", SMALL_CASES + LARGE_CASES)
+def test_flow_matches_reference_golden(name, mode):
+    spec, params, arr = load_case(name)
+    flow = build_flow(spec, params, precision=mode)
+    x, z0 = arr["x"].cuda(), arr["z0"].cuda()
+    lp, z, y = flow.log_prob(x), flow.backward(x), flow._forward(z0)
+    t_lp, t_z = TOL[mode]
+    assert rel_err(lp, arr["lp32"]) <= t_lp
+    assert rel_err(z, arr["z32"]) <= t_z
+    assert rel_err(y, arr["y32"]) <= t_z
+    assert flow.is_feasible()
+
+
+@pytest.mark.parametrize("name", SMALL_CASES + LARGE_CASES)
+def test_fp32_mode_is_as_close_to_fp64_truth_as_the_reference(name):
+    """The candidate may not be further from the fp64 evaluation than 3x the reference's own fp32 error
+    (+ 2e-6 slack for log_prob, 1e-5 for latents)."""
+    spec, params, arr = load_case(name)
+    flow = build_flow(spec, params, precision="fp32")
+    lp, z = flow.log_prob(arr["x"].cuda()), flow.backward(arr["x"].cuda())
+    assert rel_err(lp, arr["lp64"]) <= 3 * rel_err(arr["lp32"], arr["lp64"]) + 2e-6
+    assert rel_err(z, arr["z64"]) <= 3 * rel_err(arr["z32"], arr["z64"]) + 1e-5
+
+
+def test_total_log_det_matches_reference_layers():
+    spec, params, arr = load_case("d100_h50_hh")
+    flow = build_flow(spec, params)
+    per_layer = torch.stack([torch.as_tensor(l.log_abs_det_jacobian(None, None), dtype=torch.float32).reshape(()).cpu()
+                             for l in flow.layers])
+    assert rel_err(per_layer, arr["ladj32"]) <= 2e-6
+
+
+@pytest.mark.parametrize("mode", ["fp32", "fp32_simt"])
+def test_against_oracle_on_fresh_seeded_inputs(mode):
+    spec = dict(in_dims=[200], coupling_blocks=3, hidden_dims=[256, 192], affine_conjugation=True, lu_transform=2,
+                householder=2, base="normal")
+    params = O.random_params(spec, 123)
+    g = torch.Generator().manual_seed(5)
+    x = torch.rand(1000, 200, generator=g)
+    flow = build_flow(spec, params, precision=mode)
+    assert rel_err(flow.log_prob(x.cuda()), O.flow_log_prob(x, spec, params)) <= 1e-5
+    assert rel_err(flow.backward(x.cuda()), O.flow_backward(x, spec, params)) <= 3e-5
+    z = torch.randn(1000, 200, generator=g)
+    assert rel_err(flow._forward(z.cuda()), O.flow_forward(z, spec, params)) <= 3e-5
+
+
+@pytest.mark.parametrize("rows", [0, 1, 127, 129, 1000])
+def test_ragged_and_empty_batches(rows):
+    spec, params, arr = load_case("d32_h64")
+    flow = build_flow(spec, params)
+    g = torch.Generator().manual_seed(rows)
+    x = torch.rand(rows, 32, generator=g)
+    lp = flow.log_prob(x.cuda())
+    z = flow.backward(x.cuda())
+    assert lp.shape == (rows,) and z.shape == (rows, 32)
+    if rows:
+        assert rel_err(lp, O.flow_log_prob(x, spec, params)) <= 1e-5
+
+
+def test_chunking_and_host_path_do_not_change_results():
+    import usflows_b200 as U
+    spec, params, arr = load_case("d100_h50_hh")
+    flow = build_flow(spec, params)
+    g = torch.Generator().manual_seed(9)
+    x = torch.rand(5000, 100, generator=g)
+    lp_ref = flow.log_prob(x.cuda())
+    U.set_chunk_rows(1024)
+    try:
+        lp_chunked = flow.log_prob(x.cuda())
+        lp_host = flow.log_prob_host(x.pin_memory())
+    finally:
+        U.set_chunk_rows(16384)
+    assert torch.equal(lp_ref, lp_chunked)            # rows are independent: bit-identical under re-chunking
+    assert torch.equal(lp_ref.cpu(), lp_host)
+
+
+@pytest.mark.parametrize("name", ["c2", "c5"])
+def test_full_size_properties(name):
+    """BASELINE sizes: round trip x -> z -> x, log_prob == base(z) - ladj, determinism."""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from bench import WORKLOADS
+    wl = WORKLOADS[name]
+    spec = wl["spec"]
+    rows = wl["rows"] // 2
+    d = spec["in_dims"][0]
+    params = O.random_params(spec, 0)
+    flow = build_flow(spec, params, precision="fp32")
+    x = torch.rand(rows, d, device="cuda", generator=torch.Generator(device="cuda").manual_seed(1))
+    z = flow.backward(x)
+    x_rt = flow._forward(z)
+    assert rel_err(x_rt, x) <= 2e-3        # conditioning of the stack (cond(W) ~ 1e2 per affine layer) bounds this
+    lp = flow.log_prob(x)
+    assert torch.equal(lp, flow.log_prob(x))
+    ladj, bad = __import__("usflows_b200").engine.total_ladj(flow.layers)
+    assert bad == 0
+    lp2 = flow.base_distribution.log_prob(z) - ladj
+    assert rel_err(lp, lp2) <= 1e-6
+    # a bounded sample against the oracle
+    idx = torch.arange(0, rows, rows // 64)[:64]
+    assert rel_err(lp[idx], O.flow_log_prob(x[idx].cpu(), spec, params)) <= 1e-5
+
+
+def test_sample_statistics_and_shapes():
+    spec, params, _ = load_case("d32_h64")
+    flow = build_flow(spec, params)
+    s = flow.sample([4, 1000])
+    assert s.shape == (4, 1000, 32) and torch.isfinite(s).all()
+    # the base draws themselves: Laplace(0,1) has mean 0, variance 2
+    z = flow.base_distribution.sample([200000])
+    assert abs(float(z.mean())) < 0.02 and abs(float(z.var()) - 2.0) < 0.05
+    spec_n, params_n, _ = load_case("d6_hh_normal")
+    fn = build_flow(spec_n, params_n)
+    zn = fn.base_distribution.sample([200000])
+    assert abs(float(zn.mean())) < 0.02 and abs(float(zn.var()) - 1.0) < 0.03
+    # pushing base draws through _forward and back recovers them
+    z = flow.base_distribution.sample([512])
+    assert rel_err(flow.backward(flow._forward(z)), z) <= 1e-4
+
+
+def test_individual_layer_known_answers_on_gpu():
+    """reference tests/veriflow/transforms_test.py:5-67 through the CUDA kernels."""
+    import usflows_b200 as U
+    dim = 10
+    t = U.ScaleTransform([dim]).to("cuda")
+    with torch.no_grad():
+        t.scale.copy_(torch.ones(dim) * 2)
+    x = torch.ones(1, dim, device="cuda")
+    y = t(x)
+    assert (y == 2 * x).all() and (t.backward(y) == x).all()
+    assert abs(float(t.log_abs_det_jacobian(x, y)) - dim * math.log(2.0)) < 1e-5
+
+    t = U.LUTransform(dim).to("cuda")
+    with torch.no_grad():
+        t.L_raw.copy_(torch.tril(torch.ones(dim, dim)))
+        t.U_raw.copy_(torch.eye(dim))
+        t.bias_vector.copy_(torch.zeros(dim))
+    y = t(x)
+    assert (y.cpu() == (torch.arange(dim) + 1.0)).all() and (t.backward(y) == x).all()
+    assert float(t.log_abs_det_jacobian(x, y)) == 0
+
+    t = U.LeakyReLUTransform()
+    x = torch.tensor([[1.0, -1.0] * 5], device="cuda")
+    y = t(x)
+    assert (y.cpu() == x.cpu() * torch.tensor([1.0, 0.01] * 5)).all()
+    assert torch.allclose(t.backward(y), x)
+    assert abs(float(t.log_abs_det_jacobian(x, y)) - 5 * math.log(0.01)) < 1e-5
+
+    t = U.Permute(torch.tensor([2, 0, 1, 3], device="cuda"))
+    x = torch.arange(8, dtype=torch.float32, device="cuda").reshape(2, 4)
+    y = t(x)
+    assert (y.cpu() == torch.tensor([[2., 0., 1., 3.], [6., 4., 5., 7.]])).all()
+    assert (t.backward(y) == x).all()
+
+
+def test_infeasible_layer_is_reported():
+    spec, params, _ = load_case("d5_noconj")
+    flow = build_flow(spec, params)
+    assert flow.is_feasible()
+    with torch.no_grad():
+        flow.layers[-1].scale[0] = 0.0
+    assert not flow.is_feasible()

@@ -73,6 +73,12 @@ def gemm_case(engine, M, N, K, bn=0, seed=0, epi=False):
 quick = "--quick" in sys.argv
 print(torch.cuda.get_device_name(0), torch.version.cuda, flush=True)
 
+if "--tc-smoke" in sys.argv:      # run under a short `timeout`: catches protocol deadlocks cheaply
+    for eng in (ops.ENGINE_TC_3XTF32, ops.ENGINE_TC_TF32, ops.ENGINE_TC_BF16):
+        for bn in (32, 128, 208, 256):
+            print("tc-smoke", eng, bn, gemm_case(eng, 300, 520, 256, bn=bn, epi=True), flush=True)
+    sys.exit(0)
+
 
 @section("simt_gemm")
 def _():

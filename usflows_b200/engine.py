@@ -442,3 +442,39 @@ def leaky_relu_ladj(x: torch.Tensor, alpha: float) -> torch.Tensor:
     ops.leaky_relu(x2, alpha, y, cnt)
     out = cnt * math.log(alpha)
     return out.reshape(batch_shape) if x.dim() > 1 else out.reshape(())
+
+
+def profile_step(fn) -> dict:
+    """Run `fn` once with CUDA events around every hot-path kernel launch; returns milliseconds summed per
+    kernel class ("linear NxK", "ingest", "base_logprob") plus "_names" (launch order) and "_total"."""
+    records = []
+    originals = {name: getattr(ops, name) for name in ("linear", "ingest", "base_logprob")}
+
+    def wrap(name, f):
+        def inner(*a, **k):
+            if name == "linear":
+                label = f"linear {a[4]}x{a[5]}"
+            else:
+                label = name
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            f(*a, **k)
+            e1.record()
+            records.append((label, e0, e1))
+        return inner
+
+    try:
+        for name, f in originals.items():
+            setattr(ops, name, wrap(name, f))
+        torch.cuda.synchronize()
+        fn()
+        torch.cuda.synchronize()
+    finally:
+        for name, f in originals.items():
+            setattr(ops, name, f)
+    out = {}
+    for label, e0, e1 in records:
+        out[label] = out.get(label, 0.0) + e0.elapsed_time(e1)
+    out["_total"] = sum(v for k, v in out.items() if not k.startswith("_"))
+    out["_names"] = [r[0] for r in records]
+    return out

@@ -84,6 +84,56 @@ class Flow(torch.nn.Module):
             prog.run(x2, self.precision, sink=sink)
         return out.reshape(batch_shape)
 
+    def log_prob_host(self, x_host: torch.Tensor, out_host: Optional[torch.Tensor] = None,
+                      chunk_rows: Optional[int] = None) -> torch.Tensor:
+        """`log_prob` for rows living in HOST memory (pinned for full copy speed): the batch is streamed
+        through the device in chunks -- H2D copy of chunk i+1 on a side stream overlaps the kernels of
+        chunk i -- and the log-probs are copied back into `out_host`.  Returns `out_host`."""
+        if x_host.is_cuda:
+            raise RuntimeError("log_prob_host expects a host tensor; use log_prob for device tensors")
+        dev = next(self.parameters()).device
+        prog, ladj = self._program("backward")
+        base = self._base_module()
+        loc, scale = base._prepared()
+        x2 = x_host.reshape(-1, math.prod(self._event_shape()))
+        rows, d = x2.shape
+        if out_host is None:
+            out_host = torch.empty(rows, dtype=torch.float32, pin_memory=True)
+        chunk = min(chunk_rows or engine._default_chunk_rows, max(rows, 1))
+        if getattr(self, "_host_bufs", None) is None or self._host_bufs[0].shape != (chunk, d) \
+                or self._host_bufs[0].device != dev:
+            self._host_bufs = [torch.empty(chunk, d, dtype=torch.float32, device=dev) for _ in range(2)]
+            self._host_out = torch.empty(0, dtype=torch.float32, device=dev)
+            self._copy_stream = torch.cuda.Stream(device=dev)
+        if self._host_out.numel() < rows:
+            self._host_out = torch.empty(rows, dtype=torch.float32, device=dev)
+        out_dev = self._host_out[:rows]
+        main = torch.cuda.current_stream(dev)
+        copied = [torch.cuda.Event(), torch.cuda.Event()]
+        consumed = [torch.cuda.Event(), torch.cuda.Event()]
+        starts = list(range(0, rows, chunk))
+        with torch.no_grad():
+            self._copy_stream.wait_stream(main)
+            for i, r0 in enumerate(starts):
+                r1 = min(rows, r0 + chunk)
+                buf = self._host_bufs[i & 1][: r1 - r0]
+                with torch.cuda.stream(self._copy_stream):
+                    if i >= 2:
+                        self._copy_stream.wait_event(consumed[i & 1])
+                    buf.copy_(x2[r0:r1], non_blocking=True)
+                    copied[i & 1].record(self._copy_stream)
+                main.wait_event(copied[i & 1])
+
+                def sink(z_chunk, a, b, r0=r0):
+                    ops.base_logprob(ops.Act(b - a, d, f32=z_chunk), loc, scale, base.base_kind, -ladj,
+                                     out_dev[r0 + a:r0 + b])
+
+                prog.run(buf, self.precision, chunk_rows=chunk, sink=sink)
+                consumed[i & 1].record(main)
+            out_host.reshape(-1)[:rows].copy_(out_dev, non_blocking=True)
+            main.synchronize()
+        return out_host
+
     def sample(self, sample_shape: Iterable[int] = None, context: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Draw from the base and push through the layers (flows.py:247-265)."""
         if context is not None:

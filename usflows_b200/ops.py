@@ -16,6 +16,9 @@ from ._lib import (BASE_LAPLACE, BASE_NORMAL, ENGINE_SIMT, ENGINE_TC_3XTF32, ENG
                    ENGINE_TC_TF32, LinearArgs, check)
 
 
+LAUNCHES = 0     # kernels launched through this module since the caller last reset it (bench.py `gpu_launches`)
+
+
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
@@ -89,10 +92,14 @@ def linear(engine: int, a: Act, w, w_lo, N: int, K: int, *, bias=None, relu=Fals
         args.out_hi, args.out_lo, args.ld_split = _ptr(out.hi), _ptr(out.lo), _ld(out.hi)
     if out.bf16 is not None:
         args.out_bf16, args.ld_bf16 = _ptr(out.bf16), _ld(out.bf16)
+    global LAUNCHES
+    LAUNCHES += 1
     check(_lib.load().usf_linear(C.byref(args), _stream()))
 
 
 def ingest(x: torch.Tensor, out: Act, *, div=None, mul=None, sub=None) -> None:
+    global LAUNCHES
+    LAUNCHES += 1
     rows, d = x.shape
     check(_lib.load().usf_ingest(
         _ptr(x), _ld(x), rows, d, _ptr(div), _ptr(mul), _ptr(sub),
@@ -102,6 +109,8 @@ def ingest(x: torch.Tensor, out: Act, *, div=None, mul=None, sub=None) -> None:
 
 
 def base_logprob(z: Act, loc, scale, kind: int, add_const: float, out: torch.Tensor) -> None:
+    global LAUNCHES
+    LAUNCHES += 1
     p, pl = z.resid_planes()
     check(_lib.load().usf_base_logprob(_ptr(p), _ptr(pl), _ld(p), z.rows, z.width, _ptr(loc), _ptr(scale), kind,
                                        float(add_const), _ptr(out), _stream()))
