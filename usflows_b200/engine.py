@@ -340,6 +340,8 @@ class Program:
         rows = x.shape[0]
         width = self.out_width(x.shape[1])
         chunk = min(chunk_rows or _default_chunk_rows, max(rows, 1))
+        if rows == 0:                       # empty batch: nothing to launch
+            return None if sink is not None else torch.empty(0, width, dtype=torch.float32, device=x.device)
         if sink is not None:
             for r0 in range(0, rows, chunk):
                 r1 = min(rows, r0 + chunk)
