@@ -97,6 +97,8 @@ int usf_linear(const usf_linear_args* args, void* stream);
 int usf_set_accum_chunk(int k_slabs);
 /* test hook: force the tcgen05 tile width BLOCK_N (0 = automatic) */
 int usf_debug_set_block_n(int block_n);
+/* test hook: 2 = CTA-pair (cta_group::2) tcgen05 kernel (default), 1 = single-CTA tcgen05 kernel */
+int usf_debug_set_impl(int impl);
 
 /* ------------------------------------------------------------------------------------------------
  * elementwise / reduction kernels over [N_rows, d] activations (HBM-bound, 128-bit accesses)

@@ -63,6 +63,7 @@ SIGNATURES = {
     "usf_softplus": (C.c_int, [_P, _I64, _P, _P]),
     "usf_debug_set_block_n": (C.c_int, [C.c_int]),
     "usf_set_accum_chunk": (C.c_int, [C.c_int]),
+    "usf_debug_set_impl": (C.c_int, [C.c_int]),
 }
 
 

@@ -2,7 +2,7 @@
 #include "common.cuh"
 #include "elementwise.cuh"
 #include "gemm_simt.cuh"
-#include "gemm_tc.cuh"
+#include "gemm_tc2.cuh"
 #include "prep.cuh"
 
 namespace usf {
@@ -10,6 +10,7 @@ namespace usf {
 thread_local char g_err[512] = "";
 int g_force_block_n = 0;
 int g_chunk_slabs = 2;
+int g_tc_impl = 2;
 
 int num_sms() {
   static int cached[64] = {0};
@@ -93,6 +94,12 @@ int usf_device_info(int* sm_count, int* cc_major, int* cc_minor, int64_t* l2_byt
 
 int usf_debug_set_block_n(int bn) {  // test hook: force the tcgen05 tile width (0 = automatic)
   g_force_block_n = bn;
+  return USF_OK;
+}
+
+int usf_debug_set_impl(int impl) {  // test hook: 2 = CTA-pair tcgen05 kernel (default), 1 = single-CTA kernel
+  USF_REQUIRE(impl == 1 || impl == 2, "impl must be 1 or 2");
+  g_tc_impl = impl;
   return USF_OK;
 }
 

@@ -453,24 +453,4 @@ int launch_gemm_tc_3xtf32(const usf_linear_args* a, const Epilogue& ep, cudaStre
 int launch_gemm_tc_tf32(const usf_linear_args* a, const Epilogue& ep, cudaStream_t st, int bn);
 int launch_gemm_tc_bf16(const usf_linear_args* a, const Epilogue& ep, cudaStream_t st, int bn);
 
-extern int g_force_block_n;  // test hook (usf_debug_set_block_n)
-
-inline int launch_gemm_tc(const usf_linear_args* a, const Epilogue& ep, cudaStream_t st) {
-  if (a->M == 0 || a->N == 0) return USF_OK;
-  const bool bf16 = a->engine == USF_ENGINE_TC_BF16;
-  const int kmul = bf16 ? 8 : 4;
-  USF_REQUIRE(a->K > 0, "K must be positive");
-  USF_REQUIRE(a->M < (1LL << 31), "tcgen05 engine: M must fit a TMA coordinate");
-  USF_REQUIRE(aligned16(a->a) && aligned16(a->w) && a->lda % kmul == 0 && a->ldw % kmul == 0,
-              "tcgen05 engines need 16-byte aligned operands and 16-byte multiples for lda/ldw");
-  USF_REQUIRE(!a->trans_w, "trans_w is a SIMT-engine option");
-  const int bn = g_force_block_n > 0 ? g_force_block_n : pick_block_n(a->N);
-  if (a->engine == USF_ENGINE_TC_3XTF32) {
-    USF_REQUIRE(a->a_lo && a->w_lo && aligned16(a->a_lo) && aligned16(a->w_lo), "3xTF32 needs a_lo and w_lo planes");
-    return launch_gemm_tc_3xtf32(a, ep, st, bn);
-  }
-  if (a->engine == USF_ENGINE_TC_TF32) return launch_gemm_tc_tf32(a, ep, st, bn);
-  return launch_gemm_tc_bf16(a, ep, st, bn);
-}
-
 }  // namespace usf

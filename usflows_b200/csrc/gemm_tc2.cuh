@@ -1,0 +1,428 @@
+// tcgen05 contraction, CTA-pair version (cta_group::2):  out = epilogue( sum_terms A_t[M,K] . W_t[N,K]^T )
+//
+// Two CTAs of a cluster (one TPC) share every MMA: UMMA M = 256 (128 rows of A per CTA), N = BLOCK_N with
+// each CTA staging only HALF of the W tile, so the shared-memory fill traffic per MMA cycle drops by a third
+// against the single-CTA kernel (gemm_tc.cuh) -- the single-CTA kernel is bound by the L2 -> SM fill rate
+// (~40 B/cycle/SM measured), not by the tensor pipe.
+//
+//   * per CTA and K-slab (128 B of K): A tile 128 rows + W half tile BLOCK_N/2 rows, per operand plane,
+//     K-major, 128B swizzle, filled by TMA (cp.async.bulk.tensor.2d.cta_group::2); both CTAs' loads complete
+//     on the LEADER's full barrier (armed with the byte count of both)
+//   * the leader's MMA thread issues tcgen05.mma.cta_group::2; tcgen05.commit multicasts the "slot free" and
+//     "accumulator ready" arrivals to both CTAs; each CTA's epilogue drains its own 128 TMEM lanes and
+//     releases the accumulator on the leader's barrier (remote mbarrier.arrive)
+//   * fp32 mode (NTERMS = 3): the accumulation chain is closed every `chunk_slabs` K-slabs and promoted into
+//     fp32 registers with round-to-nearest (see gemm_tc.cuh); two TMEM accumulators ping-pong
+//   * epilogue: registers -> per-warp padded smem patch (16 columns at a time) -> coalesced 64 B row segments
+//     with the fused bias / ReLU / residual / column scale / post-subtract / hi-lo or bf16 re-encoding
+#pragma once
+#include "gemm_tc.cuh"
+
+namespace usf {
+namespace tc2 {
+
+using namespace tc;  // mbarrier / TMA / descriptor / TMEM helpers
+
+constexpr int PATCH_COLS = 16;                 // epilogue staging granularity
+constexpr int PATCH_LD = PATCH_COLS + 4;       // padded row pitch (floats): conflict-free v4 writes and reads
+constexpr int PATCH_BYTES = 32 * PATCH_LD * 4; // one warp: 32 rows
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_id_x() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t num_clusters_x() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// address of the same shared-memory offset in CTA `rank` of the cluster (shared::cluster window)
+__device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+template <bool BF16>
+__device__ __forceinline__ void umma_pair(uint64_t da, uint64_t db, uint32_t tmem_d, uint32_t idesc, uint32_t accumulate) {
+  if (BF16) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
+// arrive (once the MMAs issued so far have retired) on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(bar), "h"((uint16_t)3)
+      : "memory");
+}
+
+template <int BLOCK_N, int NTERMS, bool BF16>
+struct Config {
+  static_assert(BLOCK_N % 16 == 0 && BLOCK_N >= 32 && BLOCK_N <= 256, "UMMA N for M=256 (cta_group::2)");
+  static_assert(NTERMS == 1 || NTERMS == 3, "1 = single pass, 3 = tf32 split");
+  static constexpr int kBlockN = BLOCK_N;
+  static constexpr int HALF_N = BLOCK_N / 2;                 // W rows staged by each CTA (multiple of 8)
+  static constexpr int NPLANES = NTERMS == 3 ? 2 : 1;
+  static constexpr int A_TILE = BLOCK_M * SLAB_BYTES;        // 16 KB
+  static constexpr int B_TILE = HALF_N * SLAB_BYTES;         // multiple of 1024
+  static constexpr int STAGE_BYTES = NPLANES * (A_TILE + B_TILE);
+  static constexpr int EPI_BYTES = NUM_EPI_WARPS * PATCH_BYTES;
+  static constexpr int STAGES_RAW = (227 * 1024 - 1024 - 512 - EPI_BYTES) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  static_assert(STAGES >= 2, "need at least a double-buffered pipeline");
+  static constexpr int ACC_STRIDE = BLOCK_N <= 32 ? 32 : BLOCK_N <= 64 ? 64 : BLOCK_N <= 128 ? 128 : 256;
+  static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align slack*/ + 512 /*barriers*/;
+  static constexpr int ELEMS_PER_SLAB = SLAB_BYTES / (BF16 ? 2 : 4);
+  static constexpr int HALF0 = ((BLOCK_N / 16 + 1) / 2) * 16;  // columns owned by epilogue warps 4..7
+  static constexpr int HALF1 = BLOCK_N - HALF0;                // ... and by warps 8..11
+  // instruction descriptor: D=f32, A/B = tf32 (2) or bf16 (1), both K-major, N>>3, M>>4 with M = 256
+  static constexpr uint32_t IDESC = (1u << 4) | ((BF16 ? 1u : 2u) << 7) | ((BF16 ? 1u : 2u) << 10) |
+                                    ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+};
+
+// fused epilogue on 4 consecutive columns (n .. n+3) of row m, all in range, ep.vec_ok
+__device__ __forceinline__ void epi4(const Epilogue& ep, float4 t, long long m, int n) {
+  float v[4] = {t.x, t.y, t.z, t.w};
+  epi_apply4(ep, v, m, n);
+}
+
+// One epilogue warp: TMEM lanes [32*quarter, +32) x columns [col0, col0+COLS) of every tile of this CTA.
+template <class C, int COLS>
+__device__ __forceinline__ void epilogue_loop(int col0, int quarter, int lane, uint32_t rank, uint32_t tmem_base,
+                                              uint32_t tfull0, uint32_t tempty0_leader, float* patch,
+                                              long long n_tiles, int n_blocks, int k_slabs, int chunk_slabs,
+                                              long long M, int N, const Epilogue& ep) {
+  constexpr int BLOCK_N = C::kBlockN;
+  int acc = 0;
+  uint32_t acc_phase = 0;
+  const int n_chunks = (k_slabs + chunk_slabs - 1) / chunk_slabs;
+  for (long long tile = cluster_id_x(); tile < n_tiles; tile += num_clusters_x()) {
+    const long long m_idx = (tile / n_blocks) * (2 * BLOCK_M) + rank * BLOCK_M;
+    const int n_idx = (int)(tile % n_blocks) * BLOCK_N;
+    if (COLS == 0) {  // nothing to own: still take part in the barrier protocol
+      for (int c = 0; c < n_chunks; ++c) {
+        mbar_wait(tfull0 + 8u * acc, acc_phase);
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(tempty0_leader + 8u * acc);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+      continue;
+    }
+    // partial accumulators (one per K chunk) are added in place with round-to-nearest; starting from zero keeps
+    // one register copy of the tile (a "first chunk moves, later chunks add" split doubles the live registers)
+    float master[COLS > 0 ? COLS : 1];
+#pragma unroll
+    for (int i = 0; i < COLS; ++i) master[i] = 0.f;
+    for (int c = 0; c < n_chunks; ++c) {
+      mbar_wait(tfull0 + 8u * acc, acc_phase);
+      tcgen05_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * C::ACC_STRIDE + col0;
+#pragma unroll
+      for (int j = 0; j + 32 <= COLS; j += 32) {
+        float v[32];
+        tmem_ld32(taddr + j, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) master[j + i] += v[i];
+      }
+      if (COLS % 32) {
+        constexpr int j = COLS / 32 * 32;
+        float v[16];
+        tmem_ld16(taddr + j, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) master[j + i] += v[i];
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(tempty0_leader + 8u * acc);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    // registers -> padded smem patch -> coalesced row segments (4 lanes x 16 B per row, 8 rows per pass)
+    const long long row0 = m_idx + quarter * 32;
+    const int sub_r = lane >> 2, sub_c = (lane & 3) * 4;
+#pragma unroll
+    for (int j = 0; j < COLS; j += PATCH_COLS) {
+      float* prow = patch + lane * PATCH_LD;
+#pragma unroll
+      for (int i = 0; i < PATCH_COLS; i += 4)
+        *reinterpret_cast<float4*>(prow + i) = make_float4(master[j + i], master[j + i + 1], master[j + i + 2], master[j + i + 3]);
+      __syncwarp();
+      const int n = n_idx + col0 + j + sub_c;
+#pragma unroll 1
+      for (int p = 0; p < 4; ++p) {
+        const int r = p * 8 + sub_r;
+        const long long m = row0 + r;
+        const float4 t = *reinterpret_cast<const float4*>(patch + r * PATCH_LD + sub_c);
+        if (m < M && n < N) {
+          if (ep.vec_ok && n + 3 < N) {
+            epi4(ep, t, m, n);
+          } else {
+            const float tv[4] = {t.x, t.y, t.z, t.w};
+            for (int i = 0; i < 4; ++i)
+              if (n + i < N) epi_store1(ep, epi_value(ep, tv[i], m, n + i), m, n + i);
+          }
+        }
+      }
+      __syncwarp();
+    }
+  }
+}
+
+template <int BLOCK_N, int NTERMS, bool BF16>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_a_lo,
+                const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_w_lo,
+                long long M, int N, int K, int chunk_slabs, const __grid_constant__ Epilogue ep) {
+  using C = Config<BLOCK_N, NTERMS, BF16>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // same offset in both CTAs of the pair
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t epi_base = smem_base + C::STAGES * C::STAGE_BYTES;
+  const uint32_t bar_base = epi_base + C::EPI_BYTES;
+  // barrier block: full[STAGES] (leader's is used), empty[STAGES], tmem_full[2], tmem_empty[2] (leader's), tmem slot
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (C::STAGES + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * C::STAGES + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * C::STAGES + 2 + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * C::STAGES + 4);
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_gen + (tmem_slot - smem_base));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int n_blocks = (N + BLOCK_N - 1) / BLOCK_N;
+  const long long m_blocks = (M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
+  const long long n_tiles = m_blocks * n_blocks;
+  const int k_slabs = (K + C::ELEMS_PER_SLAB - 1) / C::ELEMS_PER_SLAB;
+  if (chunk_slabs <= 0 || chunk_slabs > k_slabs) chunk_slabs = k_slabs;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tm_a);
+    prefetch_tmap(&tm_w);
+    if (NTERMS == 3) { prefetch_tmap(&tm_a_lo); prefetch_tmap(&tm_w_lo); }
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < C::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+      for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 2 * NUM_EPI_WARPS); }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(C::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  cluster_sync_all();   // barriers of both CTAs initialised and visible before any remote arrive / TMA completion
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp < FIRST_EPI_WARP) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_NON_EPI));
+    if (warp == 0) {
+      // ===================== TMA producer (both CTAs) =====================
+      if (lane == 0) {
+        int stage = 0;
+        uint32_t phase = 0;
+        for (long long tile = cluster_id_x(); tile < n_tiles; tile += num_clusters_x()) {
+          const int m_idx = (int)(tile / n_blocks) * (2 * BLOCK_M) + (int)rank * BLOCK_M;
+          const int n_idx = (int)(tile % n_blocks) * BLOCK_N + (int)rank * C::HALF_N;
+          for (int ks = 0; ks < k_slabs; ++ks) {
+            mbar_wait(empty_bar(stage), phase ^ 1);
+            const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
+            const uint32_t sb = sa + C::NPLANES * C::A_TILE;
+            const int k_idx = ks * C::ELEMS_PER_SLAB;
+            const uint32_t fb = mapa(full_bar(stage), 0);
+            if (rank == 0) mbar_expect_tx(full_bar(stage), 2 * C::STAGE_BYTES);
+            tma_load_2d_pair(sa, &tm_a, fb, k_idx, m_idx);
+            tma_load_2d_pair(sb, &tm_w, fb, k_idx, n_idx);
+            if (NTERMS == 3) {
+              tma_load_2d_pair(sa + C::A_TILE, &tm_a_lo, fb, k_idx, m_idx);
+              tma_load_2d_pair(sb + C::B_TILE, &tm_w_lo, fb, k_idx, n_idx);
+            }
+            if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    } else if (warp == 1 && rank == 0) {
+      // ===================== MMA issuer (leader CTA only) =====================
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (long long tile = cluster_id_x(); tile < n_tiles; tile += num_clusters_x()) {
+        for (int ks0 = 0; ks0 < k_slabs; ks0 += chunk_slabs) {
+          const int ks1 = ks0 + chunk_slabs < k_slabs ? ks0 + chunk_slabs : k_slabs;
+          mbar_wait(tempty_bar(acc), acc_phase ^ 1);  // both CTAs' epilogues have drained this accumulator
+          tcgen05_fence_after();
+          const uint32_t tmem_d = tmem_base + acc * C::ACC_STRIDE;
+          for (int ks = ks0; ks < ks1; ++ks) {
+            mbar_wait(full_bar(stage), phase);
+            tcgen05_fence_after();
+            if (lane == 0) {
+              const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
+              const uint32_t sb = sa + C::NPLANES * C::A_TILE;
+              const uint64_t da_hi = make_smem_desc(sa), db_hi = make_smem_desc(sb);
+              if (NTERMS == 3) {  // small terms first: they meet the accumulator while it is smallest
+                const uint64_t da_lo = make_smem_desc(sa + C::A_TILE), db_lo = make_smem_desc(sb + C::B_TILE);
+#pragma unroll
+                for (int k = 0; k < SLAB_BYTES / UMMA_K_BYTES; ++k) {
+                  const uint64_t koff = (uint64_t)((k * UMMA_K_BYTES) >> 4);
+                  umma_pair<BF16>(da_lo + koff, db_hi + koff, tmem_d, C::IDESC, (ks > ks0 || k > 0) ? 1u : 0u);
+                  umma_pair<BF16>(da_hi + koff, db_lo + koff, tmem_d, C::IDESC, 1u);
+                }
+              }
+#pragma unroll
+              for (int k = 0; k < SLAB_BYTES / UMMA_K_BYTES; ++k) {
+                const uint64_t koff = (uint64_t)((k * UMMA_K_BYTES) >> 4);
+                umma_pair<BF16>(da_hi + koff, db_hi + koff, tmem_d, C::IDESC, (NTERMS == 3 || ks > ks0 || k > 0) ? 1u : 0u);
+              }
+              umma_commit_pair(empty_bar(stage));                  // slot free in both CTAs once these MMAs retire
+              if (ks == ks1 - 1) umma_commit_pair(tfull_bar(acc));  // accumulation chain complete (both CTAs)
+            }
+            __syncwarp();
+            if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+          }
+          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue warps (TMEM lane quarter = warp % 4; column half = (warp-4)/4) ======
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_EPI));
+    float* patch = reinterpret_cast<float*>(smem_gen + (epi_base - smem_base) + (warp - FIRST_EPI_WARP) * PATCH_BYTES);
+    const uint32_t tempty_leader = mapa(tempty_bar(0), 0);
+    if (warp < FIRST_EPI_WARP + 4)
+      epilogue_loop<C, C::HALF0>(0, warp & 3, lane, rank, tmem_base, tfull_bar(0), tempty_leader, patch, n_tiles,
+                                 n_blocks, k_slabs, chunk_slabs, M, N, ep);
+    else
+      epilogue_loop<C, C::HALF1>(C::HALF0, warp & 3, lane, rank, tmem_base, tfull_bar(0), tempty_leader, patch, n_tiles,
+                                 n_blocks, k_slabs, chunk_slabs, M, N, ep);
+  }
+
+  tcgen05_fence_before();
+  cluster_sync_all();   // the peer may still signal our barriers / read our smem through the MMA until here
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::TMEM_COLS) : "memory");
+  }
+}
+
+}  // namespace tc2
+
+// host side ---------------------------------------------------------------------------------------
+template <int BLOCK_N, int NTERMS, bool BF16>
+int launch_gemm_tc2_cfg(const usf_linear_args* a, const Epilogue& ep, cudaStream_t st) {
+  using C = tc2::Config<BLOCK_N, NTERMS, BF16>;
+  static bool attr_set = false;
+  auto kern = tc2::gemm_tc2_kernel<BLOCK_N, NTERMS, BF16>;
+  if (!attr_set) {
+    USF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    attr_set = true;
+  }
+  CUtensorMap ma, mal, mw, mwl;
+  int rc;
+  if ((rc = make_operand_map(&ma, a->a, a->M, a->K, a->lda, tc::BLOCK_M, BF16))) return rc;
+  if ((rc = make_operand_map(&mw, a->w, a->N, a->K, a->ldw, C::HALF_N, BF16))) return rc;
+  if (NTERMS == 3) {
+    if ((rc = make_operand_map(&mal, a->a_lo, a->M, a->K, a->lda, tc::BLOCK_M, BF16))) return rc;
+    if ((rc = make_operand_map(&mwl, a->w_lo, a->N, a->K, a->ldw, C::HALF_N, BF16))) return rc;
+  } else {
+    mal = ma;
+    mwl = mw;
+  }
+  const long long tiles = ((a->M + 2 * tc::BLOCK_M - 1) / (2 * tc::BLOCK_M)) * ((a->N + BLOCK_N - 1) / BLOCK_N);
+  const int pairs = num_sms() / 2;
+  const int grid = 2 * (int)(tiles < pairs ? tiles : pairs);
+  kern<<<grid, tc::NUM_THREADS, C::SMEM_BYTES, st>>>(ma, mal, mw, mwl, a->M, a->N, a->K,
+                                                       NTERMS == 3 ? g_chunk_slabs : 0, ep);
+  USF_CUDA_OK(cudaGetLastError());
+  return USF_OK;
+}
+
+// BLOCK_N choice for the pair kernel: least padded MMA work, ties to the wider tile
+inline int pick_block_n2(int N) {
+  static const int cands[] = {256, 208, 128, 64, 32};
+  int best = 256;
+  double best_cost = 1e30;
+  for (int bn : cands) {
+    int nb = (N + bn - 1) / bn;
+    double waste = (double)nb * bn / N;
+    double cost = waste * (1.0 + 0.25 * 128.0 / bn) * (1.0 + 0.01 * nb);  // narrow tiles re-read A more often
+    if (cost < best_cost) { best_cost = cost; best = bn; }
+  }
+  return best;
+}
+
+template <int NTERMS, bool BF16>
+int launch_gemm_tc2_terms(const usf_linear_args* a, const Epilogue& ep, cudaStream_t st, int bn) {
+  switch (bn) {
+    case 256: return launch_gemm_tc2_cfg<256, NTERMS, BF16>(a, ep, st);
+    case 208: return launch_gemm_tc2_cfg<208, NTERMS, BF16>(a, ep, st);
+    case 128: return launch_gemm_tc2_cfg<128, NTERMS, BF16>(a, ep, st);
+    case 64: return launch_gemm_tc2_cfg<64, NTERMS, BF16>(a, ep, st);
+    case 32: return launch_gemm_tc2_cfg<32, NTERMS, BF16>(a, ep, st);
+  }
+  return fail(USF_ERR_INVALID, "unsupported BLOCK_N (built: 256, 208, 128, 64, 32)%s%s");
+}
+
+int launch_gemm_tc2_3xtf32(const usf_linear_args* a, const Epilogue& ep, cudaStream_t st, int bn);
+int launch_gemm_tc2_tf32(const usf_linear_args* a, const Epilogue& ep, cudaStream_t st, int bn);
+int launch_gemm_tc2_bf16(const usf_linear_args* a, const Epilogue& ep, cudaStream_t st, int bn);
+
+extern int g_tc_impl;         // 2 = CTA-pair kernel (default), 1 = single-CTA kernel (usf_debug_set_impl)
+extern int g_force_block_n;   // test hook (usf_debug_set_block_n)
+
+inline int launch_gemm_tc(const usf_linear_args* a, const Epilogue& ep, cudaStream_t st) {
+  if (a->M == 0 || a->N == 0) return USF_OK;
+  const bool bf16 = a->engine == USF_ENGINE_TC_BF16;
+  const int kmul = bf16 ? 8 : 4;
+  USF_REQUIRE(a->K > 0, "K must be positive");
+  USF_REQUIRE(a->M < (1LL << 31) - 512, "tcgen05 engine: M must fit a TMA coordinate");
+  USF_REQUIRE(aligned16(a->a) && aligned16(a->w) && a->lda % kmul == 0 && a->ldw % kmul == 0,
+              "tcgen05 engines need 16-byte aligned operands and 16-byte multiples for lda/ldw");
+  USF_REQUIRE(!a->trans_w, "trans_w is a SIMT-engine option");
+  if (a->engine == USF_ENGINE_TC_3XTF32)
+    USF_REQUIRE(a->a_lo && a->w_lo && aligned16(a->a_lo) && aligned16(a->w_lo), "3xTF32 needs a_lo and w_lo planes");
+  if (g_tc_impl == 2) {
+    const int bn = g_force_block_n > 0 ? g_force_block_n : pick_block_n2(a->N);
+    if (a->engine == USF_ENGINE_TC_3XTF32) return launch_gemm_tc2_3xtf32(a, ep, st, bn);
+    if (a->engine == USF_ENGINE_TC_TF32) return launch_gemm_tc2_tf32(a, ep, st, bn);
+    return launch_gemm_tc2_bf16(a, ep, st, bn);
+  }
+  const int bn = g_force_block_n > 0 ? g_force_block_n : pick_block_n(a->N);
+  if (a->engine == USF_ENGINE_TC_3XTF32) return launch_gemm_tc_3xtf32(a, ep, st, bn);
+  if (a->engine == USF_ENGINE_TC_TF32) return launch_gemm_tc_tf32(a, ep, st, bn);
+  return launch_gemm_tc_bf16(a, ep, st, bn);
+}
+
+}  // namespace usf

@@ -1,8 +1,11 @@
-// Instantiations of the tcgen05 contraction for the bf16 engine (own translation unit: parallel build).
-#include "gemm_tc.cuh"
+// Instantiations of the tcgen05 contractions for the bf16 engine (own translation unit: parallel build).
+#include "gemm_tc2.cuh"
 
 namespace usf {
 int launch_gemm_tc_bf16(const usf_linear_args* a, const Epilogue& ep, cudaStream_t st, int bn) {
   return launch_gemm_tc_terms<1, true>(a, ep, st, bn);
+}
+int launch_gemm_tc2_bf16(const usf_linear_args* a, const Epilogue& ep, cudaStream_t st, int bn) {
+  return launch_gemm_tc2_terms<1, true>(a, ep, st, bn);
 }
 }  // namespace usf
