@@ -177,6 +177,12 @@ int usf_to_bf16(const float* in, int64_t rows, int32_t cols, int64_t ld_in, void
  * `work` = d floats. */
 int usf_householder_right(float* W, int32_t d, int64_t ld, const float* v, float* work, void* stream);
 
+/* C[M,N] = A[M,K] . B[K,N], row-major fp64 (leading dimensions in elements).  Composition of neighbouring
+ * affine layers into one operator (SequentialAffineTransform.matrix/inverse_matrix, transforms.py:1457-1469,
+ * and the products across Aff_i^-1 / Aff_{i+1} boundaries) in higher precision than the layers run in. */
+int usf_matmul_f64(const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc, int32_t M,
+                   int32_t N, int32_t K, void* stream);
+
 /* out[j] = softplus(in[j])  (distributions.py:211-215, base scale parameterisation) */
 int usf_softplus(const float* in, int64_t n, float* out, void* stream);
 

@@ -165,6 +165,10 @@ def matmul_f32(a, b, out, bias=None):
     out.copy_(v if bias is None else v + bias)
 
 
+def matmul_f64(a, b, out):
+    out.copy_(a @ b)
+
+
 def require_cuda(t, name="tensor", dtype=torch.float32):
     return t
 
@@ -173,5 +177,5 @@ def install(monkeypatch):
     CALLS.clear()
     for name in ["linear", "ingest", "base_logprob", "base_sample", "leaky_relu", "permute", "lu_assemble",
                  "lu_logabsdet", "vec_logabs", "tri_inverse", "transpose", "scale_rows_cols", "split_tf32", "to_bf16",
-                 "householder_right", "softplus", "matmul_f32", "require_cuda"]:
+                 "householder_right", "softplus", "matmul_f32", "matmul_f64", "require_cuda"]:
         monkeypatch.setattr(real_ops, name, globals()[name])

@@ -34,16 +34,33 @@ def test_bf16_mode_runs_with_its_own_bound(fake_ops):
 
 
 def test_kernel_count_per_log_prob(fake_ops):
-    """one ingest + 5B+1 contractions + one base-density reduction for a conjugated USFlow (B blocks)."""
-    spec, params, arr = load_case("d32_h64")
+    """one ingest + (B+1) merged affine contractions + 3B conditioner contractions + one base-density reduction
+    for a conjugated USFlow with B blocks: Aff_i^-1 . Aff_{i+1} pairs and the trailing Scale are composed into one
+    operator each (the reference runs 2B+1 affine layers + Scale)."""
+    spec, params, arr = load_case("d100_h50_hh")
     flow = build_flow(spec, params, device="cpu", precision="fp32")
     flow.log_prob(arr["x"])               # includes weight preparation
     fake_backend.CALLS.clear()
     flow.log_prob(arr["x"])               # steady state: prepared weights are cached
     kinds = [c[0] for c in fake_backend.CALLS]
     B = spec["coupling_blocks"]
+    assert spec["affine_conjugation"] and len(spec["hidden_dims"]) == 2
     assert kinds.count("ingest") == 1 and kinds.count("base_logprob") == 1
-    assert kinds.count("linear") == 5 * B + 1
+    assert kinds.count("linear") == (B + 1) + 3 * B
+
+
+def test_mask_compression_halves_the_outer_conditioner_contractions(fake_ops):
+    """d = 784: the checkerboard partition gives two 392-wide contiguous segments; the first conditioner GEMM
+    reads K = 392 columns and the last writes N = 392 columns in place."""
+    spec, params, arr = load_case("c2_d784")
+    flow = build_flow(spec, params, device="cpu", precision="fp32")
+    flow.log_prob(arr["x"][:4])
+    fake_backend.CALLS.clear()
+    flow.log_prob(arr["x"][:4])
+    shapes = [(c[3], c[4]) for c in fake_backend.CALLS if c[0] == "linear"]      # (N, K)
+    H = spec["hidden_dims"][0]
+    assert shapes.count((784, 784)) == spec["coupling_blocks"] + 1
+    assert shapes.count((H, 392)) == spec["coupling_blocks"] and shapes.count((392, H)) == spec["coupling_blocks"]
 
 
 def test_prepared_weights_follow_weight_version(fake_ops):

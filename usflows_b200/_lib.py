@@ -61,6 +61,7 @@ SIGNATURES = {
     "usf_to_bf16": (C.c_int, [_P, _I64, _I32, _I64, _P, _I64, _P]),
     "usf_householder_right": (C.c_int, [_P, _I32, _I64, _P, _P, _P]),
     "usf_softplus": (C.c_int, [_P, _I64, _P, _P]),
+    "usf_matmul_f64": (C.c_int, [_P, _I64, _P, _I64, _P, _I64, _I32, _I32, _I32, _P]),
     "usf_debug_set_block_n": (C.c_int, [C.c_int]),
     "usf_set_accum_chunk": (C.c_int, [C.c_int]),
     "usf_debug_set_impl": (C.c_int, [C.c_int]),

@@ -278,6 +278,17 @@ int usf_householder_right(float* W, int32_t d, int64_t ld, const float* v, float
   return USF_OK;
 }
 
+int usf_matmul_f64(const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc, int32_t M,
+                   int32_t N, int32_t K, void* stream) {
+  USF_REQUIRE(A && B && C && M > 0 && N > 0 && K > 0, "bad input");
+  USF_REQUIRE(C != A && C != B, "matmul_f64 cannot run in place");
+  dim3 grid((N + 63) / 64, (M + 63) / 64);
+  USF_REQUIRE(grid.y <= 65535, "matmul_f64: too many row blocks");
+  matmul_f64_kernel<<<grid, 256, 0, S(stream)>>>(A, lda, B, ldb, C, ldc, M, N, K);
+  USF_CUDA_OK(cudaGetLastError());
+  return USF_OK;
+}
+
 int usf_softplus(const float* in, int64_t n, float* out, void* stream) {
   USF_REQUIRE(in && out && n > 0, "bad input");
   softplus_kernel<<<ew_grid(n, 256), 256, 0, S(stream)>>>(in, n, out);

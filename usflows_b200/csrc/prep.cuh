@@ -259,4 +259,51 @@ tri_panel_sweep_kernel(const float* __restrict__ T, int d, long long ldt, const 
     }
 }
 
+// ---- fp64 product for weight composition: C[M,N] = A[M,K] . B[K,N], all row-major double -------------
+// Merging neighbouring affine layers (W2 . W1, W . diag, W . c) happens once per weight version; doing it in
+// fp64 keeps the merged operator closer to the exact product than the reference's chained fp32 layers.
+// 64x64x16 tiles, 256 threads, 4x4 micro tile.
+__global__ void __launch_bounds__(256)
+matmul_f64_kernel(const double* __restrict__ A, long long lda, const double* __restrict__ B, long long ldb,
+                  double* __restrict__ C, long long ldc, int M, int N, int K) {
+  __shared__ double sA[16][64 + 2];
+  __shared__ double sB[16][64 + 2];
+  const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
+  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  double acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+  for (int k0 = 0; k0 < K; k0 += 16) {
+    for (int e = tid; e < 64 * 16; e += 256) {
+      const int r = e / 16, c = e % 16;         // A tile: 64 rows x 16 k
+      const int gm = m0 + r, gk = k0 + c;
+      sA[c][r] = (gm < M && gk < K) ? A[(long long)gm * lda + gk] : 0.0;
+      const int kr = e / 64, nc = e % 64;       // B tile: 16 k x 64 cols
+      const int gk2 = k0 + kr, gn = n0 + nc;
+      sB[kr][nc] = (gk2 < K && gn < N) ? B[(long long)gk2 * ldb + gn] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      double a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { a[i] = sA[k][ty * 4 + i]; b[i] = sB[k][tx * 4 + i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int gm = m0 + ty * 4 + i, gn = n0 + tx * 4 + j;
+      if (gm < M && gn < N) C[(long long)gm * ldc + gn] = acc[i][j];
+    }
+}
+
 }  // namespace usf

@@ -30,7 +30,7 @@ from .ops import Act, ENGINE_SIMT, ENGINE_TC_3XTF32, ENGINE_TC_BF16, ENGINE_TC_T
 
 PRECISIONS = ("fp32", "fp32_simt", "tf32", "bf16")
 _default_precision = "fp32"
-_default_chunk_rows = 16384
+_default_chunk_rows = 65536
 TC_MIN_DIM = 32          # contractions narrower than this run on the SIMT engine
 
 
@@ -51,141 +51,444 @@ def set_chunk_rows(rows: int) -> None:
 
 
 # --------------------------------------------------------------------------------------------------
-# operand preparation per precision mode (cached on the owning tensor's identity)
+# lowering: layers -> primitive ops -> composed affine runs -> launch steps
 # --------------------------------------------------------------------------------------------------
-class _OperandCache:
-    """fp32 weight matrix -> the planes a contraction engine reads (tf32 hi/lo split, bf16 copy)."""
-
-    def __init__(self):
-        self._c = {}
-
-    def get(self, w: torch.Tensor, mode: str):
-        key = (w.data_ptr(), w._version, tuple(w.shape), mode)
-        hit = self._c.get(key)
-        if hit is not None:
-            return hit[1], hit[2]
-        rows, cols = w.shape
-        ld = pad4(cols)
-        if mode == "fp32":
-            buf = torch.zeros(2, rows, ld, dtype=torch.float32, device=w.device)
-            hi, lo = buf[0, :, :cols], buf[1, :, :cols]
-            ops.split_tf32(w, hi, lo)
-            res = (hi, lo)
-        elif mode == "bf16":
-            b = torch.zeros(rows, pad4(cols), dtype=torch.bfloat16, device=w.device)[:, :cols]
-            ops.to_bf16(w, b)
-            res = (b, None)
-        else:  # "tf32" / "fp32_simt": the fp32 matrix itself, re-laid with a 16-byte-multiple pitch if needed
-            if w.stride(0) % 4 == 0 and w.data_ptr() % 16 == 0:
-                res = (w, None)
-            else:
-                b = torch.zeros(rows, ld, dtype=torch.float32, device=w.device)[:, :cols]
-                b.copy_(w)
-                res = (b, None)
-        if len(self._c) > 4096:
-            self._c.clear()
-        self._c[key] = (w, res[0], res[1])   # keep `w` alive so data_ptr stays unique
-        return res
-
-
-_operands = _OperandCache()
-
-
 def _engine_for(mode: str, N: int, K: int) -> int:
     if mode == "fp32_simt" or min(N, K) < TC_MIN_DIM:
         return ENGINE_SIMT
     return {"fp32": ENGINE_TC_3XTF32, "tf32": ENGINE_TC_TF32, "bf16": ENGINE_TC_BF16}[mode]
 
 
-# --------------------------------------------------------------------------------------------------
-# program steps
-# --------------------------------------------------------------------------------------------------
 @dataclass
-class Step:
-    kind: str                                  # "mm" | "leaky" | "permute" | "vec"
-    src: str = "x"                             # slot read:  "x" (stream) or "h" (conditioner hidden)
-    dst: str = "x"
-    w: Optional[torch.Tensor] = None           # [N, K] fp32 prepared weight
-    bias: Optional[torch.Tensor] = None
-    relu: bool = False
-    resid: bool = False                        # out = x + sign * value
+class Prim:
+    """One primitive op of the lowered layer stack (direction already applied)."""
+    kind: str                                   # "aff" | "mul" | "div" | "perm" | "coupling" | "leaky"
+    W: Optional[torch.Tensor] = None            # aff: fp64 [dout, din]
+    c: Optional[torch.Tensor] = None            # aff: fp64 [dout] (y = x W^T + c)
+    v: Optional[torch.Tensor] = None            # mul / div: fp32 [d] ; perm: int64 [d]
+    prep: Optional[dict] = None                 # coupling: raw conditioner weights / biases / mask
     sign: float = 1.0
-    colscale: Optional[torch.Tensor] = None
-    postsub: Optional[torch.Tensor] = None
-    presub: Optional[torch.Tensor] = None      # planning only: subtract from the input first
-    vec_div: Optional[torch.Tensor] = None     # "vec" steps: ((x / div) * mul) - sub
-    vec_mul: Optional[torch.Tensor] = None
-    vec_sub: Optional[torch.Tensor] = None
     slope: float = 1.0
-    perm: Optional[torch.Tensor] = None
-    needs: set = field(default_factory=set)    # what the consumer of this step's output reads
 
 
-def _emit_layer(layer, direction: str, steps: List[Step]) -> None:
+def _lower_layer(layer, direction: str, out: List[Prim]) -> None:
     from . import transforms as T
     fwd = direction == "forward"
     if isinstance(layer, T.InverseTransform):
-        _emit_layer(layer.transform, "backward" if fwd else "forward", steps)
+        _lower_layer(layer.transform, "backward" if fwd else "forward", out)
         return
     if isinstance(layer, T.BlockAffineTransform):
         layer = layer.block_transform
     if isinstance(layer, T.AffineTransform):
         p = layer._prepared()
-        if fwd:    # x @ W^T + b   (transforms.py:913-934)
-            steps.append(Step("mm", w=p["matrix"], bias=p["bias"]))
-        else:      # (y - b) @ Winv^T  (transforms.py:936-962)
-            steps.append(Step("mm", w=p["inverse_matrix"], presub=p["bias"]))
+        if fwd:    # x @ W^T + b                     (transforms.py:913-934)
+            out.append(Prim("aff", W=p["matrix64"], c=p["bias"].double()))
+        else:      # (y - b) @ Winv^T = y Winv^T - Winv b   (transforms.py:936-962)
+            out.append(Prim("aff", W=p["inverse64"], c=-_matvec64(p["inverse64"], p["bias"].double())))
         return
     if isinstance(layer, T.MaskedCoupling):
-        p = layer._prepared()
-        ws, bs = p["weights"], p["biases"]
-        n = len(ws)
-        for j in range(n):
-            last = j == n - 1
-            steps.append(Step("mm", src="x" if j == 0 else "h", dst="x" if last else "h", w=ws[j], bias=bs[j],
-                              relu=not last, resid=last, sign=1.0 if fwd else -1.0))
+        out.append(Prim("coupling", prep=layer._raw(), sign=1.0 if fwd else -1.0))
         return
     if isinstance(layer, T.ScaleTransform):
         s = layer.scale.detach().reshape(-1)
         ops.require_cuda(s, "ScaleTransform.scale")
-        steps.append(Step("vec", vec_mul=s) if fwd else Step("vec", vec_div=s))
+        out.append(Prim("mul" if fwd else "div", v=s))
         return
     if isinstance(layer, T.LeakyReLUTransform):
-        steps.append(Step("leaky", slope=layer.alpha if fwd else 1.0 / layer.alpha))
+        out.append(Prim("leaky", slope=layer.alpha if fwd else 1.0 / layer.alpha))
         return
     if isinstance(layer, T.Permute):
-        perm = layer.permutation if fwd else layer.inv_permutation
-        steps.append(Step("permute", perm=perm.to(torch.int32)))
+        out.append(Prim("perm", v=(layer.permutation if fwd else layer.inv_permutation).long()))
         return
     raise NotImplementedError(f"usflows_b200: no kernel path for layer type {type(layer).__name__}")
 
 
-def _fuse(steps: List[Step]) -> List[Step]:
-    """Peephole fusion of per-feature vector ops into neighbouring kernels (see module docstring)."""
-    out: List[Step] = []
-    for st in steps:
-        prev = out[-1] if out else None
-        if st.kind == "mm" and st.presub is not None and st.src == "x":
-            if prev is not None and prev.kind == "mm" and prev.dst == "x" and prev.postsub is None:
-                prev.postsub, st.presub = st.presub, None
-            elif prev is not None and prev.kind == "vec" and prev.vec_sub is None:
-                prev.vec_sub, st.presub = st.presub, None
-            else:
-                out.append(Step("vec", vec_sub=st.presub))
-                st.presub = None
-        elif st.kind == "vec" and st.vec_mul is not None and st.vec_div is None and st.vec_sub is None:
-            if prev is not None and prev.kind == "mm" and prev.dst == "x" and prev.colscale is None and prev.postsub is None:
-                prev.colscale = st.vec_mul
-                continue
-        out.append(st)
+def _matmul64(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    out = torch.empty(a.shape[0], b.shape[1], dtype=torch.float64, device=a.device)
+    ops.matmul_f64(a.contiguous(), b.contiguous(), out)
     return out
 
 
+def _matvec64(W: torch.Tensor, v: torch.Tensor) -> torch.Tensor:
+    return _matmul64(W, v.reshape(-1, 1)).reshape(-1)
+
+
+def _compose_run(run: List[Prim]) -> Prim:
+    """Fold a run of affine / diagonal / permutation maps (applied left to right) into one dense (W, c) in fp64:
+    (W2, c2) o (W1, c1) = (W2 W1, W2 c1 + c2)."""
+    W = c = None
+    pend: List[Prim] = []                     # diagonal / permutation maps seen before the first dense one
+
+    def apply_left(W, c, p):                  # (W, c) followed by p
+        if p.kind == "mul":
+            v = p.v.double()
+            return W * v[:, None], None if c is None else c * v
+        if p.kind == "div":
+            v = 1.0 / p.v.double()
+            return W * v[:, None], None if c is None else c * v
+        if p.kind == "perm":                  # y = x[:, idx]
+            return W[p.v], None if c is None else c[p.v]
+        W2 = _matmul64(p.W, W)
+        c2 = p.c if c is None else (_matvec64(p.W, c) + (p.c if p.c is not None else 0))
+        return W2, c2
+
+    for p in run:
+        if W is None:
+            if p.kind != "aff":
+                pend.append(p)
+                continue
+            W, c = p.W, p.c
+            for q in reversed(pend):          # q happened BEFORE the dense map: fold into its columns
+                if q.kind == "mul":
+                    W = W * q.v.double()[None, :]
+                elif q.kind == "div":
+                    W = W * (1.0 / q.v.double())[None, :]
+                else:                          # x' = x[:, idx]; y = x' W^T  ->  W_new[:, idx[j]] = W[:, j]
+                    Wn = torch.zeros_like(W)
+                    Wn[:, q.v] = W
+                    W = Wn
+            continue
+        W, c = apply_left(W, c, p)
+    return Prim("aff", W=W, c=c)
+
+
+@dataclass
+class Step:
+    kind: str                                  # "mm" | "leaky" | "permute" | "vec"
+    src: str = "x"                             # "x" (stream) or "h" (conditioner hidden)
+    dst: str = "x"
+    w: Optional[torch.Tensor] = None           # operand-format weight [N, K] (hi plane / fp32 / bf16)
+    w_lo: Optional[torch.Tensor] = None
+    N: int = 0
+    K: int = 0
+    engine: int = ENGINE_SIMT
+    bias: Optional[torch.Tensor] = None
+    relu: bool = False
+    resid: bool = False                        # out = x + sign * value (in place on the stream segment `out_seg`)
+    sign: float = 1.0
+    in_seg: Optional[tuple] = None             # (col0, width) of the stream read as A (None = whole stream)
+    out_seg: Optional[tuple] = None            # (col0, width) of the stream written (None = whole / new buffer)
+    vec_div: Optional[torch.Tensor] = None     # "vec" steps: ((x / div) * mul)
+    vec_mul: Optional[torch.Tensor] = None
+    slope: float = 1.0
+    perm: Optional[torch.Tensor] = None
+    final: bool = False                        # writes the program's fp32 result
+
+
+def _operand(w64_or_32: torch.Tensor, mode: str, engine: int):
+    """fp32/fp64 weight [N, K] -> operand planes of the engine, pitch padded to a 16-byte multiple."""
+    w = w64_or_32.to(torch.float32)
+    rows, cols = w.shape
+    ld = pad4(cols)
+    if engine == ENGINE_TC_3XTF32:
+        buf = torch.zeros(2, rows, ld, dtype=torch.float32, device=w.device)
+        hi, lo = buf[0, :, :cols], buf[1, :, :cols]
+        src = torch.zeros(rows, ld, dtype=torch.float32, device=w.device)[:, :cols]
+        src.copy_(w)
+        ops.split_tf32(src, hi, lo)
+        return hi, lo
+    if engine == ENGINE_TC_BF16:
+        src = torch.zeros(rows, ld, dtype=torch.float32, device=w.device)[:, :cols]
+        src.copy_(w)
+        b = torch.zeros(rows, ld, dtype=torch.bfloat16, device=w.device)[:, :cols]
+        ops.to_bf16(src, b)
+        return b, None
+    b = torch.zeros(rows, ld, dtype=torch.float32, device=w.device)[:, :cols]
+    b.copy_(w)
+    return b, None
+
+
+class Program:
+    """Launch program of one direction of a layer stack for one precision mode and weight version."""
+
+    def __init__(self, layers, direction: str, mode: Optional[str] = None):
+        self.mode = mode or _default_precision
+        seq = list(layers) if direction == "forward" else list(reversed(list(layers)))
+        prims: List[Prim] = []
+        for layer in seq:
+            _lower_layer(layer, direction, prims)
+        # 1. compose maximal runs of affine-like maps that contain at least one dense matrix
+        items: List[Prim] = []
+        run: List[Prim] = []
+
+        def flush():
+            if not run:
+                return
+            if any(p.kind == "aff" for p in run):
+                items.append(_compose_run(run))
+            else:
+                items.extend(run)
+            run.clear()
+
+        for p in prims:
+            if p.kind in ("aff", "mul", "div", "perm"):
+                run.append(p)
+            else:
+                flush()
+                items.append(p)
+        flush()
+        self.items = items
+        # 2. widths, engine choice (tiny problems run the whole program on the SIMT engine)
+        dims = []
+        for p in items:
+            if p.kind == "aff":
+                dims += list(p.W.shape)
+            elif p.kind == "coupling":
+                for w in p.prep["weights"]:
+                    dims += list(w.shape)
+        compress = self._compression_plan(items)
+        if compress is not None:
+            dims += [compress["h1"], compress["h0"]]
+        if dims and min(dims) < TC_MIN_DIM and self.mode != "fp32_simt":
+            self.mode = "fp32_simt"
+            compress = self._compression_plan(items)
+        self.compress = compress
+        self.steps = self._emit(items, compress)
+
+    # -- mask compression: run the couplings in a feature order that makes "conditioner inputs" and "updated
+    #    features" two contiguous column segments, so the first / last conditioner GEMMs shrink to half size
+    def _compression_plan(self, items):
+        coups = [i for i, p in enumerate(items) if p.kind == "coupling"]
+        if not coups:
+            return None
+        part = items[coups[0]].prep["mask"]
+        for i in coups:
+            m = items[i].prep["mask"]
+            if m.shape != part.shape or not (torch.equal(m, part) or torch.equal(m, 1 - part)):
+                return None
+            # every block of consecutive couplings must be bounded by dense affine steps on both sides
+            j = i
+            while j >= 0 and items[j].kind == "coupling":
+                j -= 1
+            k = i
+            while k < len(items) and items[k].kind == "coupling":
+                k += 1
+            if j < 0 or k >= len(items) or items[j].kind != "aff" or items[k].kind != "aff":
+                return None
+        idx1 = torch.nonzero(part > 0.5).reshape(-1)
+        idx0 = torch.nonzero(part <= 0.5).reshape(-1)
+        h1, h0 = int(idx1.numel()), int(idx0.numel())
+        if h1 == 0 or h0 == 0:
+            return None
+        if self.mode != "fp32_simt" and (h1 % 8 or h0 % 8):
+            return None
+        return dict(part=part, idx1=idx1, idx0=idx0, order=torch.cat([idx1, idx0]), h1=h1, h0=h0)
+
+    def _emit(self, items, compress) -> List[Step]:
+        mode = self.mode
+        steps: List[Step] = []
+        n = len(items)
+        for i, p in enumerate(items):
+            if p.kind == "aff":
+                W, c = p.W, p.c
+                if compress is not None:
+                    if i > 0 and items[i - 1].kind == "coupling":
+                        W = W[:, compress["order"]]
+                    if i + 1 < n and items[i + 1].kind == "coupling":
+                        W = W[compress["order"]]
+                        c = None if c is None else c[compress["order"]]
+                N, K = W.shape
+                eng = _engine_for(mode, N, K)
+                w, w_lo = _operand(W, mode, eng)
+                bias = None if c is None else c.to(torch.float32).contiguous()
+                steps.append(Step("mm", w=w, w_lo=w_lo, N=N, K=K, engine=eng, bias=bias))
+            elif p.kind == "coupling":
+                ws, bs, mask = p.prep["weights"], p.prep["biases"], p.prep["mask"]
+                nl = len(ws)
+                in_seg = out_seg = None
+                if compress is not None:
+                    first = torch.equal(mask, compress["part"])       # conditioner reads the idx1 features
+                    idx_in = compress["idx1"] if first else compress["idx0"]
+                    idx_out = compress["idx0"] if first else compress["idx1"]
+                    h1, h0 = compress["h1"], compress["h0"]
+                    in_seg = (0, h1) if first else (h1, h0)
+                    out_seg = (h1, h0) if first else (0, h1)
+                    ws = list(ws)
+                    bs = list(bs)
+                    ws[0] = ws[0][:, idx_in]
+                    ws[-1] = ws[-1][idx_out]
+                    bs[-1] = bs[-1][idx_out]
+                else:                                                   # fold the mask into the first / last Linear
+                    m = mask.reshape(-1).to(torch.float32)
+                    ws = list(ws)
+                    bs = list(bs)
+                    ws[0] = ws[0] * m[None, :]
+                    ws[-1] = ws[-1] * (1 - m)[:, None]
+                    bs[-1] = bs[-1] * (1 - m)
+                for j in range(nl):
+                    last = j == nl - 1
+                    N, K = ws[j].shape
+                    eng = _engine_for(mode, N, K)
+                    w, w_lo = _operand(ws[j], mode, eng)
+                    steps.append(Step("mm", src="x" if j == 0 else "h", dst="x" if last else "h", w=w, w_lo=w_lo,
+                                      N=N, K=K, engine=eng, bias=bs[j].to(torch.float32).contiguous(), relu=not last,
+                                      resid=last, sign=p.sign, in_seg=in_seg if j == 0 else None,
+                                      out_seg=out_seg if last else None))
+            elif p.kind == "mul":
+                steps.append(Step("vec", vec_mul=p.v))
+            elif p.kind == "div":
+                steps.append(Step("vec", vec_div=p.v))
+            elif p.kind == "perm":
+                steps.append(Step("permute", perm=p.v.to(torch.int32)))
+            elif p.kind == "leaky":
+                steps.append(Step("leaky", slope=p.slope))
+        if not steps:
+            steps.append(Step("vec"))
+        last_x = max(i for i, st in enumerate(steps) if st.dst == "x")
+        steps[last_x].final = True
+        return steps
+
+    # ----------------------------------------------------------------------------------------------
+    def out_width(self, d_in: int) -> int:
+        w = d_in
+        for st in self.steps:
+            if st.kind == "mm" and st.dst == "x" and st.out_seg is None:
+                w = st.N
+        return w
+
+    def n_launches(self) -> int:
+        return len(self.steps)
+
+    def run(self, x: torch.Tensor, mode: Optional[str] = None, chunk_rows: Optional[int] = None,
+            out: Optional[torch.Tensor] = None, sink=None) -> Optional[torch.Tensor]:
+        """Evaluate the program on x [rows, d].  With `sink`, the final stream value of each chunk is handed
+        to `sink(chunk_f32 [r, width], r0, r1)` from a reused workspace buffer instead of being stored."""
+        ops.require_cuda(x, "input")
+        if x.dim() != 2:
+            raise RuntimeError("usflows_b200: expected a [rows, d] input")
+        x = x.contiguous()
+        rows = x.shape[0]
+        width = self.out_width(x.shape[1])
+        if rows == 0:                       # empty batch: nothing to launch
+            return None if sink is not None else torch.empty(0, width, dtype=torch.float32, device=x.device)
+        cap = chunk_rows or _default_chunk_rows
+        n_chunks = (rows + cap - 1) // cap
+        chunk = min(rows, ((rows + n_chunks - 1) // n_chunks + 255) // 256 * 256)
+        if sink is not None:
+            for r0 in range(0, rows, chunk):
+                r1 = min(rows, r0 + chunk)
+                fin = _workspace.planes(x.device, "final", r1 - r0, width, "f32")
+                self._run_chunk(x[r0:r1], fin)
+                sink(fin, r0, r1)
+            return None
+        if out is None:
+            out = torch.empty(rows, width, dtype=torch.float32, device=x.device)
+        for r0 in range(0, rows, chunk):
+            r1 = min(rows, r0 + chunk)
+            self._run_chunk(x[r0:r1], out[r0:r1])
+        return out
+
+    def _stream_planes(self) -> set:
+        return {"fp32": {"hi", "lo"}, "bf16": {"bf16", "f32"}}.get(self.mode, {"f32"})
+
+    def _hidden_planes(self) -> set:
+        return {"fp32": {"hi", "lo"}, "bf16": {"bf16"}}.get(self.mode, {"f32"})
+
+    def _run_chunk(self, x: torch.Tensor, final_out: torch.Tensor) -> None:
+        dev, rows = x.device, x.shape[0]
+        steps = self.steps
+        flip = {"x": 0, "h": 0}
+        cur: Optional[Act] = None               # stream
+        hid: Optional[Act] = None               # conditioner hidden
+
+        def new_act(slot: str, width: int, planes: set) -> Act:
+            flip[slot] ^= 1
+            a = Act(rows, width)
+            for pl in planes:
+                setattr(a, pl, _workspace.planes(dev, f"{slot}{flip[slot]}", rows, width, pl))
+            return a
+
+        def seg_view(a: Act, seg) -> Act:
+            if seg is None:
+                return a
+            c0, w = seg
+            v = Act(a.rows, w)
+            for pl in ("f32", "hi", "lo", "bf16"):
+                t = getattr(a, pl)
+                if t is not None:
+                    setattr(v, pl, t[:, c0:c0 + w])
+            return v
+
+        src_f32 = Act(rows, x.shape[1], f32=x)   # the user's tensor: read-only
+        cur = src_f32
+        for i, st in enumerate(steps):
+            nxt = steps[i + 1] if i + 1 < len(steps) else None
+            if st.kind == "mm":
+                if st.src == "x":
+                    in_coupling = st.dst == "h" or st.resid
+                    need = self._stream_planes() if in_coupling else self._operand_planes()
+                    direct_ok = st.engine == ENGINE_SIMT or (x.data_ptr() % 16 == 0 and x.stride(0) % 4 == 0)
+                    if not all(getattr(cur, pl) is not None for pl in need) or (cur is src_f32 and not direct_ok):
+                        if cur.f32 is None:
+                            raise RuntimeError("internal: activation has no fp32 plane to re-encode from")
+                        b = new_act("x", cur.width, need)
+                        ops.ingest(cur.f32, b)
+                        cur = b
+                    a = seg_view(cur, st.in_seg)
+                else:
+                    a = hid
+                if st.dst == "h":
+                    out = new_act("h", st.N, self._hidden_planes())
+                    resid = None
+                elif st.resid:                                         # coupling output
+                    if st.out_seg is not None:                         # in place on the updated column segment
+                        out = seg_view(cur, st.out_seg)
+                        resid = out
+                        full_out = cur
+                    else:
+                        resid = cur
+                        out = new_act("x", st.N, self._stream_planes())
+                        full_out = out
+                    if st.final:
+                        if st.out_seg is not None:
+                            raise RuntimeError("internal: a compressed coupling cannot be the final step")
+                        out = Act(rows, st.N, f32=final_out)
+                        full_out = out
+                    elif nxt is not None and nxt.kind in ("leaky", "permute", "vec") and full_out.f32 is None:
+                        out.f32 = _workspace.planes(dev, "xf", rows, st.N, "f32")
+                else:                                                  # affine step
+                    resid = None
+                    if st.final:
+                        out = Act(rows, st.N, f32=final_out)
+                    else:
+                        planes = set(self._stream_planes())
+                        if nxt is not None and nxt.kind in ("leaky", "permute", "vec"):
+                            planes = {"f32"}
+                        out = new_act("x", st.N, planes)
+                    full_out = out
+                ops.linear(st.engine, a, st.w, st.w_lo, st.N, st.K, bias=st.bias, relu=st.relu, resid=resid,
+                           resid_sign=st.sign, out=out)
+                if st.dst == "h":
+                    hid = out
+                else:
+                    cur = full_out
+            else:                                                      # elementwise kernels on the fp32 plane
+                if cur.f32 is None:
+                    raise RuntimeError("internal: elementwise step needs an fp32 stream plane")
+                out = Act(rows, cur.width, f32=final_out) if st.final else new_act("x", cur.width, {"f32"})
+                if st.kind == "vec":
+                    ops.ingest(cur.f32, out, div=st.vec_div, mul=st.vec_mul)
+                elif st.kind == "leaky":
+                    ops.leaky_relu(cur.f32, st.slope, out.f32)
+                else:
+                    ops.permute(cur.f32, st.perm, out.f32)
+                cur = out
+
+    def _operand_planes(self) -> set:
+        return {"fp32": {"hi", "lo"}, "bf16": {"bf16"}}.get(self.mode, {"f32"})
+
+    @classmethod
+    def from_steps(cls, steps: List[Step], mode: str) -> "Program":
+        prog = cls.__new__(cls)
+        prog.mode, prog.items, prog.compress, prog.steps = mode, [], None, steps
+        return prog
+
+
 # --------------------------------------------------------------------------------------------------
-# workspace + execution
+# workspace
 # --------------------------------------------------------------------------------------------------
 class _Workspace:
-    """Two stream buffers (x) and two hidden buffers (h) per device, each with the planes a mode needs."""
+    """Reusable device buffers keyed by (device, slot name, plane)."""
 
     def __init__(self):
         self._bufs = {}
@@ -201,167 +504,8 @@ class _Workspace:
             self._bufs[key] = buf
         return buf[:need].view(rows, ld)[:, :width]
 
-    def act(self, device, name: str, rows: int, width: int, mode: str, needs: set) -> Act:
-        a = Act(rows, width)
-        want_op = "op" in needs
-        want_res = "resid" in needs
-        want_f32 = "f32" in needs or "final" in needs
-        if mode == "fp32":
-            if want_op or want_res:
-                a.hi = self.planes(device, name, rows, width, "hi")
-                a.lo = self.planes(device, name, rows, width, "lo")
-            if want_f32:
-                a.f32 = self.planes(device, name, rows, width, "f32")
-        elif mode == "bf16":
-            if want_op:
-                a.bf16 = self.planes(device, name, rows, width, "bf16")
-            if want_res or want_f32 or "simt" in needs:
-                a.f32 = self.planes(device, name, rows, width, "f32")
-        else:
-            a.f32 = self.planes(device, name, rows, width, "f32")
-        if a.f32 is None and a.hi is None and a.bf16 is None:
-            a.f32 = self.planes(device, name, rows, width, "f32")
-        return a
-
 
 _workspace = _Workspace()
-
-
-def _run_steps(steps: List[Step], x: torch.Tensor, mode: str, final_out: torch.Tensor) -> Act:
-    """Run the program over one chunk of rows; the final stream value lands in `final_out` (fp32)."""
-    dev, rows = x.device, x.shape[0]
-    slots = {}
-    flip = {"x": 0, "h": 0}
-    last_x = max(i for i, st in enumerate(steps) if st.dst == "x")
-
-    def new_act(slot: str, width: int, needs: set, idx: int) -> Act:
-        flip[slot] ^= 1
-        a = _workspace.act(dev, f"{slot}{flip[slot]}", rows, width, mode, needs)
-        if idx == last_x:
-            a.f32 = final_out
-        return a
-
-    for i, st in enumerate(steps):
-        if st.kind == "vec":
-            if i == 0:
-                src = x
-            else:
-                cur = slots["x"]
-                if cur.f32 is None:
-                    raise RuntimeError("internal: vec step needs an fp32 stream plane")
-                src = cur.f32
-            out = new_act("x", src.shape[1], st.needs, i)
-            ops.ingest(src, out, div=st.vec_div, mul=st.vec_mul, sub=st.vec_sub)
-            slots["x"] = out
-        elif st.kind == "mm":
-            a = slots[st.src]
-            N, K = st.w.shape
-            eng = _engine_for(mode, N, K)
-            wmode = "fp32" if mode == "fp32" else ("bf16" if eng == ENGINE_TC_BF16 else "tf32")
-            w, w_lo = _operands.get(st.w, wmode)
-            if eng == ENGINE_SIMT and mode == "bf16":
-                a_use = Act(a.rows, a.width, f32=a.f32) if a.f32 is not None else None
-                if a_use is None:
-                    raise RuntimeError("internal: SIMT step in bf16 mode needs an fp32 plane")
-                a = a_use
-            resid = slots["x"] if st.resid else None
-            if st.resid and st.dst == "x" and st.src != "x":
-                # in place on the stream buffer is safe (each element is read and written by one thread),
-                # but the planes the consumer needs may differ: allocate per `needs` on the same buffer
-                out = _workspace.act(dev, f"x{flip['x']}", rows, N, mode, st.needs)
-                if i == last_x:
-                    out.f32 = final_out
-            else:
-                out = new_act(st.dst, N, st.needs, i)
-            ops.linear(eng, a, w, w_lo, N, K, bias=st.bias, relu=st.relu, resid=resid, resid_sign=st.sign,
-                       colscale=st.colscale, postsub=st.postsub, out=out)
-            slots[st.dst] = out
-        elif st.kind == "leaky":
-            cur = slots["x"]
-            out = new_act("x", cur.width, {"f32"}, i)
-            ops.leaky_relu(cur.f32, st.slope, out.f32)
-            slots["x"] = out
-        elif st.kind == "permute":
-            cur = slots["x"]
-            out = new_act("x", cur.width, {"f32"}, i)
-            ops.permute(cur.f32, st.perm, out.f32)
-            slots["x"] = out
-        else:
-            raise RuntimeError(st.kind)
-    return slots["x"]
-
-
-def _needs_reingest(steps: List[Step]) -> List[Step]:
-    """leaky/permute write only an fp32 plane; a following contraction needs operand planes -> insert ingest."""
-    out: List[Step] = []
-    for st in steps:
-        if st.kind == "mm" and st.src == "x" and out and out[-1].kind in ("leaky", "permute"):
-            out.append(Step("vec"))
-        out.append(st)
-    return out
-
-
-class Program:
-    def __init__(self, layers, direction: str):
-        steps: List[Step] = []
-        seq = list(layers) if direction == "forward" else list(reversed(list(layers)))
-        for layer in seq:
-            _emit_layer(layer, direction, steps)
-        steps = _needs_reingest(_fuse(steps))
-        if not steps or steps[0].kind != "vec":
-            steps.insert(0, Step("vec"))
-        for i, st in enumerate(steps):
-            needs = set()
-            for nxt in steps[i + 1:]:
-                if nxt.kind == "mm":
-                    if nxt.src == st.dst:
-                        needs.add("op")
-                        if min(nxt.w.shape) < TC_MIN_DIM:
-                            needs.add("simt")       # SIMT engine reads fp32-accurate planes
-                    if nxt.resid and st.dst == "x":
-                        needs.add("resid")
-                    if nxt.dst == st.dst:
-                        break
-                elif st.dst == "x":
-                    needs.add("f32")
-                    break
-            st.needs = needs
-        self.steps = steps
-
-    def run(self, x: torch.Tensor, mode: Optional[str] = None, chunk_rows: Optional[int] = None,
-            out: Optional[torch.Tensor] = None, sink=None) -> Optional[torch.Tensor]:
-        """Evaluate the program on x [rows, d].  With `sink`, the final stream value of each chunk is handed
-        to `sink(chunk_f32 [r, width], r0, r1)` from a reused workspace buffer instead of being stored."""
-        mode = mode or _default_precision
-        ops.require_cuda(x, "input")
-        if x.dim() != 2:
-            raise RuntimeError("usflows_b200: expected a [rows, d] input")
-        x = x.contiguous()
-        rows = x.shape[0]
-        width = self.out_width(x.shape[1])
-        chunk = min(chunk_rows or _default_chunk_rows, max(rows, 1))
-        if rows == 0:                       # empty batch: nothing to launch
-            return None if sink is not None else torch.empty(0, width, dtype=torch.float32, device=x.device)
-        if sink is not None:
-            for r0 in range(0, rows, chunk):
-                r1 = min(rows, r0 + chunk)
-                fin = _workspace.planes(x.device, "final", r1 - r0, width, "f32")
-                _run_steps(self.steps, x[r0:r1], mode, fin)
-                sink(fin, r0, r1)
-            return None
-        if out is None:
-            out = torch.empty(rows, width, dtype=torch.float32, device=x.device)
-        for r0 in range(0, rows, chunk):
-            r1 = min(rows, r0 + chunk)
-            _run_steps(self.steps, x[r0:r1], mode, out[r0:r1])
-        return out
-
-    def out_width(self, d_in: int) -> int:
-        w = d_in
-        for st in self.steps:
-            if st.kind == "mm" and st.dst == "x":
-                w = st.w.shape[0]
-        return w
 
 
 # --------------------------------------------------------------------------------------------------
@@ -370,32 +514,35 @@ class Program:
 def _flatten_rows(x: torch.Tensor, event_ndim: int = 1):
     ops.require_cuda(x, "input")
     batch_shape = x.shape[:x.dim() - event_ndim]
-    return x.reshape(max(1, math.prod(batch_shape)), -1), batch_shape
+    return x.reshape(math.prod(batch_shape), math.prod(x.shape[x.dim() - event_ndim:])), batch_shape
 
 
 def run_layers(layers, direction: str, x: torch.Tensor, mode: Optional[str] = None,
                chunk_rows: Optional[int] = None) -> torch.Tensor:
     x2, batch_shape = _flatten_rows(x)
     with torch.no_grad():
-        y = Program(layers, direction).run(x2, mode, chunk_rows)
+        y = Program(layers, direction, mode).run(x2, chunk_rows=chunk_rows)
     return y.reshape(*batch_shape, y.shape[-1]) if x.dim() != 2 else y
 
 
 def run_mlp(net, x: torch.Tensor, mode: Optional[str] = None) -> torch.Tensor:
     """Plain evaluation of a DenseNN (no mask, no residual) through the contraction kernels."""
     x2, batch_shape = _flatten_rows(x)
+    mode = mode or _default_precision
     lin = list(net.layers)
-    steps = [Step("vec")]
+    if min(min(l.weight.shape) for l in lin) < TC_MIN_DIM:
+        mode = "fp32_simt"
+    steps = []
     for j, l in enumerate(lin):
         last = j == len(lin) - 1
-        steps.append(Step("mm", src="x" if j == 0 else "h", dst="x" if last else "h",
-                          w=l.weight.detach(), bias=l.bias.detach(), relu=not last))
-    prog = Program([], "forward")
-    prog.steps = steps
-    for i, st in enumerate(steps):
-        st.needs = {"op"} if i < len(steps) - 1 else set()
+        N, K = l.weight.shape
+        eng = _engine_for(mode, N, K)
+        w, w_lo = _operand(l.weight.detach(), mode, eng)
+        steps.append(Step("mm", src="x" if j == 0 else "h", dst="x" if last else "h", w=w, w_lo=w_lo, N=N, K=K,
+                          engine=eng, bias=l.bias.detach().contiguous(), relu=not last, final=last))
+    prog = Program.from_steps(steps, mode)
     with torch.no_grad():
-        y = prog.run(x2, mode)
+        y = prog.run(x2)
     return y.reshape(*batch_shape, y.shape[-1]) if x.dim() != 2 else y
 
 

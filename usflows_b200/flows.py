@@ -19,6 +19,9 @@ from .transforms import (BaseTransform, BlockAffineTransform, HouseholderTransfo
                          MaskedCoupling, ScaleTransform, SequentialAffineTransform)
 
 
+HOST_CHUNK_ROWS = 16384      # rows per H2D copy / kernel batch of `log_prob_host` (copy i+1 overlaps compute i)
+
+
 class Flow(torch.nn.Module):
     """Base flow: a list of bijective layers over a base distribution (flows.py:22-292)."""
 
@@ -81,7 +84,7 @@ class Flow(torch.nn.Module):
             ops.base_logprob(ops.Act(r1 - r0, d, f32=z_chunk), loc, scale, base.base_kind, -ladj, out[r0:r1])
 
         with torch.no_grad():
-            prog.run(x2, self.precision, sink=sink)
+            prog.run(x2, sink=sink)
         return out.reshape(batch_shape)
 
     def log_prob_host(self, x_host: torch.Tensor, out_host: Optional[torch.Tensor] = None,
@@ -99,7 +102,7 @@ class Flow(torch.nn.Module):
         rows, d = x2.shape
         if out_host is None:
             out_host = torch.empty(rows, dtype=torch.float32, pin_memory=True)
-        chunk = min(chunk_rows or engine._default_chunk_rows, max(rows, 1))
+        chunk = min(chunk_rows or HOST_CHUNK_ROWS, max(rows, 1))
         if getattr(self, "_host_bufs", None) is None or self._host_bufs[0].shape != (chunk, d) \
                 or self._host_bufs[0].device != dev:
             self._host_bufs = [torch.empty(chunk, d, dtype=torch.float32, device=dev) for _ in range(2)]
@@ -128,7 +131,7 @@ class Flow(torch.nn.Module):
                     ops.base_logprob(ops.Act(b - a, d, f32=z_chunk), loc, scale, base.base_kind, -ladj,
                                      out_dev[r0 + a:r0 + b])
 
-                prog.run(buf, self.precision, chunk_rows=chunk, sink=sink)
+                prog.run(buf, chunk_rows=chunk, sink=sink)
                 consumed[i & 1].record(main)
             out_host.reshape(-1)[:rows].copy_(out_dev, non_blocking=True)
             main.synchronize()
@@ -183,10 +186,12 @@ class Flow(torch.nn.Module):
 
     def _program(self, direction: str):
         """(Program, total forward log|det J|) for the current weight version."""
-        key = self._weights_key()
+        mode = self.precision or engine.get_precision()
+        key = (mode,) + self._weights_key()
         hit = self._programs.get(direction)
         if hit is None or hit[0] != key:
-            prog = engine.Program(self.layers, direction)
+            with torch.no_grad():
+                prog = engine.Program(self.layers, direction, mode)
             ladj, n_bad = engine.total_ladj(self.layers)
             hit = (key, prog, ladj, n_bad)
             self._programs[direction] = hit
@@ -196,7 +201,7 @@ class Flow(torch.nn.Module):
         prog, _ = self._program(direction)
         x2, batch_shape = engine._flatten_rows(x, len(self._event_shape()))
         with torch.no_grad():
-            y = prog.run(x2, self.precision)
+            y = prog.run(x2)
         return y.reshape(*batch_shape, *self._event_shape())
 
 

@@ -186,3 +186,11 @@ def matmul_f32(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, bias=None) -
     M, K = a.shape
     N = b.shape[1]
     linear(ENGINE_SIMT, Act(M, K, f32=a), b, None, N, K, bias=bias, out=Act(M, N, f32=out), trans_w=True)
+
+
+def matmul_f64(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor) -> None:
+    """out = a @ b in fp64 (weight composition, once per weight version)."""
+    M, K = a.shape
+    N = b.shape[1]
+    assert a.dtype == b.dtype == out.dtype == torch.float64 and b.shape[0] == K and out.shape == (M, N)
+    check(_lib.load().usf_matmul_f64(_ptr(a), _ld(a), _ptr(b), _ld(b), _ptr(out), _ld(out), M, N, K, _stream()))

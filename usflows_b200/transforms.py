@@ -26,6 +26,12 @@ def _versions(params) -> tuple:
     return tuple((p.data_ptr(), p._version) for p in params)
 
 
+def _mm64(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    out = torch.empty(a.shape[0], b.shape[1], dtype=torch.float64, device=a.device)
+    ops.matmul_f64(a.contiguous(), b.contiguous(), out)
+    return out
+
+
 class BaseTransform(nn.Module):
     """Contract of every layer (reference transforms.py:23-69)."""
 
@@ -254,8 +260,10 @@ class LUTransform(AffineTransform):
         ops.matmul_f32(Uinv, Linv, Winv)                                       # U^-1 @ L^-1 (:1293)
         ladj = new(2)
         ops.lu_logabsdet(self.U_raw.detach(), ladj)                            # sum log|diag U| (:1303-1320)
+        # fp64 products of the same factors: what the engine composes neighbouring affine layers from
+        W64, Winv64 = _mm64(L.double(), U.double()), _mm64(Uinv.double(), Linv.double())
         return dict(matrix=W, inverse_matrix=Winv, bias=self.bias_vector.detach(), ladj=ladj,
-                    L=L, U=U, L_inv=Linv, U_inv=Uinv)
+                    L=L, U=U, L_inv=Linv, U_inv=Uinv, matrix64=W64, inverse64=Winv64)
 
     @property
     def L(self) -> torch.Tensor:
@@ -310,7 +318,7 @@ class HouseholderTransform(AffineTransform):
         Wt = torch.empty(d, d, dtype=torch.float32, device=dev)
         ops.transpose(W, Wt)                                                               # :864-868
         return dict(matrix=W, inverse_matrix=Wt, bias=torch.zeros(d, dtype=torch.float32, device=dev),
-                    ladj=torch.zeros(2, dtype=torch.float32, device=dev))
+                    ladj=torch.zeros(2, dtype=torch.float32, device=dev), matrix64=W.double(), inverse64=Wt.double())
 
 
 class SequentialAffineTransform(AffineTransform):
@@ -346,7 +354,12 @@ class SequentialAffineTransform(AffineTransform):
             ops.matmul_f32(b.reshape(1, d), p["matrix"], out, bias=p["bias"])
             b = out.reshape(d)
         ladj = torch.stack([p["ladj"] for p in parts]).sum(0)                  # :1429-1446
-        return dict(matrix=M, inverse_matrix=Minv, bias=b, ladj=ladj)
+        M64, Minv64 = parts[0]["matrix64"], parts[-1]["inverse64"]
+        for p in parts[1:]:
+            M64 = _mm64(M64, p["matrix64"])
+        for p in parts[-2::-1]:
+            Minv64 = _mm64(Minv64, p["inverse64"])
+        return dict(matrix=M, inverse_matrix=Minv, bias=b, ladj=ladj, matrix64=M64, inverse64=Minv64)
 
     def is_feasible(self) -> bool:
         return all(t.is_feasible() for t in self.transforms)
@@ -453,6 +466,16 @@ class MaskedCoupling(BaseTransform):
     def to(self, device):
         self.mask = self.mask.to(device)
         return super().to(device)
+
+    def _raw(self) -> dict:
+        """Conditioner weights / biases and the flat mask, for the engine's planner (which either folds the mask
+        into the first / last Linear or re-orders the features so both halves are contiguous)."""
+        lin = list(self.conditioner.layers)
+        for l in lin:
+            ops.require_cuda(l.weight, "conditioner parameter")
+        dev = lin[0].weight.device
+        return dict(weights=[l.weight.detach() for l in lin], biases=[l.bias.detach() for l in lin],
+                    mask=self.mask.to(dev).reshape(-1).to(torch.float32))
 
     def _prepared(self) -> dict:
         """Mask folded into the first / last Linear: (x*m) W1^T = x (W1 diag(m))^T and
