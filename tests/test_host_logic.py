@@ -34,9 +34,9 @@ def test_bf16_mode_runs_with_its_own_bound(fake_ops):
 
 
 def test_kernel_count_per_log_prob(fake_ops):
-    """one ingest + (B+1) merged affine contractions + 3B conditioner contractions + one base-density reduction
-    for a conjugated USFlow with B blocks: Aff_i^-1 . Aff_{i+1} pairs and the trailing Scale are composed into one
-    operator each (the reference runs 2B+1 affine layers + Scale)."""
+    """one ingest + (2B+1) affine contractions (Scale folded into the first) + 3B conditioner contractions + one
+    base-density reduction for a conjugated USFlow with B blocks; with `MERGE_AFFINE` the Aff_i^-1 . Aff_{i+1}
+    pairs become one operator each (B+1 affine contractions)."""
     spec, params, arr = load_case("d100_h50_hh")
     flow = build_flow(spec, params, device="cpu", precision="fp32")
     flow.log_prob(arr["x"])               # includes weight preparation
@@ -46,7 +46,18 @@ def test_kernel_count_per_log_prob(fake_ops):
     B = spec["coupling_blocks"]
     assert spec["affine_conjugation"] and len(spec["hidden_dims"]) == 2
     assert kinds.count("ingest") == 1 and kinds.count("base_logprob") == 1
-    assert kinds.count("linear") == (B + 1) + 3 * B
+    assert kinds.count("linear") == (2 * B + 1) + 3 * B
+    from usflows_b200 import engine
+    engine.MERGE_AFFINE = True
+    try:
+        merged = build_flow(spec, params, device="cpu", precision="fp32")
+        lp = merged.log_prob(arr["x"])
+        fake_backend.CALLS.clear()
+        merged.log_prob(arr["x"])
+        assert [c[0] for c in fake_backend.CALLS].count("linear") == (B + 1) + 3 * B
+        assert rel_err(lp, arr["lp32"]) < 5e-5
+    finally:
+        engine.MERGE_AFFINE = False
 
 
 def test_mask_compression_halves_the_outer_conditioner_contractions(fake_ops):
@@ -59,7 +70,7 @@ def test_mask_compression_halves_the_outer_conditioner_contractions(fake_ops):
     flow.log_prob(arr["x"][:4])
     shapes = [(c[3], c[4]) for c in fake_backend.CALLS if c[0] == "linear"]      # (N, K)
     H = spec["hidden_dims"][0]
-    assert shapes.count((784, 784)) == spec["coupling_blocks"] + 1
+    assert shapes.count((784, 784)) == 2 * spec["coupling_blocks"] + 1
     assert shapes.count((H, 392)) == spec["coupling_blocks"] and shapes.count((392, H)) == spec["coupling_blocks"]
 
 
