@@ -237,6 +237,12 @@ def main():
     launches = ops.LAUNCHES
     value = world * rows / (ms_step * 1e-3)
 
+    # the sampling pass (latent -> data) of the same model and batch size: base draws + forward layer stack
+    sample_step = lambda: flow.sample([rows])          # noqa: E731
+    for _ in range(max(1, args.warmup // 2)):
+        sample_step()
+    ms_sample = timed(sample_step, max(2, args.steps // 2))
+
     # end to end: pinned host rows in, host log-probs out, copies inside the timed region
     e2e_step = lambda: flow.log_prob_host(x_host, out_host)   # noqa: E731
     for _ in range(max(1, args.warmup // 2)):
@@ -300,6 +306,9 @@ def main():
         cpu_baseline=cpu,
         e2e=dict(value=world * rows / (ms_e2e * 1e-3), unit="samples/s", ms_per_step=ms_e2e,
                  h2d_bytes_per_step=rows * d * 4, d2h_bytes_per_step=rows * 4),
+        sample=dict(metric="sample_samples_per_sec", value=world * rows / (ms_sample * 1e-3), unit="samples/s",
+                    ms_per_step=ms_sample, tflops=rows * flops_per_sample / (ms_sample * 1e-3) / 1e12,
+                    note="Flow.sample([rows]): Philox base draws + forward pass; same algorithmic FLOPs per sample"),
         gpu_launches=launches, clocks=clocks, modes=extra_modes,
         breakdown_ms={k: v for k, v in breakdown.items() if not k.startswith("_")})
     print(json.dumps(line), flush=True)

@@ -12,3 +12,4 @@ print(f"e2e {e.get('value', 0):.4g} ({e.get('ms_per_step', 0):.2f} ms)  cpu {((d
 print("modes", {k: (round(v["value"]), round(v["tflops"], 1), v["max_rel_diff_vs_fp32_mode"]) for k, v in (d.get("modes") or {}).items()})
 print("breakdown", {k: round(v, 3) for k, v in (d.get("breakdown_ms") or {}).items()})
 print("clocks", d.get("clocks"))
+print("sample", d.get("sample"))

@@ -141,7 +141,9 @@ __device__ __forceinline__ void philox4x32_10(uint64_t seed, uint64_t ctr_lo, ui
   }
   out[0] = c[0]; out[1] = c[1]; out[2] = c[2]; out[3] = c[3];
 }
-__device__ __forceinline__ float u01_open(uint32_t x) { return ((float)(x >> 8) + 0.5f) * (1.0f / 16777216.0f); }  // (0,1)
+// 23 random bits + 1/2: every value is exactly representable in fp32, so the result stays inside (0,1)
+// (24 bits + 1/2 would round up to 1.0 for the top value and give log1p(-1) = -inf in the Laplace inverse CDF)
+__device__ __forceinline__ float u01_open(uint32_t x) { return ((float)(x >> 9) + 0.5f) * (1.0f / 8388608.0f); }
 
 __global__ void __launch_bounds__(256)
 base_sample_kernel(long long rows, int d, const float* __restrict__ loc, const float* __restrict__ scale, int kind,
