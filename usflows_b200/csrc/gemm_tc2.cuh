@@ -52,8 +52,11 @@ __device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
   return r;
 }
+// remote arrive.  No cluster-scope release: the only thing handed over is TMEM ownership, which is ordered by the
+// tcgen05 fences; a .release.cluster arrive compiles to a full ERRBAR fence per call (22% of all stall samples
+// of the first version of this kernel, profiles/r01_full_gemm_v2_fp32.md)
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1) {
   asm volatile(
