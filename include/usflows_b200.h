@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define USF_ABI_VERSION 1
+#define USF_ABI_VERSION 2
 
 #define USF_OK 0
 #define USF_ERR_INVALID (-1)     /* bad argument (shape, alignment, null pointer) */
@@ -35,6 +35,9 @@ extern "C" {
 #define USF_ENGINE_TC_3XTF32 1 /* tcgen05 kind::tf32, 3-term split (hi*hi + lo*hi + hi*lo): ~fp32 accuracy */
 #define USF_ENGINE_TC_TF32 2   /* tcgen05 kind::tf32, single pass                                      */
 #define USF_ENGINE_TC_BF16 3   /* tcgen05 kind::f16 (bf16 operands), fp32 accumulate                   */
+#define USF_ENGINE_TC_3XF16 4  /* tcgen05 kind::f16, fp16 split x = hi + lo'*2^-11 (3 products, the cross terms rescaled
+                                  in the accumulator by scale-input-d): ~fp32 accuracy at twice the tf32 rate; values
+                                  with |x| > 65000 raise the caller's overflow flag (re-run with TC_3XTF32)           */
 
 /* base distributions (distributions.py:199-238) */
 #define USF_BASE_LAPLACE 0
@@ -58,7 +61,9 @@ int usf_device_info(int* sm_count, int* cc_major, int* cc_minor, int64_t* l2_byt
  *   TC_3XTF32 a, a_lo, w, w_lo: fp32 storage holding tf32-representable values (x = hi + lo)
  *   TC_TF32   a, w fp32 (low 13 mantissa bits ignored by the tensor core)
  *   TC_BF16   a, w bf16
- * tcgen05 engines need 16-byte aligned operand pointers and lda/ldw multiples of 4 (8 for bf16).
+ *   TC_3XF16  a, a_lo, w, w_lo: fp16 planes (hi, lo' = (x - hi) * 2^11); outputs in out_h16/out_l16, residual
+ *             from resid_h16/resid_l16 (or the fp32 `resid`)
+ * tcgen05 engines need 16-byte aligned operand pointers and lda/ldw multiples of 4 (8 for bf16 / fp16).
  */
 typedef struct usf_linear_args {
   int64_t M;
@@ -87,6 +92,14 @@ typedef struct usf_linear_args {
   int64_t ld_split;
   void* out_bf16;
   int64_t ld_bf16;
+  /* fp16 split planes (any engine may write them; TC_3XF16 reads them) */
+  const void* resid_h16;
+  const void* resid_l16;
+  int64_t ldr_16;
+  void* out_h16;
+  void* out_l16;
+  int64_t ld_16;
+  int32_t* overflow_flag; /* device int, set to 1 if a value written to out_h16 exceeds the fp16 range */
 } usf_linear_args;
 
 int usf_linear(const usf_linear_args* args, void* stream);
@@ -111,6 +124,10 @@ int usf_debug_set_impl(int impl);
 int usf_ingest(const float* x, int64_t ldx, int64_t rows, int32_t d, const float* div, const float* mul,
                const float* sub, float* out_f32, int64_t ld_f32, float* out_hi, float* out_lo,
                int64_t ld_split, void* out_bf16, int64_t ld_bf16, void* stream);
+/* same, writing the fp16 split planes of the TC_3XF16 engine (+ overflow flag, may be NULL) */
+int usf_ingest_f16(const float* x, int64_t ldx, int64_t rows, int32_t d, const float* div, const float* mul,
+                   const float* sub, void* out_h16, void* out_l16, int64_t ld_16, int32_t* overflow_flag,
+                   void* stream);
 
 /* out[r] = sum_j logpdf_base(z[r,j]; loc[j], scale[j]) + add_const  (z = z_hi [+ z_lo]).
  * Replaces DistributionModule.log_prob (distributions.py:150-151; torch Laplace/Normal.log_prob +
@@ -172,6 +189,9 @@ int usf_split_tf32(const float* in, int64_t rows, int32_t cols, int64_t ld_in, f
                    int64_t ld_out, void* stream);
 int usf_to_bf16(const float* in, int64_t rows, int32_t cols, int64_t ld_in, void* out, int64_t ld_out,
                 void* stream);
+/* fp16 split planes of an fp32 matrix: hi = fp16(x), lo = fp16((x - hi) * 2^11); flag as in usf_ingest_f16 */
+int usf_split_f16(const float* in, int64_t rows, int32_t cols, int64_t ld_in, void* hi, void* lo, int64_t ld_out,
+                  int32_t* overflow_flag, void* stream);
 
 /* W <- W @ (I - 2 v v^T / v.v) in place (one Householder reflection, transforms.py:795-809);
  * `work` = d floats. */

@@ -5,7 +5,7 @@ never importable from the product package."""
 import torch
 
 from usflows_b200 import ops as real_ops
-from usflows_b200.ops import Act, ENGINE_SIMT, ENGINE_TC_3XTF32, ENGINE_TC_BF16, ENGINE_TC_TF32
+from usflows_b200.ops import Act, ENGINE_SIMT, ENGINE_TC_3XF16, ENGINE_TC_3XTF32, ENGINE_TC_BF16, ENGINE_TC_TF32
 
 CALLS = []
 
@@ -16,7 +16,23 @@ def tf32_round(x: torch.Tensor) -> torch.Tensor:
     return i.view(torch.float32)
 
 
-def _store(out: Act, v: torch.Tensor):
+def f16_split(v: torch.Tensor):
+    h = v.to(torch.float16)
+    l = ((v - h.float()) * 2048.0).to(torch.float16)
+    return h, l
+
+
+def f16_join(h, l):
+    return h.float() + l.float() / 2048.0
+
+
+def _store(out: Act, v: torch.Tensor, flag=None):
+    if out.h16 is not None:
+        h, l = f16_split(v)
+        out.h16.copy_(h)
+        out.l16.copy_(l)
+        if flag is not None and bool((~(v.abs() <= 65000.0)).any()):
+            flag.fill_(1)
     if out.f32 is not None:
         out.f32.copy_(v)
     if out.hi is not None:
@@ -28,9 +44,12 @@ def _store(out: Act, v: torch.Tensor):
 
 
 def linear(engine, a, w, w_lo, N, K, *, bias=None, relu=False, resid=None, resid_sign=1.0, colscale=None,
-           postsub=None, out=None, trans_w=False):
+           postsub=None, out=None, trans_w=False, overflow_flag=None):
     CALLS.append(("linear", engine, a.rows, N, K))
-    if engine == ENGINE_TC_BF16:
+    if engine == ENGINE_TC_3XF16:
+        assert a.h16 is not None and w.dtype == torch.float16 and w_lo is not None
+        A, W = f16_join(a.h16, a.l16), f16_join(w, w_lo)
+    elif engine == ENGINE_TC_BF16:
         A = a.bf16.float()
         W = w.float()
     elif engine == ENGINE_TC_3XTF32:
@@ -50,17 +69,20 @@ def linear(engine, a, w, w_lo, N, K, *, bias=None, relu=False, resid=None, resid
     if relu:
         v = torch.relu(v)
     if resid is not None:
-        r, rl = resid.resid_planes()
-        r = r if rl is None else r + rl
+        if resid.f32 is None and resid.hi is None and resid.h16 is not None:
+            r = f16_join(resid.h16, resid.l16)
+        else:
+            r, rl = resid.resid_planes()
+            r = r if rl is None else r + rl
         v = r + resid_sign * v
     if colscale is not None:
         v = v * colscale
     if postsub is not None:
         v = v - postsub
-    _store(out, v)
+    _store(out, v, overflow_flag)
 
 
-def ingest(x, out, *, div=None, mul=None, sub=None):
+def ingest(x, out, *, div=None, mul=None, sub=None, overflow_flag=None):
     CALLS.append(("ingest",))
     v = x
     if div is not None:
@@ -69,7 +91,7 @@ def ingest(x, out, *, div=None, mul=None, sub=None):
         v = v * mul
     if sub is not None:
         v = v - sub
-    _store(out, v)
+    _store(out, v, overflow_flag)
 
 
 def base_logprob(z, loc, scale, kind, add_const, out):
@@ -148,6 +170,14 @@ def split_tf32(a, hi, lo):
         lo.copy_(tf32_round(a - h))
 
 
+def split_f16(a, hi, lo, overflow_flag=None):
+    h, l = f16_split(a)
+    hi.copy_(h)
+    lo.copy_(l)
+    if overflow_flag is not None and bool((~(a.abs() <= 65000.0)).any()):
+        overflow_flag.fill_(1)
+
+
 def to_bf16(a, out):
     out.copy_(a.to(torch.bfloat16))
 
@@ -176,6 +206,6 @@ def require_cuda(t, name="tensor", dtype=torch.float32):
 def install(monkeypatch):
     CALLS.clear()
     for name in ["linear", "ingest", "base_logprob", "base_sample", "leaky_relu", "permute", "lu_assemble",
-                 "lu_logabsdet", "vec_logabs", "tri_inverse", "transpose", "scale_rows_cols", "split_tf32", "to_bf16",
+                 "lu_logabsdet", "vec_logabs", "tri_inverse", "transpose", "scale_rows_cols", "split_tf32", "split_f16", "to_bf16",
                  "householder_right", "softplus", "matmul_f32", "matmul_f64", "require_cuda"]:
         monkeypatch.setattr(real_ops, name, globals()[name])

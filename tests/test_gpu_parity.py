@@ -2,7 +2,8 @@
 against the CPU oracle on seeded inputs.  Run on the B200 box:  python -m pytest tests -m gpu -x -q
 
 Tolerances (norm-wise: max|a-b| / max(max|b|, 1), see helpers.rel_err):
-  fp32 mode (tcgen05 3xTF32 + fp32 promotion)  log_prob <= 1e-5 ; latents / samples <= 3e-5
+  fp32 mode (tcgen05 fp16-split, 3 products + fp32 promotion; tf32-split fallback outside the fp16 range)
+  fp32_tf32 mode (tcgen05 3xTF32 + fp32 promotion)  log_prob <= 1e-5 ; latents / samples <= 3e-5
        -- the reference's own fp32 result sits 1e-6 (log_prob) / 1e-5 (latents) from the fp64 evaluation of
           the same weights (tests/golden/report.json), so tighter agreement between two fp32 paths is noise
   fp32_simt mode (FFMA)                         same bounds
@@ -21,6 +22,7 @@ pytestmark = pytest.mark.gpu
 
 TOL = {  # mode: (log_prob, latent/sample)
     "fp32": (1e-5, 3e-5),
+    "fp32_tf32": (1e-5, 3e-5),
     "fp32_simt": (1e-5, 3e-5),
     "tf32": (2e-2, 3e-2),
     "bf16": (5e-2, 2e-1),
@@ -60,7 +62,7 @@ def test_total_log_det_matches_reference_layers():
     assert rel_err(per_layer, arr["ladj32"]) <= 2e-6
 
 
-@pytest.mark.parametrize("mode", ["fp32", "fp32_simt"])
+@pytest.mark.parametrize("mode", ["fp32", "fp32_tf32", "fp32_simt"])
 def test_against_oracle_on_fresh_seeded_inputs(mode):
     spec = dict(in_dims=[200], coupling_blocks=3, hidden_dims=[256, 192], affine_conjugation=True, lu_transform=2,
                 householder=2, base="normal")
@@ -95,6 +97,19 @@ def test_ragged_and_empty_batches(rows):
     assert lp.shape == (rows,) and z.shape == (rows, 32)
     if rows:
         assert rel_err(lp, O.flow_log_prob(x, spec, params)) <= 1e-5
+
+
+def test_fp16_range_guard_on_device():
+    """|x| > 65000 on the stream: the fp16-split engine flags the chunk and the tf32 split recomputes it."""
+    spec, params, arr = load_case("d100_h50_hh")
+    x = (arr["x"] * 3.0e5).cuda()
+    f16 = build_flow(spec, params, precision="fp32")
+    tf = build_flow(spec, params, precision="fp32_tf32")
+    assert torch.equal(f16.log_prob(x), tf.log_prob(x))
+    assert torch.equal(f16.log_prob_host(x.cpu().pin_memory()), tf.log_prob(x).cpu())
+    xs = arr["x"].cuda()
+    assert not torch.equal(f16.backward(xs), tf.backward(xs))        # different engines in range ...
+    assert rel_err(f16.backward(xs), tf.backward(xs)) <= 1e-5        # ... same accuracy class
 
 
 def test_chunking_and_host_path_do_not_change_results():

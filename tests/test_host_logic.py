@@ -13,7 +13,7 @@ def fake_ops(monkeypatch):
     return fake_backend
 
 
-@pytest.mark.parametrize("mode", ["fp32_simt", "fp32", "tf32"])
+@pytest.mark.parametrize("mode", ["fp32_simt", "fp32", "fp32_tf32", "tf32"])
 @pytest.mark.parametrize("name", SMALL_CASES + ["c2_d784"])
 def test_flow_program_matches_reference(fake_ops, name, mode):
     spec, params, arr = load_case(name)
@@ -72,6 +72,25 @@ def test_mask_compression_halves_the_outer_conditioner_contractions(fake_ops):
     H = spec["hidden_dims"][0]
     assert shapes.count((784, 784)) == 2 * spec["coupling_blocks"] + 1
     assert shapes.count((H, 392)) == spec["coupling_blocks"] and shapes.count((392, H)) == spec["coupling_blocks"]
+
+
+def test_fp16_range_guard_falls_back_to_the_tf32_split(fake_ops):
+    """Inputs that push activations past the fp16 range raise the device flag; the chunk is recomputed with the
+    tf32-split engine, so the result equals the "fp32_tf32" mode bit for bit."""
+    from usflows_b200.ops import ENGINE_TC_3XF16, ENGINE_TC_3XTF32
+    spec, params, arr = load_case("d100_h50_hh")
+    x = arr["x"] * 3.0e5
+    f16 = build_flow(spec, params, device="cpu", precision="fp32")
+    tf = build_flow(spec, params, device="cpu", precision="fp32_tf32")
+    fake_backend.CALLS.clear()
+    lp = f16.log_prob(x)
+    engines = {c[1] for c in fake_backend.CALLS if c[0] == "linear"}
+    assert engines == {ENGINE_TC_3XF16, ENGINE_TC_3XTF32}
+    assert torch.equal(lp, tf.log_prob(x))
+    # in-range inputs never touch the fallback
+    fake_backend.CALLS.clear()
+    f16.log_prob(arr["x"])
+    assert {c[1] for c in fake_backend.CALLS if c[0] == "linear"} == {ENGINE_TC_3XF16}
 
 
 def test_prepared_weights_follow_weight_version(fake_ops):

@@ -19,8 +19,9 @@ import torch  # noqa: E402
 from usflows_b200 import _lib, ops  # noqa: E402
 from usflows_b200.ops import Act  # noqa: E402
 
-ENG = {"simt": ops.ENGINE_SIMT, "3xtf32": ops.ENGINE_TC_3XTF32, "tf32": ops.ENGINE_TC_TF32, "bf16": ops.ENGINE_TC_BF16}
-PASSES = {"simt": 1, "3xtf32": 3, "tf32": 1, "bf16": 1}
+ENG = {"simt": ops.ENGINE_SIMT, "3xtf32": ops.ENGINE_TC_3XTF32, "tf32": ops.ENGINE_TC_TF32, "bf16": ops.ENGINE_TC_BF16,
+       "3xf16": ops.ENGINE_TC_3XF16}
+PASSES = {"simt": 1, "3xtf32": 3, "tf32": 1, "bf16": 1, "3xf16": 3}
 
 
 def make_case(engine, M, N, K, seed, epi, dev="cuda"):
@@ -39,6 +40,13 @@ def make_case(engine, M, N, K, seed, epi, dev="cuda"):
         ref_a, ref_w = ab.double(), wb.double()
         out.bf16 = torch.zeros(M, ldn, dtype=torch.bfloat16, device=dev)[:, :N]
         out.f32 = torch.zeros(M, ldn, device=dev)[:, :N]
+    elif engine == "3xf16":
+        ah, al = torch.zeros(2, M, ldk, dtype=torch.float16, device=dev)[:, :, :K]
+        wh, wl = torch.zeros(2, N, ldk, dtype=torch.float16, device=dev)[:, :, :K]
+        ops.split_f16(af, ah, al); ops.split_f16(wf, wh, wl)
+        act, wt = Act(M, K, h16=ah, l16=al), wh
+        ref_a, ref_w = af.double(), wf.double()
+        out.h16, out.l16 = torch.zeros(2, M, ldn, dtype=torch.float16, device=dev)[:, :, :N]
     elif engine == "3xtf32":
         ah, al = torch.zeros(2, M, ldk, device=dev)[:, :, :K]
         wh, wl = torch.zeros(2, N, ldk, device=dev)[:, :, :K]
@@ -55,7 +63,7 @@ def make_case(engine, M, N, K, seed, epi, dev="cuda"):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--engines", default="3xtf32,tf32,bf16")
+    ap.add_argument("--engines", default="3xf16,3xtf32,tf32,bf16")
     ap.add_argument("--shapes", default="16384x784x784,16384x1024x784,16384x1024x1024,16384x784x1024,16384x3072x3072")
     ap.add_argument("--chunk", type=int, default=-1)
     ap.add_argument("--bn", type=int, default=0)
@@ -94,7 +102,8 @@ def main():
                     ref = ref_a[:rows] @ ref_w.T
                     if args.epi:
                         ref = torch.relu(ref + bias.double())
-                    got = out.f32 if out.f32 is not None else (out.hi + out.lo)
+                    got = out.f32 if out.f32 is not None else (out.hi + out.lo) if out.hi is not None else \
+                        (out.h16.float() + out.l16.float() / 2048.0)
                     err = float((got[:rows].double() - ref).abs().max() / ref.abs().max())
                     rec["max_err_rel"] = err
                     tail = ref_a[M - 300:] @ ref_w.T

@@ -31,10 +31,13 @@ class LinearArgs(C.Structure):
         ("out_f32", C.c_void_p), ("ld_f32", C.c_int64),
         ("out_hi", C.c_void_p), ("out_lo", C.c_void_p), ("ld_split", C.c_int64),
         ("out_bf16", C.c_void_p), ("ld_bf16", C.c_int64),
+        ("resid_h16", C.c_void_p), ("resid_l16", C.c_void_p), ("ldr_16", C.c_int64),
+        ("out_h16", C.c_void_p), ("out_l16", C.c_void_p), ("ld_16", C.c_int64),
+        ("overflow_flag", C.c_void_p),
     ]
 
 
-ENGINE_SIMT, ENGINE_TC_3XTF32, ENGINE_TC_TF32, ENGINE_TC_BF16 = 0, 1, 2, 3
+ENGINE_SIMT, ENGINE_TC_3XTF32, ENGINE_TC_TF32, ENGINE_TC_BF16, ENGINE_TC_3XF16 = 0, 1, 2, 3, 4
 BASE_LAPLACE, BASE_NORMAL = 0, 1
 
 _P, _I64, _I32, _F, _U64 = C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_uint64
@@ -46,6 +49,8 @@ SIGNATURES = {
     "usf_device_info": (C.c_int, [C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int64)]),
     "usf_linear": (C.c_int, [C.POINTER(LinearArgs), _P]),
     "usf_ingest": (C.c_int, [_P, _I64, _I64, _I32, _P, _P, _P, _P, _I64, _P, _P, _I64, _P, _I64, _P]),
+    "usf_ingest_f16": (C.c_int, [_P, _I64, _I64, _I32, _P, _P, _P, _P, _P, _I64, _P, _P]),
+    "usf_split_f16": (C.c_int, [_P, _I64, _I32, _I64, _P, _P, _I64, _P, _P]),
     "usf_base_logprob": (C.c_int, [_P, _P, _I64, _I64, _I32, _P, _P, _I32, _F, _P, _P]),
     "usf_base_sample": (C.c_int, [_I64, _I32, _P, _P, _I32, _U64, _U64, _P, _I64, _P, _P, _I64, _P, _I64, _P]),
     "usf_leaky_relu": (C.c_int, [_P, _I64, _I64, _I32, _F, _P, _I64, _P, _P]),
@@ -90,7 +95,7 @@ def load():
         fn = getattr(lib, name)  # AttributeError if the ABI and this table disagree
         fn.restype = res
         fn.argtypes = args
-    if lib.usf_abi_version() != 1:
+    if lib.usf_abi_version() != 2:
         raise RuntimeError("usflows_b200: ABI version mismatch between _lib.py and the shared library")
     _lib = lib
     return lib

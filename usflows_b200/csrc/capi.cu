@@ -39,7 +39,7 @@ PFN_encodeTiled get_encode_tiled() {
 }
 
 int make_epilogue(const usf_linear_args* a, Epilogue* ep) {
-  USF_REQUIRE(a->out_f32 || a->out_hi || a->out_bf16, "usf_linear needs at least one output plane");
+  USF_REQUIRE(a->out_f32 || a->out_hi || a->out_bf16 || a->out_h16, "usf_linear needs at least one output plane");
   USF_REQUIRE((a->out_hi == nullptr) == (a->out_lo == nullptr), "out_hi and out_lo come as a pair");
   USF_REQUIRE(!a->resid_lo || a->resid, "resid_lo without resid");
   ep->bias = a->bias;
@@ -57,7 +57,19 @@ int make_epilogue(const usf_linear_args* a, Epilogue* ep) {
   ep->ld_bf16 = a->ld_bf16;
   ep->resid_sign = a->resid_sign;
   ep->relu = a->relu;
+  USF_REQUIRE((a->out_h16 == nullptr) == (a->out_l16 == nullptr), "out_h16 and out_l16 come as a pair");
+  USF_REQUIRE((a->resid_h16 == nullptr) == (a->resid_l16 == nullptr), "resid_h16 and resid_l16 come as a pair");
+  USF_REQUIRE(!(a->resid && a->resid_h16), "give the residual either as fp32 planes or as fp16 split planes");
+  ep->resid_h16 = reinterpret_cast<const __half*>(a->resid_h16);
+  ep->resid_l16 = reinterpret_cast<const __half*>(a->resid_l16);
+  ep->out_h16 = reinterpret_cast<__half*>(a->out_h16);
+  ep->out_l16 = reinterpret_cast<__half*>(a->out_l16);
+  ep->ldr_16 = a->ldr_16;
+  ep->ld_16 = a->ld_16;
+  ep->overflow_flag = a->overflow_flag;
   bool ok = true;
+  if (a->resid_h16) ok = ok && aligned16(a->resid_h16) && aligned16(a->resid_l16) && a->ldr_16 % 8 == 0;
+  if (a->out_h16) ok = ok && aligned16(a->out_h16) && aligned16(a->out_l16) && a->ld_16 % 8 == 0;
   if (a->bias) ok = ok && aligned16(a->bias);
   if (a->colscale) ok = ok && aligned16(a->colscale);
   if (a->postsub) ok = ok && aligned16(a->postsub);
@@ -120,7 +132,8 @@ int usf_linear(const usf_linear_args* a, void* stream) {
     case USF_ENGINE_SIMT: return launch_gemm_simt(a, ep, S(stream));
     case USF_ENGINE_TC_3XTF32:
     case USF_ENGINE_TC_TF32:
-    case USF_ENGINE_TC_BF16: return launch_gemm_tc(a, ep, S(stream));
+    case USF_ENGINE_TC_BF16:
+    case USF_ENGINE_TC_3XF16: return launch_gemm_tc(a, ep, S(stream));
   }
   return fail(USF_ERR_INVALID, "unknown engine%s%s");
 }
@@ -134,6 +147,25 @@ int usf_ingest(const float* x, int64_t ldx, int64_t rows, int32_t d, const float
   OutPlanes o{out_f32, out_hi, out_lo, reinterpret_cast<__nv_bfloat16*>(out_bf16), ld_f32, ld_split, ld_bf16};
   const bool vec = planes_vec_ok(o) && aligned16(x) && ldx % 4 == 0 && d % 4 == 0 && (!dv || aligned16(dv)) &&
                    (!mul || aligned16(mul)) && (!sub || aligned16(sub)) && (!out_bf16 || d % 8 == 0 || true);
+  if (vec)
+    ingest_kernel<true><<<ew_grid(rows * (d / 4), 256), 256, 0, S(stream)>>>(x, ldx, rows, d, dv, mul, sub, o);
+  else
+    ingest_kernel<false><<<ew_grid(rows * d, 256), 256, 0, S(stream)>>>(x, ldx, rows, d, dv, mul, sub, o);
+  USF_CUDA_OK(cudaGetLastError());
+  return USF_OK;
+}
+
+int usf_ingest_f16(const float* x, int64_t ldx, int64_t rows, int32_t d, const float* dv, const float* mul,
+                   const float* sub, void* out_h16, void* out_l16, int64_t ld_16, int32_t* overflow_flag, void* stream) {
+  USF_REQUIRE(x && rows >= 0 && d > 0 && out_h16 && out_l16, "bad input");
+  if (rows == 0) return USF_OK;
+  OutPlanes o{nullptr, nullptr, nullptr, nullptr, 0, 0, 0};
+  o.h16 = reinterpret_cast<__half*>(out_h16);
+  o.l16 = reinterpret_cast<__half*>(out_l16);
+  o.ld_16 = ld_16;
+  o.overflow_flag = overflow_flag;
+  const bool vec = planes_vec_ok(o) && aligned16(x) && ldx % 4 == 0 && d % 4 == 0 && (!dv || aligned16(dv)) &&
+                   (!mul || aligned16(mul)) && (!sub || aligned16(sub));
   if (vec)
     ingest_kernel<true><<<ew_grid(rows * (d / 4), 256), 256, 0, S(stream)>>>(x, ldx, rows, d, dv, mul, sub, o);
   else
@@ -266,6 +298,15 @@ int usf_split_tf32(const float* in, int64_t rows, int32_t cols, int64_t ld_in, f
 int usf_to_bf16(const float* in, int64_t rows, int32_t cols, int64_t ld_in, void* out, int64_t ld_out, void* stream) {
   USF_REQUIRE(in && out && rows > 0 && cols > 0, "bad input");
   to_bf16_kernel<<<ew_grid(rows * cols, 256), 256, 0, S(stream)>>>(in, rows, cols, ld_in, reinterpret_cast<__nv_bfloat16*>(out), ld_out);
+  USF_CUDA_OK(cudaGetLastError());
+  return USF_OK;
+}
+
+int usf_split_f16(const float* in, int64_t rows, int32_t cols, int64_t ld_in, void* hi, void* lo, int64_t ld_out,
+                  int32_t* overflow_flag, void* stream) {
+  USF_REQUIRE(in && hi && lo && rows > 0 && cols > 0, "bad input");
+  split_f16_kernel<<<ew_grid(rows * cols, 256), 256, 0, S(stream)>>>(in, rows, cols, ld_in, reinterpret_cast<__half*>(hi),
+                                                                     reinterpret_cast<__half*>(lo), ld_out, overflow_flag);
   USF_CUDA_OK(cudaGetLastError());
   return USF_OK;
 }

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -62,8 +63,28 @@ struct Epilogue {
   long long ldr, ld_f32, ld_split, ld_bf16;
   float resid_sign;
   int relu;
-  int vec_ok;  // every pointer 16-byte aligned and every ld a multiple of 4 (8 for bf16)
+  int vec_ok;  // every pointer 16-byte aligned and every ld a multiple of 4 (8 for bf16 / fp16)
+  // fp16 split planes (engine TC_3XF16):  x = h16 + l16 * 2^-11
+  const __half* resid_h16;
+  const __half* resid_l16;
+  __half* out_h16;
+  __half* out_l16;
+  long long ldr_16, ld_16;
+  int* overflow_flag;  // set to 1 when a value written to the fp16 planes leaves the fp16 range
 };
+
+constexpr float F16_LO_SCALE = 2048.f;          // 2^11: the low plane is stored scaled up so it stays normal
+constexpr float F16_LO_UNSCALE = 1.f / 2048.f;
+constexpr float F16_GUARD = 65000.f;            // |x| above this cannot be represented in the high plane
+
+// x -> (hi, lo') with x ~= hi + lo' * 2^-11, both fp16
+__device__ __forceinline__ void f16_split(float x, __half& hi, __half& lo) {
+  hi = __float2half_rn(x);
+  lo = __float2half_rn((x - __half2float(hi)) * F16_LO_SCALE);
+}
+__device__ __forceinline__ float f16_join(__half hi, __half lo) {
+  return fmaf(__half2float(lo), F16_LO_UNSCALE, __half2float(hi));
+}
 
 __device__ __forceinline__ float tf32_round(float x) {
   uint32_t r;
@@ -79,6 +100,7 @@ __device__ __forceinline__ float epi_value(const Epilogue& ep, float v, long lon
     if (ep.resid_lo) r += ep.resid_lo[m * ep.ldr + n];
     v = fmaf(ep.resid_sign, v, r);
   }
+  if (ep.resid_h16) v = fmaf(ep.resid_sign, v, f16_join(ep.resid_h16[m * ep.ldr_16 + n], ep.resid_l16[m * ep.ldr_16 + n]));
   if (ep.colscale) v *= __ldg(ep.colscale + n);
   if (ep.postsub) v -= __ldg(ep.postsub + n);
   return v;
@@ -92,6 +114,13 @@ __device__ __forceinline__ void epi_store1(const Epilogue& ep, float v, long lon
     ep.out_lo[m * ep.ld_split + n] = tf32_round(v - hi);
   }
   if (ep.out_bf16) ep.out_bf16[m * ep.ld_bf16 + n] = __float2bfloat16_rn(v);
+  if (ep.out_h16) {
+    __half h, l;
+    f16_split(v, h, l);
+    ep.out_h16[m * ep.ld_16 + n] = h;
+    ep.out_l16[m * ep.ld_16 + n] = l;
+    if (!(fabsf(v) <= F16_GUARD) && ep.overflow_flag) *ep.overflow_flag = 1;
+  }
 }
 
 // four consecutive columns n..n+3 of row m (n % 4 == 0, all in range, ep.vec_ok)
@@ -112,6 +141,18 @@ __device__ __forceinline__ void epi_apply4(const Epilogue& ep, float (&v)[4], lo
     }
     v[0] = fmaf(ep.resid_sign, v[0], r.x); v[1] = fmaf(ep.resid_sign, v[1], r.y);
     v[2] = fmaf(ep.resid_sign, v[2], r.z); v[3] = fmaf(ep.resid_sign, v[3], r.w);
+  }
+  if (ep.resid_h16) {
+    const uint2 rh = *reinterpret_cast<const uint2*>(ep.resid_h16 + m * ep.ldr_16 + n);
+    const uint2 rl = *reinterpret_cast<const uint2*>(ep.resid_l16 + m * ep.ldr_16 + n);
+    const __half2* h2 = reinterpret_cast<const __half2*>(&rh);
+    const __half2* l2 = reinterpret_cast<const __half2*>(&rl);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const float2 hf = __half22float2(h2[i]), lf = __half22float2(l2[i]);
+      v[2 * i] = fmaf(ep.resid_sign, v[2 * i], fmaf(lf.x, F16_LO_UNSCALE, hf.x));
+      v[2 * i + 1] = fmaf(ep.resid_sign, v[2 * i + 1], fmaf(lf.y, F16_LO_UNSCALE, hf.y));
+    }
   }
   if (ep.colscale) {
     float4 s = __ldg(reinterpret_cast<const float4*>(ep.colscale + n));
@@ -136,6 +177,19 @@ __device__ __forceinline__ void epi_apply4(const Epilogue& ep, float (&v)[4], lo
     u.x = *reinterpret_cast<uint32_t*>(&p0);
     u.y = *reinterpret_cast<uint32_t*>(&p1);
     *reinterpret_cast<uint2*>(ep.out_bf16 + m * ep.ld_bf16 + n) = u;
+  }
+  if (ep.out_h16) {
+    __align__(8) __half h[4];
+    __align__(8) __half l[4];
+    bool bad = false;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      f16_split(v[i], h[i], l[i]);
+      bad = bad || !(fabsf(v[i]) <= F16_GUARD);
+    }
+    *reinterpret_cast<uint2*>(ep.out_h16 + m * ep.ld_16 + n) = *reinterpret_cast<const uint2*>(h);
+    *reinterpret_cast<uint2*>(ep.out_l16 + m * ep.ld_16 + n) = *reinterpret_cast<const uint2*>(l);
+    if (bad && ep.overflow_flag) *ep.overflow_flag = 1;
   }
 }
 

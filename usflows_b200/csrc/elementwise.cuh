@@ -11,6 +11,10 @@ struct OutPlanes {
   float* lo;
   __nv_bfloat16* bf16;
   long long ld_f32, ld_split, ld_bf16;
+  __half* h16 = nullptr;      // fp16 split planes (x = h16 + l16 * 2^-11)
+  __half* l16 = nullptr;
+  long long ld_16 = 0;
+  int* overflow_flag = nullptr;
 };
 
 __device__ __forceinline__ void store_planes1(const OutPlanes& o, long long r, int j, float v) {
@@ -21,6 +25,13 @@ __device__ __forceinline__ void store_planes1(const OutPlanes& o, long long r, i
     o.lo[r * o.ld_split + j] = tf32_round(v - h);
   }
   if (o.bf16) o.bf16[r * o.ld_bf16 + j] = __float2bfloat16_rn(v);
+  if (o.h16) {
+    __half h, l;
+    f16_split(v, h, l);
+    o.h16[r * o.ld_16 + j] = h;
+    o.l16[r * o.ld_16 + j] = l;
+    if (!(fabsf(v) <= F16_GUARD) && o.overflow_flag) *o.overflow_flag = 1;
+  }
 }
 
 __device__ __forceinline__ void store_planes4(const OutPlanes& o, long long r, int j, const float (&v)[4]) {
@@ -39,10 +50,24 @@ __device__ __forceinline__ void store_planes4(const OutPlanes& o, long long r, i
     u.y = *reinterpret_cast<uint32_t*>(&p1);
     *reinterpret_cast<uint2*>(o.bf16 + r * o.ld_bf16 + j) = u;
   }
+  if (o.h16) {
+    __align__(8) __half h[4];
+    __align__(8) __half l[4];
+    bool bad = false;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      f16_split(v[i], h[i], l[i]);
+      bad = bad || !(fabsf(v[i]) <= F16_GUARD);
+    }
+    *reinterpret_cast<uint2*>(o.h16 + r * o.ld_16 + j) = *reinterpret_cast<const uint2*>(h);
+    *reinterpret_cast<uint2*>(o.l16 + r * o.ld_16 + j) = *reinterpret_cast<const uint2*>(l);
+    if (bad && o.overflow_flag) *o.overflow_flag = 1;
+  }
 }
 
 inline bool planes_vec_ok(const OutPlanes& o) {
   bool ok = true;
+  if (o.h16) ok = ok && aligned16(o.h16) && aligned16(o.l16) && o.ld_16 % 8 == 0;
   if (o.f32) ok = ok && aligned16(o.f32) && o.ld_f32 % 4 == 0;
   if (o.hi) ok = ok && aligned16(o.hi) && aligned16(o.lo) && o.ld_split % 4 == 0;
   if (o.bf16) ok = ok && aligned16(o.bf16) && o.ld_bf16 % 8 == 0;

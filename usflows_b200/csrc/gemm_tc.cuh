@@ -371,16 +371,17 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
 PFN_encodeTiled get_encode_tiled();
 
 // 2-D row-major [rows, cols] operand, box = 128 B of K x box_rows rows, 128B swizzle, zero OOB fill
+// dtype: 0 = fp32 / tf32, 1 = bf16, 2 = fp16
 inline int make_operand_map(CUtensorMap* map, const void* ptr, long long rows, long long cols, long long ld,
-                            int box_rows, bool bf16) {
+                            int box_rows, int dtype) {
   PFN_encodeTiled enc = get_encode_tiled();
   if (!enc) return fail(USF_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available%s%s");
-  const int esz = bf16 ? 2 : 4;
+  const int esz = dtype ? 2 : 4;
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)ld * esz};
   cuuint32_t box[2] = {(cuuint32_t)(tc::SLAB_BYTES / esz), (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+  CUresult r = enc(map, dtype == 1 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : dtype == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
                    const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -403,11 +404,11 @@ int launch_gemm_tc_cfg(const usf_linear_args* a, const Epilogue& ep, cudaStream_
   }
   CUtensorMap ma, mal, mw, mwl;
   int rc;
-  if ((rc = make_operand_map(&ma, a->a, a->M, a->K, a->lda, tc::BLOCK_M, BF16))) return rc;
-  if ((rc = make_operand_map(&mw, a->w, a->N, a->K, a->ldw, BLOCK_N, BF16))) return rc;
+  if ((rc = make_operand_map(&ma, a->a, a->M, a->K, a->lda, tc::BLOCK_M, BF16 ? 1 : 0))) return rc;
+  if ((rc = make_operand_map(&mw, a->w, a->N, a->K, a->ldw, BLOCK_N, BF16 ? 1 : 0))) return rc;
   if (NTERMS == 3) {
-    if ((rc = make_operand_map(&mal, a->a_lo, a->M, a->K, a->lda, tc::BLOCK_M, BF16))) return rc;
-    if ((rc = make_operand_map(&mwl, a->w_lo, a->N, a->K, a->ldw, BLOCK_N, BF16))) return rc;
+    if ((rc = make_operand_map(&mal, a->a_lo, a->M, a->K, a->lda, tc::BLOCK_M, BF16 ? 1 : 0))) return rc;
+    if ((rc = make_operand_map(&mwl, a->w_lo, a->N, a->K, a->ldw, BLOCK_N, BF16 ? 1 : 0))) return rc;
   } else {
     mal = ma;
     mwl = mw;

@@ -64,9 +64,22 @@ __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap
       ::"r"(dst), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1)
       : "memory");
 }
-template <bool BF16>
+constexpr int KIND_TF32 = 0, KIND_BF16 = 1, KIND_F16 = 2;   // KIND_F16: fp16 split planes (x = hi + lo' 2^-11)
+
+// D = A.B + D * 2^-11 (kind::f16 with scale-input-d): folds the scaled-up cross terms of the fp16 split into the
+// accumulator at the moment the first hi.hi product arrives
+__device__ __forceinline__ void umma_pair_f16_scale11(uint64_t da, uint64_t db, uint32_t tmem_d, uint32_t idesc) {
+  const uint32_t z = 0;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p, 11;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(1u), "r"(z)
+      : "memory");
+}
+
+template <int KIND>
 __device__ __forceinline__ void umma_pair(uint64_t da, uint64_t db, uint32_t tmem_d, uint32_t idesc, uint32_t accumulate) {
-  if (BF16) {
+  if (KIND != KIND_TF32) {
     asm volatile(
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
@@ -88,7 +101,7 @@ __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
       : "memory");
 }
 
-template <int BLOCK_N, int NTERMS, bool BF16>
+template <int BLOCK_N, int NTERMS, int KIND>
 struct Config {
   static_assert(BLOCK_N % 16 == 0 && BLOCK_N >= 32 && BLOCK_N <= 256, "UMMA N for M=256 (cta_group::2)");
   static_assert(NTERMS == 1 || NTERMS == 3, "1 = single pass, 3 = tf32 split");
@@ -105,11 +118,12 @@ struct Config {
   static constexpr int ACC_STRIDE = BLOCK_N <= 32 ? 32 : BLOCK_N <= 64 ? 64 : BLOCK_N <= 128 ? 128 : 256;
   static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align slack*/ + 512 /*barriers*/;
-  static constexpr int ELEMS_PER_SLAB = SLAB_BYTES / (BF16 ? 2 : 4);
+  static constexpr int ELEMS_PER_SLAB = SLAB_BYTES / (KIND == KIND_TF32 ? 4 : 2);
+  static constexpr uint32_t FMT = KIND == KIND_TF32 ? 2u : KIND == KIND_BF16 ? 1u : 0u;   // idesc operand format
   static constexpr int HALF0 = ((BLOCK_N / 16 + 1) / 2) * 16;  // columns owned by epilogue warps 4..7
   static constexpr int HALF1 = BLOCK_N - HALF0;                // ... and by warps 8..11
-  // instruction descriptor: D=f32, A/B = tf32 (2) or bf16 (1), both K-major, N>>3, M>>4 with M = 256
-  static constexpr uint32_t IDESC = (1u << 4) | ((BF16 ? 1u : 2u) << 7) | ((BF16 ? 1u : 2u) << 10) |
+  // instruction descriptor: D=f32, A/B = tf32 (2), bf16 (1) or f16 (0), both K-major, N>>3, M>>4 with M = 256
+  static constexpr uint32_t IDESC = (1u << 4) | (FMT << 7) | (FMT << 10) |
                                     ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
 };
 
@@ -202,12 +216,12 @@ __device__ __forceinline__ void epilogue_loop(int col0, int quarter, int lane, u
   }
 }
 
-template <int BLOCK_N, int NTERMS, bool BF16>
+template <int BLOCK_N, int NTERMS, int KIND>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_a_lo,
                 const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_w_lo,
                 long long M, int N, int K, int chunk_slabs, const __grid_constant__ Epilogue ep) {
-  using C = Config<BLOCK_N, NTERMS, BF16>;
+  using C = Config<BLOCK_N, NTERMS, KIND>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // same offset in both CTAs of the pair
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -228,6 +242,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
   const long long n_tiles = m_blocks * n_blocks;
   const int k_slabs = (K + C::ELEMS_PER_SLAB - 1) / C::ELEMS_PER_SLAB;
   if (chunk_slabs <= 0 || chunk_slabs > k_slabs) chunk_slabs = k_slabs;
+  if (KIND == KIND_F16 && NTERMS == 3) chunk_slabs = 1;   // the 2^-11 rescale happens once per accumulation chain
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tm_a);
@@ -295,19 +310,37 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
               const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
               const uint32_t sb = sa + C::NPLANES * C::A_TILE;
               const uint64_t da_hi = make_smem_desc(sa), db_hi = make_smem_desc(sb);
-              if (NTERMS == 3) {  // small terms first: they meet the accumulator while it is smallest
+              if (NTERMS == 3 && KIND == KIND_F16) {
+                // fp16 split: cross terms first (their low planes are stored scaled by 2^11), then the first
+                // hi.hi product rescales the accumulator by 2^-11; one K-slab (64 elements) per chain
                 const uint64_t da_lo = make_smem_desc(sa + C::A_TILE), db_lo = make_smem_desc(sb + C::B_TILE);
 #pragma unroll
                 for (int k = 0; k < SLAB_BYTES / UMMA_K_BYTES; ++k) {
                   const uint64_t koff = (uint64_t)((k * UMMA_K_BYTES) >> 4);
-                  umma_pair<BF16>(da_lo + koff, db_hi + koff, tmem_d, C::IDESC, (ks > ks0 || k > 0) ? 1u : 0u);
-                  umma_pair<BF16>(da_hi + koff, db_lo + koff, tmem_d, C::IDESC, 1u);
+                  umma_pair<KIND>(da_lo + koff, db_hi + koff, tmem_d, C::IDESC, k > 0 ? 1u : 0u);
+                  umma_pair<KIND>(da_hi + koff, db_lo + koff, tmem_d, C::IDESC, 1u);
                 }
-              }
+                umma_pair_f16_scale11(da_hi, db_hi, tmem_d, C::IDESC);
 #pragma unroll
-              for (int k = 0; k < SLAB_BYTES / UMMA_K_BYTES; ++k) {
-                const uint64_t koff = (uint64_t)((k * UMMA_K_BYTES) >> 4);
-                umma_pair<BF16>(da_hi + koff, db_hi + koff, tmem_d, C::IDESC, (NTERMS == 3 || ks > ks0 || k > 0) ? 1u : 0u);
+                for (int k = 1; k < SLAB_BYTES / UMMA_K_BYTES; ++k) {
+                  const uint64_t koff = (uint64_t)((k * UMMA_K_BYTES) >> 4);
+                  umma_pair<KIND>(da_hi + koff, db_hi + koff, tmem_d, C::IDESC, 1u);
+                }
+              } else {
+                if (NTERMS == 3) {  // small terms first: they meet the accumulator while it is smallest
+                  const uint64_t da_lo = make_smem_desc(sa + C::A_TILE), db_lo = make_smem_desc(sb + C::B_TILE);
+#pragma unroll
+                  for (int k = 0; k < SLAB_BYTES / UMMA_K_BYTES; ++k) {
+                    const uint64_t koff = (uint64_t)((k * UMMA_K_BYTES) >> 4);
+                    umma_pair<KIND>(da_lo + koff, db_hi + koff, tmem_d, C::IDESC, (ks > ks0 || k > 0) ? 1u : 0u);
+                    umma_pair<KIND>(da_hi + koff, db_lo + koff, tmem_d, C::IDESC, 1u);
+                  }
+                }
+#pragma unroll
+                for (int k = 0; k < SLAB_BYTES / UMMA_K_BYTES; ++k) {
+                  const uint64_t koff = (uint64_t)((k * UMMA_K_BYTES) >> 4);
+                  umma_pair<KIND>(da_hi + koff, db_hi + koff, tmem_d, C::IDESC, (NTERMS == 3 || ks > ks0 || k > 0) ? 1u : 0u);
+                }
               }
               umma_commit_pair(empty_bar(stage));                  // slot free in both CTAs once these MMAs retire
               if (ks == ks1 - 1) umma_commit_pair(tfull_bar(acc));  // accumulation chain complete (both CTAs)
@@ -343,22 +376,23 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
 }  // namespace tc2
 
 // host side ---------------------------------------------------------------------------------------
-template <int BLOCK_N, int NTERMS, bool BF16>
+template <int BLOCK_N, int NTERMS, int KIND>
 int launch_gemm_tc2_cfg(const usf_linear_args* a, const Epilogue& ep, cudaStream_t st) {
-  using C = tc2::Config<BLOCK_N, NTERMS, BF16>;
+  using C = tc2::Config<BLOCK_N, NTERMS, KIND>;
   static bool attr_set = false;
-  auto kern = tc2::gemm_tc2_kernel<BLOCK_N, NTERMS, BF16>;
+  auto kern = tc2::gemm_tc2_kernel<BLOCK_N, NTERMS, KIND>;
+  const int dt = KIND == tc2::KIND_TF32 ? 0 : KIND == tc2::KIND_BF16 ? 1 : 2;
   if (!attr_set) {
     USF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_set = true;
   }
   CUtensorMap ma, mal, mw, mwl;
   int rc;
-  if ((rc = make_operand_map(&ma, a->a, a->M, a->K, a->lda, tc::BLOCK_M, BF16))) return rc;
-  if ((rc = make_operand_map(&mw, a->w, a->N, a->K, a->ldw, C::HALF_N, BF16))) return rc;
+  if ((rc = make_operand_map(&ma, a->a, a->M, a->K, a->lda, tc::BLOCK_M, dt))) return rc;
+  if ((rc = make_operand_map(&mw, a->w, a->N, a->K, a->ldw, C::HALF_N, dt))) return rc;
   if (NTERMS == 3) {
-    if ((rc = make_operand_map(&mal, a->a_lo, a->M, a->K, a->lda, tc::BLOCK_M, BF16))) return rc;
-    if ((rc = make_operand_map(&mwl, a->w_lo, a->N, a->K, a->ldw, C::HALF_N, BF16))) return rc;
+    if ((rc = make_operand_map(&mal, a->a_lo, a->M, a->K, a->lda, tc::BLOCK_M, dt))) return rc;
+    if ((rc = make_operand_map(&mwl, a->w_lo, a->N, a->K, a->ldw, C::HALF_N, dt))) return rc;
   } else {
     mal = ma;
     mwl = mw;
@@ -386,14 +420,14 @@ inline int pick_block_n2(int N) {
   return best;
 }
 
-template <int NTERMS, bool BF16>
+template <int NTERMS, int KIND>
 int launch_gemm_tc2_terms(const usf_linear_args* a, const Epilogue& ep, cudaStream_t st, int bn) {
   switch (bn) {
-    case 256: return launch_gemm_tc2_cfg<256, NTERMS, BF16>(a, ep, st);
-    case 208: return launch_gemm_tc2_cfg<208, NTERMS, BF16>(a, ep, st);
-    case 128: return launch_gemm_tc2_cfg<128, NTERMS, BF16>(a, ep, st);
-    case 64: return launch_gemm_tc2_cfg<64, NTERMS, BF16>(a, ep, st);
-    case 32: return launch_gemm_tc2_cfg<32, NTERMS, BF16>(a, ep, st);
+    case 256: return launch_gemm_tc2_cfg<256, NTERMS, KIND>(a, ep, st);
+    case 208: return launch_gemm_tc2_cfg<208, NTERMS, KIND>(a, ep, st);
+    case 128: return launch_gemm_tc2_cfg<128, NTERMS, KIND>(a, ep, st);
+    case 64: return launch_gemm_tc2_cfg<64, NTERMS, KIND>(a, ep, st);
+    case 32: return launch_gemm_tc2_cfg<32, NTERMS, KIND>(a, ep, st);
   }
   return fail(USF_ERR_INVALID, "unsupported BLOCK_N (built: 256, 208, 128, 64, 32)%s%s");
 }
@@ -401,21 +435,26 @@ int launch_gemm_tc2_terms(const usf_linear_args* a, const Epilogue& ep, cudaStre
 int launch_gemm_tc2_3xtf32(const usf_linear_args* a, const Epilogue& ep, cudaStream_t st, int bn);
 int launch_gemm_tc2_tf32(const usf_linear_args* a, const Epilogue& ep, cudaStream_t st, int bn);
 int launch_gemm_tc2_bf16(const usf_linear_args* a, const Epilogue& ep, cudaStream_t st, int bn);
+int launch_gemm_tc2_3xf16(const usf_linear_args* a, const Epilogue& ep, cudaStream_t st, int bn);
 
 extern int g_tc_impl;         // 2 = CTA-pair kernel (default), 1 = single-CTA kernel (usf_debug_set_impl)
 extern int g_force_block_n;   // test hook (usf_debug_set_block_n)
 
 inline int launch_gemm_tc(const usf_linear_args* a, const Epilogue& ep, cudaStream_t st) {
   if (a->M == 0 || a->N == 0) return USF_OK;
-  const bool bf16 = a->engine == USF_ENGINE_TC_BF16;
-  const int kmul = bf16 ? 8 : 4;
+  const bool two_byte = a->engine == USF_ENGINE_TC_BF16 || a->engine == USF_ENGINE_TC_3XF16;
+  const int kmul = two_byte ? 8 : 4;
   USF_REQUIRE(a->K > 0, "K must be positive");
   USF_REQUIRE(a->M < (1LL << 31) - 512, "tcgen05 engine: M must fit a TMA coordinate");
   USF_REQUIRE(aligned16(a->a) && aligned16(a->w) && a->lda % kmul == 0 && a->ldw % kmul == 0,
               "tcgen05 engines need 16-byte aligned operands and 16-byte multiples for lda/ldw");
   USF_REQUIRE(!a->trans_w, "trans_w is a SIMT-engine option");
-  if (a->engine == USF_ENGINE_TC_3XTF32)
-    USF_REQUIRE(a->a_lo && a->w_lo && aligned16(a->a_lo) && aligned16(a->w_lo), "3xTF32 needs a_lo and w_lo planes");
+  if (a->engine == USF_ENGINE_TC_3XTF32 || a->engine == USF_ENGINE_TC_3XF16)
+    USF_REQUIRE(a->a_lo && a->w_lo && aligned16(a->a_lo) && aligned16(a->w_lo), "split engines need a_lo and w_lo planes");
+  if (a->engine == USF_ENGINE_TC_3XF16) {
+    const int bn = g_force_block_n > 0 ? g_force_block_n : pick_block_n2(a->N);
+    return launch_gemm_tc2_3xf16(a, ep, st, bn);
+  }
   if (g_tc_impl == 2) {
     const int bn = g_force_block_n > 0 ? g_force_block_n : pick_block_n2(a->N);
     if (a->engine == USF_ENGINE_TC_3XTF32) return launch_gemm_tc2_3xtf32(a, ep, st, bn);

@@ -6,6 +6,6 @@ int launch_gemm_tc_3xtf32(const usf_linear_args* a, const Epilogue& ep, cudaStre
   return launch_gemm_tc_terms<3, false>(a, ep, st, bn);
 }
 int launch_gemm_tc2_3xtf32(const usf_linear_args* a, const Epilogue& ep, cudaStream_t st, int bn) {
-  return launch_gemm_tc2_terms<3, false>(a, ep, st, bn);
+  return launch_gemm_tc2_terms<3, tc2::KIND_TF32>(a, ep, st, bn);
 }
 }  // namespace usf

@@ -6,6 +6,6 @@ int launch_gemm_tc_bf16(const usf_linear_args* a, const Epilogue& ep, cudaStream
   return launch_gemm_tc_terms<1, true>(a, ep, st, bn);
 }
 int launch_gemm_tc2_bf16(const usf_linear_args* a, const Epilogue& ep, cudaStream_t st, int bn) {
-  return launch_gemm_tc2_terms<1, true>(a, ep, st, bn);
+  return launch_gemm_tc2_terms<1, tc2::KIND_BF16>(a, ep, st, bn);
 }
 }  // namespace usf

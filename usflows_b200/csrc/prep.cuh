@@ -105,6 +105,22 @@ to_bf16_kernel(const float* __restrict__ in, long long rows, int cols, long long
 }
 
 __global__ void __launch_bounds__(256)
+split_f16_kernel(const float* __restrict__ in, long long rows, int cols, long long ld_in, __half* __restrict__ hi,
+                 __half* __restrict__ lo, long long ld_out, int* __restrict__ overflow_flag) {
+  const long long total = rows * cols;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cols;
+    const int c = (int)(i - r * cols);
+    const float v = in[r * ld_in + c];
+    __half h, l;
+    f16_split(v, h, l);
+    hi[r * ld_out + c] = h;
+    lo[r * ld_out + c] = l;
+    if (!(fabsf(v) <= F16_GUARD) && overflow_flag) *overflow_flag = 1;
+  }
+}
+
+__global__ void __launch_bounds__(256)
 softplus_kernel(const float* __restrict__ in, long long n, float* __restrict__ out) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const float x = in[i];

@@ -12,7 +12,10 @@ Planning folds every per-feature vector op into a neighbouring kernel:
 so a USFlow evaluation is one ingest, 5B+1 contractions and (for log_prob) one base-density reduction.
 
 Precision modes (`set_precision`, or `Flow(precision=...)`):
-  "fp32"       tcgen05 kind::tf32 with the 3-term split -- fp32-level accuracy (default)
+  "fp32"       fp32-level accuracy on tensor cores (default): tcgen05 kind::f16 on fp16 split planes
+               (x = hi + lo' 2^-11, 3 products); a chunk whose activations leave the fp16 range (|x| > 65000,
+               reported by a device flag) is re-run with "fp32_tf32"
+  "fp32_tf32"  tcgen05 kind::tf32 with the 3-term tf32 split -- fp32-level accuracy at half the rate of "fp32"
   "fp32_simt"  CUDA-core FFMA contraction (cross-check engine; also used for tiny / unaligned layers)
   "tf32"       tcgen05 kind::tf32 single pass
   "bf16"       tcgen05 kind::f16 with bf16 operands, fp32 accumulate and fp32 residual stream
@@ -26,9 +29,9 @@ from typing import List, Optional
 import torch
 
 from . import ops
-from .ops import Act, ENGINE_SIMT, ENGINE_TC_3XTF32, ENGINE_TC_BF16, ENGINE_TC_TF32, pad4
+from .ops import Act, ENGINE_SIMT, ENGINE_TC_3XF16, ENGINE_TC_3XTF32, ENGINE_TC_BF16, ENGINE_TC_TF32, pad4
 
-PRECISIONS = ("fp32", "fp32_simt", "tf32", "bf16")
+PRECISIONS = ("fp32", "fp32_tf32", "fp32_simt", "tf32", "bf16")
 _default_precision = "fp32"
 _default_chunk_rows = 65536
 TC_MIN_DIM = 32          # contractions narrower than this run on the SIMT engine
@@ -61,7 +64,7 @@ def set_chunk_rows(rows: int) -> None:
 def _engine_for(mode: str, N: int, K: int) -> int:
     if mode == "fp32_simt" or min(N, K) < TC_MIN_DIM:
         return ENGINE_SIMT
-    return {"fp32": ENGINE_TC_3XTF32, "tf32": ENGINE_TC_TF32, "bf16": ENGINE_TC_BF16}[mode]
+    return {"fp32": ENGINE_TC_3XF16, "fp32_tf32": ENGINE_TC_3XTF32, "tf32": ENGINE_TC_TF32, "bf16": ENGINE_TC_BF16}[mode]
 
 
 @dataclass
@@ -180,11 +183,18 @@ class Step:
     final: bool = False                        # writes the program's fp32 result
 
 
-def _operand(w64_or_32: torch.Tensor, mode: str, engine: int):
+def _operand(w64_or_32: torch.Tensor, mode: str, engine: int, overflow_flag: Optional[torch.Tensor] = None):
     """fp32/fp64 weight [N, K] -> operand planes of the engine, pitch padded to a 16-byte multiple."""
     w = w64_or_32.to(torch.float32)
     rows, cols = w.shape
     ld = pad4(cols)
+    if engine == ENGINE_TC_3XF16:
+        src = torch.zeros(rows, ld, dtype=torch.float32, device=w.device)[:, :cols]
+        src.copy_(w)
+        buf = torch.zeros(2, rows, ld, dtype=torch.float16, device=w.device)
+        hi, lo = buf[0, :, :cols], buf[1, :, :cols]
+        ops.split_f16(src, hi, lo, overflow_flag)
+        return hi, lo
     if engine == ENGINE_TC_3XTF32:
         buf = torch.zeros(2, rows, ld, dtype=torch.float32, device=w.device)
         hi, lo = buf[0, :, :cols], buf[1, :, :cols]
@@ -208,6 +218,10 @@ class Program:
 
     def __init__(self, layers, direction: str, mode: Optional[str] = None):
         self.mode = mode or _default_precision
+        self.layers, self.direction = list(layers), direction
+        self._fallback_prog: Optional["Program"] = None
+        self._wflag: Optional[torch.Tensor] = None          # set by weight preparation if a weight leaves fp16 range
+        self.force_fallback = False
         seq = list(layers) if direction == "forward" else list(reversed(list(layers)))
         prims: List[Prim] = []
         for layer in seq:
@@ -257,6 +271,20 @@ class Program:
             compress = self._compression_plan(items)
         self.compress = compress
         self.steps = self._emit(items, compress)
+        if self._wflag is not None and int(self._wflag.item()) != 0:
+            self.force_fallback = True                          # a weight does not fit fp16: always run 3xTF32
+
+    def _flag_for_weights(self, device) -> Optional[torch.Tensor]:
+        if self.mode != "fp32":
+            return None
+        if self._wflag is None:
+            self._wflag = torch.zeros(1, dtype=torch.int32, device=device)
+        return self._wflag
+
+    def _fallback(self) -> "Program":
+        if self._fallback_prog is None:
+            self._fallback_prog = Program(self.layers, self.direction, "fp32_tf32")
+        return self._fallback_prog
 
     # -- mask compression: run the couplings in a feature order that makes "conditioner inputs" and "updated
     #    features" two contiguous column segments, so the first / last conditioner GEMMs shrink to half size
@@ -302,7 +330,7 @@ class Program:
                         c = None if c is None else c[compress["order"]]
                 N, K = W.shape
                 eng = _engine_for(mode, N, K)
-                w, w_lo = _operand(W, mode, eng)
+                w, w_lo = _operand(W, mode, eng, self._flag_for_weights(W.device))
                 bias = None if c is None else c.to(torch.float32).contiguous()
                 steps.append(Step("mm", w=w, w_lo=w_lo, N=N, K=K, engine=eng, bias=bias))
             elif p.kind == "coupling":
@@ -332,7 +360,7 @@ class Program:
                     last = j == nl - 1
                     N, K = ws[j].shape
                     eng = _engine_for(mode, N, K)
-                    w, w_lo = _operand(ws[j], mode, eng)
+                    w, w_lo = _operand(ws[j], mode, eng, self._flag_for_weights(ws[j].device))
                     steps.append(Step("mm", src="x" if j == 0 else "h", dst="x" if last else "h", w=w, w_lo=w_lo,
                                       N=N, K=K, engine=eng, bias=bs[j].to(torch.float32).contiguous(), relu=not last,
                                       resid=last, sign=p.sign, in_seg=in_seg if j == 0 else None,
@@ -363,7 +391,8 @@ class Program:
         return len(self.steps)
 
     def run(self, x: torch.Tensor, mode: Optional[str] = None, chunk_rows: Optional[int] = None,
-            out: Optional[torch.Tensor] = None, sink=None) -> Optional[torch.Tensor]:
+            out: Optional[torch.Tensor] = None, sink=None,
+            flag_out: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
         """Evaluate the program on x [rows, d].  With `sink`, the final stream value of each chunk is handed
         to `sink(chunk_f32 [r, width], r0, r1)` from a reused workspace buffer instead of being stored."""
         ops.require_cuda(x, "input")
@@ -374,30 +403,47 @@ class Program:
         width = self.out_width(x.shape[1])
         if rows == 0:                       # empty batch: nothing to launch
             return None if sink is not None else torch.empty(0, width, dtype=torch.float32, device=x.device)
+        if self.force_fallback:
+            return self._fallback().run(x, chunk_rows=chunk_rows, out=out, sink=sink)
         cap = chunk_rows or _default_chunk_rows
         n_chunks = (rows + cap - 1) // cap
         chunk = min(rows, ((rows + n_chunks - 1) // n_chunks + 255) // 256 * 256)
-        if sink is not None:
-            for r0 in range(0, rows, chunk):
-                r1 = min(rows, r0 + chunk)
-                fin = _workspace.planes(x.device, "final", r1 - r0, width, "f32")
-                self._run_chunk(x[r0:r1], fin)
-                sink(fin, r0, r1)
-            return None
-        if out is None:
+        starts = list(range(0, rows, chunk))
+        own_flags = self.mode == "fp32" and flag_out is None
+        flags = torch.zeros(len(starts), dtype=torch.int32, device=x.device) if own_flags else None
+        if sink is None and out is None:
             out = torch.empty(rows, width, dtype=torch.float32, device=x.device)
-        for r0 in range(0, rows, chunk):
+        for ci, r0 in enumerate(starts):
             r1 = min(rows, r0 + chunk)
-            self._run_chunk(x[r0:r1], out[r0:r1])
-        return out
+            flag = flags[ci:ci + 1] if own_flags else flag_out
+            if sink is not None:
+                fin = _workspace.planes(x.device, "final", r1 - r0, width, "f32")
+                self._run_chunk(x[r0:r1], fin, flag)
+                sink(fin, r0, r1)
+            else:
+                self._run_chunk(x[r0:r1], out[r0:r1], flag)
+        if own_flags:
+            # one device->host read per call: chunks whose activations left the fp16 range are recomputed with the
+            # tf32-split engine (same accuracy class, no range limit)
+            for ci in torch.nonzero(flags).reshape(-1).tolist():
+                r0 = starts[ci]
+                r1 = min(rows, r0 + chunk)
+                fb = self._fallback()
+                if sink is not None:
+                    fin = _workspace.planes(x.device, "final", r1 - r0, width, "f32")
+                    fb._run_chunk(x[r0:r1], fin, None)
+                    sink(fin, r0, r1)
+                else:
+                    fb._run_chunk(x[r0:r1], out[r0:r1], None)
+        return None if sink is not None else out
 
     def _stream_planes(self) -> set:
-        return {"fp32": {"hi", "lo"}, "bf16": {"bf16", "f32"}}.get(self.mode, {"f32"})
+        return {"fp32": {"h16", "l16"}, "fp32_tf32": {"hi", "lo"}, "bf16": {"bf16", "f32"}}.get(self.mode, {"f32"})
 
     def _hidden_planes(self) -> set:
-        return {"fp32": {"hi", "lo"}, "bf16": {"bf16"}}.get(self.mode, {"f32"})
+        return {"fp32": {"h16", "l16"}, "fp32_tf32": {"hi", "lo"}, "bf16": {"bf16"}}.get(self.mode, {"f32"})
 
-    def _run_chunk(self, x: torch.Tensor, final_out: torch.Tensor) -> None:
+    def _run_chunk(self, x: torch.Tensor, final_out: torch.Tensor, flag: Optional[torch.Tensor] = None) -> None:
         dev, rows = x.device, x.shape[0]
         steps = self.steps
         flip = {"x": 0, "h": 0}
@@ -416,7 +462,7 @@ class Program:
                 return a
             c0, w = seg
             v = Act(a.rows, w)
-            for pl in ("f32", "hi", "lo", "bf16"):
+            for pl in ("f32", "hi", "lo", "bf16", "h16", "l16"):
                 t = getattr(a, pl)
                 if t is not None:
                     setattr(v, pl, t[:, c0:c0 + w])
@@ -435,7 +481,7 @@ class Program:
                         if cur.f32 is None:
                             raise RuntimeError("internal: activation has no fp32 plane to re-encode from")
                         b = new_act("x", cur.width, need)
-                        ops.ingest(cur.f32, b)
+                        ops.ingest(cur.f32, b, overflow_flag=flag)
                         cur = b
                     a = seg_view(cur, st.in_seg)
                 else:
@@ -470,7 +516,7 @@ class Program:
                         out = new_act("x", st.N, planes)
                     full_out = out
                 ops.linear(st.engine, a, st.w, st.w_lo, st.N, st.K, bias=st.bias, relu=st.relu, resid=resid,
-                           resid_sign=st.sign, out=out)
+                           resid_sign=st.sign, out=out, overflow_flag=flag)
                 if st.dst == "h":
                     hid = out
                 else:
@@ -488,12 +534,13 @@ class Program:
                 cur = out
 
     def _operand_planes(self) -> set:
-        return {"fp32": {"hi", "lo"}, "bf16": {"bf16"}}.get(self.mode, {"f32"})
+        return {"fp32": {"h16", "l16"}, "fp32_tf32": {"hi", "lo"}, "bf16": {"bf16"}}.get(self.mode, {"f32"})
 
     @classmethod
     def from_steps(cls, steps: List[Step], mode: str) -> "Program":
         prog = cls.__new__(cls)
         prog.mode, prog.items, prog.compress, prog.steps = mode, [], None, steps
+        prog.layers, prog.direction, prog._fallback_prog, prog._wflag, prog.force_fallback = [], "forward", None, None, False
         return prog
 
 
@@ -510,7 +557,7 @@ class _Workspace:
         ld = pad4(width)
         key = (device, name, fmt)
         need = rows * ld
-        dtype = torch.bfloat16 if fmt == "bf16" else torch.float32
+        dtype = torch.bfloat16 if fmt == "bf16" else torch.float16 if fmt in ("h16", "l16") else torch.float32
         buf = self._bufs.get(key)
         if buf is None or buf.numel() < need:
             buf = torch.empty(max(need, 1), dtype=dtype, device=device)

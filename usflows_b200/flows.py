@@ -115,6 +115,15 @@ class Flow(torch.nn.Module):
         copied = [torch.cuda.Event(), torch.cuda.Event()]
         consumed = [torch.cuda.Event(), torch.cuda.Event()]
         starts = list(range(0, rows, chunk))
+        guarded = prog.mode == "fp32" and not prog.force_fallback       # fp16-split engine: range flag per chunk
+        flags = torch.zeros(len(starts), dtype=torch.int32, device=dev) if guarded else None
+
+        def make_sink(r0):
+            def sink(z_chunk, a, b):
+                ops.base_logprob(ops.Act(b - a, d, f32=z_chunk), loc, scale, base.base_kind, -ladj,
+                                 out_dev[r0 + a:r0 + b])
+            return sink
+
         with torch.no_grad():
             self._copy_stream.wait_stream(main)
             for i, r0 in enumerate(starts):
@@ -126,13 +135,16 @@ class Flow(torch.nn.Module):
                     buf.copy_(x2[r0:r1], non_blocking=True)
                     copied[i & 1].record(self._copy_stream)
                 main.wait_event(copied[i & 1])
-
-                def sink(z_chunk, a, b, r0=r0):
-                    ops.base_logprob(ops.Act(b - a, d, f32=z_chunk), loc, scale, base.base_kind, -ladj,
-                                     out_dev[r0 + a:r0 + b])
-
-                prog.run(buf, chunk_rows=chunk, sink=sink)
+                prog.run(buf, chunk_rows=chunk, sink=make_sink(r0),
+                         flag_out=flags[i:i + 1] if guarded else None)
                 consumed[i & 1].record(main)
+            if guarded:                                   # one sync; out-of-range chunks go through the tf32 split
+                for i in torch.nonzero(flags).reshape(-1).tolist():
+                    r0 = starts[i]
+                    r1 = min(rows, r0 + chunk)
+                    buf = self._host_bufs[0][: r1 - r0]
+                    buf.copy_(x2[r0:r1])
+                    prog._fallback().run(buf, chunk_rows=chunk, sink=make_sink(r0))
             out_host.reshape(-1)[:rows].copy_(out_dev, non_blocking=True)
             main.synchronize()
         return out_host

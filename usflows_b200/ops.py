@@ -12,8 +12,8 @@ from typing import Optional
 import torch
 
 from . import _lib
-from ._lib import (BASE_LAPLACE, BASE_NORMAL, ENGINE_SIMT, ENGINE_TC_3XTF32, ENGINE_TC_BF16,  # noqa: F401
-                   ENGINE_TC_TF32, LinearArgs, check)
+from ._lib import (BASE_LAPLACE, BASE_NORMAL, ENGINE_SIMT, ENGINE_TC_3XF16, ENGINE_TC_3XTF32,  # noqa: F401
+                   ENGINE_TC_BF16, ENGINE_TC_TF32, LinearArgs, check)
 
 
 LAUNCHES = 0     # kernels launched through this module since the caller last reset it (bench.py `gpu_launches`)
@@ -57,6 +57,8 @@ class Act:
     hi: Optional[torch.Tensor] = None       # tf32-representable high part  (value = hi + lo)
     lo: Optional[torch.Tensor] = None
     bf16: Optional[torch.Tensor] = None
+    h16: Optional[torch.Tensor] = None      # fp16 split planes: value = h16 + l16 * 2^-11
+    l16: Optional[torch.Tensor] = None
 
     def resid_planes(self):
         if self.f32 is not None:
@@ -67,12 +69,15 @@ class Act:
 
 
 def linear(engine: int, a: Act, w, w_lo, N: int, K: int, *, bias=None, relu=False, resid: Optional[Act] = None,
-           resid_sign: float = 1.0, colscale=None, postsub=None, out: Act, trans_w: bool = False) -> None:
+           resid_sign: float = 1.0, colscale=None, postsub=None, out: Act, trans_w: bool = False,
+           overflow_flag: Optional[torch.Tensor] = None) -> None:
     """out = epilogue(a . w^T); see usf_linear in include/usflows_b200.h."""
     args = LinearArgs()
     args.M, args.N, args.K = a.rows, N, K
     args.engine, args.trans_w = engine, int(trans_w)
-    if engine == ENGINE_TC_BF16:
+    if engine == ENGINE_TC_3XF16:
+        args.a, args.a_lo, args.lda = _ptr(a.h16), _ptr(a.l16), _ld(a.h16)
+    elif engine == ENGINE_TC_BF16:
         args.a, args.a_lo, args.lda = _ptr(a.bf16), None, _ld(a.bf16)
     elif engine == ENGINE_TC_3XTF32:
         args.a, args.a_lo, args.lda = _ptr(a.hi), _ptr(a.lo), _ld(a.hi)
@@ -83,8 +88,11 @@ def linear(engine: int, a: Act, w, w_lo, N: int, K: int, *, bias=None, relu=Fals
     args.w, args.w_lo, args.ldw = _ptr(w), _ptr(w_lo), _ld(w)
     args.bias, args.relu, args.resid_sign = _ptr(bias), int(relu), float(resid_sign)
     if resid is not None:
-        r, rl = resid.resid_planes()
-        args.resid, args.resid_lo, args.ldr = _ptr(r), _ptr(rl), _ld(r)
+        if resid.f32 is None and resid.hi is None and resid.h16 is not None:
+            args.resid_h16, args.resid_l16, args.ldr_16 = _ptr(resid.h16), _ptr(resid.l16), _ld(resid.h16)
+        else:
+            r, rl = resid.resid_planes()
+            args.resid, args.resid_lo, args.ldr = _ptr(r), _ptr(rl), _ld(r)
     args.colscale, args.postsub = _ptr(colscale), _ptr(postsub)
     if out.f32 is not None:
         args.out_f32, args.ld_f32 = _ptr(out.f32), _ld(out.f32)
@@ -92,15 +100,23 @@ def linear(engine: int, a: Act, w, w_lo, N: int, K: int, *, bias=None, relu=Fals
         args.out_hi, args.out_lo, args.ld_split = _ptr(out.hi), _ptr(out.lo), _ld(out.hi)
     if out.bf16 is not None:
         args.out_bf16, args.ld_bf16 = _ptr(out.bf16), _ld(out.bf16)
+    if out.h16 is not None:
+        args.out_h16, args.out_l16, args.ld_16 = _ptr(out.h16), _ptr(out.l16), _ld(out.h16)
+        args.overflow_flag = _ptr(overflow_flag)
     global LAUNCHES
     LAUNCHES += 1
     check(_lib.load().usf_linear(C.byref(args), _stream()))
 
 
-def ingest(x: torch.Tensor, out: Act, *, div=None, mul=None, sub=None) -> None:
+def ingest(x: torch.Tensor, out: Act, *, div=None, mul=None, sub=None,
+           overflow_flag: Optional[torch.Tensor] = None) -> None:
     global LAUNCHES
     LAUNCHES += 1
     rows, d = x.shape
+    if out.h16 is not None:
+        check(_lib.load().usf_ingest_f16(_ptr(x), _ld(x), rows, d, _ptr(div), _ptr(mul), _ptr(sub), _ptr(out.h16),
+                                         _ptr(out.l16), _ld(out.h16), _ptr(overflow_flag), _stream()))
+        return
     check(_lib.load().usf_ingest(
         _ptr(x), _ld(x), rows, d, _ptr(div), _ptr(mul), _ptr(sub),
         _ptr(out.f32), _ld(out.f32) if out.f32 is not None else 0,
@@ -167,6 +183,11 @@ def scale_rows_cols(a, out, rowf=None, colf=None) -> None:
 
 def split_tf32(a, hi, lo) -> None:
     check(_lib.load().usf_split_tf32(_ptr(a), a.shape[0], a.shape[1], _ld(a), _ptr(hi), _ptr(lo), _ld(hi), _stream()))
+
+
+def split_f16(a, hi, lo, overflow_flag=None) -> None:
+    check(_lib.load().usf_split_f16(_ptr(a), a.shape[0], a.shape[1], _ld(a), _ptr(hi), _ptr(lo), _ld(hi),
+                                    _ptr(overflow_flag), _stream()))
 
 
 def to_bf16(a, out) -> None:
