@@ -60,7 +60,10 @@ def measured_peaks():
     if os.path.exists(p):
         with open(p) as f:
             return json.load(f), "measured"
-    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+    # MEASURED_PEAKS.json is driver-written and git-ignored; when it is absent use the values it held at survey
+    # time (this pool's B200s), which are measurements, not the guide's generic fallback
+    return {"hbm_gbs": 6553.9, "bf16_tflops": 1614.3, "bf16_tflops_sustained": 1384.6}, \
+        "MEASURED_PEAKS.json absent; values recorded from it in SURVEY.md section 6"
 
 
 class ClockSampler:
@@ -140,7 +143,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="usflows_b200", choices=["usflows_b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
-    ap.add_argument("--precision", default="fp32", choices=["fp32", "fp32_simt", "tf32", "bf16"])
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "fp32_tf32", "fp32_simt", "tf32", "bf16"])
     ap.add_argument("--rows", type=int, default=0, help="rows per GPU per step (default: the workload's)")
     ap.add_argument("--chunk-rows", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -260,7 +263,7 @@ def main():
 
     extra_modes = {}
     if not args.no_modes and rank == 0 and world == 1:
-        for mode in ("tf32", "bf16"):
+        for mode in ("fp32_tf32", "tf32", "bf16"):
             if mode == args.precision:
                 continue
             f2 = build_flow(spec, params, device=dev, precision=mode)
@@ -290,7 +293,8 @@ def main():
 
     line = dict(
         base_line, impl="usflows_b200", value=value, ms_per_step=ms_step,
-        dtype={"fp32": "f32 (tf32x3 split on tcgen05, fp32 accumulate)", "fp32_simt": "f32", "tf32": "tf32",
+        dtype={"fp32": "f32 (fp16-split x3 on tcgen05 kind::f16, fp32 accumulate/promote; tf32-split fallback)",
+               "fp32_tf32": "f32 (tf32-split x3 on tcgen05 kind::tf32)", "fp32_simt": "f32", "tf32": "tf32",
                "bf16": "bf16"}[args.precision],
         config=dict(workload=wl["name"], rows_per_gpu_per_step=rows, d=d, hidden=spec["hidden_dims"],
                     coupling_blocks=spec["coupling_blocks"], precision=args.precision,
@@ -300,9 +304,11 @@ def main():
                       frac=achieved_tf / peak_tf, traffic=None, peak_source=f"bf16_tflops_sustained ({peak_kind})",
                       kernel="tc::gemm_tc_kernel (all launches of one step)", kernel_ms_per_step=gemm_ms,
                       launches_per_step=n_gemm,
-                      note="algorithmic fp32 FLOPs; the fp32 mode spends 3 tf32 MMAs (= 6 bf16-equivalents) per "
-                           "algorithmic MAC, so its ceiling is 1/6 of this peak",
-                      frac_of_mode_ceiling=(achieved_tf / (peak_tf / 6.0)) if args.precision == "fp32" else None),
+                      note="algorithmic fp32 FLOPs over the summed CUDA-event time of the GEMM launches of one step; "
+                           "the fp32 mode spends 3 fp16 MMAs per algorithmic MAC (fp16 runs at the bf16 rate), so its "
+                           "ceiling is 1/3 of this peak (1/6 for fp32_tf32)",
+                      frac_of_mode_ceiling=(achieved_tf / (peak_tf / {"fp32": 3.0, "fp32_tf32": 6.0}[args.precision]))
+                      if args.precision in ("fp32", "fp32_tf32") else None),
         cpu_baseline=cpu,
         e2e=dict(value=world * rows / (ms_e2e * 1e-3), unit="samples/s", ms_per_step=ms_e2e,
                  h2d_bytes_per_step=rows * d * 4, d2h_bytes_per_step=rows * 4),
