@@ -148,6 +148,8 @@ def main():
     ap.add_argument("--chunk-rows", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-modes", action="store_true", help="skip the extra tf32 / bf16 mode measurements")
+    ap.add_argument("--train", action="store_true",
+                    help="also time the MLE training step (C3: global batch 8192 x n_gpus, gradient all-reduce)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -278,6 +280,36 @@ def main():
                                      max_rel_diff_vs_fp32_mode=err)
             del f2
 
+    train = None
+    if args.train:
+        # C3: Fashion-MNIST-shaped MLE training, weak scaling: 8192 rows per GPU per step, one NCCL all-reduce of the
+        # flat gradient buffer per step (usflows_b200/training.py), SophiaG lr=1e-3 wd=0 as the reference config
+        import numpy as np
+        from usflows_b200 import training
+        per_gpu = 8192
+        tflow = build_flow(spec, O.random_params(spec, 0), device=dev, precision=args.precision)
+        tparams = list(tflow.parameters())
+        opt = U.SophiaG(tparams, lr=1e-3, weight_decay=0.0)
+        gt = torch.Generator().manual_seed(100 + rank)
+        xt = torch.rand(per_gpu, d, generator=gt).to(dev)
+
+        def train_step():
+            opt.zero_grad()
+            loss = -training.log_prob_autograd(tflow, xt).sum() / (per_gpu * world)
+            loss.backward()
+            if world > 1:
+                training.allreduce_gradients(tparams)
+            opt.step()
+            return loss
+        for _ in range(3):
+            train_step()
+        ms_train = timed(train_step, max(3, args.steps))
+        train = dict(metric="train_samples_per_sec", value=world * per_gpu / (ms_train * 1e-3), unit="samples/s",
+                     ms_per_step=ms_train, global_batch=per_gpu * world, grad_floats=sum(p.numel() for p in tparams),
+                     note="forward + backward (all batch-side GEMMs on the tcgen05 tf32-split engine) + gradient "
+                          "all-reduce + SophiaG step; feasibility check not in the timed region")
+        del tflow, opt
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -315,7 +347,7 @@ def main():
         sample=dict(metric="sample_samples_per_sec", value=world * rows / (ms_sample * 1e-3), unit="samples/s",
                     ms_per_step=ms_sample, tflops=rows * flops_per_sample / (ms_sample * 1e-3) / 1e12,
                     note="Flow.sample([rows]): Philox base draws + forward pass; same algorithmic FLOPs per sample"),
-        gpu_launches=launches, clocks=clocks, modes=extra_modes,
+        train=train, gpu_launches=launches, clocks=clocks, modes=extra_modes,
         breakdown_ms={k: v for k, v in breakdown.items() if not k.startswith("_")})
     print(json.dumps(line), flush=True)
     if world > 1:

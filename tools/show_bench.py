@@ -13,3 +13,4 @@ print("modes", {k: (round(v["value"]), round(v["tflops"], 1), v["max_rel_diff_vs
 print("breakdown", {k: round(v, 3) for k, v in (d.get("breakdown_ms") or {}).items()})
 print("clocks", d.get("clocks"))
 print("sample", d.get("sample"))
+print("train", d.get("train"))

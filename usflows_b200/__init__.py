@@ -11,6 +11,7 @@ from .distributions import Independent, Laplace, Normal  # noqa: F401
 from .engine import get_precision, set_chunk_rows, set_precision  # noqa: F401
 from .flows import Flow, USFlow  # noqa: F401
 from .nn import DenseNN  # noqa: F401
+from .optim import SophiaG  # noqa: F401
 from .transforms import (AffineTransform, BaseTransform, BlockAffineTransform, HouseholderTransform,  # noqa: F401
                          InverseTransform, LeakyReLUTransform, LUTransform, MaskedCoupling, Permute, ScaleTransform,
                          SequentialAffineTransform)

@@ -161,6 +161,15 @@ class Flow(torch.nn.Module):
         y = self._run("forward", z.reshape(-1, *z.shape[z.dim() - ev:]))
         return y.reshape(*shape, *y.shape[1:])
 
+    def fit(self, data_train, optim=None, optim_params: Optional[Dict[str, Any]] = None, batch_size: int = 32,
+            shuffle: bool = True, gradient_clip: Optional[float] = None, device=None, epochs: int = 1, **kw):
+        """Maximum-likelihood training loop with the reference's signature (flows.py:113-210); returns the epoch
+        losses.  Default optimiser: `usflows_b200.optim.SophiaG`.  Under an initialised `torch.distributed`
+        process group the batch is sharded over the ranks and the gradients are all-reduced (see training.py)."""
+        from . import training
+        return training.fit(self, data_train, optim=optim, optim_params=optim_params, batch_size=batch_size,
+                            shuffle=shuffle, gradient_clip=gradient_clip, device=device, epochs=epochs, **kw)
+
     def to(self, device):
         self.device = device
         self.trainable_layers = torch.nn.ModuleList([l.to(device) for l in self.trainable_layers])
