@@ -148,6 +148,8 @@ def main():
     ap.add_argument("--chunk-rows", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-modes", action="store_true", help="skip the extra tf32 / bf16 mode measurements")
+    ap.add_argument("--only-logprob", action="store_true",
+                    help="profiling aid: warm-up + timed log_prob steps only, then exit (no JSON line)")
     ap.add_argument("--train", action="store_true",
                     help="also time the MLE training step (C3: global batch 8192 x n_gpus, gradient all-reduce)")
     args = ap.parse_args()
@@ -240,6 +242,11 @@ def main():
     ops.LAUNCHES = 0
     ms_step = timed(step, args.steps)
     launches = ops.LAUNCHES
+    if args.only_logprob:
+        if rank == 0:
+            sampler.stop()
+            print(f"log_prob: {ms_step:.3f} ms/step, {launches} launches in {args.steps} steps", flush=True)
+        return
     value = world * rows / (ms_step * 1e-3)
 
     # the sampling pass (latent -> data) of the same model and batch size: base draws + forward layer stack

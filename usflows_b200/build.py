@@ -36,7 +36,7 @@ def _digest() -> str:
     h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
     for f in _sources():
         with open(f, "rb") as fh:
-            h.update(f.encode() + b"\0" + fh.read())
+            h.update(os.path.basename(f).encode() + b"\0" + fh.read())   # path independent: the .so built here is valid on the GPU box
     return h.hexdigest()
 
 
