@@ -112,6 +112,13 @@ int usf_set_accum_chunk(int k_slabs);
 int usf_debug_set_block_n(int block_n);
 /* test hook: 2 = CTA-pair (cta_group::2) tcgen05 kernel (default), 1 = single-CTA tcgen05 kernel */
 int usf_debug_set_impl(int impl);
+/* profiling hook for the CTA-pair tcgen05 kernel: `device_buf` (512 x 8 uint64, or NULL to switch off) receives
+ * clock64() stamps of the first 512 accumulation chains of cluster 0 (0 = accumulator free seen by the MMA issuer,
+ * 1 = operands landed, 2 = chain issued, 3 = accumulator full seen by epilogue warp 4, 4 = drained, 5 = tile stored);
+ * `flags`: 1 = epilogue skips the TMEM drain, 2 = epilogue skips the store phase (timing experiments only:
+ * results are wrong with either flag set); 4 = outputs leave through the generic register/patch store path instead of
+ * the staged coalesced one (results identical; tests cover both paths). */
+int usf_debug_gemm_timeline(unsigned long long* device_buf, int flags);
 
 /* ------------------------------------------------------------------------------------------------
  * elementwise / reduction kernels over [N_rows, d] activations (HBM-bound, 128-bit accesses)

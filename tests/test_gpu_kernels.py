@@ -153,3 +153,77 @@ def test_errors_are_loud():
     with pytest.raises(RuntimeError, match="usflows_b200"):
         a = Act(4, 40, f32=torch.zeros(4, 41, device="cuda")[:, 1:])      # misaligned operand for a tcgen05 engine
         ops.linear(2, a, torch.zeros(40, 40, device="cuda"), None, 40, 40, out=Act(4, 40, f32=torch.zeros(4, 40, device="cuda")))
+
+
+def _f16_planes(t):
+    from usflows_b200 import ops
+    from usflows_b200.ops import Act
+    M, K = t.shape
+    ld = ops.pad4(K)
+    f = torch.zeros(M, ld, device="cuda")[:, :K]
+    f.copy_(t)
+    h, l = torch.zeros(2, M, ld, dtype=torch.float16, device="cuda")[:, :, :K]
+    ops.split_f16(f, h, l)
+    return Act(M, K, h16=h, l16=l), (h.double() + l.double() / 2048.0).cpu()
+
+
+@pytest.mark.parametrize("M,N,K", [(1, 40, 40), (300, 784, 1024), (1000, 392, 784), (777, 1024, 392), (257, 3072, 520),
+                                   (513, 100, 56), (2048, 224, 72), (640, 432, 1000)])
+def test_fp16_split_engine_full_epilogue(M, N, K):
+    """3 x fp16 tensor-core products with the fp16-split residual and output planes (the default fp32 mode)."""
+    from usflows_b200 import ops
+    from usflows_b200.ops import Act
+    g = torch.Generator().manual_seed(M + 3 * N + K)
+    a = torch.randn(M, K, generator=g)
+    w = torch.randn(N, K, generator=g) / K ** 0.5
+    bias, colscale, postsub = (torch.randn(N, generator=g) for _ in range(3))
+    resid = torch.randn(M, N, generator=g)
+    act, a_used = _f16_planes(a)
+    wact, w_used = _f16_planes(w)
+    racc, r_used = _f16_planes(resid)
+    flag = torch.zeros(1, dtype=torch.int32, device="cuda")
+    out = Act(M, N, f32=torch.zeros(M, ops.pad4(N), device="cuda")[:, :N])
+    out.h16, out.l16 = torch.zeros(2, M, ops.pad4(N), dtype=torch.float16, device="cuda")[:, :, :N]
+    ops.linear(ops.ENGINE_TC_3XF16, act, wact.h16, wact.l16, N, K, bias=bias.cuda(), relu=True, resid=racc, resid_sign=-1.0,
+               colscale=colscale.cuda(), postsub=postsub.cuda(), out=out, overflow_flag=flag)
+    ref = torch.relu(a_used @ w_used.T + bias.double())
+    ref = (r_used - ref) * colscale.double() - postsub.double()
+    assert rel_err(out.f32, ref) <= 3e-6
+    assert rel_err(out.h16.double() + out.l16.double() / 2048.0, out.f32) <= 1e-6
+    assert int(flag) == 0
+
+
+@pytest.mark.parametrize("eng_name,eng,fmt", [("3xtf32", 1, "split"), ("tf32", 2, "f32"), ("bf16", 3, "bf16"), ("3xf16", 4, "f16")])
+@pytest.mark.parametrize("M,N,K", [(300, 784, 392), (515, 392, 1024), (130, 600, 72), (64, 48, 40), (513, 100, 56)])
+def test_staged_store_path_equals_register_store_path(eng_name, eng, fmt, M, N, K):
+    """The staged coalesced-store epilogue and the generic register/patch epilogue produce identical bits."""
+    from usflows_b200 import _lib, ops
+    from usflows_b200.ops import Act
+    g = torch.Generator().manual_seed(M + N + K)
+    a = torch.randn(M, K, generator=g)
+    w = torch.randn(N, K, generator=g) / K ** 0.5
+    bias = torch.randn(N, generator=g).cuda()
+    act, _ = _f16_planes(a) if fmt == "f16" else _planes(a, fmt)
+    wact, _ = _f16_planes(w) if fmt == "f16" else _planes(w, fmt)
+    w_hi = wact.h16 if fmt == "f16" else wact.bf16 if fmt == "bf16" else (wact.hi if fmt == "split" else wact.f32)
+    w_lo = wact.l16 if fmt == "f16" else wact.lo
+    lib = _lib.load()
+    results = []
+    for flags in (0, 4):
+        out = Act(M, N, f32=torch.zeros(M, ops.pad4(N), device="cuda")[:, :N],
+                  hi=torch.zeros(M, ops.pad4(N), device="cuda")[:, :N], lo=torch.zeros(M, ops.pad4(N), device="cuda")[:, :N],
+                  bf16=torch.zeros(M, ops.pad4(N), device="cuda", dtype=torch.bfloat16)[:, :N])
+        out.h16, out.l16 = torch.zeros(2, M, ops.pad4(N), dtype=torch.float16, device="cuda")[:, :, :N]
+        lib.usf_debug_gemm_timeline(None, flags)
+        try:
+            ops.linear(eng, act, w_hi, w_lo, N, K, bias=bias, relu=True, out=out)
+            torch.cuda.synchronize()
+        finally:
+            lib.usf_debug_gemm_timeline(None, 0)
+        results.append(out)
+    p, q = results
+    for name in ("f32", "hi", "lo", "bf16", "h16", "l16"):
+        assert torch.equal(getattr(p, name), getattr(q, name)), name
+    # padding columns beyond N stay untouched
+    if ops.pad4(N) != N:
+        assert float(p.f32._base[:, N:].abs().max()) == 0.0 and float(p.h16._base[..., N:].abs().max()) == 0.0

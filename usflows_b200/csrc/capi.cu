@@ -11,6 +11,9 @@ thread_local char g_err[512] = "";
 int g_force_block_n = 0;
 int g_chunk_slabs = 2;
 int g_tc_impl = 2;
+unsigned long long* g_dbg_buf = nullptr;
+int g_dbg_flags = 0;
+int g_no_fast_store = 0;
 
 int num_sms() {
   static int cached[64] = {0};
@@ -79,6 +82,7 @@ int make_epilogue(const usf_linear_args* a, Epilogue* ep) {
   if (a->out_hi) ok = ok && aligned16(a->out_hi) && aligned16(a->out_lo) && a->ld_split % 4 == 0;
   if (a->out_bf16) ok = ok && aligned16(a->out_bf16) && a->ld_bf16 % 8 == 0;
   ep->vec_ok = ok ? 1 : 0;
+  ep->fast_store = 0;  // set by the pair-kernel launcher
   return USF_OK;
 }
 
@@ -112,6 +116,13 @@ int usf_debug_set_block_n(int bn) {  // test hook: force the tcgen05 tile width 
 int usf_debug_set_impl(int impl) {  // test hook: 2 = CTA-pair tcgen05 kernel (default), 1 = single-CTA kernel
   USF_REQUIRE(impl == 1 || impl == 2, "impl must be 1 or 2");
   g_tc_impl = impl;
+  return USF_OK;
+}
+
+int usf_debug_gemm_timeline(unsigned long long* device_buf, int flags) {
+  g_dbg_buf = device_buf;
+  g_dbg_flags = flags & ~4;
+  g_no_fast_store = (flags & 4) ? 1 : 0;
   return USF_OK;
 }
 

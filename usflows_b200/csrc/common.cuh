@@ -71,6 +71,7 @@ struct Epilogue {
   __half* out_l16;
   long long ldr_16, ld_16;
   int* overflow_flag;  // set to 1 when a value written to the fp16 planes leaves the fp16 range
+  int fast_store;      // pair kernel: aligned planes, N % 8 == 0: staged, coalesced 16-byte stores (else generic path)
 };
 
 constexpr float F16_LO_SCALE = 2048.f;          // 2^11: the low plane is stored scaled up so it stays normal
@@ -123,8 +124,8 @@ __device__ __forceinline__ void epi_store1(const Epilogue& ep, float v, long lon
   }
 }
 
-// four consecutive columns n..n+3 of row m (n % 4 == 0, all in range, ep.vec_ok)
-__device__ __forceinline__ void epi_apply4(const Epilogue& ep, float (&v)[4], long long m, int n) {
+// arithmetic part of the epilogue on four consecutive columns n..n+3 of row m (n % 4 == 0, all in range, ep.vec_ok)
+__device__ __forceinline__ void epi_math4(const Epilogue& ep, float (&v)[4], long long m, int n) {
   if (ep.bias) {
     float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + n));
     v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
@@ -162,6 +163,11 @@ __device__ __forceinline__ void epi_apply4(const Epilogue& ep, float (&v)[4], lo
     float4 s = __ldg(reinterpret_cast<const float4*>(ep.postsub + n));
     v[0] -= s.x; v[1] -= s.y; v[2] -= s.z; v[3] -= s.w;
   }
+}
+
+// epi_math4 followed by the stores to every requested output plane
+__device__ __forceinline__ void epi_apply4(const Epilogue& ep, float (&v)[4], long long m, int n) {
+  epi_math4(ep, v, m, n);
   if (ep.out_f32) *reinterpret_cast<float4*>(ep.out_f32 + m * ep.ld_f32 + n) = make_float4(v[0], v[1], v[2], v[3]);
   if (ep.out_hi) {
     float h[4], l[4];
@@ -179,16 +185,16 @@ __device__ __forceinline__ void epi_apply4(const Epilogue& ep, float (&v)[4], lo
     *reinterpret_cast<uint2*>(ep.out_bf16 + m * ep.ld_bf16 + n) = u;
   }
   if (ep.out_h16) {
-    __align__(8) __half h[4];
-    __align__(8) __half l[4];
-    bool bad = false;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      f16_split(v[i], h[i], l[i]);
-      bad = bad || !(fabsf(v[i]) <= F16_GUARD);
-    }
-    *reinterpret_cast<uint2*>(ep.out_h16 + m * ep.ld_16 + n) = *reinterpret_cast<const uint2*>(h);
-    *reinterpret_cast<uint2*>(ep.out_l16 + m * ep.ld_16 + n) = *reinterpret_cast<const uint2*>(l);
+    const __half2 h0 = __floats2half2_rn(v[0], v[1]), h1 = __floats2half2_rn(v[2], v[3]);
+    const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+    const __half2 l0 = __floats2half2_rn((v[0] - f0.x) * F16_LO_SCALE, (v[1] - f0.y) * F16_LO_SCALE);
+    const __half2 l1 = __floats2half2_rn((v[2] - f1.x) * F16_LO_SCALE, (v[3] - f1.y) * F16_LO_SCALE);
+    uint2 uh, ul;
+    uh.x = *reinterpret_cast<const uint32_t*>(&h0); uh.y = *reinterpret_cast<const uint32_t*>(&h1);
+    ul.x = *reinterpret_cast<const uint32_t*>(&l0); ul.y = *reinterpret_cast<const uint32_t*>(&l1);
+    *reinterpret_cast<uint2*>(ep.out_h16 + m * ep.ld_16 + n) = uh;
+    *reinterpret_cast<uint2*>(ep.out_l16 + m * ep.ld_16 + n) = ul;
+    const bool bad = !(fmaxf(fmaxf(fabsf(v[0]), fabsf(v[1])), fmaxf(fabsf(v[2]), fabsf(v[3]))) <= F16_GUARD);
     if (bad && ep.overflow_flag) *ep.overflow_flag = 1;
   }
 }

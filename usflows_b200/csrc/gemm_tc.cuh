@@ -35,8 +35,8 @@ constexpr int UMMA_K_BYTES = 32;
 constexpr int NUM_THREADS = 384;   // warpgroup 0: TMA producer, MMA issuer, 2 idle warps; warpgroups 1-2: epilogue
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int FIRST_EPI_WARP = 4;
-constexpr int REGS_NON_EPI = 40;   // setmaxnreg budget after role dispatch: 128*40 + 256*232 = 64512 (<= 65536 with slack; an exact fit can block setmaxnreg.inc forever)
-constexpr int REGS_EPI = 232;
+constexpr int REGS_NON_EPI = 56;   // setmaxnreg budget after role dispatch: 128*56 + 256*224 = 64512 (<= 65536 with slack; an exact fit can block setmaxnreg.inc forever)
+constexpr int REGS_EPI = 224;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 

@@ -64,6 +64,9 @@ __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap
       ::"r"(dst), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1)
       : "memory");
 }
+constexpr int STAGE_EPI_BYTES = 4096;          // per epilogue warp: one 32-row x (128 B | 2 x 64 B) staging box
+
+constexpr int DBG_CHAINS = 512;   // timeline slots of a debug launch (usf_debug_gemm_timeline): 8 clock64 values each
 constexpr int KIND_TF32 = 0, KIND_BF16 = 1, KIND_F16 = 2;   // KIND_F16: fp16 split planes (x = hi + lo' 2^-11)
 
 // D = A.B + D * 2^-11 (kind::f16 with scale-input-d): folds the scaled-up cross terms of the fp16 split into the
@@ -111,7 +114,8 @@ struct Config {
   static constexpr int A_TILE = BLOCK_M * SLAB_BYTES;        // 16 KB
   static constexpr int B_TILE = HALF_N * SLAB_BYTES;         // multiple of 1024
   static constexpr int STAGE_BYTES = NPLANES * (A_TILE + B_TILE);
-  static constexpr int EPI_BYTES = NUM_EPI_WARPS * PATCH_BYTES;
+  static constexpr int EPI_BYTES = NUM_EPI_WARPS * STAGE_EPI_BYTES;   // (the patch path of unaligned outputs fits too)
+  static_assert(PATCH_BYTES <= STAGE_EPI_BYTES, "patch buffer lives in the staging area");
   static constexpr int STAGES_RAW = (227 * 1024 - 1024 - 512 - EPI_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static_assert(STAGES >= 2, "need at least a double-buffered pipeline");
@@ -122,6 +126,7 @@ struct Config {
   static constexpr uint32_t FMT = KIND == KIND_TF32 ? 2u : KIND == KIND_BF16 ? 1u : 0u;   // idesc operand format
   static constexpr int HALF0 = ((BLOCK_N / 16 + 1) / 2) * 16;  // columns owned by epilogue warps 4..7
   static constexpr int HALF1 = BLOCK_N - HALF0;                // ... and by warps 8..11
+  static constexpr uint32_t IDESC_NO_N = (1u << 4) | (FMT << 7) | (FMT << 10) | ((uint32_t)(256 >> 4) << 24);
   // instruction descriptor: D=f32, A/B = tf32 (2), bf16 (1) or f16 (0), both K-major, N>>3, M>>4 with M = 256
   static constexpr uint32_t IDESC = (1u << 4) | (FMT << 7) | (FMT << 10) |
                                     ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
@@ -133,16 +138,259 @@ __device__ __forceinline__ void epi4(const Epilogue& ep, float4 t, long long m, 
   epi_apply4(ep, v, m, n);
 }
 
+// ---- staged store of one finished 32-row x W-column piece of the tile ---------------------------------------------
+// Lane r owns row r of the piece (the TMEM layout).  It converts its W values into the output plane's format and
+// writes them as 16-byte chunks into a [32 rows][RB bytes] staging box (RB = 32, 64 or 128; chunk index XOR-swizzled
+// so that neither side has bank conflicts); after a warp sync the box goes out with lanes mapped to (row, chunk), so
+// every store instruction writes whole RB-byte row segments.
+template <int RB>
+__device__ __forceinline__ uint32_t stage_off(int row, int chunk) {
+  constexpr int CPR = RB / 16, RPL = 128 / RB;
+  return (uint32_t)(row * RB + (((chunk ^ ((row / RPL) % CPR))) << 4));
+}
+// explicit shared-space accesses on 32-bit addresses: a generic pointer into dynamic shared memory makes the compiler
+// re-derive the shared window (S2UR SR_CgaCtaId + address arithmetic) at every access inside a cluster kernel
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void stg128(void* p, uint4 v) {
+  asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+template <int RB>
+__device__ __forceinline__ void stage_copy_out(uint32_t stage, int lane, uint8_t* plane, long long ld_bytes,
+                                               long long row0, long long M, int col_bytes0, int n_bytes, int dbg_flags = 0) {
+  // plane + row * ld_bytes + col_bytes0 is the first byte of the box in global memory; n_bytes = row length in bytes
+  constexpr int CPR = RB / 16, ROWS_PER_IT = 32 / CPR;
+  const int chunk = lane % CPR, rsub = lane / CPR;
+  if (col_bytes0 + chunk * 16 >= n_bytes) return;
+  uint8_t* g = plane + (row0 + rsub) * ld_bytes + col_bytes0 + chunk * 16;
+  uint4 t[CPR];
+#pragma unroll
+  for (int it = 0; it < CPR; ++it) t[it] = lds128(stage + stage_off<RB>(it * ROWS_PER_IT + rsub, chunk));
+#pragma unroll
+  for (int it = 0; it < CPR; ++it)
+    if (row0 + it * ROWS_PER_IT + rsub < M && !(dbg_flags & 8)) stg128(g + (long long)it * ROWS_PER_IT * ld_bytes, t[it]);
+}
+
+// The epilogue description, read ONCE per thread into registers.  Reading the fields from the kernel-parameter
+// constant bank where they are used costs a dependent constant load + compare + branch per feature and per group of
+// columns (~10^3 cycles per 32-column piece, measured with the clock64 timeline) -- the pieces must run on registers.
+struct EpiRegs {
+  uint32_t flags;
+  float sign;
+  const float* bias;
+  const __half* rh;
+  const __half* rl;
+  __half* oh;
+  __half* ol;
+  float* of32;
+  int ldr16, ld16, ldf32;    // row pitches in elements
+};
+constexpr uint32_t EF_BIAS = 1, EF_RELU = 2, EF_RESID16 = 4, EF_OUT16 = 8, EF_OUTF32 = 16, EF_RARE = 32;
+
+template <class T>
+__device__ __forceinline__ T* launder_ptr(T* p) {   // opaque to the compiler: stays in a register pair
+  unsigned long long u = reinterpret_cast<unsigned long long>(p);
+  asm volatile("" : "+l"(u));
+  return reinterpret_cast<T*>(u);
+}
+__device__ __forceinline__ EpiRegs load_epi_regs(const Epilogue& ep) {
+  EpiRegs r;
+  uint32_t f = 0;
+  if (ep.bias) f |= EF_BIAS;
+  if (ep.relu) f |= EF_RELU;
+  if (ep.resid_h16) f |= EF_RESID16;
+  if (ep.out_h16) f |= EF_OUT16;
+  if (ep.out_f32) f |= EF_OUTF32;
+  if (ep.resid_hi || ep.colscale || ep.postsub || ep.out_hi || ep.out_bf16) f |= EF_RARE;
+  asm volatile("" : "+r"(f));
+  r.flags = f;
+  r.sign = ep.resid_sign;
+  asm volatile("" : "+f"(r.sign));
+  r.bias = launder_ptr(ep.bias);
+  r.rh = launder_ptr(ep.resid_h16);
+  r.rl = launder_ptr(ep.resid_l16);
+  r.oh = launder_ptr(ep.out_h16);
+  r.ol = launder_ptr(ep.out_l16);
+  r.of32 = launder_ptr(ep.out_f32);
+  r.ldr16 = (int)ep.ldr_16;
+  r.ld16 = (int)ep.ld_16;
+  r.ldf32 = (int)ep.ld_f32;
+  asm volatile("" : "+r"(r.ldr16), "+r"(r.ld16), "+r"(r.ldf32));
+  return r;
+}
+
+template <int W>
+__device__ __forceinline__ void store_chunk(const Epilogue& ep, const EpiRegs& er, float (&v)[W], long long row0, int lane,
+                                            long long M, int n0, int N, uint32_t stage, int dbg_flags,
+                                            unsigned long long* dbg_slot = nullptr) {
+  const long long m = row0 + lane;
+  const uint32_t f = er.flags;
+  long long t0 = 0, t1 = 0, t2 = 0;
+  if (dbg_slot) t0 = clock64();
+  if (m < M) {
+    if (f & EF_RARE) {        // column scale / post-subtract / fp32 residual planes: the generic arithmetic
+#pragma unroll
+      for (int i = 0; i < W; i += 4) {
+        if (n0 + i < N) {     // N % 8 == 0 on this path: a group of four is inside or outside as a whole
+          float t[4] = {v[i], v[i + 1], v[i + 2], v[i + 3]};
+          epi_math4(ep, t, m, n0 + i);
+          v[i] = t[0]; v[i + 1] = t[1]; v[i + 2] = t[2]; v[i + 3] = t[3];
+        }
+      }
+    } else {
+      if (f & EF_BIAS) {
+        const float4* pb = reinterpret_cast<const float4*>(er.bias + n0);
+#pragma unroll
+        for (int q = 0; q < W / 8; ++q) {
+          if (n0 + q * 8 < N) {
+            const float4 b0 = __ldg(pb + 2 * q), b1 = __ldg(pb + 2 * q + 1);
+            v[8 * q] += b0.x; v[8 * q + 1] += b0.y; v[8 * q + 2] += b0.z; v[8 * q + 3] += b0.w;
+            v[8 * q + 4] += b1.x; v[8 * q + 5] += b1.y; v[8 * q + 6] += b1.z; v[8 * q + 7] += b1.w;
+          }
+        }
+      }
+      if (f & EF_RELU) {
+#pragma unroll
+        for (int i = 0; i < W; ++i) v[i] = fmaxf(v[i], 0.f);
+      }
+      if (f & EF_RESID16) {   // coupling: x -/+ t with x in fp16 split planes
+        const uint4* ph = reinterpret_cast<const uint4*>(er.rh + m * er.ldr16 + n0);
+        const uint4* pl = reinterpret_cast<const uint4*>(er.rl + m * er.ldr16 + n0);
+#pragma unroll
+        for (int q = 0; q < W / 8; ++q) {
+          if (n0 + q * 8 < N) {
+            const uint4 h8 = ph[q], l8 = pl[q];
+            const __half2* h2 = reinterpret_cast<const __half2*>(&h8);
+            const __half2* l2 = reinterpret_cast<const __half2*>(&l8);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 hf = __half22float2(h2[e]), lf = __half22float2(l2[e]);
+              v[8 * q + 2 * e] = fmaf(er.sign, v[8 * q + 2 * e], fmaf(lf.x, F16_LO_UNSCALE, hf.x));
+              v[8 * q + 2 * e + 1] = fmaf(er.sign, v[8 * q + 2 * e + 1], fmaf(lf.y, F16_LO_UNSCALE, hf.y));
+            }
+          }
+        }
+      }
+    }
+  }
+  if (dbg_slot) t1 = clock64();
+  if (f & EF_OUT16) {      // fp16 split planes: x = hi + lo' 2^-11
+    constexpr int RB = W * 2;
+    const uint32_t stage_lo = stage + 32 * RB;
+    const bool direct = (dbg_flags & 16) != 0;
+    uint4* gh = reinterpret_cast<uint4*>(er.oh + m * er.ld16 + n0);
+    uint4* gl = reinterpret_cast<uint4*>(er.ol + m * er.ld16 + n0);
+    __half2 amax2 = __float2half2_rn(0.f);      // running max |hi| (NaN-propagating): inf / NaN = the value left the fp16 range
+#pragma unroll
+    for (int q = 0; q < W / 8; ++q) {
+      uint32_t hp[4], lp[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float x0 = v[q * 8 + 2 * e], x1 = v[q * 8 + 2 * e + 1];
+        const __half2 h = __floats2half2_rn(x0, x1);
+        const float2 hf = __half22float2(h);
+        const __half2 l = __floats2half2_rn((x0 - hf.x) * F16_LO_SCALE, (x1 - hf.y) * F16_LO_SCALE);
+        hp[e] = *reinterpret_cast<const uint32_t*>(&h);
+        lp[e] = *reinterpret_cast<const uint32_t*>(&l);
+        if (n0 + q * 8 < N) amax2 = __hmax2_nan(amax2, __habs2(h));
+      }
+      if (direct) {
+        if (m < M && n0 + q * 8 < N) {
+          gh[q] = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+          gl[q] = make_uint4(lp[0], lp[1], lp[2], lp[3]);
+        }
+      } else {
+        sts128(stage + stage_off<RB>(lane, q), hp[0], hp[1], hp[2], hp[3]);
+        sts128(stage_lo + stage_off<RB>(lane, q), lp[0], lp[1], lp[2], lp[3]);
+      }
+    }
+    {
+      const float2 am = __half22float2(amax2);
+      if (!(am.x <= F16_GUARD && am.y <= F16_GUARD) && m < M && ep.overflow_flag) *ep.overflow_flag = 1;
+    }
+    if (dbg_slot) t2 = clock64();
+    if (!direct) {
+      __syncwarp();
+      stage_copy_out<RB>(stage, lane, reinterpret_cast<uint8_t*>(er.oh), (long long)er.ld16 * 2, row0, M, n0 * 2, N * 2, dbg_flags);
+      stage_copy_out<RB>(stage_lo, lane, reinterpret_cast<uint8_t*>(er.ol), (long long)er.ld16 * 2, row0, M, n0 * 2, N * 2, dbg_flags);
+      __syncwarp();
+    }
+    if (dbg_slot) {
+      const long long t3 = clock64();
+      dbg_slot[6] += ((unsigned long long)(t1 - t0) << 32) | (unsigned long long)(t2 - t1);
+      dbg_slot[7] += (unsigned long long)(t3 - t2);
+    }
+  }
+  if (f & EF_OUTF32) {
+    constexpr int RB = W * 4;
+#pragma unroll
+    for (int q = 0; q < W / 4; ++q)
+      sts128(stage + stage_off<RB>(lane, q), __float_as_uint(v[4 * q]), __float_as_uint(v[4 * q + 1]), __float_as_uint(v[4 * q + 2]),
+             __float_as_uint(v[4 * q + 3]));
+    __syncwarp();
+    stage_copy_out<RB>(stage, lane, reinterpret_cast<uint8_t*>(er.of32), (long long)er.ldf32 * 4, row0, M, n0 * 4, N * 4);
+    __syncwarp();
+  }
+  if (f & EF_RARE) {
+    if (ep.out_bf16) {
+      constexpr int RB = W * 2;
+#pragma unroll
+      for (int q = 0; q < W / 8; ++q) {
+        uint32_t pk[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const __nv_bfloat162 t = __floats2bfloat162_rn(v[q * 8 + 2 * e], v[q * 8 + 2 * e + 1]);
+          pk[e] = *reinterpret_cast<const uint32_t*>(&t);
+        }
+        sts128(stage + stage_off<RB>(lane, q), pk[0], pk[1], pk[2], pk[3]);
+      }
+      __syncwarp();
+      stage_copy_out<RB>(stage, lane, reinterpret_cast<uint8_t*>(ep.out_bf16), ep.ld_bf16 * 2, row0, M, n0 * 2, N * 2);
+      __syncwarp();
+    }
+    if (ep.out_hi) {       // tf32 split planes
+      constexpr int RB = W * 4;
+#pragma unroll
+      for (int q = 0; q < W / 4; ++q)
+        sts128(stage + stage_off<RB>(lane, q), __float_as_uint(tf32_round(v[4 * q])), __float_as_uint(tf32_round(v[4 * q + 1])),
+               __float_as_uint(tf32_round(v[4 * q + 2])), __float_as_uint(tf32_round(v[4 * q + 3])));
+      __syncwarp();
+      stage_copy_out<RB>(stage, lane, reinterpret_cast<uint8_t*>(ep.out_hi), ep.ld_split * 4, row0, M, n0 * 4, N * 4);
+      __syncwarp();
+#pragma unroll
+      for (int q = 0; q < W / 4; ++q)
+        sts128(stage + stage_off<RB>(lane, q), __float_as_uint(tf32_round(v[4 * q] - tf32_round(v[4 * q]))),
+               __float_as_uint(tf32_round(v[4 * q + 1] - tf32_round(v[4 * q + 1]))),
+               __float_as_uint(tf32_round(v[4 * q + 2] - tf32_round(v[4 * q + 2]))),
+               __float_as_uint(tf32_round(v[4 * q + 3] - tf32_round(v[4 * q + 3]))));
+      __syncwarp();
+      stage_copy_out<RB>(stage, lane, reinterpret_cast<uint8_t*>(ep.out_lo), ep.ld_split * 4, row0, M, n0 * 4, N * 4);
+      __syncwarp();
+    }
+  }
+}
+
 // One epilogue warp: TMEM lanes [32*quarter, +32) x columns [col0, col0+COLS) of every tile of this CTA.
 template <class C, int COLS>
 __device__ __forceinline__ void epilogue_loop(int col0, int quarter, int lane, uint32_t rank, uint32_t tmem_base,
-                                              uint32_t tfull0, uint32_t tempty0_leader, float* patch,
-                                              long long n_tiles, int n_blocks, int k_slabs, int chunk_slabs,
-                                              long long M, int N, const Epilogue& ep) {
+                                              uint32_t tfull0, uint32_t tempty0_leader, uint8_t* stage_gen,
+                                              uint32_t stage, long long n_tiles, int n_blocks, int k_slabs, int chunk_slabs,
+                                              long long M, int N, const Epilogue& ep, unsigned long long* dbg, int dbg_flags) {
   constexpr int BLOCK_N = C::kBlockN;
   int acc = 0;
   uint32_t acc_phase = 0;
   const int n_chunks = (k_slabs + chunk_slabs - 1) / chunk_slabs;
+  int dbg_chain = 0;   // timeline slot (debug launches only: dbg != nullptr on one warp of cluster 0's leader)
+  float* patch = reinterpret_cast<float*>(stage_gen);
+  asm volatile("" : "+r"(stage), "+r"(tfull0), "+r"(tempty0_leader), "+r"(tmem_base));   // keep the addresses in registers
+  const EpiRegs er = load_epi_regs(ep);
+  const bool fast_store = ep.fast_store != 0;
   for (long long tile = cluster_id_x(); tile < n_tiles; tile += num_clusters_x()) {
     const long long m_idx = (tile / n_blocks) * (2 * BLOCK_M) + rank * BLOCK_M;
     const int n_idx = (int)(tile % n_blocks) * BLOCK_N;
@@ -163,56 +411,83 @@ __device__ __forceinline__ void epilogue_loop(int col0, int quarter, int lane, u
     for (int c = 0; c < n_chunks; ++c) {
       mbar_wait(tfull0 + 8u * acc, acc_phase);
       tcgen05_fence_after();
+      if (dbg && dbg_chain < DBG_CHAINS) dbg[dbg_chain * 8 + 3] = clock64();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * C::ACC_STRIDE + col0;
+      if (!(dbg_flags & 1)) {
 #pragma unroll
-      for (int j = 0; j + 32 <= COLS; j += 32) {
-        float v[32];
-        tmem_ld32(taddr + j, v);
-        tmem_ld_wait();
+        for (int j = 0; j + 32 <= COLS; j += 32) {
+          if (n_idx + col0 + j < N) {      // columns past N hold no MMA result (the last tile of a row may be narrower)
+            float v[32];
+            tmem_ld32(taddr + j, v);
+            tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) master[j + i] += v[i];
-      }
-      if (COLS % 32) {
-        constexpr int j = COLS / 32 * 32;
-        float v[16];
-        tmem_ld16(taddr + j, v);
-        tmem_ld_wait();
+            for (int i = 0; i < 32; ++i) master[j + i] += v[i];
+          }
+        }
+        if (COLS % 32) {
+          constexpr int j = COLS / 32 * 32;
+          if (n_idx + col0 + j < N) {
+            float v[16];
+            tmem_ld16(taddr + j, v);
+            tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 16; ++i) master[j + i] += v[i];
-      }
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(tempty0_leader + 8u * acc);
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-    }
-    // registers -> padded smem patch -> coalesced row segments (4 lanes x 16 B per row, 8 rows per pass)
-    const long long row0 = m_idx + quarter * 32;
-    const int sub_r = lane >> 2, sub_c = (lane & 3) * 4;
-#pragma unroll
-    for (int j = 0; j < COLS; j += PATCH_COLS) {
-      float* prow = patch + lane * PATCH_LD;
-#pragma unroll
-      for (int i = 0; i < PATCH_COLS; i += 4)
-        *reinterpret_cast<float4*>(prow + i) = make_float4(master[j + i], master[j + i + 1], master[j + i + 2], master[j + i + 3]);
-      __syncwarp();
-      const int n = n_idx + col0 + j + sub_c;
-#pragma unroll 1
-      for (int p = 0; p < 4; ++p) {
-        const int r = p * 8 + sub_r;
-        const long long m = row0 + r;
-        const float4 t = *reinterpret_cast<const float4*>(patch + r * PATCH_LD + sub_c);
-        if (m < M && n < N) {
-          if (ep.vec_ok && n + 3 < N) {
-            epi4(ep, t, m, n);
-          } else {
-            const float tv[4] = {t.x, t.y, t.z, t.w};
-            for (int i = 0; i < 4; ++i)
-              if (n + i < N) epi_store1(ep, epi_value(ep, tv[i], m, n + i), m, n + i);
+            for (int i = 0; i < 16; ++i) master[j + i] += v[i];
           }
         }
       }
+      tcgen05_fence_before();
       __syncwarp();
+      if (dbg && dbg_chain < DBG_CHAINS) dbg[dbg_chain * 8 + 4] = clock64();
+      if (lane == 0) mbar_arrive_cluster(tempty0_leader + 8u * acc);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      ++dbg_chain;
     }
+    if (dbg_flags & 2) continue;   // debug: no store phase
+    const long long row0 = m_idx + quarter * 32;
+    if (fast_store) {
+      if (row0 < M) {
+#pragma unroll
+        for (int c = 0; c < COLS / 32; ++c) {
+          const int n0 = n_idx + col0 + c * 32;
+          if (n0 < N)
+            store_chunk<32>(ep, er, *reinterpret_cast<float(*)[32]>(&master[c * 32]), row0, lane, M, n0, N, stage, dbg_flags,
+                            (dbg && dbg_chain - 1 < DBG_CHAINS) ? dbg + (dbg_chain - 1) * 8 : nullptr);
+        }
+        if (COLS % 32) {
+          const int n0 = n_idx + col0 + COLS / 32 * 32;
+          if (n0 < N) store_chunk<16>(ep, er, *reinterpret_cast<float(*)[16]>(&master[COLS / 32 * 32]), row0, lane, M, n0, N, stage, dbg_flags);
+        }
+      }
+    } else {
+      // unaligned output planes: registers -> padded smem patch -> 64 B row segments (4 lanes x 16 B per row)
+      const int sub_r = lane >> 2, sub_c = (lane & 3) * 4;
+#pragma unroll
+      for (int j = 0; j < COLS; j += PATCH_COLS) {
+        float* prow = patch + lane * PATCH_LD;
+#pragma unroll
+        for (int i = 0; i < PATCH_COLS; i += 4)
+          *reinterpret_cast<float4*>(prow + i) = make_float4(master[j + i], master[j + i + 1], master[j + i + 2], master[j + i + 3]);
+        __syncwarp();
+        const int n = n_idx + col0 + j + sub_c;
+#pragma unroll 1
+        for (int p = 0; p < 4; ++p) {
+          const int r = p * 8 + sub_r;
+          const long long m = row0 + r;
+          const float4 t = *reinterpret_cast<const float4*>(patch + r * PATCH_LD + sub_c);
+          if (m < M && n < N) {
+            if (ep.vec_ok && n + 3 < N) {
+              epi4(ep, t, m, n);
+            } else {
+              const float tv[4] = {t.x, t.y, t.z, t.w};
+              for (int i = 0; i < 4; ++i)
+                if (n + i < N) epi_store1(ep, epi_value(ep, tv[i], m, n + i), m, n + i);
+            }
+          }
+        }
+        __syncwarp();
+      }
+    }
+    if (dbg && dbg_chain - 1 < DBG_CHAINS) dbg[(dbg_chain - 1) * 8 + 5] = clock64();
   }
 }
 
@@ -220,10 +495,12 @@ template <int BLOCK_N, int NTERMS, int KIND>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_a_lo,
                 const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_w_lo,
-                long long M, int N, int K, int chunk_slabs, const __grid_constant__ Epilogue ep) {
+                long long M, int N, int K, int chunk_slabs, const __grid_constant__ Epilogue ep,
+                unsigned long long* dbg_buf, int dbg_flags) {
   using C = Config<BLOCK_N, NTERMS, KIND>;
   extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // same offset in both CTAs of the pair
+  uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // same offset in both CTAs of the pair
+  asm volatile("" : "+r"(smem_base));   // opaque: otherwise every use re-derives it (S2UR SR_CgaCtaId + arithmetic)
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   const uint32_t epi_base = smem_base + C::STAGES * C::STAGE_BYTES;
   const uint32_t bar_base = epi_base + C::EPI_BYTES;
@@ -243,6 +520,13 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
   const int k_slabs = (K + C::ELEMS_PER_SLAB - 1) / C::ELEMS_PER_SLAB;
   if (chunk_slabs <= 0 || chunk_slabs > k_slabs) chunk_slabs = k_slabs;
   if (KIND == KIND_F16 && NTERMS == 3) chunk_slabs = 1;   // the 2^-11 rescale happens once per accumulation chain
+  // the last tile of a tile row is only as wide as N needs (UMMA N is a run-time field of the instruction descriptor;
+  // multiples of 16 for M = 256), and the last K-slab only issues the 32-byte K steps that hold data
+  auto tile_width = [&](int n_idx) {
+    const int rest = (N - n_idx + 15) & ~15;
+    return rest < 32 ? 32 : rest < BLOCK_N ? rest : BLOCK_N;
+  };
+  const int last_ksteps = ((K - (k_slabs - 1) * C::ELEMS_PER_SLAB) * (SLAB_BYTES / C::ELEMS_PER_SLAB) + UMMA_K_BYTES - 1) / UMMA_K_BYTES;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tm_a);
@@ -273,7 +557,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         uint32_t phase = 0;
         for (long long tile = cluster_id_x(); tile < n_tiles; tile += num_clusters_x()) {
           const int m_idx = (int)(tile / n_blocks) * (2 * BLOCK_M) + (int)rank * BLOCK_M;
-          const int n_idx = (int)(tile % n_blocks) * BLOCK_N + (int)rank * C::HALF_N;
+          const int n_tile = (int)(tile % n_blocks) * BLOCK_N;
+          const int n_idx = n_tile + (int)rank * (tile_width(n_tile) >> 1);   // this CTA stages its half of the W rows
           for (int ks = 0; ks < k_slabs; ++ks) {
             mbar_wait(empty_bar(stage), phase ^ 1);
             const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
@@ -297,49 +582,64 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      int dbg_chain = 0;
+      unsigned long long* dbg_mma = (cluster_id_x() == 0 && lane == 0) ? dbg_buf : nullptr;
       for (long long tile = cluster_id_x(); tile < n_tiles; tile += num_clusters_x()) {
+        const uint32_t idesc = C::IDESC_NO_N | ((uint32_t)(tile_width((int)(tile % n_blocks) * BLOCK_N) >> 3) << 17);
         for (int ks0 = 0; ks0 < k_slabs; ks0 += chunk_slabs) {
           const int ks1 = ks0 + chunk_slabs < k_slabs ? ks0 + chunk_slabs : k_slabs;
           mbar_wait(tempty_bar(acc), acc_phase ^ 1);  // both CTAs' epilogues have drained this accumulator
           tcgen05_fence_after();
+          if (dbg_mma && dbg_chain < DBG_CHAINS) dbg_mma[dbg_chain * 8 + 0] = clock64();
           const uint32_t tmem_d = tmem_base + acc * C::ACC_STRIDE;
           for (int ks = ks0; ks < ks1; ++ks) {
             mbar_wait(full_bar(stage), phase);
             tcgen05_fence_after();
+            if (dbg_mma && dbg_chain < DBG_CHAINS) dbg_mma[dbg_chain * 8 + 1] = clock64();
             if (lane == 0) {
               const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
               const uint32_t sb = sa + C::NPLANES * C::A_TILE;
               const uint64_t da_hi = make_smem_desc(sa), db_hi = make_smem_desc(sb);
+              constexpr int KSTEPS = SLAB_BYTES / UMMA_K_BYTES;
+              const int nk = ks == k_slabs - 1 ? last_ksteps : KSTEPS;
               if (NTERMS == 3 && KIND == KIND_F16) {
                 // fp16 split: cross terms first (their low planes are stored scaled by 2^11), then the first
                 // hi.hi product rescales the accumulator by 2^-11; one K-slab (64 elements) per chain
                 const uint64_t da_lo = make_smem_desc(sa + C::A_TILE), db_lo = make_smem_desc(sb + C::B_TILE);
 #pragma unroll
-                for (int k = 0; k < SLAB_BYTES / UMMA_K_BYTES; ++k) {
-                  const uint64_t koff = (uint64_t)((k * UMMA_K_BYTES) >> 4);
-                  umma_pair<KIND>(da_lo + koff, db_hi + koff, tmem_d, C::IDESC, k > 0 ? 1u : 0u);
-                  umma_pair<KIND>(da_hi + koff, db_lo + koff, tmem_d, C::IDESC, 1u);
+                for (int k = 0; k < KSTEPS; ++k) {
+                  if (k < nk) {
+                    const uint64_t koff = (uint64_t)((k * UMMA_K_BYTES) >> 4);
+                    umma_pair<KIND>(da_lo + koff, db_hi + koff, tmem_d, idesc, k > 0 ? 1u : 0u);
+                    umma_pair<KIND>(da_hi + koff, db_lo + koff, tmem_d, idesc, 1u);
+                  }
                 }
-                umma_pair_f16_scale11(da_hi, db_hi, tmem_d, C::IDESC);
+                umma_pair_f16_scale11(da_hi, db_hi, tmem_d, idesc);
 #pragma unroll
-                for (int k = 1; k < SLAB_BYTES / UMMA_K_BYTES; ++k) {
-                  const uint64_t koff = (uint64_t)((k * UMMA_K_BYTES) >> 4);
-                  umma_pair<KIND>(da_hi + koff, db_hi + koff, tmem_d, C::IDESC, 1u);
+                for (int k = 1; k < KSTEPS; ++k) {
+                  if (k < nk) {
+                    const uint64_t koff = (uint64_t)((k * UMMA_K_BYTES) >> 4);
+                    umma_pair<KIND>(da_hi + koff, db_hi + koff, tmem_d, idesc, 1u);
+                  }
                 }
               } else {
                 if (NTERMS == 3) {  // small terms first: they meet the accumulator while it is smallest
                   const uint64_t da_lo = make_smem_desc(sa + C::A_TILE), db_lo = make_smem_desc(sb + C::B_TILE);
 #pragma unroll
-                  for (int k = 0; k < SLAB_BYTES / UMMA_K_BYTES; ++k) {
-                    const uint64_t koff = (uint64_t)((k * UMMA_K_BYTES) >> 4);
-                    umma_pair<KIND>(da_lo + koff, db_hi + koff, tmem_d, C::IDESC, (ks > ks0 || k > 0) ? 1u : 0u);
-                    umma_pair<KIND>(da_hi + koff, db_lo + koff, tmem_d, C::IDESC, 1u);
+                  for (int k = 0; k < KSTEPS; ++k) {
+                    if (k < nk) {
+                      const uint64_t koff = (uint64_t)((k * UMMA_K_BYTES) >> 4);
+                      umma_pair<KIND>(da_lo + koff, db_hi + koff, tmem_d, idesc, (ks > ks0 || k > 0) ? 1u : 0u);
+                      umma_pair<KIND>(da_hi + koff, db_lo + koff, tmem_d, idesc, 1u);
+                    }
                   }
                 }
 #pragma unroll
-                for (int k = 0; k < SLAB_BYTES / UMMA_K_BYTES; ++k) {
-                  const uint64_t koff = (uint64_t)((k * UMMA_K_BYTES) >> 4);
-                  umma_pair<KIND>(da_hi + koff, db_hi + koff, tmem_d, C::IDESC, (NTERMS == 3 || ks > ks0 || k > 0) ? 1u : 0u);
+                for (int k = 0; k < KSTEPS; ++k) {
+                  if (k < nk) {
+                    const uint64_t koff = (uint64_t)((k * UMMA_K_BYTES) >> 4);
+                    umma_pair<KIND>(da_hi + koff, db_hi + koff, tmem_d, idesc, (NTERMS == 3 || ks > ks0 || k > 0) ? 1u : 0u);
+                  }
                 }
               }
               umma_commit_pair(empty_bar(stage));                  // slot free in both CTAs once these MMAs retire
@@ -348,6 +648,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
             __syncwarp();
             if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
           }
+          if (dbg_mma && dbg_chain < DBG_CHAINS) dbg_mma[dbg_chain * 8 + 2] = clock64();
+          ++dbg_chain;
           if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
       }
@@ -355,14 +657,19 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
   } else {
     // ===================== epilogue warps (TMEM lane quarter = warp % 4; column half = (warp-4)/4) ======
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_EPI));
-    float* patch = reinterpret_cast<float*>(smem_gen + (epi_base - smem_base) + (warp - FIRST_EPI_WARP) * PATCH_BYTES);
+    const uint32_t stage_u32 = epi_base + (warp - FIRST_EPI_WARP) * STAGE_EPI_BYTES;
+    uint8_t* stage = smem_gen + (stage_u32 - smem_base);
     const uint32_t tempty_leader = mapa(tempty_bar(0), 0);
-    if (warp < FIRST_EPI_WARP + 4)
-      epilogue_loop<C, C::HALF0>(0, warp & 3, lane, rank, tmem_base, tfull_bar(0), tempty_leader, patch, n_tiles,
-                                 n_blocks, k_slabs, chunk_slabs, M, N, ep);
+    unsigned long long* dbg_epi = (cluster_id_x() == 0 && rank == 0 && warp == FIRST_EPI_WARP && lane == 0) ? dbg_buf : nullptr;
+    if (C::HALF0 == C::HALF1)     // one copy of the epilogue code serves both column halves
+      epilogue_loop<C, C::HALF0>(warp < FIRST_EPI_WARP + 4 ? 0 : C::HALF0, warp & 3, lane, rank, tmem_base, tfull_bar(0),
+                                 tempty_leader, stage, stage_u32, n_tiles, n_blocks, k_slabs, chunk_slabs, M, N, ep, dbg_epi, dbg_flags);
+    else if (warp < FIRST_EPI_WARP + 4)
+      epilogue_loop<C, C::HALF0>(0, warp & 3, lane, rank, tmem_base, tfull_bar(0), tempty_leader, stage, stage_u32, n_tiles,
+                                 n_blocks, k_slabs, chunk_slabs, M, N, ep, dbg_epi, dbg_flags);
     else
-      epilogue_loop<C, C::HALF1>(C::HALF0, warp & 3, lane, rank, tmem_base, tfull_bar(0), tempty_leader, patch, n_tiles,
-                                 n_blocks, k_slabs, chunk_slabs, M, N, ep);
+      epilogue_loop<C, C::HALF1>(C::HALF0, warp & 3, lane, rank, tmem_base, tfull_bar(0), tempty_leader, stage, stage_u32,
+                                 n_tiles, n_blocks, k_slabs, chunk_slabs, M, N, ep, nullptr, dbg_flags);
   }
 
   tcgen05_fence_before();
@@ -376,8 +683,12 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
 }  // namespace tc2
 
 // host side ---------------------------------------------------------------------------------------
+extern unsigned long long* g_dbg_buf;   // debug timeline buffer (usf_debug_gemm_timeline), normally null
+extern int g_dbg_flags;                 // debug: 1 = epilogue skips the TMEM drain, 2 = no store phase
+extern int g_no_fast_store;             // test hook: 1 = always use the register/patch store path (usf_debug_gemm_timeline flag 4)
+
 template <int BLOCK_N, int NTERMS, int KIND>
-int launch_gemm_tc2_cfg(const usf_linear_args* a, const Epilogue& ep, cudaStream_t st) {
+int launch_gemm_tc2_cfg(const usf_linear_args* a, const Epilogue& ep_in, cudaStream_t st) {
   using C = tc2::Config<BLOCK_N, NTERMS, KIND>;
   static bool attr_set = false;
   auto kern = tc2::gemm_tc2_kernel<BLOCK_N, NTERMS, KIND>;
@@ -397,11 +708,15 @@ int launch_gemm_tc2_cfg(const usf_linear_args* a, const Epilogue& ep, cudaStream
     mal = ma;
     mwl = mw;
   }
+  // aligned output planes (16-byte aligned, pitch a 16-byte multiple, N a multiple of 8) leave through the staged,
+  // coalesced store path; anything else through the generic register/patch path
+  Epilogue ep = ep_in;
+  ep.fast_store = (ep.vec_ok && a->N % 8 == 0 && !g_no_fast_store) ? 1 : 0;
   const long long tiles = ((a->M + 2 * tc::BLOCK_M - 1) / (2 * tc::BLOCK_M)) * ((a->N + BLOCK_N - 1) / BLOCK_N);
   const int pairs = num_sms() / 2;
   const int grid = 2 * (int)(tiles < pairs ? tiles : pairs);
   kern<<<grid, tc::NUM_THREADS, C::SMEM_BYTES, st>>>(ma, mal, mw, mwl, a->M, a->N, a->K,
-                                                       NTERMS == 3 ? g_chunk_slabs : 0, ep);
+                                                       NTERMS == 3 ? g_chunk_slabs : 0, ep, g_dbg_buf, g_dbg_flags);
   USF_CUDA_OK(cudaGetLastError());
   return USF_OK;
 }
