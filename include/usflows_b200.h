@@ -108,6 +108,11 @@ int usf_linear(const usf_linear_args* args, void* stream);
  * added into fp32 registers with round-to-nearest (the tensor core truncates when it accumulates; long
  * chains carry a systematic toward-zero bias).  0 = accumulate the whole K in TMEM.  Default 2. */
 int usf_set_accum_chunk(int k_slabs);
+/* fp16-split engine (TC_3XF16), CTA-pair kernel: the first `chains` (0, 1 or 2; default 2) accumulation chains of every output tile
+ * span twice the usual number of K-slabs, so the tensor core keeps running on the next tile while the epilogue warps
+ * still store the previous one (two TMEM accumulators = two chains of run-ahead).  Not applied to TC_3XTF32: its
+ * chains already hold 48 MMA steps and the toward-zero accumulation bias of longer chains shows in the gradients. */
+int usf_set_accum_lead(int chains);
 /* test hook: force the tcgen05 tile width BLOCK_N (0 = automatic) */
 int usf_debug_set_block_n(int block_n);
 /* test hook: 2 = CTA-pair (cta_group::2) tcgen05 kernel (default), 1 = single-CTA tcgen05 kernel */

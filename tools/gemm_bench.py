@@ -70,11 +70,14 @@ def main():
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--check", action="store_true")
     ap.add_argument("--epi", action="store_true", help="bias + relu epilogue")
+    ap.add_argument("--lead", type=int, default=-1)
     args = ap.parse_args()
     lib = _lib.load()
     if args.chunk >= 0:
         lib.usf_set_accum_chunk(args.chunk)
     lib.usf_debug_set_block_n(args.bn)
+    if args.lead >= 0:
+        lib.usf_set_accum_lead(args.lead)
     print(torch.cuda.get_device_name(0), flush=True)
     for eng in args.engines.split(","):
         for shp in args.shapes.split(","):

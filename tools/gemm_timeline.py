@@ -33,11 +33,14 @@ def main():
     ap.add_argument("--chunk", type=int, default=-1)
     ap.add_argument("--flags", default="0,1,2,3")
     ap.add_argument("--iters", type=int, default=10)
+    ap.add_argument("--lead", type=int, default=-1)
     args = ap.parse_args()
     lib = _lib.load()
     lib.usf_debug_set_block_n(args.bn)
     if args.chunk >= 0:
         lib.usf_set_accum_chunk(args.chunk)
+    if args.lead >= 0:
+        lib.usf_set_accum_lead(args.lead)
     M, N, K = (int(v) for v in args.shape.split("x"))
     eng = args.engine
     act, wt, wl, bias, out, _, _ = make_case(eng, M, N, K, 0, False)

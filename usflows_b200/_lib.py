@@ -69,6 +69,7 @@ SIGNATURES = {
     "usf_matmul_f64": (C.c_int, [_P, _I64, _P, _I64, _P, _I64, _I32, _I32, _I32, _P]),
     "usf_debug_set_block_n": (C.c_int, [C.c_int]),
     "usf_set_accum_chunk": (C.c_int, [C.c_int]),
+    "usf_set_accum_lead": (C.c_int, [C.c_int]),
     "usf_debug_set_impl": (C.c_int, [C.c_int]),
     "usf_debug_gemm_timeline": (C.c_int, [_P, C.c_int]),
 }

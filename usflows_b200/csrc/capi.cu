@@ -10,6 +10,7 @@ namespace usf {
 thread_local char g_err[512] = "";
 int g_force_block_n = 0;
 int g_chunk_slabs = 2;
+int g_lead_chains = 2;
 int g_tc_impl = 2;
 unsigned long long* g_dbg_buf = nullptr;
 int g_dbg_flags = 0;
@@ -123,6 +124,12 @@ int usf_debug_gemm_timeline(unsigned long long* device_buf, int flags) {
   g_dbg_buf = device_buf;
   g_dbg_flags = flags & ~4;
   g_no_fast_store = (flags & 4) ? 1 : 0;
+  return USF_OK;
+}
+
+int usf_set_accum_lead(int chains) {  // leading double-length accumulation chains per tile (MMA run-ahead); 0 = none
+  USF_REQUIRE(chains >= 0 && chains <= 2, "lead chains must be 0, 1 or 2 (two TMEM accumulators)");
+  g_lead_chains = chains;
   return USF_OK;
 }
 

@@ -66,6 +66,18 @@ __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap
 }
 constexpr int STAGE_EPI_BYTES = 4096;          // per epilogue warp: one 32-row x (128 B | 2 x 64 B) staging box
 
+// Accumulation-chain schedule of one tile: the first `lead` chains span 2 * chunk K-slabs, the others `chunk`.
+// Longer leading chains let the MMA issuer run further ahead while the epilogue warps are still storing the previous
+// tile (two TMEM accumulators = two chains of run-ahead); they cost a little accumulation accuracy (longer chains).
+__device__ __forceinline__ int chain_lead(int k_slabs, int chunk, int lead) {
+  const int fit = k_slabs / (2 * chunk);
+  return lead < fit ? lead : fit;
+}
+__device__ __forceinline__ int chain_count(int k_slabs, int chunk, int lead) {
+  const int l = chain_lead(k_slabs, chunk, lead);
+  return l + (k_slabs - 2 * chunk * l + chunk - 1) / chunk;
+}
+
 constexpr int DBG_CHAINS = 512;   // timeline slots of a debug launch (usf_debug_gemm_timeline): 8 clock64 values each
 constexpr int KIND_TF32 = 0, KIND_BF16 = 1, KIND_F16 = 2;   // KIND_F16: fp16 split planes (x = hi + lo' 2^-11)
 
@@ -380,15 +392,19 @@ __device__ __forceinline__ void store_chunk(const Epilogue& ep, const EpiRegs& e
 template <class C, int COLS>
 __device__ __forceinline__ void epilogue_loop(int col0, int quarter, int lane, uint32_t rank, uint32_t tmem_base,
                                               uint32_t tfull0, uint32_t tempty0_leader, uint8_t* stage_gen,
-                                              uint32_t stage, long long n_tiles, int n_blocks, int k_slabs, int chunk_slabs,
+                                              uint32_t stage, long long n_tiles, int n_blocks, int k_slabs, int chunk_slabs, int lead,
                                               long long M, int N, const Epilogue& ep, unsigned long long* dbg, int dbg_flags) {
   constexpr int BLOCK_N = C::kBlockN;
   int acc = 0;
   uint32_t acc_phase = 0;
-  const int n_chunks = (k_slabs + chunk_slabs - 1) / chunk_slabs;
+  int n_chunks = chain_count(k_slabs, chunk_slabs, lead);
   int dbg_chain = 0;   // timeline slot (debug launches only: dbg != nullptr on one warp of cluster 0's leader)
   float* patch = reinterpret_cast<float*>(stage_gen);
-  asm volatile("" : "+r"(stage), "+r"(tfull0), "+r"(tempty0_leader), "+r"(tmem_base));   // keep the addresses in registers
+  // everything the tile loop needs lives in registers from here on (opaque to the compiler): re-deriving these from
+  // special registers / the parameter bank inside the loop costs a dependent S2R / LDC per use
+  asm volatile("" : "+r"(stage), "+r"(tfull0), "+r"(tempty0_leader), "+r"(tmem_base));
+  asm volatile("" : "+l"(M), "+r"(N), "+r"(lane), "+r"(quarter), "+r"(col0), "+r"(rank), "+r"(n_blocks), "+l"(n_tiles),
+               "+r"(n_chunks), "+r"(dbg_flags));
   const EpiRegs er = load_epi_regs(ep);
   const bool fast_store = ep.fast_store != 0;
   for (long long tile = cluster_id_x(); tile < n_tiles; tile += num_clusters_x()) {
@@ -495,7 +511,7 @@ template <int BLOCK_N, int NTERMS, int KIND>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_a_lo,
                 const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_w_lo,
-                long long M, int N, int K, int chunk_slabs, const __grid_constant__ Epilogue ep,
+                long long M, int N, int K, int chunk_slabs, int lead_chains, const __grid_constant__ Epilogue ep,
                 unsigned long long* dbg_buf, int dbg_flags) {
   using C = Config<BLOCK_N, NTERMS, KIND>;
   extern __shared__ uint8_t smem_raw[];
@@ -586,43 +602,74 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
       unsigned long long* dbg_mma = (cluster_id_x() == 0 && lane == 0) ? dbg_buf : nullptr;
       for (long long tile = cluster_id_x(); tile < n_tiles; tile += num_clusters_x()) {
         const uint32_t idesc = C::IDESC_NO_N | ((uint32_t)(tile_width((int)(tile % n_blocks) * BLOCK_N) >> 3) << 17);
-        for (int ks0 = 0; ks0 < k_slabs; ks0 += chunk_slabs) {
-          const int ks1 = ks0 + chunk_slabs < k_slabs ? ks0 + chunk_slabs : k_slabs;
+        const int lead = chain_lead(k_slabs, chunk_slabs, lead_chains);
+        int ks0 = 0;
+        for (int c = 0; ks0 < k_slabs; ++c) {
+          const int span = c < lead ? 2 * chunk_slabs : chunk_slabs;
+          const int ks1 = ks0 + span < k_slabs ? ks0 + span : k_slabs;
           mbar_wait(tempty_bar(acc), acc_phase ^ 1);  // both CTAs' epilogues have drained this accumulator
           tcgen05_fence_after();
           if (dbg_mma && dbg_chain < DBG_CHAINS) dbg_mma[dbg_chain * 8 + 0] = clock64();
           const uint32_t tmem_d = tmem_base + acc * C::ACC_STRIDE;
-          for (int ks = ks0; ks < ks1; ++ks) {
-            mbar_wait(full_bar(stage), phase);
-            tcgen05_fence_after();
-            if (dbg_mma && dbg_chain < DBG_CHAINS) dbg_mma[dbg_chain * 8 + 1] = clock64();
-            if (lane == 0) {
-              const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
-              const uint32_t sb = sa + C::NPLANES * C::A_TILE;
-              const uint64_t da_hi = make_smem_desc(sa), db_hi = make_smem_desc(sb);
-              constexpr int KSTEPS = SLAB_BYTES / UMMA_K_BYTES;
-              const int nk = ks == k_slabs - 1 ? last_ksteps : KSTEPS;
-              if (NTERMS == 3 && KIND == KIND_F16) {
-                // fp16 split: cross terms first (their low planes are stored scaled by 2^11), then the first
-                // hi.hi product rescales the accumulator by 2^-11; one K-slab (64 elements) per chain
+          constexpr int KSTEPS = SLAB_BYTES / UMMA_K_BYTES;
+          if (NTERMS == 3 && KIND == KIND_F16) {
+            // fp16 split: the cross terms of EVERY slab of the chain first (their low planes are stored scaled by
+            // 2^11), then the first hi.hi product rescales the accumulator by 2^-11, then the other hi.hi products.
+            // A chain holds its (1 or 2) pipeline stages until its last product has been issued.
+            int st = stage;
+            uint32_t ph = phase;
+            for (int ks = ks0; ks < ks1; ++ks) {
+              mbar_wait(full_bar(st), ph);
+              tcgen05_fence_after();
+              if (lane == 0) {
+                const uint32_t sa = smem_base + st * C::STAGE_BYTES;
+                const uint32_t sb = sa + C::NPLANES * C::A_TILE;
+                const uint64_t da_hi = make_smem_desc(sa), db_hi = make_smem_desc(sb);
                 const uint64_t da_lo = make_smem_desc(sa + C::A_TILE), db_lo = make_smem_desc(sb + C::B_TILE);
+                const int nk = ks == k_slabs - 1 ? last_ksteps : KSTEPS;
 #pragma unroll
                 for (int k = 0; k < KSTEPS; ++k) {
                   if (k < nk) {
                     const uint64_t koff = (uint64_t)((k * UMMA_K_BYTES) >> 4);
-                    umma_pair<KIND>(da_lo + koff, db_hi + koff, tmem_d, idesc, k > 0 ? 1u : 0u);
+                    umma_pair<KIND>(da_lo + koff, db_hi + koff, tmem_d, idesc, (ks > ks0 || k > 0) ? 1u : 0u);
                     umma_pair<KIND>(da_hi + koff, db_lo + koff, tmem_d, idesc, 1u);
                   }
                 }
-                umma_pair_f16_scale11(da_hi, db_hi, tmem_d, idesc);
+              }
+              __syncwarp();
+              if (++st == C::STAGES) { st = 0; ph ^= 1; }
+            }
+            if (dbg_mma && dbg_chain < DBG_CHAINS) dbg_mma[dbg_chain * 8 + 1] = clock64();
+            for (int ks = ks0; ks < ks1; ++ks) {
+              if (lane == 0) {
+                const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
+                const uint32_t sb = sa + C::NPLANES * C::A_TILE;
+                const uint64_t da_hi = make_smem_desc(sa), db_hi = make_smem_desc(sb);
+                const int nk = ks == k_slabs - 1 ? last_ksteps : KSTEPS;
+                if (ks == ks0) umma_pair_f16_scale11(da_hi, db_hi, tmem_d, idesc);
 #pragma unroll
-                for (int k = 1; k < KSTEPS; ++k) {
-                  if (k < nk) {
+                for (int k = 0; k < KSTEPS; ++k) {
+                  if (k < nk && (k > 0 || ks > ks0)) {
                     const uint64_t koff = (uint64_t)((k * UMMA_K_BYTES) >> 4);
                     umma_pair<KIND>(da_hi + koff, db_hi + koff, tmem_d, idesc, 1u);
                   }
                 }
-              } else {
+                umma_commit_pair(empty_bar(stage));                  // slot free in both CTAs once these MMAs retire
+                if (ks == ks1 - 1) umma_commit_pair(tfull_bar(acc));  // accumulation chain complete (both CTAs)
+              }
+              __syncwarp();
+              if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+            }
+          } else {
+            for (int ks = ks0; ks < ks1; ++ks) {
+              mbar_wait(full_bar(stage), phase);
+              tcgen05_fence_after();
+              if (dbg_mma && dbg_chain < DBG_CHAINS) dbg_mma[dbg_chain * 8 + 1] = clock64();
+              if (lane == 0) {
+                const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
+                const uint32_t sb = sa + C::NPLANES * C::A_TILE;
+                const uint64_t da_hi = make_smem_desc(sa), db_hi = make_smem_desc(sb);
+                const int nk = ks == k_slabs - 1 ? last_ksteps : KSTEPS;
                 if (NTERMS == 3) {  // small terms first: they meet the accumulator while it is smallest
                   const uint64_t da_lo = make_smem_desc(sa + C::A_TILE), db_lo = make_smem_desc(sb + C::B_TILE);
 #pragma unroll
@@ -641,13 +688,14 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
                     umma_pair<KIND>(da_hi + koff, db_hi + koff, tmem_d, idesc, (NTERMS == 3 || ks > ks0 || k > 0) ? 1u : 0u);
                   }
                 }
+                umma_commit_pair(empty_bar(stage));                  // slot free in both CTAs once these MMAs retire
+                if (ks == ks1 - 1) umma_commit_pair(tfull_bar(acc));  // accumulation chain complete (both CTAs)
               }
-              umma_commit_pair(empty_bar(stage));                  // slot free in both CTAs once these MMAs retire
-              if (ks == ks1 - 1) umma_commit_pair(tfull_bar(acc));  // accumulation chain complete (both CTAs)
+              __syncwarp();
+              if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
             }
-            __syncwarp();
-            if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
           }
+          ks0 = ks1;
           if (dbg_mma && dbg_chain < DBG_CHAINS) dbg_mma[dbg_chain * 8 + 2] = clock64();
           ++dbg_chain;
           if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -663,13 +711,13 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     unsigned long long* dbg_epi = (cluster_id_x() == 0 && rank == 0 && warp == FIRST_EPI_WARP && lane == 0) ? dbg_buf : nullptr;
     if (C::HALF0 == C::HALF1)     // one copy of the epilogue code serves both column halves
       epilogue_loop<C, C::HALF0>(warp < FIRST_EPI_WARP + 4 ? 0 : C::HALF0, warp & 3, lane, rank, tmem_base, tfull_bar(0),
-                                 tempty_leader, stage, stage_u32, n_tiles, n_blocks, k_slabs, chunk_slabs, M, N, ep, dbg_epi, dbg_flags);
+                                 tempty_leader, stage, stage_u32, n_tiles, n_blocks, k_slabs, chunk_slabs, lead_chains, M, N, ep, dbg_epi, dbg_flags);
     else if (warp < FIRST_EPI_WARP + 4)
       epilogue_loop<C, C::HALF0>(0, warp & 3, lane, rank, tmem_base, tfull_bar(0), tempty_leader, stage, stage_u32, n_tiles,
-                                 n_blocks, k_slabs, chunk_slabs, M, N, ep, dbg_epi, dbg_flags);
+                                 n_blocks, k_slabs, chunk_slabs, lead_chains, M, N, ep, dbg_epi, dbg_flags);
     else
       epilogue_loop<C, C::HALF1>(C::HALF0, warp & 3, lane, rank, tmem_base, tfull_bar(0), tempty_leader, stage, stage_u32,
-                                 n_tiles, n_blocks, k_slabs, chunk_slabs, M, N, ep, nullptr, dbg_flags);
+                                 n_tiles, n_blocks, k_slabs, chunk_slabs, lead_chains, M, N, ep, nullptr, dbg_flags);
   }
 
   tcgen05_fence_before();
@@ -684,6 +732,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
 
 // host side ---------------------------------------------------------------------------------------
 extern unsigned long long* g_dbg_buf;   // debug timeline buffer (usf_debug_gemm_timeline), normally null
+extern int g_lead_chains;               // leading double-length accumulation chains per tile (usf_set_accum_lead)
 extern int g_dbg_flags;                 // debug: 1 = epilogue skips the TMEM drain, 2 = no store phase
 extern int g_no_fast_store;             // test hook: 1 = always use the register/patch store path (usf_debug_gemm_timeline flag 4)
 
@@ -716,7 +765,8 @@ int launch_gemm_tc2_cfg(const usf_linear_args* a, const Epilogue& ep_in, cudaStr
   const int pairs = num_sms() / 2;
   const int grid = 2 * (int)(tiles < pairs ? tiles : pairs);
   kern<<<grid, tc::NUM_THREADS, C::SMEM_BYTES, st>>>(ma, mal, mw, mwl, a->M, a->N, a->K,
-                                                       NTERMS == 3 ? g_chunk_slabs : 0, ep, g_dbg_buf, g_dbg_flags);
+                                                       NTERMS == 3 ? g_chunk_slabs : 0, (NTERMS == 3 && KIND == tc2::KIND_F16) ? g_lead_chains : 0, ep,
+                                                       g_dbg_buf, g_dbg_flags);
   USF_CUDA_OK(cudaGetLastError());
   return USF_OK;
 }
