@@ -203,7 +203,8 @@ struct EpiRegs {
   float* of32;
   int ldr16, ld16, ldf32;    // row pitches in elements
 };
-constexpr uint32_t EF_BIAS = 1, EF_RELU = 2, EF_RESID16 = 4, EF_OUT16 = 8, EF_OUTF32 = 16, EF_RARE = 32;
+constexpr uint32_t EF_BIAS = 1, EF_RELU = 2, EF_RESID16 = 4, EF_OUT16 = 8, EF_OUTF32 = 16, EF_RARE = 32, EF_RESID32 = 64,
+                   EF_OUTSPLIT = 128, EF_OUTBF16 = 256;
 
 template <class T>
 __device__ __forceinline__ T* launder_ptr(T* p) {   // opaque to the compiler: stays in a register pair
@@ -219,7 +220,10 @@ __device__ __forceinline__ EpiRegs load_epi_regs(const Epilogue& ep) {
   if (ep.resid_h16) f |= EF_RESID16;
   if (ep.out_h16) f |= EF_OUT16;
   if (ep.out_f32) f |= EF_OUTF32;
-  if (ep.resid_hi || ep.colscale || ep.postsub || ep.out_hi || ep.out_bf16) f |= EF_RARE;
+  if (ep.resid_hi) f |= EF_RESID32;
+  if (ep.out_hi) f |= EF_OUTSPLIT;
+  if (ep.out_bf16) f |= EF_OUTBF16;
+  if (ep.colscale || ep.postsub) f |= EF_RARE;
   asm volatile("" : "+r"(f));
   r.flags = f;
   r.sign = ep.resid_sign;
@@ -289,6 +293,24 @@ __device__ __forceinline__ void store_chunk(const Epilogue& ep, const EpiRegs& e
           }
         }
       }
+      if (f & EF_RESID32) {   // fp32 residual stream (bf16 mode) or tf32 split planes (hi + lo)
+        // (the engines other than the fp16-split one: their pointers are read from the parameter bank once per piece)
+        const float* r32lo = ep.resid_lo;
+        const float4* pr = reinterpret_cast<const float4*>(ep.resid_hi + m * ep.ldr + n0);
+        const float4* pl = reinterpret_cast<const float4*>(r32lo + m * ep.ldr + n0);
+#pragma unroll
+        for (int q = 0; q < W / 4; ++q) {
+          if (n0 + q * 4 < N) {
+            float4 r = pr[q];
+            if (r32lo) {
+              const float4 l = pl[q];
+              r.x += l.x; r.y += l.y; r.z += l.z; r.w += l.w;
+            }
+            v[4 * q] = fmaf(er.sign, v[4 * q], r.x); v[4 * q + 1] = fmaf(er.sign, v[4 * q + 1], r.y);
+            v[4 * q + 2] = fmaf(er.sign, v[4 * q + 2], r.z); v[4 * q + 3] = fmaf(er.sign, v[4 * q + 3], r.w);
+          }
+        }
+      }
     }
   }
   if (dbg_slot) t1 = clock64();
@@ -349,8 +371,8 @@ __device__ __forceinline__ void store_chunk(const Epilogue& ep, const EpiRegs& e
     stage_copy_out<RB>(stage, lane, reinterpret_cast<uint8_t*>(er.of32), (long long)er.ldf32 * 4, row0, M, n0 * 4, N * 4);
     __syncwarp();
   }
-  if (f & EF_RARE) {
-    if (ep.out_bf16) {
+  {
+    if (f & EF_OUTBF16) {
       constexpr int RB = W * 2;
 #pragma unroll
       for (int q = 0; q < W / 8; ++q) {
@@ -366,7 +388,7 @@ __device__ __forceinline__ void store_chunk(const Epilogue& ep, const EpiRegs& e
       stage_copy_out<RB>(stage, lane, reinterpret_cast<uint8_t*>(ep.out_bf16), ep.ld_bf16 * 2, row0, M, n0 * 2, N * 2);
       __syncwarp();
     }
-    if (ep.out_hi) {       // tf32 split planes
+    if (f & EF_OUTSPLIT) {   // tf32 split planes
       constexpr int RB = W * 4;
 #pragma unroll
       for (int q = 0; q < W / 4; ++q)
