@@ -122,7 +122,8 @@ int usf_debug_set_impl(int impl);
  * 1 = operands landed, 2 = chain issued, 3 = accumulator full seen by epilogue warp 4, 4 = drained, 5 = tile stored);
  * `flags`: 1 = epilogue skips the TMEM drain, 2 = epilogue skips the store phase (timing experiments only:
  * results are wrong with either flag set); 4 = outputs leave through the generic register/patch store path instead of
- * the staged coalesced one (results identical; tests cover both paths). */
+ * the staged coalesced one; 32 = the epilogue warps copy their staged boxes out themselves instead of issuing
+ * TMA stores (results identical with 4 and 32; tests cover the paths). */
 int usf_debug_gemm_timeline(unsigned long long* device_buf, int flags);
 
 /* ------------------------------------------------------------------------------------------------

@@ -209,7 +209,7 @@ def test_staged_store_path_equals_register_store_path(eng_name, eng, fmt, M, N, 
     w_lo = wact.l16 if fmt == "f16" else wact.lo
     lib = _lib.load()
     results = []
-    for flags in (0, 4):
+    for flags in (0, 4, 32):
         out = Act(M, N, f32=torch.zeros(M, ops.pad4(N), device="cuda")[:, :N],
                   hi=torch.zeros(M, ops.pad4(N), device="cuda")[:, :N], lo=torch.zeros(M, ops.pad4(N), device="cuda")[:, :N],
                   bf16=torch.zeros(M, ops.pad4(N), device="cuda", dtype=torch.bfloat16)[:, :N])
@@ -221,9 +221,41 @@ def test_staged_store_path_equals_register_store_path(eng_name, eng, fmt, M, N, 
         finally:
             lib.usf_debug_gemm_timeline(None, 0)
         results.append(out)
-    p, q = results
-    for name in ("f32", "hi", "lo", "bf16", "h16", "l16"):
-        assert torch.equal(getattr(p, name), getattr(q, name)), name
+    p = results[0]
+    for q in results[1:]:
+        for name in ("f32", "hi", "lo", "bf16", "h16", "l16"):
+            assert torch.equal(getattr(p, name), getattr(q, name)), name
     # padding columns beyond N stay untouched
     if ops.pad4(N) != N:
         assert float(p.f32._base[:, N:].abs().max()) == 0.0 and float(p.h16._base[..., N:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("M,N,K", [(300, 784, 392), (70000, 1024, 128), (515, 400, 1024), (130, 608, 72), (64, 48, 40)])
+def test_tma_store_path_equals_inline_store(M, N, K):
+    """fp16-split planes only (the hot configuration): boxes stored by TMA == stored by the epilogue warps themselves,
+    including the in-place coupling form (residual read from the planes that are written)."""
+    from usflows_b200 import _lib, ops
+    from usflows_b200.ops import Act
+    g = torch.Generator().manual_seed(M + N + K)
+    a = torch.randn(M, K, generator=g)
+    w = torch.randn(N, K, generator=g) / K ** 0.5
+    bias = torch.randn(N, generator=g).cuda()
+    x0 = torch.randn(M, N, generator=g)
+    act, _ = _f16_planes(a)
+    wact, _ = _f16_planes(w)
+    lib = _lib.load()
+    outs = []
+    for flags in (0, 32, 4):
+        stream, _ = _f16_planes(x0)                       # fresh copy of the stream for the in-place update
+        lib.usf_debug_gemm_timeline(None, flags)
+        try:
+            ops.linear(ops.ENGINE_TC_3XF16, act, wact.h16, wact.l16, N, K, bias=bias, resid=stream, resid_sign=-1.0,
+                       out=Act(M, N, h16=stream.h16, l16=stream.l16))
+            torch.cuda.synchronize()
+        finally:
+            lib.usf_debug_gemm_timeline(None, 0)
+        outs.append(stream)
+    for q in outs[1:]:
+        assert torch.equal(outs[0].h16, q.h16) and torch.equal(outs[0].l16, q.l16)
+    ref = x0.double() - (a.double() @ w.double().T + bias.double().cpu())
+    assert rel_err(outs[0].h16.double() + outs[0].l16.double() / 2048.0, ref) <= 2e-5

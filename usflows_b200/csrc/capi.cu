@@ -15,6 +15,7 @@ int g_tc_impl = 2;
 unsigned long long* g_dbg_buf = nullptr;
 int g_dbg_flags = 0;
 int g_no_fast_store = 0;
+int g_no_async_store = 0;
 
 int num_sms() {
   static int cached[64] = {0};
@@ -84,6 +85,7 @@ int make_epilogue(const usf_linear_args* a, Epilogue* ep) {
   if (a->out_bf16) ok = ok && aligned16(a->out_bf16) && a->ld_bf16 % 8 == 0;
   ep->vec_ok = ok ? 1 : 0;
   ep->fast_store = 0;  // set by the pair-kernel launcher
+  ep->async_store = 0;
   return USF_OK;
 }
 
@@ -122,8 +124,9 @@ int usf_debug_set_impl(int impl) {  // test hook: 2 = CTA-pair tcgen05 kernel (d
 
 int usf_debug_gemm_timeline(unsigned long long* device_buf, int flags) {
   g_dbg_buf = device_buf;
-  g_dbg_flags = flags & ~4;
+  g_dbg_flags = flags & ~(4 | 32);
   g_no_fast_store = (flags & 4) ? 1 : 0;
+  g_no_async_store = (flags & 32) ? 1 : 0;
   return USF_OK;
 }
 

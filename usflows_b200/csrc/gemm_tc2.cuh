@@ -410,12 +410,95 @@ __device__ __forceinline__ void store_chunk(const Epilogue& ep, const EpiRegs& e
   }
 }
 
+// ---- asynchronous store path (fp16-split planes only) ---------------------------------------------------------------
+// The epilogue warp converts 16 columns of its row at a time into one of two 2 KB staging buffers (32-byte rows in the
+// hardware's 32B swizzle) and one lane issues two TMA tensor stores (hi box, lo box).  The stores run asynchronously:
+// the SM -> L2 write path (~32 B/cycle/SM, >= 4 096 cycles for the 128 KB of one tile) works under the conversion of
+// the next pieces and under the next tile's main loop, and the M / N edges are clipped by the hardware.
+struct StoreMaps { CUtensorMap h16, l16; };    // [M rows, N cols] fp16, box = 32 rows x 16 columns, SWIZZLE_32B
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+constexpr int ASYNC_W = 16;                        // columns per hand-over
+constexpr int ASYNC_BUF_BYTES = 2 * 32 * ASYNC_W * 2;   // hi box + lo box = 2 KB
+
+__device__ __forceinline__ void async_math16(const EpiRegs& er, float (&v)[ASYNC_W], long long m, bool row_ok, int n0, int N) {
+  const uint32_t f = er.flags;
+  constexpr int W = ASYNC_W;
+  if (!row_ok) return;
+  if (f & EF_BIAS) {
+    const float4* pb = reinterpret_cast<const float4*>(er.bias + n0);
+#pragma unroll
+    for (int q = 0; q < W / 8; ++q) {
+      if (n0 + 8 * q < N) {          // N % 8 == 0: a group of eight columns is inside or outside as a whole
+        const float4 b0 = __ldg(pb + 2 * q), b1 = __ldg(pb + 2 * q + 1);
+        v[8 * q] += b0.x; v[8 * q + 1] += b0.y; v[8 * q + 2] += b0.z; v[8 * q + 3] += b0.w;
+        v[8 * q + 4] += b1.x; v[8 * q + 5] += b1.y; v[8 * q + 6] += b1.z; v[8 * q + 7] += b1.w;
+      }
+    }
+  }
+  if (f & EF_RELU) {
+#pragma unroll
+    for (int i = 0; i < W; ++i) v[i] = fmaxf(v[i], 0.f);
+  }
+  if (f & EF_RESID16) {   // coupling: x -/+ t with x in fp16 split planes (possibly the planes being written: in place)
+    const uint4* ph = reinterpret_cast<const uint4*>(er.rh + m * er.ldr16 + n0);
+    const uint4* pl = reinterpret_cast<const uint4*>(er.rl + m * er.ldr16 + n0);
+#pragma unroll
+    for (int q = 0; q < W / 8; ++q) {
+      if (n0 + 8 * q < N) {
+        const uint4 h8 = ph[q], l8 = pl[q];
+        const __half2* h2 = reinterpret_cast<const __half2*>(&h8);
+        const __half2* l2 = reinterpret_cast<const __half2*>(&l8);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 hf = __half22float2(h2[e]), lf = __half22float2(l2[e]);
+          v[8 * q + 2 * e] = fmaf(er.sign, v[8 * q + 2 * e], fmaf(lf.x, F16_LO_UNSCALE, hf.x));
+          v[8 * q + 2 * e + 1] = fmaf(er.sign, v[8 * q + 2 * e + 1], fmaf(lf.y, F16_LO_UNSCALE, hf.y));
+        }
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void async_stage16(const Epilogue& ep, const float (&v)[ASYNC_W], bool row_ok, int lane, int n0,
+                                              int N, uint32_t buf) {
+  constexpr int W = ASYNC_W;
+  constexpr int RB = W * 2;
+  __half2 amax2 = __float2half2_rn(0.f);
+#pragma unroll
+  for (int q = 0; q < W / 8; ++q) {
+    uint32_t hp[4], lp[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float x0 = v[q * 8 + 2 * e], x1 = v[q * 8 + 2 * e + 1];
+      const __half2 h = __floats2half2_rn(x0, x1);
+      const float2 hf = __half22float2(h);
+      const __half2 l = __floats2half2_rn((x0 - hf.x) * F16_LO_SCALE, (x1 - hf.y) * F16_LO_SCALE);
+      hp[e] = *reinterpret_cast<const uint32_t*>(&h);
+      lp[e] = *reinterpret_cast<const uint32_t*>(&l);
+      if (n0 + 8 * q < N) amax2 = __hmax2_nan(amax2, __habs2(h));   // columns past N hold no result
+    }
+    sts128(buf + stage_off<RB>(lane, q), hp[0], hp[1], hp[2], hp[3]);
+    sts128(buf + 32 * RB + stage_off<RB>(lane, q), lp[0], lp[1], lp[2], lp[3]);
+  }
+  const float2 am = __half22float2(amax2);
+  if (!(am.x <= F16_GUARD && am.y <= F16_GUARD) && row_ok && ep.overflow_flag) *ep.overflow_flag = 1;
+}
+
 // One epilogue warp: TMEM lanes [32*quarter, +32) x columns [col0, col0+COLS) of every tile of this CTA.
 template <class C, int COLS>
 __device__ __forceinline__ void epilogue_loop(int col0, int quarter, int lane, uint32_t rank, uint32_t tmem_base,
                                               uint32_t tfull0, uint32_t tempty0_leader, uint8_t* stage_gen,
                                               uint32_t stage, long long n_tiles, int n_blocks, int k_slabs, int chunk_slabs, int lead,
-                                              long long M, int N, const Epilogue& ep, unsigned long long* dbg, int dbg_flags) {
+                                              long long M, int N, const Epilogue& ep, unsigned long long* dbg, int dbg_flags,
+                                              const StoreMaps& smaps) {
   constexpr int BLOCK_N = C::kBlockN;
   int acc = 0;
   uint32_t acc_phase = 0;
@@ -429,6 +512,8 @@ __device__ __forceinline__ void epilogue_loop(int col0, int quarter, int lane, u
                "+r"(n_chunks), "+r"(dbg_flags));
   const EpiRegs er = load_epi_regs(ep);
   const bool fast_store = ep.fast_store != 0;
+  const bool async_store = ep.async_store != 0;
+  uint32_t hand = 0;     // TMA store groups committed so far: staging buffer = hand & 1
   for (long long tile = cluster_id_x(); tile < n_tiles; tile += num_clusters_x()) {
     const long long m_idx = (tile / n_blocks) * (2 * BLOCK_M) + rank * BLOCK_M;
     const int n_idx = (int)(tile % n_blocks) * BLOCK_N;
@@ -482,7 +567,36 @@ __device__ __forceinline__ void epilogue_loop(int col0, int quarter, int lane, u
     }
     if (dbg_flags & 2) continue;   // debug: no store phase
     const long long row0 = m_idx + quarter * 32;
-    if (fast_store) {
+    if (async_store) {
+      if (row0 < M) {
+        const long long m = row0 + lane;
+        const bool row_ok = m < M;
+        const long long t_start = dbg ? clock64() : 0;
+#pragma unroll
+        for (int c = 0; c < COLS / ASYNC_W; ++c) {
+          const int n0 = n_idx + col0 + c * ASYNC_W;
+          if (n0 < N) {
+            float(&piece)[ASYNC_W] = *reinterpret_cast<float(*)[ASYNC_W]>(&master[c * ASYNC_W]);
+            async_math16(er, piece, m, row_ok, n0, N);
+            const uint32_t buf = stage + (hand & 1) * ASYNC_BUF_BYTES;
+            if (hand >= 2) {                                  // the store that last read this buffer has drained it
+              if (lane == 0) bulk_wait_read1();
+              __syncwarp();
+            }
+            async_stage16(ep, piece, row_ok, lane, n0, N, buf);
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&smaps.h16, buf, n0, (int)row0);
+              tma_store_2d(&smaps.l16, buf + 32 * ASYNC_W * 2, n0, (int)row0);
+              bulk_commit();
+            }
+            ++hand;
+          }
+        }
+        if (dbg && dbg_chain - 1 < DBG_CHAINS) dbg[(dbg_chain - 1) * 8 + 6] = (unsigned long long)(clock64() - t_start) << 32;
+      }
+    } else if (fast_store) {
       if (row0 < M) {
 #pragma unroll
         for (int c = 0; c < COLS / 32; ++c) {
@@ -527,6 +641,8 @@ __device__ __forceinline__ void epilogue_loop(int col0, int quarter, int lane, u
     }
     if (dbg && dbg_chain - 1 < DBG_CHAINS) dbg[(dbg_chain - 1) * 8 + 5] = clock64();
   }
+  if (async_store && lane == 0) bulk_wait0();   // staging memory and the stores outlive their reads / writes
+  __syncwarp();
 }
 
 template <int BLOCK_N, int NTERMS, int KIND>
@@ -534,7 +650,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_a_lo,
                 const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_w_lo,
                 long long M, int N, int K, int chunk_slabs, int lead_chains, const __grid_constant__ Epilogue ep,
-                unsigned long long* dbg_buf, int dbg_flags) {
+                const __grid_constant__ StoreMaps smaps, unsigned long long* dbg_buf, int dbg_flags) {
   using C = Config<BLOCK_N, NTERMS, KIND>;
   extern __shared__ uint8_t smem_raw[];
   uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // same offset in both CTAs of the pair
@@ -733,13 +849,13 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     unsigned long long* dbg_epi = (cluster_id_x() == 0 && rank == 0 && warp == FIRST_EPI_WARP && lane == 0) ? dbg_buf : nullptr;
     if (C::HALF0 == C::HALF1)     // one copy of the epilogue code serves both column halves
       epilogue_loop<C, C::HALF0>(warp < FIRST_EPI_WARP + 4 ? 0 : C::HALF0, warp & 3, lane, rank, tmem_base, tfull_bar(0),
-                                 tempty_leader, stage, stage_u32, n_tiles, n_blocks, k_slabs, chunk_slabs, lead_chains, M, N, ep, dbg_epi, dbg_flags);
+                                 tempty_leader, stage, stage_u32, n_tiles, n_blocks, k_slabs, chunk_slabs, lead_chains, M, N, ep, dbg_epi, dbg_flags, smaps);
     else if (warp < FIRST_EPI_WARP + 4)
       epilogue_loop<C, C::HALF0>(0, warp & 3, lane, rank, tmem_base, tfull_bar(0), tempty_leader, stage, stage_u32, n_tiles,
-                                 n_blocks, k_slabs, chunk_slabs, lead_chains, M, N, ep, dbg_epi, dbg_flags);
+                                 n_blocks, k_slabs, chunk_slabs, lead_chains, M, N, ep, dbg_epi, dbg_flags, smaps);
     else
       epilogue_loop<C, C::HALF1>(C::HALF0, warp & 3, lane, rank, tmem_base, tfull_bar(0), tempty_leader, stage, stage_u32,
-                                 n_tiles, n_blocks, k_slabs, chunk_slabs, lead_chains, M, N, ep, nullptr, dbg_flags);
+                                 n_tiles, n_blocks, k_slabs, chunk_slabs, lead_chains, M, N, ep, nullptr, dbg_flags, smaps);
   }
 
   tcgen05_fence_before();
@@ -756,7 +872,27 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
 extern unsigned long long* g_dbg_buf;   // debug timeline buffer (usf_debug_gemm_timeline), normally null
 extern int g_lead_chains;               // leading double-length accumulation chains per tile (usf_set_accum_lead)
 extern int g_dbg_flags;                 // debug: 1 = epilogue skips the TMEM drain, 2 = no store phase
+extern int g_no_async_store;            // test hook: 1 = the epilogue warps store themselves (flag 32)
 extern int g_no_fast_store;             // test hook: 1 = always use the register/patch store path (usf_debug_gemm_timeline flag 4)
+
+// fp16 output plane [rows, cols] (row pitch ld halves) for the TMA store path: box = 32 rows x 16 columns, 32B swizzle
+inline int make_store_map16(CUtensorMap* map, const void* ptr, long long rows, long long cols, long long ld) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (!enc) return fail(USF_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available%s%s");
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)tc2::ASYNC_W, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    snprintf(g_err, sizeof(g_err), "cuTensorMapEncodeTiled (store map) failed with CUresult %d (rows=%lld cols=%lld ld=%lld)",
+             (int)r, rows, cols, ld);
+    return USF_ERR_CUDA;
+  }
+  return USF_OK;
+}
 
 template <int BLOCK_N, int NTERMS, int KIND>
 int launch_gemm_tc2_cfg(const usf_linear_args* a, const Epilogue& ep_in, cudaStream_t st) {
@@ -783,11 +919,19 @@ int launch_gemm_tc2_cfg(const usf_linear_args* a, const Epilogue& ep_in, cudaStr
   // coalesced store path; anything else through the generic register/patch path
   Epilogue ep = ep_in;
   ep.fast_store = (ep.vec_ok && a->N % 8 == 0 && !g_no_fast_store) ? 1 : 0;
+  ep.async_store = (ep.fast_store && !g_no_async_store && ep.out_h16 && !ep.out_f32 && !ep.out_hi && !ep.out_bf16 &&
+                    !ep.colscale && !ep.postsub && !ep.resid_hi) ? 1 : 0;
+  tc2::StoreMaps sm;
+  memset(&sm, 0, sizeof(sm));
+  if (ep.async_store) {
+    if ((rc = make_store_map16(&sm.h16, ep.out_h16, a->M, a->N, ep.ld_16))) return rc;
+    if ((rc = make_store_map16(&sm.l16, ep.out_l16, a->M, a->N, ep.ld_16))) return rc;
+  }
   const long long tiles = ((a->M + 2 * tc::BLOCK_M - 1) / (2 * tc::BLOCK_M)) * ((a->N + BLOCK_N - 1) / BLOCK_N);
   const int pairs = num_sms() / 2;
   const int grid = 2 * (int)(tiles < pairs ? tiles : pairs);
   kern<<<grid, tc::NUM_THREADS, C::SMEM_BYTES, st>>>(ma, mal, mw, mwl, a->M, a->N, a->K,
-                                                       NTERMS == 3 ? g_chunk_slabs : 0, (NTERMS == 3 && KIND == tc2::KIND_F16) ? g_lead_chains : 0, ep,
+                                                       NTERMS == 3 ? g_chunk_slabs : 0, (NTERMS == 3 && KIND == tc2::KIND_F16) ? g_lead_chains : 0, ep, sm,
                                                        g_dbg_buf, g_dbg_flags);
   USF_CUDA_OK(cudaGetLastError());
   return USF_OK;
