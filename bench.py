@@ -60,10 +60,9 @@ def measured_peaks():
     if os.path.exists(p):
         with open(p) as f:
             return json.load(f), "measured"
-    # MEASURED_PEAKS.json is driver-written and git-ignored; when it is absent use the values it held at survey
-    # time (this pool's B200s), which are measurements, not the guide's generic fallback
-    return {"hbm_gbs": 6553.9, "bf16_tflops": 1614.3, "bf16_tflops_sustained": 1384.6}, \
-        "MEASURED_PEAKS.json absent; values recorded from it in SURVEY.md section 6"
+    # MEASURED_PEAKS.json is driver-written; when it is absent use the fallback /opt/skills/guides/B200_PROFILING.md
+    # states (6.65 TB/s, 1.59 PFLOP/s burst, ~1.4 PFLOP/s sustained under the power cap) and say so
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
 
 
 class ClockSampler:
@@ -266,6 +265,13 @@ def main():
     breakdown = engine.profile_step(lambda: flow.log_prob(x))
     gemm_ms = sum(v for k, v in breakdown.items() if k.startswith("linear"))
     peaks, peak_kind = measured_peaks()
+    # DRAM traffic of the dominant kernel per launch, from the committed ncu --set full capture (profiles/): the mean of
+    # dram__bytes_read.sum + dram__bytes_write.sum over the captured launches of one step
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(tpath) and args.workload == "c2" and args.precision == "fp32":
+        with open(tpath) as f:
+            traffic = json.load(f).get("dram_bytes_per_launch")
     achieved_tf = rows * flops_per_sample / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
     peak_tf = peaks["bf16_tflops_sustained"]
     n_gemm = sum(1 for k in breakdown.get("_names", []) if k.startswith("linear")) or 1
@@ -340,8 +346,9 @@ def main():
                     chunk_rows=engine._default_chunk_rows, l2="inputs larger than L2, no flush",
                     flops_per_sample=flops_per_sample, prep_ms_once_per_weight_version=prep_ms),
         roofline=dict(bound="tensor", achieved=achieved_tf, peak=peak_tf, unit="TFLOP/s",
-                      frac=achieved_tf / peak_tf, traffic=None, peak_source=f"bf16_tflops_sustained ({peak_kind})",
-                      kernel="tc::gemm_tc_kernel (all launches of one step)", kernel_ms_per_step=gemm_ms,
+                      frac=achieved_tf / peak_tf, traffic=traffic,
+                      peak_source=f"bf16_tflops_sustained, of {peak_kind}",
+                      kernel="tc2::gemm_tc2_kernel (CTA-pair tcgen05, all launches of one step)", kernel_ms_per_step=gemm_ms,
                       launches_per_step=n_gemm,
                       note="algorithmic fp32 FLOPs over the summed CUDA-event time of the GEMM launches of one step; "
                            "the fp32 mode spends 3 fp16 MMAs per algorithmic MAC (fp16 runs at the bf16 rate), so its "

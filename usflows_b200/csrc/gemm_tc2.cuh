@@ -428,21 +428,24 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 constexpr int ASYNC_W = 16;                        // columns per hand-over
 constexpr int ASYNC_BUF_BYTES = 2 * 32 * ASYNC_W * 2;   // hi box + lo box = 2 KB
 
-__device__ __forceinline__ void async_math16(const EpiRegs& er, float (&v)[ASYNC_W], long long m, bool row_ok, int n0, int N) {
+// `bias4` = this lane's four bias values of the warp's column range (lane l holds columns 4l .. 4l+3 of the range,
+// loaded once per tile before the last drain); piece `piece` (16 columns) takes its values from lanes 4*piece .. +3
+// by shuffle, so no global load sits between two TMA stores
+__device__ __forceinline__ void async_math16(const EpiRegs& er, float (&v)[ASYNC_W], const float4& bias4, int piece,
+                                             long long m, bool row_ok, int n0, int N) {
   const uint32_t f = er.flags;
   constexpr int W = ASYNC_W;
-  if (!row_ok) return;
-  if (f & EF_BIAS) {
-    const float4* pb = reinterpret_cast<const float4*>(er.bias + n0);
+  if (f & EF_BIAS) {                 // (all lanes take part in the shuffles)
 #pragma unroll
-    for (int q = 0; q < W / 8; ++q) {
-      if (n0 + 8 * q < N) {          // N % 8 == 0: a group of eight columns is inside or outside as a whole
-        const float4 b0 = __ldg(pb + 2 * q), b1 = __ldg(pb + 2 * q + 1);
-        v[8 * q] += b0.x; v[8 * q + 1] += b0.y; v[8 * q + 2] += b0.z; v[8 * q + 3] += b0.w;
-        v[8 * q + 4] += b1.x; v[8 * q + 5] += b1.y; v[8 * q + 6] += b1.z; v[8 * q + 7] += b1.w;
-      }
+    for (int q = 0; q < W / 4; ++q) {
+      const int src = piece * (W / 4) + q;
+      v[4 * q] += __shfl_sync(0xffffffffu, bias4.x, src);
+      v[4 * q + 1] += __shfl_sync(0xffffffffu, bias4.y, src);
+      v[4 * q + 2] += __shfl_sync(0xffffffffu, bias4.z, src);
+      v[4 * q + 3] += __shfl_sync(0xffffffffu, bias4.w, src);
     }
   }
+  if (!row_ok) return;
   if (f & EF_RELU) {
 #pragma unroll
     for (int i = 0; i < W; ++i) v[i] = fmaxf(v[i], 0.f);
@@ -531,7 +534,12 @@ __device__ __forceinline__ void epilogue_loop(int col0, int quarter, int lane, u
     float master[COLS > 0 ? COLS : 1];
 #pragma unroll
     for (int i = 0; i < COLS; ++i) master[i] = 0.f;
+    float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int c = 0; c < n_chunks; ++c) {
+      if (c == n_chunks - 1 && async_store && (er.flags & EF_BIAS)) {   // in flight during the last drain
+        const int nb = n_idx + col0 + 4 * lane;
+        if (4 * lane < COLS && nb < N) bias4 = __ldg(reinterpret_cast<const float4*>(er.bias + nb));
+      }
       mbar_wait(tfull0 + 8u * acc, acc_phase);
       tcgen05_fence_after();
       if (dbg && dbg_chain < DBG_CHAINS) dbg[dbg_chain * 8 + 3] = clock64();
@@ -577,7 +585,7 @@ __device__ __forceinline__ void epilogue_loop(int col0, int quarter, int lane, u
           const int n0 = n_idx + col0 + c * ASYNC_W;
           if (n0 < N) {
             float(&piece)[ASYNC_W] = *reinterpret_cast<float(*)[ASYNC_W]>(&master[c * ASYNC_W]);
-            async_math16(er, piece, m, row_ok, n0, N);
+            async_math16(er, piece, bias4, c, m, row_ok, n0, N);
             const uint32_t buf = stage + (hand & 1) * ASYNC_BUF_BYTES;
             if (hand >= 2) {                                  // the store that last read this buffer has drained it
               if (lane == 0) bulk_wait_read1();
