@@ -336,6 +336,27 @@ def main():
                           f"reference (torch CPU, per-call weight re-preparation as the reference does)",
                    amortised_value=v_am)
 
+    roofline = dict(bound="tensor", achieved=achieved_tf, peak=peak_tf, unit="TFLOP/s",
+                    frac=achieved_tf / peak_tf, traffic=traffic,
+                    peak_source=f"bf16_tflops_sustained, of {peak_kind}",
+                    kernel="tc2::gemm_tc2_kernel (CTA-pair tcgen05, all launches of one step)", kernel_ms_per_step=gemm_ms,
+                    launches_per_step=n_gemm,
+                    note="algorithmic fp32 FLOPs over the summed CUDA-event time of the GEMM launches of one step; "
+                         "the fp32 mode spends 3 fp16 MMAs per algorithmic MAC (fp16 runs at the bf16 rate), so its "
+                         "ceiling is 1/3 of this peak (1/6 for fp32_tf32)",
+                    frac_of_mode_ceiling=(achieved_tf / (peak_tf / {"fp32": 3.0, "fp32_tf32": 6.0}[args.precision]))
+                    if args.precision in ("fp32", "fp32_tf32") else None)
+    if breakdown.get("flow_small"):
+        # tiny event size: the whole stack is one FP32-FMA bound launch (usf_flow_small); neither HBM nor the tensor pipe
+        # bounds it, so the figure is set against the nominal FP32 FMA rate of the part (stated, not measured)
+        sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
+        fma_peak = sm_count * 128 * 2 * 1.965e9 / 1e12
+        ach = rows * flops_per_sample / (breakdown["flow_small"] * 1e-3) / 1e12
+        roofline = dict(bound="fp32_fma", achieved=ach, peak=fma_peak, unit="TFLOP/s", frac=ach / fma_peak, traffic=None,
+                        peak_source="nominal: SMs x 128 FMA lanes x 2 x 1965 MHz", kernel="flow_small_kernel",
+                        kernel_ms_per_step=breakdown["flow_small"], launches_per_step=1,
+                        hbm_gbs_for_context=rows * (4 * d + 4) / (breakdown["flow_small"] * 1e-3) / 1e9)
+
     line = dict(
         base_line, impl="usflows_b200", value=value, ms_per_step=ms_step,
         dtype={"fp32": "f32 (fp16-split x3 on tcgen05 kind::f16, fp32 accumulate/promote; tf32-split fallback)",
@@ -345,16 +366,7 @@ def main():
                     coupling_blocks=spec["coupling_blocks"], precision=args.precision,
                     chunk_rows=engine._default_chunk_rows, l2="inputs larger than L2, no flush",
                     flops_per_sample=flops_per_sample, prep_ms_once_per_weight_version=prep_ms),
-        roofline=dict(bound="tensor", achieved=achieved_tf, peak=peak_tf, unit="TFLOP/s",
-                      frac=achieved_tf / peak_tf, traffic=traffic,
-                      peak_source=f"bf16_tflops_sustained, of {peak_kind}",
-                      kernel="tc2::gemm_tc2_kernel (CTA-pair tcgen05, all launches of one step)", kernel_ms_per_step=gemm_ms,
-                      launches_per_step=n_gemm,
-                      note="algorithmic fp32 FLOPs over the summed CUDA-event time of the GEMM launches of one step; "
-                           "the fp32 mode spends 3 fp16 MMAs per algorithmic MAC (fp16 runs at the bf16 rate), so its "
-                           "ceiling is 1/3 of this peak (1/6 for fp32_tf32)",
-                      frac_of_mode_ceiling=(achieved_tf / (peak_tf / {"fp32": 3.0, "fp32_tf32": 6.0}[args.precision]))
-                      if args.precision in ("fp32", "fp32_tf32") else None),
+        roofline=roofline,
         cpu_baseline=cpu,
         e2e=dict(value=world * rows / (ms_e2e * 1e-3), unit="samples/s", ms_per_step=ms_e2e,
                  h2d_bytes_per_step=rows * d * 4, d2h_bytes_per_step=rows * 4),

@@ -127,6 +127,19 @@ int usf_debug_set_impl(int impl);
 int usf_debug_gemm_timeline(unsigned long long* device_buf, int flags);
 
 /* ------------------------------------------------------------------------------------------------
+ * whole layer stack in one launch for tiny event sizes (d <= 8, conditioner width <= 64): replaces the per-layer loop
+ * of Flow.log_prob / Flow.sample (flows.py:234-245, 258-265) where a layer is far below one MMA tile (BASELINE config C1:
+ * d = 2, H = 32).  Rows and hidden activations live in registers, the weights of all layers in shared memory.
+ *   prog : n_ops pairs (code, offset): code = 0 affine `x <- W x + c` (W [D,D] row-major then c [D] at blob + offset) or
+ *          1 | (n_mid << 8) coupling `x <- x + W_last relu(.. relu(W_0 x + b_0) ..) + b_last` with blocks
+ *          W_0 [H,D], b_0 [H], n_mid x (W [H,H], b [H]), W_last [D,H], b_last [D]; mask and sign folded into W_0 / W_last.
+ *   blob : fp32 weights, 16-byte aligned, every op block starting at a multiple of 4 floats; d padded to D in {2,4,8}
+ *          (identity / zero padding), hidden widths padded to H in {32,64} with zeros.
+ * out [rows, d] receives the transformed rows (the base density runs through usf_base_logprob). */
+int usf_flow_small(const float* x, int64_t ldx, int64_t rows, int32_t d, const int32_t* prog, int32_t n_ops,
+                   const float* blob, int32_t blob_floats, int32_t D, int32_t H, float* out, int64_t ldo, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * elementwise / reduction kernels over [N_rows, d] activations (HBM-bound, 128-bit accesses)
  */
 

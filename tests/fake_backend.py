@@ -115,6 +115,33 @@ def base_sample(out, loc, scale, kind, seed, offset):
     _store(out, loc + scale * e)
 
 
+def flow_small(x, prog_i32, blob, n_ops, D, H, out):
+    """The op-list semantics of usf_flow_small (include/usflows_b200.h), row by row in torch."""
+    CALLS.append(("flow_small", n_ops, D, H))
+    rows, d = x.shape
+    v = torch.zeros(rows, D)
+    v[:, :d] = x
+    prog = prog_i32.tolist()
+    for op in range(n_ops):
+        code, off = prog[2 * op], prog[2 * op + 1]
+        w = blob[off:]
+        if code & 0xff == 0:
+            W, c = w[:D * D].reshape(D, D), w[D * D:D * D + D]
+            v = v @ W.T + c
+        else:
+            n_mid = code >> 8
+            W0, b0 = w[:H * D].reshape(H, D), w[H * D:H * D + H]
+            h = torch.relu(v @ W0.T + b0)
+            w = w[H * D + H:]
+            for _ in range(n_mid):
+                Wm, bm = w[:H * H].reshape(H, H), w[H * H:H * H + H]
+                h = torch.relu(h @ Wm.T + bm)
+                w = w[H * H + H:]
+            Wl, bl = w[:D * H].reshape(D, H), w[D * H:D * H + D]
+            v = v + (h @ Wl.T + bl)
+    out.copy_(v[:, :d])
+
+
 def leaky_relu(x, slope, y, neg_count=None):
     y.copy_(torch.where(x >= 0, x, x * slope))
     if neg_count is not None:
@@ -205,7 +232,7 @@ def require_cuda(t, name="tensor", dtype=torch.float32):
 
 def install(monkeypatch):
     CALLS.clear()
-    for name in ["linear", "ingest", "base_logprob", "base_sample", "leaky_relu", "permute", "lu_assemble",
+    for name in ["flow_small", "linear", "ingest", "base_logprob", "base_sample", "leaky_relu", "permute", "lu_assemble",
                  "lu_logabsdet", "vec_logabs", "tri_inverse", "transpose", "scale_rows_cols", "split_tf32", "split_f16", "to_bf16",
                  "householder_right", "softplus", "matmul_f32", "matmul_f64", "require_cuda"]:
         monkeypatch.setattr(real_ops, name, globals()[name])

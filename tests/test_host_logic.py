@@ -166,3 +166,27 @@ def test_individual_layers(fake_ops):
     x = torch.arange(dim, dtype=torch.float32).reshape(1, dim)
     assert (t(x) == x).all() and (t.backward(x) == x).all()
     assert float(t.log_abs_det_jacobian(x, x)) == 0
+
+
+@pytest.mark.parametrize("name,fused", [("c1_d2_laplace", True), ("d6_hh_normal", True), ("d5_noconj", True),
+                                         ("d32_h64", False)])
+def test_tiny_flows_run_as_one_launch(fake_ops, name, fused):
+    """d <= 8 with conditioner width <= 64: the whole layer stack is one usf_flow_small launch (+ the base density);
+    wider flows keep the per-layer contractions.  Switching the fusion off gives the same numbers."""
+    import fake_backend
+    from usflows_b200 import engine
+    spec, params, arr = load_case(name)
+    flow = build_flow(spec, params, device="cpu", precision="fp32")
+    fake_backend.CALLS.clear()
+    lp = flow.log_prob(arr["x"])
+    kinds = [c[0] for c in fake_backend.CALLS]
+    assert ("flow_small" in kinds) == fused
+    if fused:
+        assert kinds.count("flow_small") == 1 and "linear" not in kinds and kinds.count("base_logprob") == 1
+        engine.FUSE_SMALL = False
+        try:
+            flow2 = build_flow(spec, params, device="cpu", precision="fp32")
+            assert rel_err(flow2.log_prob(arr["x"]), lp) < 2e-5      # fp32 both ways, different summation order
+            assert rel_err(flow2._forward(arr["z0"]), flow._forward(arr["z0"])) < 2e-5
+        finally:
+            engine.FUSE_SMALL = True

@@ -1,6 +1,7 @@
 // C ABI of libusflows_b200.so (see include/usflows_b200.h for the contract of every entry point).
 #include "common.cuh"
 #include "elementwise.cuh"
+#include "flow_small.cuh"
 #include "gemm_simt.cuh"
 #include "gemm_tc2.cuh"
 #include "prep.cuh"
@@ -157,6 +158,12 @@ int usf_linear(const usf_linear_args* a, void* stream) {
     case USF_ENGINE_TC_3XF16: return launch_gemm_tc(a, ep, S(stream));
   }
   return fail(USF_ERR_INVALID, "unknown engine%s%s");
+}
+
+int usf_flow_small(const float* x, int64_t ldx, int64_t rows, int32_t d, const int32_t* prog, int32_t n_ops,
+                   const float* blob, int32_t blob_floats, int32_t D, int32_t H, float* out, int64_t ldo, void* stream) {
+  USF_REQUIRE(x && prog && blob && out && rows >= 0 && n_ops >= 0 && blob_floats > 0, "bad input");
+  return launch_flow_small(x, ldx, rows, d, prog, n_ops, blob, blob_floats, D, H, out, ldo, S(stream));
 }
 
 int usf_ingest(const float* x, int64_t ldx, int64_t rows, int32_t d, const float* dv, const float* mul,

@@ -40,6 +40,7 @@ MERGE_AFFINE = False     # compose NEIGHBOURING dense affine layers (Aff_i^-1 . 
                          # the condition numbers of BOTH layers (the chained form only by one) -- measured 3-4x
                          # further from the fp64 evaluation than the reference on the ill-conditioned fixtures
 COMPRESS_MASK = True     # run couplings on contiguous column halves when the mask allows it
+FUSE_SMALL = True        # d <= 8 and conditioner width <= 64: the whole layer stack in ONE launch (usf_flow_small)
 
 
 def set_precision(mode: str) -> None:
@@ -255,6 +256,7 @@ class Program:
                 items.append(p)
         flush()
         self.items = items
+        self.small = self._pack_small(items) if FUSE_SMALL else None
         # 2. widths, engine choice (tiny problems run the whole program on the SIMT engine)
         dims = []
         for p in items:
@@ -273,6 +275,77 @@ class Program:
         self.steps = self._emit(items, compress)
         if self._wflag is not None and int(self._wflag.item()) != 0:
             self.force_fallback = True                          # a weight does not fit fp16: always run 3xTF32
+
+    # -- tiny event sizes: pack every layer into one weight blob + op list for the whole-flow kernel
+    @staticmethod
+    def _pack_small(items):
+        if not items or any(p.kind not in ("aff", "coupling") for p in items):
+            return None
+        d = None
+        hidden = 0
+        for p in items:
+            if p.kind == "aff":
+                if p.W.shape[0] != p.W.shape[1]:
+                    return None
+                dd = p.W.shape[0]
+            else:
+                ws = p.prep["weights"]
+                if len(ws) < 2:
+                    return None
+                dd = ws[0].shape[1]
+                if ws[-1].shape[0] != dd:
+                    return None
+                hidden = max([hidden] + [w.shape[0] for w in ws[:-1]])
+            if d is None:
+                d = dd
+            if dd != d:
+                return None
+        if d is None or d > 8 or hidden > 64:
+            return None
+        D = 2 if d <= 2 else 4 if d <= 4 else 8
+        H = 32 if hidden <= 32 else 64
+        dev = (items[0].W if items[0].kind == "aff" else items[0].prep["weights"][0]).device
+        prog, blocks, off = [], [], 0
+
+        def pad2(t, r, c):
+            o = torch.zeros(r, c, dtype=torch.float32, device=dev)
+            o[:t.shape[0], :t.shape[1]] = t.to(torch.float32)
+            return o
+
+        def pad1(t, n):
+            o = torch.zeros(n, dtype=torch.float32, device=dev)
+            o[:t.shape[0]] = t.to(torch.float32)
+            return o
+
+        for p in items:
+            parts = []
+            if p.kind == "aff":
+                W = torch.eye(D, dtype=torch.float32, device=dev)
+                W[:d, :d] = p.W.to(torch.float32)
+                c = pad1(p.c if p.c is not None else torch.zeros(d, device=dev), D)
+                parts = [W.reshape(-1), c]
+                code = 0
+            else:
+                ws, bs, m = p.prep["weights"], p.prep["biases"], p.prep["mask"].reshape(-1).to(torch.float32)
+                parts.append(pad2(ws[0] * m[None, :], H, D).reshape(-1))
+                parts.append(pad1(bs[0], H))
+                for w, b in zip(ws[1:-1], bs[1:-1]):
+                    parts.append(pad2(w, H, H).reshape(-1))
+                    parts.append(pad1(b, H))
+                g = float(p.sign) * (1 - m)
+                parts.append(pad2(ws[-1] * g[:, None], D, H).reshape(-1))
+                parts.append(pad1(bs[-1] * g, D))
+                code = 1 | ((len(ws) - 2) << 8)
+            blk = torch.cat(parts)
+            if blk.numel() % 4:
+                blk = torch.cat([blk, torch.zeros(4 - blk.numel() % 4, dtype=torch.float32, device=dev)])
+            prog += [code, off]
+            off += blk.numel()
+            blocks.append(blk)
+        if off * 4 > 200 * 1024:
+            return None
+        return dict(prog=torch.tensor(prog, dtype=torch.int32, device=dev), blob=torch.cat(blocks).contiguous(),
+                    n_ops=len(items), D=D, H=H, d=d)
 
     def _flag_for_weights(self, device) -> Optional[torch.Tensor]:
         if self.mode != "fp32":
@@ -403,6 +476,14 @@ class Program:
         width = self.out_width(x.shape[1])
         if rows == 0:                       # empty batch: nothing to launch
             return None if sink is not None else torch.empty(0, width, dtype=torch.float32, device=x.device)
+        if self.small is not None and x.shape[1] == self.small["d"]:
+            sm = self.small
+            res = out if (out is not None and sink is None) else torch.empty(rows, sm["d"], dtype=torch.float32, device=x.device)
+            ops.flow_small(x, sm["prog"], sm["blob"], sm["n_ops"], sm["D"], sm["H"], res)
+            if sink is not None:
+                sink(res, 0, rows)
+                return None
+            return res
         if self.force_fallback:
             return self._fallback().run(x, chunk_rows=chunk_rows, out=out, sink=sink)
         cap = chunk_rows or _default_chunk_rows
@@ -539,7 +620,7 @@ class Program:
     @classmethod
     def from_steps(cls, steps: List[Step], mode: str) -> "Program":
         prog = cls.__new__(cls)
-        prog.mode, prog.items, prog.compress, prog.steps = mode, [], None, steps
+        prog.mode, prog.items, prog.compress, prog.steps, prog.small = mode, [], None, steps, None
         prog.layers, prog.direction, prog._fallback_prog, prog._wflag, prog.force_fallback = [], "forward", None, None, False
         return prog
 
@@ -552,6 +633,7 @@ class _Workspace:
 
     def __init__(self):
         self._bufs = {}
+        self.generation = 0          # bumped whenever a buffer is (re)allocated: captured CUDA graphs go stale
 
     def planes(self, device, name: str, rows: int, width: int, fmt: str) -> torch.Tensor:
         ld = pad4(width)
@@ -562,6 +644,7 @@ class _Workspace:
         if buf is None or buf.numel() < need:
             buf = torch.empty(max(need, 1), dtype=dtype, device=device)
             self._bufs[key] = buf
+            self.generation += 1
         return buf[:need].view(rows, ld)[:, :width]
 
 
@@ -657,7 +740,7 @@ def profile_step(fn) -> dict:
     """Run `fn` once with CUDA events around every hot-path kernel launch; returns milliseconds summed per
     kernel class ("linear NxK", "ingest", "base_logprob") plus "_names" (launch order) and "_total"."""
     records = []
-    originals = {name: getattr(ops, name) for name in ("linear", "ingest", "base_logprob")}
+    originals = {name: getattr(ops, name) for name in ("linear", "ingest", "base_logprob", "flow_small")}
 
     def wrap(name, f):
         def inner(*a, **k):

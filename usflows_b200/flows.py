@@ -19,7 +19,29 @@ from .transforms import (BaseTransform, BlockAffineTransform, HouseholderTransfo
                          MaskedCoupling, ScaleTransform, SequentialAffineTransform)
 
 
+HOST_CUDA_GRAPHS = True       # `log_prob_host`: replay one captured CUDA graph per full-size chunk
 HOST_CHUNK_ROWS = 16384      # rows per H2D copy / kernel batch of `log_prob_host` (copy i+1 overlaps compute i)
+
+
+def _wave_aligned_chunk_rows(prog, device) -> int:
+    """Rows per H2D copy / kernel batch of `log_prob_host`: the smallest multiple of 256-row tile rows >= HOST_CHUNK_ROWS / 2
+    for which the widest layer's tile count is a whole number of waves of the persistent CTA-pair kernel (one tile per
+    SM pair and wave).  A small first copy keeps the pipeline fill short (the copy of chunk i+1 hides under the kernels
+    of chunk i); whole waves keep the tail of every launch full."""
+    import ctypes
+    from . import _lib
+    if getattr(prog, "small", None) is not None:                 # one launch per chunk: copy granularity only
+        return max(HOST_CHUNK_ROWS, (32 << 20) // (4 * prog.small["d"]))
+    widest = max([st.N for st in prog.steps if st.kind == "mm"] or [0])
+    if widest < 32:
+        return HOST_CHUNK_ROWS
+    sm = ctypes.c_int(0)
+    _lib.check(_lib.load().usf_device_info(ctypes.byref(sm), None, None, None))
+    pairs = max(1, sm.value // 2)
+    n_blocks = -(-widest // 256) if widest % 256 == 0 else -(-widest // 208)
+    unit = pairs // math.gcd(pairs, n_blocks)                 # tile rows (of 256 rows) per whole number of waves
+    k = max(1, -(-(HOST_CHUNK_ROWS // 2) // (256 * unit)))
+    return 256 * unit * k
 
 
 class Flow(torch.nn.Module):
@@ -87,6 +109,28 @@ class Flow(torch.nn.Module):
             prog.run(x2, sink=sink)
         return out.reshape(batch_shape)
 
+    def _chunk_graph(self, prog, slot: int, buf: torch.Tensor, d: int) -> dict:
+        """CUDA graph of the launch program of one full-size chunk reading host-staging buffer `slot`."""
+        cache = self.__dict__.setdefault("_host_graphs", {})
+        key = (id(prog), slot, buf.data_ptr(), tuple(buf.shape))
+        ent = cache.get(key)
+        if ent is not None and ent["gen"] == engine._workspace.generation:
+            return ent
+        dev = buf.device
+        rows, width = buf.shape[0], prog.out_width(d)
+        flag = torch.zeros(1, dtype=torch.int32, device=dev) if prog.mode == "fp32" else None
+        fin = engine._workspace.planes(dev, f"final_host{slot}", rows, width, "f32")
+        prog._run_chunk(buf, fin, flag)                   # eager pass: sizes every workspace buffer before capture
+        torch.cuda.synchronize(dev)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            prog._run_chunk(buf, fin, flag)
+        ent = dict(graph=graph, fin=fin, flag=flag, gen=engine._workspace.generation)
+        for k in [k for k in cache if k[1] == slot]:      # one live graph per staging buffer
+            del cache[k]
+        cache[key] = ent
+        return ent
+
     def log_prob_host(self, x_host: torch.Tensor, out_host: Optional[torch.Tensor] = None,
                       chunk_rows: Optional[int] = None) -> torch.Tensor:
         """`log_prob` for rows living in HOST memory (pinned for full copy speed): the batch is streamed
@@ -102,7 +146,7 @@ class Flow(torch.nn.Module):
         rows, d = x2.shape
         if out_host is None:
             out_host = torch.empty(rows, dtype=torch.float32, pin_memory=True)
-        chunk = min(chunk_rows or HOST_CHUNK_ROWS, max(rows, 1))
+        chunk = min(chunk_rows or _wave_aligned_chunk_rows(prog, dev), max(rows, 1))
         if getattr(self, "_host_bufs", None) is None or self._host_bufs[0].shape != (chunk, d) \
                 or self._host_bufs[0].device != dev:
             self._host_bufs = [torch.empty(chunk, d, dtype=torch.float32, device=dev) for _ in range(2)]
@@ -124,7 +168,13 @@ class Flow(torch.nn.Module):
                                  out_dev[r0 + a:r0 + b])
             return sink
 
+        use_graphs = HOST_CUDA_GRAPHS and not prog.force_fallback and rows >= chunk and getattr(prog, "small", None) is None
         with torch.no_grad():
+            graphs = [self._chunk_graph(prog, s, self._host_bufs[s], d) for s in range(2)] if use_graphs else None
+            if graphs is not None:
+                for g in graphs:
+                    if g["flag"] is not None:
+                        g["flag"].zero_()
             self._copy_stream.wait_stream(main)
             for i, r0 in enumerate(starts):
                 r1 = min(rows, r0 + chunk)
@@ -135,11 +185,20 @@ class Flow(torch.nn.Module):
                     buf.copy_(x2[r0:r1], non_blocking=True)
                     copied[i & 1].record(self._copy_stream)
                 main.wait_event(copied[i & 1])
-                prog.run(buf, chunk_rows=chunk, sink=make_sink(r0),
-                         flag_out=flags[i:i + 1] if guarded else None)
+                if graphs is not None and r1 - r0 == chunk:
+                    # one graph launch replaces the ~23 kernel launches of the chunk: the host-side launch cost
+                    # (~40 us per launch through ctypes + tensor-map encoding) is what bounds small chunks otherwise
+                    graphs[i & 1]["graph"].replay()
+                    make_sink(r0)(graphs[i & 1]["fin"], 0, chunk)
+                else:
+                    prog.run(buf, chunk_rows=chunk, sink=make_sink(r0),
+                             flag_out=flags[i:i + 1] if guarded else None)
                 consumed[i & 1].record(main)
             if guarded:                                   # one sync; out-of-range chunks go through the tf32 split
-                for i in torch.nonzero(flags).reshape(-1).tolist():
+                redo = set(torch.nonzero(flags).reshape(-1).tolist())
+                if graphs is not None and any(int(g["flag"].item()) != 0 for g in graphs if g["flag"] is not None):
+                    redo = set(range(len(starts)))        # a graph's flag is not per chunk: recompute all of them
+                for i in sorted(redo):
                     r0 = starts[i]
                     r1 = min(rows, r0 + chunk)
                     buf = self._host_bufs[0][: r1 - r0]

@@ -140,6 +140,16 @@ def base_sample(out: Act, loc, scale, kind: int, seed: int, offset: int) -> None
         _ptr(out.bf16), _ld(out.bf16) if out.bf16 is not None else 0, _stream()))
 
 
+def flow_small(x: torch.Tensor, prog_i32: torch.Tensor, blob: torch.Tensor, n_ops: int, D: int, H: int,
+               out: torch.Tensor) -> None:
+    """Whole layer stack in one launch (d <= 8, conditioner width <= 64); see usf_flow_small."""
+    global LAUNCHES
+    LAUNCHES += 1
+    rows, d = x.shape
+    check(_lib.load().usf_flow_small(_ptr(x), _ld(x), rows, d, _ptr(prog_i32), n_ops, _ptr(blob), blob.numel(), D, H,
+                                     _ptr(out), _ld(out), _stream()))
+
+
 def leaky_relu(x: torch.Tensor, slope: float, y: torch.Tensor, neg_count: Optional[torch.Tensor] = None) -> None:
     rows, d = x.shape
     check(_lib.load().usf_leaky_relu(_ptr(x), _ld(x), rows, d, float(slope), _ptr(y), _ld(y), _ptr(neg_count), _stream()))
