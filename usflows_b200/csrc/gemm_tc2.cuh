@@ -411,11 +411,13 @@ __device__ __forceinline__ void store_chunk(const Epilogue& ep, const EpiRegs& e
 }
 
 // ---- asynchronous store path (fp16-split planes only) ---------------------------------------------------------------
-// The epilogue warp converts 16 columns of its row at a time into one of two 2 KB staging buffers (32-byte rows in the
-// hardware's 32B swizzle) and one lane issues two TMA tensor stores (hi box, lo box).  The stores run asynchronously:
-// the SM -> L2 write path (~32 B/cycle/SM, >= 4 096 cycles for the 128 KB of one tile) works under the conversion of
-// the next pieces and under the next tile's main loop, and the M / N edges are clipped by the hardware.
-struct StoreMaps { CUtensorMap h16, l16; };    // [M rows, N cols] fp16, box = 32 rows x 16 columns, SWIZZLE_32B
+// The epilogue warp converts W = 32 columns of its row at a time (16 for the tail of a 112 / 96 column range), FIRST the
+// hi plane into staging box A, THEN the lo plane into box B; one lane issues a TMA tensor store per box.  Rows of a box
+// are W * 2 = 64 bytes (hardware 64B swizzle; 32B for the tail): whole 64-byte segments per row on the SM -> L2 write
+// path, which is what bounds this phase.  Each plane has its own box, so a box is rewritten two store groups later
+// (`cp.async.bulk.wait_group.read 1`): the stores run under the conversion of the next plane / piece and under the next
+// tile's main loop, and the M / N edges are clipped by the hardware.
+struct StoreMaps { CUtensorMap h32, l32, h16, l16; };    // [M rows, N cols] fp16; box = 32 rows x 32 (64B swizzle) / 16 columns (32B)
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                ::"l"(map), "r"(src), "r"(c0), "r"(c1)
@@ -425,20 +427,19 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-constexpr int ASYNC_W = 16;                        // columns per hand-over
-constexpr int ASYNC_BUF_BYTES = 2 * 32 * ASYNC_W * 2;   // hi box + lo box = 2 KB
+constexpr int ASYNC_BOX_BYTES = 32 * 32 * 2;       // one 32-row x 32-column fp16 box = 2 KB (box A at +0, box B at +2 KB)
 
 // `bias4` = this lane's four bias values of the warp's column range (lane l holds columns 4l .. 4l+3 of the range,
-// loaded once per tile before the last drain); piece `piece` (16 columns) takes its values from lanes 4*piece .. +3
-// by shuffle, so no global load sits between two TMA stores
-__device__ __forceinline__ void async_math16(const EpiRegs& er, float (&v)[ASYNC_W], const float4& bias4, int piece,
-                                             long long m, bool row_ok, int n0, int N) {
+// loaded once per tile before the last drain); the piece starting at column `c_first` of the range takes its values
+// from lanes c_first/4 .. by shuffle, so no global load sits between two TMA stores
+template <int W>
+__device__ __forceinline__ void async_math(const EpiRegs& er, float (&v)[W], const float4& bias4, int c_first,
+                                           long long m, bool row_ok, int n0, int N) {
   const uint32_t f = er.flags;
-  constexpr int W = ASYNC_W;
   if (f & EF_BIAS) {                 // (all lanes take part in the shuffles)
 #pragma unroll
     for (int q = 0; q < W / 4; ++q) {
-      const int src = piece * (W / 4) + q;
+      const int src = c_first / 4 + q;
       v[4 * q] += __shfl_sync(0xffffffffu, bias4.x, src);
       v[4 * q + 1] += __shfl_sync(0xffffffffu, bias4.y, src);
       v[4 * q + 2] += __shfl_sync(0xffffffffu, bias4.z, src);
@@ -455,7 +456,7 @@ __device__ __forceinline__ void async_math16(const EpiRegs& er, float (&v)[ASYNC
     const uint4* pl = reinterpret_cast<const uint4*>(er.rl + m * er.ldr16 + n0);
 #pragma unroll
     for (int q = 0; q < W / 8; ++q) {
-      if (n0 + 8 * q < N) {
+      if (n0 + 8 * q < N) {          // N % 8 == 0: a group of eight columns is inside or outside as a whole
         const uint4 h8 = ph[q], l8 = pl[q];
         const __half2* h2 = reinterpret_cast<const __half2*>(&h8);
         const __half2* l2 = reinterpret_cast<const __half2*>(&l8);
@@ -470,29 +471,61 @@ __device__ __forceinline__ void async_math16(const EpiRegs& er, float (&v)[ASYNC
   }
 }
 
-__device__ __forceinline__ void async_stage16(const Epilogue& ep, const float (&v)[ASYNC_W], bool row_ok, int lane, int n0,
-                                              int N, uint32_t buf) {
-  constexpr int W = ASYNC_W;
+// one plane (LO = false: hi, true: lo' = (x - hi) 2^11) of a W-column piece -> staging box (row = lane)
+template <int W, bool LO>
+__device__ __forceinline__ void async_stage_plane(const Epilogue& ep, const float (&v)[W], bool row_ok, int lane, int n0, int N,
+                                                  uint32_t box) {
   constexpr int RB = W * 2;
   __half2 amax2 = __float2half2_rn(0.f);
 #pragma unroll
   for (int q = 0; q < W / 8; ++q) {
-    uint32_t hp[4], lp[4];
+    uint32_t pk[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const float x0 = v[q * 8 + 2 * e], x1 = v[q * 8 + 2 * e + 1];
       const __half2 h = __floats2half2_rn(x0, x1);
-      const float2 hf = __half22float2(h);
-      const __half2 l = __floats2half2_rn((x0 - hf.x) * F16_LO_SCALE, (x1 - hf.y) * F16_LO_SCALE);
-      hp[e] = *reinterpret_cast<const uint32_t*>(&h);
-      lp[e] = *reinterpret_cast<const uint32_t*>(&l);
-      if (n0 + 8 * q < N) amax2 = __hmax2_nan(amax2, __habs2(h));   // columns past N hold no result
+      if (LO) {
+        const float2 hf = __half22float2(h);
+        const __half2 l = __floats2half2_rn((x0 - hf.x) * F16_LO_SCALE, (x1 - hf.y) * F16_LO_SCALE);
+        pk[e] = *reinterpret_cast<const uint32_t*>(&l);
+      } else {
+        pk[e] = *reinterpret_cast<const uint32_t*>(&h);
+        if (n0 + 8 * q < N) amax2 = __hmax2_nan(amax2, __habs2(h));   // columns past N hold no result
+      }
     }
-    sts128(buf + stage_off<RB>(lane, q), hp[0], hp[1], hp[2], hp[3]);
-    sts128(buf + 32 * RB + stage_off<RB>(lane, q), lp[0], lp[1], lp[2], lp[3]);
+    sts128(box + stage_off<RB>(lane, q), pk[0], pk[1], pk[2], pk[3]);
   }
-  const float2 am = __half22float2(amax2);
-  if (!(am.x <= F16_GUARD && am.y <= F16_GUARD) && row_ok && ep.overflow_flag) *ep.overflow_flag = 1;
+  if (!LO) {
+    const float2 am = __half22float2(amax2);
+    if (!(am.x <= F16_GUARD && am.y <= F16_GUARD) && row_ok && ep.overflow_flag) *ep.overflow_flag = 1;
+  }
+}
+
+// a whole W-column piece: arithmetic, then plane by plane: wait for the box, stage, TMA store
+template <int W>
+__device__ __forceinline__ void async_piece(const Epilogue& ep, const EpiRegs& er, const StoreMaps& smaps, float (&v)[W],
+                                            const float4& bias4, int c_first, long long m, bool row_ok, int lane, int n0, int N,
+                                            long long row0, uint32_t stage, uint32_t& groups) {
+  async_math<W>(er, v, bias4, c_first, m, row_ok, n0, N);
+  const CUtensorMap* mh = W == 32 ? &smaps.h32 : &smaps.h16;
+  const CUtensorMap* ml = W == 32 ? &smaps.l32 : &smaps.l16;
+#pragma unroll
+  for (int plane = 0; plane < 2; ++plane) {
+    if (groups >= 2) {                                // the store that last read this box (two groups ago) has drained it
+      if (lane == 0) bulk_wait_read1();
+      __syncwarp();
+    }
+    const uint32_t box = stage + plane * ASYNC_BOX_BYTES;
+    if (plane == 0) async_stage_plane<W, false>(ep, v, row_ok, lane, n0, N, box);
+    else async_stage_plane<W, true>(ep, v, row_ok, lane, n0, N, box);
+    fence_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_2d(plane == 0 ? mh : ml, box, n0, (int)row0);
+      bulk_commit();
+    }
+    ++groups;
+  }
 }
 
 // One epilogue warp: TMEM lanes [32*quarter, +32) x columns [col0, col0+COLS) of every tile of this CTA.
@@ -516,7 +549,7 @@ __device__ __forceinline__ void epilogue_loop(int col0, int quarter, int lane, u
   const EpiRegs er = load_epi_regs(ep);
   const bool fast_store = ep.fast_store != 0;
   const bool async_store = ep.async_store != 0;
-  uint32_t hand = 0;     // TMA store groups committed so far: staging buffer = hand & 1
+  uint32_t hand = 0;     // TMA store groups committed so far by this warp
   for (long long tile = cluster_id_x(); tile < n_tiles; tile += num_clusters_x()) {
     const long long m_idx = (tile / n_blocks) * (2 * BLOCK_M) + rank * BLOCK_M;
     const int n_idx = (int)(tile % n_blocks) * BLOCK_N;
@@ -581,26 +614,18 @@ __device__ __forceinline__ void epilogue_loop(int col0, int quarter, int lane, u
         const bool row_ok = m < M;
         const long long t_start = dbg ? clock64() : 0;
 #pragma unroll
-        for (int c = 0; c < COLS / ASYNC_W; ++c) {
-          const int n0 = n_idx + col0 + c * ASYNC_W;
-          if (n0 < N) {
-            float(&piece)[ASYNC_W] = *reinterpret_cast<float(*)[ASYNC_W]>(&master[c * ASYNC_W]);
-            async_math16(er, piece, bias4, c, m, row_ok, n0, N);
-            const uint32_t buf = stage + (hand & 1) * ASYNC_BUF_BYTES;
-            if (hand >= 2) {                                  // the store that last read this buffer has drained it
-              if (lane == 0) bulk_wait_read1();
-              __syncwarp();
-            }
-            async_stage16(ep, piece, row_ok, lane, n0, N, buf);
-            fence_async_smem();
-            __syncwarp();
-            if (lane == 0) {
-              tma_store_2d(&smaps.h16, buf, n0, (int)row0);
-              tma_store_2d(&smaps.l16, buf + 32 * ASYNC_W * 2, n0, (int)row0);
-              bulk_commit();
-            }
-            ++hand;
-          }
+        for (int c = 0; c < COLS / 32; ++c) {
+          const int n0 = n_idx + col0 + c * 32;
+          if (n0 < N)
+            async_piece<32>(ep, er, smaps, *reinterpret_cast<float(*)[32]>(&master[c * 32]), bias4, c * 32, m, row_ok, lane,
+                            n0, N, row0, stage, hand);
+        }
+        if (COLS % 32) {
+          constexpr int c_first = COLS / 32 * 32;
+          const int n0 = n_idx + col0 + c_first;
+          if (n0 < N)
+            async_piece<16>(ep, er, smaps, *reinterpret_cast<float(*)[16]>(&master[c_first]), bias4, c_first, m, row_ok, lane,
+                            n0, N, row0, stage, hand);
         }
         if (dbg && dbg_chain - 1 < DBG_CHAINS) dbg[(dbg_chain - 1) * 8 + 6] = (unsigned long long)(clock64() - t_start) << 32;
       }
@@ -883,16 +908,18 @@ extern int g_dbg_flags;                 // debug: 1 = epilogue skips the TMEM dr
 extern int g_no_async_store;            // test hook: 1 = the epilogue warps store themselves (flag 32)
 extern int g_no_fast_store;             // test hook: 1 = always use the register/patch store path (usf_debug_gemm_timeline flag 4)
 
-// fp16 output plane [rows, cols] (row pitch ld halves) for the TMA store path: box = 32 rows x 16 columns, 32B swizzle
-inline int make_store_map16(CUtensorMap* map, const void* ptr, long long rows, long long cols, long long ld) {
+// fp16 output plane [rows, cols] (row pitch ld halves) for the TMA store path: box = 32 rows x box_cols (32: 64B swizzle,
+// 16: 32B swizzle) columns
+inline int make_store_map16(CUtensorMap* map, const void* ptr, long long rows, long long cols, long long ld, int box_cols) {
   PFN_encodeTiled enc = get_encode_tiled();
   if (!enc) return fail(USF_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available%s%s");
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {(cuuint32_t)tc2::ASYNC_W, 32};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, 32};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, box_cols == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B,
+                   CU_TENSOR_MAP_L2_PROMOTION_NONE,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     snprintf(g_err, sizeof(g_err), "cuTensorMapEncodeTiled (store map) failed with CUresult %d (rows=%lld cols=%lld ld=%lld)",
@@ -932,8 +959,10 @@ int launch_gemm_tc2_cfg(const usf_linear_args* a, const Epilogue& ep_in, cudaStr
   tc2::StoreMaps sm;
   memset(&sm, 0, sizeof(sm));
   if (ep.async_store) {
-    if ((rc = make_store_map16(&sm.h16, ep.out_h16, a->M, a->N, ep.ld_16))) return rc;
-    if ((rc = make_store_map16(&sm.l16, ep.out_l16, a->M, a->N, ep.ld_16))) return rc;
+    if ((rc = make_store_map16(&sm.h32, ep.out_h16, a->M, a->N, ep.ld_16, 32))) return rc;
+    if ((rc = make_store_map16(&sm.l32, ep.out_l16, a->M, a->N, ep.ld_16, 32))) return rc;
+    if ((rc = make_store_map16(&sm.h16, ep.out_h16, a->M, a->N, ep.ld_16, 16))) return rc;
+    if ((rc = make_store_map16(&sm.l16, ep.out_l16, a->M, a->N, ep.ld_16, 16))) return rc;
   }
   const long long tiles = ((a->M + 2 * tc::BLOCK_M - 1) / (2 * tc::BLOCK_M)) * ((a->N + BLOCK_N - 1) / BLOCK_N);
   const int pairs = num_sms() / 2;
