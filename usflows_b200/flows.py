@@ -83,6 +83,17 @@ class Flow(torch.nn.Module):
             return self.backward(x)
         raise ValueError(f"Unknown export mode {self.export}")
 
+    def reference_module(self, export_mode: str = "log_prob") -> torch.nn.Module:
+        """Frozen pure-PyTorch module with the reference's semantics of this flow (for ONNX export / inspection on any
+        device; never used by `log_prob` / `sample`, which run on the CUDA kernels only)."""
+        from .export import ReferenceSemantics
+        return ReferenceSemantics(self, export_mode)
+
+    def to_onnx(self, path: str, export_mode: str = "log_prob", **export_kwargs) -> None:
+        """Saves the model as an ONNX file (flows.py:212-223); `export_mode` as `Flow.export`."""
+        from .export import to_onnx
+        to_onnx(self, path, export_mode, **export_kwargs)
+
     def _forward(self, x: torch.Tensor) -> torch.Tensor:
         """latent -> data through every layer's `forward` (flows.py:45-55)."""
         return self._run("forward", x)
