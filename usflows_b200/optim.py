@@ -54,16 +54,31 @@ class SophiaG(Optimizer):
         for group in self.param_groups:
             beta1, _ = group["betas"]
             lr, rho, wd = group["lr"], group["rho"], group["weight_decay"]
+            ps, gs, ms, hs = [], [], [], []
             for p in group["params"]:
                 if p.grad is None:
                     continue
                 if p.grad.is_sparse:
                     raise RuntimeError("SophiaG does not support sparse gradients")
-                g = -p.grad if group["maximize"] else p.grad
                 st = self._state(p)
                 st["step"] += 1
-                p.mul_(1 - lr * wd)
-                m = st["exp_avg"].mul_(beta1).add_(g, alpha=1 - beta1)
-                ratio = (m.abs() / (rho * bs * st["hessian"] + 1e-15)).clamp_(max=1.0)
-                p.addcmul_(m.sign(), ratio, value=-lr)
+                ps.append(p)
+                gs.append(p.grad)
+                ms.append(st["exp_avg"])
+                hs.append(st["hessian"])
+            if not ps:
+                continue
+            # the same elementwise arithmetic as the per-parameter loop of sophia.py:170-199, issued as multi-tensor
+            # ops (one launch per operation for ALL parameters instead of ~8 launches per parameter)
+            if group["maximize"]:
+                gs = torch._foreach_neg(gs)
+            torch._foreach_mul_(ps, 1 - lr * wd)
+            torch._foreach_mul_(ms, beta1)
+            torch._foreach_add_(ms, gs, alpha=1 - beta1)
+            den = torch._foreach_mul(hs, rho * bs)
+            torch._foreach_add_(den, 1e-15)
+            ratio = torch._foreach_abs(ms)
+            torch._foreach_div_(ratio, den)
+            torch._foreach_clamp_max_(ratio, 1.0)
+            torch._foreach_addcmul_(ps, torch._foreach_sign(ms), ratio, value=-lr)
         return loss

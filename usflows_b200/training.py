@@ -98,9 +98,16 @@ def _eye(d, ref):
     return torch.eye(d, dtype=ref.dtype, device=ref.device)
 
 
-def affine_parts(t):
+def affine_parts(t, cache: Optional[dict] = None):
     """(W, W^-1, b, log|det W|) of an AffineTransform as differentiable tensors (transforms.py:1271-1320,
-    795-809, 1457-1476)."""
+    795-809, 1457-1476).  `cache` (one dict per autograd pass) shares the result between a block and the
+    `InverseTransform` that wraps the same layer object (affine conjugation): the d^3 products and triangular solves
+    are built once per layer and step, and autograd sums the gradients of both uses."""
+    if cache is not None:
+        hit = cache.get(id(t))
+        if hit is None:
+            hit = cache[id(t)] = affine_parts(t)
+        return hit
     from . import transforms as T
     if isinstance(t, T.LUTransform):
         d = t.dim
@@ -128,14 +135,14 @@ def affine_parts(t):
     raise NotImplementedError(f"usflows_b200: training of {type(t).__name__} is not built")
 
 
-def _layer_backward(layer, y: torch.Tensor, inverse: bool = False):
+def _layer_backward(layer, y: torch.Tensor, inverse: bool = False, cache: Optional[dict] = None):
     """(density direction value, forward log|det J|) of one layer; `inverse` swaps the direction."""
     from . import transforms as T
     if isinstance(layer, T.InverseTransform):
-        x, ladj = _layer_backward(layer.transform, y, not inverse)
+        x, ladj = _layer_backward(layer.transform, y, not inverse, cache)
         return x, -ladj
     if isinstance(layer, T.BlockAffineTransform):
-        W, Winv, b, ladj = affine_parts(layer.block_transform)
+        W, Winv, b, ladj = affine_parts(layer.block_transform, cache)
         ladj = ladj * layer.n_blocks
         if inverse:                                     # the layer's forward: x W^T + b      (transforms.py:913-934)
             return linear(y, W, b), ladj
@@ -175,8 +182,9 @@ def log_prob_autograd(flow, x: torch.Tensor) -> torch.Tensor:
     """`Flow.log_prob` (flows.py:225-245) as an autograd graph over the flow's parameters."""
     z = x.reshape(x.shape[0], -1)
     total = z.new_zeros(())
+    cache: dict = {}
     for layer in reversed(flow.layers):
-        z, ladj = _layer_backward(layer, z)
+        z, ladj = _layer_backward(layer, z, cache=cache)
         total = total + ladj
     return base_log_prob(flow.base_distribution, z) - total
 
