@@ -215,3 +215,32 @@ def test_infeasible_layer_is_reported():
     with torch.no_grad():
         flow.layers[-1].scale[0] = 0.0
     assert not flow.is_feasible()
+
+
+def test_small_batch_graph_replay_is_bit_identical():
+    """`log_prob` on <= SMALL_BATCH_GRAPH_ROWS rows replays a captured CUDA graph: same bits as launch by launch, also
+    after a weight update (new program, new graph) and for a batch that leaves the fp16 range (falls through)."""
+    from usflows_b200 import flows
+    spec, params, arr = load_case("d100_h50_hh")
+    flow = build_flow(spec, params, precision="fp32")
+    x = arr["x"].cuda()
+    keep = flows.SMALL_BATCH_GRAPH_ROWS
+    try:
+        flows.SMALL_BATCH_GRAPH_ROWS = 0
+        plain = flow.log_prob(x)
+        flows.SMALL_BATCH_GRAPH_ROWS = 4096
+        a = flow.log_prob(x)
+        b = flow.log_prob(x)                      # second call: replay only
+        assert torch.equal(a, plain) and torch.equal(b, plain)
+        big = x * 1e6                             # activations leave the fp16 range: tf32-split re-run, same answer as without graphs
+        g = flow.log_prob(big)
+        flows.SMALL_BATCH_GRAPH_ROWS = 0
+        assert torch.equal(g, flow.log_prob(big))
+        with torch.no_grad():
+            flow.trainable_layers[-1].scale.mul_(1.5)
+        flows.SMALL_BATCH_GRAPH_ROWS = 4096
+        c = flow.log_prob(x)
+        flows.SMALL_BATCH_GRAPH_ROWS = 0
+        assert torch.equal(c, flow.log_prob(x)) and not torch.equal(c, plain)
+    finally:
+        flows.SMALL_BATCH_GRAPH_ROWS = keep

@@ -19,6 +19,7 @@ from .transforms import (BaseTransform, BlockAffineTransform, HouseholderTransfo
                          MaskedCoupling, ScaleTransform, SequentialAffineTransform)
 
 
+SMALL_BATCH_GRAPH_ROWS = 4096   # `log_prob` on at most this many rows replays one captured CUDA graph (0 = off)
 HOST_CUDA_GRAPHS = True       # `log_prob_host`: replay one captured CUDA graph per full-size chunk
 HOST_CHUNK_ROWS = 16384      # rows per H2D copy / kernel batch of `log_prob_host` (copy i+1 overlaps compute i)
 
@@ -110,8 +111,14 @@ class Flow(torch.nn.Module):
         base = self._base_module()
         loc, scale = base._prepared()
         x2, batch_shape = engine._flatten_rows(x, len(self._event_shape()))
-        out = torch.empty(x2.shape[0], dtype=torch.float32, device=x2.device)
         d = x2.shape[1]
+        rows = x2.shape[0]
+        if x2.is_cuda and 0 < rows <= SMALL_BATCH_GRAPH_ROWS and getattr(prog, "small", None) is None \
+                and not prog.force_fallback and not torch.cuda.is_current_stream_capturing():
+            lp = self._log_prob_small_batch(prog, ladj, x2)
+            if lp is not None:
+                return lp.reshape(batch_shape)
+        out = torch.empty(rows, dtype=torch.float32, device=x2.device)
 
         def sink(z_chunk, r0, r1):
             ops.base_logprob(ops.Act(r1 - r0, d, f32=z_chunk), loc, scale, base.base_kind, -ladj, out[r0:r1])
@@ -119,6 +126,47 @@ class Flow(torch.nn.Module):
         with torch.no_grad():
             prog.run(x2, sink=sink)
         return out.reshape(batch_shape)
+
+    def _log_prob_small_batch(self, prog, ladj: float, x2: torch.Tensor):
+        """Small batches are bound by the host-side cost of ~23 kernel launches (~40 us each through ctypes + tensor-map
+        encoding), not by the kernels: the launch program + base density of a given row count is captured ONCE into a CUDA
+        graph over fixed staging buffers and replayed (input copied in, result cloned out).  Returns None when a value
+        left the fp16 range (the caller then takes the launch-by-launch route, which handles the tf32-split re-run)."""
+        cache = self.__dict__.setdefault("_lp_graphs", {})
+        rows, d = x2.shape
+        dev = x2.device
+        key = (id(prog), rows, str(dev))
+        ent = cache.get(key)
+        if ent is None or ent["gen"] != engine._workspace.generation:
+            base = self._base_module()
+            loc, scale = base._prepared()
+            xin = torch.empty(rows, d, dtype=torch.float32, device=dev)
+            out = torch.empty(rows, dtype=torch.float32, device=dev)
+            flag = torch.zeros(1, dtype=torch.int32, device=dev) if prog.mode == "fp32" else None
+            width = prog.out_width(d)
+            fin = engine._workspace.planes(dev, "final_small", rows, width, "f32")
+
+            def body():
+                prog._run_chunk(xin, fin, flag)
+                ops.base_logprob(ops.Act(rows, width, f32=fin), loc, scale, base.base_kind, -ladj, out)
+            with torch.no_grad():
+                xin.copy_(x2)
+                body()                                        # eager pass: sizes every workspace buffer before capture
+                torch.cuda.synchronize(dev)
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    body()
+            if len(cache) >= 8:                               # a few row counts per weight version; drop the oldest
+                cache.pop(next(iter(cache)))
+            ent = cache[key] = dict(graph=graph, x=xin, out=out, flag=flag, prog=prog, gen=engine._workspace.generation)
+        with torch.no_grad():
+            ent["x"].copy_(x2)
+            if ent["flag"] is not None:
+                ent["flag"].zero_()
+            ent["graph"].replay()
+            if ent["flag"] is not None and int(ent["flag"].item()) != 0:
+                return None
+            return ent["out"].clone()
 
     def _chunk_graph(self, prog, slot: int, buf: torch.Tensor, d: int) -> dict:
         """CUDA graph of the launch program of one full-size chunk reading host-staging buffer `slot`."""
