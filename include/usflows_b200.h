@@ -117,6 +117,9 @@ int usf_set_accum_lead(int chains);
 int usf_debug_set_block_n(int block_n);
 /* test hook: 2 = CTA-pair (cta_group::2) tcgen05 kernel (default), 1 = single-CTA tcgen05 kernel */
 int usf_debug_set_impl(int impl);
+/* test hook: 1 (default) = the kernels of an evaluation are chained with programmatic dependent launch, 0 = plain
+ * stream order */
+int usf_debug_set_pdl(int on);
 /* profiling hook for the CTA-pair tcgen05 kernel: `device_buf` (512 x 8 uint64, or NULL to switch off) receives
  * clock64() stamps of the first 512 accumulation chains of cluster 0 (0 = accumulator free seen by the MMA issuer,
  * 1 = operands landed, 2 = chain issued, 3 = accumulator full seen by epilogue warp 4, 4 = drained, 5 = tile stored);

@@ -27,3 +27,10 @@ print(f"device log_prob: {ms:.2f} ms")
 for chunk in (None, 9472, 18944, 16384):
     ms = timed(lambda: flow.log_prob_host(x_host, out_host, chunk_rows=chunk))
     print(f"log_prob_host chunk {chunk}: {ms:.2f} ms = {rows/ms/1e3:.2f} M rows/s")
+from usflows_b200 import _lib
+for pdl in (0, 1):
+    _lib.load().usf_debug_set_pdl(pdl)
+    flow._host_graphs = {}                                  # re-capture with / without programmatic edges
+    ms_dev = timed(lambda: flow.log_prob(x))
+    ms = timed(lambda: flow.log_prob_host(x_host, out_host))
+    print(f"pdl={pdl}: device log_prob {ms_dev:.3f} ms, log_prob_host {ms:.3f} ms = {rows/ms/1e3:.2f} M rows/s")

@@ -16,6 +16,7 @@ int g_tc_impl = 2;
 unsigned long long* g_dbg_buf = nullptr;
 int g_dbg_flags = 0;
 int g_no_fast_store = 0;
+int g_use_pdl = 1;
 int g_no_async_store = 0;
 
 int num_sms() {
@@ -131,6 +132,11 @@ int usf_debug_gemm_timeline(unsigned long long* device_buf, int flags) {
   return USF_OK;
 }
 
+int usf_debug_set_pdl(int on) {  // test hook: programmatic dependent launch of the kernel chain (default on)
+  g_use_pdl = on ? 1 : 0;
+  return USF_OK;
+}
+
 int usf_set_accum_lead(int chains) {  // leading double-length accumulation chains per tile (MMA run-ahead); 0 = none
   USF_REQUIRE(chains >= 0 && chains <= 2, "lead chains must be 0, 1 or 2 (two TMEM accumulators)");
   g_lead_chains = chains;
@@ -176,9 +182,9 @@ int usf_ingest(const float* x, int64_t ldx, int64_t rows, int32_t d, const float
   const bool vec = planes_vec_ok(o) && aligned16(x) && ldx % 4 == 0 && d % 4 == 0 && (!dv || aligned16(dv)) &&
                    (!mul || aligned16(mul)) && (!sub || aligned16(sub)) && (!out_bf16 || d % 8 == 0 || true);
   if (vec)
-    ingest_kernel<true><<<ew_grid(rows * (d / 4), 256), 256, 0, S(stream)>>>(x, ldx, rows, d, dv, mul, sub, o);
+    USF_CUDA_OK(launch_chain(ingest_kernel<true>, dim3(ew_grid(rows * (d / 4), 256)), dim3(256), 0, S(stream), x, (long long)ldx, (long long)rows, (int)d, dv, mul, sub, o));
   else
-    ingest_kernel<false><<<ew_grid(rows * d, 256), 256, 0, S(stream)>>>(x, ldx, rows, d, dv, mul, sub, o);
+    USF_CUDA_OK(launch_chain(ingest_kernel<false>, dim3(ew_grid(rows * d, 256)), dim3(256), 0, S(stream), x, (long long)ldx, (long long)rows, (int)d, dv, mul, sub, o));
   USF_CUDA_OK(cudaGetLastError());
   return USF_OK;
 }
@@ -195,9 +201,9 @@ int usf_ingest_f16(const float* x, int64_t ldx, int64_t rows, int32_t d, const f
   const bool vec = planes_vec_ok(o) && aligned16(x) && ldx % 4 == 0 && d % 4 == 0 && (!dv || aligned16(dv)) &&
                    (!mul || aligned16(mul)) && (!sub || aligned16(sub));
   if (vec)
-    ingest_kernel<true><<<ew_grid(rows * (d / 4), 256), 256, 0, S(stream)>>>(x, ldx, rows, d, dv, mul, sub, o);
+    USF_CUDA_OK(launch_chain(ingest_kernel<true>, dim3(ew_grid(rows * (d / 4), 256)), dim3(256), 0, S(stream), x, (long long)ldx, (long long)rows, (int)d, dv, mul, sub, o));
   else
-    ingest_kernel<false><<<ew_grid(rows * d, 256), 256, 0, S(stream)>>>(x, ldx, rows, d, dv, mul, sub, o);
+    USF_CUDA_OK(launch_chain(ingest_kernel<false>, dim3(ew_grid(rows * d, 256)), dim3(256), 0, S(stream), x, (long long)ldx, (long long)rows, (int)d, dv, mul, sub, o));
   USF_CUDA_OK(cudaGetLastError());
   return USF_OK;
 }
@@ -210,9 +216,9 @@ int usf_base_logprob(const float* z, const float* z_lo, int64_t ldz, int64_t row
   const bool vec = aligned16(z) && (!z_lo || aligned16(z_lo)) && ldz % 4 == 0 && d % 4 == 0 && aligned16(loc) && aligned16(scale);
   const int grid = ew_grid(rows * 32, BLP_THREADS);
   if (vec)
-    base_logprob_kernel<true><<<grid, BLP_THREADS, 0, S(stream)>>>(z, z_lo, ldz, rows, d, loc, scale, base_kind, add_const, out);
+    USF_CUDA_OK(launch_chain(base_logprob_kernel<true>, dim3(grid), dim3(BLP_THREADS), 0, S(stream), z, z_lo, (long long)ldz, (long long)rows, (int)d, loc, scale, (int)base_kind, add_const, out));
   else
-    base_logprob_kernel<false><<<grid, BLP_THREADS, 0, S(stream)>>>(z, z_lo, ldz, rows, d, loc, scale, base_kind, add_const, out);
+    USF_CUDA_OK(launch_chain(base_logprob_kernel<false>, dim3(grid), dim3(BLP_THREADS), 0, S(stream), z, z_lo, (long long)ldz, (long long)rows, (int)d, loc, scale, (int)base_kind, add_const, out));
   USF_CUDA_OK(cudaGetLastError());
   return USF_OK;
 }

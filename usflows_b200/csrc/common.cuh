@@ -46,6 +46,32 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 int num_sms();  // cached cudaDevAttrMultiProcessorCount of the current device
 
 // ---------------------------------------------------------------------------------------------
+// programmatic dependent launch: the kernels of one evaluation form a chain on one stream; with the attribute set, the
+// next kernel's CTAs are scheduled while the current kernel drains (launch latency and the next kernel's prologue --
+// barrier init, TMEM allocation, tensor-map prefetch -- hide under the tail) and block in `griddep_wait()` until the
+// previous grid has completed and its memory is visible.  Every kernel launched this way executes griddep_wait() before
+// its first access to global memory.
+// ---------------------------------------------------------------------------------------------
+extern int g_use_pdl;
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <class... KArgs, class... Args>
+inline cudaError_t launch_chain(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = g_use_pdl ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
+// ---------------------------------------------------------------------------------------------
 // fused epilogue shared by the tcgen05 and the SIMT contraction kernels
 //   v = acc (+ bias[n]) ; relu ; v = resid[m,n] + sign * v ; v *= colscale[n] ; v -= postsub[n]
 //   then written to any of: fp32 plane, tf32 hi/lo split planes, bf16 plane.

@@ -79,6 +79,8 @@ template <bool VEC>
 __global__ void __launch_bounds__(256)
 ingest_kernel(const float* __restrict__ x, long long ldx, long long rows, int d, const float* __restrict__ dv,
               const float* __restrict__ mul, const float* __restrict__ sub, OutPlanes o) {
+  griddep_launch_dependents();
+  griddep_wait();
   if (VEC) {
     const int d4 = d >> 2;
     const long long total = rows * d4;
@@ -120,6 +122,8 @@ __global__ void __launch_bounds__(BLP_THREADS)
 base_logprob_kernel(const float* __restrict__ z, const float* __restrict__ z_lo, long long ldz, long long rows, int d,
                     const float* __restrict__ loc, const float* __restrict__ scale, int kind, float add_const,
                     float* __restrict__ out) {
+  griddep_launch_dependents();
+  griddep_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int wpb = BLP_THREADS / 32;
   for (long long r = (long long)blockIdx.x * wpb + warp; r < rows; r += (long long)gridDim.x * wpb) {

@@ -734,6 +734,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
   cluster_sync_all();   // barriers of both CTAs initialised and visible before any remote arrive / TMA completion
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  // everything above touched only this CTA's shared / tensor memory and kernel parameters: it may run while the previous
+  // kernel of the chain still drains; from here on global memory written by that kernel is read
+  griddep_launch_dependents();
+  griddep_wait();
 
   if (warp < FIRST_EPI_WARP) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_NON_EPI));
@@ -967,10 +971,9 @@ int launch_gemm_tc2_cfg(const usf_linear_args* a, const Epilogue& ep_in, cudaStr
   const long long tiles = ((a->M + 2 * tc::BLOCK_M - 1) / (2 * tc::BLOCK_M)) * ((a->N + BLOCK_N - 1) / BLOCK_N);
   const int pairs = num_sms() / 2;
   const int grid = 2 * (int)(tiles < pairs ? tiles : pairs);
-  kern<<<grid, tc::NUM_THREADS, C::SMEM_BYTES, st>>>(ma, mal, mw, mwl, a->M, a->N, a->K,
-                                                       NTERMS == 3 ? g_chunk_slabs : 0, (NTERMS == 3 && KIND == tc2::KIND_F16) ? g_lead_chains : 0, ep, sm,
-                                                       g_dbg_buf, g_dbg_flags);
-  USF_CUDA_OK(cudaGetLastError());
+  USF_CUDA_OK(launch_chain(kern, dim3(grid), dim3(tc::NUM_THREADS), (size_t)C::SMEM_BYTES, st, ma, mal, mw, mwl, (long long)a->M,
+                           (int)a->N, (int)a->K, NTERMS == 3 ? g_chunk_slabs : 0,
+                           (NTERMS == 3 && KIND == tc2::KIND_F16) ? g_lead_chains : 0, ep, sm, g_dbg_buf, g_dbg_flags));
   return USF_OK;
 }
 
