@@ -165,6 +165,17 @@ int usf_base_logprob(const float* z, const float* z_lo, int64_t ldz, int64_t row
                      const float* loc, const float* scale, int32_t base_kind, float add_const,
                      float* out, void* stream);
 
+/* Affine coupling update (EXTENSION: the reference's MaskedCoupling, transforms.py:254-347, is additive only; this is
+ * the scale-and-shift form named by the task).  st [rows, 2h]: conditioner outputs of the h updated features, log-scale s
+ * in columns [0,h), shift t in [h,2h).  direction +1: x <- x*exp(s) + t, -1: x <- (x - t)*exp(-s), s clamped to
+ * [s_min, s_max]; x is given in the planes of the engine mode (any of f32 / hi+lo / bf16 / h16+l16) and updated in place;
+ * row_ladj[r] += sum_j s[r,j] (the layer's forward log|det J| of that row; may be NULL). */
+int usf_affine_couple(const float* st, int64_t ld_st, int64_t rows, int32_t h, float* x_f32, int64_t ld_f32, float* x_hi,
+                      float* x_lo, int64_t ld_split, void* x_bf16, int64_t ld_bf16, void* x_h16, void* x_l16, int64_t ld_16,
+                      int32_t* overflow_flag, float direction, float s_min, float s_max, float* row_ladj, void* stream);
+/* out[i] -= v[i]: per-row log-determinants leave the log-density (flows.py:234-245 with data-dependent layers) */
+int usf_sub_rows(float* out, const float* v, int64_t n, void* stream);
+
 /* z[r,j] = loc[j] + scale[j] * eps with eps ~ Laplace(0,1) or N(0,1) from Philox4x32-10(seed, offset).
  * Replaces DistributionModule.sample (distributions.py:147-148) in Flow.sample (flows.py:258). */
 int usf_base_sample(int64_t rows, int32_t d, const float* loc, const float* scale, int32_t base_kind,

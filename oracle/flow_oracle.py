@@ -255,6 +255,41 @@ def coupling_backward(y: Tensor, layer: dict, params, n_layers: int) -> Tensor:
 
 
 # --------------------------------------------------------------------------------------------------
+# Affine (scale-and-shift) coupling -- EXTENSION, spec["coupling"] == "affine".  The reference has no such layer
+# (its MaskedCoupling is additive, transforms.py:316-326 returns 0.0), so there is NO reference output to pin this
+# against: "parity unpinned" for this layer.  The form is the task's "masked affine coupling" with the clamped
+# log-scale of pyro.distributions.transforms.AffineCoupling (pyro-ppl 1.8.6): the conditioner emits [s | t] (2d values),
+#   forward  y = x * exp((1-m) s) + (1-m) t,   backward x = (y - (1-m) t) * exp(-(1-m) s),   s = clamp(s, lo, hi),
+#   forward log|det J| per row = sum_j (1-m_j) s_j.
+# Tests check it by round trip and against the autograd Jacobian in fp64.
+# --------------------------------------------------------------------------------------------------
+AFFINE_CLIP = (-5.0, 3.0)
+
+
+def affine_coupling_terms(x: Tensor, layer: dict, params, n_layers: int):
+    m = layer["mask"].to(x.dtype)
+    st = dense_nn(x * m, layer["prefix"], params, n_layers)
+    d = m.numel()
+    s = (1 - m) * st[..., :d].clamp(*AFFINE_CLIP)
+    t = (1 - m) * st[..., d:]
+    return s, t
+
+
+def affine_coupling_forward(x: Tensor, layer: dict, params, n_layers: int) -> Tensor:
+    s, t = affine_coupling_terms(x, layer, params, n_layers)
+    return x * torch.exp(s) + t
+
+
+def affine_coupling_backward(y: Tensor, layer: dict, params, n_layers: int) -> Tensor:
+    s, t = affine_coupling_terms(y, layer, params, n_layers)      # the masked features are unchanged by the layer
+    return (y - t) * torch.exp(-s)
+
+
+def affine_coupling_ladj(x_or_y: Tensor, layer: dict, params, n_layers: int) -> Tensor:
+    return affine_coupling_terms(x_or_y, layer, params, n_layers)[0].sum(-1)
+
+
+# --------------------------------------------------------------------------------------------------
 # elementwise layers (transforms.py:73-171, 174-251, 417-474)
 # --------------------------------------------------------------------------------------------------
 def scale_forward(x: Tensor, scale: Tensor) -> Tensor:
@@ -363,6 +398,8 @@ def layer_forward(x, layer, spec, params):
     if k == "inv_affine":                      # InverseTransform.forward -> inner.backward (:362-368)
         return block_affine_backward(x, layer["inner"], params, in_dims)
     if k == "coupling":
+        if spec.get("coupling") == "affine":
+            return affine_coupling_forward(x, layer, params, _n_cond_layers(spec))
         return coupling_forward(x, layer, params, _n_cond_layers(spec))
     if k == "scale":
         return scale_forward(x, params[layer["prefix"] + "scale"])
@@ -377,6 +414,8 @@ def layer_backward(y, layer, spec, params):
     if k == "inv_affine":                      # InverseTransform.backward -> inner.forward (:370-376)
         return block_affine_forward(y, layer["inner"], params, in_dims)
     if k == "coupling":
+        if spec.get("coupling") == "affine":
+            return affine_coupling_backward(y, layer, params, _n_cond_layers(spec))
         return coupling_backward(y, layer, params, _n_cond_layers(spec))
     if k == "scale":
         return scale_backward(y, params[layer["prefix"] + "scale"])
@@ -424,7 +463,10 @@ def flow_log_prob(x: Tensor, spec: dict, params, dtype=torch.float32) -> Tensor:
     log_det = torch.zeros(x.shape[0], dtype=dtype)
     for layer in reversed(build_layers(spec)):
         y = layer_backward(x, layer, spec, params)
-        log_det = log_det - layer_ladj(layer, spec, params)
+        if layer["kind"] == "coupling" and spec.get("coupling") == "affine":       # data-dependent log-det (extension)
+            log_det = log_det - affine_coupling_ladj(x, layer, params, _n_cond_layers(spec))
+        else:
+            log_det = log_det - layer_ladj(layer, spec, params)
         x = y
     return base_log_prob(x, spec, params) + log_det
 
@@ -522,7 +564,7 @@ def random_params(spec: dict, seed: int = 0, min_abs_scale: float = 0.1) -> Dict
                     w[torch.arange(d0), torch.randperm(d0, generator=g)] = 1.0
                     out[q + "w_0"] = w
         elif layer["kind"] == "coupling":
-            dims = [dtot] + hidden + [dtot]
+            dims = [dtot] + hidden + [2 * dtot if spec.get("coupling") == "affine" else dtot]
             for j in range(len(dims) - 1):
                 bound = 1 / math.sqrt(dims[j])
                 out[f"{p}layers.{j}.weight"] = uni((dims[j + 1], dims[j]), bound)

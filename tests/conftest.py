@@ -20,3 +20,12 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+@pytest.fixture
+def fake_ops(monkeypatch):
+    """The emulated backend (tests/fake_backend.py) in place of the C ABI: host logic without a GPU."""
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import fake_backend
+    fake_backend.install(monkeypatch)
+    return fake_backend

@@ -142,6 +142,29 @@ def flow_small(x, prog_i32, blob, n_ops, D, H, out):
     out.copy_(v[:, :d])
 
 
+def affine_couple(st, x, direction, s_min, s_max, row_ladj=None, overflow_flag=None):
+    CALLS.append(("affine_couple", direction))
+    h = x.width
+    s = st[:, :h].clamp(s_min, s_max)
+    t = st[:, h:2 * h]
+    if x.f32 is not None:
+        v = x.f32
+    elif x.h16 is not None:
+        v = f16_join(x.h16, x.l16)
+    elif x.hi is not None:
+        v = x.hi + x.lo
+    else:
+        v = x.bf16.float()
+    new = v * torch.exp(s) + t if direction > 0 else (v - t) * torch.exp(-s)
+    _store(x, new, overflow_flag)
+    if row_ladj is not None:
+        row_ladj += s.sum(-1)
+
+
+def sub_rows(out, v):
+    out -= v
+
+
 def leaky_relu(x, slope, y, neg_count=None):
     y.copy_(torch.where(x >= 0, x, x * slope))
     if neg_count is not None:
@@ -232,7 +255,7 @@ def require_cuda(t, name="tensor", dtype=torch.float32):
 
 def install(monkeypatch):
     CALLS.clear()
-    for name in ["flow_small", "linear", "ingest", "base_logprob", "base_sample", "leaky_relu", "permute", "lu_assemble",
+    for name in ["affine_couple", "sub_rows", "flow_small", "linear", "ingest", "base_logprob", "base_sample", "leaky_relu", "permute", "lu_assemble",
                  "lu_logabsdet", "vec_logabs", "tri_inverse", "transpose", "scale_rows_cols", "split_tf32", "split_f16", "to_bf16",
                  "householder_right", "softplus", "matmul_f32", "matmul_f64", "require_cuda"]:
         monkeypatch.setattr(real_ops, name, globals()[name])

@@ -31,7 +31,9 @@ def build_flow(spec, params, device="cuda", precision=None):
     flow = U.USFlow(
         base_distribution=base_cls(torch.zeros(d), torch.ones(d)), in_dims=list(spec["in_dims"]),
         coupling_blocks=spec["coupling_blocks"], conditioner_cls=U.DenseNN,
-        conditioner_args=dict(input_dim=d, hidden_dims=list(spec["hidden_dims"]), param_dims=[d]),
+        conditioner_args=dict(input_dim=d, hidden_dims=list(spec["hidden_dims"]),
+                              param_dims=[d, d] if spec.get("coupling") == "affine" else [d]),
+        coupling=spec.get("coupling", "additive"),
         prior_scale=1.0, lu_transform=spec.get("lu_transform", 1), householder=spec.get("householder", 1),
         affine_conjugation=spec.get("affine_conjugation", False), precision=precision)
     res = flow.load_state_dict(params, strict=True)

@@ -244,3 +244,59 @@ def test_small_batch_graph_replay_is_bit_identical():
         assert torch.equal(c, flow.log_prob(x)) and not torch.equal(c, plain)
     finally:
         flows.SMALL_BATCH_GRAPH_ROWS = keep
+
+
+AFFINE_SPECS = {
+    "d8_h32": dict(in_dims=[8], coupling_blocks=2, hidden_dims=[32, 32], affine_conjugation=True, lu_transform=1,
+                   householder=0, base="laplace", coupling="affine"),
+    "d64_h96": dict(in_dims=[64], coupling_blocks=2, hidden_dims=[96, 96], affine_conjugation=True, lu_transform=1,
+                    householder=0, base="normal", coupling="affine"),
+    "d784_h256": dict(in_dims=[784], coupling_blocks=2, hidden_dims=[256, 256], affine_conjugation=True, lu_transform=1,
+                      householder=0, base="laplace", coupling="affine"),
+}
+
+
+@pytest.mark.parametrize("mode,tol", [("fp32", 3e-5), ("fp32_tf32", 3e-5), ("fp32_simt", 3e-5)])
+@pytest.mark.parametrize("name", sorted(AFFINE_SPECS))
+def test_affine_coupling_extension_matches_its_restatement(name, mode, tol):
+    """Scale-and-shift coupling (extension; the reference has no such layer): the CUDA path against the fp64 evaluation of
+    the CPU restatement (tests/test_affine_coupling.py pins that restatement to first principles), incl. the per-row
+    log-determinants, chunking and the host-buffer path."""
+    spec = AFFINE_SPECS[name]
+    params = O.random_params(spec, 11)
+    g = torch.Generator().manual_seed(5)
+    d = spec["in_dims"][0]
+    last = len(spec["hidden_dims"])
+    for k in list(params):                      # log-scales of a freshly initialised conditioner are O(1): per-feature factors
+        if k.endswith(f"conditioner.layers.{last}.weight") or k.endswith(f"conditioner.layers.{last}.bias"):
+            params[k] = params[k].clone()       # of e^+-1 through dense LU layers make the random model ill-conditioned;
+            params[k][:d] *= 0.1                # a trained flow keeps them small
+    x = torch.rand(700, d, generator=g)
+    z0 = torch.randn(300, d, generator=g)
+    flow = build_flow(spec, params, precision=mode)
+    # the random LU layers are ill-conditioned (latents up to 1e6 at d = 784): the bound is the tolerance plus 3x the
+    # error the restatement itself makes in fp32 (the same rule as for the reference-pinned cases)
+    def bound(fn, arg, floor):
+        w64 = fn(arg, spec, params, torch.float64)
+        return w64, floor + 3.0 * rel_err(fn(arg, spec, params, torch.float32), w64)
+    want_lp, b_lp = bound(O.flow_log_prob, x, tol)
+    want_z, b_z = bound(O.flow_backward, x, 3 * tol)
+    want_y, b_y = bound(O.flow_forward, z0, 3 * tol)
+    got = flow.log_prob(x.cuda())
+    assert rel_err(got, want_lp) <= b_lp
+    assert rel_err(flow.backward(x.cuda()), want_z) <= b_z
+    assert rel_err(flow._forward(z0.cuda()), want_y) <= b_y
+    if mode == "fp32":
+        import usflows_b200 as U
+        U.set_chunk_rows(256)
+        try:
+            assert torch.equal(flow.log_prob(x.cuda()), got)             # per-row log-dets follow the chunks
+        finally:
+            U.set_chunk_rows(65536)
+        assert torch.equal(flow.log_prob_host(x.pin_memory()).cuda(), got)
+        layer = [l for l in flow.layers if type(l).__name__ == "MaskedAffineCoupling"][0]
+        m = layer.mask.reshape(-1).cpu()
+        st = O.dense_nn(x * m, "", {k[len("trainable_layers.1.conditioner."):]: v for k, v in params.items()
+                                    if k.startswith("trainable_layers.1.conditioner.")}, len(spec["hidden_dims"]) + 1)
+        want_ladj = ((1 - m) * st[:, :d].clamp(-5.0, 3.0)).sum(-1)
+        assert rel_err(layer.log_abs_det_jacobian(x.cuda()), want_ladj) <= 3e-5

@@ -7,12 +7,6 @@ import fake_backend
 from helpers import LARGE_CASES, SMALL_CASES, build_flow, load_case, rel_err
 
 
-@pytest.fixture
-def fake_ops(monkeypatch):
-    fake_backend.install(monkeypatch)
-    return fake_backend
-
-
 @pytest.mark.parametrize("mode", ["fp32_simt", "fp32", "fp32_tf32", "tf32"])
 @pytest.mark.parametrize("name", SMALL_CASES + ["c2_d784"])
 def test_flow_program_matches_reference(fake_ops, name, mode):

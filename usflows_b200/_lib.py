@@ -54,6 +54,8 @@ SIGNATURES = {
     "usf_base_logprob": (C.c_int, [_P, _P, _I64, _I64, _I32, _P, _P, _I32, _F, _P, _P]),
     "usf_flow_small": (C.c_int, [_P, _I64, _I64, _I32, _P, _I32, _P, _I32, _I32, _I32, _P, _I64, _P]),
     "usf_base_sample": (C.c_int, [_I64, _I32, _P, _P, _I32, _U64, _U64, _P, _I64, _P, _P, _I64, _P, _I64, _P]),
+    "usf_affine_couple": (C.c_int, [_P, _I64, _I64, _I32, _P, _I64, _P, _P, _I64, _P, _I64, _P, _P, _I64, _P, _F, _F, _F, _P, _P]),
+    "usf_sub_rows": (C.c_int, [_P, _P, _I64, _P]),
     "usf_leaky_relu": (C.c_int, [_P, _I64, _I64, _I32, _F, _P, _I64, _P, _P]),
     "usf_permute": (C.c_int, [_P, _I64, _I64, _I32, _P, _P, _I64, _P]),
     "usf_lu_assemble": (C.c_int, [_P, _P, _I32, _I64, _P, _P, _I64, _I32, _P]),

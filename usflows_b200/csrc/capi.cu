@@ -237,6 +237,29 @@ int usf_base_sample(int64_t rows, int32_t d, const float* loc, const float* scal
   return USF_OK;
 }
 
+int usf_affine_couple(const float* st, int64_t ld_st, int64_t rows, int32_t h, float* x_f32, int64_t ld_f32, float* x_hi,
+                      float* x_lo, int64_t ld_split, void* x_bf16, int64_t ld_bf16, void* x_h16, void* x_l16, int64_t ld_16,
+                      int32_t* overflow_flag, float direction, float s_min, float s_max, float* row_ladj, void* stream) {
+  USF_REQUIRE(st && rows >= 0 && h > 0, "bad input");
+  USF_REQUIRE(x_f32 || x_hi || x_bf16 || x_h16, "usf_affine_couple needs the planes of x");
+  USF_REQUIRE((x_hi == nullptr) == (x_lo == nullptr) && (x_h16 == nullptr) == (x_l16 == nullptr), "planes come as pairs");
+  USF_REQUIRE(direction == 1.f || direction == -1.f, "direction must be +1 or -1");
+  if (rows == 0) return USF_OK;
+  XPlanes p{x_f32, x_hi, x_lo, reinterpret_cast<__nv_bfloat16*>(x_bf16), reinterpret_cast<__half*>(x_h16),
+            reinterpret_cast<__half*>(x_l16), ld_f32, ld_split, ld_bf16, ld_16, overflow_flag};
+  affine_couple_kernel<<<ew_grid(rows * 32, 256), 256, 0, S(stream)>>>(st, ld_st, rows, h, p, direction, s_min, s_max, row_ladj);
+  USF_CUDA_OK(cudaGetLastError());
+  return USF_OK;
+}
+
+int usf_sub_rows(float* out, const float* v, int64_t n, void* stream) {
+  USF_REQUIRE(out && v && n >= 0, "bad input");
+  if (n == 0) return USF_OK;
+  sub_rows_kernel<<<ew_grid(n, 256), 256, 0, S(stream)>>>(out, v, n);
+  USF_CUDA_OK(cudaGetLastError());
+  return USF_OK;
+}
+
 int usf_leaky_relu(const float* x, int64_t ldx, int64_t rows, int32_t d, float slope, float* y, int64_t ldy,
                    float* neg_count, void* stream) {
   USF_REQUIRE(x && y && d > 0 && rows >= 0, "bad input");

@@ -233,6 +233,69 @@ leaky_relu_kernel(const float* __restrict__ x, long long ldx, long long rows, in
   }
 }
 
+// ---- affine coupling update (extension: the reference's coupling is additive only) ------------------------------------
+// st [rows, 2h] holds the conditioner outputs of the updated features: log-scale s in columns [0, h), shift t in [h, 2h).
+//   direction +1 (latent -> data): x <- x * exp(s) + t        direction -1 (data -> latent): x <- (x - t) * exp(-s)
+// with s clamped to [s_min, s_max]; the row's forward log|det J| = sum_j s_j is ADDED to row_ladj[r] (one warp per row,
+// shuffle reduction: the order of the sum is fixed).  x lives in whatever planes the engine mode uses and is updated in
+// place.
+struct XPlanes {
+  float* f32;
+  float* hi;
+  float* lo;
+  __nv_bfloat16* bf16;
+  __half* h16;
+  __half* l16;
+  long long ld_f32, ld_split, ld_bf16, ld_16;
+  int* overflow_flag;
+};
+__device__ __forceinline__ float xplanes_load(const XPlanes& p, long long r, int j) {
+  if (p.f32) return p.f32[r * p.ld_f32 + j];
+  if (p.h16) return f16_join(p.h16[r * p.ld_16 + j], p.l16[r * p.ld_16 + j]);
+  if (p.hi) return p.hi[r * p.ld_split + j] + p.lo[r * p.ld_split + j];
+  return __bfloat162float(p.bf16[r * p.ld_bf16 + j]);
+}
+__device__ __forceinline__ void xplanes_store(const XPlanes& p, long long r, int j, float v) {
+  if (p.f32) p.f32[r * p.ld_f32 + j] = v;
+  if (p.h16) {
+    __half h, l;
+    f16_split(v, h, l);
+    p.h16[r * p.ld_16 + j] = h;
+    p.l16[r * p.ld_16 + j] = l;
+    if (!(fabsf(v) <= F16_GUARD) && p.overflow_flag) *p.overflow_flag = 1;
+  }
+  if (p.hi) {
+    const float h = tf32_round(v);
+    p.hi[r * p.ld_split + j] = h;
+    p.lo[r * p.ld_split + j] = tf32_round(v - h);
+  }
+  if (p.bf16) p.bf16[r * p.ld_bf16 + j] = __float2bfloat16_rn(v);
+}
+
+__global__ void __launch_bounds__(256)
+affine_couple_kernel(const float* __restrict__ st, long long ld_st, long long rows, int h, XPlanes x, float direction,
+                     float s_min, float s_max, float* __restrict__ row_ladj) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (long long r = (long long)blockIdx.x * 8 + warp; r < rows; r += (long long)gridDim.x * 8) {
+    float acc = 0.f;
+    for (int j = lane; j < h; j += 32) {
+      const float s = fminf(fmaxf(st[r * ld_st + j], s_min), s_max);
+      const float t = st[r * ld_st + h + j];
+      const float v = xplanes_load(x, r, j);
+      xplanes_store(x, r, j, direction > 0.f ? fmaf(v, expf(s), t) : (v - t) * expf(-s));
+      acc += s;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0 && row_ladj) row_ladj[r] += acc;
+  }
+}
+
+// out[r] -= v[r]  (per-row log-determinants of affine couplings leave the density)
+__global__ void __launch_bounds__(256) sub_rows_kernel(float* __restrict__ out, const float* __restrict__ v, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) out[i] -= v[i];
+}
+
 __global__ void __launch_bounds__(256)
 permute_kernel(const float* __restrict__ x, long long ldx, long long rows, int d, const int* __restrict__ perm,
                float* __restrict__ y, long long ldy) {

@@ -163,7 +163,7 @@ def _compose_run(run: List[Prim]) -> Prim:
 
 @dataclass
 class Step:
-    kind: str                                  # "mm" | "leaky" | "permute" | "vec"
+    kind: str                                  # "mm" | "leaky" | "permute" | "vec" | "affine" (affine coupling update)
     src: str = "x"                             # "x" (stream) or "h" (conditioner hidden)
     dst: str = "x"
     w: Optional[torch.Tensor] = None           # operand-format weight [N, K] (hi plane / fp32 / bf16)
@@ -182,6 +182,7 @@ class Step:
     slope: float = 1.0
     perm: Optional[torch.Tensor] = None
     final: bool = False                        # writes the program's fp32 result
+    clip: Optional[tuple] = None               # "affine" steps: (log-scale min, max)
 
 
 def _operand(w64_or_32: torch.Tensor, mode: str, engine: int, overflow_flag: Optional[torch.Tensor] = None):
@@ -256,6 +257,7 @@ class Program:
                 items.append(p)
         flush()
         self.items = items
+        self.has_row_ladj = any(p.kind == "coupling" and p.prep.get("affine") for p in items)
         self.small = self._pack_small(items) if FUSE_SMALL else None
         # 2. widths, engine choice (tiny problems run the whole program on the SIMT engine)
         dims = []
@@ -290,7 +292,7 @@ class Program:
                 dd = p.W.shape[0]
             else:
                 ws = p.prep["weights"]
-                if len(ws) < 2:
+                if len(ws) < 2 or p.prep.get("affine"):
                     return None
                 dd = ws[0].shape[1]
                 if ws[-1].shape[0] != dd:
@@ -409,7 +411,11 @@ class Program:
             elif p.kind == "coupling":
                 ws, bs, mask = p.prep["weights"], p.prep["biases"], p.prep["mask"]
                 nl = len(ws)
+                affine = bool(p.prep.get("affine"))
+                dfull = mask.numel()
                 in_seg = out_seg = None
+                ws = list(ws)
+                bs = list(bs)
                 if compress is not None:
                     first = torch.equal(mask, compress["part"])       # conditioner reads the idx1 features
                     idx_in = compress["idx1"] if first else compress["idx0"]
@@ -417,23 +423,29 @@ class Program:
                     h1, h0 = compress["h1"], compress["h0"]
                     in_seg = (0, h1) if first else (h1, h0)
                     out_seg = (h1, h0) if first else (0, h1)
-                    ws = list(ws)
-                    bs = list(bs)
                     ws[0] = ws[0][:, idx_in]
-                    ws[-1] = ws[-1][idx_out]
-                    bs[-1] = bs[-1][idx_out]
+                    if affine:                                          # rows [0,d): log-scale, [d,2d): shift
+                        ws[-1] = torch.cat([ws[-1][idx_out], ws[-1][dfull + idx_out]])
+                        bs[-1] = torch.cat([bs[-1][idx_out], bs[-1][dfull + idx_out]])
+                    else:
+                        ws[-1] = ws[-1][idx_out]
+                        bs[-1] = bs[-1][idx_out]
                 else:                                                   # fold the mask into the first / last Linear
                     m = mask.reshape(-1).to(torch.float32)
-                    ws = list(ws)
-                    bs = list(bs)
                     ws[0] = ws[0] * m[None, :]
-                    ws[-1] = ws[-1] * (1 - m)[:, None]
-                    bs[-1] = bs[-1] * (1 - m)
+                    g = torch.cat([1 - m, 1 - m]) if affine else 1 - m
+                    ws[-1] = ws[-1] * g[:, None]
+                    bs[-1] = bs[-1] * g
                 for j in range(nl):
                     last = j == nl - 1
                     N, K = ws[j].shape
                     eng = _engine_for(mode, N, K)
                     w, w_lo = _operand(ws[j], mode, eng, self._flag_for_weights(ws[j].device))
+                    if last and affine:
+                        steps.append(Step("mm", src="x" if j == 0 else "h", dst="st", w=w, w_lo=w_lo, N=N, K=K, engine=eng,
+                                          bias=bs[j].to(torch.float32).contiguous(), in_seg=in_seg if j == 0 else None))
+                        steps.append(Step("affine", sign=p.sign, out_seg=out_seg, N=N // 2, clip=tuple(p.prep["clip"])))
+                        continue
                     steps.append(Step("mm", src="x" if j == 0 else "h", dst="x" if last else "h", w=w, w_lo=w_lo,
                                       N=N, K=K, engine=eng, bias=bs[j].to(torch.float32).contiguous(), relu=not last,
                                       resid=last, sign=p.sign, in_seg=in_seg if j == 0 else None,
@@ -449,6 +461,9 @@ class Program:
         if not steps:
             steps.append(Step("vec"))
         last_x = max(i for i, st in enumerate(steps) if st.dst == "x")
+        if steps[last_x].kind == "affine":
+            raise NotImplementedError("usflows_b200: a flow ending in an affine coupling needs a following layer "
+                                      "(USFlow ends in an LU layer and a scale)")
         steps[last_x].final = True
         return steps
 
@@ -465,7 +480,7 @@ class Program:
 
     def run(self, x: torch.Tensor, mode: Optional[str] = None, chunk_rows: Optional[int] = None,
             out: Optional[torch.Tensor] = None, sink=None,
-            flag_out: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
+            flag_out: Optional[torch.Tensor] = None, ladj_rows: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
         """Evaluate the program on x [rows, d].  With `sink`, the final stream value of each chunk is handed
         to `sink(chunk_f32 [r, width], r0, r1)` from a reused workspace buffer instead of being stored."""
         ops.require_cuda(x, "input")
@@ -485,7 +500,7 @@ class Program:
                 return None
             return res
         if self.force_fallback:
-            return self._fallback().run(x, chunk_rows=chunk_rows, out=out, sink=sink)
+            return self._fallback().run(x, chunk_rows=chunk_rows, out=out, sink=sink, ladj_rows=ladj_rows)
         cap = chunk_rows or _default_chunk_rows
         n_chunks = (rows + cap - 1) // cap
         chunk = min(rows, ((rows + n_chunks - 1) // n_chunks + 255) // 256 * 256)
@@ -497,12 +512,13 @@ class Program:
         for ci, r0 in enumerate(starts):
             r1 = min(rows, r0 + chunk)
             flag = flags[ci:ci + 1] if own_flags else flag_out
+            lr = None if ladj_rows is None else ladj_rows[r0:r1]
             if sink is not None:
                 fin = _workspace.planes(x.device, "final", r1 - r0, width, "f32")
-                self._run_chunk(x[r0:r1], fin, flag)
+                self._run_chunk(x[r0:r1], fin, flag, lr)
                 sink(fin, r0, r1)
             else:
-                self._run_chunk(x[r0:r1], out[r0:r1], flag)
+                self._run_chunk(x[r0:r1], out[r0:r1], flag, lr)
         if own_flags:
             # one device->host read per call: chunks whose activations left the fp16 range are recomputed with the
             # tf32-split engine (same accuracy class, no range limit)
@@ -510,12 +526,15 @@ class Program:
                 r0 = starts[ci]
                 r1 = min(rows, r0 + chunk)
                 fb = self._fallback()
+                lr = None if ladj_rows is None else ladj_rows[r0:r1]
+                if lr is not None:
+                    lr.zero_()                                  # the abandoned pass already added its log-scales
                 if sink is not None:
                     fin = _workspace.planes(x.device, "final", r1 - r0, width, "f32")
-                    fb._run_chunk(x[r0:r1], fin, None)
+                    fb._run_chunk(x[r0:r1], fin, None, lr)
                     sink(fin, r0, r1)
                 else:
-                    fb._run_chunk(x[r0:r1], out[r0:r1], None)
+                    fb._run_chunk(x[r0:r1], out[r0:r1], None, lr)
         return None if sink is not None else out
 
     def _stream_planes(self) -> set:
@@ -524,12 +543,14 @@ class Program:
     def _hidden_planes(self) -> set:
         return {"fp32": {"h16", "l16"}, "fp32_tf32": {"hi", "lo"}, "bf16": {"bf16"}}.get(self.mode, {"f32"})
 
-    def _run_chunk(self, x: torch.Tensor, final_out: torch.Tensor, flag: Optional[torch.Tensor] = None) -> None:
+    def _run_chunk(self, x: torch.Tensor, final_out: torch.Tensor, flag: Optional[torch.Tensor] = None,
+                   ladj_rows: Optional[torch.Tensor] = None) -> None:
         dev, rows = x.device, x.shape[0]
         steps = self.steps
         flip = {"x": 0, "h": 0}
         cur: Optional[Act] = None               # stream
         hid: Optional[Act] = None               # conditioner hidden
+        st_buf: Optional[torch.Tensor] = None   # affine coupling: [log-scale | shift] of the updated features
 
         def new_act(slot: str, width: int, planes: set) -> Act:
             flip[slot] ^= 1
@@ -555,7 +576,7 @@ class Program:
             nxt = steps[i + 1] if i + 1 < len(steps) else None
             if st.kind == "mm":
                 if st.src == "x":
-                    in_coupling = st.dst == "h" or st.resid
+                    in_coupling = st.dst in ("h", "st") or st.resid
                     need = self._stream_planes() if in_coupling else self._operand_planes()
                     direct_ok = st.engine == ENGINE_SIMT or (x.data_ptr() % 16 == 0 and x.stride(0) % 4 == 0)
                     if not all(getattr(cur, pl) is not None for pl in need) or (cur is src_f32 and not direct_ok):
@@ -567,7 +588,10 @@ class Program:
                     a = seg_view(cur, st.in_seg)
                 else:
                     a = hid
-                if st.dst == "h":
+                if st.dst == "st":                                    # affine coupling: log-scales and shifts, fp32
+                    out = Act(rows, st.N, f32=_workspace.planes(dev, "st", rows, st.N, "f32"))
+                    resid = None
+                elif st.dst == "h":
                     out = new_act("h", st.N, self._hidden_planes())
                     resid = None
                 elif st.resid:                                         # coupling output
@@ -598,10 +622,21 @@ class Program:
                     full_out = out
                 ops.linear(st.engine, a, st.w, st.w_lo, st.N, st.K, bias=st.bias, relu=st.relu, resid=resid,
                            resid_sign=st.sign, out=out, overflow_flag=flag)
-                if st.dst == "h":
+                if st.dst == "st":
+                    st_buf = out.f32
+                elif st.dst == "h":
                     hid = out
                 else:
                     cur = full_out
+            elif st.kind == "affine":                                  # x_seg <- x_seg * exp(s) + t  (or the inverse), in place
+                if cur is src_f32:                                     # never update the caller's tensor
+                    b = new_act("x", cur.width, self._stream_planes())
+                    ops.ingest(cur.f32, b, overflow_flag=flag)
+                    cur = b
+                target = seg_view(cur, st.out_seg)
+                ops.affine_couple(st_buf, target, st.sign, st.clip[0], st.clip[1], row_ladj=ladj_rows, overflow_flag=flag)
+                if nxt is not None and nxt.kind in ("leaky", "permute", "vec") and cur.f32 is None:
+                    raise NotImplementedError("usflows_b200: an elementwise layer directly after an affine coupling is not built")
             else:                                                      # elementwise kernels on the fp32 plane
                 if cur.f32 is None:
                     raise RuntimeError("internal: elementwise step needs an fp32 stream plane")
@@ -620,7 +655,7 @@ class Program:
     @classmethod
     def from_steps(cls, steps: List[Step], mode: str) -> "Program":
         prog = cls.__new__(cls)
-        prog.mode, prog.items, prog.compress, prog.steps, prog.small = mode, [], None, steps, None
+        prog.mode, prog.items, prog.compress, prog.steps, prog.small, prog.has_row_ladj = mode, [], None, steps, None, False
         prog.layers, prog.direction, prog._fallback_prog, prog._wflag, prog.force_fallback = [], "forward", None, None, False
         return prog
 

@@ -60,6 +60,13 @@ class ReferenceSemantics(torch.nn.Module):
                 self.kinds.append("affine")
                 for t in (W, Winv, b, ladj):
                     reg(t)
+            elif isinstance(layer, T.MaskedAffineCoupling):
+                self.kinds.append("affine_coupling")
+                reg(layer.mask.reshape(-1))
+                reg(torch.tensor([layer.log_scale_min_clip, layer.log_scale_max_clip]))
+                for lin in layer.conditioner.layers:
+                    reg(lin.weight)
+                    reg(lin.bias)
             elif isinstance(layer, T.MaskedCoupling):
                 self.kinds.append("coupling")
                 reg(layer.mask.reshape(-1))
@@ -114,6 +121,19 @@ class ReferenceSemantics(torch.nn.Module):
                     h = torch.relu(h)
             t = (1 - m) * h
             return (x + t if to_data else x - t), None              # transforms.py:277-306, 316-326
+        if kind == "affine_coupling":
+            m, clip = ts[0], ts[1]
+            h = x * m
+            n_lin = (len(ts) - 2) // 2
+            for j in range(n_lin):
+                h = torch.nn.functional.linear(h, ts[2 + 2 * j], ts[3 + 2 * j])
+                if j < n_lin - 1:
+                    h = torch.relu(h)
+            d = m.numel()
+            ls = (1 - m) * torch.minimum(torch.maximum(h[:, :d], clip[0]), clip[1])
+            t = (1 - m) * h[:, d:]
+            y = x * torch.exp(ls) + t if to_data else (x - t) * torch.exp(-ls)
+            return y, sign * ls.sum(-1)
         if kind == "scale":
             s = ts[0]
             return (x * s if to_data else x / s), sign * s.abs().log().sum()   # transforms.py:105-144

@@ -15,6 +15,7 @@ import torch
 
 from . import engine, ops
 from .distributions import DistributionModule, Independent
+from .transforms import MaskedAffineCoupling
 from .transforms import (BaseTransform, BlockAffineTransform, HouseholderTransform, InverseTransform, LUTransform,
                          MaskedCoupling, ScaleTransform, SequentialAffineTransform)
 
@@ -129,7 +130,7 @@ class Flow(torch.nn.Module):
         d = x2.shape[1]
         rows = x2.shape[0]
         if x2.is_cuda and 0 < rows <= SMALL_BATCH_GRAPH_ROWS and getattr(prog, "small", None) is None \
-                and not prog.force_fallback and not torch.cuda.is_current_stream_capturing():
+                and not prog.force_fallback and not prog.has_row_ladj and not torch.cuda.is_current_stream_capturing():
             lp = self._log_prob_small_batch(prog, ladj, x2)
             if lp is not None:
                 return lp.reshape(batch_shape)
@@ -139,7 +140,13 @@ class Flow(torch.nn.Module):
             ops.base_logprob(ops.Act(r1 - r0, d, f32=z_chunk), loc, scale, base.base_kind, -ladj, out[r0:r1])
 
         with torch.no_grad():
-            prog.run(x2, sink=sink)
+            if prog.has_row_ladj:          # affine couplings: per-row log-determinants next to the model constant
+                row_ladj = torch.zeros(rows, dtype=torch.float32, device=x2.device)
+                prog.run(x2, sink=sink, ladj_rows=row_ladj)
+                if rows:
+                    ops.sub_rows(out, row_ladj)
+            else:
+                prog.run(x2, sink=sink)
         return out.reshape(batch_shape)
 
     def _log_prob_small_batch(self, prog, ladj: float, x2: torch.Tensor):
@@ -242,7 +249,9 @@ class Flow(torch.nn.Module):
                                  out_dev[r0 + a:r0 + b])
             return sink
 
-        use_graphs = HOST_CUDA_GRAPHS and not prog.force_fallback and rows >= chunk and getattr(prog, "small", None) is None
+        use_graphs = HOST_CUDA_GRAPHS and not prog.force_fallback and rows >= chunk and getattr(prog, "small", None) is None \
+            and not prog.has_row_ladj
+        row_ladj = torch.zeros(rows, dtype=torch.float32, device=dev) if prog.has_row_ladj else None
         with torch.no_grad():
             graphs = [self._chunk_graph(prog, s, self._host_bufs[s], d) for s in range(2)] if use_graphs else None
             if graphs is not None:
@@ -266,7 +275,8 @@ class Flow(torch.nn.Module):
                     make_sink(r0)(graphs[i & 1]["fin"], 0, chunk)
                 else:
                     prog.run(buf, chunk_rows=chunk, sink=make_sink(r0),
-                             flag_out=flags[i:i + 1] if guarded else None)
+                             flag_out=flags[i:i + 1] if guarded else None,
+                             ladj_rows=None if row_ladj is None else row_ladj[r0:r1])
                 consumed[i & 1].record(main)
             if guarded:                                   # one sync; out-of-range chunks go through the tf32 split
                 redo = set(torch.nonzero(flags).reshape(-1).tolist())
@@ -277,7 +287,12 @@ class Flow(torch.nn.Module):
                     r1 = min(rows, r0 + chunk)
                     buf = self._host_bufs[0][: r1 - r0]
                     buf.copy_(x2[r0:r1])
-                    prog._fallback().run(buf, chunk_rows=chunk, sink=make_sink(r0))
+                    if row_ladj is not None:
+                        row_ladj[r0:r1].zero_()
+                    prog._fallback().run(buf, chunk_rows=chunk, sink=make_sink(r0),
+                                         ladj_rows=None if row_ladj is None else row_ladj[r0:r1])
+            if row_ladj is not None and rows:
+                ops.sub_rows(out_dev, row_ladj)
             out_host.reshape(-1)[:rows].copy_(out_dev, non_blocking=True)
             main.synchronize()
         return out_host
@@ -387,6 +402,12 @@ class USFlow(Flow):
             raise ValueError("Number of Householder vectors transforms must be non-negative")
         self.lu_transform = lu_transform
         self.householder = householder
+        # EXTENSION (not in the reference, whose coupling is additive only): coupling="affine" builds scale-and-shift
+        # couplings; the conditioner then has to emit 2*d values (DenseNN: param_dims=[d, d])
+        coupling = kwargs.pop("coupling", "additive")
+        if coupling not in ("additive", "affine"):
+            raise ValueError(f"Unknown coupling type {coupling}")
+        self.coupling = coupling
 
         layers = []
         mask = self.mask_Generator(in_dims)
@@ -398,7 +419,8 @@ class USFlow(Flow):
             if affine_layers:
                 block_affine_layer = BlockAffineTransform(in_dims, SequentialAffineTransform(affine_layers))
                 layers.append(block_affine_layer)
-            layers.append(MaskedCoupling(mask, conditioner_cls(**conditioner_args)))
+            coupling_cls = MaskedAffineCoupling if coupling == "affine" else MaskedCoupling
+            layers.append(coupling_cls(mask, conditioner_cls(**conditioner_args)))
             if affine_conjugation and block_affine_layer is not None:
                 layers.append(InverseTransform(block_affine_layer))   # shares parameters (flows.py:469-470)
             mask = 1 - mask

@@ -28,6 +28,7 @@ class DenseNN(torch.nn.Module):
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         from . import engine
-        if self.count_params != 1:
-            raise NotImplementedError("usflows_b200.nn.DenseNN: only len(param_dims) == 1 is built")
-        return engine.run_mlp(self, x)
+        out = engine.run_mlp(self, x)
+        if self.count_params == 1:
+            return out
+        return tuple(out.split(self.param_dims, dim=-1))       # pyro.nn.DenseNN returns one tensor per entry of param_dims

@@ -150,6 +150,24 @@ def flow_small(x: torch.Tensor, prog_i32: torch.Tensor, blob: torch.Tensor, n_op
                                      _ptr(out), _ld(out), _stream()))
 
 
+def affine_couple(st: torch.Tensor, x: Act, direction: float, s_min: float, s_max: float,
+                  row_ladj: Optional[torch.Tensor] = None, overflow_flag: Optional[torch.Tensor] = None) -> None:
+    """In-place affine coupling update of the planes of `x` [rows, h] from st [rows, 2h]; see usf_affine_couple."""
+    global LAUNCHES
+    LAUNCHES += 1
+    check(_lib.load().usf_affine_couple(
+        _ptr(st), _ld(st), x.rows, x.width,
+        _ptr(x.f32), _ld(x.f32) if x.f32 is not None else 0,
+        _ptr(x.hi), _ptr(x.lo), _ld(x.hi) if x.hi is not None else 0,
+        _ptr(x.bf16), _ld(x.bf16) if x.bf16 is not None else 0,
+        _ptr(x.h16), _ptr(x.l16), _ld(x.h16) if x.h16 is not None else 0,
+        _ptr(overflow_flag), float(direction), float(s_min), float(s_max), _ptr(row_ladj), _stream()))
+
+
+def sub_rows(out: torch.Tensor, v: torch.Tensor) -> None:
+    check(_lib.load().usf_sub_rows(_ptr(out), _ptr(v), out.numel(), _stream()))
+
+
 def leaky_relu(x: torch.Tensor, slope: float, y: torch.Tensor, neg_count: Optional[torch.Tensor] = None) -> None:
     rows, d = x.shape
     check(_lib.load().usf_leaky_relu(_ptr(x), _ld(x), rows, d, float(slope), _ptr(y), _ld(y), _ptr(neg_count), _stream()))

@@ -151,6 +151,19 @@ def _layer_backward(layer, y: torch.Tensor, inverse: bool = False, cache: Option
         s = layer.scale.reshape(-1)
         ladj = s.abs().log().sum()
         return (y * s if inverse else y / s), ladj      # transforms.py:105-125, 135-144
+    if isinstance(layer, T.MaskedAffineCoupling):
+        m = layer.mask.reshape(-1).to(y.dtype)
+        h = y * m
+        lin = list(layer.conditioner.layers)
+        for j, l in enumerate(lin):
+            h = linear(h, l.weight, l.bias)
+            if j < len(lin) - 1:
+                h = torch.relu(h)
+        d = m.numel()
+        s = (1 - m) * h[:, :d].clamp(layer.log_scale_min_clip, layer.log_scale_max_clip)
+        t = (1 - m) * h[:, d:]
+        ladj = s.sum(-1)                                               # per row
+        return (y * torch.exp(s) + t if inverse else (y - t) * torch.exp(-s)), ladj
     if isinstance(layer, T.MaskedCoupling):
         m = layer.mask.reshape(-1).to(y.dtype)
         h = y * m
@@ -181,7 +194,7 @@ def base_log_prob(base, z: torch.Tensor) -> torch.Tensor:
 def log_prob_autograd(flow, x: torch.Tensor) -> torch.Tensor:
     """`Flow.log_prob` (flows.py:225-245) as an autograd graph over the flow's parameters."""
     z = x.reshape(x.shape[0], -1)
-    total = z.new_zeros(())
+    total = z.new_zeros(())                      # scalar, or [rows] once a data-dependent log-det joins
     cache: dict = {}
     for layer in reversed(flow.layers):
         z, ladj = _layer_backward(layer, z, cache=cache)

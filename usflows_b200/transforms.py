@@ -508,3 +508,40 @@ class MaskedCoupling(BaseTransform):
             self._prep_cache = dict(weights=ws, biases=bs)
             self._prep_key = key
         return self._prep_cache
+
+
+class MaskedAffineCoupling(MaskedCoupling):
+    """y = x * exp((1 - mask) * s) + (1 - mask) * t  with (s, t) = conditioner(x * mask), s clamped to
+    [log_scale_min_clip, log_scale_max_clip]; forward log|det J| of a row = sum_j (1 - mask_j) s_j.
+
+    EXTENSION: the reference's `MaskedCoupling` (transforms.py:254-347) is additive only; this scale-and-shift form is
+    the "masked affine coupling" the task names, with the clamped log-scale of pyro's `AffineCoupling`.  The
+    conditioner is a `usflows_b200.nn.DenseNN` with `param_dims=[d, d]` (log-scale block first, then shift).  Its
+    log-det is data dependent, so a flow containing it carries a per-row log-det vector next to the model constant."""
+
+    def __init__(self, mask: torch.Tensor, conditioner: nn.Module, log_scale_min_clip: float = -5.0,
+                 log_scale_max_clip: float = 3.0):
+        super().__init__(mask, conditioner)
+        d = int(mask.numel())
+        out = list(conditioner.layers)[-1].weight.shape[0]
+        if out != 2 * d:
+            raise ValueError(f"MaskedAffineCoupling: the conditioner must emit 2*d = {2 * d} values (param_dims=[d, d]), got {out}")
+        self.log_scale_min_clip = float(log_scale_min_clip)
+        self.log_scale_max_clip = float(log_scale_max_clip)
+
+    def _raw(self) -> dict:
+        raw = super()._raw()
+        raw.update(affine=True, clip=(self.log_scale_min_clip, self.log_scale_max_clip))
+        return raw
+
+    def log_abs_det_jacobian(self, x=None, y=None, context=None):
+        """Per-row forward log|det J| (needs the input x of `forward`, or equivalently its output y: the conditioner
+        sees only the masked features, which the layer leaves unchanged)."""
+        from . import engine
+        ref = x if x is not None else y
+        if ref is None:
+            raise ValueError("MaskedAffineCoupling.log_abs_det_jacobian needs x or y (the log-det is data dependent)")
+        m = self.mask.to(ref.device).reshape(-1).to(torch.float32)
+        st = engine.run_mlp(self.conditioner, (ref.reshape(-1, m.numel()) * m).contiguous())
+        s = st[:, :m.numel()].clamp(self.log_scale_min_clip, self.log_scale_max_clip)
+        return ((1 - m) * s).sum(-1).reshape(ref.shape[:-1])
