@@ -40,6 +40,14 @@ WORKLOADS = {
     "c5": dict(spec=dict(in_dims=[3072], coupling_blocks=4, hidden_dims=[1024, 1024], affine_conjugation=True,
                          lu_transform=1, householder=0, base="laplace"), rows=32768, cpu_rows=2048,
                name="C5 3072-D USFlow (B=4, MLP 1024x1024, Laplace) batch log_prob"),
+    # C2's shape with the reference's own MLP-style conditioner (networks.ConvNet, vector branch: 2 gated blocks of width
+    # 1024 with LayerNorm) and the base of its live MNIST configuration (experiments/mnist/mnist.yaml:79-92: L1-radial,
+    # LogNormal radius) -- SURVEY 8f rows 2 and 4
+    "c2cn": dict(spec=dict(in_dims=[784], coupling_blocks=4, conditioner="convnet", c_hidden=[1024, 1024], gating=True,
+                           normalize_layers=True, affine_conjugation=True, lu_transform=1, householder=0, base="radial",
+                           p=1, norm="lognormal"), rows=65536, cpu_rows=4096,
+                 name="C2-shaped 784-D USFlow (B=4, ConvNet conditioner 2 gated blocks x 1024 + LayerNorm, L1-radial "
+                      "LogNormal base) batch log_prob"),
     "c1": dict(spec=dict(in_dims=[2], coupling_blocks=10, hidden_dims=[32, 32], affine_conjugation=True,
                          lu_transform=1, householder=0, base="laplace"), rows=1 << 20, cpu_rows=65536,
                name="C1 2-D USFlow (B=10, MLP 32x32, Laplace) batch log_prob"),
@@ -49,8 +57,15 @@ WORKLOADS = {
 def algorithmic_flops_per_sample(spec) -> float:
     """(2B+1) * 2 d^2 + B * 2 (d H + H^2 + H d) with conjugation (B+1 affine layers without)."""
     d, B = spec["in_dims"][0], spec["coupling_blocks"]
-    dims = [d] + list(spec["hidden_dims"]) + [d]
-    mlp = sum(2 * dims[i] * dims[i + 1] for i in range(len(dims) - 1))
+    if spec.get("conditioner") == "convnet":       # Linear(d,h0) + per block [h_in h + h 2h (+ proj)] + Linear(h_last, d)
+        ch = list(spec["c_hidden"])
+        mlp = 2 * d * ch[0] + 2 * ch[-1] * d
+        for i, oc in enumerate(ch):
+            ic = ch[i - 1] if i > 0 else ch[0]
+            mlp += 2 * ic * oc + (2 * oc * 2 * oc if spec.get("gating", True) else 0) + (2 * ic * oc if ic != oc else 0)
+    else:
+        dims = [d] + list(spec["hidden_dims"]) + [d]
+        mlp = sum(2 * dims[i] * dims[i + 1] for i in range(len(dims) - 1))
     n_aff = 2 * B + 1 if spec.get("affine_conjugation") else B + 1
     return n_aff * 2 * d * d + B * mlp
 
@@ -172,7 +187,7 @@ def main():
         rows = args.rows or wl["cpu_rows"]
         v_asis, v_am, cores, t = cpu_reference_run(wl, max(1, args.steps), max(1, min(args.warmup, 1)), rows)
         line = dict(base_line, impl="reference", value=v_asis, ms_per_step=t * 1e3, dtype="f32",
-                    config=dict(workload=wl["name"], rows_per_step=rows, d=d, hidden=spec["hidden_dims"],
+                    config=dict(workload=wl["name"], rows_per_step=rows, d=d, hidden=spec.get("hidden_dims", spec.get("c_hidden")),
                                 coupling_blocks=spec["coupling_blocks"], engine="torch CPU (oracle port of the reference)"),
                     cpu_baseline=dict(value=v_asis, unit="samples/s", cores=cores, kind="port",
                                       sample=f"{rows} rows x {max(1, args.steps)} steps of the same workload; "
@@ -362,7 +377,7 @@ def main():
         dtype={"fp32": "f32 (fp16-split x3 on tcgen05 kind::f16, fp32 accumulate/promote; tf32-split fallback)",
                "fp32_tf32": "f32 (tf32-split x3 on tcgen05 kind::tf32)", "fp32_simt": "f32", "tf32": "tf32",
                "bf16": "bf16"}[args.precision],
-        config=dict(workload=wl["name"], rows_per_gpu_per_step=rows, d=d, hidden=spec["hidden_dims"],
+        config=dict(workload=wl["name"], rows_per_gpu_per_step=rows, d=d, hidden=spec.get("hidden_dims", spec.get("c_hidden")),
                     coupling_blocks=spec["coupling_blocks"], precision=args.precision,
                     chunk_rows=engine._default_chunk_rows, l2="inputs larger than L2, no flush",
                     flops_per_sample=flops_per_sample, prep_ms_once_per_weight_version=prep_ms),

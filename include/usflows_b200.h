@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define USF_ABI_VERSION 2
+#define USF_ABI_VERSION 3
 
 #define USF_OK 0
 #define USF_ERR_INVALID (-1)     /* bad argument (shape, alignment, null pointer) */
@@ -42,6 +42,21 @@ extern "C" {
 /* base distributions (distributions.py:199-238) */
 #define USF_BASE_LAPLACE 0
 #define USF_BASE_NORMAL 1
+
+/* Lp-radial base distribution (distributions.py:327-372): the norm and the distribution of the radius */
+#define USF_LP_INF 0
+#define USF_LP_1 1
+#define USF_LP_2 2
+#define USF_NORM_LOGNORMAL 0     /* params = [mu, sigma]                                  (distributions.py:181-197) */
+#define USF_NORM_GAMMA_MIXTURE 1 /* params = [logits (K) | concentration (K) | rate (K)]  (distributions.py:674-707) */
+
+/* output planes of an activation in the operand format(s) of an engine mode; unused planes are NULL */
+typedef struct usf_planes {
+  float* f32;  int64_t ld_f32;
+  float* hi;   float* lo;  int64_t ld_split;   /* tf32 split  */
+  void* bf16;  int64_t ld_bf16;
+  void* h16;   void* l16;  int64_t ld_16;      /* fp16 split (x = h16 + l16 * 2^-11) */
+} usf_planes;
 
 const char* usf_last_error(void);
 int usf_abi_version(void);
@@ -181,6 +196,30 @@ int usf_sub_rows(float* out, const float* v, int64_t n, void* stream);
 int usf_base_sample(int64_t rows, int32_t d, const float* loc, const float* scale, int32_t base_kind,
                     uint64_t seed, uint64_t offset, float* out_f32, int64_t ld_f32, float* out_hi,
                     float* out_lo, int64_t ld_split, void* out_bf16, int64_t ld_bf16, void* stream);
+
+/* Lp-radial base density:  out[r] = log f_R(r_r) - [dv_const + (d-1) log r_r] + add_const,  r_r = ||z[r,:] - loc||_p
+ * (z = z [+ z_lo]); f_R is LogNormal(mu, sigma) or a K-component Gamma mixture (K <= 128), `norm_params` as listed at
+ * USF_NORM_*, already constrained (sigma, concentration, rate > 0; logits raw).  dv_const = the r-independent part of
+ * log dV_p^d/dr.  Replaces RadialDistribution.log_prob + log_delta_volume (distributions.py:501-549), the norm
+ * distributions' log_prob (torch LogNormal / MixtureSameFamily(Categorical, Gamma)) and the `+ log_det` of Flow.log_prob. */
+int usf_radial_logprob(const float* z, const float* z_lo, int64_t ldz, int64_t rows, int32_t d, const float* loc,
+                       int32_t p_kind, int32_t norm_kind, const float* norm_params, int32_t n_comp, float dv_const,
+                       float add_const, float* out, void* stream);
+/* z[r,:] = loc + R_r * u_r,  R_r ~ f_R,  u_r uniform on the unit Lp sphere (p = 2: normalised Gaussian, p = 1: signed
+ * Dirichlet(1..1), p = inf: uniform cube face with one coordinate pinned to +1, as UniformUnitLpBall.sample,
+ * distributions.py:286-316); Philox4x32-10(seed, offset).  Replaces RadialDistribution.sample (distributions.py:478-499). */
+int usf_radial_sample(int64_t rows, int32_t d, const float* loc, int32_t p_kind, int32_t norm_kind,
+                      const float* norm_params, int32_t n_comp, uint64_t seed, uint64_t offset, float* out, int64_t ldo,
+                      void* stream);
+
+/* Row-wise glue of networks.ConvNet's vector branch (networks.py:205-245, 287-307) between two usf_linear calls:
+ *   v = gated ? xres[r,j] + o[r,j] * sigmoid(o[r,n+j]) : o[r,j]        (GatedMLP: o = [val | gate], xres = x or proj(x))
+ *   v = gamma ? LayerNorm_row(v; gamma, beta, eps) : v                  (LayerNormVector, biased variance)
+ *   y_f32 <- v (may alias xres);  act <- act_relu ? max(v,0) : v;  raw <- v     (each of y_f32 / act / raw may be NULL)
+ * n <= 6144.  overflow_flag: set when a value written to fp16 split planes leaves the fp16 range (may be NULL). */
+int usf_gate_norm(const float* o, int64_t ldo, const float* xres, int64_t ldx, int64_t rows, int32_t n, int32_t gated,
+                  const float* gamma, const float* beta, float eps, float* y_f32, int64_t ldy, const usf_planes* act,
+                  int32_t act_relu, const usf_planes* raw, int32_t* overflow_flag, void* stream);
 
 /* y = x >= 0 ? x : slope * x ; optional per-row count of negative inputs (for log|det J| = log(slope)*count).
  * Replaces LeakyReLUTransform.forward/backward (transforms.py:434-454). */

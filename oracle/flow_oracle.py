@@ -20,7 +20,9 @@ the reference has no test for it, so that single function is "parity unpinned" a
 
 The model is described by
   spec  : dict(in_dims, coupling_blocks, hidden_dims, affine_conjugation, lu_transform, householder,
-               base ("laplace"|"normal"), masktype ("checkerboard"|"channel"))
+               base ("laplace"|"normal"|"radial" with p (1|2|"inf"), norm ("lognormal"|"gammamm"), n_comp),
+               masktype ("checkerboard"|"channel"),
+               conditioner ("densenn" (default) | "convnet" with c_hidden, gating, normalize_layers))
   params: dict name -> torch CPU tensor, keyed exactly like the reference `USFlow.state_dict()`.
 """
 from __future__ import annotations
@@ -242,16 +244,51 @@ def dense_nn(x: Tensor, prefix: str, params, n_layers: int) -> Tensor:
     return F.linear(h, params[f"{prefix}layers.{j}.weight"], params[f"{prefix}layers.{j}.bias"])
 
 
-def coupling_forward(x: Tensor, layer: dict, params, n_layers: int) -> Tensor:
+def convnet_vector(x: Tensor, prefix: str, params, spec: dict) -> Tensor:
+    """networks.ConvNet.forward for 1-D in_dims (networks.py:379-389) over the module list built at :287-307:
+    Linear(d, h0) -> per hidden width [GatedMLP (:222-245) | Sequential(ReLU, Linear)] [-> LayerNormVector (:205-219)]
+    -> Linear(h_last, c_out).  State-dict names `nn.{i}. ...` as the reference's nn.Sequential numbers them."""
+    c_hidden = list(spec["c_hidden"])
+    gating, normalize = spec.get("gating", True), spec.get("normalize_layers", True)
+    h = F.linear(x, params[f"{prefix}nn.0.weight"], params[f"{prefix}nn.0.bias"])
+    idx = 1
+    for i, out_ch in enumerate(c_hidden):
+        in_ch = c_hidden[i - 1] if i > 0 else c_hidden[0]
+        q = f"{prefix}nn.{idx}."
+        if gating:                                               # GatedMLP.forward, networks.py:237-245
+            out = F.linear(F.relu(h), params[q + "net1.1.weight"], params[q + "net1.1.bias"])
+            out = F.linear(F.relu(out), params[q + "net1.3.weight"], params[q + "net1.3.bias"])
+            val, gate = out.chunk(2, dim=1)
+            res = val * torch.sigmoid(gate)
+            if in_ch != out_ch:
+                h = F.linear(h, params[q + "proj.weight"], params[q + "proj.bias"])
+            h = h + res
+        else:                                                    # nn.Sequential(nonlinearity, nn.Linear), networks.py:300
+            h = F.linear(F.relu(h), params[q + "1.weight"], params[q + "1.bias"])
+        idx += 1
+        if normalize:                                            # LayerNormVector -> nn.LayerNorm(eps=1e-5)
+            q = f"{prefix}nn.{idx}.layernorm."
+            h = F.layer_norm(h, (out_ch,), params[q + "weight"], params[q + "bias"], 1e-5)
+            idx += 1
+    return F.linear(h, params[f"{prefix}nn.{idx}.weight"], params[f"{prefix}nn.{idx}.bias"])
+
+
+def conditioner(x: Tensor, layer: dict, params, n_layers: int, spec=None) -> Tensor:
+    if spec is not None and spec.get("conditioner") == "convnet":
+        return convnet_vector(x, layer["prefix"], params, spec)
+    return dense_nn(x, layer["prefix"], params, n_layers)
+
+
+def coupling_forward(x: Tensor, layer: dict, params, n_layers: int, spec=None) -> Tensor:
     """transforms.py:277-290: x + (1 - mask) * conditioner(x * mask)."""
     m = layer["mask"].to(x.dtype)
-    return x + (1 - m) * dense_nn(x * m, layer["prefix"], params, n_layers)
+    return x + (1 - m) * conditioner(x * m, layer, params, n_layers, spec)
 
 
-def coupling_backward(y: Tensor, layer: dict, params, n_layers: int) -> Tensor:
+def coupling_backward(y: Tensor, layer: dict, params, n_layers: int, spec=None) -> Tensor:
     """transforms.py:292-306: y - (1 - mask) * conditioner(y * mask)."""
     m = layer["mask"].to(y.dtype)
-    return y - (1 - m) * dense_nn(y * m, layer["prefix"], params, n_layers)
+    return y - (1 - m) * conditioner(y * m, layer, params, n_layers, spec)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -360,6 +397,8 @@ def base_log_prob(z: Tensor, spec: dict, params) -> Tensor:
     (DIndependent, distributions.py:133-137).
     Laplace: -log(2 s) - |z - mu| / s ;  Normal: -(z-mu)^2/(2 s^2) - log s - log sqrt(2 pi)."""
     loc = params["base_distribution.loc"]
+    if spec.get("base") == "radial":
+        return radial_log_prob(z, spec, params)
     s = base_scale(params)
     if spec.get("base", "laplace") == "laplace":
         lp = -torch.log(2 * s) - torch.abs(z - loc) / s
@@ -367,6 +406,49 @@ def base_log_prob(z: Tensor, spec: dict, params) -> Tensor:
         var = s ** 2
         lp = -((z - loc) ** 2) / (2 * var) - s.log() - math.log(math.sqrt(2 * math.pi))
     return lp.sum(dim=tuple(range(z.dim() - loc.dim(), z.dim()))) if loc.dim() >= 1 else lp
+
+
+def _radial_p(spec) -> float:
+    return math.inf if spec["p"] == "inf" else float(spec["p"])
+
+
+def radial_norm_distribution(spec: dict, params):
+    """The torch distribution the reference's DistributionModule builds for the radius (distributions.py:129-138):
+    LogNormal(loc, softplus(scale_unconstrained)) made Independent over its batch dim (:181-197), or
+    MixtureSameFamily(Categorical(logits), Gamma(softplus(.), softplus(.))) (:674-707)."""
+    q = "base_distribution.norm_distribution."
+    if spec["norm"] == "lognormal":
+        d = torch.distributions.LogNormal(params[q + "loc"], F.softplus(params[q + "scale_unconstrained"]))
+        return torch.distributions.Independent(d, len(d.batch_shape))
+    conc = F.softplus(params[q + "concentration_unconstrained"])
+    rate = F.softplus(params[q + "rate_unconstrained"])
+    return torch.distributions.MixtureSameFamily(torch.distributions.Categorical(logits=params[q + "mixture_logits"]),
+                                                 torch.distributions.Gamma(conc, rate), validate_args=False)
+
+
+def radial_log_delta_volume(p: float, r: Tensor, dim: int) -> Tensor:
+    """distributions.py:514-549, term by term in the reference's order."""
+    if p == 1:
+        log_denominator = sum([math.log(i) for i in range(1, dim)])
+        return math.log(2) * dim + torch.log(r) * (dim - 1) - log_denominator
+    if p == 2:
+        log_numerator = math.log(dim) + (dim / 2) * math.log(math.pi) + (dim - 1) * torch.log(r)
+        return log_numerator - math.lgamma((dim / 2) + 1)
+    return math.log(dim) + dim * math.log(2) + (dim - 1) * torch.log(r)
+
+
+def radial_log_prob(x: Tensor, spec: dict, params) -> Tensor:
+    """RadialDistribution.log_prob (distributions.py:501-512): r = ||x - loc||_p over the event dims,
+    norm_distribution.log_prob(r[..., None])[..., 0] - log_delta_volume(p, r)."""
+    loc = params["base_distribution.loc"]
+    p = _radial_p(spec)
+    x = x - loc
+    event_dims = tuple(range(x.dim() - loc.dim(), x.dim()))
+    r = x.norm(p=p, dim=event_dims)
+    log_prob_norm = radial_norm_distribution(spec, params).log_prob(r.unsqueeze(-1))
+    if log_prob_norm.dim() > r.dim():
+        log_prob_norm = log_prob_norm.squeeze(-1)
+    return log_prob_norm - radial_log_delta_volume(p, r, loc.numel())
 
 
 def base_sample_from_uniform(u: Tensor, spec: dict, params) -> Tensor:
@@ -387,7 +469,7 @@ def _cast(params, dtype):
 
 
 def _n_cond_layers(spec) -> int:
-    return len(spec["hidden_dims"]) + 1
+    return len(spec.get("hidden_dims", [])) + 1
 
 
 def layer_forward(x, layer, spec, params):
@@ -400,7 +482,7 @@ def layer_forward(x, layer, spec, params):
     if k == "coupling":
         if spec.get("coupling") == "affine":
             return affine_coupling_forward(x, layer, params, _n_cond_layers(spec))
-        return coupling_forward(x, layer, params, _n_cond_layers(spec))
+        return coupling_forward(x, layer, params, _n_cond_layers(spec), spec)
     if k == "scale":
         return scale_forward(x, params[layer["prefix"] + "scale"])
     raise ValueError(k)
@@ -416,7 +498,7 @@ def layer_backward(y, layer, spec, params):
     if k == "coupling":
         if spec.get("coupling") == "affine":
             return affine_coupling_backward(y, layer, params, _n_cond_layers(spec))
-        return coupling_backward(y, layer, params, _n_cond_layers(spec))
+        return coupling_backward(y, layer, params, _n_cond_layers(spec), spec)
     if k == "scale":
         return scale_backward(y, params[layer["prefix"] + "scale"])
     raise ValueError(k)
@@ -501,7 +583,8 @@ def flow_log_prob_amortised(x: Tensor, spec: dict, params, dtype=torch.float32, 
                 prepared[i] = (_view_w(affine_matrix(layer["inner"], params), rank),
                                affine_bias(layer["inner"], params))
         prepared["ladj"] = sum(layer_ladj(l, spec, params) for l in layers)
-        prepared["base_scale"] = base_scale(params)
+        if spec.get("base") != "radial":
+            prepared["base_scale"] = base_scale(params)
     x = x.to(dtype)
     conv = _CONV[len(in_dims)]
     for i in range(len(layers) - 1, -1, -1):
@@ -514,7 +597,7 @@ def flow_log_prob_amortised(x: Tensor, spec: dict, params, dtype=torch.float32, 
             w, b = prepared[i]
             x = conv(x, w, b)
         elif k == "coupling":
-            x = coupling_backward(x, layer, params, _n_cond_layers(spec))
+            x = coupling_backward(x, layer, params, _n_cond_layers(spec), spec)
         else:
             x = scale_backward(x, params[layer["prefix"] + "scale"])
     return base_log_prob(x, spec, params) - prepared["ladj"], prepared
@@ -533,7 +616,7 @@ def random_params(spec: dict, seed: int = 0, min_abs_scale: float = 0.1) -> Dict
     g = torch.Generator().manual_seed(seed)
     in_dims = list(spec["in_dims"])
     d0, dtot = in_dims[0], math.prod(in_dims)
-    hidden = list(spec["hidden_dims"])
+    hidden = list(spec.get("hidden_dims", []))
     out: Dict[str, Tensor] = {}
 
     def uni(shape, bound):
@@ -563,6 +646,30 @@ def random_params(spec: dict, seed: int = 0, min_abs_scale: float = 0.1) -> Dict
                     w = torch.zeros(d0, d0)
                     w[torch.arange(d0), torch.randperm(d0, generator=g)] = 1.0
                     out[q + "w_0"] = w
+        elif layer["kind"] == "coupling" and spec.get("conditioner") == "convnet":
+            def lin(name, n_out, n_in):
+                bound = 1 / math.sqrt(n_in)
+                out[f"{p}{name}.weight"] = uni((n_out, n_in), bound)
+                out[f"{p}{name}.bias"] = uni((n_out,), bound)
+
+            ch = list(spec["c_hidden"])
+            lin("nn.0", ch[0], dtot)
+            idx = 1
+            for i, oc in enumerate(ch):
+                ic = ch[i - 1] if i > 0 else ch[0]
+                if spec.get("gating", True):
+                    lin(f"nn.{idx}.net1.1", oc, ic)
+                    lin(f"nn.{idx}.net1.3", 2 * oc, oc)
+                    if ic != oc:
+                        lin(f"nn.{idx}.proj", oc, ic)
+                else:
+                    lin(f"nn.{idx}.1", oc, ic)
+                idx += 1
+                if spec.get("normalize_layers", True):        # non-trivial affine part so gamma / beta are exercised
+                    out[f"{p}nn.{idx}.layernorm.weight"] = 1 + uni((oc,), 0.2)
+                    out[f"{p}nn.{idx}.layernorm.bias"] = uni((oc,), 0.2)
+                    idx += 1
+            lin(f"nn.{idx}", dtot, ch[-1])
         elif layer["kind"] == "coupling":
             dims = [dtot] + hidden + [2 * dtot if spec.get("coupling") == "affine" else dtot]
             for j in range(len(dims) - 1):
@@ -578,6 +685,18 @@ def random_params(spec: dict, seed: int = 0, min_abs_scale: float = 0.1) -> Dict
             s = torch.where(s.abs() < min_abs_scale, torch.where(s < 0, -min_abs_scale, min_abs_scale) *
                             torch.ones_like(s), s)
             out[p + "scale"] = s
+    if spec.get("base") == "radial":
+        q = "base_distribution.norm_distribution."
+        out["base_distribution.loc"] = uni(tuple(in_dims), 0.1)
+        if spec["norm"] == "lognormal":                       # experiments/mnist/mnist.yaml:86-92 (loc 6, scale .35 at d=784)
+            out[q + "loc"] = torch.full((1,), 0.5 * math.log(dtot))
+            out[q + "scale_unconstrained"] = inv_softplus(torch.full((1,), 0.35))
+        else:                                                 # experiments/synthetic/gaussian_mixture.yaml:84-91
+            K = int(spec.get("n_comp", 20))
+            out[q + "concentration_unconstrained"] = inv_softplus(0.2 + torch.rand(K, generator=g) * math.sqrt(dtot))
+            out[q + "rate_unconstrained"] = inv_softplus(0.5 + torch.rand(K, generator=g))
+            out[q + "mixture_logits"] = torch.rand(K, generator=g)
+        return out
     out["base_distribution.loc"] = torch.zeros(tuple(in_dims))
     out["base_distribution.scale_unconstrained"] = inv_softplus(torch.ones(tuple(in_dims)))
     return out

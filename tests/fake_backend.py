@@ -161,6 +161,66 @@ def affine_couple(st, x, direction, s_min, s_max, row_ladj=None, overflow_flag=N
         row_ladj += s.sum(-1)
 
 
+def _radial_norm_logpdf(r, norm_kind, params, K):
+    logr = r.log()
+    if norm_kind == real_ops.NORM_LOGNORMAL:
+        mu, sg = params[0], params[1]
+        return -((logr - mu) ** 2) / (2 * sg ** 2) - sg.log() - 0.9189385332046727 - logr
+    logits, a, b = params[:K], params[K:2 * K], params[2 * K:]
+    t = torch.log_softmax(logits, 0) + a * b.log() - torch.lgamma(a) + torch.xlogy(a - 1, r[:, None]) - b * r[:, None]
+    return torch.logsumexp(t, -1)
+
+
+def radial_logprob(z, loc, p_kind, norm_kind, norm_params, n_comp, dv_const, add_const, out):
+    CALLS.append(("radial_logprob", p_kind, norm_kind))
+    p, pl = z.resid_planes()
+    v = (p if pl is None else p + pl) - loc
+    r = v.abs().sum(-1) if p_kind == real_ops.LP_1 else v.pow(2).sum(-1).sqrt() if p_kind == real_ops.LP_2 \
+        else v.abs().max(-1).values
+    out.copy_(_radial_norm_logpdf(r, norm_kind, norm_params, n_comp) - (dv_const + (z.width - 1) * r.log()) + add_const)
+
+
+def radial_sample(out, loc, p_kind, norm_kind, norm_params, n_comp, seed, offset):
+    g = torch.Generator().manual_seed((seed + offset) % (2 ** 63))
+    rows, d = out.shape
+    if norm_kind == real_ops.NORM_LOGNORMAL:
+        r = torch.exp(norm_params[0] + norm_params[1] * torch.randn(rows, generator=g))
+    else:
+        K = n_comp
+        k = torch.multinomial(torch.softmax(norm_params[:K], 0), rows, replacement=True, generator=g)
+        r = torch.distributions.Gamma(norm_params[K:2 * K][k], norm_params[2 * K:][k]).sample()
+    if p_kind == real_ops.LP_2:
+        u = torch.randn(rows, d, generator=g)
+        u = u / u.norm(dim=-1, keepdim=True)
+    elif p_kind == real_ops.LP_1:
+        e = -torch.log(torch.rand(rows, d, generator=g))
+        u = e / e.sum(-1, keepdim=True) * (torch.randint(0, 2, (rows, d), generator=g) * 2 - 1)
+    else:
+        u = torch.rand(rows, d, generator=g) * 2 - 1
+        u[torch.arange(rows), torch.randint(0, d, (rows,), generator=g)] = 1.0
+    out.copy_(loc + r[:, None] * u)
+
+
+def gate_norm(o, n, *, xres=None, gated=False, gamma=None, beta=None, eps=1e-5, y_f32=None, act=None, act_relu=False,
+              raw=None, overflow_flag=None):
+    CALLS.append(("gate_norm", n, bool(gated), gamma is not None, bool(act_relu), raw is not None, y_f32 is not None))
+    v = o[:, :n]
+    if gated:
+        assert o.shape[1] == 2 * n and xres is not None and xres.shape[1] == n
+        v = xres + v * torch.sigmoid(o[:, n:2 * n])
+    else:
+        assert o.shape[1] == n
+    if gamma is not None:
+        v = torch.nn.functional.layer_norm(v, (n,), gamma, beta, eps)
+    v = v.clone()
+    if y_f32 is not None:
+        y_f32.copy_(v)
+    if raw is not None:
+        _store(raw, v, overflow_flag)
+    if act is not None:
+        _store(act, torch.relu(v) if act_relu else v, overflow_flag)
+
+
 def sub_rows(out, v):
     out -= v
 
@@ -255,7 +315,7 @@ def require_cuda(t, name="tensor", dtype=torch.float32):
 
 def install(monkeypatch):
     CALLS.clear()
-    for name in ["affine_couple", "sub_rows", "flow_small", "linear", "ingest", "base_logprob", "base_sample", "leaky_relu", "permute", "lu_assemble",
+    for name in ["radial_logprob", "radial_sample", "gate_norm", "affine_couple", "sub_rows", "flow_small", "linear", "ingest", "base_logprob", "base_sample", "leaky_relu", "permute", "lu_assemble",
                  "lu_logabsdet", "vec_logabs", "tri_inverse", "transpose", "scale_rows_cols", "split_tf32", "split_f16", "to_bf16",
                  "householder_right", "softplus", "matmul_f32", "matmul_f64", "require_cuda"]:
         monkeypatch.setattr(real_ops, name, globals()[name])

@@ -10,6 +10,9 @@ from oracle import flow_oracle as O
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 SMALL_CASES = ["c1_d2_laplace", "d2_refinit", "d6_hh_normal", "d5_noconj", "d32_h64", "d100_h50_hh"]
 LARGE_CASES = ["c2_d784", "c4_d3072_b2"]
+# networks.ConvNet (vector branch) conditioners, Lp-radial bases (LogNormal / GammaMM radius)
+EXT_CASES = ["d64_convnet", "d64_convnet_proj_radial2", "d40_convnet_plain_gmm1", "d64_convnet_noln", "d32_radial_inf",
+             "d784_radial1_lognormal"]
 
 
 def load_case(name):
@@ -27,12 +30,27 @@ def build_flow(spec, params, device="cuda", precision=None):
     """usflows_b200.USFlow with the reference state-dict loaded."""
     import usflows_b200 as U
     d = spec["in_dims"][0]
-    base_cls = U.Laplace if spec.get("base", "laplace") == "laplace" else U.Normal
+    if spec.get("base") == "radial":
+        if spec["norm"] == "lognormal":
+            nd = U.LogNormal(torch.ones(1), torch.ones(1))
+        else:
+            K = spec.get("n_comp", 20)
+            nd = U.GammaMM(torch.ones(K), torch.ones(K), torch.ones(K) / K)
+        base = U.RadialDistribution(torch.zeros(d), nd, p=float("inf") if spec["p"] == "inf" else float(spec["p"]))
+    else:
+        base = (U.Laplace if spec.get("base", "laplace") == "laplace" else U.Normal)(torch.zeros(d), torch.ones(d))
+    if spec.get("conditioner") == "convnet":
+        cond_cls = U.ConvNet
+        cond_args = dict(in_dims=[d], c_hidden=list(spec["c_hidden"]), gating=spec.get("gating", True),
+                         normalize_layers=spec.get("normalize_layers", True))
+    else:
+        cond_cls = U.DenseNN
+        cond_args = dict(input_dim=d, hidden_dims=list(spec["hidden_dims"]),
+                         param_dims=[d, d] if spec.get("coupling") == "affine" else [d])
     flow = U.USFlow(
-        base_distribution=base_cls(torch.zeros(d), torch.ones(d)), in_dims=list(spec["in_dims"]),
-        coupling_blocks=spec["coupling_blocks"], conditioner_cls=U.DenseNN,
-        conditioner_args=dict(input_dim=d, hidden_dims=list(spec["hidden_dims"]),
-                              param_dims=[d, d] if spec.get("coupling") == "affine" else [d]),
+        base_distribution=base, in_dims=list(spec["in_dims"]),
+        coupling_blocks=spec["coupling_blocks"], conditioner_cls=cond_cls,
+        conditioner_args=cond_args,
         coupling=spec.get("coupling", "additive"),
         prior_scale=1.0, lu_transform=spec.get("lu_transform", 1), householder=spec.get("householder", 1),
         affine_conjugation=spec.get("affine_conjugation", False), precision=precision)

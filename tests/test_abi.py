@@ -24,7 +24,18 @@ def test_header_symbols_are_exported_and_bound():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in the header but not exported"
         assert name in _lib.SIGNATURES, f"{name} has no ctypes signature in _lib.py"
-    assert lib.usf_abi_version() == 2
+    assert lib.usf_abi_version() == 3
+
+
+def test_planes_struct_layout_matches_header():
+    from usflows_b200 import _lib
+    with open(os.path.join(ROOT, "include", "usflows_b200.h")) as f:
+        text = f.read()
+    body = re.search(r"typedef struct usf_planes \{(.*?)\} usf_planes;", text, flags=re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    fields = re.findall(r"\b([A-Za-z_0-9]+);", body)
+    assert fields == [f[0] for f in _lib.Planes._fields_]
+    assert ctypes.sizeof(_lib.Planes) == 10 * 8
 
 
 def test_linear_args_layout_matches_header():

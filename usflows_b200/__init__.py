@@ -2,15 +2,16 @@
 
 Drop-in for the hot path of aai-institute/USFlows: `Flow` / `USFlow` `log_prob`, `sample`, `backward`,
 `_forward` over LU / Householder affine layers, additive masked couplings with MLP conditioners, scale,
-leaky-ReLU and permute layers, and Laplace / Normal base densities.  Python host code calls hand-written
+leaky-ReLU and permute layers, Laplace / Normal / Lp-radial base densities, DenseNN and (vector-branch) ConvNet
+conditioners.  Python host code calls hand-written
 CUDA (tcgen05 + TMEM + TMA contractions, fused elementwise kernels) through the C ABI in
 include/usflows_b200.h.  CUDA tensors only -- there is no CPU fallback.
 """
 from . import distributions, nn, transforms  # noqa: F401
-from .distributions import Independent, Laplace, Normal  # noqa: F401
+from .distributions import GammaMM, Independent, Laplace, LogNormal, Normal, RadialDistribution  # noqa: F401
 from .engine import get_precision, set_chunk_rows, set_precision  # noqa: F401
 from .flows import Flow, USFlow  # noqa: F401
-from .nn import DenseNN  # noqa: F401
+from .nn import ConvNet, DenseNN, GatedMLP, LayerNormVector  # noqa: F401
 from .optim import SophiaG  # noqa: F401
 from .transforms import MaskedAffineCoupling  # noqa: F401
 from .transforms import (AffineTransform, BaseTransform, BlockAffineTransform, HouseholderTransform,  # noqa: F401

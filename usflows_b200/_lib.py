@@ -37,8 +37,21 @@ class LinearArgs(C.Structure):
     ]
 
 
+class Planes(C.Structure):
+    """Mirror of `usf_planes` (include/usflows_b200.h)."""
+
+    _fields_ = [
+        ("f32", C.c_void_p), ("ld_f32", C.c_int64),
+        ("hi", C.c_void_p), ("lo", C.c_void_p), ("ld_split", C.c_int64),
+        ("bf16", C.c_void_p), ("ld_bf16", C.c_int64),
+        ("h16", C.c_void_p), ("l16", C.c_void_p), ("ld_16", C.c_int64),
+    ]
+
+
 ENGINE_SIMT, ENGINE_TC_3XTF32, ENGINE_TC_TF32, ENGINE_TC_BF16, ENGINE_TC_3XF16 = 0, 1, 2, 3, 4
 BASE_LAPLACE, BASE_NORMAL = 0, 1
+LP_INF, LP_1, LP_2 = 0, 1, 2
+NORM_LOGNORMAL, NORM_GAMMA_MIXTURE = 0, 1
 
 _P, _I64, _I32, _F, _U64 = C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_uint64
 
@@ -56,6 +69,10 @@ SIGNATURES = {
     "usf_base_sample": (C.c_int, [_I64, _I32, _P, _P, _I32, _U64, _U64, _P, _I64, _P, _P, _I64, _P, _I64, _P]),
     "usf_affine_couple": (C.c_int, [_P, _I64, _I64, _I32, _P, _I64, _P, _P, _I64, _P, _I64, _P, _P, _I64, _P, _F, _F, _F, _P, _P]),
     "usf_sub_rows": (C.c_int, [_P, _P, _I64, _P]),
+    "usf_radial_logprob": (C.c_int, [_P, _P, _I64, _I64, _I32, _P, _I32, _I32, _P, _I32, _F, _F, _P, _P]),
+    "usf_radial_sample": (C.c_int, [_I64, _I32, _P, _I32, _I32, _P, _I32, _U64, _U64, _P, _I64, _P]),
+    "usf_gate_norm": (C.c_int, [_P, _I64, _P, _I64, _I64, _I32, _I32, _P, _P, _F, _P, _I64, C.POINTER(Planes), _I32,
+                                C.POINTER(Planes), _P, _P]),
     "usf_leaky_relu": (C.c_int, [_P, _I64, _I64, _I32, _F, _P, _I64, _P, _P]),
     "usf_permute": (C.c_int, [_P, _I64, _I64, _I32, _P, _P, _I64, _P]),
     "usf_lu_assemble": (C.c_int, [_P, _P, _I32, _I64, _P, _P, _I64, _I32, _P]),
@@ -101,7 +118,7 @@ def load():
         fn = getattr(lib, name)  # AttributeError if the ABI and this table disagree
         fn.restype = res
         fn.argtypes = args
-    if lib.usf_abi_version() != 2:
+    if lib.usf_abi_version() != 3:
         raise RuntimeError("usflows_b200: ABI version mismatch between _lib.py and the shared library")
     _lib = lib
     return lib

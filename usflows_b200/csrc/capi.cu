@@ -1,10 +1,12 @@
 // C ABI of libusflows_b200.so (see include/usflows_b200.h for the contract of every entry point).
 #include "common.cuh"
+#include "conditioner.cuh"
 #include "elementwise.cuh"
 #include "flow_small.cuh"
 #include "gemm_simt.cuh"
 #include "gemm_tc2.cuh"
 #include "prep.cuh"
+#include "radial.cuh"
 
 namespace usf {
 
@@ -248,6 +250,73 @@ int usf_affine_couple(const float* st, int64_t ld_st, int64_t rows, int32_t h, f
   XPlanes p{x_f32, x_hi, x_lo, reinterpret_cast<__nv_bfloat16*>(x_bf16), reinterpret_cast<__half*>(x_h16),
             reinterpret_cast<__half*>(x_l16), ld_f32, ld_split, ld_bf16, ld_16, overflow_flag};
   affine_couple_kernel<<<ew_grid(rows * 32, 256), 256, 0, S(stream)>>>(st, ld_st, rows, h, p, direction, s_min, s_max, row_ladj);
+  USF_CUDA_OK(cudaGetLastError());
+  return USF_OK;
+}
+
+int usf_radial_logprob(const float* z, const float* z_lo, int64_t ldz, int64_t rows, int32_t d, const float* loc,
+                       int32_t p_kind, int32_t norm_kind, const float* norm_params, int32_t n_comp, float dv_const,
+                       float add_const, float* out, void* stream) {
+  USF_REQUIRE(z && loc && norm_params && out && d > 0 && rows >= 0, "bad input");
+  USF_REQUIRE(p_kind == USF_LP_INF || p_kind == USF_LP_1 || p_kind == USF_LP_2, "p must be 1, 2 or inf");
+  USF_REQUIRE(norm_kind == USF_NORM_LOGNORMAL || (norm_kind == USF_NORM_GAMMA_MIXTURE && n_comp >= 1 && n_comp <= RAD_MAX_COMP),
+              "unknown norm distribution / too many mixture components");
+  if (rows == 0) return USF_OK;
+  const bool vec = aligned16(z) && (!z_lo || aligned16(z_lo)) && ldz % 4 == 0 && d % 4 == 0 && aligned16(loc);
+  const int grid = ew_grid(rows * 32, RAD_THREADS);
+  if (vec)
+    radial_logprob_kernel<true><<<grid, RAD_THREADS, 0, S(stream)>>>(z, z_lo, ldz, rows, d, loc, p_kind, norm_kind, norm_params, n_comp, dv_const, add_const, out);
+  else
+    radial_logprob_kernel<false><<<grid, RAD_THREADS, 0, S(stream)>>>(z, z_lo, ldz, rows, d, loc, p_kind, norm_kind, norm_params, n_comp, dv_const, add_const, out);
+  USF_CUDA_OK(cudaGetLastError());
+  return USF_OK;
+}
+
+int usf_radial_sample(int64_t rows, int32_t d, const float* loc, int32_t p_kind, int32_t norm_kind,
+                      const float* norm_params, int32_t n_comp, uint64_t seed, uint64_t offset, float* out, int64_t ldo,
+                      void* stream) {
+  USF_REQUIRE(loc && norm_params && out && d > 0 && rows >= 0 && ldo >= d, "bad input");
+  USF_REQUIRE(p_kind == USF_LP_INF || p_kind == USF_LP_1 || p_kind == USF_LP_2, "p must be 1, 2 or inf");
+  USF_REQUIRE(norm_kind == USF_NORM_LOGNORMAL || (norm_kind == USF_NORM_GAMMA_MIXTURE && n_comp >= 1 && n_comp <= RAD_MAX_COMP),
+              "unknown norm distribution / too many mixture components");
+  if (rows == 0) return USF_OK;
+  radial_sample_kernel<<<ew_grid(rows * 32, RAD_THREADS), RAD_THREADS, 0, S(stream)>>>(rows, d, loc, p_kind, norm_kind, norm_params, n_comp, seed, offset, out, ldo);
+  USF_CUDA_OK(cudaGetLastError());
+  return USF_OK;
+}
+
+static OutPlanes to_out_planes(const usf_planes* p, int32_t* overflow_flag) {
+  OutPlanes o{nullptr, nullptr, nullptr, nullptr, 0, 0, 0};
+  if (!p) return o;
+  o.f32 = p->f32; o.ld_f32 = p->ld_f32;
+  o.hi = p->hi; o.lo = p->lo; o.ld_split = p->ld_split;
+  o.bf16 = reinterpret_cast<__nv_bfloat16*>(p->bf16); o.ld_bf16 = p->ld_bf16;
+  o.h16 = reinterpret_cast<__half*>(p->h16); o.l16 = reinterpret_cast<__half*>(p->l16); o.ld_16 = p->ld_16;
+  o.overflow_flag = overflow_flag;
+  return o;
+}
+
+int usf_gate_norm(const float* o, int64_t ldo, const float* xres, int64_t ldx, int64_t rows, int32_t n, int32_t gated,
+                  const float* gamma, const float* beta, float eps, float* y_f32, int64_t ldy, const usf_planes* act,
+                  int32_t act_relu, const usf_planes* raw, int32_t* overflow_flag, void* stream) {
+  USF_REQUIRE(o && rows >= 0 && n > 0 && n <= 6144, "bad input (n must be in 1..6144)");
+  USF_REQUIRE(!gated || xres, "a gated update needs the residual stream");
+  USF_REQUIRE((gamma == nullptr) == (beta == nullptr), "gamma and beta come as a pair");
+  USF_REQUIRE(y_f32 || act || raw, "usf_gate_norm needs at least one output");
+  if (act) USF_REQUIRE((act->hi == nullptr) == (act->lo == nullptr) && (act->h16 == nullptr) == (act->l16 == nullptr), "planes come as pairs");
+  if (raw) USF_REQUIRE((raw->hi == nullptr) == (raw->lo == nullptr) && (raw->h16 == nullptr) == (raw->l16 == nullptr), "planes come as pairs");
+  if (rows == 0) return USF_OK;
+  const OutPlanes a = to_out_planes(act, overflow_flag), rw = to_out_planes(raw, overflow_flag);
+  bool vec = n % 4 == 0 && aligned16(o) && ldo % 4 == 0 && (!gated || (aligned16(xres) && ldx % 4 == 0)) &&
+             (!gamma || (aligned16(gamma) && aligned16(beta))) && (!y_f32 || (aligned16(y_f32) && ldy % 4 == 0));
+  if (act) vec = vec && planes_vec_ok(a);
+  if (raw) vec = vec && planes_vec_ok(rw);
+  const size_t smem = (size_t)(GN_THREADS / 32) * n * sizeof(float);
+  const int grid = ew_grid(rows * 32, GN_THREADS);
+  auto kern = vec ? gate_norm_kernel<true> : gate_norm_kernel<false>;
+  if (smem > 48 * 1024) USF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<grid, GN_THREADS, smem, S(stream)>>>(o, ldo, xres, ldx, rows, n, gated ? 1 : 0, gamma, beta, eps, y_f32, ldy, a,
+                                             act ? 1 : 0, act_relu ? 1 : 0, rw, raw ? 1 : 0);
   USF_CUDA_OK(cudaGetLastError());
   return USF_OK;
 }

@@ -1,5 +1,7 @@
 """Base distributions as modules with constrained learnable parameters -- drop-in mirrors of the reference's
-`DistributionModule`, `Laplace`, `Normal`, `Independent` (src/usflows/distributions.py:117-238, 709-728).
+`DistributionModule`, `Laplace`, `Normal`, `Independent` (src/usflows/distributions.py:117-238, 709-728) and of the
+Lp-radial family `RadialDistribution` with `LogNormal` / `GammaMM` radius distributions (:181-197, 327-372, 478-549,
+674-707) that the reference's image configurations use as the base (experiments/mnist/mnist.yaml:79-92).
 
 Parameter names match the reference (`loc`, `scale_unconstrained`, scale = softplus(scale_unconstrained)).
 `log_prob` and `sample` run the fused base-density / Philox sampling kernels; no torch.distributions object is
@@ -7,6 +9,7 @@ rebuilt per call (the reference does that on every access, distributions.py:129-
 """
 from __future__ import annotations
 
+import math
 from typing import Iterable, Optional
 
 import torch
@@ -39,6 +42,15 @@ class DistributionModule(Module):
                 loc = self.loc.detach().reshape(-1).contiguous()
             self._prep_cache, self._prep_key = (loc, scale), key
         return self._prep_cache
+
+    def _density_into(self, z: "ops.Act", add_const: float, out: torch.Tensor) -> None:
+        """out[r] = log p(z[r, :]) + add_const on the current stream (the tail of `Flow.log_prob`)."""
+        loc, scale = self._prepared()
+        ops.base_logprob(z, loc, scale, self.base_kind, add_const, out)
+
+    def _sample_into(self, out: torch.Tensor, seed: int, offset: int) -> None:
+        loc, scale = self._prepared()
+        ops.base_sample(ops.Act(out.shape[0], out.shape[1], f32=out), loc, scale, self.base_kind, seed, offset)
 
     @property
     def event_shape(self) -> torch.Size:
@@ -109,3 +121,159 @@ class Independent(Module):
 
     def sample(self, sample_shape=None):
         return self._base_distribution.sample(sample_shape)
+
+
+# --------------------------------------------------------------------------------------------------
+# Lp-radial base distributions (distributions.py:327-549)
+# --------------------------------------------------------------------------------------------------
+class _RadiusDistribution(Module):
+    """Distribution of the radial component: a parameter container (reference parameter names) whose density is
+    evaluated inside the radial kernels (`usf_radial_logprob` / `usf_radial_sample`)."""
+
+    norm_kind: int = -1
+
+    def _params(self):
+        raise NotImplementedError
+
+    def _norm_params(self):
+        """(kind, n_components, device fp32 vector in the layout of USF_NORM_*), cached per weight version."""
+        ps = self._params()
+        key = tuple((p.data_ptr(), p._version) for p in ps)
+        if getattr(self, "_prep_key", None) != key:
+            for p in ps:
+                ops.require_cuda(p, "norm_distribution parameter")
+            with torch.no_grad():
+                self._prep_cache = self._pack()
+            self._prep_key = key
+        return self._prep_cache
+
+    def log_prob(self, r):
+        raise NotImplementedError("usflows_b200: radius distributions are evaluated as part of a RadialDistribution")
+
+    sample = log_prob
+
+
+def _softplus_vec(raw: torch.Tensor) -> torch.Tensor:
+    raw = raw.detach().reshape(-1).contiguous()
+    out = torch.empty_like(raw)
+    ops.softplus(raw, out)
+    return out
+
+
+class LogNormal(_RadiusDistribution):
+    """log R ~ Normal(loc, softplus(scale_unconstrained))  (distributions.py:181-197); one-element loc / scale."""
+
+    norm_kind = ops.NORM_LOGNORMAL
+
+    def __init__(self, loc: torch.Tensor, scale: torch.Tensor, device: str = "cpu"):
+        super().__init__()
+        if loc.numel() != 1 or scale.numel() != 1:
+            raise NotImplementedError("usflows_b200.LogNormal: one radius distribution per flow (1-element loc / scale)")
+        self.loc = Parameter(loc)
+        self.scale_unconstrained = Parameter(inv_softplus(scale))
+        self.to(device)
+
+    def _params(self):
+        return (self.loc, self.scale_unconstrained)
+
+    def _pack(self):
+        buf = torch.empty(2, dtype=torch.float32, device=self.loc.device)
+        buf[0:1].copy_(self.loc.detach().reshape(-1))
+        buf[1:2].copy_(_softplus_vec(self.scale_unconstrained))
+        return ops.NORM_LOGNORMAL, 1, buf
+
+
+class GammaMM(_RadiusDistribution):
+    """Mixture of K Gamma(concentration_k, rate_k) with weights softmax(mixture_logits)  (distributions.py:674-707)."""
+
+    norm_kind = ops.NORM_GAMMA_MIXTURE
+
+    def __init__(self, concentration: torch.Tensor, rate: torch.Tensor, mixture_weights: torch.Tensor, device: str = "cpu"):
+        super().__init__()
+        if concentration.dim() != 1 or rate.shape != concentration.shape or mixture_weights.shape != concentration.shape:
+            raise NotImplementedError("usflows_b200.GammaMM: 1-D [K] concentration / rate / mixture_weights")
+        self.concentration_unconstrained = Parameter(inv_softplus(concentration))
+        self.rate_unconstrained = Parameter(inv_softplus(rate))
+        self.mixture_logits = Parameter(mixture_weights)      # used as logits, as the reference does (:701)
+        self.to(device)
+
+    def _params(self):
+        return (self.mixture_logits, self.concentration_unconstrained, self.rate_unconstrained)
+
+    def _pack(self):
+        K = self.mixture_logits.numel()
+        buf = torch.empty(3 * K, dtype=torch.float32, device=self.mixture_logits.device)
+        buf[:K].copy_(self.mixture_logits.detach())
+        buf[K:2 * K].copy_(_softplus_vec(self.concentration_unconstrained))
+        buf[2 * K:].copy_(_softplus_vec(self.rate_unconstrained))
+        return ops.NORM_GAMMA_MIXTURE, K, buf
+
+
+class RadialDistribution(Module):
+    """Lp-radial distribution: x = loc + R u, R ~ norm_distribution, u uniform on the unit Lp sphere, p in {1, 2, inf}
+    (distributions.py:327-372).  log_prob(x) = log f_R(||x - loc||_p) - log dV_p^d/dr (:501-549)."""
+
+    def __init__(self, loc: torch.Tensor, norm_distribution: _RadiusDistribution, p: float, n_batch_dims: int = 0,
+                 device: str = "cpu"):
+        super().__init__()
+        if not isinstance(p, float):
+            raise ValueError("p must be a float.")
+        if p <= 0:
+            raise ValueError("p must be positive.")
+        if p not in (1.0, 2.0, math.inf):
+            raise ValueError(f"p={p} not implemented. Use p=1,2, or infinity")
+        if n_batch_dims != 0:
+            raise NotImplementedError("usflows_b200.RadialDistribution: n_batch_dims > 0 is not built")
+        self.norm_distribution = norm_distribution
+        self.event_shape = loc.shape[n_batch_dims:]
+        self.batch_shape = loc.shape[:n_batch_dims]
+        self.device = device
+        self.loc = Parameter(loc.to(device))
+        self.p = p
+        self.n_batch_dims = n_batch_dims
+        self.dim = int(math.prod(loc.shape[n_batch_dims:]))
+        self.shape = loc.shape
+        self._seed_offset = 0
+        self.to(device)
+
+    @property
+    def _p_kind(self) -> int:
+        return ops.LP_1 if self.p == 1.0 else ops.LP_2 if self.p == 2.0 else ops.LP_INF
+
+    def log_delta_volume_const(self) -> float:
+        """r-independent part of log dV_p^d/dr (distributions.py:514-549): the full value is this + (d - 1) log r."""
+        d = self.dim
+        if self.p == 1.0:        # (2r)^(d-1) 2 / (d-1)!   as written at :527-531
+            return math.log(2) * d - sum(math.log(i) for i in range(1, d))
+        if self.p == 2.0:        # d pi^(d/2) r^(d-1) / Gamma(d/2 + 1)
+            return math.log(d) + (d / 2) * math.log(math.pi) - math.lgamma(d / 2 + 1)
+        return math.log(d) + d * math.log(2)
+
+    def _prepared(self):
+        ops.require_cuda(self.loc, "base_distribution.loc")
+        kind, K, params = self.norm_distribution._norm_params()
+        key = (self.loc.data_ptr(), self.loc._version)
+        if getattr(self, "_loc_key", None) != key:
+            self._loc_flat, self._loc_key = self.loc.detach().reshape(-1).contiguous(), key
+        return self._loc_flat, kind, K, params
+
+    def _density_into(self, z: "ops.Act", add_const: float, out: torch.Tensor) -> None:
+        loc, kind, K, params = self._prepared()
+        ops.radial_logprob(z, loc, self._p_kind, kind, params, K, self.log_delta_volume_const(), add_const, out)
+
+    def _sample_into(self, out: torch.Tensor, seed: int, offset: int) -> None:
+        loc, kind, K, params = self._prepared()
+        ops.radial_sample(out, loc, self._p_kind, kind, params, K, seed, offset)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        return self.log_prob(x)
+
+    def log_prob(self, x: torch.Tensor) -> torch.Tensor:
+        from . import engine
+        return engine.base_log_prob(self, x)
+
+    def sample(self, sample_shape: Optional[Iterable[int]] = None) -> torch.Tensor:
+        from . import engine
+        if sample_shape is None:                     # the reference peels the sample dim again in this case (:480-497)
+            return engine.base_sample(self, [1]).squeeze(0)
+        return engine.base_sample(self, sample_shape)

@@ -164,8 +164,9 @@ def _compose_run(run: List[Prim]) -> Prim:
 @dataclass
 class Step:
     kind: str                                  # "mm" | "leaky" | "permute" | "vec" | "affine" (affine coupling update)
-    src: str = "x"                             # "x" (stream) or "h" (conditioner hidden)
-    dst: str = "x"
+                                               # | "gate" (ConvNet conditioner: gate + LayerNorm + re-encoding)
+    src: str = "x"                             # "x" (stream), "h" (conditioner hidden) or "hr" (its un-rectified copy)
+    dst: str = "x"                             # "x", "h", "st" (fp32 scratch) or "r" (fp32 residual of the conditioner)
     w: Optional[torch.Tensor] = None           # operand-format weight [N, K] (hi plane / fp32 / bf16)
     w_lo: Optional[torch.Tensor] = None
     N: int = 0
@@ -183,6 +184,10 @@ class Step:
     perm: Optional[torch.Tensor] = None
     final: bool = False                        # writes the program's fp32 result
     clip: Optional[tuple] = None               # "affine" steps: (log-scale min, max)
+    gated: bool = False                        # "gate" steps: x + val * sigmoid(gate) (else: pass the scratch through)
+    ln: Optional[tuple] = None                 #   (gamma, beta, eps) of the LayerNormVector that follows, or None
+    keep_f32: bool = False                     #   keep the result as the fp32 residual of the next gated block
+    want_raw: bool = False                     #   also write un-rectified operand planes (input of the next block's proj)
 
 
 def _operand(w64_or_32: torch.Tensor, mode: str, engine: int, overflow_flag: Optional[torch.Tensor] = None):
@@ -213,6 +218,43 @@ def _operand(w64_or_32: torch.Tensor, mode: str, engine: int, overflow_flag: Opt
     b = torch.zeros(rows, ld, dtype=torch.float32, device=w.device)[:, :cols]
     b.copy_(w)
     return b, None
+
+
+def convnet_steps(mode: str, desc: dict, first_w, first_b, last_w, last_b, wflag=None, *, in_seg=None, out_seg=None,
+                  resid: bool = False, sign: float = 1.0) -> List[Step]:
+    """Launch steps of a `nn.ConvNet` vector conditioner (networks.py:287-307): every Linear is one contraction, the
+    GatedMLP gate (networks.py:237-245), the LayerNormVector and the ReLU / re-encoding in front of the next Linear are
+    one `gate` step.  `desc` = dict(first, blocks, last) of detached (weight, bias) tensors; `first_*` / `last_*` are the
+    outer Linears as the caller wants them run (mask folded / compressed)."""
+    steps: List[Step] = []
+
+    def mm(w, b, **kw):
+        N, K = w.shape
+        eng = _engine_for(mode, N, K)
+        wo, wl = _operand(w, mode, eng, wflag)
+        steps.append(Step("mm", w=wo, w_lo=wl, N=N, K=K, engine=eng, bias=b.to(torch.float32).contiguous(), **kw))
+
+    blocks = desc["blocks"]
+
+    def gate(n, blk, nxt):
+        steps.append(Step("gate", src="st", dst="h", N=n, gated=bool(blk and blk["gated"]), ln=blk["ln"] if blk else None,
+                          relu=nxt is not None, keep_f32=nxt is not None and nxt["gated"] and nxt["proj"] is None,
+                          want_raw=nxt is not None and nxt["proj"] is not None))
+
+    mm(first_w, first_b, src="x", dst="st", in_seg=in_seg)
+    gate(first_w.shape[0], None, blocks[0] if blocks else None)
+    for i, blk in enumerate(blocks):
+        nxt = blocks[i + 1] if i + 1 < len(blocks) else None
+        if blk["gated"]:
+            mm(*blk["lin1"], src="h", dst="h", relu=True)              # relu(Linear(relu(x)))
+            if blk["proj"] is not None:
+                mm(*blk["proj"], src="hr", dst="r")                    # residual = proj(x)
+            mm(*blk["lin2"], src="h", dst="st")                        # [val | gate]
+        else:
+            mm(*blk["lin1"], src="h", dst="st")                        # Linear(relu(x))
+        gate(blk["lin1"][0].shape[0], blk, nxt)
+    mm(last_w, last_b, src="h", dst="x", resid=resid, sign=sign, out_seg=out_seg)
+    return steps
 
 
 class Program:
@@ -292,7 +334,7 @@ class Program:
                 dd = p.W.shape[0]
             else:
                 ws = p.prep["weights"]
-                if len(ws) < 2 or p.prep.get("affine"):
+                if len(ws) < 2 or p.prep.get("affine") or p.prep.get("net"):
                     return None
                 dd = ws[0].shape[1]
                 if ws[-1].shape[0] != dd:
@@ -408,6 +450,24 @@ class Program:
                 w, w_lo = _operand(W, mode, eng, self._flag_for_weights(W.device))
                 bias = None if c is None else c.to(torch.float32).contiguous()
                 steps.append(Step("mm", w=w, w_lo=w_lo, N=N, K=K, engine=eng, bias=bias))
+            elif p.kind == "coupling" and p.prep.get("net") == "convnet":
+                desc, mask = p.prep["desc"], p.prep["mask"]
+                first_w, first_b = desc["first"]
+                last_w, last_b = desc["last"]
+                in_seg = out_seg = None
+                if compress is not None:
+                    first = torch.equal(mask, compress["part"])
+                    idx_in = compress["idx1"] if first else compress["idx0"]
+                    idx_out = compress["idx0"] if first else compress["idx1"]
+                    h1, h0 = compress["h1"], compress["h0"]
+                    in_seg = (0, h1) if first else (h1, h0)
+                    out_seg = (h1, h0) if first else (0, h1)
+                    first_w, last_w, last_b = first_w[:, idx_in], last_w[idx_out], last_b[idx_out]
+                else:                                                   # fold the mask into the first / last Linear
+                    m = mask.reshape(-1).to(torch.float32)
+                    first_w, last_w, last_b = first_w * m[None, :], last_w * (1 - m)[:, None], last_b * (1 - m)
+                steps += convnet_steps(mode, desc, first_w, first_b, last_w, last_b, self._flag_for_weights(first_w.device),
+                                       in_seg=in_seg, out_seg=out_seg, resid=True, sign=p.sign)
             elif p.kind == "coupling":
                 ws, bs, mask = p.prep["weights"], p.prep["biases"], p.prep["mask"]
                 nl = len(ws)
@@ -550,7 +610,9 @@ class Program:
         flip = {"x": 0, "h": 0}
         cur: Optional[Act] = None               # stream
         hid: Optional[Act] = None               # conditioner hidden
-        st_buf: Optional[torch.Tensor] = None   # affine coupling: [log-scale | shift] of the updated features
+        hid_raw: Optional[Act] = None           # ConvNet conditioner: un-rectified planes of the hidden (input of a proj)
+        res_buf: Optional[torch.Tensor] = None  # ConvNet conditioner: fp32 residual stream of the gated blocks
+        st_buf: Optional[torch.Tensor] = None   # fp32 scratch: affine coupling [log-scale | shift], ConvNet [val | gate]
 
         def new_act(slot: str, width: int, planes: set) -> Act:
             flip[slot] ^= 1
@@ -587,9 +649,9 @@ class Program:
                         cur = b
                     a = seg_view(cur, st.in_seg)
                 else:
-                    a = hid
-                if st.dst == "st":                                    # affine coupling: log-scales and shifts, fp32
-                    out = Act(rows, st.N, f32=_workspace.planes(dev, "st", rows, st.N, "f32"))
+                    a = hid_raw if st.src == "hr" else hid
+                if st.dst in ("st", "r"):                             # fp32 scratch (affine coupling's [s | t], ConvNet)
+                    out = Act(rows, st.N, f32=_workspace.planes(dev, st.dst, rows, st.N, "f32"))
                     resid = None
                 elif st.dst == "h":
                     out = new_act("h", st.N, self._hidden_planes())
@@ -624,10 +686,28 @@ class Program:
                            resid_sign=st.sign, out=out, overflow_flag=flag)
                 if st.dst == "st":
                     st_buf = out.f32
+                elif st.dst == "r":
+                    res_buf = out.f32
                 elif st.dst == "h":
                     hid = out
                 else:
                     cur = full_out
+            elif st.kind == "gate":                                    # ConvNet conditioner glue between two contractions
+                act = new_act("h", st.N, self._hidden_planes())
+                raw = None
+                if st.want_raw:
+                    raw = Act(rows, st.N)
+                    for pl in self._hidden_planes():
+                        setattr(raw, pl, _workspace.planes(dev, "hr", rows, st.N, pl))
+                y = None
+                if st.keep_f32:                                        # gated: in place on the residual stream
+                    y = res_buf if st.gated else _workspace.planes(dev, "r", rows, st.N, "f32")
+                gamma, beta, eps = st.ln if st.ln is not None else (None, None, 0.0)
+                ops.gate_norm(st_buf, st.N, xres=res_buf if st.gated else None, gated=st.gated, gamma=gamma, beta=beta,
+                              eps=eps, y_f32=y, act=act, act_relu=st.relu, raw=raw, overflow_flag=flag)
+                hid, hid_raw = act, raw
+                if y is not None:
+                    res_buf = y
             elif st.kind == "affine":                                  # x_seg <- x_seg * exp(s) + t  (or the inverse), in place
                 if cur is src_f32:                                     # never update the caller's tensor
                     b = new_act("x", cur.width, self._stream_planes())
@@ -740,10 +820,10 @@ def base_log_prob(base, z: torch.Tensor, add_const: float = 0.0) -> torch.Tensor
     z2, batch_shape = _flatten_rows(z, len(base.event_shape))
     if z2.shape[1] != d:
         raise RuntimeError("usflows_b200: event shape mismatch in base log_prob")
-    loc, scale = base._prepared()
     z2 = z2.contiguous()
     out = torch.empty(z2.shape[0], dtype=torch.float32, device=z2.device)
-    ops.base_logprob(Act(z2.shape[0], d, f32=z2), loc, scale, base.base_kind, add_const, out)
+    if z2.shape[0]:                                             # empty batch: nothing to launch
+        base._density_into(Act(z2.shape[0], d, f32=z2), add_const, out)
     return out.reshape(batch_shape)
 
 
@@ -753,11 +833,10 @@ def base_sample(base, sample_shape=None) -> torch.Tensor:
     shape = [int(s) for s in sample_shape]
     rows = max(1, math.prod(shape))
     d = math.prod(base.event_shape)
-    loc, scale = base._prepared()
-    out = torch.empty(rows, d, dtype=torch.float32, device=loc.device)
+    out = torch.empty(rows, d, dtype=torch.float32, device=base._prepared()[0].device)
     seed = int(torch.initial_seed())
     base._seed_offset += 1
-    ops.base_sample(Act(rows, d, f32=out), loc, scale, base.base_kind, seed, base._seed_offset)
+    base._sample_into(out, seed, base._seed_offset)
     return out.reshape(*shape, *base.event_shape)
 
 
@@ -775,7 +854,8 @@ def profile_step(fn) -> dict:
     """Run `fn` once with CUDA events around every hot-path kernel launch; returns milliseconds summed per
     kernel class ("linear NxK", "ingest", "base_logprob") plus "_names" (launch order) and "_total"."""
     records = []
-    originals = {name: getattr(ops, name) for name in ("linear", "ingest", "base_logprob", "flow_small")}
+    originals = {name: getattr(ops, name) for name in ("linear", "ingest", "base_logprob", "flow_small", "gate_norm", "radial_logprob",
+                                                         "affine_couple")}
 
     def wrap(name, f):
         def inner(*a, **k):
@@ -805,3 +885,40 @@ def profile_step(fn) -> dict:
     out["_total"] = sum(v for k, v in out.items() if not k.startswith("_"))
     out["_names"] = [r[0] for r in records]
     return out
+
+
+def _convnet_desc(net) -> dict:
+    """(weight, bias) tensors of a `nn.ConvNet` in the structure `convnet_steps` reads."""
+    d = net._describe()
+    for prm in net.parameters():
+        ops.require_cuda(prm, "conditioner parameter")
+
+    def wb(lin):
+        return None if lin is None else (lin.weight.detach(), lin.bias.detach())
+
+    blocks = [dict(gated=b["gated"], lin1=wb(b["lin1"]), lin2=wb(b["lin2"]), proj=wb(b["proj"]),
+                   ln=None if b["ln"] is None else (b["ln"].weight.detach().contiguous(), b["ln"].bias.detach().contiguous(),
+                                                   float(b["ln"].eps))) for b in d["blocks"]]
+    return dict(first=wb(d["first"]), blocks=blocks, last=wb(d["last"]))
+
+
+def _convnet_weights(desc: dict) -> list:
+    ws = [desc["first"][0], desc["last"][0]]
+    for b in desc["blocks"]:
+        ws += [t[0] for t in (b["lin1"], b["lin2"], b["proj"]) if t is not None]
+    return ws
+
+
+def run_conditioner(net, x: torch.Tensor, mode: Optional[str] = None) -> torch.Tensor:
+    """Plain evaluation of a `nn.ConvNet` (no mask, no residual) through the same kernels a coupling uses."""
+    x2, batch_shape = _flatten_rows(x)
+    mode = mode or _default_precision
+    desc = _convnet_desc(net)
+    if min(min(w.shape) for w in _convnet_weights(desc)) < TC_MIN_DIM:
+        mode = "fp32_simt"
+    steps = convnet_steps(mode, desc, *desc["first"], *desc["last"])
+    steps[-1].final = True
+    prog = Program.from_steps(steps, mode)
+    with torch.no_grad():
+        y = prog.run(x2)
+    return y.reshape(*batch_shape, y.shape[-1]) if x.dim() != 2 else y

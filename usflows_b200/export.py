@@ -60,6 +60,8 @@ class ReferenceSemantics(torch.nn.Module):
                 self.kinds.append("affine")
                 for t in (W, Winv, b, ladj):
                     reg(t)
+            elif isinstance(layer, T.MaskedCoupling) and not hasattr(layer.conditioner, "layers"):
+                raise NotImplementedError("usflows_b200: export of couplings with a ConvNet conditioner is not built")
             elif isinstance(layer, T.MaskedAffineCoupling):
                 self.kinds.append("affine_coupling")
                 reg(layer.mask.reshape(-1))
@@ -90,6 +92,8 @@ class ReferenceSemantics(torch.nn.Module):
             self.n_tensors.append(count - start)
         base = flow.base_distribution
         base = base.base_dist if isinstance(base, Independent) else base
+        if not hasattr(base, "scale_unconstrained"):
+            raise NotImplementedError(f"usflows_b200: export with a {type(base).__name__} base is not built")
         self.base_kind = "laplace" if type(base).__name__ == "Laplace" else "normal"
         raw = base.scale_unconstrained.detach()
         loc = base.loc.detach().reshape(-1)

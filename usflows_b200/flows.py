@@ -125,7 +125,7 @@ class Flow(torch.nn.Module):
             raise NotImplementedError("usflows_b200: context-conditioned evaluation is not built")
         prog, ladj = self._program("backward")
         base = self._base_module()
-        loc, scale = base._prepared()
+        base._prepared()                  # parameter-side work happens here, outside any graph capture
         x2, batch_shape = engine._flatten_rows(x, len(self._event_shape()))
         d = x2.shape[1]
         rows = x2.shape[0]
@@ -137,7 +137,7 @@ class Flow(torch.nn.Module):
         out = torch.empty(rows, dtype=torch.float32, device=x2.device)
 
         def sink(z_chunk, r0, r1):
-            ops.base_logprob(ops.Act(r1 - r0, d, f32=z_chunk), loc, scale, base.base_kind, -ladj, out[r0:r1])
+            base._density_into(ops.Act(r1 - r0, d, f32=z_chunk), -ladj, out[r0:r1])
 
         with torch.no_grad():
             if prog.has_row_ladj:          # affine couplings: per-row log-determinants next to the model constant
@@ -161,7 +161,7 @@ class Flow(torch.nn.Module):
         ent = cache.get(key)
         if ent is None or ent["gen"] != engine._workspace.generation:
             base = self._base_module()
-            loc, scale = base._prepared()
+            base._prepared()                  # parameter-side work happens here, outside any graph capture
             xin = torch.empty(rows, d, dtype=torch.float32, device=dev)
             out = torch.empty(rows, dtype=torch.float32, device=dev)
             flag = torch.zeros(1, dtype=torch.int32, device=dev) if prog.mode == "fp32" else None
@@ -170,7 +170,7 @@ class Flow(torch.nn.Module):
 
             def body():
                 prog._run_chunk(xin, fin, flag)
-                ops.base_logprob(ops.Act(rows, width, f32=fin), loc, scale, base.base_kind, -ladj, out)
+                base._density_into(ops.Act(rows, width, f32=fin), -ladj, out)
             with torch.no_grad():
                 xin.copy_(x2)
                 body()                                        # eager pass: sizes every workspace buffer before capture
@@ -222,7 +222,7 @@ class Flow(torch.nn.Module):
         dev = next(self.parameters()).device
         prog, ladj = self._program("backward")
         base = self._base_module()
-        loc, scale = base._prepared()
+        base._prepared()                  # parameter-side work happens here, outside any graph capture
         x2 = x_host.reshape(-1, math.prod(self._event_shape()))
         rows, d = x2.shape
         if out_host is None:
@@ -245,8 +245,7 @@ class Flow(torch.nn.Module):
 
         def make_sink(r0):
             def sink(z_chunk, a, b):
-                ops.base_logprob(ops.Act(b - a, d, f32=z_chunk), loc, scale, base.base_kind, -ladj,
-                                 out_dev[r0 + a:r0 + b])
+                base._density_into(ops.Act(b - a, d, f32=z_chunk), -ladj, out_dev[r0 + a:r0 + b])
             return sink
 
         use_graphs = HOST_CUDA_GRAPHS and not prog.force_fallback and rows >= chunk and getattr(prog, "small", None) is None \

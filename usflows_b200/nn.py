@@ -32,3 +32,90 @@ class DenseNN(torch.nn.Module):
         if self.count_params == 1:
             return out
         return tuple(out.split(self.param_dims, dim=-1))       # pyro.nn.DenseNN returns one tensor per entry of param_dims
+
+
+# --------------------------------------------------------------------------------------------------
+# The reference's own MLP-style conditioner: `networks.ConvNet` with 1-D in_dims (networks.py:205-245, 248-307, 379-389)
+# --------------------------------------------------------------------------------------------------
+def _require_relu(nonlinearity) -> None:
+    if not isinstance(nonlinearity, torch.nn.ReLU):
+        raise NotImplementedError("usflows_b200.nn: only the ReLU nonlinearity is fused")
+
+
+class LayerNormVector(torch.nn.Module):
+    """Parameter container of a LayerNorm over the feature dim (networks.py:205-219; keys `layernorm.weight|bias`)."""
+
+    def __init__(self, features: int, eps: float = 1e-5):
+        super().__init__()
+        self.layernorm = torch.nn.LayerNorm(features, eps=eps)
+
+
+class GatedMLP(torch.nn.Module):
+    """x [-> proj] + val * sigmoid(gate), [val | gate] = Linear(out, 2 out)(relu(Linear(in, out)(relu(x))))
+    (networks.py:222-245).  Parameter container: keys `net1.1.*`, `net1.3.*`, `proj.*` as in the reference."""
+
+    def __init__(self, in_features: int, out_features: int, nonlinearity=torch.nn.ReLU()):
+        super().__init__()
+        _require_relu(nonlinearity)
+        self.net1 = torch.nn.Sequential(nonlinearity, torch.nn.Linear(in_features, out_features), nonlinearity,
+                                        torch.nn.Linear(out_features, 2 * out_features))
+        self.proj = torch.nn.Linear(in_features, out_features) if in_features != out_features else None
+
+
+class ConvNet(torch.nn.Module):
+    """`networks.ConvNet` for vector inputs (`in_dims=[d]`): Linear(d, h0) -> [GatedMLP | ReLU+Linear -> LayerNormVector]*
+    -> Linear(h_last, c_out), same constructor arguments and state-dict names (`nn.{i}. ...`) as the reference
+    (networks.py:262-307).  A parameter container: inside a `MaskedCoupling` its contractions run on the tcgen05 /
+    SIMT kernels and the gate / LayerNorm glue on `usf_gate_norm`; calling the module evaluates it through the same
+    kernels.  Spatial in_dims (the convolutional branch, networks.py:308-377) are not built."""
+
+    def __init__(self, in_dims, c_hidden, c_out: int = -1, nonlinearity=torch.nn.ReLU(), kernel_size: int = 3,
+                 stride: int = 1, dilation: int = 1, padding=None, normalize_layers: bool = True, gating: bool = True):
+        super().__init__()
+        _require_relu(nonlinearity)
+        try:
+            in_dims = list(in_dims)
+        except TypeError:
+            raise ValueError("in_dims must be an iterable like [C, H, W] or [C] for vector")
+        if len(in_dims) != 1:
+            raise NotImplementedError("usflows_b200.nn.ConvNet: only the vector branch (in_dims=[d]) is built")
+        c_in = int(in_dims[0])
+        c_out = c_out if c_out > 0 else c_in
+        assert len(c_hidden) > 0 and all(h > 0 for h in c_hidden), "c_hidden must be non-empty list of positive ints"
+        hidden = [int(h) for h in c_hidden]
+        layers = [torch.nn.Linear(c_in, hidden[0])]
+        for i, out_ch in enumerate(hidden):
+            in_ch = hidden[i - 1] if i > 0 else hidden[0]
+            if gating:
+                layers.append(GatedMLP(in_ch, out_ch, nonlinearity=nonlinearity))
+            else:
+                layers.append(torch.nn.Sequential(nonlinearity, torch.nn.Linear(in_ch, out_ch)))
+            if normalize_layers:
+                layers.append(LayerNormVector(out_ch))
+        layers.append(torch.nn.Linear(hidden[-1], c_out))
+        self.nn = torch.nn.Sequential(*layers)
+        self.is_vector = True
+        self._vector_in_features = c_in
+
+    def _describe(self) -> dict:
+        """Structure of the network as the engine's planner reads it: first / last Linear and the hidden blocks."""
+        mods = list(self.nn)
+        blocks, i = [], 1
+        while i < len(mods) - 1:
+            m = mods[i]
+            if isinstance(m, GatedMLP):
+                blk = dict(gated=True, lin1=m.net1[1], lin2=m.net1[3], proj=m.proj, ln=None)
+            else:
+                blk = dict(gated=False, lin1=m[1], lin2=None, proj=None, ln=None)
+            i += 1
+            if i < len(mods) - 1 and isinstance(mods[i], LayerNormVector):
+                blk["ln"] = mods[i].layernorm
+                i += 1
+            blocks.append(blk)
+        return dict(first=mods[0], blocks=blocks, last=mods[-1])
+
+    def forward(self, x: torch.Tensor, context=None) -> torch.Tensor:
+        from . import engine
+        if x.dim() == 3 and x.shape[-1] == 1:
+            x = x.reshape(x.shape[0], x.shape[1])
+        return engine.run_conditioner(self, x)

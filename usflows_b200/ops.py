@@ -13,7 +13,8 @@ import torch
 
 from . import _lib
 from ._lib import (BASE_LAPLACE, BASE_NORMAL, ENGINE_SIMT, ENGINE_TC_3XF16, ENGINE_TC_3XTF32,  # noqa: F401
-                   ENGINE_TC_BF16, ENGINE_TC_TF32, LinearArgs, check)
+                   ENGINE_TC_BF16, ENGINE_TC_TF32, LP_1, LP_2, LP_INF, NORM_GAMMA_MIXTURE, NORM_LOGNORMAL, LinearArgs,
+                   Planes, check)
 
 
 LAUNCHES = 0     # kernels launched through this module since the caller last reset it (bench.py `gpu_launches`)
@@ -162,6 +163,53 @@ def affine_couple(st: torch.Tensor, x: Act, direction: float, s_min: float, s_ma
         _ptr(x.bf16), _ld(x.bf16) if x.bf16 is not None else 0,
         _ptr(x.h16), _ptr(x.l16), _ld(x.h16) if x.h16 is not None else 0,
         _ptr(overflow_flag), float(direction), float(s_min), float(s_max), _ptr(row_ladj), _stream()))
+
+
+def radial_logprob(z: Act, loc, p_kind: int, norm_kind: int, norm_params: torch.Tensor, n_comp: int, dv_const: float,
+                   add_const: float, out: torch.Tensor) -> None:
+    """Lp-radial base density of the rows of z; see usf_radial_logprob."""
+    global LAUNCHES
+    LAUNCHES += 1
+    p, pl = z.resid_planes()
+    check(_lib.load().usf_radial_logprob(_ptr(p), _ptr(pl), _ld(p), z.rows, z.width, _ptr(loc), p_kind, norm_kind,
+                                         _ptr(norm_params), n_comp, float(dv_const), float(add_const), _ptr(out),
+                                         _stream()))
+
+
+def radial_sample(out: torch.Tensor, loc, p_kind: int, norm_kind: int, norm_params: torch.Tensor, n_comp: int,
+                  seed: int, offset: int) -> None:
+    rows, d = out.shape
+    check(_lib.load().usf_radial_sample(rows, d, _ptr(loc), p_kind, norm_kind, _ptr(norm_params), n_comp,
+                                        seed & (2**64 - 1), offset & (2**64 - 1), _ptr(out), _ld(out), _stream()))
+
+
+def _planes_struct(a: Optional[Act]):
+    if a is None:
+        return None
+    p = Planes()
+    if a.f32 is not None:
+        p.f32, p.ld_f32 = _ptr(a.f32), _ld(a.f32)
+    if a.hi is not None:
+        p.hi, p.lo, p.ld_split = _ptr(a.hi), _ptr(a.lo), _ld(a.hi)
+    if a.bf16 is not None:
+        p.bf16, p.ld_bf16 = _ptr(a.bf16), _ld(a.bf16)
+    if a.h16 is not None:
+        p.h16, p.l16, p.ld_16 = _ptr(a.h16), _ptr(a.l16), _ld(a.h16)
+    return p
+
+
+def gate_norm(o: torch.Tensor, n: int, *, xres: Optional[torch.Tensor] = None, gated: bool = False, gamma=None, beta=None,
+              eps: float = 1e-5, y_f32: Optional[torch.Tensor] = None, act: Optional[Act] = None, act_relu: bool = False,
+              raw: Optional[Act] = None, overflow_flag: Optional[torch.Tensor] = None) -> None:
+    """GatedMLP gate + LayerNormVector + re-encoding between two contractions of a ConvNet conditioner; see usf_gate_norm."""
+    global LAUNCHES
+    LAUNCHES += 1
+    pa, pr = _planes_struct(act), _planes_struct(raw)
+    check(_lib.load().usf_gate_norm(
+        _ptr(o), _ld(o), _ptr(xres), _ld(xres) if xres is not None else 0, o.shape[0], n, int(gated), _ptr(gamma),
+        _ptr(beta), float(eps), _ptr(y_f32), _ld(y_f32) if y_f32 is not None else 0,
+        C.byref(pa) if pa is not None else None, int(act_relu), C.byref(pr) if pr is not None else None,
+        _ptr(overflow_flag), _stream()))
 
 
 def sub_rows(out: torch.Tensor, v: torch.Tensor) -> None:

@@ -166,21 +166,66 @@ def _layer_backward(layer, y: torch.Tensor, inverse: bool = False, cache: Option
         return (y * torch.exp(s) + t if inverse else (y - t) * torch.exp(-s)), ladj
     if isinstance(layer, T.MaskedCoupling):
         m = layer.mask.reshape(-1).to(y.dtype)
-        h = y * m
-        lin = list(layer.conditioner.layers)
-        for j, l in enumerate(lin):
-            h = linear(h, l.weight, l.bias)
-            if j < len(lin) - 1:
-                h = torch.relu(h)
-        t = (1 - m) * h
+        t = (1 - m) * _conditioner(layer.conditioner, y * m)
         return (y + t if inverse else y - t), y.new_zeros(())      # transforms.py:277-306, 316-326
     raise NotImplementedError(f"usflows_b200: training of {type(layer).__name__} is not built")
 
 
+def _conditioner(net, h: torch.Tensor) -> torch.Tensor:
+    """Conditioner network as an autograd graph: contractions on the library's kernels, element-wise glue in torch."""
+    from .nn import ConvNet
+    if isinstance(net, ConvNet):                      # networks.py:222-245 (GatedMLP), 205-219 (LayerNormVector), 287-307
+        d = net._describe()
+        x = linear(h, d["first"].weight, d["first"].bias)
+        for blk in d["blocks"]:
+            a = linear(torch.relu(x), blk["lin1"].weight, blk["lin1"].bias)
+            if blk["gated"]:
+                o = linear(torch.relu(a), blk["lin2"].weight, blk["lin2"].bias)
+                val, gate = o.chunk(2, dim=1)
+                if blk["proj"] is not None:
+                    x = linear(x, blk["proj"].weight, blk["proj"].bias)
+                x = x + val * torch.sigmoid(gate)
+            else:
+                x = a
+            if blk["ln"] is not None:
+                ln = blk["ln"]
+                x = torch.nn.functional.layer_norm(x, ln.normalized_shape, ln.weight, ln.bias, ln.eps)
+        return linear(x, d["last"].weight, d["last"].bias)
+    lin = list(net.layers)
+    for j, l in enumerate(lin):
+        h = linear(h, l.weight, l.bias)
+        if j < len(lin) - 1:
+            h = torch.relu(h)
+    return h
+
+
+def _radial_log_prob(b, z: torch.Tensor) -> torch.Tensor:
+    """Differentiable Lp-radial log-density (distributions.py:501-549) with LogNormal / GammaMM radius distributions."""
+    from .distributions import GammaMM, LogNormal
+    v = z - b.loc.reshape(-1)
+    r = v.abs().sum(-1) if b.p == 1.0 else v.pow(2).sum(-1).sqrt() if b.p == 2.0 else v.abs().max(-1).values
+    logr = r.log()
+    nd = b.norm_distribution
+    sp = torch.nn.functional.softplus
+    if isinstance(nd, LogNormal):
+        mu, sg = nd.loc.reshape(()), sp(nd.scale_unconstrained).reshape(())
+        lp = -((logr - mu) ** 2) / (2 * sg ** 2) - sg.log() - 0.5 * math.log(2 * math.pi) - logr
+    elif isinstance(nd, GammaMM):
+        a, rate = sp(nd.concentration_unconstrained), sp(nd.rate_unconstrained)
+        t = torch.log_softmax(nd.mixture_logits, 0) + a * rate.log() - torch.lgamma(a) \
+            + torch.xlogy(a - 1, r[:, None]) - rate * r[:, None]
+        lp = torch.logsumexp(t, -1)
+    else:
+        raise NotImplementedError(f"usflows_b200: training with radius distribution {type(nd).__name__} is not built")
+    return lp - (b.log_delta_volume_const() + (b.dim - 1) * logr)
+
+
 def base_log_prob(base, z: torch.Tensor) -> torch.Tensor:
     """Differentiable Laplace / Normal log-density summed over the event (distributions.py:150-151, 199-238)."""
-    from .distributions import Independent
+    from .distributions import Independent, RadialDistribution
     b = base.base_dist if isinstance(base, Independent) else base
+    if isinstance(b, RadialDistribution):
+        return _radial_log_prob(b, z)
     loc = b.loc.reshape(-1)
     raw = b.scale_unconstrained
     scale = torch.nn.functional.softplus(raw.expand_as(b.loc) if raw.dim() == 0 else raw).reshape(-1)

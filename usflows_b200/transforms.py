@@ -470,6 +470,13 @@ class MaskedCoupling(BaseTransform):
     def _raw(self) -> dict:
         """Conditioner weights / biases and the flat mask, for the engine's planner (which either folds the mask
         into the first / last Linear or re-orders the features so both halves are contiguous)."""
+        from .nn import ConvNet
+        if isinstance(self.conditioner, ConvNet):          # the reference's own MLP-style conditioner (networks.py:287-307)
+            from . import engine
+            desc = engine._convnet_desc(self.conditioner)
+            dev = desc["first"][0].device
+            return dict(net="convnet", desc=desc, weights=engine._convnet_weights(desc),
+                        mask=self.mask.to(dev).reshape(-1).to(torch.float32))
         lin = list(self.conditioner.layers)
         for l in lin:
             ops.require_cuda(l.weight, "conditioner parameter")
