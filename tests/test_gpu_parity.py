@@ -129,6 +129,23 @@ def test_chunking_and_host_path_do_not_change_results():
     assert torch.equal(lp_ref.cpu(), lp_host)
 
 
+def test_host_path_growing_chunk_schedule_is_bit_identical():
+    """`log_prob_host` streams a growing chunk schedule (first copy small, later chunks larger), one captured CUDA graph
+    per (staging buffer, chunk size): same bits as the device-resident pass, also on replay and for other row counts."""
+    spec, params, arr = load_case("d100_h50_hh")
+    flow = build_flow(spec, params)
+    g = torch.Generator().manual_seed(10)
+    x = torch.rand(70000, 100, generator=g)
+    want = flow.log_prob(x.cuda()).cpu()
+    xp = x.pin_memory()
+    assert torch.equal(flow.log_prob_host(xp), want)
+    assert torch.equal(flow.log_prob_host(xp), want)                          # graph replay
+    assert len({k[3] for k in flow._host_graphs}) >= 2                        # more than one chunk size was captured
+    assert torch.equal(flow.log_prob_host(xp[:45001]), want[:45001])          # other schedule, cached + new graphs
+    assert torch.equal(flow.log_prob_host(xp, chunk_rows=8192), want)         # explicit uniform chunks
+    assert torch.equal(flow.log_prob_host(xp), want)
+
+
 @pytest.mark.parametrize("name", ["c2", "c5"])
 def test_full_size_properties(name):
     """BASELINE sizes: round trip x -> z -> x, log_prob == base(z) - ladj, determinism."""

@@ -23,6 +23,10 @@ from .transforms import (BaseTransform, BlockAffineTransform, HouseholderTransfo
 SMALL_BATCH_GRAPH_ROWS = 4096   # `log_prob` on at most this many rows replays one captured CUDA graph (0 = off)
 HOST_CUDA_GRAPHS = True       # `log_prob_host`: replay one captured CUDA graph per full-size chunk
 HOST_CHUNK_ROWS = 16384      # rows per H2D copy / kernel batch of `log_prob_host` (copy i+1 overlaps compute i)
+HOST_CHUNK_GROWTH = 2        # `log_prob_host` chunk i+1 holds this many times the rows of chunk i (1 = uniform chunks) ...
+HOST_CHUNK_MAX_UNITS = 2     # ... up to this many times the first chunk.  Measured on C2 (65 536 rows, B200): uniform 7.11 ms,
+                             # x2 capped at 2 units 6.68 ms, x2 capped at 4 / 8 units 7.0 ms (a copy twice as long as the
+                             # kernels it hides under stalls them: a row copies only 1.4x faster than it computes)
 
 
 class _plain_stream_order:
@@ -207,8 +211,10 @@ class Flow(torch.nn.Module):
         with _plain_stream_order(), torch.cuda.graph(graph):
             prog._run_chunk(buf, fin, flag)
         ent = dict(graph=graph, fin=fin, flag=flag, gen=engine._workspace.generation)
-        for k in [k for k in cache if k[1] == slot]:      # one live graph per staging buffer
-            del cache[k]
+        for k in [k for k in cache if k[1] == slot and (k[2] != key[2] or cache[k]["gen"] != ent["gen"])]:
+            del cache[k]                                  # graphs of a replaced staging buffer / of stale workspaces
+        while sum(1 for k in cache if k[1] == slot) >= 6:  # a few chunk sizes per staging buffer; drop the oldest
+            del cache[next(k for k in cache if k[1] == slot)]
         cache[key] = ent
         return ent
 
@@ -227,9 +233,22 @@ class Flow(torch.nn.Module):
         rows, d = x2.shape
         if out_host is None:
             out_host = torch.empty(rows, dtype=torch.float32, pin_memory=True)
-        chunk = min(chunk_rows or _wave_aligned_chunk_rows(prog, dev), max(rows, 1))
-        if getattr(self, "_host_bufs", None) is None or self._host_bufs[0].shape != (chunk, d) \
-                or self._host_bufs[0].device != dev:
+        # Chunk schedule.  The H2D copy of chunk i+1 hides under the kernels of chunk i (a row copies faster than it
+        # computes), so only the FIRST copy is exposed: start with the smallest wave-aligned chunk and let the later
+        # ones grow (fewer kernel boundaries, fuller tails).  An explicit `chunk_rows` gives uniform chunks.
+        unit = min(chunk_rows or _wave_aligned_chunk_rows(prog, dev), max(rows, 1))
+        sizes, left, cur = [], rows, unit
+        while left > 0:
+            take = min(cur, left)
+            if left - take < unit // 2:                  # do not leave a sliver for a last launch sequence
+                take = left
+            sizes.append(take)
+            left -= take
+            if not chunk_rows:
+                cur = min(cur * HOST_CHUNK_GROWTH, unit * HOST_CHUNK_MAX_UNITS)
+        chunk = max(sizes) if sizes else unit
+        if getattr(self, "_host_bufs", None) is None or self._host_bufs[0].shape[0] < chunk \
+                or self._host_bufs[0].shape[1] != d or self._host_bufs[0].device != dev:
             self._host_bufs = [torch.empty(chunk, d, dtype=torch.float32, device=dev) for _ in range(2)]
             self._host_out = torch.empty(0, dtype=torch.float32, device=dev)
             self._copy_stream = torch.cuda.Stream(device=dev)
@@ -239,7 +258,7 @@ class Flow(torch.nn.Module):
         main = torch.cuda.current_stream(dev)
         copied = [torch.cuda.Event(), torch.cuda.Event()]
         consumed = [torch.cuda.Event(), torch.cuda.Event()]
-        starts = list(range(0, rows, chunk))
+        starts = [sum(sizes[:i]) for i in range(len(sizes))]
         guarded = prog.mode == "fp32" and not prog.force_fallback       # fp16-split engine: range flag per chunk
         flags = torch.zeros(len(starts), dtype=torch.int32, device=dev) if guarded else None
 
@@ -248,18 +267,25 @@ class Flow(torch.nn.Module):
                 base._density_into(ops.Act(b - a, d, f32=z_chunk), -ladj, out_dev[r0 + a:r0 + b])
             return sink
 
-        use_graphs = HOST_CUDA_GRAPHS and not prog.force_fallback and rows >= chunk and getattr(prog, "small", None) is None \
+        use_graphs = HOST_CUDA_GRAPHS and not prog.force_fallback and rows >= unit and getattr(prog, "small", None) is None \
             and not prog.has_row_ladj
         row_ladj = torch.zeros(rows, dtype=torch.float32, device=dev) if prog.has_row_ladj else None
         with torch.no_grad():
-            graphs = [self._chunk_graph(prog, s, self._host_bufs[s], d) for s in range(2)] if use_graphs else None
-            if graphs is not None:
-                for g in graphs:
+            graphs = None
+            if use_graphs:                                # one graph per (staging buffer, chunk size), largest first so
+                graphs = {}                               # that the shared workspaces are sized once
+                for _ in range(2):                        # a workspace that grew while capturing invalidates earlier graphs
+                    for i in sorted(range(len(sizes)), key=lambda j: -sizes[j]):
+                        if sizes[i] >= unit // 2:
+                            graphs[(i & 1, sizes[i])] = self._chunk_graph(prog, i & 1, self._host_bufs[i & 1][:sizes[i]], d)
+                    if all(g["gen"] == engine._workspace.generation for g in graphs.values()):
+                        break
+                for g in graphs.values():
                     if g["flag"] is not None:
                         g["flag"].zero_()
             self._copy_stream.wait_stream(main)
             for i, r0 in enumerate(starts):
-                r1 = min(rows, r0 + chunk)
+                r1 = r0 + sizes[i]
                 buf = self._host_bufs[i & 1][: r1 - r0]
                 with torch.cuda.stream(self._copy_stream):
                     if i >= 2:
@@ -267,11 +293,12 @@ class Flow(torch.nn.Module):
                     buf.copy_(x2[r0:r1], non_blocking=True)
                     copied[i & 1].record(self._copy_stream)
                 main.wait_event(copied[i & 1])
-                if graphs is not None and r1 - r0 == chunk:
+                g = None if graphs is None else graphs.get((i & 1, sizes[i]))
+                if g is not None:
                     # one graph launch replaces the ~23 kernel launches of the chunk: the host-side launch cost
                     # (~40 us per launch through ctypes + tensor-map encoding) is what bounds small chunks otherwise
-                    graphs[i & 1]["graph"].replay()
-                    make_sink(r0)(graphs[i & 1]["fin"], 0, chunk)
+                    g["graph"].replay()
+                    make_sink(r0)(g["fin"], 0, sizes[i])
                 else:
                     prog.run(buf, chunk_rows=chunk, sink=make_sink(r0),
                              flag_out=flags[i:i + 1] if guarded else None,
@@ -279,11 +306,11 @@ class Flow(torch.nn.Module):
                 consumed[i & 1].record(main)
             if guarded:                                   # one sync; out-of-range chunks go through the tf32 split
                 redo = set(torch.nonzero(flags).reshape(-1).tolist())
-                if graphs is not None and any(int(g["flag"].item()) != 0 for g in graphs if g["flag"] is not None):
+                if graphs and any(int(g["flag"].item()) != 0 for g in graphs.values() if g["flag"] is not None):
                     redo = set(range(len(starts)))        # a graph's flag is not per chunk: recompute all of them
                 for i in sorted(redo):
                     r0 = starts[i]
-                    r1 = min(rows, r0 + chunk)
+                    r1 = r0 + sizes[i]
                     buf = self._host_bufs[0][: r1 - r0]
                     buf.copy_(x2[r0:r1])
                     if row_ladj is not None:
