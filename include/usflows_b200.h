@@ -214,12 +214,32 @@ int usf_radial_sample(int64_t rows, int32_t d, const float* loc, int32_t p_kind,
 
 /* Row-wise glue of networks.ConvNet's vector branch (networks.py:205-245, 287-307) between two usf_linear calls:
  *   v = gated ? xres[r,j] + o[r,j] * sigmoid(o[r,n+j]) : o[r,j]        (GatedMLP: o = [val | gate], xres = x or proj(x))
- *   v = gamma ? LayerNorm_row(v; gamma, beta, eps) : v                  (LayerNormVector, biased variance)
+ *   v = pre_relu ? max(v, 0) : v                                        (ConvNet2D: GatedConv -> ReLU -> LayerNormChannels)
+ *   v = gamma ? LayerNorm_row(v; gamma, beta, eps) : v                  (LayerNormVector / LayerNormChannels, biased variance)
  *   y_f32 <- v (may alias xres);  act <- act_relu ? max(v,0) : v;  raw <- v     (each of y_f32 / act / raw may be NULL)
  * n <= 6144.  overflow_flag: set when a value written to fp16 split planes leaves the fp16 range (may be NULL). */
 int usf_gate_norm(const float* o, int64_t ldo, const float* xres, int64_t ldx, int64_t rows, int32_t n, int32_t gated,
-                  const float* gamma, const float* beta, float eps, float* y_f32, int64_t ldy, const usf_planes* act,
+                  int32_t pre_relu, const float* gamma, const float* beta, float eps, float* y_f32, int64_t ldy, const usf_planes* act,
                   int32_t act_relu, const usf_planes* raw, int32_t* overflow_flag, void* stream);
+
+/* ---- image-shaped flows (in_dims = [C, H, W]): channels-last rows [N*H*W, C] inside the layer stack ----------------
+ * out[n, b, a] = f(in[n, a, b]) for in [N, A, B] (NCHW -> channels-last rows with A = C, B = H*W, and back with A = H*W,
+ * B = C); f multiplies (scale_mode 1) or divides (2) by `scale`, indexed in the order of the NCHW side (scale_on_input:
+ * the input is the NCHW side).  Replaces the layout the reference's conv calls imply and ScaleTransform.forward/backward
+ * over [C, H, W] (transforms.py:105-125). */
+int usf_layout_transpose(const float* in, int64_t n, int32_t a, int32_t b, const float* scale, int32_t scale_mode,
+                         int32_t scale_on_input, float* out, void* stream);
+/* Operand rows of a k x k convolution (stride 1, zero padding 'same', dilation) over channels-last rows:
+ *   out[r, (kh*k + kw)*C + c] = g(in[pixel (h + (kh - k/2) dil, w + (kw - k/2) dil) of r's image, c]), 0 outside;
+ *   g = optional multiply by mask[(h'*W + w')*C + c] (the coupling's x * mask, transforms.py:286), then optional ReLU.
+ * With usf_linear over K = k*k*C this replaces nn.Conv2d in ConvNet2D / GatedConv (networks.py:61-121, 405-510); the
+ * weight is the conv weight permuted to [C_out, kh, kw, C_in]. */
+int usf_im2col(const float* in, int64_t ld_in, int64_t n_images, int32_t h, int32_t w, int32_t c, int32_t k, int32_t dilation,
+               const float* mask, int32_t relu, const usf_planes* out, int32_t* overflow_flag, void* stream);
+/* x[r, c] += sign * g[(r mod hw)*c_dim + c] * t[r, c]: MaskedCoupling.forward/backward with a mask over [C, H, W]
+ * (transforms.py:284-290, 301-306; g = 1 - mask in channels-last order). */
+int usf_masked_add(float* x, int64_t ldx, const float* t, int64_t ldt, int64_t rows, int32_t c, int32_t hw, const float* g,
+                   float sign, void* stream);
 
 /* y = x >= 0 ? x : slope * x ; optional per-row count of negative inputs (for log|det J| = log(slope)*count).
  * Replaces LeakyReLUTransform.forward/backward (transforms.py:434-454). */

@@ -22,7 +22,9 @@ The model is described by
   spec  : dict(in_dims, coupling_blocks, hidden_dims, affine_conjugation, lu_transform, householder,
                base ("laplace"|"normal"|"radial" with p (1|2|"inf"), norm ("lognormal"|"gammamm"), n_comp),
                masktype ("checkerboard"|"channel"),
-               conditioner ("densenn" (default) | "convnet" with c_hidden, gating, normalize_layers))
+               conditioner ("densenn" (default) | "convnet" with c_hidden, gating, normalize_layers
+                            | "convnet2d" with c_hidden (int), num_layers, kernel_size, gating, normalize_layers: image-shaped
+                              in_dims = [C, H, W]))
   params: dict name -> torch CPU tensor, keyed exactly like the reference `USFlow.state_dict()`.
 """
 from __future__ import annotations
@@ -273,7 +275,38 @@ def convnet_vector(x: Tensor, prefix: str, params, spec: dict) -> Tensor:
     return F.linear(h, params[f"{prefix}nn.{idx}.weight"], params[f"{prefix}nn.{idx}.bias"])
 
 
+def convnet2d(x: Tensor, prefix: str, params, spec: dict) -> Tensor:
+    """networks.ConvNet2D.forward (networks.py:496-506) over the module list built at :441-494: Conv k x k -> per layer
+    [GatedConv (:103-121) | Conv k x k] -> nonlinearity -> [LayerNormChannels (:53-58)] -> Conv k x k, padding 'same'.
+    State-dict names `nn.{i}. ...` as nn.Sequential numbers them (the parameter-free ReLU modules take an index too)."""
+    L = spec["num_layers"]
+    gating, normalize = spec.get("gating", True), spec.get("normalize_layers", True)
+    h = F.conv2d(x, params[f"{prefix}nn.0.weight"], params[f"{prefix}nn.0.bias"], padding="same")
+    idx = 1
+    for _ in range(L):
+        q = f"{prefix}nn.{idx}."
+        if gating:
+            out = F.conv2d(F.relu(h), params[q + "net.1.weight"], params[q + "net.1.bias"], padding="same")
+            out = F.conv2d(F.relu(out), params[q + "net.3.weight"], params[q + "net.3.bias"], padding="same")
+            val, gate = out.chunk(2, dim=1)
+            h = h + val * torch.sigmoid(gate)
+        else:
+            h = F.conv2d(h, params[q + "weight"], params[q + "bias"], padding="same")
+        h = F.relu(h)
+        idx += 2
+        if normalize:
+            q = f"{prefix}nn.{idx}."
+            mean = h.mean(dim=1, keepdim=True)
+            var = h.var(dim=1, unbiased=False, keepdim=True)
+            h = (h - mean) / torch.sqrt(var + 1e-5)
+            h = h * params[q + "gamma"] + params[q + "beta"]
+            idx += 1
+    return F.conv2d(h, params[f"{prefix}nn.{idx}.weight"], params[f"{prefix}nn.{idx}.bias"], padding="same")
+
+
 def conditioner(x: Tensor, layer: dict, params, n_layers: int, spec=None) -> Tensor:
+    if spec is not None and spec.get("conditioner") == "convnet2d":
+        return convnet2d(x, layer["prefix"], params, spec)
     if spec is not None and spec.get("conditioner") == "convnet":
         return convnet_vector(x, layer["prefix"], params, spec)
     return dense_nn(x, layer["prefix"], params, n_layers)
@@ -646,6 +679,27 @@ def random_params(spec: dict, seed: int = 0, min_abs_scale: float = 0.1) -> Dict
                     w = torch.zeros(d0, d0)
                     w[torch.arange(d0), torch.randperm(d0, generator=g)] = 1.0
                     out[q + "w_0"] = w
+        elif layer["kind"] == "coupling" and spec.get("conditioner") == "convnet2d":
+            def conv(name, n_out, n_in, k):
+                bound = 1 / math.sqrt(n_in * k * k)
+                out[f"{p}{name}.weight"] = uni((n_out, n_in, k, k), bound)
+                out[f"{p}{name}.bias"] = uni((n_out,), bound)
+
+            ch, k = int(spec["c_hidden"]), int(spec.get("kernel_size", 3))
+            conv("nn.0", ch, d0, k)
+            idx = 1
+            for _ in range(spec["num_layers"]):
+                if spec.get("gating", True):
+                    conv(f"nn.{idx}.net.1", ch, ch, k)
+                    conv(f"nn.{idx}.net.3", 2 * ch, ch, 1)
+                else:
+                    conv(f"nn.{idx}", ch, ch, k)
+                idx += 2
+                if spec.get("normalize_layers", True):
+                    out[f"{p}nn.{idx}.gamma"] = 1 + uni((1, ch, 1, 1), 0.2)
+                    out[f"{p}nn.{idx}.beta"] = uni((1, ch, 1, 1), 0.2)
+                    idx += 1
+            conv(f"nn.{idx}", d0, ch, k)
         elif layer["kind"] == "coupling" and spec.get("conditioner") == "convnet":
             def lin(name, n_out, n_in):
                 bound = 1 / math.sqrt(n_in)

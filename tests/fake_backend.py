@@ -202,7 +202,7 @@ def radial_sample(out, loc, p_kind, norm_kind, norm_params, n_comp, seed, offset
 
 
 def gate_norm(o, n, *, xres=None, gated=False, gamma=None, beta=None, eps=1e-5, y_f32=None, act=None, act_relu=False,
-              raw=None, overflow_flag=None):
+              raw=None, overflow_flag=None, pre_relu=False):
     CALLS.append(("gate_norm", n, bool(gated), gamma is not None, bool(act_relu), raw is not None, y_f32 is not None))
     v = o[:, :n]
     if gated:
@@ -210,6 +210,8 @@ def gate_norm(o, n, *, xres=None, gated=False, gamma=None, beta=None, eps=1e-5, 
         v = xres + v * torch.sigmoid(o[:, n:2 * n])
     else:
         assert o.shape[1] == n
+    if pre_relu:
+        v = torch.relu(v)
     if gamma is not None:
         v = torch.nn.functional.layer_norm(v, (n,), gamma, beta, eps)
     v = v.clone()
@@ -219,6 +221,34 @@ def gate_norm(o, n, *, xres=None, gated=False, gamma=None, beta=None, eps=1e-5, 
         _store(raw, v, overflow_flag)
     if act is not None:
         _store(act, torch.relu(v) if act_relu else v, overflow_flag)
+
+
+def layout_transpose(x, n, a, b, out, scale=None, scale_mode=0, scale_on_input=True):
+    CALLS.append(("layout_transpose", a, b, scale_mode if scale is not None else 0))
+    v = x.reshape(n, a, b)
+    if scale is not None and scale_mode:
+        s = scale.reshape(a, b) if scale_on_input else scale.reshape(b, a).T
+        v = v * s if scale_mode == 1 else v / s
+    out.reshape(n, b, a).copy_(v.transpose(1, 2))
+
+
+def im2col(x, n_images, h, w, c, k, dilation, out, *, mask=None, relu=False, overflow_flag=None):
+    CALLS.append(("im2col", c, k, mask is not None, bool(relu)))
+    v = x.reshape(n_images, h, w, c)
+    if mask is not None:
+        v = v * mask.reshape(h, w, c)
+    if relu:
+        v = torch.relu(v)
+    pad = (k // 2) * dilation
+    vp = torch.nn.functional.pad(v, (0, 0, pad, pad, pad, pad))
+    cols = [vp[:, kh * dilation:kh * dilation + h, kw * dilation:kw * dilation + w, :] for kh in range(k) for kw in range(k)]
+    _store(out, torch.cat(cols, dim=-1).reshape(n_images * h * w, k * k * c), overflow_flag)
+
+
+def masked_add(x, t, hw, g, sign):
+    CALLS.append(("masked_add", sign))
+    rows, c = x.shape
+    x += sign * g.reshape(hw, c).repeat(rows // hw, 1) * t
 
 
 def sub_rows(out, v):
@@ -315,7 +345,7 @@ def require_cuda(t, name="tensor", dtype=torch.float32):
 
 def install(monkeypatch):
     CALLS.clear()
-    for name in ["radial_logprob", "radial_sample", "gate_norm", "affine_couple", "sub_rows", "flow_small", "linear", "ingest", "base_logprob", "base_sample", "leaky_relu", "permute", "lu_assemble",
+    for name in ["layout_transpose", "im2col", "masked_add", "radial_logprob", "radial_sample", "gate_norm", "affine_couple", "sub_rows", "flow_small", "linear", "ingest", "base_logprob", "base_sample", "leaky_relu", "permute", "lu_assemble",
                  "lu_logabsdet", "vec_logabs", "tri_inverse", "transpose", "scale_rows_cols", "split_tf32", "split_f16", "to_bf16",
                  "householder_right", "softplus", "matmul_f32", "matmul_f64", "require_cuda"]:
         monkeypatch.setattr(real_ops, name, globals()[name])

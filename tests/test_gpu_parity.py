@@ -15,7 +15,7 @@ import math
 import pytest
 import torch
 
-from helpers import EXT_CASES, LARGE_CASES, SMALL_CASES, build_flow, load_case, rel_err
+from helpers import EXT_CASES, IMG_CASES, LARGE_CASES, SMALL_CASES, build_flow, load_case, rel_err
 from oracle import flow_oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -30,7 +30,7 @@ TOL = {  # mode: (log_prob, latent/sample)
 
 
 @pytest.mark.parametrize("mode", list(TOL))
-@pytest.mark.parametrize("name", SMALL_CASES + LARGE_CASES + EXT_CASES)
+@pytest.mark.parametrize("name", SMALL_CASES + LARGE_CASES + EXT_CASES + IMG_CASES)
 def test_flow_matches_reference_golden(name, mode):
     spec, params, arr = load_case(name)
     flow = build_flow(spec, params, precision=mode)
@@ -43,7 +43,7 @@ def test_flow_matches_reference_golden(name, mode):
     assert flow.is_feasible()
 
 
-@pytest.mark.parametrize("name", SMALL_CASES + LARGE_CASES + EXT_CASES)
+@pytest.mark.parametrize("name", SMALL_CASES + LARGE_CASES + EXT_CASES + IMG_CASES)
 def test_fp32_mode_is_as_close_to_fp64_truth_as_the_reference(name):
     """The candidate may not be further from the fp64 evaluation than 3x the reference's own fp32 error
     (+ 2e-6 slack for log_prob, 1e-5 for latents)."""

@@ -4,11 +4,11 @@ import pytest
 import torch
 
 import fake_backend
-from helpers import EXT_CASES, LARGE_CASES, SMALL_CASES, build_flow, load_case, rel_err
+from helpers import EXT_CASES, IMG_CASES, LARGE_CASES, SMALL_CASES, build_flow, load_case, rel_err
 
 
 @pytest.mark.parametrize("mode", ["fp32_simt", "fp32", "fp32_tf32", "tf32"])
-@pytest.mark.parametrize("name", SMALL_CASES + ["c2_d784"] + EXT_CASES)
+@pytest.mark.parametrize("name", SMALL_CASES + ["c2_d784"] + EXT_CASES + IMG_CASES)
 def test_flow_program_matches_reference(fake_ops, name, mode):
     spec, params, arr = load_case(name)
     flow = build_flow(spec, params, device="cpu", precision=mode)

@@ -5,6 +5,7 @@
 #include "flow_small.cuh"
 #include "gemm_simt.cuh"
 #include "gemm_tc2.cuh"
+#include "image.cuh"
 #include "prep.cuh"
 #include "radial.cuh"
 
@@ -297,7 +298,7 @@ static OutPlanes to_out_planes(const usf_planes* p, int32_t* overflow_flag) {
 }
 
 int usf_gate_norm(const float* o, int64_t ldo, const float* xres, int64_t ldx, int64_t rows, int32_t n, int32_t gated,
-                  const float* gamma, const float* beta, float eps, float* y_f32, int64_t ldy, const usf_planes* act,
+                  int32_t pre_relu, const float* gamma, const float* beta, float eps, float* y_f32, int64_t ldy, const usf_planes* act,
                   int32_t act_relu, const usf_planes* raw, int32_t* overflow_flag, void* stream) {
   USF_REQUIRE(o && rows >= 0 && n > 0 && n <= 6144, "bad input (n must be in 1..6144)");
   USF_REQUIRE(!gated || xres, "a gated update needs the residual stream");
@@ -315,8 +316,46 @@ int usf_gate_norm(const float* o, int64_t ldo, const float* xres, int64_t ldx, i
   const int grid = ew_grid(rows * 32, GN_THREADS);
   auto kern = vec ? gate_norm_kernel<true> : gate_norm_kernel<false>;
   if (smem > 48 * 1024) USF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<grid, GN_THREADS, smem, S(stream)>>>(o, ldo, xres, ldx, rows, n, gated ? 1 : 0, gamma, beta, eps, y_f32, ldy, a,
+  kern<<<grid, GN_THREADS, smem, S(stream)>>>(o, ldo, xres, ldx, rows, n, gated ? 1 : 0, pre_relu ? 1 : 0, gamma, beta, eps, y_f32, ldy, a,
                                              act ? 1 : 0, act_relu ? 1 : 0, rw, raw ? 1 : 0);
+  USF_CUDA_OK(cudaGetLastError());
+  return USF_OK;
+}
+
+int usf_layout_transpose(const float* in, int64_t n, int32_t a, int32_t b, const float* scale, int32_t scale_mode,
+                         int32_t scale_on_input, float* out, void* stream) {
+  USF_REQUIRE(in && out && n >= 0 && a > 0 && b > 0, "bad input");
+  USF_REQUIRE(scale_mode >= 0 && scale_mode <= 2 && (scale_mode == 0 || scale), "scale_mode 0 (none), 1 (multiply) or 2 (divide)");
+  if (n == 0) return USF_OK;
+  const long long tiles = (long long)n * ((a + 31) / 32) * ((b + 31) / 32);
+  layout_kernel<<<ew_grid(tiles * 256, 256), 256, 0, S(stream)>>>(in, n, a, b, scale, scale_mode, scale_on_input, out);
+  USF_CUDA_OK(cudaGetLastError());
+  return USF_OK;
+}
+
+int usf_im2col(const float* in, int64_t ld_in, int64_t n_images, int32_t h, int32_t w, int32_t c, int32_t k, int32_t dilation,
+               const float* mask, int32_t relu, const usf_planes* out, int32_t* overflow_flag, void* stream) {
+  USF_REQUIRE(in && out && n_images >= 0 && h > 0 && w > 0 && c > 0 && ld_in >= c, "bad input");
+  USF_REQUIRE(k >= 1 && (k & 1) && dilation >= 1, "odd kernel size (padding 'same') and dilation >= 1");
+  USF_REQUIRE((out->hi == nullptr) == (out->lo == nullptr) && (out->h16 == nullptr) == (out->l16 == nullptr), "planes come as pairs");
+  USF_REQUIRE(out->f32 || out->hi || out->bf16 || out->h16, "usf_im2col needs an output plane");
+  if (n_images == 0) return USF_OK;
+  const OutPlanes o = to_out_planes(out, overflow_flag);
+  const long long rows = (long long)n_images * h * w;
+  const bool vec = c % 4 == 0 && aligned16(in) && ld_in % 4 == 0 && (!mask || aligned16(mask)) && planes_vec_ok(o);
+  if (vec)
+    im2col_kernel<true><<<ew_grid(rows * k * k * (c / 4), 256), 256, 0, S(stream)>>>(in, ld_in, rows, h, w, c, k, dilation, mask, relu ? 1 : 0, o);
+  else
+    im2col_kernel<false><<<ew_grid(rows * k * k * c, 256), 256, 0, S(stream)>>>(in, ld_in, rows, h, w, c, k, dilation, mask, relu ? 1 : 0, o);
+  USF_CUDA_OK(cudaGetLastError());
+  return USF_OK;
+}
+
+int usf_masked_add(float* x, int64_t ldx, const float* t, int64_t ldt, int64_t rows, int32_t c, int32_t hw, const float* g,
+                   float sign, void* stream) {
+  USF_REQUIRE(x && t && g && rows >= 0 && c > 0 && hw > 0 && ldx >= c && ldt >= c, "bad input");
+  if (rows == 0) return USF_OK;
+  masked_add_kernel<<<ew_grid(rows * c, 256), 256, 0, S(stream)>>>(x, ldx, t, ldt, rows, c, hw, g, sign);
   USF_CUDA_OK(cudaGetLastError());
   return USF_OK;
 }

@@ -4,6 +4,7 @@
 // ONE pass over the row (HBM-bound):
 //
 //   v = gated ? xres[r, j] + o[r, j] * sigmoid(o[r, n + j]) : o[r, j]          o = [val | gate] of the preceding Linear
+//   v = pre_relu ? max(v, 0) : v                                               (ConvNet2D: GatedConv -> ReLU -> LayerNorm)
 //   v = gamma ? (v - mean_r) / sqrt(var_r + eps) * gamma[j] + beta[j] : v        (biased variance, as nn.LayerNorm)
 //   y_f32 <- v;   act planes <- relu ? max(v, 0) : v;   raw planes <- v            (every output optional)
 //
@@ -21,7 +22,7 @@ constexpr int GN_THREADS = 256;
 template <bool VEC>
 __global__ void __launch_bounds__(GN_THREADS)
 gate_norm_kernel(const float* __restrict__ o, long long ldo, const float* xres, long long ldx, long long rows,
-                 int n, int gated, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                 int n, int gated, int pre_relu, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                  float* y_f32, long long ldy, OutPlanes act, int act_on, int act_relu, OutPlanes raw, int raw_on) {
   extern __shared__ __align__(16) float gn_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -42,6 +43,7 @@ gate_norm_kernel(const float* __restrict__ o, long long ldo, const float* xres, 
           v.z = x.z + v.z * (1.f / (1.f + expf(-g.z)));
           v.w = x.w + v.w * (1.f / (1.f + expf(-g.w)));
         }
+        if (pre_relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
         *reinterpret_cast<float4*>(row + j) = v;
         sum += (v.x + v.y) + (v.z + v.w);
       }
@@ -49,6 +51,7 @@ gate_norm_kernel(const float* __restrict__ o, long long ldo, const float* xres, 
       for (int j = lane; j < n; j += 32) {
         float v = orow[j];
         if (gated) v = xr[j] + v * (1.f / (1.f + expf(-orow[n + j])));
+        if (pre_relu) v = fmaxf(v, 0.f);
         row[j] = v;
         sum += v;
       }

@@ -43,9 +43,18 @@ class DistributionModule(Module):
             self._prep_cache, self._prep_key = (loc, scale), key
         return self._prep_cache
 
-    def _density_into(self, z: "ops.Act", add_const: float, out: torch.Tensor) -> None:
-        """out[r] = log p(z[r, :]) + add_const on the current stream (the tail of `Flow.log_prob`)."""
+    def _permuted(self, perm: torch.Tensor):
+        """Prepared parameters re-ordered for an event held in another element order (channels-last images)."""
         loc, scale = self._prepared()
+        key = (self._prep_key, perm.data_ptr())
+        if getattr(self, "_perm_key", None) != key:
+            self._perm_cache, self._perm_key = (loc[perm].contiguous(), scale[perm].contiguous()), key
+        return self._perm_cache
+
+    def _density_into(self, z: "ops.Act", add_const: float, out: torch.Tensor, perm: Optional[torch.Tensor] = None) -> None:
+        """out[r] = log p(z[r, :]) + add_const on the current stream (the tail of `Flow.log_prob`); with `perm`, column j
+        of z holds event element perm[j]."""
+        loc, scale = self._prepared() if perm is None else self._permuted(perm)
         ops.base_logprob(z, loc, scale, self.base_kind, add_const, out)
 
     def _sample_into(self, out: torch.Tensor, seed: int, offset: int) -> None:
@@ -257,8 +266,13 @@ class RadialDistribution(Module):
             self._loc_flat, self._loc_key = self.loc.detach().reshape(-1).contiguous(), key
         return self._loc_flat, kind, K, params
 
-    def _density_into(self, z: "ops.Act", add_const: float, out: torch.Tensor) -> None:
+    def _density_into(self, z: "ops.Act", add_const: float, out: torch.Tensor, perm: Optional[torch.Tensor] = None) -> None:
         loc, kind, K, params = self._prepared()
+        if perm is not None:                         # the Lp norm does not depend on the element order; loc does
+            key = (self._loc_key, perm.data_ptr())
+            if getattr(self, "_perm_key", None) != key:
+                self._perm_loc, self._perm_key = loc[perm].contiguous(), key
+            loc = self._perm_loc
         ops.radial_logprob(z, loc, self._p_kind, kind, params, K, self.log_delta_volume_const(), add_const, out)
 
     def _sample_into(self, out: torch.Tensor, seed: int, offset: int) -> None:

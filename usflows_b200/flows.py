@@ -13,7 +13,7 @@ from typing import Any, Dict, Iterable, List, Literal, Optional, Type
 
 import torch
 
-from . import engine, ops
+from . import engine, image_engine, ops
 from .distributions import DistributionModule, Independent
 from .transforms import MaskedAffineCoupling
 from .transforms import (BaseTransform, BlockAffineTransform, HouseholderTransform, InverseTransform, LUTransform,
@@ -133,6 +133,13 @@ class Flow(torch.nn.Module):
         x2, batch_shape = engine._flatten_rows(x, len(self._event_shape()))
         d = x2.shape[1]
         rows = x2.shape[0]
+        if isinstance(prog, image_engine.ImageProgram):      # image-shaped event: the latent arrives channels-last
+            out = torch.empty(rows, dtype=torch.float32, device=x2.device)
+            perm = self._channels_last_perm(x2.device)
+            with torch.no_grad():
+                prog.run(x2, sink=lambda z, r0, r1: base._density_into(ops.Act(r1 - r0, d, f32=z), -ladj, out[r0:r1],
+                                                                       perm=perm))
+            return out.reshape(batch_shape)
         if x2.is_cuda and 0 < rows <= SMALL_BATCH_GRAPH_ROWS and getattr(prog, "small", None) is None \
                 and not prog.force_fallback and not prog.has_row_ladj and not torch.cuda.is_current_stream_capturing():
             lp = self._log_prob_small_batch(prog, ladj, x2)
@@ -233,6 +240,12 @@ class Flow(torch.nn.Module):
         rows, d = x2.shape
         if out_host is None:
             out_host = torch.empty(rows, dtype=torch.float32, pin_memory=True)
+        if isinstance(prog, image_engine.ImageProgram):      # image-shaped events: plain chunked copies (no overlap yet)
+            step = max(1, chunk_rows or HOST_CHUNK_ROWS)
+            for r0 in range(0, rows, step):
+                lp = self.log_prob(x2[r0:r0 + step].to(dev, non_blocking=True).reshape(-1, *self._event_shape()))
+                out_host.reshape(-1)[r0:r0 + step].copy_(lp)
+            return out_host
         # Chunk schedule.  The H2D copy of chunk i+1 hides under the kernels of chunk i (a row copies faster than it
         # computes), so only the FIRST copy is exposed: start with the smallest wave-aligned chunk and let the later
         # ones grow (fewer kernel boundaries, fuller tails).  An explicit `chunk_rows` gives uniform chunks.
@@ -376,6 +389,13 @@ class Flow(torch.nn.Module):
     def _event_shape(self):
         return self.base_distribution.event_shape
 
+    def _channels_last_perm(self, device) -> torch.Tensor:
+        C, H, W = self._event_shape()
+        key = (C, H, W, str(device))
+        if getattr(self, "_cl_perm_key", None) != key:
+            self._cl_perm, self._cl_perm_key = image_engine.channels_last_index(C, H * W, device), key
+        return self._cl_perm
+
     def _weights_key(self):
         return tuple((p.data_ptr(), p._version) for p in self.parameters())
 
@@ -386,7 +406,13 @@ class Flow(torch.nn.Module):
         hit = self._programs.get(direction)
         if hit is None or hit[0] != key:
             with torch.no_grad():
-                prog = engine.Program(self.layers, direction, mode)
+                ev = tuple(self._event_shape())
+                if len(ev) == 3:
+                    prog = image_engine.ImageProgram(self.layers, direction, mode, ev)
+                elif len(ev) == 1:
+                    prog = engine.Program(self.layers, direction, mode)
+                else:
+                    raise NotImplementedError("usflows_b200: events of shape [d] and [C, H, W] are built")
             ladj, n_bad = engine.total_ladj(self.layers)
             hit = (key, prog, ladj, n_bad)
             self._programs[direction] = hit

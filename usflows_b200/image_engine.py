@@ -1,0 +1,273 @@
+"""Execution of flows over image-shaped events (`in_dims = [C, H, W]`): the reference's 1x1-convolution mode of
+`BlockAffineTransform` (transforms.py:904-962), `MaskedCoupling` with masks over [C, H, W] (flows.py:494-536) and
+`networks.ConvNet2D` conditioners (networks.py:405-510), `ScaleTransform` over [C, H, W] (transforms.py:105-125).
+
+Inside the layer stack a batch lives channels-last as a row matrix [N*H*W, C] (csrc/image.cuh):
+  BlockAffineTransform    -> usf_linear over N*H*W rows with the C x C matrix (the same contraction as the flat case)
+  k x k convolution       -> usf_im2col (zero padding 'same'; fused with the coupling's `x * mask` and the ReLU in front
+                             of the convolution) + usf_linear with K = k*k*C_in
+  1 x 1 convolution       -> usf_linear (bias / ReLU in the epilogue)
+  gate, ReLU, LayerNormChannels -> usf_gate_norm (one pass over the row)
+  x +- (1 - mask) * t     -> usf_masked_add
+  ScaleTransform and the NCHW <-> channels-last conversion -> usf_layout_transpose at the two ends of a pass
+  base density            -> the flat kernels on the same memory viewed as [N, H*W*C], loc / scale permuted once.
+The stream is kept in fp32; every contraction reads operand planes of the engine `engine._engine_for` picks for its
+shape (tcgen05 split engines for widths >= 32, the SIMT engine below that -- e.g. the 16-channel MNIST squeeze).
+"""
+from __future__ import annotations
+
+import math
+from typing import List, Optional
+
+import torch
+
+from . import engine, ops
+from .engine import Prim, _engine_for, _lower_layer, _operand, _workspace
+from .ops import Act, ENGINE_SIMT, ENGINE_TC_3XF16, ENGINE_TC_3XTF32, ENGINE_TC_BF16, ENGINE_TC_TF32
+
+_PLANES = {ENGINE_SIMT: ("f32",), ENGINE_TC_TF32: ("f32",), ENGINE_TC_3XF16: ("h16", "l16"), ENGINE_TC_3XTF32: ("hi", "lo"),
+           ENGINE_TC_BF16: ("bf16",)}
+IMAGE_CHUNK_ROWS = 1 << 19          # channels-last rows (N*H*W) per chunk: bounds the im2col workspace (rows x k*k*C)
+
+
+def _act(dev, name: str, rows: int, width: int, eng: int) -> Act:
+    a = Act(rows, width)
+    for pl in _PLANES[eng]:
+        setattr(a, pl, _workspace.planes(dev, name, rows, width, pl))
+    return a
+
+
+def _dense(dev, name: str, rows: int, width: int) -> torch.Tensor:
+    """Dense fp32 [rows, width] workspace (no row padding: the layout kernel writes whole images contiguously)."""
+    return _workspace.planes(dev, name, 1, rows * width, "f32").view(rows, width)
+
+
+class _Gemm:
+    """One contraction out = A . W^T + b with its weight in the operand format of the engine chosen for its shape."""
+
+    def __init__(self, mode: str, w: torch.Tensor, b: Optional[torch.Tensor], wflag):
+        self.N, self.K = w.shape
+        self.engine = _engine_for(mode, self.N, self.K)
+        self.w, self.w_lo = _operand(w, mode, self.engine, wflag if self.engine == ENGINE_TC_3XF16 else None)
+        self.bias = None if b is None else b.to(torch.float32).contiguous()
+
+    def __call__(self, a: Act, out: Act, relu: bool = False, flag=None) -> None:
+        ops.linear(self.engine, a, self.w, self.w_lo, self.N, self.K, bias=self.bias, relu=relu, out=out,
+                   overflow_flag=flag)
+
+
+def _conv_weight(conv) -> torch.Tensor:
+    """nn.Conv2d weight [C_out, C_in, kh, kw] -> contraction weight [C_out, (kh, kw, C_in)] (the usf_im2col column order)."""
+    w = conv.weight.detach()
+    return w.permute(0, 2, 3, 1).reshape(w.shape[0], -1).contiguous()
+
+
+class _ConvNet2DPlan:
+    """Launch plan of a ConvNet2D (networks.py:405-510) over channels-last rows."""
+
+    def __init__(self, net, mode: str, wflag, H: int, W: int):
+        d = net._describe()
+        for prm in net.parameters():
+            ops.require_cuda(prm, "conditioner parameter")
+        self.k, self.dil, self.H, self.W = d["k"], d["dilation"], H, W
+        self.c_in = d["first"].weight.shape[1]
+        self.first = _Gemm(mode, _conv_weight(d["first"]), d["first"].bias.detach(), wflag)
+        self.blocks = []
+        for b in d["blocks"]:
+            ln = None if b["ln"] is None else (b["ln"].gamma.detach().reshape(-1).contiguous(),
+                                               b["ln"].beta.detach().reshape(-1).contiguous(), float(b["ln"].eps))
+            g1 = _Gemm(mode, _conv_weight(b["conv1"]), b["conv1"].bias.detach(), wflag)
+            g2 = None if not b["gated"] else _Gemm(mode, _conv_weight(b["conv2"]), b["conv2"].bias.detach(), wflag)
+            self.blocks.append((b["gated"], g1, g2, ln))
+        self.last = _Gemm(mode, _conv_weight(d["last"]), d["last"].bias.detach(), wflag)
+        self.gemms = [self.first, self.last] + [g for b in self.blocks for g in b[1:3] if g is not None]
+
+    def run(self, x_rows: torch.Tensor, n_images: int, mask_cl: Optional[torch.Tensor], flag) -> torch.Tensor:
+        """t = net(x * mask) as fp32 rows [n*H*W, c_out] (a workspace buffer)."""
+        dev, rows = x_rows.device, x_rows.shape[0]
+        H, W, k, dil = self.H, self.W, self.k, self.dil
+
+        def conv(src: torch.Tensor, c: int, g: _Gemm, out: Act, *, mask=None, relu_in=False, relu_out=False):
+            if k == 1:
+                cols = _act(dev, "img_cols", rows, c, g.engine)
+                ops.im2col(src, n_images, H, W, c, 1, 1, cols, mask=mask, relu=relu_in, overflow_flag=flag)
+            else:
+                cols = _act(dev, "img_cols", rows, k * k * c, g.engine)
+                ops.im2col(src, n_images, H, W, c, k, dil, cols, mask=mask, relu=relu_in, overflow_flag=flag)
+            g(cols, out, relu=relu_out, flag=flag)
+
+        f32 = lambda name, width: Act(rows, width, f32=_workspace.planes(dev, name, rows, width, "f32"))   # noqa: E731
+        y = f32("img_y", self.first.N)                       # residual stream of the conditioner
+        conv(x_rows, self.c_in, self.first, y, mask=mask_cl)
+        for gated, g1, g2, ln in self.blocks:
+            gamma, beta, eps = ln if ln is not None else (None, None, 0.0)
+            if gated:                                        # GatedConv (networks.py:100-121) -> ReLU -> LayerNormChannels
+                hid = _act(dev, "img_h", rows, g1.N, g2.engine)
+                conv(y.f32, g1.K // (k * k), g1, hid, relu_in=True, relu_out=True)
+                vg = f32("img_st", g2.N)
+                g2(hid, vg, flag=flag)
+                ops.gate_norm(vg.f32, g1.K // (k * k), xres=y.f32, gated=True, pre_relu=True, gamma=gamma, beta=beta,
+                              eps=eps, y_f32=y.f32)
+            else:                                            # Conv k x k -> ReLU -> LayerNormChannels
+                o = f32("img_st", g1.N)
+                conv(y.f32, g1.K // (k * k), g1, o)
+                y2 = f32("img_y", g1.N)
+                ops.gate_norm(o.f32, g1.N, gated=False, pre_relu=True, gamma=gamma, beta=beta, eps=eps, y_f32=y2.f32)
+                y = y2
+        t = f32("img_t", self.last.N)
+        conv(y.f32, self.last.K // (k * k), self.last, t)
+        return t.f32
+
+
+class ImageProgram:
+    """Launch program of one direction of a layer stack over image-shaped events, for one mode and weight version."""
+
+    small = None
+    has_row_ladj = False
+
+    def __init__(self, layers, direction: str, mode: str, in_dims):
+        self.mode = mode or engine.get_precision()
+        self.layers, self.direction = list(layers), direction
+        self.C, self.H, self.W = (int(v) for v in in_dims)
+        self.HW = self.H * self.W
+        self.force_fallback = False
+        self._fallback_prog: Optional["ImageProgram"] = None
+        self._wflag: Optional[torch.Tensor] = None
+        seq = list(layers) if direction == "forward" else list(reversed(list(layers)))
+        prims: List[Prim] = []
+        for layer in seq:
+            _lower_layer(layer, direction, prims)
+        self.entry_scale = self.exit_scale = None            # (vector in NCHW order, mode 1 = multiply / 2 = divide)
+        if prims and prims[0].kind in ("mul", "div"):
+            self.entry_scale = (prims[0].v.contiguous(), 1 if prims[0].kind == "mul" else 2)
+            prims = prims[1:]
+        if prims and prims[-1].kind in ("mul", "div"):
+            self.exit_scale = (prims[-1].v.contiguous(), 1 if prims[-1].kind == "mul" else 2)
+            prims = prims[:-1]
+        self.ops = []
+        for p in prims:
+            if p.kind == "aff":                              # 1x1 convolution with the C x C matrix (transforms.py:904-962)
+                dev = p.W.device
+                self.ops.append(("aff", _Gemm(self.mode, p.W, p.c, self._flag(dev))))
+            elif p.kind == "coupling" and p.prep.get("net") == "convnet2d":
+                dev = p.prep["mask"].device
+                m = p.prep["mask"].reshape(self.C, self.HW).t().contiguous()          # channels-last order
+                plan = _ConvNet2DPlan(p.prep["module"], self.mode, self._flag(dev), self.H, self.W)
+                self.ops.append(("coupling", plan, m.reshape(-1), (1 - m).reshape(-1).contiguous(), p.sign))
+            else:
+                raise NotImplementedError(f"usflows_b200: no image-shaped kernel path for a '{p.kind}' step here "
+                                          "(ScaleTransform is supported at either end of the stack)")
+        if self._wflag is not None and int(self._wflag.item()) != 0:
+            self.force_fallback = True
+
+    def _flag(self, dev):
+        if self.mode != "fp32":
+            return None
+        if self._wflag is None:
+            self._wflag = torch.zeros(1, dtype=torch.int32, device=dev)
+        return self._wflag
+
+    def _fallback(self) -> "ImageProgram":
+        if self._fallback_prog is None:
+            self._fallback_prog = ImageProgram(self.layers, self.direction, "fp32_tf32", (self.C, self.H, self.W))
+        return self._fallback_prog
+
+    def out_width(self, d_in: int) -> int:
+        return d_in
+
+    # ----------------------------------------------------------------------------------------------
+    def _run_chunk(self, x: torch.Tensor, out: torch.Tensor, nchw_out: bool, flag) -> None:
+        """x [n, C*H*W] (NCHW, read-only) -> out [n, C*H*W]: NCHW when `nchw_out`, else channels-last ([n, H*W*C])."""
+        dev, n = x.device, x.shape[0]
+        rows, C, HW = n * self.HW, self.C, self.HW
+        direct = not nchw_out and self.exit_scale is None    # the channels-last stream itself is the result
+        bufs = [_dense(dev, "img_x0", rows, C), _dense(dev, "img_x1", rows, C)]
+        which, cur = 0, bufs[0]
+        es = self.entry_scale
+        ops.layout_transpose(x, n, C, HW, cur, scale=None if es is None else es[0], scale_mode=0 if es is None else es[1],
+                             scale_on_input=True)
+        for idx, op in enumerate(self.ops):
+            if op[0] == "aff":
+                g = op[1]
+                a = Act(rows, C, f32=cur)
+                if _PLANES[g.engine] != ("f32",):            # tensor-core engine: re-encode the fp32 stream into its planes
+                    a = _act(dev, "img_a", rows, C, g.engine)
+                    ops.ingest(cur, a, overflow_flag=flag)
+                if direct and idx == len(self.ops) - 1:
+                    dst = out.view(rows, C)
+                else:
+                    which ^= 1
+                    dst = bufs[which]
+                g(a, Act(rows, C, f32=dst), flag=flag)
+                cur = dst
+            else:
+                _, plan, mask_cl, inv_cl, sign = op
+                t = plan.run(cur, n, mask_cl, flag)
+                ops.masked_add(cur, t, HW, inv_cl, sign)
+        if direct:
+            if cur.data_ptr() != out.data_ptr():
+                out.view(rows, C).copy_(cur)
+            return
+        xs = self.exit_scale
+        if nchw_out:
+            ops.layout_transpose(cur, n, HW, C, out, scale=None if xs is None else xs[0], scale_mode=0 if xs is None else xs[1],
+                                 scale_on_input=False)
+        else:                                                # channels-last result with a trailing scale: two conversions
+            tmp = _dense(dev, "img_tmp", n, C * HW)
+            ops.layout_transpose(cur, n, HW, C, tmp, scale=xs[0], scale_mode=xs[1], scale_on_input=False)
+            ops.layout_transpose(tmp, n, C, HW, out)
+
+    def run(self, x: torch.Tensor, nchw_out: bool = True, sink=None, chunk_rows: Optional[int] = None) -> Optional[torch.Tensor]:
+        """x [N, C*H*W] -> [N, C*H*W] (NCHW order), or per chunk `sink(channels_last_chunk [n, H*W*C], r0, r1)`."""
+        ops.require_cuda(x, "input")
+        x = x.contiguous()
+        N, d = x.shape
+        if d != self.C * self.HW:
+            raise RuntimeError("usflows_b200: event shape mismatch")
+        out = None if sink is not None else torch.empty(N, d, dtype=torch.float32, device=x.device)
+        if N == 0:
+            return out
+        if self.force_fallback:
+            return self._fallback().run(x, nchw_out, sink, chunk_rows)
+        per = max(1, (chunk_rows or IMAGE_CHUNK_ROWS) // self.HW)
+        starts = list(range(0, N, per))
+        flags = torch.zeros(len(starts), dtype=torch.int32, device=x.device) if self.mode == "fp32" else None
+
+        def one(prog, i, r0, flag):
+            r1 = min(N, r0 + per)
+            if sink is not None:
+                fin = _dense(x.device, "img_final", r1 - r0, d)
+                prog._run_chunk(x[r0:r1], fin, False, flag)
+                sink(fin, r0, r1)
+            else:
+                prog._run_chunk(x[r0:r1], out[r0:r1], nchw_out, flag)
+
+        for i, r0 in enumerate(starts):
+            one(self, i, r0, None if flags is None else flags[i:i + 1])
+        if flags is not None:                                # chunks that left the fp16 range: tf32-split engine
+            for i in torch.nonzero(flags).reshape(-1).tolist():
+                one(self._fallback(), i, starts[i], None)
+        return out
+
+
+def channels_last_index(C: int, HW: int, device) -> torch.Tensor:
+    """perm with flat_channels_last[j] = flat_nchw[perm[j]]."""
+    return torch.arange(C * HW, device=device).reshape(C, HW).t().reshape(-1)
+
+
+def run_convnet2d(net, x: torch.Tensor, mode: Optional[str] = None) -> torch.Tensor:
+    """Plain evaluation of a `nn.ConvNet2D` on x [N, C, H, W] through the kernels a coupling uses."""
+    ops.require_cuda(x, "input")
+    N, C, H, W = x.shape
+    mode = mode or engine.get_precision()
+    with torch.no_grad():
+        plan = _ConvNet2DPlan(net, mode, None, H, W)
+        rows = N * H * W
+        cur = torch.empty(rows, C, dtype=torch.float32, device=x.device)
+        if N == 0:
+            return torch.empty(0, plan.last.N, H, W, dtype=torch.float32, device=x.device)
+        ops.layout_transpose(x.contiguous(), N, C, H * W, cur)
+        t = plan.run(cur, N, None, None)
+        out = torch.empty(N, t.shape[1], H, W, dtype=torch.float32, device=x.device)
+        ops.layout_transpose(t.contiguous() if t.stride(0) != t.shape[1] else t, N, H * W, t.shape[1], out)
+    return out

@@ -119,3 +119,86 @@ class ConvNet(torch.nn.Module):
         if x.dim() == 3 and x.shape[-1] == 1:
             x = x.reshape(x.shape[0], x.shape[1])
         return engine.run_conditioner(self, x)
+
+
+# --------------------------------------------------------------------------------------------------
+# Convolutional conditioner of the image-shaped flows: `networks.ConvNet2D` (networks.py:40-121, 405-510)
+# --------------------------------------------------------------------------------------------------
+class LayerNormChannels(torch.nn.Module):
+    """Parameter container of the per-pixel LayerNorm over channels (networks.py:40-58; keys `gamma`, `beta`)."""
+
+    def __init__(self, c_in: int, eps: float = 1e-5):
+        super().__init__()
+        self.gamma = torch.nn.Parameter(torch.ones(1, c_in, 1, 1))
+        self.beta = torch.nn.Parameter(torch.zeros(1, c_in, 1, 1))
+        self.eps = eps
+
+
+class GatedConv(torch.nn.Module):
+    """x + val * sigmoid(gate), [val | gate] = Conv1x1(c_hidden, 2 c_in)(relu(Conv k x k(c_in, c_hidden)(relu(x))))
+    (networks.py:61-121).  Parameter container: keys `net.1.*`, `net.3.*`."""
+
+    def __init__(self, c_in: int, c_hidden: int, kernel_size: int = 3, padding=1, stride: int = 1,
+                 nonlinearity=torch.nn.ReLU(), dilation: int = 1):
+        super().__init__()
+        _require_relu(nonlinearity)
+        assert stride == 1, "Stride > 1 cannot be used to skip connection."
+        self.net = torch.nn.Sequential(
+            nonlinearity, torch.nn.Conv2d(c_in, c_hidden, kernel_size=kernel_size, padding=padding, stride=stride,
+                                          dilation=dilation),
+            nonlinearity, torch.nn.Conv2d(c_hidden, 2 * c_in, kernel_size=1, padding=0))
+
+
+class ConvNet2D(torch.nn.Module):
+    """`networks.ConvNet2D`: Conv k x k (c_in, c_hidden) -> [GatedConv | Conv k x k, ReLU, LayerNormChannels] x num_layers
+    -> Conv k x k (c_hidden, c_out), same constructor arguments and state-dict names as the reference
+    (networks.py:405-494).  A parameter container: inside a `MaskedCoupling` over image-shaped `in_dims` every
+    convolution runs as a row gather (usf_im2col) + contraction over channels-last rows, the gate / ReLU / LayerNorm
+    glue on usf_gate_norm.  Shape-preserving convolutions only: stride 1 and padding 'same' (or kernel_size // 2 *
+    dilation), which is what the reference's couplings need (transforms.py:284-290 adds the output to x)."""
+
+    def __init__(self, c_in: int, c_hidden: int = 3, c_out: int = -1, num_layers: int = 3, nonlinearity=torch.nn.ReLU(),
+                 kernel_size: int = 3, stride: int = 1, dilation: int = 1, padding=0, normalize_layers: bool = True,
+                 gating: bool = True):
+        super().__init__()
+        _require_relu(nonlinearity)
+        if padding is None:
+            padding = kernel_size // 2
+        if stride != 1 or kernel_size % 2 != 1 or not (padding == "same" or padding == (kernel_size // 2) * dilation):
+            raise NotImplementedError("usflows_b200.nn.ConvNet2D: stride 1, odd kernel_size and padding 'same' only")
+        self.nonlinearity = nonlinearity
+        c_out = c_out if c_out > 0 else c_in
+        conv = lambda i, o: torch.nn.Conv2d(i, o, kernel_size=kernel_size, padding=padding, stride=stride,   # noqa: E731
+                                            dilation=dilation)
+        layers = [conv(c_in, c_hidden)]
+        for _ in range(num_layers):
+            if gating:
+                layers += [GatedConv(c_hidden, c_hidden, kernel_size=kernel_size, padding=padding, stride=stride,
+                                     dilation=dilation), nonlinearity]
+            else:
+                layers += [conv(c_hidden, c_hidden), nonlinearity]
+            if normalize_layers:
+                layers += [LayerNormChannels(c_hidden)]
+        layers += [conv(c_hidden, c_out)]
+        self.nn = torch.nn.Sequential(*layers)
+        self.kernel_size, self.dilation = kernel_size, dilation
+
+    def _describe(self) -> dict:
+        mods = [m for m in self.nn if not isinstance(m, torch.nn.ReLU)]
+        blocks, i = [], 1
+        while i < len(mods) - 1:
+            m = mods[i]
+            if isinstance(m, GatedConv):
+                blk = dict(gated=True, conv1=m.net[1], conv2=m.net[3], ln=None)
+            else:
+                blk = dict(gated=False, conv1=m, conv2=None, ln=None)
+            i += 1
+            if i < len(mods) - 1 and isinstance(mods[i], LayerNormChannels):
+                blk["ln"] = mods[i]
+                i += 1
+            blocks.append(blk)
+        return dict(first=mods[0], blocks=blocks, last=mods[-1], k=self.kernel_size, dilation=self.dilation)
+
+    def forward(self, x: torch.Tensor, context=None) -> torch.Tensor:
+        from . import image_engine
+        return image_engine.run_convnet2d(self, x)

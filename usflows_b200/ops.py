@@ -200,16 +200,42 @@ def _planes_struct(a: Optional[Act]):
 
 def gate_norm(o: torch.Tensor, n: int, *, xres: Optional[torch.Tensor] = None, gated: bool = False, gamma=None, beta=None,
               eps: float = 1e-5, y_f32: Optional[torch.Tensor] = None, act: Optional[Act] = None, act_relu: bool = False,
-              raw: Optional[Act] = None, overflow_flag: Optional[torch.Tensor] = None) -> None:
+              raw: Optional[Act] = None, overflow_flag: Optional[torch.Tensor] = None, pre_relu: bool = False) -> None:
     """GatedMLP gate + LayerNormVector + re-encoding between two contractions of a ConvNet conditioner; see usf_gate_norm."""
     global LAUNCHES
     LAUNCHES += 1
     pa, pr = _planes_struct(act), _planes_struct(raw)
     check(_lib.load().usf_gate_norm(
-        _ptr(o), _ld(o), _ptr(xres), _ld(xres) if xres is not None else 0, o.shape[0], n, int(gated), _ptr(gamma),
+        _ptr(o), _ld(o), _ptr(xres), _ld(xres) if xres is not None else 0, o.shape[0], n, int(gated), int(pre_relu), _ptr(gamma),
         _ptr(beta), float(eps), _ptr(y_f32), _ld(y_f32) if y_f32 is not None else 0,
         C.byref(pa) if pa is not None else None, int(act_relu), C.byref(pr) if pr is not None else None,
         _ptr(overflow_flag), _stream()))
+
+
+def layout_transpose(x: torch.Tensor, n: int, a: int, b: int, out: torch.Tensor, scale=None, scale_mode: int = 0,
+                     scale_on_input: bool = True) -> None:
+    """out[n, b, a] = in[n, a, b] (x| /) scale; see usf_layout_transpose."""
+    global LAUNCHES
+    LAUNCHES += 1
+    check(_lib.load().usf_layout_transpose(_ptr(x), n, a, b, _ptr(scale), scale_mode if scale is not None else 0,
+                                           int(scale_on_input), _ptr(out), _stream()))
+
+
+def im2col(x: torch.Tensor, n_images: int, h: int, w: int, c: int, k: int, dilation: int, out: Act, *, mask=None,
+           relu: bool = False, overflow_flag: Optional[torch.Tensor] = None) -> None:
+    """Operand rows [n*h*w, k*k*c] of a k x k 'same' convolution over channels-last rows; see usf_im2col."""
+    global LAUNCHES
+    LAUNCHES += 1
+    p = _planes_struct(out)
+    check(_lib.load().usf_im2col(_ptr(x), _ld(x), n_images, h, w, c, k, dilation, _ptr(mask), int(relu), C.byref(p),
+                                 _ptr(overflow_flag), _stream()))
+
+
+def masked_add(x: torch.Tensor, t: torch.Tensor, hw: int, g: torch.Tensor, sign: float) -> None:
+    global LAUNCHES
+    LAUNCHES += 1
+    check(_lib.load().usf_masked_add(_ptr(x), _ld(x), _ptr(t), _ld(t), x.shape[0], x.shape[1], hw, _ptr(g), float(sign),
+                                     _stream()))
 
 
 def sub_rows(out: torch.Tensor, v: torch.Tensor) -> None:

@@ -379,8 +379,9 @@ class SequentialAffineTransform(AffineTransform):
 
 
 class BlockAffineTransform(BaseTransform):
-    """Applies an AffineTransform over `in_dims[0]` (transforms.py:874-1029).  Flat inputs (1-D `in_dims`)
-    are supported; the 1x1-convolution modes of image-shaped `in_dims` are not built yet."""
+    """Applies an AffineTransform over `in_dims[0]` (transforms.py:874-1029): `F.linear` for flat `in_dims=[d]`, a 1x1
+    convolution over the channels for `in_dims=[C, H, W]` (run as the same contraction over channels-last rows, see
+    image_engine.py); log|det| = inner x prod(in_dims[1:])."""
 
     def __init__(self, in_dims: Iterable[int], block_transform: AffineTransform):
         super().__init__()
@@ -390,8 +391,8 @@ class BlockAffineTransform(BaseTransform):
         self.block_size = self.in_dims[0]
         self.input_rank = len(self.in_dims) - 1
         self.n_blocks = math.prod(self.in_dims[1:])
-        if self.input_rank != 0:
-            raise NotImplementedError("usflows_b200: only flat in_dims=[d] is implemented (SURVEY 8f, next-3)")
+        if self.input_rank not in (0, 2):
+            raise NotImplementedError("usflows_b200: in_dims=[d] (flat) and [C, H, W] (1x1 convolution) are built")
         self.block_transform = block_transform
 
     def log_abs_det_jacobian(self, x=None, y=None, context=None):
@@ -470,7 +471,13 @@ class MaskedCoupling(BaseTransform):
     def _raw(self) -> dict:
         """Conditioner weights / biases and the flat mask, for the engine's planner (which either folds the mask
         into the first / last Linear or re-orders the features so both halves are contiguous)."""
-        from .nn import ConvNet
+        from .nn import ConvNet, ConvNet2D
+        if isinstance(self.conditioner, ConvNet2D):        # image-shaped events (image_engine.py)
+            ws = [m.weight.detach().reshape(m.weight.shape[0], -1) for m in self.conditioner.modules()
+                  if isinstance(m, nn.Conv2d)]
+            dev = ws[0].device
+            return dict(net="convnet2d", module=self.conditioner, weights=ws,
+                        mask=self.mask.to(dev).reshape(-1).to(torch.float32))
         if isinstance(self.conditioner, ConvNet):          # the reference's own MLP-style conditioner (networks.py:287-307)
             from . import engine
             desc = engine._convnet_desc(self.conditioner)
