@@ -48,6 +48,14 @@ WORKLOADS = {
                            p=1, norm="lognormal"), rows=65536, cpu_rows=4096,
                  name="C2-shaped 784-D USFlow (B=4, ConvNet conditioner 2 gated blocks x 1024 + LayerNorm, L1-radial "
                       "LogNormal base) batch log_prob"),
+    # the reference's live MNIST configuration (experiments/mnist/mnist.yaml:44-92): 28x28 images squeezed to [16, 7, 7],
+    # 15 coupling blocks, ConvNet2D conditioner (32 hidden channels, 3 gated 3x3 blocks, LayerNormChannels), conjugated
+    # 1x1-convolution LU layers, L1-radial LogNormal base -- SURVEY 8f row 3
+    "mnist_img": dict(spec=dict(in_dims=[16, 7, 7], coupling_blocks=15, conditioner="convnet2d", c_hidden=32, num_layers=3,
+                                kernel_size=3, gating=True, normalize_layers=True, affine_conjugation=True, lu_transform=1,
+                                householder=0, base="radial", p=1, norm="lognormal"), rows=16384, cpu_rows=256,
+                      name="MNIST [16,7,7] USFlow (B=15, ConvNet2D 32 ch x 3 gated 3x3 blocks + LayerNorm, 1x1-conv LU, "
+                           "L1-radial LogNormal base) batch log_prob"),
     "c1": dict(spec=dict(in_dims=[2], coupling_blocks=10, hidden_dims=[32, 32], affine_conjugation=True,
                          lu_transform=1, householder=0, base="laplace"), rows=1 << 20, cpu_rows=65536,
                name="C1 2-D USFlow (B=10, MLP 32x32, Laplace) batch log_prob"),
@@ -57,6 +65,13 @@ WORKLOADS = {
 def algorithmic_flops_per_sample(spec) -> float:
     """(2B+1) * 2 d^2 + B * 2 (d H + H^2 + H d) with conjugation (B+1 affine layers without)."""
     d, B = spec["in_dims"][0], spec["coupling_blocks"]
+    if spec.get("conditioner") == "convnet2d":     # per pixel: 1x1-conv affine layers 2 C^2; k x k convolutions 2 k^2 Cin Cout
+        C, hw = spec["in_dims"][0], spec["in_dims"][1] * spec["in_dims"][2]
+        ch, kk, L = spec["c_hidden"], spec.get("kernel_size", 3) ** 2, spec["num_layers"]
+        per_block = 2 * kk * ch * ch + (2 * ch * 2 * ch if spec.get("gating", True) else 0)
+        cond = 2 * kk * C * ch + L * per_block + 2 * kk * ch * C
+        n_aff = 2 * B + 1 if spec.get("affine_conjugation") else B + 1
+        return hw * (n_aff * 2 * C * C + B * cond)
     if spec.get("conditioner") == "convnet":       # Linear(d,h0) + per block [h_in h + h 2h (+ proj)] + Linear(h_last, d)
         ch = list(spec["c_hidden"])
         mlp = 2 * d * ch[0] + 2 * ch[-1] * d
@@ -134,7 +149,7 @@ def cpu_reference_run(wl, steps: int, warmup: int, rows: int):
     spec = wl["spec"]
     params = O.random_params(spec, 0)
     g = torch.Generator().manual_seed(1)
-    x = torch.rand(rows, spec["in_dims"][0], generator=g)
+    x = torch.rand(rows, *spec["in_dims"], generator=g)
     with torch.no_grad():
         for _ in range(warmup):
             O.flow_log_prob(x, spec, params)
@@ -173,7 +188,9 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     wl = WORKLOADS[args.workload]
     spec = wl["spec"]
-    d = spec["in_dims"][0]
+    d = 1
+    for v in spec["in_dims"]:
+        d *= v
     flops_per_sample = algorithmic_flops_per_sample(spec)
 
     base_line = dict(metric="log_prob_samples_per_sec", unit="samples/s", n_gpus=args.gpus, steps=args.steps,
@@ -219,7 +236,7 @@ def main():
     params = O.random_params(spec, 0)
     flow = build_flow(spec, params, device=dev, precision=args.precision)
     g = torch.Generator().manual_seed(1 + rank)
-    x_host = torch.rand(rows, d, generator=g).pin_memory()
+    x_host = torch.rand(rows, *spec["in_dims"], generator=g).pin_memory()
     x = x_host.to(dev)
     out_host = torch.empty(rows, dtype=torch.float32).pin_memory()
 
@@ -279,6 +296,8 @@ def main():
     # kernel-class breakdown of one step (events around every launch; after the timed region)
     breakdown = engine.profile_step(lambda: flow.log_prob(x))
     gemm_ms = sum(v for k, v in breakdown.items() if k.startswith("linear"))
+    if len(spec["in_dims"]) > 1:            # image path: the gathers feed the contractions and belong to the convolution
+        gemm_ms += breakdown.get("im2col", 0.0)
     peaks, peak_kind = measured_peaks()
     # DRAM traffic of the dominant kernel per launch, from the committed ncu --set full capture (profiles/): the mean of
     # dram__bytes_read.sum + dram__bytes_write.sum over the captured launches of one step

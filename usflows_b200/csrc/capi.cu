@@ -312,9 +312,16 @@ int usf_gate_norm(const float* o, int64_t ldo, const float* xres, int64_t ldx, i
              (!gamma || (aligned16(gamma) && aligned16(beta))) && (!y_f32 || (aligned16(y_f32) && ldy % 4 == 0));
   if (act) vec = vec && planes_vec_ok(a);
   if (raw) vec = vec && planes_vec_ok(rw);
-  const size_t smem = (size_t)(GN_THREADS / 32) * n * sizeof(float);
-  const int grid = ew_grid(rows * 32, GN_THREADS);
-  auto kern = vec ? gate_norm_kernel<true> : gate_norm_kernel<false>;
+  // lanes per row: enough to cover the row once (4 elements per lane on the vector path), at least 4, at most a warp
+  const int per_lane = vec ? 4 : 1;
+  int G = 4;
+  while (G < 32 && G * per_lane < n) G *= 2;
+  const size_t smem = (size_t)(GN_THREADS / 32) * (32 / G) * n * sizeof(float);
+  const int grid = ew_grid(rows * G, GN_THREADS);
+  void (*kern)(const float*, long long, const float*, long long, long long, int, int, int, const float*, const float*, float,
+               float*, long long, OutPlanes, int, int, OutPlanes, int) = nullptr;
+  if (vec) kern = G == 4 ? gate_norm_kernel<true, 4> : G == 8 ? gate_norm_kernel<true, 8> : G == 16 ? gate_norm_kernel<true, 16> : gate_norm_kernel<true, 32>;
+  else kern = G == 4 ? gate_norm_kernel<false, 4> : G == 8 ? gate_norm_kernel<false, 8> : G == 16 ? gate_norm_kernel<false, 16> : gate_norm_kernel<false, 32>;
   if (smem > 48 * 1024) USF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<grid, GN_THREADS, smem, S(stream)>>>(o, ldo, xres, ldx, rows, n, gated ? 1 : 0, pre_relu ? 1 : 0, gamma, beta, eps, y_f32, ldy, a,
                                              act ? 1 : 0, act_relu ? 1 : 0, rw, raw ? 1 : 0);
@@ -343,10 +350,12 @@ int usf_im2col(const float* in, int64_t ld_in, int64_t n_images, int32_t h, int3
   const OutPlanes o = to_out_planes(out, overflow_flag);
   const long long rows = (long long)n_images * h * w;
   const bool vec = c % 4 == 0 && aligned16(in) && ld_in % 4 == 0 && (!mask || aligned16(mask)) && planes_vec_ok(o);
-  if (vec)
-    im2col_kernel<true><<<ew_grid(rows * k * k * (c / 4), 256), 256, 0, S(stream)>>>(in, ld_in, rows, h, w, c, k, dilation, mask, relu ? 1 : 0, o);
+  if (vec && c % 8 == 0)
+    im2col_kernel<8><<<ew_grid(rows * k * k * (c / 8), 256), 256, 0, S(stream)>>>(in, ld_in, rows, h, w, c, k, dilation, mask, relu ? 1 : 0, o);
+  else if (vec)
+    im2col_kernel<4><<<ew_grid(rows * k * k * (c / 4), 256), 256, 0, S(stream)>>>(in, ld_in, rows, h, w, c, k, dilation, mask, relu ? 1 : 0, o);
   else
-    im2col_kernel<false><<<ew_grid(rows * k * k * c, 256), 256, 0, S(stream)>>>(in, ld_in, rows, h, w, c, k, dilation, mask, relu ? 1 : 0, o);
+    im2col_kernel<1><<<ew_grid(rows * k * k * c, 256), 256, 0, S(stream)>>>(in, ld_in, rows, h, w, c, k, dilation, mask, relu ? 1 : 0, o);
   USF_CUDA_OK(cudaGetLastError());
   return USF_OK;
 }

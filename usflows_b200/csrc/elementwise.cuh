@@ -65,6 +65,37 @@ __device__ __forceinline__ void store_planes4(const OutPlanes& o, long long r, i
   }
 }
 
+// 8 consecutive values: 16-byte stores into the 16-bit planes (two 16-byte stores per 32-bit plane)
+__device__ __forceinline__ void store_planes8(const OutPlanes& o, long long r, int j, const float (&v)[8]) {
+  const float a[4] = {v[0], v[1], v[2], v[3]}, b[4] = {v[4], v[5], v[6], v[7]};
+  if (o.f32 || o.hi) {
+    OutPlanes w = o;
+    w.bf16 = nullptr;
+    w.h16 = nullptr;
+    store_planes4(w, r, j, a);
+    store_planes4(w, r, j + 4, b);
+  }
+  if (o.bf16) {
+    __align__(16) __nv_bfloat16 t[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t[i] = __float2bfloat16_rn(v[i]);
+    *reinterpret_cast<uint4*>(o.bf16 + r * o.ld_bf16 + j) = *reinterpret_cast<const uint4*>(t);
+  }
+  if (o.h16) {
+    __align__(16) __half h[8];
+    __align__(16) __half l[8];
+    bool bad = false;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      f16_split(v[i], h[i], l[i]);
+      bad = bad || !(fabsf(v[i]) <= F16_GUARD);
+    }
+    *reinterpret_cast<uint4*>(o.h16 + r * o.ld_16 + j) = *reinterpret_cast<const uint4*>(h);
+    *reinterpret_cast<uint4*>(o.l16 + r * o.ld_16 + j) = *reinterpret_cast<const uint4*>(l);
+    if (bad && o.overflow_flag) *o.overflow_flag = 1;
+  }
+}
+
 inline bool planes_vec_ok(const OutPlanes& o) {
   bool ok = true;
   if (o.h16) ok = ok && aligned16(o.h16) && aligned16(o.l16) && o.ld_16 % 8 == 0;

@@ -55,24 +55,42 @@ layout_kernel(const float* __restrict__ in, long long N, int A, int B, const flo
 // im2col for a k x k convolution, stride 1, zero padding 'same', dilation dil, over channels-last rows:
 //   out[r, (kh * k + kw) * C + c] = g(in[n, h + (kh - k/2) dil, w + (kw - k/2) dil, c])      (0 outside the image)
 //   g(v) = relu ? max(v, 0) : v, after v *= mask[(h' * W + w') * C + c] when mask != NULL (coupling mask, channels-last)
-// written in the operand planes of the consuming contraction.  VEC: C % 4 == 0 and aligned planes (4 channels / thread).
-template <bool VEC>
+// written in the operand planes of the consuming contraction.  VEC: channels per thread (1, or 4 / 8 with aligned planes
+// and C % VEC == 0; 8 channels give 16-byte stores into the 16-bit operand planes).
+template <int VEC>
 __global__ void __launch_bounds__(256)
 im2col_kernel(const float* __restrict__ in, long long ld_in, long long rows, int H, int W, int C, int k, int dil,
               const float* __restrict__ mask, int relu, OutPlanes o) {
   const int HW = H * W, kk = k * k, half = k >> 1;
-  const int cg = VEC ? (C >> 2) : C;
+  const int cg = C / VEC;
   const long long total = rows * kk * cg;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long r = i / (kk * cg);
     const int rem = (int)(i - r * (kk * cg));
-    const int tap = rem / cg, c = (rem - tap * cg) * (VEC ? 4 : 1);
+    const int tap = rem / cg, c = (rem - tap * cg) * VEC;
     const int p = (int)(r % HW), h = p / W, w = p - h * W;
     const int hh = h + (tap / k - half) * dil, ww = w + (tap % k - half) * dil;
     const bool inside = hh >= 0 && hh < H && ww >= 0 && ww < W;
     const long long rs = r + (long long)(hh - h) * W + (ww - w);
     const int col = tap * C + c;
-    if (VEC) {
+    if (VEC == 8) {
+      float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (inside) {
+        const float4 t0 = *reinterpret_cast<const float4*>(in + rs * ld_in + c);
+        const float4 t1 = *reinterpret_cast<const float4*>(in + rs * ld_in + c + 4);
+        v[0] = t0.x; v[1] = t0.y; v[2] = t0.z; v[3] = t0.w; v[4] = t1.x; v[5] = t1.y; v[6] = t1.z; v[7] = t1.w;
+        if (mask) {
+          const float4 m0 = __ldg(reinterpret_cast<const float4*>(mask + (long long)(hh * W + ww) * C + c));
+          const float4 m1 = __ldg(reinterpret_cast<const float4*>(mask + (long long)(hh * W + ww) * C + c + 4));
+          v[0] *= m0.x; v[1] *= m0.y; v[2] *= m0.z; v[3] *= m0.w; v[4] *= m1.x; v[5] *= m1.y; v[6] *= m1.z; v[7] *= m1.w;
+        }
+        if (relu) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) v[q] = fmaxf(v[q], 0.f);
+        }
+      }
+      store_planes8(o, r, col, v);
+    } else if (VEC == 4) {
       float v[4] = {0.f, 0.f, 0.f, 0.f};
       if (inside) {
         const float4 t = *reinterpret_cast<const float4*>(in + rs * ld_in + c);

@@ -45,7 +45,15 @@ def _dense(dev, name: str, rows: int, width: int) -> torch.Tensor:
 class _Gemm:
     """One contraction out = A . W^T + b with its weight in the operand format of the engine chosen for its shape."""
 
-    def __init__(self, mode: str, w: torch.Tensor, b: Optional[torch.Tensor], wflag):
+    def __init__(self, mode: str, w: torch.Tensor, b: Optional[torch.Tensor], wflag, pad_n: bool = False):
+        self.n_true = w.shape[0]
+        if pad_n and mode != "fp32_simt" and w.shape[0] < engine.TC_MIN_DIM <= w.shape[1]:
+            # a narrow output (the c_in channels of the conditioner's last convolution) would fall to the SIMT engine:
+            # zero rows up to the tensor-core minimum width cost nothing there (the caller reads the first n_true columns)
+            extra = engine.TC_MIN_DIM - w.shape[0]
+            w = torch.cat([w, torch.zeros(extra, w.shape[1], dtype=w.dtype, device=w.device)])
+            if b is not None:
+                b = torch.cat([b, torch.zeros(extra, dtype=b.dtype, device=b.device)])
         self.N, self.K = w.shape
         self.engine = _engine_for(mode, self.N, self.K)
         self.w, self.w_lo = _operand(w, mode, self.engine, wflag if self.engine == ENGINE_TC_3XF16 else None)
@@ -79,7 +87,7 @@ class _ConvNet2DPlan:
             g1 = _Gemm(mode, _conv_weight(b["conv1"]), b["conv1"].bias.detach(), wflag)
             g2 = None if not b["gated"] else _Gemm(mode, _conv_weight(b["conv2"]), b["conv2"].bias.detach(), wflag)
             self.blocks.append((b["gated"], g1, g2, ln))
-        self.last = _Gemm(mode, _conv_weight(d["last"]), d["last"].bias.detach(), wflag)
+        self.last = _Gemm(mode, _conv_weight(d["last"]), d["last"].bias.detach(), wflag, pad_n=True)
         self.gemms = [self.first, self.last] + [g for b in self.blocks for g in b[1:3] if g is not None]
 
     def run(self, x_rows: torch.Tensor, n_images: int, mask_cl: Optional[torch.Tensor], flag) -> torch.Tensor:
@@ -116,7 +124,7 @@ class _ConvNet2DPlan:
                 y = y2
         t = f32("img_t", self.last.N)
         conv(y.f32, self.last.K // (k * k), self.last, t)
-        return t.f32
+        return t.f32[:, :self.last.n_true]
 
 
 class ImageProgram:
@@ -265,7 +273,7 @@ def run_convnet2d(net, x: torch.Tensor, mode: Optional[str] = None) -> torch.Ten
         rows = N * H * W
         cur = torch.empty(rows, C, dtype=torch.float32, device=x.device)
         if N == 0:
-            return torch.empty(0, plan.last.N, H, W, dtype=torch.float32, device=x.device)
+            return torch.empty(0, plan.last.n_true, H, W, dtype=torch.float32, device=x.device)
         ops.layout_transpose(x.contiguous(), N, C, H * W, cur)
         t = plan.run(cur, N, None, None)
         out = torch.empty(N, t.shape[1], H, W, dtype=torch.float32, device=x.device)
