@@ -232,6 +232,9 @@ def main():
 
     if args.chunk_rows:
         U.set_chunk_rows(args.chunk_rows)
+        if len(spec["in_dims"]) > 1:                 # image-shaped events: channels-last rows (N*H*W) per chunk
+            from usflows_b200 import image_engine
+            image_engine.IMAGE_CHUNK_ROWS = args.chunk_rows
     rows = args.rows or wl["rows"]
     params = O.random_params(spec, 0)
     flow = build_flow(spec, params, device=dev, precision=args.precision)

@@ -236,6 +236,14 @@ int usf_layout_transpose(const float* in, int64_t n, int32_t a, int32_t b, const
  * weight is the conv weight permuted to [C_out, kh, kw, C_in]. */
 int usf_im2col(const float* in, int64_t ld_in, int64_t n_images, int32_t h, int32_t w, int32_t c, int32_t k, int32_t dilation,
                const float* mask, int32_t relu, const usf_planes* out, int32_t* overflow_flag, void* stream);
+/* The same convolution WITHOUT the materialised operand rows (implicit GEMM on tcgen05): out = epilogue(conv(g(act)))
+ * over channels-last rows act [n*h*w, c_in]; `a` describes the contraction part as for usf_linear -- M = n*h*w,
+ * K = k*k*c_in, N <= 64, w / w_lo = tf32 hi / lo planes of the weight [N, K] in the usf_im2col column order (a->a, a->a_lo,
+ * a->engine are ignored), bias, relu and the output planes; no residual / colscale / postsub.  fp32-accurate (3-term tf32
+ * split).  c_in % 16 == 0.  The whole weight stays resident in shared memory: USF_ERR_UNSUPPORTED when
+ * 3 * 32 KB + ceil(K/32) * 2 * (N <= 32 ? 32 : 64) * 128 B exceeds 227 KB (use usf_im2col + usf_linear then). */
+int usf_conv2d_rows(const usf_linear_args* a, const float* act, int64_t ld_act, int64_t n_images, int32_t h, int32_t w,
+                    int32_t c_in, int32_t k, int32_t dilation, const float* mask, int32_t relu_in, void* stream);
 /* x[r, c] += sign * g[(r mod hw)*c_dim + c] * t[r, c]: MaskedCoupling.forward/backward with a mask over [C, H, W]
  * (transforms.py:284-290, 301-306; g = 1 - mask in channels-last order). */
 int usf_masked_add(float* x, int64_t ldx, const float* t, int64_t ldt, int64_t rows, int32_t c, int32_t hw, const float* g,

@@ -8,6 +8,7 @@ from usflows_b200 import ops as real_ops
 from usflows_b200.ops import Act, ENGINE_SIMT, ENGINE_TC_3XF16, ENGINE_TC_3XTF32, ENGINE_TC_BF16, ENGINE_TC_TF32
 
 CALLS = []
+real_conv2d_rows_supported = real_ops.conv2d_rows_supported
 
 
 def tf32_round(x: torch.Tensor) -> torch.Tensor:
@@ -245,6 +246,24 @@ def im2col(x, n_images, h, w, c, k, dilation, out, *, mask=None, relu=False, ove
     _store(out, torch.cat(cols, dim=-1).reshape(n_images * h * w, k * k * c), overflow_flag)
 
 
+def conv2d_rows(x, n_images, h, w, c, k, dilation, w_hi, w_lo, N, *, bias=None, relu=False, out=None, mask=None,
+                relu_in=False, overflow_flag=None):
+    CALLS.append(("conv2d_rows", c, k, N, mask is not None, bool(relu_in), bool(relu)))
+    cols = Act(n_images * h * w, k * k * c, f32=torch.empty(n_images * h * w, k * k * c))
+    im2col(x, n_images, h, w, c, k, dilation, cols, mask=mask, relu=relu_in)
+    CALLS.pop()
+    v = cols.f32 @ (w_hi + w_lo).T
+    if bias is not None:
+        v = v + bias
+    if relu:
+        v = torch.relu(v)
+    _store(out, v, overflow_flag)
+
+
+def conv2d_rows_supported(N, K, c_in):
+    return real_conv2d_rows_supported(N, K, c_in)
+
+
 def masked_add(x, t, hw, g, sign):
     CALLS.append(("masked_add", sign))
     rows, c = x.shape
@@ -345,7 +364,7 @@ def require_cuda(t, name="tensor", dtype=torch.float32):
 
 def install(monkeypatch):
     CALLS.clear()
-    for name in ["layout_transpose", "im2col", "masked_add", "radial_logprob", "radial_sample", "gate_norm", "affine_couple", "sub_rows", "flow_small", "linear", "ingest", "base_logprob", "base_sample", "leaky_relu", "permute", "lu_assemble",
+    for name in ["conv2d_rows", "layout_transpose", "im2col", "masked_add", "radial_logprob", "radial_sample", "gate_norm", "affine_couple", "sub_rows", "flow_small", "linear", "ingest", "base_logprob", "base_sample", "leaky_relu", "permute", "lu_assemble",
                  "lu_logabsdet", "vec_logabs", "tri_inverse", "transpose", "scale_rows_cols", "split_tf32", "split_f16", "to_bf16",
                  "householder_right", "softplus", "matmul_f32", "matmul_f64", "require_cuda"]:
         monkeypatch.setattr(real_ops, name, globals()[name])

@@ -29,13 +29,25 @@ def test_image_launch_plan(fake_ops):
     B, L = spec["coupling_blocks"], spec["num_layers"]
     assert names.count("layout_transpose") == 1                       # NCHW -> channels-last, fused with x / scale
     assert [c for c in fake_ops.CALLS if c[0] == "layout_transpose"][0][1:] == (16, 49, 2)
-    assert names.count("im2col") == B * (2 + L)                        # one per k x k convolution
+    assert names.count("conv2d_rows") == B * (2 + L)                   # one implicit-GEMM launch per k x k convolution
+    assert names.count("im2col") == 0
     assert names.count("gate_norm") == B * L
     assert names.count("masked_add") == B
-    assert names.count("linear") == (2 * B + 1) + B * (2 + 2 * L)     # 1x1-conv affine layers + conditioner convolutions
+    assert names.count("linear") == (2 * B + 1) + B * L               # 1x1-conv affine layers + the 1x1 gate convolutions
     assert names.count("radial_logprob") == 1                          # on the channels-last memory, loc permuted
-    first = [c for c in fake_ops.CALLS if c[0] == "im2col"][0]
-    assert first[1:] == (16, 3, True, False)                           # coupling mask fused into the first gather
+    first = [c for c in fake_ops.CALLS if c[0] == "conv2d_rows"][0]
+    assert first[1:] == (16, 3, 32, True, False, False)                # coupling mask fused into the first gather
+    from usflows_b200 import image_engine
+    image_engine.IMPLICIT_CONV = False                                 # the gather + contraction route
+    try:
+        fake_ops.CALLS.clear()
+        lp2 = build_flow(spec, params, device="cpu", precision="fp32").log_prob(arr["x"])
+        names2 = [c[0] for c in fake_ops.CALLS]
+    finally:
+        image_engine.IMPLICIT_CONV = True
+    assert names2.count("im2col") == B * (2 + L) and names2.count("conv2d_rows") == 0
+    assert names2.count("linear") == (2 * B + 1) + B * (2 + 2 * L)
+    assert rel_err(lp2, lp) < 1e-5
     # rows of the contractions: N * H * W
     assert {c[2] for c in fake_ops.CALLS if c[0] == "linear"} == {arr["x"].shape[0] * 49}
 
@@ -111,6 +123,53 @@ def test_im2col_kernel_matches_conv(geom, fmt):
     got = _join(cols).cpu() @ w.permute(0, 2, 3, 1).reshape(5, -1).t()
     want = F.conv2d(torch.relu(x * mask), w, padding="same", dilation=dil).permute(0, 2, 3, 1).reshape(rows, 5)
     assert rel_err(got, want) <= (3e-2 if fmt == "bf16" else 1e-5)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fmt", ["f32", "h16", "tf32"])
+@pytest.mark.parametrize("geom", [(300, 7, 7, 32, 32, 3, 1), (64, 7, 7, 16, 32, 3, 1), (17, 5, 3, 16, 20, 3, 1), (9, 8, 8, 16, 64, 3, 1),
+                                  (11, 9, 6, 32, 12, 3, 2), (5, 4, 4, 32, 16, 3, 1), (2000, 7, 7, 32, 32, 3, 1), (3, 6, 5, 64, 8, 1, 1)])
+def test_implicit_gemm_convolution_matches_conv2d(geom, fmt):
+    """usf_conv2d_rows (A tiles gathered into shared memory, tcgen05 tf32 split) == F.conv2d(padding='same') in fp64 on
+    the same (masked, rectified) input, with bias and ReLU in the epilogue; ragged last tile, K tails, border pixels."""
+    from test_radial_convnet import _join, _planes
+    from usflows_b200 import engine, ops
+    n, H, W, C, N, k, dil = geom
+    assert ops.conv2d_rows_supported(N, k * k * C, C)
+    g = torch.Generator().manual_seed(H * W + C + N)
+    x = torch.randn(n, C, H, W, generator=g)
+    mask = (torch.rand(C, H, W, generator=g) > 0.5).float()
+    w = torch.randn(N, C, k, k, generator=g) / (k * C ** 0.5)
+    b = torch.randn(N, generator=g)
+    rows = n * H * W
+    x_cl = x.permute(0, 2, 3, 1).reshape(rows, C).contiguous().cuda()
+    m_cl = mask.permute(1, 2, 0).reshape(-1).contiguous().cuda()
+    w_hi, w_lo = engine._operand(w.permute(0, 2, 3, 1).reshape(N, -1).cuda(), "fp32_tf32", ops.ENGINE_TC_3XTF32)
+    out = _planes(rows, N, fmt)
+    ops.conv2d_rows(x_cl, n, H, W, C, k, dil, w_hi, w_lo, N, bias=b.cuda(), relu=True, out=out, mask=m_cl, relu_in=True)
+    want = torch.relu(F.conv2d(torch.relu(x * mask).double(), w.double(), b.double(), padding="same", dilation=dil))
+    want = want.permute(0, 2, 3, 1).reshape(rows, N)
+    assert rel_err(_join(out), want) <= 2e-6
+    # without mask / ReLUs, against the gather + contraction route
+    out2 = _planes(rows, N, "f32")
+    ops.conv2d_rows(x_cl, n, H, W, C, k, dil, w_hi, w_lo, N, out=out2)
+    want2 = F.conv2d(x.double(), w.double(), padding="same", dilation=dil).permute(0, 2, 3, 1).reshape(rows, N)
+    assert rel_err(out2.f32, want2) <= 2e-6
+
+
+@pytest.mark.gpu
+def test_implicit_and_gathered_convolution_paths_agree_on_a_flow():
+    from usflows_b200 import image_engine
+    spec, params, arr = load_case("img_mnist_16x7x7")
+    x = arr["x"].cuda()
+    lp = build_flow(spec, params).log_prob(x)
+    image_engine.IMPLICIT_CONV = False
+    try:
+        lp_gather = build_flow(spec, params).log_prob(x)
+    finally:
+        image_engine.IMPLICIT_CONV = True
+    assert rel_err(lp, arr["lp32"]) <= 1e-5 and rel_err(lp_gather, arr["lp32"]) <= 1e-5
+    assert rel_err(lp, lp_gather) <= 2e-6
 
 
 @pytest.mark.gpu

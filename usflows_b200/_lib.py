@@ -73,6 +73,7 @@ SIGNATURES = {
     "usf_radial_sample": (C.c_int, [_I64, _I32, _P, _I32, _I32, _P, _I32, _U64, _U64, _P, _I64, _P]),
     "usf_layout_transpose": (C.c_int, [_P, _I64, _I32, _I32, _P, _I32, _I32, _P, _P]),
     "usf_im2col": (C.c_int, [_P, _I64, _I64, _I32, _I32, _I32, _I32, _I32, _P, _I32, C.POINTER(Planes), _P, _P]),
+    "usf_conv2d_rows": (C.c_int, [C.POINTER(LinearArgs), _P, _I64, _I64, _I32, _I32, _I32, _I32, _I32, _P, _I32, _P]),
     "usf_masked_add": (C.c_int, [_P, _I64, _P, _I64, _I64, _I32, _I32, _P, _F, _P]),
     "usf_gate_norm": (C.c_int, [_P, _I64, _P, _I64, _I64, _I32, _I32, _I32, _P, _P, _F, _P, _I64, C.POINTER(Planes), _I32,
                                 C.POINTER(Planes), _P, _P]),

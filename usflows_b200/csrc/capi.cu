@@ -1,6 +1,7 @@
 // C ABI of libusflows_b200.so (see include/usflows_b200.h for the contract of every entry point).
 #include "common.cuh"
 #include "conditioner.cuh"
+#include "conv_tc.cuh"
 #include "elementwise.cuh"
 #include "flow_small.cuh"
 #include "gemm_simt.cuh"
@@ -358,6 +359,23 @@ int usf_im2col(const float* in, int64_t ld_in, int64_t n_images, int32_t h, int3
     im2col_kernel<1><<<ew_grid(rows * k * k * c, 256), 256, 0, S(stream)>>>(in, ld_in, rows, h, w, c, k, dilation, mask, relu ? 1 : 0, o);
   USF_CUDA_OK(cudaGetLastError());
   return USF_OK;
+}
+
+int usf_conv2d_rows(const usf_linear_args* a, const float* act, int64_t ld_act, int64_t n_images, int32_t h, int32_t w,
+                    int32_t c_in, int32_t k, int32_t dilation, const float* mask, int32_t relu_in, void* stream) {
+  USF_REQUIRE(a && act && a->w && a->w_lo, "null argument (the weight comes as tf32 hi / lo planes)");
+  USF_REQUIRE(n_images >= 0 && h > 0 && w > 0 && c_in > 0 && c_in % 16 == 0 && ld_act >= c_in && ld_act % 4 == 0 && aligned16(act),
+              "channels-last rows with C % 16 == 0 and 16-byte aligned rows");
+  USF_REQUIRE(k >= 1 && (k & 1) && dilation >= 1, "odd kernel size (padding 'same') and dilation >= 1");
+  USF_REQUIRE(a->M == n_images * (int64_t)h * w && a->K == k * k * c_in && a->N >= 1, "M = n*h*w, K = k*k*c_in");
+  USF_REQUIRE(!mask || aligned16(mask), "unaligned mask");
+  USF_REQUIRE(!a->resid && !a->resid_h16 && !a->colscale && !a->postsub, "usf_conv2d_rows: bias / ReLU epilogue only");
+  if (a->M == 0) return USF_OK;
+  Epilogue ep;
+  int rc = make_epilogue(a, &ep);
+  if (rc) return rc;
+  ConvGeom g{act, ld_act, h, w, c_in, k, dilation, mask, relu_in ? 1 : 0};
+  return launch_conv_tc(a, g, ep, S(stream));
 }
 
 int usf_masked_add(float* x, int64_t ldx, const float* t, int64_t ldt, int64_t rows, int32_t c, int32_t hw, const float* g,

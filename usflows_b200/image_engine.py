@@ -27,6 +27,7 @@ from .ops import Act, ENGINE_SIMT, ENGINE_TC_3XF16, ENGINE_TC_3XTF32, ENGINE_TC_
 
 _PLANES = {ENGINE_SIMT: ("f32",), ENGINE_TC_TF32: ("f32",), ENGINE_TC_3XF16: ("h16", "l16"), ENGINE_TC_3XTF32: ("hi", "lo"),
            ENGINE_TC_BF16: ("bf16",)}
+IMPLICIT_CONV = True                # k x k convolutions as implicit GEMMs (usf_conv2d_rows) where the shape allows it
 IMAGE_CHUNK_ROWS = 1 << 19          # channels-last rows (N*H*W) per chunk: bounds the im2col workspace (rows x k*k*C)
 
 
@@ -45,7 +46,8 @@ def _dense(dev, name: str, rows: int, width: int) -> torch.Tensor:
 class _Gemm:
     """One contraction out = A . W^T + b with its weight in the operand format of the engine chosen for its shape."""
 
-    def __init__(self, mode: str, w: torch.Tensor, b: Optional[torch.Tensor], wflag, pad_n: bool = False):
+    def __init__(self, mode: str, w: torch.Tensor, b: Optional[torch.Tensor], wflag, pad_n: bool = False,
+                 conv_cin: int = 0):
         self.n_true = w.shape[0]
         if pad_n and mode != "fp32_simt" and w.shape[0] < engine.TC_MIN_DIM <= w.shape[1]:
             # a narrow output (the c_in channels of the conditioner's last convolution) would fall to the SIMT engine:
@@ -58,6 +60,10 @@ class _Gemm:
         self.engine = _engine_for(mode, self.N, self.K)
         self.w, self.w_lo = _operand(w, mode, self.engine, wflag if self.engine == ENGINE_TC_3XF16 else None)
         self.bias = None if b is None else b.to(torch.float32).contiguous()
+        # implicit-GEMM convolution: tf32 hi / lo planes of the same weight (the kernel computes in the 3-term tf32 split)
+        self.conv_w = None
+        if conv_cin and IMPLICIT_CONV and mode in ("fp32", "fp32_tf32") and ops.conv2d_rows_supported(self.N, self.K, conv_cin):
+            self.conv_w = _operand(w, "fp32_tf32", ENGINE_TC_3XTF32)
 
     def __call__(self, a: Act, out: Act, relu: bool = False, flag=None) -> None:
         ops.linear(self.engine, a, self.w, self.w_lo, self.N, self.K, bias=self.bias, relu=relu, out=out,
@@ -79,15 +85,17 @@ class _ConvNet2DPlan:
             ops.require_cuda(prm, "conditioner parameter")
         self.k, self.dil, self.H, self.W = d["k"], d["dilation"], H, W
         self.c_in = d["first"].weight.shape[1]
-        self.first = _Gemm(mode, _conv_weight(d["first"]), d["first"].bias.detach(), wflag)
+        kk = self.k * self.k
+        cin = lambda conv: conv.weight.shape[1] if kk > 1 else 0      # noqa: E731  (1x1 convolutions are plain contractions)
+        self.first = _Gemm(mode, _conv_weight(d["first"]), d["first"].bias.detach(), wflag, conv_cin=cin(d["first"]))
         self.blocks = []
         for b in d["blocks"]:
             ln = None if b["ln"] is None else (b["ln"].gamma.detach().reshape(-1).contiguous(),
                                                b["ln"].beta.detach().reshape(-1).contiguous(), float(b["ln"].eps))
-            g1 = _Gemm(mode, _conv_weight(b["conv1"]), b["conv1"].bias.detach(), wflag)
+            g1 = _Gemm(mode, _conv_weight(b["conv1"]), b["conv1"].bias.detach(), wflag, conv_cin=cin(b["conv1"]))
             g2 = None if not b["gated"] else _Gemm(mode, _conv_weight(b["conv2"]), b["conv2"].bias.detach(), wflag)
             self.blocks.append((b["gated"], g1, g2, ln))
-        self.last = _Gemm(mode, _conv_weight(d["last"]), d["last"].bias.detach(), wflag, pad_n=True)
+        self.last = _Gemm(mode, _conv_weight(d["last"]), d["last"].bias.detach(), wflag, pad_n=True, conv_cin=cin(d["last"]))
         self.gemms = [self.first, self.last] + [g for b in self.blocks for g in b[1:3] if g is not None]
 
     def run(self, x_rows: torch.Tensor, n_images: int, mask_cl: Optional[torch.Tensor], flag) -> torch.Tensor:
@@ -96,6 +104,10 @@ class _ConvNet2DPlan:
         H, W, k, dil = self.H, self.W, self.k, self.dil
 
         def conv(src: torch.Tensor, c: int, g: _Gemm, out: Act, *, mask=None, relu_in=False, relu_out=False):
+            if g.conv_w is not None and src.stride(0) % 4 == 0:        # no gathered copy in memory: implicit GEMM
+                ops.conv2d_rows(src, n_images, H, W, c, k, dil, g.conv_w[0], g.conv_w[1], g.N, bias=g.bias, relu=relu_out,
+                                out=out, mask=mask, relu_in=relu_in, overflow_flag=flag)
+                return
             if k == 1:
                 cols = _act(dev, "img_cols", rows, c, g.engine)
                 ops.im2col(src, n_images, H, W, c, 1, 1, cols, mask=mask, relu=relu_in, overflow_flag=flag)

@@ -231,6 +231,39 @@ def im2col(x: torch.Tensor, n_images: int, h: int, w: int, c: int, k: int, dilat
                                  _ptr(overflow_flag), _stream()))
 
 
+CONV_TC_SMEM_LIMIT = 227 * 1024
+
+
+def conv2d_rows_supported(N: int, K: int, c_in: int) -> bool:
+    """Whether usf_conv2d_rows serves this shape (N <= 64, C % 16 == 0, whole weight resident in shared memory)."""
+    bn = 32 if N <= 32 else 64
+    return N <= 64 and c_in % 16 == 0 and 3 * 32768 + ((K + 31) // 32) * 2 * bn * 128 + 1280 <= CONV_TC_SMEM_LIMIT
+
+
+def conv2d_rows(x: torch.Tensor, n_images: int, h: int, w: int, c: int, k: int, dilation: int, w_hi, w_lo, N: int, *,
+                bias=None, relu: bool = False, out: Act, mask=None, relu_in: bool = False,
+                overflow_flag: Optional[torch.Tensor] = None) -> None:
+    """k x k 'same' convolution over channels-last rows as an implicit GEMM on tcgen05; see usf_conv2d_rows."""
+    global LAUNCHES
+    LAUNCHES += 1
+    args = LinearArgs()
+    args.M, args.N, args.K = n_images * h * w, N, k * k * c
+    args.engine = ENGINE_TC_3XTF32
+    args.w, args.w_lo, args.ldw = _ptr(w_hi), _ptr(w_lo), _ld(w_hi)
+    args.bias, args.relu, args.resid_sign = _ptr(bias), int(relu), 1.0
+    if out.f32 is not None:
+        args.out_f32, args.ld_f32 = _ptr(out.f32), _ld(out.f32)
+    if out.hi is not None:
+        args.out_hi, args.out_lo, args.ld_split = _ptr(out.hi), _ptr(out.lo), _ld(out.hi)
+    if out.bf16 is not None:
+        args.out_bf16, args.ld_bf16 = _ptr(out.bf16), _ld(out.bf16)
+    if out.h16 is not None:
+        args.out_h16, args.out_l16, args.ld_16 = _ptr(out.h16), _ptr(out.l16), _ld(out.h16)
+        args.overflow_flag = _ptr(overflow_flag)
+    check(_lib.load().usf_conv2d_rows(C.byref(args), _ptr(x), _ld(x), n_images, h, w, c, k, dilation, _ptr(mask),
+                                      int(relu_in), _stream()))
+
+
 def masked_add(x: torch.Tensor, t: torch.Tensor, hw: int, g: torch.Tensor, sign: float) -> None:
     global LAUNCHES
     LAUNCHES += 1
