@@ -3,7 +3,7 @@ agree with the outputs of the REAL reference (golden fixtures) -- and must not l
 import pytest
 import torch
 
-from helpers import SMALL_CASES, build_flow, load_case, rel_err
+from helpers import EXT_CASES, IMG_CASES, SMALL_CASES, build_flow, load_case, rel_err
 
 
 def _flow(name):
@@ -23,6 +23,22 @@ def test_reference_module_reproduces_the_reference(name):
     assert rel_err(y, arr["y32"]) <= bound(arr["y32"], arr["y64"], 5e-6)
     s = flow.reference_module("sample")(torch.zeros(7, arr["x"].shape[1]))
     assert s.shape == (7, arr["x"].shape[1]) and torch.isfinite(s).all()
+
+
+@pytest.mark.parametrize("name", EXT_CASES[:5] + IMG_CASES)
+def test_reference_module_covers_convnet_radial_and_image_flows(name):
+    """ConvNet (vector) / ConvNet2D conditioners, Lp-radial bases, image-shaped events."""
+    flow, arr = _flow(name)
+    lp = flow.reference_module("log_prob")(arr["x"])
+    z = flow.reference_module("backward")(arr["x"])
+    y = flow.reference_module("forward")(arr["z0"])
+    bound = lambda a32, a64, floor: 3.0 * rel_err(a32, a64) + floor      # noqa: E731
+    assert lp.shape == arr["lp32"].shape and z.shape == arr["z32"].shape
+    assert rel_err(lp, arr["lp32"]) <= bound(arr["lp32"], arr["lp64"], 5e-6)
+    assert rel_err(z, arr["z32"]) <= bound(arr["z32"], arr["z64"], 5e-6)
+    assert rel_err(y, arr["y32"]) <= bound(arr["y32"], arr["y64"], 5e-6)
+    traced = torch.jit.trace(flow.reference_module("log_prob").eval(), (arr["x"][:4],))
+    assert torch.equal(traced(arr["x"][4:]), flow.reference_module("log_prob")(arr["x"][4:]))
 
 
 @pytest.mark.parametrize("mode", ["log_prob", "backward", "forward"])

@@ -83,6 +83,31 @@ def test_convnet2d_module_matches_oracle(fake_ops):
         U.ConvNet2D(c_in=4, c_hidden=8, padding=0)                     # not shape preserving
 
 
+@pytest.mark.parametrize("name", ["img_c4_4x4", "img_c6_5x3_plain_channel", "img_mnist_16x7x7"])
+def test_image_training_pass_matches_oracle_gradients(fake_ops, name):
+    """`Flow.fit`'s autograd pass (flows.py:195-199) for image-shaped flows: loss and every parameter gradient against
+    autograd through the oracle (= the reference's own ops)."""
+    from usflows_b200 import training
+    spec, params, arr = load_case(name)
+    flow = build_flow(spec, params, device="cpu")
+    x = arr["x"][:12]
+    loss = -training.log_prob_autograd(flow, x).mean()
+    loss.backward()
+    p = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in params.items()}
+    want_loss = -O.flow_log_prob(x, spec, p).mean()
+    want_loss.backward()
+    assert abs(float(loss.detach()) - float(want_loss.detach())) <= 2e-5 * max(1.0, abs(float(want_loss.detach())))
+    got = dict(flow.named_parameters())
+    checked = 0
+    for key in got:
+        if "conditioner" in key or key.startswith("base_distribution") or key.endswith("scale"):
+            g, w = got[key].grad, p[key].grad
+            assert g is not None and w is not None, key
+            assert float((g - w).abs().max()) <= 3e-4 * max(1.0, float(w.abs().max())), key
+            checked += 1
+    assert checked >= 8
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 @pytest.mark.gpu
 @pytest.mark.parametrize("shape", [(3, 16, 49), (5, 49, 16), (2, 3, 1024), (1, 100, 70), (7, 1, 5)])
@@ -230,6 +255,17 @@ def test_mnist_config_full_batch_properties():
     assert rel_err(flow.base_distribution.log_prob(z) - total, lp) <= 1e-5
     want = O.flow_log_prob(x[:64].cpu(), spec, params, dtype=torch.float64)
     assert rel_err(lp[:64], want) <= 1e-5
+
+
+@pytest.mark.gpu
+def test_image_flow_fit_runs_and_lowers_the_loss():
+    spec, params, arr = load_case("img_mnist_16x7x7")
+    flow = build_flow(spec, params)
+    losses = flow.fit(arr["x"].cuda(), optim=torch.optim.Adam, optim_params=dict(lr=1e-3), batch_size=24, epochs=6,
+                      shuffle=False)
+    assert all(torch.isfinite(torch.as_tensor(float(l))) for l in losses)
+    assert float(losses[-1]) < float(losses[0])
+    assert bool(torch.isfinite(flow.log_prob(arr["x"].cuda())).all())     # the kernels follow the updated weights
 
 
 @pytest.mark.gpu

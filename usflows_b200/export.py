@@ -31,6 +31,8 @@ class ReferenceSemantics(torch.nn.Module):
         if mode not in ("log_prob", "backward", "forward", "sample"):
             raise ValueError(f"Unknown export mode {mode}")
         self.mode = mode
+        self.event_shape = tuple(int(v) for v in flow._event_shape())
+        self.plans = {}                      # layer index -> op list of a ConvNet / ConvNet2D conditioner
         self.kinds: List[str] = []
         self.inverted: List[bool] = []
         self.n_tensors: List[int] = []
@@ -49,8 +51,6 @@ class ReferenceSemantics(torch.nn.Module):
             self.inverted.append(inv)
             start = count
             if isinstance(layer, T.BlockAffineTransform):
-                if len(layer.in_dims) != 1:
-                    raise NotImplementedError("usflows_b200: image-shaped in_dims are not built")
                 W, Winv, b, ladj = _affine_tensors(layer.block_transform)
                 self.kinds.append("affine")
                 for t in (W, Winv, b, ladj * layer.n_blocks):
@@ -60,8 +60,11 @@ class ReferenceSemantics(torch.nn.Module):
                 self.kinds.append("affine")
                 for t in (W, Winv, b, ladj):
                     reg(t)
-            elif isinstance(layer, T.MaskedCoupling) and not hasattr(layer.conditioner, "layers"):
-                raise NotImplementedError("usflows_b200: export of couplings with a ConvNet conditioner is not built")
+            elif type(layer) is T.MaskedCoupling and not hasattr(layer.conditioner, "layers"):
+                # the reference's own conditioners: networks.ConvNet (vector branch) / networks.ConvNet2D
+                self.kinds.append("coupling_net")
+                reg(layer.mask.reshape(1, *layer.mask.shape[-len(self.event_shape):]))
+                self.plans[len(self.kinds) - 1] = self._net_plan(layer.conditioner, reg, start)
             elif isinstance(layer, T.MaskedAffineCoupling):
                 self.kinds.append("affine_coupling")
                 reg(layer.mask.reshape(-1))
@@ -77,7 +80,7 @@ class ReferenceSemantics(torch.nn.Module):
                     reg(lin.bias)
             elif isinstance(layer, T.ScaleTransform):
                 self.kinds.append("scale")
-                reg(layer.scale.reshape(-1))
+                reg(layer.scale.reshape(self.event_shape))
             elif isinstance(layer, T.LeakyReLUTransform):
                 self.kinds.append("leaky")
                 reg(torch.tensor(float(layer.alpha)))
@@ -92,14 +95,107 @@ class ReferenceSemantics(torch.nn.Module):
             self.n_tensors.append(count - start)
         base = flow.base_distribution
         base = base.base_dist if isinstance(base, Independent) else base
-        if not hasattr(base, "scale_unconstrained"):
-            raise NotImplementedError(f"usflows_b200: export with a {type(base).__name__} base is not built")
-        self.base_kind = "laplace" if type(base).__name__ == "Laplace" else "normal"
-        raw = base.scale_unconstrained.detach()
-        loc = base.loc.detach().reshape(-1)
-        scale = torch.nn.functional.softplus(raw.expand_as(base.loc) if raw.dim() == 0 else raw).reshape(-1)
-        self.register_buffer("loc", loc.clone().to(torch.float32))
-        self.register_buffer("scale", scale.clone().to(torch.float32))
+        sp = torch.nn.functional.softplus
+        self.register_buffer("loc", base.loc.detach().clone().to(torch.float32).reshape(self.event_shape))
+        if type(base).__name__ == "RadialDistribution":            # distributions.py:501-549
+            nd = base.norm_distribution
+            self.base_kind, self.p, self.dv_const = "radial", base.p, base.log_delta_volume_const()
+            if type(nd).__name__ == "LogNormal":
+                self.norm_kind = "lognormal"
+                self.register_buffer("r_mu", nd.loc.detach().clone().reshape(()))
+                self.register_buffer("r_sigma", sp(nd.scale_unconstrained.detach()).reshape(()))
+            else:
+                self.norm_kind = "gammamm"
+                self.register_buffer("r_logw", torch.log_softmax(nd.mixture_logits.detach(), 0))
+                self.register_buffer("r_conc", sp(nd.concentration_unconstrained.detach()))
+                self.register_buffer("r_rate", sp(nd.rate_unconstrained.detach()))
+        else:
+            self.base_kind = "laplace" if type(base).__name__ == "Laplace" else "normal"
+            raw = base.scale_unconstrained.detach()
+            scale = sp(raw.expand_as(base.loc) if raw.dim() == 0 else raw).reshape(self.event_shape)
+            self.register_buffer("scale", scale.clone().to(torch.float32))
+
+    @staticmethod
+    def _net_plan(net, reg, start):
+        """Op list of a ConvNet (vector) / ConvNet2D conditioner; tensors are registered in order, ops refer to them by
+        position (networks.py:222-245, 287-307 / 61-121, 441-494)."""
+        d = net._describe()
+        conv = "conv1" in (d["blocks"][0] if d["blocks"] else {}) or hasattr(net, "kernel_size")
+        plan, n = [], [1]                            # tensor 0 of the layer is the mask
+
+        def lin(m, tag):
+            reg(m.weight)
+            reg(m.bias)
+            plan.append((tag, n[0], int(m.dilation[0]) if hasattr(m, "dilation") else 1))
+            n[0] += 2
+
+        lin(d["first"], "conv" if conv else "lin")
+        for blk in d["blocks"]:
+            if conv:
+                if blk["gated"]:
+                    plan.append(("save", 0, 0))
+                    plan.append(("relu", 0, 0))
+                    lin(blk["conv1"], "conv")
+                    plan.append(("relu", 0, 0))
+                    lin(blk["conv2"], "conv")
+                    plan.append(("gate", 0, 0))
+                else:
+                    lin(blk["conv1"], "conv")
+                plan.append(("relu", 0, 0))
+                if blk["ln"] is not None:
+                    reg(blk["ln"].gamma)
+                    reg(blk["ln"].beta)
+                    plan.append(("ln_channels", n[0], float(blk["ln"].eps)))
+                    n[0] += 2
+            else:
+                if blk["gated"]:
+                    plan.append(("save", 0, 0))
+                    plan.append(("relu", 0, 0))
+                    lin(blk["lin1"], "lin")
+                    plan.append(("relu", 0, 0))
+                    lin(blk["lin2"], "lin")
+                    if blk["proj"] is not None:
+                        reg(blk["proj"].weight)
+                        reg(blk["proj"].bias)
+                        plan.append(("proj", n[0], 0))
+                        n[0] += 2
+                    plan.append(("gate", 0, 0))
+                else:
+                    plan.append(("relu", 0, 0))
+                    lin(blk["lin1"], "lin")
+                if blk["ln"] is not None:
+                    reg(blk["ln"].weight)
+                    reg(blk["ln"].bias)
+                    plan.append(("ln", n[0], float(blk["ln"].eps)))
+                    n[0] += 2
+        lin(d["last"], "conv" if conv else "lin")
+        return plan
+
+    @staticmethod
+    def _run_plan(plan, ts, h):
+        F = torch.nn.functional
+        saved = None
+        for op, i, arg in plan:
+            if op == "lin":
+                h = F.linear(h, ts[i], ts[i + 1])
+            elif op == "conv":
+                h = F.conv2d(h, ts[i], ts[i + 1], padding="same", dilation=arg)
+            elif op == "relu":
+                h = torch.relu(h)
+            elif op == "save":
+                saved = h
+            elif op == "proj":
+                saved = F.linear(saved, ts[i], ts[i + 1])
+            elif op == "gate":
+                val, gate = h.chunk(2, dim=1)
+                h = saved + val * torch.sigmoid(gate)
+            elif op == "ln":
+                h = F.layer_norm(h, (h.shape[1],), ts[i], ts[i + 1], arg)
+            else:                                    # LayerNormChannels, networks.py:53-58
+                mean = h.mean(dim=1, keepdim=True)
+                var = h.var(dim=1, unbiased=False, keepdim=True)
+                h = (h - mean) / torch.sqrt(var + arg) * ts[i] + ts[i + 1]
+        return h
 
     # -- per-layer algebra: `to_data` = the layer's forward (latent -> data), else its backward -------------------
     def _tensors(self, i: int):
@@ -113,8 +209,16 @@ class ReferenceSemantics(torch.nn.Module):
         sign = -1.0 if self.inverted[i] else 1.0
         if kind == "affine":
             W, Winv, b, ladj = ts
-            y = torch.nn.functional.linear(x, W, b) if to_data else torch.nn.functional.linear(x - b, Winv)
+            if len(self.event_shape) == 3:                          # 1x1 convolution over the channels (transforms.py:904-962)
+                conv = torch.nn.functional.conv2d
+                y = conv(x, W[:, :, None, None], b) if to_data else conv(x - b.view(1, -1, 1, 1), Winv[:, :, None, None])
+            else:
+                y = torch.nn.functional.linear(x, W, b) if to_data else torch.nn.functional.linear(x - b, Winv)
             return y, sign * ladj                                   # transforms.py:913-980
+        if kind == "coupling_net":
+            m = ts[0]
+            t = (1 - m) * self._run_plan(self.plans[i], ts, x * m)
+            return (x + t if to_data else x - t), None              # transforms.py:277-306, 316-326
         if kind == "coupling":
             m = ts[0]
             h = x * m
@@ -172,6 +276,8 @@ class ReferenceSemantics(torch.nn.Module):
         if self.mode == "forward":
             return self._to_data(x)
         if self.mode == "sample":          # one base draw per row of `x` (shape donor), then latent -> data
+            if self.base_kind == "radial":
+                raise NotImplementedError("usflows_b200: the exported sampler covers Laplace / Normal bases")
             if self.base_kind == "laplace":
                 u = torch.rand_like(x) - 0.5
                 e = -torch.sign(u) * torch.log1p(-2.0 * u.abs())
@@ -179,19 +285,31 @@ class ReferenceSemantics(torch.nn.Module):
                 e = torch.randn_like(x)
             return self._to_data(self.loc + self.scale * e)
         z, total = self._to_latent(x)      # flows.py:234-245
+        ev = tuple(range(1, z.dim()))
+        if self.base_kind == "radial":     # distributions.py:501-549
+            v = z - self.loc
+            r = v.abs().sum(ev) if self.p == 1.0 else v.pow(2).sum(ev).sqrt() if self.p == 2.0 else v.abs().amax(ev)
+            logr = r.log()
+            if self.norm_kind == "lognormal":
+                lpr = -((logr - self.r_mu) ** 2) / (2 * self.r_sigma ** 2) - self.r_sigma.log() \
+                    - 0.5 * math.log(2 * math.pi) - logr
+            else:
+                t = self.r_logw + self.r_conc * self.r_rate.log() - torch.lgamma(self.r_conc) \
+                    + (self.r_conc - 1) * logr[:, None] - self.r_rate * r[:, None]
+                lpr = torch.logsumexp(t, -1)
+            return lpr - (self.dv_const + (self.loc.numel() - 1) * logr) - total
         if self.base_kind == "laplace":
             lp = -torch.log(2 * self.scale) - (z - self.loc).abs() / self.scale
         else:
             lp = -((z - self.loc) ** 2) / (2 * self.scale ** 2) - self.scale.log() - 0.5 * math.log(2 * math.pi)
-        return lp.sum(-1) - total
+        return lp.sum(ev) - total
 
 
 def to_onnx(flow, path: str, export_mode: str = "log_prob", **export_kwargs) -> None:
     """`Flow.to_onnx` (flows.py:212-223): the frozen reference-semantics module, traced on one base-shaped row.
     Needs the `onnx` package like any `torch.onnx.export`."""
     module = ReferenceSemantics(flow, export_mode).cpu().eval()
-    d = module.loc.numel()
-    dummy = torch.zeros(1, d, dtype=torch.float32)
+    dummy = torch.zeros(1, *module.event_shape, dtype=torch.float32)
     export_kwargs.setdefault("input_names", ["x"])
     export_kwargs.setdefault("output_names", [export_mode])
     export_kwargs.setdefault("dynamic_axes", {"x": {0: "rows"}, export_mode: {0: "rows"}})

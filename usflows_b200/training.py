@@ -135,11 +135,13 @@ def affine_parts(t, cache: Optional[dict] = None):
     raise NotImplementedError(f"usflows_b200: training of {type(t).__name__} is not built")
 
 
-def _layer_backward(layer, y: torch.Tensor, inverse: bool = False, cache: Optional[dict] = None):
-    """(density direction value, forward log|det J|) of one layer; `inverse` swaps the direction."""
+def _layer_backward(layer, y: torch.Tensor, inverse: bool = False, cache: Optional[dict] = None, geom=None):
+    """(density direction value, forward log|det J|) of one layer; `inverse` swaps the direction.  For image-shaped events
+    `geom = (C, H, W)` and y holds channels-last rows [N*H*W, C] (the layout of image_engine.py): the 1x1 convolution of a
+    BlockAffineTransform is then the same `linear` as the flat case, per-element vectors are indexed per pixel."""
     from . import transforms as T
     if isinstance(layer, T.InverseTransform):
-        x, ladj = _layer_backward(layer.transform, y, not inverse, cache)
+        x, ladj = _layer_backward(layer.transform, y, not inverse, cache, geom)
         return x, -ladj
     if isinstance(layer, T.BlockAffineTransform):
         W, Winv, b, ladj = affine_parts(layer.block_transform, cache)
@@ -148,10 +150,17 @@ def _layer_backward(layer, y: torch.Tensor, inverse: bool = False, cache: Option
             return linear(y, W, b), ladj
         return linear(y - b, Winv), ladj                # (y - b) Winv^T                       (transforms.py:936-962)
     if isinstance(layer, T.ScaleTransform):
+        ladj = layer.scale.abs().log().sum()
+        if geom is not None:                             # scale over [C, H, W], applied per pixel of every image
+            C, H, W = geom
+            s = layer.scale.reshape(C, H * W).t()
+            y3 = y.reshape(-1, H * W, C)
+            return (y3 * s if inverse else y3 / s).reshape(-1, C), ladj
         s = layer.scale.reshape(-1)
-        ladj = s.abs().log().sum()
         return (y * s if inverse else y / s), ladj      # transforms.py:105-125, 135-144
     if isinstance(layer, T.MaskedAffineCoupling):
+        if geom is not None:
+            raise NotImplementedError("usflows_b200: affine couplings over image-shaped events are not built")
         m = layer.mask.reshape(-1).to(y.dtype)
         h = y * m
         lin = list(layer.conditioner.layers)
@@ -164,6 +173,13 @@ def _layer_backward(layer, y: torch.Tensor, inverse: bool = False, cache: Option
         t = (1 - m) * h[:, d:]
         ladj = s.sum(-1)                                               # per row
         return (y * torch.exp(s) + t if inverse else (y - t) * torch.exp(-s)), ladj
+    if isinstance(layer, T.MaskedCoupling) and geom is not None:
+        C, H, W = geom
+        m = layer.mask.reshape(C, H * W).t().to(y.dtype)                # channels-last mask [H*W, C]
+        y3 = y.reshape(-1, H * W, C)
+        t = _convnet2d_rows(layer.conditioner, (y3 * m).reshape(-1, C), geom).reshape(-1, H * W, C)
+        t = (1 - m) * t
+        return ((y3 + t) if inverse else (y3 - t)).reshape(-1, C), y.new_zeros(())
     if isinstance(layer, T.MaskedCoupling):
         m = layer.mask.reshape(-1).to(y.dtype)
         t = (1 - m) * _conditioner(layer.conditioner, y * m)
@@ -197,6 +213,57 @@ def _conditioner(net, h: torch.Tensor) -> torch.Tensor:
         if j < len(lin) - 1:
             h = torch.relu(h)
     return h
+
+
+_GATHER_INDEX = {}
+
+
+def _gather_index(H: int, W: int, k: int, dil: int, device) -> torch.Tensor:
+    """[H*W, k*k] source pixel of every (pixel, tap) of a k x k 'same' convolution; H*W = the zero pixel (padding)."""
+    key = (H, W, k, dil, str(device))
+    if key not in _GATHER_INDEX:
+        hh, ww = torch.meshgrid(torch.arange(H), torch.arange(W), indexing="ij")
+        cols = []
+        for kh in range(k):
+            for kw in range(k):
+                sh, sw = hh + (kh - k // 2) * dil, ww + (kw - k // 2) * dil
+                ok = (sh >= 0) & (sh < H) & (sw >= 0) & (sw < W)
+                cols.append(torch.where(ok, sh * W + sw, torch.full_like(sh, H * W)).reshape(-1))
+        _GATHER_INDEX[key] = torch.stack(cols, dim=1).to(device)
+    return _GATHER_INDEX[key]
+
+
+def _conv_rows(x: torch.Tensor, conv, geom) -> torch.Tensor:
+    """nn.Conv2d (stride 1, padding 'same') over channels-last rows [N*H*W, C_in] as gather (torch indexing, carries the
+    autograd bookkeeping) + `linear` (contraction forward / dX / dW on the library's kernels)."""
+    C, H, W = geom
+    cin, k = conv.weight.shape[1], conv.weight.shape[2]
+    w = conv.weight.permute(0, 2, 3, 1).reshape(conv.weight.shape[0], -1)        # the usf_im2col column order
+    if k == 1:
+        return linear(x, w, conv.bias)
+    idx = _gather_index(H, W, k, conv.dilation[0], x.device)
+    x3 = x.reshape(-1, H * W, cin)
+    xp = torch.cat([x3, x3.new_zeros(x3.shape[0], 1, cin)], dim=1)
+    cols = xp[:, idx.reshape(-1), :].reshape(-1, k * k * cin)
+    return linear(cols, w, conv.bias)
+
+
+def _convnet2d_rows(net, x: torch.Tensor, geom) -> torch.Tensor:
+    """networks.ConvNet2D (networks.py:441-506) over channels-last rows as an autograd graph."""
+    d = net._describe()
+    h = _conv_rows(x, d["first"], geom)
+    for blk in d["blocks"]:
+        if blk["gated"]:                                  # GatedConv.forward, networks.py:103-121
+            o = _conv_rows(torch.relu(_conv_rows(torch.relu(h), blk["conv1"], geom)), blk["conv2"], geom)
+            val, gate = o.chunk(2, dim=1)
+            h = h + val * torch.sigmoid(gate)
+        else:
+            h = _conv_rows(h, blk["conv1"], geom)
+        h = torch.relu(h)
+        if blk["ln"] is not None:                         # LayerNormChannels, networks.py:53-58 (per pixel = per row)
+            ln = blk["ln"]
+            h = torch.nn.functional.layer_norm(h, (h.shape[1],), ln.gamma.reshape(-1), ln.beta.reshape(-1), ln.eps)
+    return _conv_rows(h, d["last"], geom)
 
 
 def _radial_log_prob(b, z: torch.Tensor) -> torch.Tensor:
@@ -238,12 +305,21 @@ def base_log_prob(base, z: torch.Tensor) -> torch.Tensor:
 
 def log_prob_autograd(flow, x: torch.Tensor) -> torch.Tensor:
     """`Flow.log_prob` (flows.py:225-245) as an autograd graph over the flow's parameters."""
-    z = x.reshape(x.shape[0], -1)
+    ev = tuple(flow._event_shape())
+    geom = None
+    if len(ev) == 3:                             # image-shaped event: channels-last rows [N*H*W, C] through the layers
+        geom = ev
+        C, H, W = ev
+        z = x.reshape(-1, C, H * W).transpose(1, 2).reshape(-1, C)
+    else:
+        z = x.reshape(x.shape[0], -1)
     total = z.new_zeros(())                      # scalar, or [rows] once a data-dependent log-det joins
     cache: dict = {}
     for layer in reversed(flow.layers):
-        z, ladj = _layer_backward(layer, z, cache=cache)
+        z, ladj = _layer_backward(layer, z, cache=cache, geom=geom)
         total = total + ladj
+    if geom is not None:                         # back to the NCHW element order the base parameters are stored in
+        z = z.reshape(-1, H * W, C).transpose(1, 2).reshape(-1, C * H * W)
     return base_log_prob(flow.base_distribution, z) - total
 
 
