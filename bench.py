@@ -299,8 +299,8 @@ def main():
     # kernel-class breakdown of one step (events around every launch; after the timed region)
     breakdown = engine.profile_step(lambda: flow.log_prob(x))
     gemm_ms = sum(v for k, v in breakdown.items() if k.startswith("linear"))
-    if len(spec["in_dims"]) > 1:            # image path: the gathers feed the contractions and belong to the convolution
-        gemm_ms += breakdown.get("im2col", 0.0)
+    if len(spec["in_dims"]) > 1:            # image path: the convolutions (implicit GEMM, or gather + contraction)
+        gemm_ms += breakdown.get("im2col", 0.0) + breakdown.get("conv2d_rows", 0.0)
     peaks, peak_kind = measured_peaks()
     # DRAM traffic of the dominant kernel per launch, from the committed ncu --set full capture (profiles/): the mean of
     # dram__bytes_read.sum + dram__bytes_write.sum over the captured launches of one step
@@ -376,7 +376,10 @@ def main():
     roofline = dict(bound="tensor", achieved=achieved_tf, peak=peak_tf, unit="TFLOP/s",
                     frac=achieved_tf / peak_tf, traffic=traffic,
                     peak_source=f"bf16_tflops_sustained, of {peak_kind}",
-                    kernel="tc2::gemm_tc2_kernel (CTA-pair tcgen05, all launches of one step)", kernel_ms_per_step=gemm_ms,
+                    kernel="tc2::gemm_tc2_kernel (CTA-pair tcgen05, all launches of one step)" if len(spec["in_dims"]) == 1
+                    else "convtc::conv_tc_kernel (implicit-GEMM tcgen05 convolution) + tc2::gemm_tc2_kernel / SIMT 1x1 "
+                         "convolutions, all launches of one step",
+                    kernel_ms_per_step=gemm_ms,
                     launches_per_step=n_gemm,
                     note="algorithmic fp32 FLOPs over the summed CUDA-event time of the GEMM launches of one step; "
                          "the fp32 mode spends 3 fp16 MMAs per algorithmic MAC (fp16 runs at the bf16 rate), so its "

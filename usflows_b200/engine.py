@@ -855,7 +855,8 @@ def profile_step(fn) -> dict:
     kernel class ("linear NxK", "ingest", "base_logprob") plus "_names" (launch order) and "_total"."""
     records = []
     originals = {name: getattr(ops, name) for name in ("linear", "ingest", "base_logprob", "flow_small", "gate_norm", "radial_logprob",
-                                                         "affine_couple", "im2col", "layout_transpose", "masked_add")}
+                                                         "affine_couple", "im2col", "conv2d_rows", "layout_transpose",
+                                                         "masked_add")}
 
     def wrap(name, f):
         def inner(*a, **k):
