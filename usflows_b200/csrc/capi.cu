@@ -15,6 +15,7 @@ namespace usf {
 thread_local char g_err[512] = "";
 int g_force_block_n = 0;
 int g_chunk_slabs = 2;
+int g_conv_chunk_slabs = 3;
 int g_lead_chains = 2;
 int g_tc_impl = 2;
 unsigned long long* g_dbg_buf = nullptr;
@@ -150,6 +151,7 @@ int usf_set_accum_lead(int chains) {  // leading double-length accumulation chai
 int usf_set_accum_chunk(int k_slabs) {  // 3xTF32 mode: K-slabs (32 elements each) per accumulation chain; 0 = whole K
   USF_REQUIRE(k_slabs >= 0, "negative chunk");
   g_chunk_slabs = k_slabs;
+  g_conv_chunk_slabs = k_slabs;           // (defaults differ: 2 for the contractions, 3 for usf_conv2d_rows)
   return USF_OK;
 }
 

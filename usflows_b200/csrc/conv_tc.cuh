@@ -270,6 +270,10 @@ inline size_t conv_tc_smem_bytes(int block_n, int K) {
 }
 
 extern int g_dbg_flags;
+// K-slabs (32 tf32 elements each) per TMEM accumulation chain of the convolution: 3 = 96 elements per chain (the chain
+// hand-over is what bounds the kernel: 388 us at 2, 363 us at 3, 356 us at 9 slabs for the 3x3 32->32 convolution; the
+// truncation bias of a 96-element chain is ~5e-7 relative, measured 5e-6 at 1024 elements)
+extern int g_conv_chunk_slabs;
 template <int BLOCK_N>
 int launch_conv_tc_cfg(const usf_linear_args* a, const ConvGeom& g, const Epilogue& ep, cudaStream_t st) {
   auto kern = convtc::conv_tc_kernel<BLOCK_N>;
@@ -286,7 +290,7 @@ int launch_conv_tc_cfg(const usf_linear_args* a, const ConvGeom& g, const Epilog
   const long long tiles = (a->M + tc::BLOCK_M - 1) / tc::BLOCK_M;
   const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
   kern<<<grid, convtc::conv_threads(BLOCK_N), smem, st>>>(mw, mwl, g.act, g.ld_act, a->M, g.H, g.W, g.Cin, g.ksize, g.dil, g.mask,
-                                                 g.relu_in, a->N, a->K, g_chunk_slabs, ep, g_dbg_flags, conv_tc_stages(BLOCK_N, a->K));
+                                                 g.relu_in, a->N, a->K, g_conv_chunk_slabs, ep, g_dbg_flags, conv_tc_stages(BLOCK_N, a->K));
   USF_CUDA_OK(cudaGetLastError());
   return USF_OK;
 }
