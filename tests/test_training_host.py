@@ -96,7 +96,7 @@ def test_fit_decreases_the_loss(fake_ops):
     assert float(-flow.log_prob(x).mean()) < l0        # the inference engine sees the updated weights
 
 
-def _dp_worker(rank, world, port, name, tmp):
+def _dp_worker(rank, world, port, name, tmp, rows=90):
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
 
@@ -107,27 +107,29 @@ def _dp_worker(rank, world, port, name, tmp):
     spec, params, arr = load_case(name)
     flow = build_flow(spec, params, device="cpu")
     np.random.seed(7)
-    data = torch.utils.data.TensorDataset(arr["x"][:90])
-    losses = flow.fit(data, optim=torch.optim.SGD, optim_params=dict(lr=1e-4), batch_size=30, gradient_clip=1.0,
-                      device="cpu", epochs=1)
+    data = torch.utils.data.TensorDataset(arr["x"][:rows])
+    losses = flow.fit(data, optim=torch.optim.SGD, optim_params=dict(lr=1e-4), batch_size=rows // 3 if rows >= 30 else rows // 2,
+                      gradient_clip=1.0, device="cpu", epochs=1)
     if rank == 0:
         torch.save({"losses": losses, "state": {k: v.clone() for k, v in flow.state_dict().items()}}, tmp)
     dist.barrier()
     dist.destroy_process_group()
 
 
-def test_data_parallel_fit_matches_single_process(fake_ops, tmp_path):
-    """world_size 2 over gloo: sharded batches + one gradient all-reduce == the single-process mean-loss step."""
-    name = "d6_hh_normal"
+@pytest.mark.parametrize("name,port,rows", [("d6_hh_normal", 29517, 90), ("img_c4_4x4", 29518, 24),
+                                            ("d64_convnet_proj_radial2", 29519, 40)])
+def test_data_parallel_fit_matches_single_process(fake_ops, tmp_path, name, port, rows):
+    """world_size 2 over gloo: sharded batches + one gradient all-reduce == the single-process mean-loss step (flat DenseNN
+    flow, image-shaped ConvNet2D flow, ConvNet conditioner with a radial base)."""
     out = str(tmp_path / "dp.pt")
-    mp.spawn(_dp_worker, args=(2, 29517, name, out), nprocs=2, join=True)
+    mp.spawn(_dp_worker, args=(2, port, name, out, rows), nprocs=2, join=True)
     got = torch.load(out)
     spec, params, arr = load_case(name)
     flow = build_flow(spec, params, device="cpu")
     np.random.seed(7)
-    data = torch.utils.data.TensorDataset(arr["x"][:90])
-    losses = flow.fit(data, optim=torch.optim.SGD, optim_params=dict(lr=1e-4), batch_size=30, gradient_clip=1.0,
-                      device="cpu", epochs=1, distributed=False)
+    data = torch.utils.data.TensorDataset(arr["x"][:rows])
+    losses = flow.fit(data, optim=torch.optim.SGD, optim_params=dict(lr=1e-4), batch_size=rows // 3 if rows >= 30 else rows // 2,
+                      gradient_clip=1.0, device="cpu", epochs=1, distributed=False)
     assert np.isfinite(losses[0])
     assert abs(losses[0] - got["losses"][0]) <= 1e-5 * max(1.0, abs(losses[0]))
     for k, v in flow.state_dict().items():
