@@ -1,5 +1,5 @@
-python -m pytest tests/test_gpu_parity.py -m gpu -q -k "host or chunk" 2>&1 | tail -15 > gpurun_out/r1t_pytest.log
-python - > gpurun_out/r1t_e2e.log 2>&1 <<'PY'
+python -m pytest tests/test_gpu_parity.py -m gpu -q -k "host or chunk" 2>&1 | tail -15 > gpurun_out/r1i_pytest.log
+python - > gpurun_out/r1i_e2e.log 2>&1 <<'PY'
 import os, sys, time
 sys.path.insert(0, os.getcwd()); sys.path.insert(0, os.path.join(os.getcwd(), "tests"))
 import torch
@@ -21,9 +21,13 @@ def timed(fn, n=10):
     torch.cuda.synchronize()
     return (time.perf_counter() - t0) / n * 1e3
 print(f"device log_prob: {timed(lambda: flow.log_prob(x)):.3f} ms")
-for growth, mx in ((1, 1), (2, 2), (2, 4), (2, 8), (3, 9), (4, 4), (4, 16)):
-    F.HOST_CHUNK_GROWTH, F.HOST_CHUNK_MAX_UNITS = growth, mx
+for units in ((1,), (1, 2), (1, 1, 2), (1, 1, 2, 3), (1, 1, 2, 2), (1, 1, 1, 2, 2), (1, 2, 4)):
+    F.HOST_CHUNK_UNITS = units
     ms = timed(lambda: flow.log_prob_host(x_host, out_host))
-    print(f"growth {growth} max {mx}: {ms:.3f} ms = {rows/ms/1e3:.2f} M rows/s")
+    print(f"chunk units {units}: {ms:.3f} ms = {rows/ms/1e3:.2f} M rows/s")
+F.HOST_CHUNK_UNITS = (1, 1, 2, 3)
+F.HOST_STAGE_BYTES = 0
+ms = timed(lambda: flow.log_prob_host(x_host, out_host))
+print(f"two-buffer ring, units (1, 1, 2, 3): {ms:.3f} ms = {rows/ms/1e3:.2f} M rows/s")
 PY
-cat gpurun_out/r1t_pytest.log | tail -5; cat gpurun_out/r1t_e2e.log
+cat gpurun_out/r1i_pytest.log | tail -5; cat gpurun_out/r1i_e2e.log

@@ -23,10 +23,11 @@ from .transforms import (BaseTransform, BlockAffineTransform, HouseholderTransfo
 SMALL_BATCH_GRAPH_ROWS = 4096   # `log_prob` on at most this many rows replays one captured CUDA graph (0 = off)
 HOST_CUDA_GRAPHS = True       # `log_prob_host`: replay one captured CUDA graph per full-size chunk
 HOST_CHUNK_ROWS = 16384      # rows per H2D copy / kernel batch of `log_prob_host` (copy i+1 overlaps compute i)
-HOST_CHUNK_GROWTH = 2        # `log_prob_host` chunk i+1 holds this many times the rows of chunk i (1 = uniform chunks) ...
-HOST_CHUNK_MAX_UNITS = 2     # ... up to this many times the first chunk.  Measured on C2 (65 536 rows, B200): uniform 7.11 ms,
-                             # x2 capped at 2 units 6.68 ms, x2 capped at 4 / 8 units 7.0 ms (a copy twice as long as the
-                             # kernels it hides under stalls them: a row copies only 1.4x faster than it computes)
+HOST_CHUNK_UNITS = (1, 1, 2, 3)   # `log_prob_host` chunk sizes in wave-aligned units (the last entry repeats).  Only the first
+                             # copy is exposed, later chunks may grow as fast as the copy stays ahead of the kernels: a C2
+                             # row copies 1.4x faster than it computes, so chunk k may hold ~1.4x the rows of chunk k-1.
+                             # Measured on C2 (65 536 rows, B200): uniform 7.11 ms, (1, 2, 2, ..) 6.68 ms, (1, 2, 4, ..) 7.0 ms
+HOST_STAGE_BYTES = 1 << 30   # the whole batch is staged on the device when it fits (copies run back to back); else a 2-buffer ring
 
 
 class _plain_stream_order:
@@ -250,28 +251,36 @@ class Flow(torch.nn.Module):
         # computes), so only the FIRST copy is exposed: start with the smallest wave-aligned chunk and let the later
         # ones grow (fewer kernel boundaries, fuller tails).  An explicit `chunk_rows` gives uniform chunks.
         unit = min(chunk_rows or _wave_aligned_chunk_rows(prog, dev), max(rows, 1))
-        sizes, left, cur = [], rows, unit
+        sizes, left = [], rows
         while left > 0:
-            take = min(cur, left)
+            mult = 1 if chunk_rows else HOST_CHUNK_UNITS[min(len(sizes), len(HOST_CHUNK_UNITS) - 1)]
+            take = min(unit * mult, left)
             if left - take < unit // 2:                  # do not leave a sliver for a last launch sequence
                 take = left
             sizes.append(take)
             left -= take
-            if not chunk_rows:
-                cur = min(cur * HOST_CHUNK_GROWTH, unit * HOST_CHUNK_MAX_UNITS)
         chunk = max(sizes) if sizes else unit
-        if getattr(self, "_host_bufs", None) is None or self._host_bufs[0].shape[0] < chunk \
-                or self._host_bufs[0].shape[1] != d or self._host_bufs[0].device != dev:
-            self._host_bufs = [torch.empty(chunk, d, dtype=torch.float32, device=dev) for _ in range(2)]
+        starts = [sum(sizes[:i]) for i in range(len(sizes))]
+        # staging: one device buffer per chunk (slices of one allocation holding the whole batch) when that fits -- the
+        # copies then run back to back on the copy stream, independent of the kernels --, else two buffers used in turn
+        whole = rows * d * 4 <= HOST_STAGE_BYTES
+        need = max(rows, 1) if whole else 2 * chunk
+        if getattr(self, "_host_stage", None) is None or self._host_stage.shape[0] < need \
+                or self._host_stage.shape[1] != d or self._host_stage.device != dev:
+            self._host_stage = torch.empty(need, d, dtype=torch.float32, device=dev)
             self._host_out = torch.empty(0, dtype=torch.float32, device=dev)
             self._copy_stream = torch.cuda.Stream(device=dev)
+        n_buf = max(1, len(sizes)) if whole else 2
+        if whole:
+            bufs = [self._host_stage[starts[i]:starts[i] + sizes[i]] for i in range(len(sizes))] or [self._host_stage[:0]]
+        else:
+            bufs = [self._host_stage[:chunk], self._host_stage[chunk:2 * chunk]]
         if self._host_out.numel() < rows:
             self._host_out = torch.empty(rows, dtype=torch.float32, device=dev)
         out_dev = self._host_out[:rows]
         main = torch.cuda.current_stream(dev)
-        copied = [torch.cuda.Event(), torch.cuda.Event()]
-        consumed = [torch.cuda.Event(), torch.cuda.Event()]
-        starts = [sum(sizes[:i]) for i in range(len(sizes))]
+        copied = [torch.cuda.Event() for _ in range(n_buf)]
+        consumed = [torch.cuda.Event() for _ in range(n_buf)]
         guarded = prog.mode == "fp32" and not prog.force_fallback       # fp16-split engine: range flag per chunk
         flags = torch.zeros(len(starts), dtype=torch.int32, device=dev) if guarded else None
 
@@ -290,7 +299,7 @@ class Flow(torch.nn.Module):
                 for _ in range(2):                        # a workspace that grew while capturing invalidates earlier graphs
                     for i in sorted(range(len(sizes)), key=lambda j: -sizes[j]):
                         if sizes[i] >= unit // 2:
-                            graphs[(i & 1, sizes[i])] = self._chunk_graph(prog, i & 1, self._host_bufs[i & 1][:sizes[i]], d)
+                            graphs[(i % n_buf, sizes[i])] = self._chunk_graph(prog, i % n_buf, bufs[i % n_buf][:sizes[i]], d)
                     if all(g["gen"] == engine._workspace.generation for g in graphs.values()):
                         break
                 for g in graphs.values():
@@ -299,14 +308,15 @@ class Flow(torch.nn.Module):
             self._copy_stream.wait_stream(main)
             for i, r0 in enumerate(starts):
                 r1 = r0 + sizes[i]
-                buf = self._host_bufs[i & 1][: r1 - r0]
+                slot = i % n_buf
+                buf = bufs[slot][: r1 - r0]
                 with torch.cuda.stream(self._copy_stream):
-                    if i >= 2:
-                        self._copy_stream.wait_event(consumed[i & 1])
+                    if i >= n_buf:
+                        self._copy_stream.wait_event(consumed[slot])
                     buf.copy_(x2[r0:r1], non_blocking=True)
-                    copied[i & 1].record(self._copy_stream)
-                main.wait_event(copied[i & 1])
-                g = None if graphs is None else graphs.get((i & 1, sizes[i]))
+                    copied[slot].record(self._copy_stream)
+                main.wait_event(copied[slot])
+                g = None if graphs is None else graphs.get((slot, sizes[i]))
                 if g is not None:
                     # one graph launch replaces the ~23 kernel launches of the chunk: the host-side launch cost
                     # (~40 us per launch through ctypes + tensor-map encoding) is what bounds small chunks otherwise
@@ -316,7 +326,7 @@ class Flow(torch.nn.Module):
                     prog.run(buf, chunk_rows=chunk, sink=make_sink(r0),
                              flag_out=flags[i:i + 1] if guarded else None,
                              ladj_rows=None if row_ladj is None else row_ladj[r0:r1])
-                consumed[i & 1].record(main)
+                consumed[slot].record(main)
             if guarded:                                   # one sync; out-of-range chunks go through the tf32 split
                 redo = set(torch.nonzero(flags).reshape(-1).tolist())
                 if graphs and any(int(g["flag"].item()) != 0 for g in graphs.values() if g["flag"] is not None):
@@ -324,7 +334,7 @@ class Flow(torch.nn.Module):
                 for i in sorted(redo):
                     r0 = starts[i]
                     r1 = r0 + sizes[i]
-                    buf = self._host_bufs[0][: r1 - r0]
+                    buf = bufs[i % n_buf][: r1 - r0]
                     buf.copy_(x2[r0:r1])
                     if row_ladj is not None:
                         row_ladj[r0:r1].zero_()
