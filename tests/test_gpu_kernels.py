@@ -132,6 +132,23 @@ def test_triangular_inverse_and_lu_prep(d):
     assert float(out2[1]) == 0
 
 
+def test_reference_known_answer_triangular_solve():
+    """The reference's own triangular-solve test (tests/veriflow/linalg_test.py:7-20: all-ones lower / upper triangular
+    10 x 10 systems, 10 random right-hand sides, tolerance 1e-5), through the kernels that replace the triangular
+    solves on this path: X = T^-1 by usf_tri_inverse, then x = X y as a contraction."""
+    from usflows_b200 import ops
+    torch.manual_seed(0)
+    x = torch.stack([torch.rand(10) for _ in range(10)])
+    for lower in (True, False):
+        M = torch.tril(torch.ones(10, 10)) if lower else torch.triu(torch.ones(10, 10))
+        y = torch.stack([M @ xi for xi in x])
+        X = torch.empty(10, 10, device="cuda")
+        ops.tri_inverse(M.cuda(), lower, False, X)
+        got = torch.empty(10, 10, device="cuda")
+        ops.linear(ops.ENGINE_SIMT, ops.Act(10, 10, f32=y.cuda()), X, None, 10, 10, out=ops.Act(10, 10, f32=got))
+        assert bool(((got.cpu() - x).abs() < 1e-5).all())
+
+
 def test_householder_and_transpose():
     from usflows_b200 import ops
     g = torch.Generator().manual_seed(3)
