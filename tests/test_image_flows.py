@@ -153,7 +153,7 @@ def test_im2col_kernel_matches_conv(geom, fmt):
 @pytest.mark.gpu
 @pytest.mark.parametrize("fmt", ["f32", "h16", "tf32"])
 @pytest.mark.parametrize("geom", [(300, 7, 7, 32, 32, 3, 1), (64, 7, 7, 16, 32, 3, 1), (17, 5, 3, 16, 20, 3, 1), (9, 8, 8, 16, 64, 3, 1),
-                                  (11, 9, 6, 32, 12, 3, 2), (5, 4, 4, 32, 16, 3, 1), (2000, 7, 7, 32, 32, 3, 1), (3, 6, 5, 64, 8, 1, 1)])
+                                  (11, 9, 6, 32, 12, 3, 2), (5, 4, 4, 32, 16, 3, 1), (2000, 7, 7, 32, 32, 3, 1), (3, 6, 5, 64, 8, 1, 1), (4, 6, 6, 16, 16, 5, 1)])
 def test_implicit_gemm_convolution_matches_conv2d(geom, fmt):
     """usf_conv2d_rows (A tiles gathered into shared memory, tcgen05 tf32 split) == F.conv2d(padding='same') in fp64 on
     the same (masked, rectified) input, with bias and ReLU in the epilogue; ragged last tile, K tails, border pixels."""

@@ -1,0 +1,86 @@
+"""Seeded sweep over randomly drawn flow configurations (flat and image-shaped events, every conditioner and base family,
+with / without conjugation, Householder, gating, LayerNorm, mask types): the launch planner on the emulated backend and the
+exportable reference semantics against the CPU oracle.  Host logic only (no GPU); the oracle itself is pinned against the
+real reference by tests/test_oracle.py."""
+import random
+
+import pytest
+import torch
+
+from helpers import build_flow, rel_err
+from oracle import flow_oracle as O
+
+
+def _draw(seed: int):
+    rng = random.Random(seed)
+    image = rng.random() < 0.4
+    spec = dict(coupling_blocks=rng.randint(1, 3), affine_conjugation=rng.random() < 0.6, lu_transform=rng.randint(1, 2),
+                householder=rng.choice([0, 0, 1, 2]), masktype=rng.choice(["checkerboard", "channel"]) if image else "checkerboard")
+    if image:
+        spec["in_dims"] = [rng.choice([4, 6, 8, 16]), rng.randint(3, 6), rng.randint(3, 6)]
+        spec.update(conditioner="convnet2d", c_hidden=rng.choice([4, 8, 16]), num_layers=rng.randint(1, 3),
+                    kernel_size=rng.choice([1, 3, 3, 5]), gating=rng.random() < 0.7, normalize_layers=rng.random() < 0.7)
+    else:
+        d = rng.choice([8, 12, 16, 24, 40])
+        spec["in_dims"] = [d]
+        if rng.random() < 0.5:
+            widths = [rng.choice([8, 16, 24]) for _ in range(rng.randint(1, 3))]
+            spec.update(conditioner="convnet", c_hidden=widths, gating=rng.random() < 0.7,
+                        normalize_layers=rng.random() < 0.7)
+        else:
+            spec["hidden_dims"] = [rng.choice([8, 16, 32]) for _ in range(rng.randint(1, 3))]
+    base = rng.choice(["laplace", "normal", "radial", "radial"])
+    spec["base"] = base
+    if base == "radial":
+        spec.update(p=rng.choice([1, 2, "inf"]), norm=rng.choice(["lognormal", "gammamm"]), n_comp=rng.randint(2, 9))
+    return spec
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_random_configuration_matches_oracle(fake_ops, seed):
+    spec = _draw(seed)
+    params = O.random_params(spec, 1000 + seed)
+    g = torch.Generator().manual_seed(seed)
+    n = 9
+    x = torch.rand(n, *spec["in_dims"], generator=g)
+    z0 = torch.randn(n, *spec["in_dims"], generator=g)
+    want_lp = O.flow_log_prob(x, spec, params, dtype=torch.float64)
+    want_z = O.flow_backward(x, spec, params, dtype=torch.float64)
+    want_y = O.flow_forward(z0, spec, params, dtype=torch.float64)
+    e_lp = rel_err(O.flow_log_prob(x, spec, params), want_lp)
+    e_z = rel_err(O.flow_backward(x, spec, params), want_z)
+    e_y = rel_err(O.flow_forward(z0, spec, params), want_y)
+    for mode in ("fp32_simt", "fp32"):
+        flow = build_flow(spec, params, device="cpu", precision=mode)
+        assert rel_err(flow.log_prob(x), want_lp) <= 3 * e_lp + 2e-5, (spec, mode)
+        assert rel_err(flow.backward(x), want_z) <= 3 * e_z + 5e-5, (spec, mode)
+        assert rel_err(flow._forward(z0), want_y) <= 3 * e_y + 5e-5, (spec, mode)
+        assert flow.sample([3]).shape == (3, *spec["in_dims"])
+    module = flow.reference_module("log_prob")
+    assert rel_err(module(x), want_lp) <= 3 * e_lp + 2e-5, spec
+    assert rel_err(flow.reference_module("backward")(x), want_z) <= 3 * e_z + 5e-5, spec
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", range(24))
+def test_random_configuration_matches_oracle_on_gpu(seed):
+    """The same sweep through the C ABI on the device (default fp32 mode and the tf32-split engine)."""
+    spec = _draw(seed)
+    params = O.random_params(spec, 1000 + seed)
+    g = torch.Generator().manual_seed(seed)
+    n = 300
+    x = torch.rand(n, *spec["in_dims"], generator=g)
+    z0 = torch.randn(n, *spec["in_dims"], generator=g)
+    want_lp = O.flow_log_prob(x, spec, params, dtype=torch.float64)
+    want_z = O.flow_backward(x, spec, params, dtype=torch.float64)
+    want_y = O.flow_forward(z0, spec, params, dtype=torch.float64)
+    e_lp = rel_err(O.flow_log_prob(x, spec, params), want_lp)
+    e_z = rel_err(O.flow_backward(x, spec, params), want_z)
+    e_y = rel_err(O.flow_forward(z0, spec, params), want_y)
+    for mode in ("fp32", "fp32_tf32"):
+        flow = build_flow(spec, params, precision=mode)
+        assert rel_err(flow.log_prob(x.cuda()), want_lp) <= 3 * e_lp + 1e-5, (spec, mode)
+        assert rel_err(flow.backward(x.cuda()), want_z) <= 3 * e_z + 3e-5, (spec, mode)
+        assert rel_err(flow._forward(z0.cuda()), want_y) <= 3 * e_y + 3e-5, (spec, mode)
+    s = flow.sample([5])
+    assert s.shape == (5, *spec["in_dims"]) and bool(torch.isfinite(s).all())
