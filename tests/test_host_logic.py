@@ -184,3 +184,25 @@ def test_tiny_flows_run_as_one_launch(fake_ops, name, fused):
             assert rel_err(flow2._forward(arr["z0"]), flow._forward(arr["z0"])) < 2e-5
         finally:
             engine.FUSE_SMALL = True
+
+
+def test_replicas_of_the_row_shard_driver_are_independent_and_keep_the_aliasing(fake_ops):
+    """parallel.replicate: a replica shares no storage with the source flow, keeps the InverseTransform <-> block parameter
+    aliasing (flows.py:469-470) and evaluates to the same bits; row blocks cover every row once."""
+    from usflows_b200 import parallel
+    spec, params, arr = load_case("d100_h50_hh")
+    flow = build_flow(spec, params, device="cpu", precision="fp32")
+    want = flow.log_prob(arr["x"])                                   # fills the caches a replica must not copy
+    rep = parallel.replicate(flow, "cpu")
+    assert torch.equal(rep.log_prob(arr["x"]), want)
+    src = {id(p): n for n, p in flow.named_parameters()}
+    for n, p in rep.named_parameters():
+        assert id(p) not in src and p.data_ptr() != dict(flow.named_parameters())[n].data_ptr()
+    inv = [l for l in rep.layers if type(l).__name__ == "InverseTransform"]
+    assert inv and all(any(l.transform is b for b in rep.layers) for l in inv)          # aliasing preserved
+    with torch.no_grad():
+        next(rep.parameters()).add_(0.25)
+    assert torch.equal(flow.log_prob(arr["x"]), want)                 # the source is untouched
+    for n, world in ((10, 3), (7, 8), (0, 2), (65536, 8)):
+        cuts = [parallel.shard_bounds(n, r, world) for r in range(world)]
+        assert cuts[0][0] == 0 and cuts[-1][1] == n and all(a[1] == b[0] for a, b in zip(cuts, cuts[1:]))

@@ -206,9 +206,13 @@ def test_radial_sample_properties(p, norm):
         assert bool(((v / r[:, None]).max(-1).values - 1).abs().max() < 1e-5)
     else:
         assert abs(float((v > 0).double().mean()) - 0.5) < 0.002
-    torch.manual_seed(1234)
-    base._seed_offset = 0
+    x_next = base.sample([n])                        # the next call draws from another Philox stream ...
+    assert not torch.equal(x_next, x)
+    other = _radial_module(spec, params)             # ... and so does another object in the same process
+    assert not torch.equal(other.sample([n]), x) and not torch.equal(other.sample([n]), x_next)
+    torch.manual_seed(1234)                          # re-seeding reproduces the sequence of calls
     assert torch.equal(base.sample([n]), x)
+    assert torch.equal(other.sample([n]), x_next)
     assert base.sample().shape == (d,)               # sample_shape=None peels the sample dim (distributions.py:480-497)
     # log_prob of its own samples is finite and consistent with the oracle
     lp = base.log_prob(x[:512])

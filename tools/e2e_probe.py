@@ -3,7 +3,7 @@ import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import torch
-from helpers import build_flow
+from usflows_b200.builders import build_flow
 from oracle import flow_oracle as O
 import bench
 

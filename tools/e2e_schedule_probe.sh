@@ -3,7 +3,7 @@ python - > gpurun_out/r1i_e2e.log 2>&1 <<'PY'
 import os, sys, time
 sys.path.insert(0, os.getcwd()); sys.path.insert(0, os.path.join(os.getcwd(), "tests"))
 import torch
-from helpers import build_flow
+from usflows_b200.builders import build_flow
 from oracle import flow_oracle as O
 import bench
 from usflows_b200 import flows as F

@@ -4,7 +4,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import torch
 from usflows_b200 import flows
-from helpers import build_flow
+from usflows_b200.builders import build_flow
 from oracle import flow_oracle as O
 import bench
 for wl in ("c2", "c5"):

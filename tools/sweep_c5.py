@@ -19,7 +19,7 @@ import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
 import bench  # noqa: E402
-from helpers import build_flow  # noqa: E402
+from usflows_b200.builders import build_flow  # noqa: E402
 from oracle import flow_oracle as O  # noqa: E402   (parameters only)
 
 

@@ -5,7 +5,7 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import torch
 import usflows_b200 as U
 from usflows_b200 import training
-from helpers import build_flow
+from usflows_b200.builders import build_flow
 from oracle import flow_oracle as O
 import bench
 spec = bench.WORKLOADS["c2"]["spec"]

@@ -1,0 +1,48 @@
+"""Construction of a `USFlow` from a plain spec dict -- the shape vocabulary `bench.py`, `__graft_entry__.smoke()`, the
+tools and the tests share (in_dims, coupling_blocks, hidden_dims | conditioner/c_hidden, base, ...; SURVEY 8d lists the
+BASELINE configurations in these terms).  Mirrors what the reference's experiment configs do through
+`config["model_cfg"]["type"](**params)` (src/usflows/explib/hyperopt.py:101-102)."""
+from __future__ import annotations
+
+import torch
+
+
+def build_flow(spec, params=None, device="cuda", precision=None):
+    """usflows_b200.USFlow of the given spec; `params` (a reference-layout state dict) is loaded when given."""
+    import usflows_b200 as U
+    d = spec["in_dims"][0]
+    ev = tuple(spec["in_dims"])
+    if spec.get("base") == "radial":
+        if spec["norm"] == "lognormal":
+            nd = U.LogNormal(torch.ones(1), torch.ones(1))
+        else:
+            K = spec.get("n_comp", 20)
+            nd = U.GammaMM(torch.ones(K), torch.ones(K), torch.ones(K) / K)
+        base = U.RadialDistribution(torch.zeros(*ev), nd, p=float("inf") if spec["p"] == "inf" else float(spec["p"]))
+    else:
+        base = (U.Laplace if spec.get("base", "laplace") == "laplace" else U.Normal)(torch.zeros(*ev), torch.ones(*ev))
+    if spec.get("conditioner") == "convnet2d":
+        cond_cls = U.ConvNet2D
+        cond_args = dict(c_in=d, c_hidden=spec["c_hidden"], num_layers=spec["num_layers"], padding="same",
+                         kernel_size=spec.get("kernel_size", 3), normalize_layers=spec.get("normalize_layers", True),
+                         gating=spec.get("gating", True))
+    elif spec.get("conditioner") == "convnet":
+        cond_cls = U.ConvNet
+        cond_args = dict(in_dims=[d], c_hidden=list(spec["c_hidden"]), gating=spec.get("gating", True),
+                         normalize_layers=spec.get("normalize_layers", True))
+    else:
+        cond_cls = U.DenseNN
+        cond_args = dict(input_dim=d, hidden_dims=list(spec["hidden_dims"]),
+                         param_dims=[d, d] if spec.get("coupling") == "affine" else [d])
+    flow = U.USFlow(
+        base_distribution=base, in_dims=list(spec["in_dims"]),
+        coupling_blocks=spec["coupling_blocks"], conditioner_cls=cond_cls,
+        conditioner_args=cond_args,
+        coupling=spec.get("coupling", "additive"),
+        prior_scale=1.0, lu_transform=spec.get("lu_transform", 1), householder=spec.get("householder", 1),
+        affine_conjugation=spec.get("affine_conjugation", False), masktype=spec.get("masktype", "checkerboard"),
+        precision=precision)
+    if params is not None:
+        res = flow.load_state_dict(params, strict=True)
+        assert not res.missing_keys and not res.unexpected_keys
+    return flow.to(device)

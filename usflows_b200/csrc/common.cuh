@@ -44,6 +44,15 @@ inline int fail(int code, const char* fmt, const char* a = "", const char* b = "
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 int num_sms();  // cached cudaDevAttrMultiProcessorCount of the current device
+// Function attributes (the opt-in dynamic shared memory size) are PER DEVICE: a process that drives several GPUs (the
+// row-shard driver usflows_b200.parallel) has to set them once on each.  Index of the current device for the
+// per-device "already set" tables of the launchers.
+constexpr int MAX_DEVICES = 64;
+inline int current_device_slot() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEVICES) return 0;
+  return dev;
+}
 
 // ---------------------------------------------------------------------------------------------
 // programmatic dependent launch: the kernels of one evaluation form a chain on one stream; with the attribute set, the

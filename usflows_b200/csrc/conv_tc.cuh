@@ -278,7 +278,8 @@ template <int BLOCK_N>
 int launch_conv_tc_cfg(const usf_linear_args* a, const ConvGeom& g, const Epilogue& ep, cudaStream_t st) {
   auto kern = convtc::conv_tc_kernel<BLOCK_N>;
   const size_t smem = conv_tc_smem_bytes(BLOCK_N, a->K);
-  static size_t attr_bytes = 0;
+  static size_t attr_bytes_dev[MAX_DEVICES] = {0};
+  size_t& attr_bytes = attr_bytes_dev[current_device_slot()];
   if (smem > attr_bytes) {
     USF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_bytes = smem;

@@ -130,7 +130,8 @@ int launch_flow_small_cfg(const float* x, long long ldx, long long rows, int d, 
                           int blob_floats, float* out, long long ldo, cudaStream_t st) {
   auto kern = flow_small_kernel<D, H, R>;
   const size_t smem = (size_t)blob_floats * sizeof(float);
-  static size_t attr_bytes = 0;
+  static size_t attr_bytes_dev[MAX_DEVICES] = {0};
+  size_t& attr_bytes = attr_bytes_dev[current_device_slot()];
   if (smem > 48 * 1024 && smem > attr_bytes) {
     USF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_bytes = smem;

@@ -396,7 +396,8 @@ inline int make_operand_map(CUtensorMap* map, const void* ptr, long long rows, l
 template <int BLOCK_N, int NTERMS, bool BF16>
 int launch_gemm_tc_cfg(const usf_linear_args* a, const Epilogue& ep, cudaStream_t st) {
   using C = tc::Config<BLOCK_N, NTERMS, BF16>;
-  static bool attr_set = false;
+  static bool attr_set_dev[MAX_DEVICES] = {false};
+  bool& attr_set = attr_set_dev[current_device_slot()];
   auto kern = tc::gemm_tc_kernel<BLOCK_N, NTERMS, BF16>;
   if (!attr_set) {
     USF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));

@@ -936,7 +936,8 @@ inline int make_store_map16(CUtensorMap* map, const void* ptr, long long rows, l
 template <int BLOCK_N, int NTERMS, int KIND>
 int launch_gemm_tc2_cfg(const usf_linear_args* a, const Epilogue& ep_in, cudaStream_t st) {
   using C = tc2::Config<BLOCK_N, NTERMS, KIND>;
-  static bool attr_set = false;
+  static bool attr_set_dev[MAX_DEVICES] = {false};
+  bool& attr_set = attr_set_dev[current_device_slot()];
   auto kern = tc2::gemm_tc2_kernel<BLOCK_N, NTERMS, KIND>;
   const int dt = KIND == tc2::KIND_TF32 ? 0 : KIND == tc2::KIND_BF16 ? 1 : 2;
   if (!attr_set) {

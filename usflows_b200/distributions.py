@@ -25,14 +25,13 @@ class DistributionModule(Module):
     def __init__(self, n_batch_dims: int = 0):
         super().__init__()
         self.n_batch_dims = n_batch_dims
-        self._seed_offset = 0
 
     # -- prepared parameters (scale = softplus(scale_unconstrained)), cached per weight version ------
     def _prepared(self):
         key = tuple((p.data_ptr(), p._version) for p in (self.loc, self.scale_unconstrained))
         if getattr(self, "_prep_key", None) != key:
             ops.require_cuda(self.loc, "base_distribution.loc")
-            with torch.no_grad():
+            with torch.no_grad(), ops.on_device(self.loc):
                 raw = self.scale_unconstrained.detach()
                 if raw.dim() == 0:                                 # scalar scale expands to loc's shape (:228-232)
                     raw = raw.expand_as(self.loc)
@@ -165,7 +164,8 @@ class _RadiusDistribution(Module):
 def _softplus_vec(raw: torch.Tensor) -> torch.Tensor:
     raw = raw.detach().reshape(-1).contiguous()
     out = torch.empty_like(raw)
-    ops.softplus(raw, out)
+    with ops.on_device(raw):
+        ops.softplus(raw, out)
     return out
 
 
@@ -242,7 +242,6 @@ class RadialDistribution(Module):
         self.n_batch_dims = n_batch_dims
         self.dim = int(math.prod(loc.shape[n_batch_dims:]))
         self.shape = loc.shape
-        self._seed_offset = 0
         self.to(device)
 
     @property

@@ -778,13 +778,18 @@ def _flatten_rows(x: torch.Tensor, event_ndim: int = 1):
 def run_layers(layers, direction: str, x: torch.Tensor, mode: Optional[str] = None,
                chunk_rows: Optional[int] = None) -> torch.Tensor:
     x2, batch_shape = _flatten_rows(x)
-    with torch.no_grad():
+    with torch.no_grad(), ops.on_device(x2):
         y = Program(layers, direction, mode).run(x2, chunk_rows=chunk_rows)
     return y.reshape(*batch_shape, y.shape[-1]) if x.dim() != 2 else y
 
 
 def run_mlp(net, x: torch.Tensor, mode: Optional[str] = None) -> torch.Tensor:
     """Plain evaluation of a DenseNN (no mask, no residual) through the contraction kernels."""
+    with ops.on_device(x):
+        return _run_mlp(net, x, mode)
+
+
+def _run_mlp(net, x, mode):
     x2, batch_shape = _flatten_rows(x)
     mode = mode or _default_precision
     lin = list(net.layers)
@@ -799,7 +804,7 @@ def run_mlp(net, x: torch.Tensor, mode: Optional[str] = None) -> torch.Tensor:
         steps.append(Step("mm", src="x" if j == 0 else "h", dst="x" if last else "h", w=w, w_lo=w_lo, N=N, K=K,
                           engine=eng, bias=l.bias.detach().contiguous(), relu=not last, final=last))
     prog = Program.from_steps(steps, mode)
-    with torch.no_grad():
+    with torch.no_grad(), ops.on_device(x2):
         y = prog.run(x2)
     return y.reshape(*batch_shape, y.shape[-1]) if x.dim() != 2 else y
 
@@ -823,7 +828,8 @@ def base_log_prob(base, z: torch.Tensor, add_const: float = 0.0) -> torch.Tensor
     z2 = z2.contiguous()
     out = torch.empty(z2.shape[0], dtype=torch.float32, device=z2.device)
     if z2.shape[0]:                                             # empty batch: nothing to launch
-        base._density_into(Act(z2.shape[0], d, f32=z2), add_const, out)
+        with ops.on_device(z2):
+            base._density_into(Act(z2.shape[0], d, f32=z2), add_const, out)
     return out.reshape(batch_shape)
 
 
@@ -834,10 +840,40 @@ def base_sample(base, sample_shape=None) -> torch.Tensor:
     rows = max(1, math.prod(shape))
     d = math.prod(base.event_shape)
     out = torch.empty(rows, d, dtype=torch.float32, device=base._prepared()[0].device)
-    seed = int(torch.initial_seed())
-    base._seed_offset += 1
-    base._sample_into(out, seed, base._seed_offset)
+    seed, offset = philox_call_stream(out.device)
+    with ops.on_device(out):
+        base._sample_into(out, seed, offset)
     return out.reshape(*shape, *base.event_shape)
+
+
+class _Salt(__import__("threading").local):
+    value = 0
+
+
+philox_salt = _Salt()            # thread-local: the row-shard driver (parallel.py) gives every device its own stream family
+PHILOX_CALL_STRIDE = 0x1000      # the kernels derive sub-streams at offset + [0, 0x200): calls must not overlap there
+_philox_calls = 0                # fallback call counter (non-CUDA devices: the emulated backend of the CPU tests)
+
+
+def philox_call_stream(device) -> tuple:
+    """(seed, offset) of the Philox stream of ONE sampling call.  Taken from torch's CUDA generator of the device so that
+    `torch.manual_seed(s)` reproduces samples and every call in the process -- of any flow / distribution object --
+    draws from its own stream: the generator's offset advances by 4 per call (it is a process-global, monotonically
+    increasing counter that a re-seed resets), and the call index is spread by PHILOX_CALL_STRIDE because the kernels
+    use offset + small constants for their sub-streams (radius, rejection rounds, extremal coordinate)."""
+    global _philox_calls
+    device = torch.device(device)
+    if device.type == "cuda":
+        gen = torch.cuda.default_generators[device.index if device.index is not None else torch.cuda.current_device()]
+        seed, off = int(gen.initial_seed()), int(gen.get_offset())
+        gen.set_offset(off + 4)
+        call = off // 4
+    else:
+        seed, call = int(torch.initial_seed()), _philox_calls
+        _philox_calls += 1
+    if philox_salt.value:
+        seed = (seed ^ (philox_salt.value * 0x9E3779B97F4A7C15)) & ((1 << 64) - 1)
+    return seed, (call * PHILOX_CALL_STRIDE) & ((1 << 62) - 1)
 
 
 def leaky_relu_ladj(x: torch.Tensor, alpha: float) -> torch.Tensor:
@@ -912,6 +948,11 @@ def _convnet_weights(desc: dict) -> list:
 
 def run_conditioner(net, x: torch.Tensor, mode: Optional[str] = None) -> torch.Tensor:
     """Plain evaluation of a `nn.ConvNet` (no mask, no residual) through the same kernels a coupling uses."""
+    with ops.on_device(x):
+        return _run_conditioner(net, x, mode)
+
+
+def _run_conditioner(net, x, mode):
     x2, batch_shape = _flatten_rows(x)
     mode = mode or _default_precision
     desc = _convnet_desc(net)
@@ -920,6 +961,6 @@ def run_conditioner(net, x: torch.Tensor, mode: Optional[str] = None) -> torch.T
     steps = convnet_steps(mode, desc, *desc["first"], *desc["last"])
     steps[-1].final = True
     prog = Program.from_steps(steps, mode)
-    with torch.no_grad():
+    with torch.no_grad(), ops.on_device(x2):
         y = prog.run(x2)
     return y.reshape(*batch_shape, y.shape[-1]) if x.dim() != 2 else y

@@ -9,6 +9,7 @@ every USFlow layer) computed once per weight version.  CUDA 
 from __future__ import annotations
 
 import math
+import threading
 from typing import Any, Dict, Iterable, List, Literal, Optional, Type
 
 import torch
@@ -28,20 +29,29 @@ HOST_CHUNK_UNITS = (1, 1, 2, 3)   # `log_prob_host` chunk sizes in wave-aligned 
                              # row copies 1.4x faster than it computes, so chunk k may hold ~1.4x the rows of chunk k-1.
                              # Measured on C2 (65 536 rows, B200): uniform 7.11 ms, (1, 2, 2, ..) 6.68 ms, (1, 2, 4, ..) 7.0 ms
 HOST_STAGE_BYTES = 1 << 30   # the whole batch is staged on the device when it fits (copies run back to back); else a 2-buffer ring
+HOST_MAX_STAGE_SLICES = 8    # ... and when it needs at most this many chunks (one captured graph + result buffer per slice)
+
+
+_capture_lock = threading.Lock()     # one graph capture at a time per process (the launch-mode switch below is global)
 
 
 class _plain_stream_order:
     """Kernels captured into a CUDA graph are launched without programmatic dependent launch: inside a graph the
     programmatic edges bought nothing and cost 4% on the chunked host path (measured); on a plain stream they hide the
-    launch latency and the next kernel's prologue (-1.7% per step)."""
+    launch latency and the next kernel's prologue (-1.7% per step).  Holds the process-wide capture lock: the row-shard
+    driver (parallel.py) warms several devices up from several threads."""
 
     def __enter__(self):
         from . import _lib
+        _capture_lock.acquire()
         _lib.check(_lib.load().usf_debug_set_pdl(0))
 
     def __exit__(self, *exc):
         from . import _lib
-        _lib.check(_lib.load().usf_debug_set_pdl(1))
+        try:
+            _lib.check(_lib.load().usf_debug_set_pdl(1))
+        finally:
+            _capture_lock.release()
         return False
 
 
@@ -128,6 +138,10 @@ class Flow(torch.nn.Module):
         """log p(x) = base.log_prob(z) - sum_k log|det J_k|  (flows.py:225-245)."""
         if context is not None:
             raise NotImplementedError("usflows_b200: context-conditioned evaluation is not built")
+        with ops.on_device(x):
+            return self._log_prob(x)
+
+    def _log_prob(self, x: torch.Tensor) -> torch.Tensor:
         prog, ladj = self._program("backward")
         base = self._base_module()
         base._prepared()                  # parameter-side work happens here, outside any graph capture
@@ -166,10 +180,12 @@ class Flow(torch.nn.Module):
         encoding), not by the kernels: the launch program + base density of a given row count is captured ONCE into a CUDA
         graph over fixed staging buffers and replayed (input copied in, result cloned out).  Returns None when a value
         left the fp16 range (the caller then takes the launch-by-launch route, which handles the tf32-split re-run)."""
-        cache = self.__dict__.setdefault("_lp_graphs", {})
+        # the cache lives ON the Program (one Program per weight version and mode): graphs of a replaced weight version die
+        # with their Program instead of surviving under a recycled id() with dangling operand pointers
+        cache = prog.__dict__.setdefault("_lp_graphs", {})
         rows, d = x2.shape
         dev = x2.device
-        key = (id(prog), rows, str(dev))
+        key = (rows, str(dev))
         ent = cache.get(key)
         if ent is None or ent["gen"] != engine._workspace.generation:
             base = self._base_module()
@@ -188,11 +204,11 @@ class Flow(torch.nn.Module):
                 body()                                        # eager pass: sizes every workspace buffer before capture
                 torch.cuda.synchronize(dev)
                 graph = torch.cuda.CUDAGraph()
-                with _plain_stream_order(), torch.cuda.graph(graph):
+                with _plain_stream_order(), torch.cuda.graph(graph, capture_error_mode="thread_local"):
                     body()
             if len(cache) >= 8:                               # a few row counts per weight version; drop the oldest
                 cache.pop(next(iter(cache)))
-            ent = cache[key] = dict(graph=graph, x=xin, out=out, flag=flag, prog=prog, gen=engine._workspace.generation)
+            ent = cache[key] = dict(graph=graph, x=xin, out=out, flag=flag, gen=engine._workspace.generation)
         with torch.no_grad():
             ent["x"].copy_(x2)
             if ent["flag"] is not None:
@@ -204,8 +220,8 @@ class Flow(torch.nn.Module):
 
     def _chunk_graph(self, prog, slot: int, buf: torch.Tensor, d: int) -> dict:
         """CUDA graph of the launch program of one full-size chunk reading host-staging buffer `slot`."""
-        cache = self.__dict__.setdefault("_host_graphs", {})
-        key = (id(prog), slot, buf.data_ptr(), tuple(buf.shape))
+        cache = prog.__dict__.setdefault("_host_graphs", {})     # on the Program: see _log_prob_small_batch
+        key = (slot, buf.data_ptr(), tuple(buf.shape))
         ent = cache.get(key)
         if ent is not None and ent["gen"] == engine._workspace.generation:
             return ent
@@ -216,13 +232,13 @@ class Flow(torch.nn.Module):
         prog._run_chunk(buf, fin, flag)                   # eager pass: sizes every workspace buffer before capture
         torch.cuda.synchronize(dev)
         graph = torch.cuda.CUDAGraph()
-        with _plain_stream_order(), torch.cuda.graph(graph):
+        with _plain_stream_order(), torch.cuda.graph(graph, capture_error_mode="thread_local"):
             prog._run_chunk(buf, fin, flag)
         ent = dict(graph=graph, fin=fin, flag=flag, gen=engine._workspace.generation)
-        for k in [k for k in cache if k[1] == slot and (k[2] != key[2] or cache[k]["gen"] != ent["gen"])]:
+        for k in [k for k in cache if k[0] == slot and (k[1] != key[1] or cache[k]["gen"] != ent["gen"])]:
             del cache[k]                                  # graphs of a replaced staging buffer / of stale workspaces
-        while sum(1 for k in cache if k[1] == slot) >= 6:  # a few chunk sizes per staging buffer; drop the oldest
-            del cache[next(k for k in cache if k[1] == slot)]
+        while sum(1 for k in cache if k[0] == slot) >= 6:  # a few chunk sizes per staging buffer; drop the oldest
+            del cache[next(k for k in cache if k[0] == slot)]
         cache[key] = ent
         return ent
 
@@ -233,6 +249,10 @@ class Flow(torch.nn.Module):
         chunk i -- and the log-probs are copied back into `out_host`.  Returns `out_host`."""
         if x_host.is_cuda:
             raise RuntimeError("log_prob_host expects a host tensor; use log_prob for device tensors")
+        with ops.on_device(next(self.parameters())):
+            return self._log_prob_host(x_host, out_host, chunk_rows)
+
+    def _log_prob_host(self, x_host, out_host, chunk_rows):
         dev = next(self.parameters()).device
         prog, ladj = self._program("backward")
         base = self._base_module()
@@ -263,7 +283,7 @@ class Flow(torch.nn.Module):
         starts = [sum(sizes[:i]) for i in range(len(sizes))]
         # staging: one device buffer per chunk (slices of one allocation holding the whole batch) when that fits -- the
         # copies then run back to back on the copy stream, independent of the kernels --, else two buffers used in turn
-        whole = rows * d * 4 <= HOST_STAGE_BYTES
+        whole = rows * d * 4 <= HOST_STAGE_BYTES and len(sizes) <= HOST_MAX_STAGE_SLICES
         need = max(rows, 1) if whole else 2 * chunk
         if getattr(self, "_host_stage", None) is None or self._host_stage.shape[0] < need \
                 or self._host_stage.shape[1] != d or self._host_stage.device != dev:
@@ -353,9 +373,10 @@ class Flow(torch.nn.Module):
         if sample_shape is None:
             sample_shape = [1]
         shape = [int(s) for s in sample_shape]
-        z = self.base_distribution.sample(shape)
-        ev = len(self._event_shape())
-        y = self._run("forward", z.reshape(-1, *z.shape[z.dim() - ev:]))
+        with ops.on_device(next(self.parameters())):
+            z = self.base_distribution.sample(shape)
+            ev = len(self._event_shape())
+            y = self._run("forward", z.reshape(-1, *z.shape[z.dim() - ev:]))
         return y.reshape(*shape, *y.shape[1:])
 
     def fit(self, data_train, optim=None, optim_params: Optional[Dict[str, Any]] = None, batch_size: int = 32,
@@ -429,9 +450,9 @@ class Flow(torch.nn.Module):
         return hit[1], hit[2]
 
     def _run(self, direction: str, x: torch.Tensor) -> torch.Tensor:
-        prog, _ = self._program(direction)
         x2, batch_shape = engine._flatten_rows(x, len(self._event_shape()))
-        with torch.no_grad():
+        with torch.no_grad(), ops.on_device(x2):
+            prog, _ = self._program(direction)
             y = prog.run(x2)
         return y.reshape(*batch_shape, *self._event_shape())
 

@@ -24,6 +24,27 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+class on_device:
+    """Makes the device of `t` the current CUDA device for the duration of the block.  The C ABI launches on the
+    stream it is handed and has no device argument: `_stream()` is the current stream of the CURRENT device, so every
+    public entry point (Flow.log_prob / sample / ..., the layer and distribution methods) runs its launches inside
+    this guard -- a flow living on cuda:1 works while cuda:0 is current, as it does in the reference's plain PyTorch."""
+
+    def __init__(self, t):
+        dev = t.device if isinstance(t, torch.Tensor) else torch.device(t)
+        self._guard = torch.cuda.device(dev) if dev.type == "cuda" and torch.cuda.is_available() else None
+
+    def __enter__(self):
+        if self._guard is not None:
+            self._guard.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if self._guard is not None:
+            self._guard.__exit__(*exc)
+        return False
+
+
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 

@@ -334,8 +334,9 @@ def shard_bounds(n: int, rank: int, world: int):
 
 
 def allreduce_gradients(params: List[torch.nn.Parameter], group=None) -> int:
-    """One all-reduce(sum) over the flat fp32 gradient buffer; returns the number of floats exchanged.
-    Parameters without a gradient on this rank (an empty shard) contribute zeros."""
+    """One blocking all-reduce(sum) over the flat fp32 gradient buffer; returns the number of floats exchanged.
+    Parameters without a gradient on this rank (an empty shard) contribute zeros.  (`GradReducer` is the bucketed,
+    overlapped form `fit` and `TrainStep` use; this one stays as the simple reference for the tests.)"""
     import torch.distributed as dist
     params = [p for p in params if p.requires_grad]
     if not params:
@@ -354,10 +355,192 @@ def allreduce_gradients(params: List[torch.nn.Parameter], group=None) -> int:
     return off
 
 
+class GradReducer:
+    """Bucketed gradient all-reduce overlapped with the backward pass.
+
+    Parameters are grouped into buckets in REVERSE registration order -- the order in which the density pass's backward
+    produces their gradients: base density first, then the layers from the data end of the stack to the latent end.  A
+    post-accumulate-grad hook per parameter (it fires once per backward pass, after the contributions of a block and of
+    the InverseTransform that aliases it have been summed) copies the gradient into its bucket; the bucket that just
+    became complete goes out as ONE asynchronous all-reduce(sum) (NCCL on its own stream over NVLink / NVSwitch; gloo in
+    the CPU tests) while the backward pass keeps running.  `finish()` waits for the buckets in flight, sends the ones a
+    rank could not complete (parameters without a gradient contribute zeros, e.g. an empty shard) and copies the sums
+    back into `p.grad`.  The result equals `allreduce_gradients` bit for bit on two ranks (sum of two numbers)."""
+
+    def __init__(self, params, group=None, bucket_bytes: int = 16 << 20):
+        import torch.distributed as dist
+        self.dist, self.group = dist, group
+        self.params = [p for p in params if p.requires_grad]
+        self.buckets: List[dict] = []
+        cur, cur_bytes = [], 0
+        for p in reversed(self.params):
+            cur.append(p)
+            cur_bytes += p.numel() * 4
+            if cur_bytes >= bucket_bytes:
+                self.buckets.append(dict(params=cur))
+                cur, cur_bytes = [], 0
+        if cur:
+            self.buckets.append(dict(params=cur))
+        self._where = {}
+        for bi, b in enumerate(self.buckets):
+            n = sum(p.numel() for p in b["params"])
+            ref = b["params"][0]
+            b["flat"] = torch.zeros(n, dtype=torch.float32, device=ref.device)
+            b["views"], off = [], 0
+            for p in b["params"]:
+                b["views"].append(b["flat"][off:off + p.numel()].view_as(p))
+                self._where[id(p)] = (bi, len(b["views"]) - 1)
+                off += p.numel()
+            b["ready"], b["work"] = 0, None
+        self.floats = sum(b["flat"].numel() for b in self.buckets)
+        self.bytes_per_step = 4 * self.floats
+        self._armed = False
+        self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in self.params]
+
+    def close(self) -> None:
+        for h in self._hooks:
+            h.remove()
+        self._hooks = []
+
+    def begin(self) -> None:
+        """Arm the hooks for one backward pass."""
+        for b in self.buckets:
+            b["ready"], b["work"] = 0, None
+            b["filled"] = [False] * len(b["params"])
+        self._armed = True
+
+    def _launch(self, b) -> None:
+        b["work"] = self.dist.all_reduce(b["flat"], op=self.dist.ReduceOp.SUM, group=self.group, async_op=True)
+
+    def _on_grad(self, p) -> None:
+        if not self._armed:
+            return
+        bi, vi = self._where[id(p)]
+        b = self.buckets[bi]
+        if b["filled"][vi]:
+            return
+        b["views"][vi].copy_(p.grad)
+        b["filled"][vi] = True
+        b["ready"] += 1
+        if b["ready"] == len(b["params"]):
+            self._launch(b)
+
+    def finish(self) -> int:
+        """Complete the exchange of this step; returns the number of floats all-reduced."""
+        self._armed = False
+        for b in self.buckets:
+            if b["work"] is None:                       # incomplete on this rank: missing gradients are zeros
+                for vi, p in enumerate(b["params"]):
+                    if not b["filled"][vi]:
+                        if p.grad is None:
+                            b["views"][vi].zero_()
+                        else:
+                            b["views"][vi].copy_(p.grad)
+                self._launch(b)
+        for b in self.buckets:
+            b["work"].wait()
+            for p, v in zip(b["params"], b["views"]):
+                if p.grad is None:
+                    p.grad = v.clone()
+                else:
+                    p.grad.copy_(v)
+        return self.floats
+
+
+class TrainStep:
+    """One maximum-likelihood step of `Flow.fit` (flows.py:195-207) as a reusable object: zero_grad, density pass and its
+    backward on the library's kernels, the (overlapped) gradient all-reduce when a process group is given, optimiser
+    step, and the invertibility check as a DEVICE counter (`infeasible` accumulates the number of zero diagonal / scale
+    entries seen after each step; the caller reads it when it wants to, not once per step).  `global_rows` is the size of
+    the global batch (the loss is the global mean, so shard gradients add up to the single-process gradient)."""
+
+    def __init__(self, flow, opt, group=None, distributed: Optional[bool] = None, gradient_clip: Optional[float] = None):
+        import torch.distributed as dist
+        self.flow, self.opt, self.group, self.clip = flow, opt, group, gradient_clip
+        if distributed is None:
+            distributed = dist.is_available() and dist.is_initialized()
+        self.distributed = distributed
+        self.rank = dist.get_rank(group) if distributed else 0
+        self.world = dist.get_world_size(group) if distributed else 1
+        self.params = [p for p in flow.parameters()]
+        self.reducer = GradReducer(self.params, group) if distributed and self.world > 1 else None
+        dev = self.params[0].device
+        self.infeasible = torch.zeros((), dtype=torch.float32, device=dev)
+        self.allreduce_bytes = self.reducer.bytes_per_step if self.reducer is not None else 0
+
+    def close(self) -> None:
+        if self.reducer is not None:
+            self.reducer.close()
+
+    def step(self, sample: torch.Tensor, global_rows: Optional[int] = None) -> torch.Tensor:
+        """Runs the step on this rank's shard `sample` [rows, ...]; returns this rank's share of the loss (a device
+        scalar: the sum over ranks is the global mean loss)."""
+        flow = self.flow
+        rows = sample.shape[0]
+        total = global_rows if global_rows is not None else rows * self.world
+        self.opt.zero_grad()
+        if self.reducer is not None:
+            self.reducer.begin()
+        if rows > 0:
+            loss = -log_prob_autograd(flow, sample).sum() / total
+            if self.rank == 0:                          # the prior is a function of the weights only: count it once
+                prior = flow.log_prior()
+                if isinstance(prior, torch.Tensor) or prior != 0:
+                    loss = loss - prior
+            loss.backward()
+            local = loss.detach()
+        else:
+            local = torch.zeros((), device=self.params[0].device)
+        if self.reducer is not None:
+            self.reducer.finish()
+        if self.clip is not None:
+            torch.nn.utils.clip_grad_norm_(self.params, self.clip)
+        self.opt.step()
+        self.infeasible += infeasible_count(flow)
+        return local
+
+
+def infeasible_count(flow) -> torch.Tensor:
+    """Number of zero entries on the U diagonals / in the scale vectors of the flow's layers as a device scalar (the
+    reference's `is_feasible`, transforms.py:150-152, 1347-1349, without the per-layer host synchronisation)."""
+    from . import transforms as T
+    tot = None
+    seen = set()
+
+    def visit(t):
+        nonlocal tot
+        if id(t) in seen:
+            return
+        seen.add(id(t))
+        if isinstance(t, T.InverseTransform):
+            visit(t.transform)
+        elif isinstance(t, T.BlockAffineTransform):
+            visit(t.block_transform)
+        elif isinstance(t, T.SequentialAffineTransform):
+            for s in t.transforms:
+                visit(s)
+        elif isinstance(t, T.LUTransform):
+            c = (t.U_raw.detach().diagonal() == 0).sum()
+            tot = c if tot is None else tot + c
+        elif isinstance(t, T.ScaleTransform):
+            c = (t.scale.detach() == 0).sum()
+            tot = c if tot is None else tot + c
+
+    for layer in flow.layers:
+        visit(layer)
+    if tot is None:
+        return torch.zeros((), dtype=torch.float32, device=next(flow.parameters()).device)
+    return tot.to(torch.float32)
+
+
 def fit(flow, data_train, optim=None, optim_params: Optional[Dict[str, Any]] = None, batch_size: int = 32,
         shuffle: bool = True, gradient_clip: Optional[float] = None, device=None, epochs: int = 1,
-        distributed: Optional[bool] = None, group=None, max_steps: Optional[int] = None) -> List[float]:
-    """Reference-compatible `Flow.fit` (flows.py:113-210); `batch_size` is the GLOBAL batch when distributed."""
+        distributed: Optional[bool] = None, group=None, max_steps: Optional[int] = None,
+        feasibility_every: int = 16) -> List[float]:
+    """Reference-compatible `Flow.fit` (flows.py:113-210); `batch_size` is the GLOBAL batch when distributed.  The
+    invertibility check of flows.py:204-205 runs on the device after every step and is READ every `feasibility_every`
+    steps and at the end of every epoch (one host synchronisation per that many steps instead of one per layer per
+    step); the losses stay on the device until the epoch ends."""
     import torch.distributed as dist
     from .optim import SophiaG
     if flow.soft_training:
@@ -370,46 +553,48 @@ def fit(flow, data_train, optim=None, optim_params: Optional[Dict[str, Any]] = N
     opt = optim(params, **optim_params) if optim_params is not None else optim(params)
     if distributed is None:
         distributed = dist.is_available() and dist.is_initialized()
-    rank = dist.get_rank(group) if distributed else 0
-    world = dist.get_world_size(group) if distributed else 1
+    ts = TrainStep(model, opt, group=group, distributed=distributed, gradient_clip=gradient_clip)
+    rank, world = ts.rank, ts.world
+
+    def check_feasible():
+        if float(ts.infeasible) != 0:                                                  # flows.py:204-205
+            raise RuntimeError("Model is not invertible")
 
     N = len(data_train)
     epoch_losses: List[float] = []
     steps = 0
-    for _ in range(epochs):
-        losses = []
-        perm = np.random.choice(N, N, replace=False) if shuffle else np.arange(N)     # flows.py:160
-        if distributed:                                  # every rank walks the same permutation
-            pt = torch.from_numpy(perm).to(device if torch.device(device).type == "cuda" else "cpu")
-            dist.broadcast(pt, src=0, group=group)
-            perm = pt.cpu().numpy()
-        data = data_train[perm] if isinstance(data_train, torch.Tensor) else data_train[perm][0]
-        if not isinstance(data, torch.Tensor):
-            data = torch.as_tensor(np.asarray(data), dtype=torch.float32)
-        for idx in range(0, N, batch_size):
-            end = min(idx + batch_size, N)
-            lo, hi = shard_bounds(end - idx, rank, world)
-            sample = data[idx + lo:idx + hi].to(device=device, dtype=torch.float32)
-            opt.zero_grad()
-            if hi > lo:
-                loss = -log_prob_autograd(model, sample).sum() / (end - idx) - model.log_prior()
-                loss.backward()
-                local = loss.detach()
-            else:
-                local = torch.zeros((), device=device)
-            if distributed:
-                allreduce_gradients(params, group)
-                dist.all_reduce(local, op=dist.ReduceOp.SUM, group=group)
-            losses.append(float(local))
-            if gradient_clip is not None:
-                torch.nn.utils.clip_grad_norm_(params, gradient_clip)
-            opt.step()
-            if not model.is_feasible():                                                # flows.py:204-205
-                raise RuntimeError("Model is not invertible")
-            steps += 1
-            if max_steps is not None and steps >= max_steps:
-                break
-        epoch_losses.append(float(np.mean(losses)) if losses else float("nan"))
-        if max_steps is not None and steps >= max_steps:
-            break
+    try:
+        with ops.on_device(params[0]):
+            for _ in range(epochs):
+                losses = []
+                perm = np.random.choice(N, N, replace=False) if shuffle else np.arange(N)     # flows.py:160
+                if distributed:                                  # every rank walks the same permutation
+                    pt = torch.from_numpy(perm).to(device if torch.device(device).type == "cuda" else "cpu")
+                    dist.broadcast(pt, src=0, group=group)
+                    perm = pt.cpu().numpy()
+                data = data_train[perm] if isinstance(data_train, torch.Tensor) else data_train[perm][0]
+                if not isinstance(data, torch.Tensor):
+                    data = torch.as_tensor(np.asarray(data), dtype=torch.float32)
+                for idx in range(0, N, batch_size):
+                    end = min(idx + batch_size, N)
+                    lo, hi = shard_bounds(end - idx, rank, world)
+                    sample = data[idx + lo:idx + hi].to(device=device, dtype=torch.float32)
+                    losses.append(ts.step(sample, global_rows=end - idx))
+                    steps += 1
+                    if steps % max(1, feasibility_every) == 0:
+                        check_feasible()
+                    if max_steps is not None and steps >= max_steps:
+                        break
+                check_feasible()
+                if losses:
+                    tot = torch.stack(losses)
+                    if distributed and world > 1:               # one exchange per epoch: the per-step global losses
+                        dist.all_reduce(tot, op=dist.ReduceOp.SUM, group=group)
+                    epoch_losses.append(float(tot.mean()))
+                else:
+                    epoch_losses.append(float("nan"))
+                if max_steps is not None and steps >= max_steps:
+                    break
+    finally:
+        ts.close()
     return epoch_losses

@@ -103,7 +103,8 @@ class ScaleTransform(BaseTransform):
         if getattr(self, "_ladj_key", None) != key:
             ops.require_cuda(self.scale, "ScaleTransform.scale")
             out = torch.empty(2, dtype=torch.float32, device=self.scale.device)
-            ops.vec_logabs(self.scale.detach().reshape(-1), out)
+            with ops.on_device(out):
+                ops.vec_logabs(self.scale.detach().reshape(-1), out)
             self._ladj_cache, self._ladj_key = out, key
         return self._ladj_cache
 
@@ -186,7 +187,7 @@ class AffineTransform(BaseTransform):
         if getattr(self, "_prep_key", None) != key:
             for p in self._prep_params():
                 ops.require_cuda(p, f"{type(self).__name__} parameter")
-            with torch.no_grad():
+            with torch.no_grad(), ops.on_device(self._prep_params()[0]):
                 self._prep_cache = self._prepare()
             self._prep_key = key
         return self._prep_cache
@@ -503,7 +504,7 @@ class MaskedCoupling(BaseTransform):
             dev = params[0].device
             m = self.mask.to(dev).reshape(-1).to(torch.float32).contiguous()
             inv = (1 - m).contiguous()
-            with torch.no_grad():
+            with torch.no_grad(), ops.on_device(dev):
                 ws = [l.weight.detach() for l in lin]
                 bs = [l.bias.detach() for l in lin]
                 w_first = torch.empty_like(ws[0])
