@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define USF_ABI_VERSION 3
+#define USF_ABI_VERSION 4
 
 #define USF_OK 0
 #define USF_ERR_INVALID (-1)     /* bad argument (shape, alignment, null pointer) */
@@ -115,6 +115,13 @@ typedef struct usf_linear_args {
   void* out_l16;
   int64_t ld_16;
   int32_t* overflow_flag; /* device int, set to 1 if a value written to out_h16 exceeds the fp16 range */
+  /* ABI 4.  split_k > 1 (CTA-pair tcgen05 engines only; ignored elsewhere): the contraction over K is cut into up to
+   * split_k pieces that run on different CTA pairs and are summed into out_f32 with vector reductions -- for products
+   * with a small output and a long K, i.e. the weight gradients dW[N_w, K_w] = dY^T . X of the training pass
+   * (reference: autograd of F.linear, flows.py:199).  Requires out_f32 (16-byte aligned, ld_f32 % 4 == 0, N % 8 == 0)
+   * as the only output and no bias / relu / residual / colscale / postsub; the library zero-fills out_f32 first. */
+  int32_t split_k;
+  int32_t reserved0;
 } usf_linear_args;
 
 int usf_linear(const usf_linear_args* args, void* stream);
@@ -312,6 +319,56 @@ int usf_matmul_f64(const double* A, int64_t lda, const double* B, int64_t ldb, d
 
 /* out[j] = softplus(in[j])  (distributions.py:211-215, base scale parameterisation) */
 int usf_softplus(const float* in, int64_t n, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Training step (ABI 4).  Replaces what torch autograd does behind Flow.fit's loss.backward() (flows.py:199):
+ * the batch-side products dX = dY . W and dW = dY^T . X are usf_linear calls (dW with split_k); these entries are the
+ * passes between them and the weight-side algebra of LUTransform (transforms.py:1271-1293 and its derivative).
+ * ------------------------------------------------------------------------------------------------ */
+/* One pass over a [rows, n] matrix given as fp16 split planes (h, l) or as fp32 (src_f32, when h == NULL):
+ *   value <- 0 where mask_h[r, j] <= 0 (ReLU backward: mask_h = hi plane of the saved post-ReLU activation);
+ *   value <- sign * value;  out planes [rows, n] (may alias the input);  t planes = the TRANSPOSE [n, rows] (the K-major
+ *   operand of dW = dY^T . X);  colsum[j] += sum_r value (bias gradient);  colsum2[j] += sum_r value * mul[r, j].
+ * Every output is optional.  n % 8 == 0, 16-byte aligned planes, pitches multiples of 16 bytes. */
+typedef struct usf_glue_args {
+  const void* h; const void* l; int64_t ld;
+  const float* src_f32; int64_t ld_src;
+  int64_t rows; int32_t n; int32_t reserved0;
+  const void* mask_h; int64_t ld_mask;
+  float sign; int32_t reserved1;
+  void* out_h; void* out_l; int64_t ld_out;
+  void* t_h; void* t_l; int64_t ld_t;
+  float* colsum;
+  const float* mul; int64_t ld_mul;
+  float* colsum2;
+  int32_t* overflow_flag;
+} usf_glue_args;
+int usf_planes_glue(const usf_glue_args* args, void* stream);
+
+/* g = d(-log p(z)) / dz of the Laplace / Normal base density (distributions.py:199-238), un-normalised, as fp16 split
+ * planes g [rows, d] and (optional) transposed planes t [d, rows]; dloc[j] += sum_r d(-log p)/dloc_j,
+ * dscale[j] += sum_r d(-log p)/dscale_j (scale = softplus'ed).  d % 8 == 0. */
+int usf_base_backward(const float* z, int64_t ldz, int64_t rows, int32_t d, const float* loc, const float* scale,
+                      int32_t kind, void* g_h, void* g_l, int64_t ld_g, void* t_h, void* t_l, int64_t ld_t,
+                      float* dloc, float* dscale, void* stream);
+
+/* Weight-side copy: out[i, j] = scale * S[ri(i), cj(j)] with S = src (transpose = 0) or src^T (1); row_idx / col_idx are
+ * optional int32 gather indices; written as fp32 (out_f32) and / or fp16 split operand planes (out_h, out_l). */
+int usf_mat_prep(const float* src, int64_t ld_src, int32_t rows, int32_t cols, int32_t transpose, const int32_t* row_idx,
+                 const int32_t* col_idx, float scale, float* out_f32, int64_t ld_f32, void* out_h, void* out_l,
+                 int64_t ld_16, int32_t* overflow_flag, void* stream);
+
+/* out = scale * (strict lower part of src, mode 0 | upper part incl. diagonal, mode 1) [+ coef / diag_src[i, i] on the
+ * diagonal, mode 1]: the gradient masks of LUTransform (transforms.py:1209-1213) and d(sum log|diag U|)/dU. */
+int usf_tri_mask(const float* src, int64_t ld_src, int32_t d, int32_t mode, float scale, const float* diag_src,
+                 int64_t ld_diag, float coef, float* out, int64_t ld_out, void* stream);
+
+/* Inverses of a stack of n_mats (<= 32) lower-triangular [d, d] matrices (pitch ld, matrix stride mat_stride floats) by
+ * recursive block doubling; bit m of unit_mask: matrix m has an implicit unit diagonal (L of LUTransform).  X and tmp are
+ * stacks of the same geometry (tmp: scratch).  Replaces torch.inverse(L) / torch.inverse(U) (transforms.py:1291-1292) for
+ * all layers of a flow in 1 + 2 log2(d / 64) launches. */
+int usf_tri_inverse_batched(const float* T, float* X, float* tmp, int32_t d, int64_t ld, int64_t mat_stride,
+                            int32_t n_mats, uint32_t unit_mask, void* stream);
 
 #ifdef __cplusplus
 }

@@ -358,6 +358,95 @@ def matmul_f64(a, b, out):
     out.copy_(a @ b)
 
 
+# ---- training step (emulation of the "Training step" entries of include/usflows_b200.h) -------------------------------
+def linear_splitk(engine, a_t, w_t, N, K, out, split_k):
+    CALLS.append(("linear_splitk", a_t.rows, N, K, split_k))
+    assert engine == ENGINE_TC_3XF16 and a_t.h16.shape == (a_t.rows, K) and w_t.h16.shape == (N, K)
+    A, W = f16_join(a_t.h16, a_t.l16), f16_join(w_t.h16, w_t.l16)
+    out.copy_(A @ W.T)
+
+
+def planes_glue(src, *, rows, n, mask_h=None, sign=1.0, out=None, t=None, colsum=None, mul=None, colsum2=None,
+                overflow_flag=None):
+    CALLS.append(("planes_glue", rows, n))
+    if isinstance(src, Act):
+        h, l = src.h16.clone(), src.l16.clone()
+    else:
+        h, l = f16_split(src)
+        if overflow_flag is not None and bool((~(src.abs() <= 65000.0)).any()):
+            overflow_flag.fill_(1)
+    assert h.shape == (rows, n)
+    if mask_h is not None:
+        keep = mask_h.float() > 0
+        h, l = h * keep, l * keep
+    if sign < 0:
+        h, l = -h, -l
+    if out is not None:
+        out.h16.copy_(h)
+        out.l16.copy_(l)
+    if t is not None:
+        t.h16.copy_(h.t())
+        t.l16.copy_(l.t())
+    v = f16_join(h, l)
+    if colsum is not None:
+        colsum.add_(v.sum(0))
+    if colsum2 is not None:
+        colsum2.add_((v * mul).sum(0))
+
+
+def base_backward(z, loc, scale, kind, g, t, dloc, dscale):
+    CALLS.append(("base_backward",))
+    zz = z - loc
+    if kind == real_ops.BASE_LAPLACE:
+        gv = zz.sign() / scale
+        ds = 1 / scale - zz.abs() / scale ** 2
+    else:
+        gv = zz / scale ** 2
+        ds = 1 / scale - zz ** 2 / scale ** 3
+    h, l = f16_split(gv)
+    g.h16.copy_(h)
+    g.l16.copy_(l)
+    if t is not None:
+        t.h16.copy_(h.t())
+        t.l16.copy_(l.t())
+    if dloc is not None:
+        dloc.add_(-gv.sum(0))
+    if dscale is not None:
+        dscale.add_(ds.sum(0))
+
+
+def mat_prep(src, *, transpose=False, row_idx=None, col_idx=None, scale=1.0, out_f32=None, out=None, overflow_flag=None):
+    v = src.t() if transpose else src
+    if row_idx is not None:
+        v = v[row_idx.long()]
+    if col_idx is not None:
+        v = v[:, col_idx.long()]
+    v = scale * v
+    ref = out_f32 if out_f32 is not None else out.h16
+    v = v[:ref.shape[0], :ref.shape[1]]
+    if out_f32 is not None:
+        out_f32.copy_(v)
+    if out is not None:
+        h, l = f16_split(v)
+        out.h16.copy_(h)
+        out.l16.copy_(l)
+
+
+def tri_mask(src, mode, scale, out, diag_src=None, coef=0.0):
+    v = scale * (src.tril(-1) if mode == 0 else src.triu())
+    if diag_src is not None and mode == 1:
+        v = v + torch.diag(coef / diag_src.diagonal())
+    out.copy_(v)
+
+
+def tri_inverse_batched(T, X, tmp, unit_mask):
+    for m in range(T.shape[0]):
+        t = T[m].tril()
+        if (unit_mask >> m) & 1:
+            t = t.tril(-1) + torch.eye(t.shape[0])
+        X[m].copy_(torch.linalg.solve_triangular(t, torch.eye(t.shape[0]), upper=False))
+
+
 def require_cuda(t, name="tensor", dtype=torch.float32):
     return t
 
@@ -366,5 +455,6 @@ def install(monkeypatch):
     CALLS.clear()
     for name in ["conv2d_rows", "layout_transpose", "im2col", "masked_add", "radial_logprob", "radial_sample", "gate_norm", "affine_couple", "sub_rows", "flow_small", "linear", "ingest", "base_logprob", "base_sample", "leaky_relu", "permute", "lu_assemble",
                  "lu_logabsdet", "vec_logabs", "tri_inverse", "transpose", "scale_rows_cols", "split_tf32", "split_f16", "to_bf16",
-                 "householder_right", "softplus", "matmul_f32", "matmul_f64", "require_cuda"]:
+                 "householder_right", "softplus", "matmul_f32", "matmul_f64", "require_cuda", "linear_splitk", "planes_glue",
+                 "base_backward", "mat_prep", "tri_mask", "tri_inverse_batched"]:
         monkeypatch.setattr(real_ops, name, globals()[name])

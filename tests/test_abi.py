@@ -24,7 +24,7 @@ def test_header_symbols_are_exported_and_bound():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in the header but not exported"
         assert name in _lib.SIGNATURES, f"{name} has no ctypes signature in _lib.py"
-    assert lib.usf_abi_version() == 3
+    assert lib.usf_abi_version() == 4
 
 
 def test_planes_struct_layout_matches_header():
@@ -47,7 +47,18 @@ def test_linear_args_layout_matches_header():
     body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
     fields = re.findall(r"\b([A-Za-z_0-9]+);", body)
     assert fields == [f[0] for f in _lib.LinearArgs._fields_]
-    assert ctypes.sizeof(_lib.LinearArgs) == 8 + 4 * 4 + 6 * 8 + 8 + 4 + 4 + 3 * 8 + 2 * 8 + 2 * 8 + 3 * 8 + 2 * 8 + 7 * 8
+    assert ctypes.sizeof(_lib.LinearArgs) == 8 + 4 * 4 + 6 * 8 + 8 + 4 + 4 + 3 * 8 + 2 * 8 + 2 * 8 + 3 * 8 + 2 * 8 + 7 * 8 + 8
+
+
+def test_glue_args_layout_matches_header():
+    from usflows_b200 import _lib
+    with open(os.path.join(ROOT, "include", "usflows_b200.h")) as f:
+        text = f.read()
+    body = re.search(r"typedef struct usf_glue_args \{(.*?)\} usf_glue_args;", text, flags=re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    fields = re.findall(r"\b([A-Za-z_0-9]+);", body)
+    assert fields == [f[0] for f in _lib.GlueArgs._fields_]
+    assert ctypes.sizeof(_lib.GlueArgs) == 21 * 8
 
 
 def test_invalid_arguments_fail_loudly_without_gpu():

@@ -276,3 +276,137 @@ def test_tma_store_path_equals_inline_store(M, N, K):
         assert torch.equal(outs[0].h16, q.h16) and torch.equal(outs[0].l16, q.l16)
     ref = x0.double() - (a.double() @ w.double().T + bias.double().cpu())
     assert rel_err(outs[0].h16.double() + outs[0].l16.double() / 2048.0, ref) <= 2e-5
+
+
+# ---- training-step kernels (ABI 4) -----------------------------------------------------------------------------------
+def _f16_planes(t):
+    from usflows_b200 import ops
+    from usflows_b200.ops import Act
+    M, K = t.shape
+    buf = torch.zeros(2, M, ops.pad4(K), dtype=torch.float16, device="cuda")
+    a = Act(M, K, h16=buf[0, :, :K], l16=buf[1, :, :K])
+    src = torch.zeros(M, ops.pad4(K), device="cuda")[:, :K]
+    src.copy_(t)
+    ops.split_f16(src, a.h16, a.l16)
+    return a, (a.h16.double() + a.l16.double() / 2048.0).cpu()
+
+
+@pytest.mark.parametrize("n_out,k_out,rows,split", [(784, 784, 8192, 8), (1024, 392, 4096, 16), (392, 1024, 1000, 5),
+                                                    (64, 48, 300, 3), (256, 256, 77, 4), (784, 784, 8192, 1)])
+def test_split_k_weight_gradient_contraction(n_out, k_out, rows, split):
+    """dW[n, k] = sum_r dY[r, n] X[r, k] as usf_linear on the TRANSPOSED planes with the batch rows as K, cut into split_k
+    pieces that meet in fp32 memory (red.global.add.v4.f32)."""
+    from usflows_b200 import ops
+    g = torch.Generator().manual_seed(rows + n_out)
+    dy = torch.randn(rows, n_out, generator=g)
+    x = torch.randn(rows, k_out, generator=g)
+    dyT, dy_used = _f16_planes(dy.t().contiguous())
+    xT, x_used = _f16_planes(x.t().contiguous())
+    out = torch.full((n_out, ops.pad4(k_out, 4)), 7.0, device="cuda")[:, :k_out]        # stale content must not survive
+    ops.linear_splitk(ops.ENGINE_TC_3XF16, dyT, xT, k_out, rows, out, split)
+    ref = dy_used @ x_used.t()
+    assert rel_err(out, ref) <= 3e-6
+    ops.linear_splitk(ops.ENGINE_TC_3XF16, dyT, xT, k_out, rows, out, split)           # same result on a second call
+    assert rel_err(out, ref) <= 3e-6
+
+
+@pytest.mark.parametrize("rows,n", [(8192, 784), (300, 392), (65, 64), (1000, 1024), (7, 40)])
+def test_planes_glue_mask_transpose_colsum(rows, n):
+    from usflows_b200 import ops
+    from usflows_b200.ops import Act
+    g = torch.Generator().manual_seed(rows + n)
+    v = torch.randn(rows, n, generator=g)
+    act = torch.relu(torch.randn(rows, n, generator=g))
+    mul = torch.randn(rows, n, generator=g)
+    src, v_used = _f16_planes(v)
+    mask, _ = _f16_planes(act)
+    new = lambda r, c: Act(r, c, h16=torch.zeros(r, ops.pad4(c), dtype=torch.float16, device="cuda")[:, :c],   # noqa: E731
+                           l16=torch.zeros(r, ops.pad4(c), dtype=torch.float16, device="cuda")[:, :c])
+    out, t = new(rows, n), new(n, rows)
+    cs, cs2 = torch.ones(n, device="cuda"), torch.zeros(n, device="cuda")
+    mulp = torch.zeros(rows, ops.pad4(n, 4), device="cuda")[:, :n]
+    mulp.copy_(mul)
+    ops.planes_glue(src, rows=rows, n=n, mask_h=mask.h16, sign=-1.0, out=out, t=t, colsum=cs, mul=mulp, colsum2=cs2)
+    want = -(v_used * (act > 0))
+    got = out.h16.double().cpu() + out.l16.double().cpu() / 2048.0
+    assert torch.equal(got, want)                                            # mask / sign are exact on the planes
+    got_t = t.h16.double().cpu() + t.l16.double().cpu() / 2048.0
+    assert torch.equal(got_t, want.t())
+    assert rel_err(cs, 1.0 + want.sum(0)) <= 1e-5                            # accumulates onto the existing content
+    assert rel_err(cs2, (want * mul.double()).sum(0)) <= 1e-5
+    # fp32 input, in place on planes, transposed only
+    t2 = new(n, rows)
+    vp = torch.zeros(rows, ops.pad4(n, 4), device="cuda")[:, :n]
+    vp.copy_(v)
+    ops.planes_glue(vp, rows=rows, n=n, t=t2)
+    assert torch.equal(t2.h16.double().cpu() + t2.l16.double().cpu() / 2048.0, v_used.t())
+
+
+@pytest.mark.parametrize("kind", [0, 1])
+def test_base_backward_matches_autograd(kind):
+    from usflows_b200 import ops
+    from usflows_b200.ops import Act
+    rows, d = 500, 96
+    g = torch.Generator().manual_seed(kind)
+    z = torch.randn(rows, d, generator=g) * 2
+    loc = torch.randn(d, generator=g) * 0.3
+    scale = torch.rand(d, generator=g) + 0.5
+    zz, ll, ss = z.double().requires_grad_(), loc.double().requires_grad_(), scale.double().requires_grad_()
+    dist = torch.distributions.Laplace(ll, ss) if kind == 0 else torch.distributions.Normal(ll, ss)
+    (-dist.log_prob(zz).sum()).backward()
+    new = lambda r, c: Act(r, c, h16=torch.zeros(r, ops.pad4(c), dtype=torch.float16, device="cuda")[:, :c],   # noqa: E731
+                           l16=torch.zeros(r, ops.pad4(c), dtype=torch.float16, device="cuda")[:, :c])
+    gp, tp = new(rows, d), new(d, rows)
+    dloc, dscale = torch.zeros(d, device="cuda"), torch.zeros(d, device="cuda")
+    zp = torch.zeros(rows, ops.pad4(d, 4), device="cuda")[:, :d]
+    zp.copy_(z)
+    ops.base_backward(zp, loc.cuda(), scale.cuda(), kind, gp, tp, dloc, dscale)
+    got = gp.h16.double().cpu() + gp.l16.double().cpu() / 2048.0
+    assert rel_err(got, zz.grad) <= 1e-6
+    assert torch.equal(tp.h16.cpu(), gp.h16.cpu().t()) and torch.equal(tp.l16.cpu(), gp.l16.cpu().t())
+    assert rel_err(dloc, ll.grad) <= 1e-5 and rel_err(dscale, ss.grad) <= 1e-5
+
+
+@pytest.mark.parametrize("d", [40, 64, 200, 784])
+def test_batched_triangular_inverse(d):
+    from usflows_b200 import ops
+    g = torch.Generator().manual_seed(d)
+    n = 6
+    T = torch.randn(n, d, d, generator=g).tril() / d ** 0.5
+    for m in range(n):
+        T[m].diagonal().copy_(torch.where(torch.rand(d, generator=g) < 0.5, -1.0, 1.0) * (0.5 + torch.rand(d, generator=g)))
+    junk = torch.randn(n, d, d, generator=g).triu(1)                   # content above the diagonal is ignored
+    Td = (T + junk).cuda()
+    X, tmp = torch.full_like(Td, 3.0), torch.zeros_like(Td)
+    unit_mask = 0b010101
+    ops.tri_inverse_batched(Td, X, tmp, unit_mask)
+    for m in range(n):
+        t = T[m].double()
+        if (unit_mask >> m) & 1:
+            t = t.tril(-1) + torch.eye(d, dtype=torch.float64)
+        want = torch.linalg.solve_triangular(t, torch.eye(d, dtype=torch.float64), upper=False)
+        assert rel_err(X[m], want) <= 1e-4 * max(1.0, float(torch.linalg.cond(t)) * 1e-3), m
+        assert float(X[m].triu(1).abs().max()) == 0.0
+
+
+def test_mat_prep_and_tri_mask():
+    from usflows_b200 import ops
+    from usflows_b200.ops import Act
+    g = torch.Generator().manual_seed(2)
+    src = torch.randn(50, 72, generator=g).cuda()
+    ri = torch.randperm(72, generator=g).to(torch.int32).cuda()
+    ci = torch.randperm(50, generator=g).to(torch.int32).cuda()
+    out = torch.zeros(72, 52, device="cuda")[:, :50]
+    pl = Act(72, 50, h16=torch.zeros(72, 56, dtype=torch.float16, device="cuda")[:, :50],
+             l16=torch.zeros(72, 56, dtype=torch.float16, device="cuda")[:, :50])
+    ops.mat_prep(src, transpose=True, row_idx=ri, col_idx=ci, scale=-2.0, out_f32=out, out=pl)
+    want = -2.0 * src.t()[ri.long()][:, ci.long()]
+    assert torch.equal(out, want)
+    assert rel_err(pl.h16.double() + pl.l16.double() / 2048.0, want) <= 1e-6
+    sq = torch.randn(40, 40, generator=g).cuda()
+    diag_src = (torch.randn(40, 40, generator=g) + 3 * torch.eye(40)).cuda()
+    o0, o1 = torch.zeros(40, 40, device="cuda"), torch.zeros(40, 40, device="cuda")
+    ops.tri_mask(sq, 0, 0.5, o0)
+    ops.tri_mask(sq, 1, 0.5, o1, diag_src=diag_src, coef=2.0)
+    assert torch.equal(o0, 0.5 * sq.tril(-1))
+    assert rel_err(o1, 0.5 * sq.triu() + torch.diag(2.0 / diag_src.diagonal())) <= 1e-6

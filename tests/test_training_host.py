@@ -96,6 +96,15 @@ def test_fit_decreases_the_loss(fake_ops):
     assert float(-flow.log_prob(x).mean()) < l0        # the inference engine sees the updated weights
 
 
+def _dp_case(name, rows):
+    """A golden fixture, or ("engine:<spec>") a flow inside the scope of the hand-written training pass."""
+    if not name.startswith("engine:"):
+        return load_case(name)
+    spec = ENGINE_SPECS[name.split(":", 1)[1]]
+    g = torch.Generator().manual_seed(8)
+    return spec, O.random_params(spec, 21), {"x": torch.rand(rows, spec["in_dims"][0], generator=g)}
+
+
 def _dp_worker(rank, world, port, name, tmp, rows=90):
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -104,7 +113,7 @@ def _dp_worker(rank, world, port, name, tmp, rows=90):
         def setattr(self, obj, attr, val):
             setattr(obj, attr, val)
     fake_backend.install(MP())
-    spec, params, arr = load_case(name)
+    spec, params, arr = _dp_case(name, rows)
     flow = build_flow(spec, params, device="cpu")
     np.random.seed(7)
     data = torch.utils.data.TensorDataset(arr["x"][:rows])
@@ -117,14 +126,15 @@ def _dp_worker(rank, world, port, name, tmp, rows=90):
 
 
 @pytest.mark.parametrize("name,port,rows", [("d6_hh_normal", 29517, 90), ("img_c4_4x4", 29518, 24),
-                                            ("d64_convnet_proj_radial2", 29519, 40)])
+                                            ("d64_convnet_proj_radial2", 29519, 40),
+                                            ("engine:conj_laplace_3layer", 29520, 99)])
 def test_data_parallel_fit_matches_single_process(fake_ops, tmp_path, name, port, rows):
     """world_size 2 over gloo: sharded batches + one gradient all-reduce == the single-process mean-loss step (flat DenseNN
     flow, image-shaped ConvNet2D flow, ConvNet conditioner with a radial base)."""
     out = str(tmp_path / "dp.pt")
     mp.spawn(_dp_worker, args=(2, port, name, out, rows), nprocs=2, join=True)
     got = torch.load(out)
-    spec, params, arr = load_case(name)
+    spec, params, arr = _dp_case(name, rows)
     flow = build_flow(spec, params, device="cpu")
     np.random.seed(7)
     data = torch.utils.data.TensorDataset(arr["x"][:rows])
@@ -144,3 +154,67 @@ def test_shard_bounds_cover_every_row_once():
             assert cuts[0][0] == 0 and cuts[-1][1] == n
             assert all(cuts[i][1] == cuts[i + 1][0] for i in range(world - 1))
             assert max(h - l for l, h in cuts) - min(h - l for l, h in cuts) <= 1
+
+
+def _compare_grads(flow, params, want, tol):
+    got = dict(flow.named_parameters())
+    checked = 0
+    for key, g in want.items():
+        if key not in got or got[key].grad is None:
+            continue
+        parts = key.split(".")
+        ref = g
+        if parts[0] == "trainable_layers" and parts[2] == "block_transform":
+            cand = ".".join([parts[0], str(int(parts[1]) + 2), "transform"] + parts[2:])
+            if cand in want and torch.equal(params[cand], params[key]):
+                ref = ref + want[cand]
+        if key.endswith("L_raw"):
+            ref = ref.tril(-1)
+        if key.endswith("U_raw"):
+            ref = ref.triu()
+        assert rel_err(got[key].grad, ref) <= tol, (key, rel_err(got[key].grad, ref))
+        checked += 1
+    return checked
+
+
+ENGINE_SPECS = {
+    "conj_normal": dict(in_dims=[64], coupling_blocks=2, hidden_dims=[64, 48], affine_conjugation=True, lu_transform=1,
+                        householder=0, base="normal"),
+    "conj_laplace_3layer": dict(in_dims=[48], coupling_blocks=3, hidden_dims=[40, 56, 32], affine_conjugation=True,
+                                lu_transform=1, householder=0, base="laplace"),
+    "noconj": dict(in_dims=[32], coupling_blocks=2, hidden_dims=[32, 32], affine_conjugation=False, lu_transform=1,
+                   householder=0, base="laplace"),
+}
+
+
+@pytest.mark.parametrize("name", list(ENGINE_SPECS))
+def test_hand_written_backward_matches_the_oracle(fake_ops, name):
+    """train_engine.TrainEngine (manual forward + backward, every contraction a C-ABI call) against autograd through the
+    oracle: loss and every parameter gradient."""
+    from usflows_b200 import train_engine
+    spec = ENGINE_SPECS[name]
+    params = O.random_params(spec, 21)
+    flow = build_flow(spec, params, device="cpu")
+    assert train_engine.supports(flow)
+    g = torch.Generator().manual_seed(4)
+    x = torch.rand(96, spec["in_dims"][0], generator=g)
+    eng = train_engine.TrainEngine(flow, 96)
+    loss = eng.step(x, 96)
+    want_loss, want = _oracle_grads(spec, params, x)
+    assert abs(float(loss) - want_loss) <= 2e-5 * max(1.0, abs(want_loss))
+    # (Laplace: a latent within rounding distance of loc may flip one sign; these seeds have none)
+    assert _compare_grads(flow, params, want, 2e-4) >= 6
+    # a second step on other rows re-uses every buffer
+    x2 = torch.rand(96, spec["in_dims"][0], generator=g)
+    loss2 = eng.step(x2, 96)
+    want_loss2, want2 = _oracle_grads(spec, params, x2)
+    assert abs(float(loss2) - want_loss2) <= 2e-5 * max(1.0, abs(want_loss2))
+    assert _compare_grads(flow, params, want2, 2e-4) >= 6
+    assert int(eng.flag) == 0
+
+
+def test_engine_scope(fake_ops):
+    from usflows_b200 import train_engine
+    for name, ok in (("d100_h50_hh", False), ("d6_hh_normal", False), ("d64_convnet", False)):
+        spec, params, _ = load_case(name)
+        assert train_engine.supports(build_flow(spec, params, device="cpu")) is ok

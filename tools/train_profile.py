@@ -13,11 +13,10 @@ flow = build_flow(spec, O.random_params(spec, 0), device="cuda", precision="fp32
 params = list(flow.parameters())
 opt = U.SophiaG(params, lr=1e-3, weight_decay=0.0)
 x = torch.rand(8192, 784, device="cuda")
+ts = training.TrainStep(flow, opt, distributed=False, engine=None if "--autograd" not in sys.argv else False)
+print("hand-written pass:", ts.use_engine)
 def step():
-    opt.zero_grad()
-    loss = -training.log_prob_autograd(flow, x).sum() / 8192
-    loss.backward()
-    opt.step()
+    ts.step(x)
 for _ in range(3): step()
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -34,6 +34,25 @@ class LinearArgs(C.Structure):
         ("resid_h16", C.c_void_p), ("resid_l16", C.c_void_p), ("ldr_16", C.c_int64),
         ("out_h16", C.c_void_p), ("out_l16", C.c_void_p), ("ld_16", C.c_int64),
         ("overflow_flag", C.c_void_p),
+        ("split_k", C.c_int32), ("reserved0", C.c_int32),
+    ]
+
+
+class GlueArgs(C.Structure):
+    """Mirror of `usf_glue_args` (include/usflows_b200.h)."""
+
+    _fields_ = [
+        ("h", C.c_void_p), ("l", C.c_void_p), ("ld", C.c_int64),
+        ("src_f32", C.c_void_p), ("ld_src", C.c_int64),
+        ("rows", C.c_int64), ("n", C.c_int32), ("reserved0", C.c_int32),
+        ("mask_h", C.c_void_p), ("ld_mask", C.c_int64),
+        ("sign", C.c_float), ("reserved1", C.c_int32),
+        ("out_h", C.c_void_p), ("out_l", C.c_void_p), ("ld_out", C.c_int64),
+        ("t_h", C.c_void_p), ("t_l", C.c_void_p), ("ld_t", C.c_int64),
+        ("colsum", C.c_void_p),
+        ("mul", C.c_void_p), ("ld_mul", C.c_int64),
+        ("colsum2", C.c_void_p),
+        ("overflow_flag", C.c_void_p),
     ]
 
 
@@ -91,6 +110,11 @@ SIGNATURES = {
     "usf_householder_right": (C.c_int, [_P, _I32, _I64, _P, _P, _P]),
     "usf_softplus": (C.c_int, [_P, _I64, _P, _P]),
     "usf_matmul_f64": (C.c_int, [_P, _I64, _P, _I64, _P, _I64, _I32, _I32, _I32, _P]),
+    "usf_planes_glue": (C.c_int, [C.POINTER(GlueArgs), _P]),
+    "usf_base_backward": (C.c_int, [_P, _I64, _I64, _I32, _P, _P, _I32, _P, _P, _I64, _P, _P, _I64, _P, _P, _P]),
+    "usf_mat_prep": (C.c_int, [_P, _I64, _I32, _I32, _I32, _P, _P, _F, _P, _I64, _P, _P, _I64, _P, _P]),
+    "usf_tri_mask": (C.c_int, [_P, _I64, _I32, _I32, _F, _P, _I64, _F, _P, _I64, _P]),
+    "usf_tri_inverse_batched": (C.c_int, [_P, _P, _P, _I32, _I64, _I64, _I32, C.c_uint32, _P]),
     "usf_debug_set_block_n": (C.c_int, [C.c_int]),
     "usf_set_accum_chunk": (C.c_int, [C.c_int]),
     "usf_set_accum_lead": (C.c_int, [C.c_int]),
@@ -122,7 +146,7 @@ def load():
         fn = getattr(lib, name)  # AttributeError if the ABI and this table disagree
         fn.restype = res
         fn.argtypes = args
-    if lib.usf_abi_version() != 3:
+    if lib.usf_abi_version() != 4:
         raise RuntimeError("usflows_b200: ABI version mismatch between _lib.py and the shared library")
     _lib = lib
     return lib

@@ -9,6 +9,7 @@
 #include "image.cuh"
 #include "prep.cuh"
 #include "radial.cuh"
+#include "train.cuh"
 
 namespace usf {
 
@@ -93,6 +94,7 @@ int make_epilogue(const usf_linear_args* a, Epilogue* ep) {
   ep->vec_ok = ok ? 1 : 0;
   ep->fast_store = 0;  // set by the pair-kernel launcher
   ep->async_store = 0;
+  ep->atomic_out = 0;
   return USF_OK;
 }
 
@@ -167,7 +169,10 @@ int usf_linear(const usf_linear_args* a, void* stream) {
     case USF_ENGINE_TC_3XTF32:
     case USF_ENGINE_TC_TF32:
     case USF_ENGINE_TC_BF16:
-    case USF_ENGINE_TC_3XF16: return launch_gemm_tc(a, ep, S(stream));
+    case USF_ENGINE_TC_3XF16:
+      if (a->split_k > 1 && (g_tc_impl == 2 || a->engine == USF_ENGINE_TC_3XF16) && a->M > 0 && a->N > 0)   // partial tiles are added: start from zero
+        USF_CUDA_OK(cudaMemset2DAsync(a->out_f32, (size_t)a->ld_f32 * 4, 0, (size_t)a->N * 4, (size_t)a->M, S(stream)));
+      return launch_gemm_tc(a, ep, S(stream));
   }
   return fail(USF_ERR_INVALID, "unknown engine%s%s");
 }
@@ -522,6 +527,82 @@ int usf_matmul_f64(const double* A, int64_t lda, const double* B, int64_t ldb, d
   matmul_f64_kernel<<<grid, 256, 0, S(stream)>>>(A, lda, B, ldb, C, ldc, M, N, K);
   USF_CUDA_OK(cudaGetLastError());
   return USF_OK;
+}
+
+int usf_planes_glue(const usf_glue_args* g, void* stream) {
+  USF_REQUIRE(g != nullptr, "null args");
+  GlueArgs a;
+  a.h = reinterpret_cast<const __half*>(g->h);
+  a.l = reinterpret_cast<const __half*>(g->l);
+  a.ld = g->ld;
+  a.src_f32 = g->src_f32;
+  a.ld_src = g->ld_src;
+  a.rows = g->rows;
+  a.n = g->n;
+  a.mask_h = reinterpret_cast<const __half*>(g->mask_h);
+  a.ld_mask = g->ld_mask;
+  a.sign = g->sign;
+  a.out_h = reinterpret_cast<__half*>(g->out_h);
+  a.out_l = reinterpret_cast<__half*>(g->out_l);
+  a.ld_out = g->ld_out;
+  a.t_h = reinterpret_cast<__half*>(g->t_h);
+  a.t_l = reinterpret_cast<__half*>(g->t_l);
+  a.ld_t = g->ld_t;
+  a.colsum = g->colsum;
+  a.mul = g->mul;
+  a.ld_mul = g->ld_mul;
+  a.colsum2 = g->colsum2;
+  a.overflow_flag = g->overflow_flag;
+  USF_REQUIRE(a.rows >= 0 && a.n >= 0, "negative extent");
+  USF_REQUIRE((a.h == nullptr) == (a.l == nullptr) && (a.out_h == nullptr) == (a.out_l == nullptr) &&
+                  (a.t_h == nullptr) == (a.t_l == nullptr), "planes come as (hi, lo) pairs");
+  USF_REQUIRE(a.rows < (1LL << 31) && (a.rows + GL_TILE - 1) / GL_TILE <= 65535, "planes glue: too many rows for one launch");
+  return launch_planes_glue(a, S(stream));
+}
+
+int usf_base_backward(const float* z, int64_t ldz, int64_t rows, int32_t d, const float* loc, const float* scale,
+                      int32_t kind, void* g_h, void* g_l, int64_t ld_g, void* t_h, void* t_l, int64_t ld_t, float* dloc,
+                      float* dscale, void* stream) {
+  USF_REQUIRE(z && loc && scale && g_h && g_l && rows >= 0 && d > 0 && d % 8 == 0, "bad input");
+  USF_REQUIRE(kind == USF_BASE_LAPLACE || kind == USF_BASE_NORMAL, "unknown base kind");
+  USF_REQUIRE((t_h == nullptr) == (t_l == nullptr), "planes come as (hi, lo) pairs");
+  USF_REQUIRE(aligned16(g_h) && aligned16(g_l) && ld_g % 8 == 0 && (!t_h || (aligned16(t_h) && aligned16(t_l) && ld_t % 8 == 0)),
+              "base backward: 16-byte aligned planes");
+  if (rows == 0) return USF_OK;
+  USF_REQUIRE((rows + GL_TILE - 1) / GL_TILE <= 65535, "base backward: too many rows for one launch");
+  dim3 grid((d + GL_TILE - 1) / GL_TILE, (unsigned)((rows + GL_TILE - 1) / GL_TILE));
+  base_backward_kernel<<<grid, 256, 0, S(stream)>>>(z, ldz, rows, d, loc, scale, kind, reinterpret_cast<__half*>(g_h),
+                                                    reinterpret_cast<__half*>(g_l), ld_g, reinterpret_cast<__half*>(t_h),
+                                                    reinterpret_cast<__half*>(t_l), ld_t, dloc, dscale);
+  USF_CUDA_OK(cudaGetLastError());
+  return USF_OK;
+}
+
+int usf_mat_prep(const float* src, int64_t ld_src, int32_t rows, int32_t cols, int32_t transpose, const int32_t* row_idx,
+                 const int32_t* col_idx, float scale, float* out_f32, int64_t ld_f32, void* out_h, void* out_l, int64_t ld_16,
+                 int32_t* overflow_flag, void* stream) {
+  USF_REQUIRE(src && rows > 0 && cols > 0 && (out_f32 || out_h), "bad input");
+  USF_REQUIRE((out_h == nullptr) == (out_l == nullptr), "planes come as (hi, lo) pairs");
+  USF_REQUIRE(src != out_f32, "mat_prep cannot run in place");
+  mat_prep_kernel<<<ew_grid((long long)rows * cols, 256), 256, 0, S(stream)>>>(
+      src, ld_src, rows, cols, transpose, row_idx, col_idx, scale, out_f32, ld_f32, reinterpret_cast<__half*>(out_h),
+      reinterpret_cast<__half*>(out_l), ld_16, overflow_flag);
+  USF_CUDA_OK(cudaGetLastError());
+  return USF_OK;
+}
+
+int usf_tri_mask(const float* src, int64_t ld_src, int32_t d, int32_t mode, float scale, const float* diag_src,
+                 int64_t ld_diag, float coef, float* out, int64_t ld_out, void* stream) {
+  USF_REQUIRE(src && out && d > 0 && (mode == 0 || mode == 1), "bad input");
+  tri_mask_kernel<<<ew_grid((long long)d * d, 256), 256, 0, S(stream)>>>(src, ld_src, d, mode, scale, diag_src, ld_diag, coef,
+                                                                         out, ld_out);
+  USF_CUDA_OK(cudaGetLastError());
+  return USF_OK;
+}
+
+int usf_tri_inverse_batched(const float* T, float* X, float* tmp, int32_t d, int64_t ld, int64_t mat_stride, int32_t n_mats,
+                            uint32_t unit_mask, void* stream) {
+  return launch_tri_inverse_batched(T, X, tmp, d, ld, mat_stride, n_mats, unit_mask, S(stream));
 }
 
 int usf_softplus(const float* in, int64_t n, float* out, void* stream) {

@@ -108,6 +108,7 @@ struct Epilogue {
   int* overflow_flag;  // set to 1 when a value written to the fp16 planes leaves the fp16 range
   int fast_store;      // pair kernel: aligned planes, N % 8 == 0: staged, coalesced 16-byte stores (else generic path)
   int async_store;     // pair kernel: fp16-split planes only -> staged boxes leave through TMA tensor stores
+  int atomic_out;      // pair kernel, split-K: partial tiles are ADDED to out_f32 (red.global.add.v4.f32)
 };
 
 constexpr float F16_LO_SCALE = 2048.f;          // 2^11: the low plane is stored scaled up so it stays normal

@@ -78,6 +78,23 @@ __device__ __forceinline__ int chain_count(int k_slabs, int chunk, int lead) {
   return l + (k_slabs - 2 * chunk * l + chunk - 1) / chunk;
 }
 
+// Work item of the persistent loop: output tile (m_blk, n_blk) x K range [ks_begin, ks_begin + nks) in K-slabs.  With
+// split_k > 1 (dW = dY^T . X of the training pass: a small output and a contraction over all batch rows) the K range of a
+// tile is cut into split_k pieces that run on different CTA pairs and meet in the fp32 output through red.global.add.
+struct TileCoord { long long m_blk; int n_blk; int ks_begin; int nks; };
+__device__ __forceinline__ TileCoord decode_tile(long long tile, int n_blocks, int split_k, int k_slabs) {
+  TileCoord t;
+  const int sk = (int)(tile % split_k);
+  const long long mn = tile / split_k;
+  t.m_blk = mn / n_blocks;
+  t.n_blk = (int)(mn % n_blocks);
+  const int per = (k_slabs + split_k - 1) / split_k;
+  t.ks_begin = sk * per;
+  const int rest = k_slabs - t.ks_begin;
+  t.nks = rest < per ? rest : per;     // > 0: the launcher keeps (split_k - 1) * per < k_slabs
+  return t;
+}
+
 constexpr int DBG_CHAINS = 512;   // timeline slots of a debug launch (usf_debug_gemm_timeline): 8 clock64 values each
 constexpr int KIND_TF32 = 0, KIND_BF16 = 1, KIND_F16 = 2;   // KIND_F16: fp16 split planes (x = hi + lo' 2^-11)
 
@@ -173,9 +190,15 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
 __device__ __forceinline__ void stg128(void* p, uint4 v) {
   asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
+// four fp32 values added to memory (split-K partial tiles): one vector reduction per 16 bytes
+__device__ __forceinline__ void red_add128(void* p, uint4 v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(__uint_as_float(v.x)), "f"(__uint_as_float(v.y)),
+               "f"(__uint_as_float(v.z)), "f"(__uint_as_float(v.w)) : "memory");
+}
 template <int RB>
 __device__ __forceinline__ void stage_copy_out(uint32_t stage, int lane, uint8_t* plane, long long ld_bytes,
-                                               long long row0, long long M, int col_bytes0, int n_bytes, int dbg_flags = 0) {
+                                               long long row0, long long M, int col_bytes0, int n_bytes, int dbg_flags = 0,
+                                               bool atomic = false) {
   // plane + row * ld_bytes + col_bytes0 is the first byte of the box in global memory; n_bytes = row length in bytes
   constexpr int CPR = RB / 16, ROWS_PER_IT = 32 / CPR;
   const int chunk = lane % CPR, rsub = lane / CPR;
@@ -186,7 +209,10 @@ __device__ __forceinline__ void stage_copy_out(uint32_t stage, int lane, uint8_t
   for (int it = 0; it < CPR; ++it) t[it] = lds128(stage + stage_off<RB>(it * ROWS_PER_IT + rsub, chunk));
 #pragma unroll
   for (int it = 0; it < CPR; ++it)
-    if (row0 + it * ROWS_PER_IT + rsub < M && !(dbg_flags & 8)) stg128(g + (long long)it * ROWS_PER_IT * ld_bytes, t[it]);
+    if (row0 + it * ROWS_PER_IT + rsub < M && !(dbg_flags & 8)) {
+      if (atomic) red_add128(g + (long long)it * ROWS_PER_IT * ld_bytes, t[it]);
+      else stg128(g + (long long)it * ROWS_PER_IT * ld_bytes, t[it]);
+    }
 }
 
 // The epilogue description, read ONCE per thread into registers.  Reading the fields from the kernel-parameter
@@ -204,7 +230,7 @@ struct EpiRegs {
   int ldr16, ld16, ldf32;    // row pitches in elements
 };
 constexpr uint32_t EF_BIAS = 1, EF_RELU = 2, EF_RESID16 = 4, EF_OUT16 = 8, EF_OUTF32 = 16, EF_RARE = 32, EF_RESID32 = 64,
-                   EF_OUTSPLIT = 128, EF_OUTBF16 = 256;
+                   EF_OUTSPLIT = 128, EF_OUTBF16 = 256, EF_ATOMIC = 512;
 
 template <class T>
 __device__ __forceinline__ T* launder_ptr(T* p) {   // opaque to the compiler: stays in a register pair
@@ -224,6 +250,7 @@ __device__ __forceinline__ EpiRegs load_epi_regs(const Epilogue& ep) {
   if (ep.out_hi) f |= EF_OUTSPLIT;
   if (ep.out_bf16) f |= EF_OUTBF16;
   if (ep.colscale || ep.postsub) f |= EF_RARE;
+  if (ep.atomic_out) f |= EF_ATOMIC;
   asm volatile("" : "+r"(f));
   r.flags = f;
   r.sign = ep.resid_sign;
@@ -368,7 +395,8 @@ __device__ __forceinline__ void store_chunk(const Epilogue& ep, const EpiRegs& e
       sts128(stage + stage_off<RB>(lane, q), __float_as_uint(v[4 * q]), __float_as_uint(v[4 * q + 1]), __float_as_uint(v[4 * q + 2]),
              __float_as_uint(v[4 * q + 3]));
     __syncwarp();
-    stage_copy_out<RB>(stage, lane, reinterpret_cast<uint8_t*>(er.of32), (long long)er.ldf32 * 4, row0, M, n0 * 4, N * 4);
+    stage_copy_out<RB>(stage, lane, reinterpret_cast<uint8_t*>(er.of32), (long long)er.ldf32 * 4, row0, M, n0 * 4, N * 4, 0,
+                       (f & EF_ATOMIC) != 0);
     __syncwarp();
   }
   {
@@ -532,27 +560,35 @@ __device__ __forceinline__ void async_piece(const Epilogue& ep, const EpiRegs& e
 template <class C, int COLS>
 __device__ __forceinline__ void epilogue_loop(int col0, int quarter, int lane, uint32_t rank, uint32_t tmem_base,
                                               uint32_t tfull0, uint32_t tempty0_leader, uint8_t* stage_gen,
-                                              uint32_t stage, long long n_tiles, int n_blocks, int k_slabs, int chunk_slabs, int lead,
+                                              uint32_t stage, long long n_tiles, int n_blocks, int k_slabs, int split_k, int chunk_slabs, int lead,
                                               long long M, int N, const Epilogue& ep, unsigned long long* dbg, int dbg_flags,
                                               const StoreMaps& smaps) {
   constexpr int BLOCK_N = C::kBlockN;
   int acc = 0;
   uint32_t acc_phase = 0;
-  int n_chunks = chain_count(k_slabs, chunk_slabs, lead);
+  int n_chunks = chain_count(k_slabs, chunk_slabs, lead);   // (split_k == 1; recomputed per work item otherwise)
   int dbg_chain = 0;   // timeline slot (debug launches only: dbg != nullptr on one warp of cluster 0's leader)
   float* patch = reinterpret_cast<float*>(stage_gen);
   // everything the tile loop needs lives in registers from here on (opaque to the compiler): re-deriving these from
   // special registers / the parameter bank inside the loop costs a dependent S2R / LDC per use
   asm volatile("" : "+r"(stage), "+r"(tfull0), "+r"(tempty0_leader), "+r"(tmem_base));
   asm volatile("" : "+l"(M), "+r"(N), "+r"(lane), "+r"(quarter), "+r"(col0), "+r"(rank), "+r"(n_blocks), "+l"(n_tiles),
-               "+r"(n_chunks), "+r"(dbg_flags));
+               "+r"(n_chunks), "+r"(dbg_flags), "+r"(split_k), "+r"(k_slabs));
   const EpiRegs er = load_epi_regs(ep);
   const bool fast_store = ep.fast_store != 0;
   const bool async_store = ep.async_store != 0;
   uint32_t hand = 0;     // TMA store groups committed so far by this warp
   for (long long tile = cluster_id_x(); tile < n_tiles; tile += num_clusters_x()) {
-    const long long m_idx = (tile / n_blocks) * (2 * BLOCK_M) + rank * BLOCK_M;
-    const int n_idx = (int)(tile % n_blocks) * BLOCK_N;
+    long long m_blk = tile / n_blocks;
+    int n_blk = (int)(tile % n_blocks);
+    if (split_k > 1) {
+      const TileCoord tc = decode_tile(tile, n_blocks, split_k, k_slabs);
+      m_blk = tc.m_blk;
+      n_blk = tc.n_blk;
+      n_chunks = chain_count(tc.nks, chunk_slabs, lead);
+    }
+    const long long m_idx = m_blk * (2 * BLOCK_M) + rank * BLOCK_M;
+    const int n_idx = n_blk * BLOCK_N;
     if (COLS == 0) {  // nothing to own: still take part in the barrier protocol
       for (int c = 0; c < n_chunks; ++c) {
         mbar_wait(tfull0 + 8u * acc, acc_phase);
@@ -682,7 +718,7 @@ template <int BLOCK_N, int NTERMS, int KIND>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_a_lo,
                 const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_w_lo,
-                long long M, int N, int K, int chunk_slabs, int lead_chains, const __grid_constant__ Epilogue ep,
+                long long M, int N, int K, int chunk_slabs, int lead_chains, int split_k, const __grid_constant__ Epilogue ep,
                 const __grid_constant__ StoreMaps smaps, unsigned long long* dbg_buf, int dbg_flags) {
   using C = Config<BLOCK_N, NTERMS, KIND>;
   extern __shared__ uint8_t smem_raw[];
@@ -703,8 +739,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
   const uint32_t rank = cluster_ctarank();
   const int n_blocks = (N + BLOCK_N - 1) / BLOCK_N;
   const long long m_blocks = (M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
-  const long long n_tiles = m_blocks * n_blocks;
   const int k_slabs = (K + C::ELEMS_PER_SLAB - 1) / C::ELEMS_PER_SLAB;
+  if (split_k < 1) split_k = 1;
+  const long long n_tiles = m_blocks * n_blocks * split_k;
   if (chunk_slabs <= 0 || chunk_slabs > k_slabs) chunk_slabs = k_slabs;
   if (KIND == KIND_F16 && NTERMS == 3) chunk_slabs = 1;   // the 2^-11 rescale happens once per accumulation chain
   // the last tile of a tile row is only as wide as N needs (UMMA N is a run-time field of the instruction descriptor;
@@ -731,6 +768,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
   }
   tcgen05_fence_before();
+  __syncthreads();      // (orders the allocator's write of the TMEM base address for this CTA's readers: a plain CTA barrier,
+                        //  which compute-sanitizer's racecheck tracks -- it does not model barrier.cluster)
   cluster_sync_all();   // barriers of both CTAs initialised and visible before any remote arrive / TMA completion
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
@@ -747,14 +786,15 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         int stage = 0;
         uint32_t phase = 0;
         for (long long tile = cluster_id_x(); tile < n_tiles; tile += num_clusters_x()) {
-          const int m_idx = (int)(tile / n_blocks) * (2 * BLOCK_M) + (int)rank * BLOCK_M;
-          const int n_tile = (int)(tile % n_blocks) * BLOCK_N;
+          const TileCoord tc = decode_tile(tile, n_blocks, split_k, k_slabs);
+          const int m_idx = (int)tc.m_blk * (2 * BLOCK_M) + (int)rank * BLOCK_M;
+          const int n_tile = tc.n_blk * BLOCK_N;
           const int n_idx = n_tile + (int)rank * (tile_width(n_tile) >> 1);   // this CTA stages its half of the W rows
-          for (int ks = 0; ks < k_slabs; ++ks) {
+          for (int ks = 0; ks < tc.nks; ++ks) {
             mbar_wait(empty_bar(stage), phase ^ 1);
             const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
             const uint32_t sb = sa + C::NPLANES * C::A_TILE;
-            const int k_idx = ks * C::ELEMS_PER_SLAB;
+            const int k_idx = (tc.ks_begin + ks) * C::ELEMS_PER_SLAB;
             const uint32_t fb = mapa(full_bar(stage), 0);
             if (rank == 0) mbar_expect_tx(full_bar(stage), 2 * C::STAGE_BYTES);
             tma_load_2d_pair(sa, &tm_a, fb, k_idx, m_idx);
@@ -776,12 +816,14 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
       int dbg_chain = 0;
       unsigned long long* dbg_mma = (cluster_id_x() == 0 && lane == 0) ? dbg_buf : nullptr;
       for (long long tile = cluster_id_x(); tile < n_tiles; tile += num_clusters_x()) {
-        const uint32_t idesc = C::IDESC_NO_N | ((uint32_t)(tile_width((int)(tile % n_blocks) * BLOCK_N) >> 3) << 17);
-        const int lead = chain_lead(k_slabs, chunk_slabs, lead_chains);
+        const TileCoord tc = decode_tile(tile, n_blocks, split_k, k_slabs);
+        const uint32_t idesc = C::IDESC_NO_N | ((uint32_t)(tile_width(tc.n_blk * BLOCK_N) >> 3) << 17);
+        const int lead = chain_lead(tc.nks, chunk_slabs, lead_chains);
+        const int ks_last = k_slabs - 1 - tc.ks_begin;   // index (within this work item) of the K tail slab, if it is here
         int ks0 = 0;
-        for (int c = 0; ks0 < k_slabs; ++c) {
+        for (int c = 0; ks0 < tc.nks; ++c) {
           const int span = c < lead ? 2 * chunk_slabs : chunk_slabs;
-          const int ks1 = ks0 + span < k_slabs ? ks0 + span : k_slabs;
+          const int ks1 = ks0 + span < tc.nks ? ks0 + span : tc.nks;
           mbar_wait(tempty_bar(acc), acc_phase ^ 1);  // both CTAs' epilogues have drained this accumulator
           tcgen05_fence_after();
           if (dbg_mma && dbg_chain < DBG_CHAINS) dbg_mma[dbg_chain * 8 + 0] = clock64();
@@ -801,7 +843,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
                 const uint32_t sb = sa + C::NPLANES * C::A_TILE;
                 const uint64_t da_hi = make_smem_desc(sa), db_hi = make_smem_desc(sb);
                 const uint64_t da_lo = make_smem_desc(sa + C::A_TILE), db_lo = make_smem_desc(sb + C::B_TILE);
-                const int nk = ks == k_slabs - 1 ? last_ksteps : KSTEPS;
+                const int nk = ks == ks_last ? last_ksteps : KSTEPS;
 #pragma unroll
                 for (int k = 0; k < KSTEPS; ++k) {
                   if (k < nk) {
@@ -820,7 +862,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
                 const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
                 const uint32_t sb = sa + C::NPLANES * C::A_TILE;
                 const uint64_t da_hi = make_smem_desc(sa), db_hi = make_smem_desc(sb);
-                const int nk = ks == k_slabs - 1 ? last_ksteps : KSTEPS;
+                const int nk = ks == ks_last ? last_ksteps : KSTEPS;
                 if (ks == ks0) umma_pair_f16_scale11(da_hi, db_hi, tmem_d, idesc);
 #pragma unroll
                 for (int k = 0; k < KSTEPS; ++k) {
@@ -844,7 +886,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
                 const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
                 const uint32_t sb = sa + C::NPLANES * C::A_TILE;
                 const uint64_t da_hi = make_smem_desc(sa), db_hi = make_smem_desc(sb);
-                const int nk = ks == k_slabs - 1 ? last_ksteps : KSTEPS;
+                const int nk = ks == ks_last ? last_ksteps : KSTEPS;
                 if (NTERMS == 3) {  // small terms first: they meet the accumulator while it is smallest
                   const uint64_t da_lo = make_smem_desc(sa + C::A_TILE), db_lo = make_smem_desc(sb + C::B_TILE);
 #pragma unroll
@@ -886,13 +928,13 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     unsigned long long* dbg_epi = (cluster_id_x() == 0 && rank == 0 && warp == FIRST_EPI_WARP && lane == 0) ? dbg_buf : nullptr;
     if (C::HALF0 == C::HALF1)     // one copy of the epilogue code serves both column halves
       epilogue_loop<C, C::HALF0>(warp < FIRST_EPI_WARP + 4 ? 0 : C::HALF0, warp & 3, lane, rank, tmem_base, tfull_bar(0),
-                                 tempty_leader, stage, stage_u32, n_tiles, n_blocks, k_slabs, chunk_slabs, lead_chains, M, N, ep, dbg_epi, dbg_flags, smaps);
+                                 tempty_leader, stage, stage_u32, n_tiles, n_blocks, k_slabs, split_k, chunk_slabs, lead_chains, M, N, ep, dbg_epi, dbg_flags, smaps);
     else if (warp < FIRST_EPI_WARP + 4)
       epilogue_loop<C, C::HALF0>(0, warp & 3, lane, rank, tmem_base, tfull_bar(0), tempty_leader, stage, stage_u32, n_tiles,
-                                 n_blocks, k_slabs, chunk_slabs, lead_chains, M, N, ep, dbg_epi, dbg_flags, smaps);
+                                 n_blocks, k_slabs, split_k, chunk_slabs, lead_chains, M, N, ep, dbg_epi, dbg_flags, smaps);
     else
       epilogue_loop<C, C::HALF1>(C::HALF0, warp & 3, lane, rank, tmem_base, tfull_bar(0), tempty_leader, stage, stage_u32,
-                                 n_tiles, n_blocks, k_slabs, chunk_slabs, lead_chains, M, N, ep, nullptr, dbg_flags, smaps);
+                                 n_tiles, n_blocks, k_slabs, split_k, chunk_slabs, lead_chains, M, N, ep, nullptr, dbg_flags, smaps);
   }
 
   tcgen05_fence_before();
@@ -969,12 +1011,24 @@ int launch_gemm_tc2_cfg(const usf_linear_args* a, const Epilogue& ep_in, cudaStr
     if ((rc = make_store_map16(&sm.h16, ep.out_h16, a->M, a->N, ep.ld_16, 16))) return rc;
     if ((rc = make_store_map16(&sm.l16, ep.out_l16, a->M, a->N, ep.ld_16, 16))) return rc;
   }
-  const long long tiles = ((a->M + 2 * tc::BLOCK_M - 1) / (2 * tc::BLOCK_M)) * ((a->N + BLOCK_N - 1) / BLOCK_N);
+  // split-K (training: dW = dY^T . X): the K-slabs of a tile are cut into `split_k` work items that add their partial tiles
+  // into the fp32 output (red.global.add.v4.f32); the caller zeroes / pre-loads the output (usf_linear does, see capi.cu)
+  int split_k = 1;
+  if (a->split_k > 1) {
+    const int k_slabs = (int)((a->K + C::ELEMS_PER_SLAB - 1) / C::ELEMS_PER_SLAB);
+    const int per = (k_slabs + a->split_k - 1) / a->split_k;
+    split_k = (k_slabs + per - 1) / per;                    // every work item gets at least one slab
+    USF_REQUIRE(ep.fast_store && ep.out_f32 && !ep.out_h16 && !ep.out_hi && !ep.out_bf16 && !ep.bias && !ep.relu &&
+                    !ep.resid_hi && !ep.resid_h16 && !ep.colscale && !ep.postsub,
+                "split_k > 1 accumulates plain partial products into an aligned fp32 output (no other epilogue feature)");
+    ep.atomic_out = split_k > 1 ? 1 : 0;
+  }
+  const long long tiles = ((a->M + 2 * tc::BLOCK_M - 1) / (2 * tc::BLOCK_M)) * ((a->N + BLOCK_N - 1) / BLOCK_N) * split_k;
   const int pairs = num_sms() / 2;
   const int grid = 2 * (int)(tiles < pairs ? tiles : pairs);
   USF_CUDA_OK(launch_chain(kern, dim3(grid), dim3(tc::NUM_THREADS), (size_t)C::SMEM_BYTES, st, ma, mal, mw, mwl, (long long)a->M,
                            (int)a->N, (int)a->K, NTERMS == 3 ? g_chunk_slabs : 0,
-                           (NTERMS == 3 && KIND == tc2::KIND_F16) ? g_lead_chains : 0, ep, sm, g_dbg_buf, g_dbg_flags));
+                           (NTERMS == 3 && KIND == tc2::KIND_F16) ? g_lead_chains : 0, split_k, ep, sm, g_dbg_buf, g_dbg_flags));
   return USF_OK;
 }
 

@@ -371,3 +371,83 @@ def matmul_f64(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor) -> None:
     N = b.shape[1]
     assert a.dtype == b.dtype == out.dtype == torch.float64 and b.shape[0] == K and out.shape == (M, N)
     check(_lib.load().usf_matmul_f64(_ptr(a), _ld(a), _ptr(b), _ld(b), _ptr(out), _ld(out), M, N, K, _stream()))
+
+
+# ---- training step (see include/usflows_b200.h, "Training step") -------------------------------------------------------
+def linear_splitk(engine: int, a_t: Act, w_t: Act, N: int, K: int, out: torch.Tensor, split_k: int) -> None:
+    """out[M, N] (fp32) = a_t[M, K] . w_t[N, K]^T with the contraction cut into `split_k` pieces (dW = dY^T . X: a_t and w_t are
+    the TRANSPOSED planes of dY and X, K = batch rows).  The library zero-fills `out`."""
+    args = LinearArgs()
+    args.M, args.N, args.K = a_t.rows, N, K
+    args.engine = engine
+    if engine == ENGINE_TC_3XF16:
+        args.a, args.a_lo, args.lda = _ptr(a_t.h16), _ptr(a_t.l16), _ld(a_t.h16)
+        args.w, args.w_lo, args.ldw = _ptr(w_t.h16), _ptr(w_t.l16), _ld(w_t.h16)
+    else:
+        raise RuntimeError("usflows_b200: linear_splitk runs on the fp16-split tcgen05 engine")
+    args.resid_sign = 1.0
+    args.out_f32, args.ld_f32 = _ptr(out), _ld(out)
+    args.split_k = int(split_k)
+    global LAUNCHES
+    LAUNCHES += 1
+    check(_lib.load().usf_linear(C.byref(args), _stream()))
+
+
+def planes_glue(src, *, rows: int, n: int, mask_h=None, sign: float = 1.0, out: Optional[Act] = None, t: Optional[Act] = None,
+                colsum=None, mul=None, colsum2=None, overflow_flag=None) -> None:
+    """One pass between two contractions of the training step; `src` is an Act with fp16 split planes or an fp32 tensor."""
+    from ._lib import GlueArgs
+    g = GlueArgs()
+    if isinstance(src, Act):
+        g.h, g.l, g.ld = _ptr(src.h16), _ptr(src.l16), _ld(src.h16)
+    else:
+        g.src_f32, g.ld_src = _ptr(src), _ld(src)
+    g.rows, g.n, g.sign = rows, n, float(sign)
+    if mask_h is not None:
+        g.mask_h, g.ld_mask = _ptr(mask_h), _ld(mask_h)
+    if out is not None:
+        g.out_h, g.out_l, g.ld_out = _ptr(out.h16), _ptr(out.l16), _ld(out.h16)
+    if t is not None:
+        g.t_h, g.t_l, g.ld_t = _ptr(t.h16), _ptr(t.l16), _ld(t.h16)
+    g.colsum = _ptr(colsum)
+    if colsum2 is not None:
+        g.mul, g.ld_mul, g.colsum2 = _ptr(mul), _ld(mul), _ptr(colsum2)
+    g.overflow_flag = _ptr(overflow_flag)
+    global LAUNCHES
+    LAUNCHES += 1
+    check(_lib.load().usf_planes_glue(C.byref(g), _stream()))
+
+
+def base_backward(z: torch.Tensor, loc, scale, kind: int, g: Act, t: Optional[Act], dloc, dscale) -> None:
+    """d(-log p)/dz of the Laplace / Normal base as planes (+ transposed planes) and the column sums for loc / scale."""
+    global LAUNCHES
+    LAUNCHES += 1
+    rows, d = z.shape
+    check(_lib.load().usf_base_backward(_ptr(z), _ld(z), rows, d, _ptr(loc), _ptr(scale), kind, _ptr(g.h16), _ptr(g.l16),
+                                        _ld(g.h16), _ptr(t.h16) if t is not None else None,
+                                        _ptr(t.l16) if t is not None else None, _ld(t.h16) if t is not None else 0,
+                                        _ptr(dloc), _ptr(dscale), _stream()))
+
+
+def mat_prep(src: torch.Tensor, *, transpose: bool = False, row_idx=None, col_idx=None, scale: float = 1.0,
+             out_f32: Optional[torch.Tensor] = None, out: Optional[Act] = None, overflow_flag=None) -> None:
+    """Weight-side copy / transpose / gather / split of an fp32 matrix; the output shape decides rows x cols."""
+    ref = out_f32 if out_f32 is not None else out.h16
+    rows, cols = ref.shape
+    check(_lib.load().usf_mat_prep(_ptr(src), _ld(src), rows, cols, int(transpose), _ptr(row_idx), _ptr(col_idx), float(scale),
+                                   _ptr(out_f32), _ld(out_f32) if out_f32 is not None else 0,
+                                   _ptr(out.h16) if out is not None else None, _ptr(out.l16) if out is not None else None,
+                                   _ld(out.h16) if out is not None else 0, _ptr(overflow_flag), _stream()))
+
+
+def tri_mask(src: torch.Tensor, mode: int, scale: float, out: torch.Tensor, diag_src=None, coef: float = 0.0) -> None:
+    d = src.shape[0]
+    check(_lib.load().usf_tri_mask(_ptr(src), _ld(src), d, mode, float(scale), _ptr(diag_src),
+                                   _ld(diag_src) if diag_src is not None else 0, float(coef), _ptr(out), _ld(out), _stream()))
+
+
+def tri_inverse_batched(T: torch.Tensor, X: torch.Tensor, tmp: torch.Tensor, unit_mask: int) -> None:
+    """Inverses of the lower-triangular matrices T[m] (stack [n_mats, d, d], contiguous) into X[m]."""
+    n_mats, d, _ = T.shape
+    check(_lib.load().usf_tri_inverse_batched(_ptr(T), _ptr(X), _ptr(tmp), d, T.stride(1), T.stride(0), n_mats,
+                                              unit_mask & 0xFFFFFFFF, _stream()))

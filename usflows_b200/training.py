@@ -25,6 +25,9 @@ from . import engine, ops
 from .ops import Act, ENGINE_SIMT, ENGINE_TC_3XTF32, pad4
 
 TRAIN_MODE = "fp32_tf32"
+TRAIN_ENGINE_NOTE = ("train_engine.TrainEngine where the flow is in its scope (flat LU / DenseNN-coupling stacks: fp16-split "
+                     "tcgen05 contractions forward, dX, split-K dW; own weight-side kernels), else torch autograd over the "
+                     "library's tf32-split contractions")
 
 
 # --------------------------------------------------------------------------------------------------
@@ -358,22 +361,27 @@ def allreduce_gradients(params: List[torch.nn.Parameter], group=None) -> int:
 class GradReducer:
     """Bucketed gradient all-reduce overlapped with the backward pass.
 
-    Parameters are grouped into buckets in REVERSE registration order -- the order in which the density pass's backward
-    produces their gradients: base density first, then the layers from the data end of the stack to the latent end.  A
-    post-accumulate-grad hook per parameter (it fires once per backward pass, after the contributions of a block and of
+    Parameters are grouped into buckets in the order in which the density pass's backward produces their gradients: base
+    density first, then the layers in registration order (the pass walks the layer list backwards, so its backward reaches
+    coupling block 0 first and the final affine / scale layers last).  A post-accumulate-grad hook per parameter (it fires once per backward pass, after the contributions of a block and of
     the InverseTransform that aliases it have been summed) copies the gradient into its bucket; the bucket that just
     became complete goes out as ONE asynchronous all-reduce(sum) (NCCL on its own stream over NVLink / NVSwitch; gloo in
     the CPU tests) while the backward pass keeps running.  `finish()` waits for the buckets in flight, sends the ones a
     rank could not complete (parameters without a gradient contribute zeros, e.g. an empty shard) and copies the sums
     back into `p.grad`.  The result equals `allreduce_gradients` bit for bit on two ranks (sum of two numbers)."""
 
-    def __init__(self, params, group=None, bucket_bytes: int = 16 << 20):
+    def __init__(self, params, group=None, bucket_bytes: int = 16 << 20, first: Optional[list] = None):
         import torch.distributed as dist
         self.dist, self.group = dist, group
         self.params = [p for p in params if p.requires_grad]
+        # expected order of readiness: `first` (the base density's parameters), then REGISTRATION order -- the density pass
+        # walks the layer list backwards (flows.py:235), so its backward pass reaches block 0 first and the scale layer last
+        head = [p for p in (first or []) if p.requires_grad]
+        ids = {id(p) for p in head}
+        order = head + [p for p in self.params if id(p) not in ids]
         self.buckets: List[dict] = []
         cur, cur_bytes = [], 0
-        for p in reversed(self.params):
+        for p in order:
             cur.append(p)
             cur_bytes += p.numel() * 4
             if cur_bytes >= bucket_bytes:
@@ -411,6 +419,10 @@ class GradReducer:
 
     def _launch(self, b) -> None:
         b["work"] = self.dist.all_reduce(b["flat"], op=self.dist.ReduceOp.SUM, group=self.group, async_op=True)
+
+    def push(self, p) -> None:
+        """Hand-written backward passes (train_engine.py) announce a finished gradient here (no autograd hook fires)."""
+        self._on_grad(p)
 
     def _on_grad(self, p) -> None:
         if not self._armed:
@@ -454,18 +466,30 @@ class TrainStep:
     entries seen after each step; the caller reads it when it wants to, not once per step).  `global_rows` is the size of
     the global batch (the loss is the global mean, so shard gradients add up to the single-process gradient)."""
 
-    def __init__(self, flow, opt, group=None, distributed: Optional[bool] = None, gradient_clip: Optional[float] = None):
+    def __init__(self, flow, opt, group=None, distributed: Optional[bool] = None, gradient_clip: Optional[float] = None,
+                 engine: Optional[bool] = None):
         import torch.distributed as dist
+        from . import train_engine
         self.flow, self.opt, self.group, self.clip = flow, opt, group, gradient_clip
+        # hand-written forward / backward (train_engine.py) where the flow is in its scope, torch autograd over the
+        # library's contractions (`log_prob_autograd`) otherwise; `engine=False` forces the autograd route
+        prior = flow.log_prior()
+        self.use_engine = (engine is not False) and train_engine.supports(flow) \
+            and not isinstance(prior, torch.Tensor) and prior == 0
+        if engine is True and not self.use_engine:
+            raise NotImplementedError("usflows_b200: this flow is outside the scope of the hand-written training pass")
+        self._engines: Dict[int, Any] = {}
         if distributed is None:
             distributed = dist.is_available() and dist.is_initialized()
         self.distributed = distributed
         self.rank = dist.get_rank(group) if distributed else 0
         self.world = dist.get_world_size(group) if distributed else 1
         self.params = [p for p in flow.parameters()]
-        self.reducer = GradReducer(self.params, group) if distributed and self.world > 1 else None
+        base_params = list(flow.base_distribution.parameters())
+        self.reducer = GradReducer(self.params, group, first=base_params) if distributed and self.world > 1 else None
         dev = self.params[0].device
         self.infeasible = torch.zeros((), dtype=torch.float32, device=dev)
+        self.out_of_range = torch.zeros((), dtype=torch.float32, device=dev)   # fp16-split range flag of the engine passes
         self.allreduce_bytes = self.reducer.bytes_per_step if self.reducer is not None else 0
 
     def close(self) -> None:
@@ -481,7 +505,17 @@ class TrainStep:
         self.opt.zero_grad()
         if self.reducer is not None:
             self.reducer.begin()
-        if rows > 0:
+        if rows > 0 and self.use_engine:
+            from . import train_engine
+            eng = self._engines.get(rows)
+            if eng is None:
+                if len(self._engines) >= 2:                    # full batches + one ragged last batch
+                    self._engines.pop(next(iter(self._engines)))
+                eng = self._engines[rows] = train_engine.TrainEngine(flow, rows)
+            eng.flag.zero_()
+            local = eng.step(sample.reshape(rows, -1), total, self.reducer)
+            self.out_of_range += eng.flag[0]
+        elif rows > 0:
             loss = -log_prob_autograd(flow, sample).sum() / total
             if self.rank == 0:                          # the prior is a function of the weights only: count it once
                 prior = flow.log_prior()
@@ -559,6 +593,13 @@ def fit(flow, data_train, optim=None, optim_params: Optional[Dict[str, Any]] = N
     def check_feasible():
         if float(ts.infeasible) != 0:                                                  # flows.py:204-205
             raise RuntimeError("Model is not invertible")
+        if ts.use_engine and float(ts.out_of_range) != 0:
+            # a value left the fp16-split range inside the hand-written pass (its gradients were not finite for the
+            # affected steps): continue on the autograd route, whose tf32-split contractions have the fp32 range
+            import warnings
+            warnings.warn("usflows_b200: activations / gradients left the fp16-split range; training continues on the "
+                          "tf32-split autograd route")
+            ts.use_engine = False
 
     N = len(data_train)
     epoch_losses: List[float] = []
