@@ -353,10 +353,21 @@ int usf_base_backward(const float* z, int64_t ldz, int64_t rows, int32_t d, cons
                       float* dloc, float* dscale, void* stream);
 
 /* Weight-side copy: out[i, j] = scale * S[ri(i), cj(j)] with S = src (transpose = 0) or src^T (1); row_idx / col_idx are
- * optional int32 gather indices; written as fp32 (out_f32) and / or fp16 split operand planes (out_h, out_l). */
+ * optional int32 gather indices; written as fp32 (out_f32) and / or fp16 split operand planes (out_h, out_l) and / or the
+ * TRANSPOSED operand planes outT [cols, rows] of the same matrix (the operand of dX = dY . M next to the one of x . M^T). */
 int usf_mat_prep(const float* src, int64_t ld_src, int32_t rows, int32_t cols, int32_t transpose, const int32_t* row_idx,
                  const int32_t* col_idx, float scale, float* out_f32, int64_t ld_f32, void* out_h, void* out_l,
-                 int64_t ld_16, int32_t* overflow_flag, void* stream);
+                 int64_t ld_16, void* outT_h, void* outT_l, int64_t ld_T, int32_t* overflow_flag, void* stream);
+
+/* The bias path of an inverse affine layer, y = (x - b) W^-T = x W^-T + c with c = -W^-1 b (transforms.py:936-962):
+ *   usf_rowdot:  out[i] = alpha * sum_k W[row_idx ? row_idx[i] : i, k] * v[k]        (c = rowdot(W^-1, b, -1))
+ *   usf_colcomb: out[j] += alpha * sum_i v[i] * W[i, j]                               (db -= dc . W^-1)
+ *   usf_rank1:   A[i, j] += alpha * u[i] * v[j]                                       (dW^-1 -= dc (x) b) */
+int usf_rowdot(const float* W, int64_t ld, int32_t n_rows, int32_t K, const int32_t* row_idx, const float* v, float alpha,
+               float* out, void* stream);
+int usf_colcomb(const float* W, int64_t ld, int32_t rows, int32_t cols, const float* v, float alpha, float* out,
+                void* stream);
+int usf_rank1(float* A, int64_t ld, int32_t rows, int32_t cols, const float* u, const float* v, float alpha, void* stream);
 
 /* out = scale * (strict lower part of src, mode 0 | upper part incl. diagonal, mode 1) [+ coef / diag_src[i, i] on the
  * diagonal, mode 1]: the gradient masks of LUTransform (transforms.py:1209-1213) and d(sum log|diag U|)/dU. */

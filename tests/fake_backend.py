@@ -415,21 +415,38 @@ def base_backward(z, loc, scale, kind, g, t, dloc, dscale):
         dscale.add_(ds.sum(0))
 
 
-def mat_prep(src, *, transpose=False, row_idx=None, col_idx=None, scale=1.0, out_f32=None, out=None, overflow_flag=None):
+def mat_prep(src, *, transpose=False, row_idx=None, col_idx=None, scale=1.0, out_f32=None, out=None, out_t=None,
+             overflow_flag=None):
     v = src.t() if transpose else src
     if row_idx is not None:
         v = v[row_idx.long()]
     if col_idx is not None:
         v = v[:, col_idx.long()]
     v = scale * v
-    ref = out_f32 if out_f32 is not None else out.h16
-    v = v[:ref.shape[0], :ref.shape[1]]
+    shape = out_f32.shape if out_f32 is not None else out.h16.shape if out is not None else out_t.h16.shape[::-1]
+    v = v[:shape[0], :shape[1]]
     if out_f32 is not None:
         out_f32.copy_(v)
+    h, l = f16_split(v)
     if out is not None:
-        h, l = f16_split(v)
         out.h16.copy_(h)
         out.l16.copy_(l)
+    if out_t is not None:
+        out_t.h16.copy_(h.t())
+        out_t.l16.copy_(l.t())
+
+
+def rowdot(W, v, alpha, out, row_idx=None):
+    Wr = W if row_idx is None else W[row_idx.long()]
+    out.copy_(alpha * (Wr[:out.numel()] @ v))
+
+
+def colcomb(W, v, alpha, out):
+    out.add_(alpha * (v @ W))
+
+
+def rank1(A, u, v, alpha):
+    A.add_(alpha * torch.outer(u, v))
 
 
 def tri_mask(src, mode, scale, out, diag_src=None, coef=0.0):
@@ -456,5 +473,5 @@ def install(monkeypatch):
     for name in ["conv2d_rows", "layout_transpose", "im2col", "masked_add", "radial_logprob", "radial_sample", "gate_norm", "affine_couple", "sub_rows", "flow_small", "linear", "ingest", "base_logprob", "base_sample", "leaky_relu", "permute", "lu_assemble",
                  "lu_logabsdet", "vec_logabs", "tri_inverse", "transpose", "scale_rows_cols", "split_tf32", "split_f16", "to_bf16",
                  "householder_right", "softplus", "matmul_f32", "matmul_f64", "require_cuda", "linear_splitk", "planes_glue",
-                 "base_backward", "mat_prep", "tri_mask", "tri_inverse_batched"]:
+                 "base_backward", "mat_prep", "tri_mask", "tri_inverse_batched", "rowdot", "colcomb", "rank1"]:
         monkeypatch.setattr(real_ops, name, globals()[name])

@@ -399,10 +399,26 @@ def test_mat_prep_and_tri_mask():
     out = torch.zeros(72, 52, device="cuda")[:, :50]
     pl = Act(72, 50, h16=torch.zeros(72, 56, dtype=torch.float16, device="cuda")[:, :50],
              l16=torch.zeros(72, 56, dtype=torch.float16, device="cuda")[:, :50])
-    ops.mat_prep(src, transpose=True, row_idx=ri, col_idx=ci, scale=-2.0, out_f32=out, out=pl)
+    plt = Act(50, 72, h16=torch.zeros(50, 72, dtype=torch.float16, device="cuda"),
+              l16=torch.zeros(50, 72, dtype=torch.float16, device="cuda"))
+    ops.mat_prep(src, transpose=True, row_idx=ri, col_idx=ci, scale=-2.0, out_f32=out, out=pl, out_t=plt)
     want = -2.0 * src.t()[ri.long()][:, ci.long()]
     assert torch.equal(out, want)
     assert rel_err(pl.h16.double() + pl.l16.double() / 2048.0, want) <= 1e-6
+    assert torch.equal(plt.h16, pl.h16.t()) and torch.equal(plt.l16, pl.l16.t())
+    # the bias path of an inverse affine layer: row dots (gathered rows), column combination, rank-1 update
+    W = torch.randn(40, 56, generator=g).cuda()
+    v, u = torch.randn(56, generator=g).cuda(), torch.randn(40, generator=g).cuda()
+    rows_i = torch.randperm(40, generator=g).to(torch.int32).cuda()
+    o = torch.zeros(40, device="cuda")
+    ops.rowdot(W, v, -1.0, o, row_idx=rows_i)
+    assert rel_err(o, -(W[rows_i.long()].double() @ v.double())) <= 1e-6
+    acc = torch.ones(56, device="cuda")
+    ops.colcomb(W, u, 0.5, acc)
+    assert rel_err(acc, 1.0 + 0.5 * (u.double() @ W.double())) <= 1e-6
+    A = W.clone()
+    ops.rank1(A, u, v, -2.0)
+    assert rel_err(A, W.double() - 2.0 * torch.outer(u.double(), v.double())) <= 1e-6
     sq = torch.randn(40, 40, generator=g).cuda()
     diag_src = (torch.randn(40, 40, generator=g) + 3 * torch.eye(40)).cuda()
     o0, o1 = torch.zeros(40, 40, device="cuda"), torch.zeros(40, 40, device="cuda")

@@ -112,7 +112,10 @@ SIGNATURES = {
     "usf_matmul_f64": (C.c_int, [_P, _I64, _P, _I64, _P, _I64, _I32, _I32, _I32, _P]),
     "usf_planes_glue": (C.c_int, [C.POINTER(GlueArgs), _P]),
     "usf_base_backward": (C.c_int, [_P, _I64, _I64, _I32, _P, _P, _I32, _P, _P, _I64, _P, _P, _I64, _P, _P, _P]),
-    "usf_mat_prep": (C.c_int, [_P, _I64, _I32, _I32, _I32, _P, _P, _F, _P, _I64, _P, _P, _I64, _P, _P]),
+    "usf_mat_prep": (C.c_int, [_P, _I64, _I32, _I32, _I32, _P, _P, _F, _P, _I64, _P, _P, _I64, _P, _P, _I64, _P, _P]),
+    "usf_rowdot": (C.c_int, [_P, _I64, _I32, _I32, _P, _P, _F, _P, _P]),
+    "usf_colcomb": (C.c_int, [_P, _I64, _I32, _I32, _P, _F, _P, _P]),
+    "usf_rank1": (C.c_int, [_P, _I64, _I32, _I32, _P, _P, _F, _P]),
     "usf_tri_mask": (C.c_int, [_P, _I64, _I32, _I32, _F, _P, _I64, _F, _P, _I64, _P]),
     "usf_tri_inverse_batched": (C.c_int, [_P, _P, _P, _I32, _I64, _I64, _I32, C.c_uint32, _P]),
     "usf_debug_set_block_n": (C.c_int, [C.c_int]),

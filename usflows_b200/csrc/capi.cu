@@ -580,13 +580,37 @@ int usf_base_backward(const float* z, int64_t ldz, int64_t rows, int32_t d, cons
 
 int usf_mat_prep(const float* src, int64_t ld_src, int32_t rows, int32_t cols, int32_t transpose, const int32_t* row_idx,
                  const int32_t* col_idx, float scale, float* out_f32, int64_t ld_f32, void* out_h, void* out_l, int64_t ld_16,
-                 int32_t* overflow_flag, void* stream) {
-  USF_REQUIRE(src && rows > 0 && cols > 0 && (out_f32 || out_h), "bad input");
-  USF_REQUIRE((out_h == nullptr) == (out_l == nullptr), "planes come as (hi, lo) pairs");
+                 void* outT_h, void* outT_l, int64_t ld_T, int32_t* overflow_flag, void* stream) {
+  USF_REQUIRE(src && rows > 0 && cols > 0 && (out_f32 || out_h || outT_h), "bad input");
+  USF_REQUIRE((out_h == nullptr) == (out_l == nullptr) && (outT_h == nullptr) == (outT_l == nullptr),
+              "planes come as (hi, lo) pairs");
   USF_REQUIRE(src != out_f32, "mat_prep cannot run in place");
   mat_prep_kernel<<<ew_grid((long long)rows * cols, 256), 256, 0, S(stream)>>>(
       src, ld_src, rows, cols, transpose, row_idx, col_idx, scale, out_f32, ld_f32, reinterpret_cast<__half*>(out_h),
-      reinterpret_cast<__half*>(out_l), ld_16, overflow_flag);
+      reinterpret_cast<__half*>(out_l), ld_16, reinterpret_cast<__half*>(outT_h), reinterpret_cast<__half*>(outT_l), ld_T,
+      overflow_flag);
+  USF_CUDA_OK(cudaGetLastError());
+  return USF_OK;
+}
+
+int usf_rowdot(const float* W, int64_t ld, int32_t n_rows, int32_t K, const int32_t* row_idx, const float* v, float alpha,
+               float* out, void* stream) {
+  USF_REQUIRE(W && v && out && n_rows > 0 && K > 0, "bad input");
+  rowdot_kernel<<<(n_rows * 32 + 255) / 256, 256, 0, S(stream)>>>(W, ld, n_rows, K, row_idx, v, alpha, out);
+  USF_CUDA_OK(cudaGetLastError());
+  return USF_OK;
+}
+
+int usf_colcomb(const float* W, int64_t ld, int32_t rows, int32_t cols, const float* v, float alpha, float* out, void* stream) {
+  USF_REQUIRE(W && v && out && rows > 0 && cols > 0, "bad input");
+  colcomb_kernel<<<(cols + 255) / 256, 256, 0, S(stream)>>>(W, ld, rows, cols, v, alpha, out);
+  USF_CUDA_OK(cudaGetLastError());
+  return USF_OK;
+}
+
+int usf_rank1(float* A, int64_t ld, int32_t rows, int32_t cols, const float* u, const float* v, float alpha, void* stream) {
+  USF_REQUIRE(A && u && v && rows > 0 && cols > 0, "bad input");
+  rank1_kernel<<<ew_grid((long long)rows * cols, 256), 256, 0, S(stream)>>>(A, ld, rows, cols, u, v, alpha);
   USF_CUDA_OK(cudaGetLastError());
   return USF_OK;
 }

@@ -265,7 +265,7 @@ base_backward_kernel(const float* __restrict__ z, long long ldz, long long rows,
 __global__ void __launch_bounds__(256)
 mat_prep_kernel(const float* __restrict__ src, long long ld_src, int rows, int cols, int transpose,
                 const int* __restrict__ row_idx, const int* __restrict__ col_idx, float scale, float* out_f32, long long ld_f32,
-                __half* out_h, __half* out_l, long long ld_16, int* overflow_flag) {
+                __half* out_h, __half* out_l, long long ld_16, __half* outT_h, __half* outT_l, long long ld_T, int* overflow_flag) {
   const long long total = (long long)rows * cols;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int r = (int)(i / cols), c = (int)(i - (long long)r * cols);
@@ -273,13 +273,54 @@ mat_prep_kernel(const float* __restrict__ src, long long ld_src, int rows, int c
     const int sc = col_idx ? __ldg(col_idx + c) : c;
     const float v = scale * (transpose ? src[(long long)sc * ld_src + sr] : src[(long long)sr * ld_src + sc]);
     if (out_f32) out_f32[(long long)r * ld_f32 + c] = v;
-    if (out_h) {
+    if (out_h || outT_h) {
       __half h, l;
       f16_split(v, h, l);
-      out_h[(long long)r * ld_16 + c] = h;
-      out_l[(long long)r * ld_16 + c] = l;
+      if (out_h) {
+        out_h[(long long)r * ld_16 + c] = h;
+        out_l[(long long)r * ld_16 + c] = l;
+      }
+      if (outT_h) {                      // the transposed operand planes of the same matrix (dX = dY . M reads M^T)
+        outT_h[(long long)c * ld_T + r] = h;
+        outT_l[(long long)c * ld_T + r] = l;
+      }
       if (!(fabsf(v) <= F16_GUARD) && overflow_flag) *overflow_flag = 1;
     }
+  }
+}
+
+// ---- small vector / matrix products of the bias path (c = -W^-1 b and its derivative) -------------------------------
+// out[i] = alpha * sum_k W[r(i), k] v[k]      (one warp per output row)
+__global__ void __launch_bounds__(256)
+rowdot_kernel(const float* __restrict__ W, long long ld, int n_rows, int K, const int* __restrict__ row_idx,
+              const float* __restrict__ v, float alpha, float* __restrict__ out) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= n_rows) return;
+  const float* w = W + (long long)(row_idx ? __ldg(row_idx + warp) : warp) * ld;
+  float s = 0.f;
+  for (int k = lane; k < K; k += 32) s = fmaf(w[k], __ldg(v + k), s);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) out[warp] = alpha * s;
+}
+// out[j] += alpha * sum_i v[i] W[i, j]        (one thread per column, rows walked together: coalesced)
+__global__ void __launch_bounds__(256)
+colcomb_kernel(const float* __restrict__ W, long long ld, int rows, int cols, const float* __restrict__ v, float alpha,
+               float* __restrict__ out) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= cols) return;
+  float s = 0.f;
+  for (int i = 0; i < rows; ++i) s = fmaf(__ldg(v + i), W[(long long)i * ld + j], s);
+  out[j] += alpha * s;
+}
+// A[i, j] += alpha * u[i] v[j]
+__global__ void __launch_bounds__(256)
+rank1_kernel(float* __restrict__ A, long long ld, int rows, int cols, const float* __restrict__ u, const float* __restrict__ v,
+             float alpha) {
+  const long long total = (long long)rows * cols;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / cols), c = (int)(i - (long long)r * cols);
+    A[(long long)r * ld + c] = fmaf(alpha * __ldg(u + r), __ldg(v + c), A[(long long)r * ld + c]);
   }
 }
 

@@ -430,14 +430,40 @@ def base_backward(z: torch.Tensor, loc, scale, kind: int, g: Act, t: Optional[Ac
 
 
 def mat_prep(src: torch.Tensor, *, transpose: bool = False, row_idx=None, col_idx=None, scale: float = 1.0,
-             out_f32: Optional[torch.Tensor] = None, out: Optional[Act] = None, overflow_flag=None) -> None:
-    """Weight-side copy / transpose / gather / split of an fp32 matrix; the output shape decides rows x cols."""
-    ref = out_f32 if out_f32 is not None else out.h16
-    rows, cols = ref.shape
+             out_f32: Optional[torch.Tensor] = None, out: Optional[Act] = None, out_t: Optional[Act] = None,
+             overflow_flag=None) -> None:
+    """Weight-side copy / transpose / gather / split of an fp32 matrix; the output shape decides rows x cols (`out_t`
+    receives the transposed planes [cols, rows] of the same result)."""
+    if out_f32 is not None:
+        rows, cols = out_f32.shape
+    elif out is not None:
+        rows, cols = out.h16.shape
+    else:
+        cols, rows = out_t.h16.shape
+    global LAUNCHES
+    LAUNCHES += 1
     check(_lib.load().usf_mat_prep(_ptr(src), _ld(src), rows, cols, int(transpose), _ptr(row_idx), _ptr(col_idx), float(scale),
                                    _ptr(out_f32), _ld(out_f32) if out_f32 is not None else 0,
                                    _ptr(out.h16) if out is not None else None, _ptr(out.l16) if out is not None else None,
-                                   _ld(out.h16) if out is not None else 0, _ptr(overflow_flag), _stream()))
+                                   _ld(out.h16) if out is not None else 0,
+                                   _ptr(out_t.h16) if out_t is not None else None, _ptr(out_t.l16) if out_t is not None else None,
+                                   _ld(out_t.h16) if out_t is not None else 0, _ptr(overflow_flag), _stream()))
+
+
+def rowdot(W: torch.Tensor, v: torch.Tensor, alpha: float, out: torch.Tensor, row_idx=None) -> None:
+    """out[i] = alpha * W[row_idx[i] or i, :] . v"""
+    check(_lib.load().usf_rowdot(_ptr(W), _ld(W), out.numel(), W.shape[1], _ptr(row_idx), _ptr(v), float(alpha), _ptr(out),
+                                 _stream()))
+
+
+def colcomb(W: torch.Tensor, v: torch.Tensor, alpha: float, out: torch.Tensor) -> None:
+    """out[j] += alpha * sum_i v[i] W[i, j]"""
+    check(_lib.load().usf_colcomb(_ptr(W), _ld(W), W.shape[0], W.shape[1], _ptr(v), float(alpha), _ptr(out), _stream()))
+
+
+def rank1(A: torch.Tensor, u: torch.Tensor, v: torch.Tensor, alpha: float) -> None:
+    """A[i, j] += alpha * u[i] v[j]"""
+    check(_lib.load().usf_rank1(_ptr(A), _ld(A), A.shape[0], A.shape[1], _ptr(u), _ptr(v), float(alpha), _stream()))
 
 
 def tri_mask(src: torch.Tensor, mode: int, scale: float, out: torch.Tensor, diag_src=None, coef: float = 0.0) -> None:

@@ -256,10 +256,20 @@ class TrainEngine:
 
     # ------------------------------------------------------------------------------------------------------------
     def _split_k(self, n_out: int, k_out: int, rows: int) -> int:
-        tiles = -(-n_out // 256) * -(-k_out // 256)
+        """Number of K pieces of a dW product: the one that minimises (waves of the persistent CTA-pair grid) x (K-slabs per
+        piece + the fixed cost of a work item: accumulator drain + reduction into memory, ~4 slabs' worth)."""
+        bn = 256 if k_out % 256 == 0 or k_out > 832 else 208
+        tiles = -(-n_out // 256) * -(-k_out // bn)
         k_slabs = -(-rows // 64)
-        want = max(1, -(-2 * self._pairs // tiles))
-        return max(1, min(want, k_slabs // 4 if k_slabs >= 8 else 1))
+        best, best_cost = 1, None
+        for s in range(1, max(1, k_slabs // 2) + 1):
+            per = -(-k_slabs // s)
+            if (s - 1) * per >= k_slabs:
+                continue
+            cost = -(-tiles * s // self._pairs) * (per + 4)
+            if best_cost is None or cost < best_cost:
+                best, best_cost = s, cost
+        return best
 
     def _gemm(self, a: Act, w: Act, N: int, K: int, *, bias=None, relu=False, resid=None, sign=1.0, out: Act) -> None:
         ops.linear(ENGINE_TC_3XF16, a, w.h16, w.l16, N, K, bias=bias, relu=relu, resid=resid, resid_sign=sign, out=out,
@@ -276,10 +286,8 @@ class TrainEngine:
         for st in self.lus.values():
             i = st.index
             L, UT, Linv, UinvT = self.T[2 * i], self.T[2 * i + 1], self.X[2 * i], self.X[2 * i + 1]
-            ops.mat_prep(L, out=st.pL, overflow_flag=self.flag)
-            ops.mat_prep(UT, out=st.pUT, overflow_flag=self.flag)
-            ops.mat_prep(UT, transpose=True, out=st.pU, overflow_flag=self.flag)
-            ops.mat_prep(L, transpose=True, out=st.pLT, overflow_flag=self.flag)
+            ops.mat_prep(L, out=st.pL, out_t=st.pLT, overflow_flag=self.flag)
+            ops.mat_prep(UT, out=st.pUT, out_t=st.pU, overflow_flag=self.flag)
             if st.need_w:                                                            # W = L U      (transforms.py:1281-1283)
                 ops.linear(ENGINE_TC_3XF16, st.pL, st.pUT.h16, st.pUT.l16, d, d, out=Act(d, d, f32=st.W), overflow_flag=self.flag)
             if st.need_winv:                                                         # W^-1 = U^-1 L^-1   (transforms.py:1289-1293)
@@ -287,24 +295,19 @@ class TrainEngine:
                 ops.mat_prep(Linv, transpose=True, out=st.pLinvT, overflow_flag=self.flag)
                 ops.linear(ENGINE_TC_3XF16, st.pUinv, st.pLinvT.h16, st.pLinvT.l16, d, d, out=Act(d, d, f32=st.Winv),
                            overflow_flag=self.flag)
-                ops.mat_prep(st.Winv, out=st.pWinv, overflow_flag=self.flag)
-                ops.mat_prep(st.Winv, transpose=True, out=st.pWinvT, overflow_flag=self.flag)
+                ops.mat_prep(st.Winv, out=st.pWinv, out_t=st.pWinvT, overflow_flag=self.flag)
         for op in self.plan:
             if op["kind"] == "aff":
                 st = op["lu"]
                 P = st.W if op["fwd"] else st.Winv
                 r = self.order if op["perm_out"] else None
                 c = self.order if op["perm_in"] else None
-                ops.mat_prep(P, row_idx=r, col_idx=c, out=op["M"], overflow_flag=self.flag)
-                ops.mat_prep(P, transpose=True, row_idx=c, col_idx=r, out=op["MT"], overflow_flag=self.flag)
-                b = st.lu.bias_vector.detach().reshape(1, d)
+                ops.mat_prep(P, row_idx=r, col_idx=c, out=op["M"], out_t=op["MT"], overflow_flag=self.flag)
+                b = st.lu.bias_vector.detach()
                 if op["fwd"]:                                                        # y = x W^T + b   (transforms.py:913-934)
-                    ops.mat_prep(b, col_idx=r, out_f32=op["c"].reshape(1, d))
+                    ops.mat_prep(b.reshape(1, d), col_idx=r, out_f32=op["c"].reshape(1, d))
                 else:                                                                # y = (x - b) W^-T = x W^-T - W^-1 b  (:936-962)
-                    ops.mat_prep(b, scale=-1.0, out_f32=st.vec)
-                    Mf = st.tmp
-                    ops.mat_prep(st.Winv, row_idx=r, out_f32=Mf)
-                    ops.linear(ENGINE_SIMT, Act(1, d, f32=st.vec), Mf, None, d, d, out=Act(1, d, f32=op["c"].reshape(1, d)))
+                    ops.rowdot(st.Winv, b, -1.0, op["c"], row_idx=r)
             else:
                 n_l = len(op["layers"])
                 for j, L in enumerate(op["layers"]):
@@ -312,8 +315,7 @@ class TrainEngine:
                     bias = L["lin"].bias.detach()
                     ci = op["idx_in"] if j == 0 else None
                     ri = op["idx_out"] if j == n_l - 1 else None
-                    ops.mat_prep(w, row_idx=ri, col_idx=ci, out=L["W"], overflow_flag=self.flag)
-                    ops.mat_prep(w, transpose=True, row_idx=ci, col_idx=ri, out=L["WT"], overflow_flag=self.flag)
+                    ops.mat_prep(w, row_idx=ri, col_idx=ci, out=L["W"], out_t=L["WT"], overflow_flag=self.flag)
                     ops.mat_prep(bias.reshape(1, -1), col_idx=ri, out_f32=L["b"].reshape(1, -1))
 
     # ------------------------------------------------------------------------------------------------------------
@@ -450,13 +452,9 @@ class TrainEngine:
             st.dWinv.add_(st.tmp)
             # c = -W^-1 b (rows in the use's order):  dW^-1 -= dc (x) b ,  db -= dc . W^-1
             ops.mat_prep(op["dc"].reshape(1, d), col_idx=r, scale=inv_total, out_f32=st.vec)   # dc in the true row order
-            dcv = st.vec.reshape(d, 1)
-            bvec = st.lu.bias_vector.detach().reshape(d, 1)
-            ops.linear(ENGINE_SIMT, Act(d, 1, f32=dcv), bvec, None, d, 1, resid=Act(d, d, f32=st.dWinv), resid_sign=-1.0,
-                       out=Act(d, d, f32=st.dWinv))
-            ops.mat_prep(st.Winv, transpose=True, out_f32=st.tmp)                   # (W^-1)^T as the [N, K] operand
-            ops.linear(ENGINE_SIMT, Act(1, d, f32=st.vec), st.tmp, None, d, d, out=Act(1, d, f32=st.vec2))
-            st.db.sub_(st.vec2.reshape(-1))
+            dcv = st.vec.reshape(-1)
+            ops.rank1(st.dWinv, dcv, st.lu.bias_vector.detach(), -1.0)
+            ops.colcomb(st.Winv, dcv, -1.0, st.db)
 
     def _lu_backward(self, st: _LU, inv_total: float, share: float) -> None:
         """dW, dW^-1 -> dL_raw, dU_raw (transforms.py:1271-1293 differentiated; masks of :1209-1213)."""
@@ -471,8 +469,7 @@ class TrainEngine:
             src = st.dWtot
         else:
             src = st.dW
-        ops.mat_prep(src, out=st.pdWtot, overflow_flag=self.flag)
-        ops.mat_prep(src, transpose=True, out=st.pdWtotT, overflow_flag=self.flag)
+        ops.mat_prep(src, out=st.pdWtot, out_t=st.pdWtotT, overflow_flag=self.flag)
         ops.linear(E, st.pdWtot, st.pU.h16, st.pU.l16, d, d, out=Act(d, d, f32=st.dL), overflow_flag=self.flag)     # dW_tot U^T
         ops.linear(E, st.pLT, st.pdWtotT.h16, st.pdWtotT.l16, d, d, out=Act(d, d, f32=st.dU), overflow_flag=self.flag)  # L^T dW_tot
         ops.tri_mask(st.dL, 0, 1.0, st.gL)

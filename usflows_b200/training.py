@@ -467,7 +467,7 @@ class TrainStep:
     the global batch (the loss is the global mean, so shard gradients add up to the single-process gradient)."""
 
     def __init__(self, flow, opt, group=None, distributed: Optional[bool] = None, gradient_clip: Optional[float] = None,
-                 engine: Optional[bool] = None):
+                 engine: Optional[bool] = None, graph: Optional[bool] = None):
         import torch.distributed as dist
         from . import train_engine
         self.flow, self.opt, self.group, self.clip = flow, opt, group, gradient_clip
@@ -479,6 +479,14 @@ class TrainStep:
         if engine is True and not self.use_engine:
             raise NotImplementedError("usflows_b200: this flow is outside the scope of the hand-written training pass")
         self._engines: Dict[int, Any] = {}
+        # whole-step CUDA graphs: for the optimisers known to be capturable (this package's SophiaG; torch optimisers
+        # built with capturable=True), unless switched off
+        from .optim import SophiaG
+        capturable = isinstance(opt, SophiaG) or all(g.get("capturable", False) for g in opt.param_groups)
+        self.graph = bool(capturable) if graph is None else bool(graph)
+        self._graphs: Dict[tuple, dict] = {}
+        self._graph_warm: Dict[tuple, int] = {}
+        self._lr_sig = self._lr_signature()
         if distributed is None:
             distributed = dist.is_available() and dist.is_initialized()
         self.distributed = distributed
@@ -496,13 +504,62 @@ class TrainStep:
         if self.reducer is not None:
             self.reducer.close()
 
+    # -- CUDA-graph replay of the whole step ------------------------------------------------------------------------
+    # The hand-written pass is ~400 launches of 5-60 us: issued one by one from Python (ctypes + tensor-map encoding,
+    # ~15 us each) the host bounds the step.  Every shape and every buffer of `TrainEngine` is static, so after two
+    # eager steps the sequence [engine pass -> gradient exchange -> clip -> optimiser -> invertibility check] is
+    # captured once per (rows, global batch) and replayed; the NCCL all-reduces of the buckets are captured with it
+    # (on NCCL's stream, so they still overlap the remaining backward kernels).  Optimisers that cannot be captured
+    # (host-side state reads) keep the eager route: `graph=False`, or automatically when the capture fails.
     def step(self, sample: torch.Tensor, global_rows: Optional[int] = None) -> torch.Tensor:
         """Runs the step on this rank's shard `sample` [rows, ...]; returns this rank's share of the loss (a device
         scalar: the sum over ranks is the global mean loss)."""
-        flow = self.flow
         rows = sample.shape[0]
         total = global_rows if global_rows is not None else rows * self.world
-        self.opt.zero_grad()
+        if self.graph and self.use_engine and rows > 0 and sample.is_cuda and float(self._lr_signature()) == self._lr_sig:
+            key = (rows, total)
+            if key in self._graphs:
+                ent = self._graphs[key]
+                ent["x"].copy_(sample.reshape(rows, -1))
+                ent["graph"].replay()
+                return ent["loss"].clone()
+            n = self._graph_warm.get(key, 0)
+            if n >= 2:
+                got = self._capture(sample, rows, total)
+                if got is not None:
+                    return got
+            else:
+                self._graph_warm[key] = n + 1
+        return self._eager_step(sample, rows, total)
+
+    def _lr_signature(self) -> float:
+        """Hyper-parameters baked into a captured optimiser step (a scheduler changing them invalidates the graphs)."""
+        return sum(float(g.get("lr", 0.0)) * (i + 1) for i, g in enumerate(self.opt.param_groups))
+
+    def _capture(self, sample: torch.Tensor, rows: int, total: int):
+        x_static = torch.empty(rows, sample.numel() // rows, dtype=torch.float32, device=sample.device)
+        x_static.copy_(sample.reshape(rows, -1))
+        out = {}
+        graph = torch.cuda.CUDAGraph()
+        try:
+            from .flows import _plain_stream_order
+            torch.cuda.synchronize(sample.device)
+            with _plain_stream_order(), torch.cuda.graph(graph, capture_error_mode="thread_local"):
+                out["loss"] = self._eager_step(x_static, rows, total, zero_grad=False)
+        except Exception as e:                                  # noqa: BLE001  (optimiser / collective not capturable)
+            import warnings
+            warnings.warn(f"usflows_b200: the training step is not CUDA-graph capturable here ({e!r}); running eagerly")
+            self.graph = False
+            torch.cuda.synchronize(sample.device)
+            return None
+        self._graphs[(rows, total)] = dict(graph=graph, x=x_static, loss=out["loss"])
+        graph.replay()                                          # capturing does not execute: this is the step itself
+        return out["loss"].clone()
+
+    def _eager_step(self, sample: torch.Tensor, rows: int, total: int, zero_grad: bool = True) -> torch.Tensor:
+        flow = self.flow
+        if zero_grad:
+            self.opt.zero_grad()
         if self.reducer is not None:
             self.reducer.begin()
         if rows > 0 and self.use_engine:
