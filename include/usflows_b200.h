@@ -146,7 +146,8 @@ int usf_debug_set_pdl(int on);
  * clock64() stamps of the first 512 accumulation chains of cluster 0 (0 = accumulator free seen by the MMA issuer,
  * 1 = operands landed, 2 = chain issued, 3 = accumulator full seen by epilogue warp 4, 4 = drained, 5 = tile stored);
  * `flags`: 1 = epilogue skips the TMEM drain, 2 = epilogue skips the store phase (timing experiments only:
- * results are wrong with either flag set); 4 = outputs leave through the generic register/patch store path instead of
+ * results are wrong with either flag set); 256 = the coupling residual is read lane-per-row instead of coalesced through the
+ * epilogue warp's in-box (same bits, slower); 4 = outputs leave through the generic register/patch store path instead of
  * the staged coalesced one; 32 = the epilogue warps copy their staged boxes out themselves instead of issuing
  * TMA stores (results identical with 4 and 32; tests cover the paths). */
 int usf_debug_gemm_timeline(unsigned long long* device_buf, int flags);

@@ -247,7 +247,8 @@ def test_staged_store_path_equals_register_store_path(eng_name, eng, fmt, M, N, 
         assert float(p.f32._base[:, N:].abs().max()) == 0.0 and float(p.h16._base[..., N:].abs().max()) == 0.0
 
 
-@pytest.mark.parametrize("M,N,K", [(300, 784, 392), (70000, 1024, 128), (515, 400, 1024), (130, 608, 72), (64, 48, 40)])
+@pytest.mark.parametrize("M,N,K", [(300, 784, 392), (70000, 1024, 128), (515, 400, 1024), (130, 608, 72), (64, 48, 40),
+                                   (1000, 392, 1024), (257, 112, 64)])
 def test_tma_store_path_equals_inline_store(M, N, K):
     """fp16-split planes only (the hot configuration): boxes stored by TMA == stored by the epilogue warps themselves,
     including the in-place coupling form (residual read from the planes that are written)."""
@@ -262,7 +263,7 @@ def test_tma_store_path_equals_inline_store(M, N, K):
     wact, _ = _f16_planes(w)
     lib = _lib.load()
     outs = []
-    for flags in (0, 32, 4):
+    for flags in (0, 256, 32, 4):                         # 256: residual read lane-per-row instead of through the in-box
         stream, _ = _f16_planes(x0)                       # fresh copy of the stream for the in-place update
         lib.usf_debug_gemm_timeline(None, flags)
         try:

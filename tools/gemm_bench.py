@@ -71,6 +71,8 @@ def main():
     ap.add_argument("--check", action="store_true")
     ap.add_argument("--epi", action="store_true", help="bias + relu epilogue")
     ap.add_argument("--lead", type=int, default=-1)
+    ap.add_argument("--resid", action="store_true", help="3xf16: in-place coupling residual (out = out - (a.w^T + bias))")
+    ap.add_argument("--flags", type=int, default=0, help="usf_debug_gemm_timeline flags (256 = residual without the in-box)")
     args = ap.parse_args()
     lib = _lib.load()
     if args.chunk >= 0:
@@ -85,7 +87,11 @@ def main():
             act, wt, wl, bias, out, ref_a, ref_w = make_case(eng, M, N, K, 0, args.epi)
 
             def run():
-                ops.linear(ENG[eng], act, wt, wl, N, K, bias=bias, relu=args.epi, out=out)
+                if args.resid and eng == "3xf16":
+                    ops.linear(ENG[eng], act, wt, wl, N, K, bias=bias, resid=out, resid_sign=-1.0, out=out)
+                else:
+                    ops.linear(ENG[eng], act, wt, wl, N, K, bias=bias, relu=args.epi, out=out)
+            lib.usf_debug_gemm_timeline(None, args.flags)
             rec = dict(engine=eng, M=M, N=N, K=K, bn=args.bn, chunk=args.chunk)
             try:
                 for _ in range(3):

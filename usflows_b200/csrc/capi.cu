@@ -585,7 +585,7 @@ int usf_mat_prep(const float* src, int64_t ld_src, int32_t rows, int32_t cols, i
   USF_REQUIRE((out_h == nullptr) == (out_l == nullptr) && (outT_h == nullptr) == (outT_l == nullptr),
               "planes come as (hi, lo) pairs");
   USF_REQUIRE(src != out_f32, "mat_prep cannot run in place");
-  mat_prep_kernel<<<ew_grid((long long)rows * cols, 256), 256, 0, S(stream)>>>(
+  mat_prep_kernel<<<dim3((cols + 31) / 32, (rows + 31) / 32), 256, 0, S(stream)>>>(
       src, ld_src, rows, cols, transpose, row_idx, col_idx, scale, out_f32, ld_f32, reinterpret_cast<__half*>(out_h),
       reinterpret_cast<__half*>(out_l), ld_16, reinterpret_cast<__half*>(outT_h), reinterpret_cast<__half*>(outT_l), ld_T,
       overflow_flag);
@@ -603,7 +603,7 @@ int usf_rowdot(const float* W, int64_t ld, int32_t n_rows, int32_t K, const int3
 
 int usf_colcomb(const float* W, int64_t ld, int32_t rows, int32_t cols, const float* v, float alpha, float* out, void* stream) {
   USF_REQUIRE(W && v && out && rows > 0 && cols > 0, "bad input");
-  colcomb_kernel<<<(cols + 255) / 256, 256, 0, S(stream)>>>(W, ld, rows, cols, v, alpha, out);
+  colcomb_kernel<<<dim3((cols + 255) / 256, (rows + CC_ROWS - 1) / CC_ROWS), 256, 0, S(stream)>>>(W, ld, rows, cols, v, alpha, out);
   USF_CUDA_OK(cudaGetLastError());
   return USF_OK;
 }

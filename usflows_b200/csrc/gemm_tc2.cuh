@@ -65,6 +65,7 @@ __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap
       : "memory");
 }
 constexpr int STAGE_EPI_BYTES = 4096;          // per epilogue warp: one 32-row x (128 B | 2 x 64 B) staging box
+constexpr int INBOX_BYTES = 2048;              // per epilogue warp: one plane of a 32-row x 32-column residual piece
 
 // Accumulation-chain schedule of one tile: the first `lead` chains span 2 * chunk K-slabs, the others `chunk`.
 // Longer leading chains let the MMA issuer run further ahead while the epilogue warps are still storing the previous
@@ -143,8 +144,14 @@ struct Config {
   static constexpr int A_TILE = BLOCK_M * SLAB_BYTES;        // 16 KB
   static constexpr int B_TILE = HALF_N * SLAB_BYTES;         // multiple of 1024
   static constexpr int STAGE_BYTES = NPLANES * (A_TILE + B_TILE);
-  static constexpr int EPI_BYTES = NUM_EPI_WARPS * STAGE_EPI_BYTES;   // (the patch path of unaligned outputs fits too)
   static_assert(PATCH_BYTES <= STAGE_EPI_BYTES, "patch buffer lives in the staging area");
+  // a 2 KB "in-box" per epilogue warp (coalesced loads of the coupling residual, see coop_resid_row) where it does not cost
+  // a pipeline stage: BLOCK_N = 208 and narrower on the fp16-split engine
+  static constexpr int STAGES_PLAIN = (227 * 1024 - 1024 - 512 - NUM_EPI_WARPS * STAGE_EPI_BYTES) / STAGE_BYTES;
+  static constexpr int STAGES_INBOX = (227 * 1024 - 1024 - 512 - NUM_EPI_WARPS * (STAGE_EPI_BYTES + INBOX_BYTES)) / STAGE_BYTES;
+  static constexpr bool INBOX = KIND == KIND_F16 && NTERMS == 3 &&
+                                (STAGES_INBOX >= 8 || STAGES_INBOX == STAGES_PLAIN);
+  static constexpr int EPI_BYTES = NUM_EPI_WARPS * (STAGE_EPI_BYTES + (INBOX ? INBOX_BYTES : 0));
   static constexpr int STAGES_RAW = (227 * 1024 - 1024 - 512 - EPI_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static_assert(STAGES >= 2, "need at least a double-buffered pipeline");
@@ -457,12 +464,44 @@ __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 constexpr int ASYNC_BOX_BYTES = 32 * 32 * 2;       // one 32-row x 32-column fp16 box = 2 KB (box A at +0, box B at +2 KB)
 
+// Coupling residual, read COALESCED.  A lane owns one row of the piece (the TMEM layout), but 32 lanes reading 16 bytes
+// of 32 different rows cost one LSU tag lookup per lane and instruction (measured: +80 us on the 392 x 1024 layer of C2,
+// profiles/r01_timeline_pair_f16.md).  Here the warp reads the piece with lanes mapped to (row group, 16-byte chunk) --
+// every load instruction covers whole RB-byte row segments of 32 / CPR rows -- drops it into the warp's in-box (same
+// XOR swizzle as the staging boxes: conflict-free both ways) and every lane picks its own row up from there.
+__device__ __forceinline__ uint4 ldg128(const void* p) {
+  uint4 v;
+  asm volatile("ld.global.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
+template <int W>
+__device__ __forceinline__ void coop_resid_row(const __half* plane, int ldr, long long row0, long long M, int n0, int N, int lane,
+                                               uint32_t inbox, uint4 (&row)[W / 8]) {
+  constexpr int RB = W * 2, CPR = RB / 16, RPI = 32 / CPR;
+  const int chunk = lane % CPR, rsub = lane / CPR;
+  uint4 t[CPR];
+  const bool col_ok = n0 + chunk * 8 < N;
+#pragma unroll
+  for (int it = 0; it < CPR; ++it) {
+    const long long r = row0 + rsub + RPI * it;
+    t[it] = make_uint4(0u, 0u, 0u, 0u);
+    if (col_ok && r < M) t[it] = ldg128(plane + r * ldr + n0 + chunk * 8);
+  }
+#pragma unroll
+  for (int it = 0; it < CPR; ++it) sts128(inbox + stage_off<RB>(rsub + RPI * it, chunk), t[it].x, t[it].y, t[it].z, t[it].w);
+  __syncwarp();
+#pragma unroll
+  for (int q = 0; q < W / 8; ++q) row[q] = lds128(inbox + stage_off<RB>(lane, q));
+  __syncwarp();          // every lane has its row: the box may be rewritten
+}
+
 // `bias4` = this lane's four bias values of the warp's column range (lane l holds columns 4l .. 4l+3 of the range,
 // loaded once per tile before the last drain); the piece starting at column `c_first` of the range takes its values
 // from lanes c_first/4 .. by shuffle, so no global load sits between two TMA stores
 template <int W>
 __device__ __forceinline__ void async_math(const EpiRegs& er, float (&v)[W], const float4& bias4, int c_first,
-                                           long long m, bool row_ok, int n0, int N) {
+                                           long long m, bool row_ok, int n0, int N, long long row0, long long M, int lane,
+                                           uint32_t inbox) {
   const uint32_t f = er.flags;
   if (f & EF_BIAS) {                 // (all lanes take part in the shuffles)
 #pragma unroll
@@ -473,6 +512,30 @@ __device__ __forceinline__ void async_math(const EpiRegs& er, float (&v)[W], con
       v[4 * q + 2] += __shfl_sync(0xffffffffu, bias4.z, src);
       v[4 * q + 3] += __shfl_sync(0xffffffffu, bias4.w, src);
     }
+  }
+  if ((f & EF_RESID16) && inbox != 0) {   // (all lanes take part: rows past M load nothing and use nothing)
+    uint4 rowh[W / 8], rowl[W / 8];
+    coop_resid_row<W>(er.rh, er.ldr16, row0, M, n0, N, lane, inbox, rowh);
+    coop_resid_row<W>(er.rl, er.ldr16, row0, M, n0, N, lane, inbox, rowl);
+    if (!row_ok) return;
+    if (f & EF_RELU) {
+#pragma unroll
+      for (int i = 0; i < W; ++i) v[i] = fmaxf(v[i], 0.f);
+    }
+#pragma unroll
+    for (int q = 0; q < W / 8; ++q) {
+      if (n0 + 8 * q < N) {
+        const __half2* h2 = reinterpret_cast<const __half2*>(&rowh[q]);
+        const __half2* l2 = reinterpret_cast<const __half2*>(&rowl[q]);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 hf = __half22float2(h2[e]), lf = __half22float2(l2[e]);
+          v[8 * q + 2 * e] = fmaf(er.sign, v[8 * q + 2 * e], fmaf(lf.x, F16_LO_UNSCALE, hf.x));
+          v[8 * q + 2 * e + 1] = fmaf(er.sign, v[8 * q + 2 * e + 1], fmaf(lf.y, F16_LO_UNSCALE, hf.y));
+        }
+      }
+    }
+    return;
   }
   if (!row_ok) return;
   if (f & EF_RELU) {
@@ -533,8 +596,8 @@ __device__ __forceinline__ void async_stage_plane(const Epilogue& ep, const floa
 template <int W>
 __device__ __forceinline__ void async_piece(const Epilogue& ep, const EpiRegs& er, const StoreMaps& smaps, float (&v)[W],
                                             const float4& bias4, int c_first, long long m, bool row_ok, int lane, int n0, int N,
-                                            long long row0, uint32_t stage, uint32_t& groups) {
-  async_math<W>(er, v, bias4, c_first, m, row_ok, n0, N);
+                                            long long row0, uint32_t stage, uint32_t& groups, long long M, uint32_t inbox) {
+  async_math<W>(er, v, bias4, c_first, m, row_ok, n0, N, row0, M, lane, inbox);
   const CUtensorMap* mh = W == 32 ? &smaps.h32 : &smaps.h16;
   const CUtensorMap* ml = W == 32 ? &smaps.l32 : &smaps.l16;
 #pragma unroll
@@ -560,7 +623,7 @@ __device__ __forceinline__ void async_piece(const Epilogue& ep, const EpiRegs& e
 template <class C, int COLS>
 __device__ __forceinline__ void epilogue_loop(int col0, int quarter, int lane, uint32_t rank, uint32_t tmem_base,
                                               uint32_t tfull0, uint32_t tempty0_leader, uint8_t* stage_gen,
-                                              uint32_t stage, long long n_tiles, int n_blocks, int k_slabs, int split_k, int chunk_slabs, int lead,
+                                              uint32_t stage, uint32_t inbox, long long n_tiles, int n_blocks, int k_slabs, int split_k, int chunk_slabs, int lead,
                                               long long M, int N, const Epilogue& ep, unsigned long long* dbg, int dbg_flags,
                                               const StoreMaps& smaps) {
   constexpr int BLOCK_N = C::kBlockN;
@@ -571,7 +634,7 @@ __device__ __forceinline__ void epilogue_loop(int col0, int quarter, int lane, u
   float* patch = reinterpret_cast<float*>(stage_gen);
   // everything the tile loop needs lives in registers from here on (opaque to the compiler): re-deriving these from
   // special registers / the parameter bank inside the loop costs a dependent S2R / LDC per use
-  asm volatile("" : "+r"(stage), "+r"(tfull0), "+r"(tempty0_leader), "+r"(tmem_base));
+  asm volatile("" : "+r"(stage), "+r"(tfull0), "+r"(tempty0_leader), "+r"(tmem_base), "+r"(inbox));
   asm volatile("" : "+l"(M), "+r"(N), "+r"(lane), "+r"(quarter), "+r"(col0), "+r"(rank), "+r"(n_blocks), "+l"(n_tiles),
                "+r"(n_chunks), "+r"(dbg_flags), "+r"(split_k), "+r"(k_slabs));
   const EpiRegs er = load_epi_regs(ep);
@@ -654,14 +717,14 @@ __device__ __forceinline__ void epilogue_loop(int col0, int quarter, int lane, u
           const int n0 = n_idx + col0 + c * 32;
           if (n0 < N)
             async_piece<32>(ep, er, smaps, *reinterpret_cast<float(*)[32]>(&master[c * 32]), bias4, c * 32, m, row_ok, lane,
-                            n0, N, row0, stage, hand);
+                            n0, N, row0, stage, hand, M, inbox);
         }
         if (COLS % 32) {
           constexpr int c_first = COLS / 32 * 32;
           const int n0 = n_idx + col0 + c_first;
           if (n0 < N)
             async_piece<16>(ep, er, smaps, *reinterpret_cast<float(*)[16]>(&master[c_first]), bias4, c_first, m, row_ok, lane,
-                            n0, N, row0, stage, hand);
+                            n0, N, row0, stage, hand, M, inbox);
         }
         if (dbg && dbg_chain - 1 < DBG_CHAINS) dbg[(dbg_chain - 1) * 8 + 6] = (unsigned long long)(clock64() - t_start) << 32;
       }
@@ -924,16 +987,18 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_EPI));
     const uint32_t stage_u32 = epi_base + (warp - FIRST_EPI_WARP) * STAGE_EPI_BYTES;
     uint8_t* stage = smem_gen + (stage_u32 - smem_base);
+    const uint32_t inbox_u32 = (C::INBOX && !(dbg_flags & 256))
+                                   ? epi_base + NUM_EPI_WARPS * STAGE_EPI_BYTES + (warp - FIRST_EPI_WARP) * INBOX_BYTES : 0u;
     const uint32_t tempty_leader = mapa(tempty_bar(0), 0);
     unsigned long long* dbg_epi = (cluster_id_x() == 0 && rank == 0 && warp == FIRST_EPI_WARP && lane == 0) ? dbg_buf : nullptr;
     if (C::HALF0 == C::HALF1)     // one copy of the epilogue code serves both column halves
       epilogue_loop<C, C::HALF0>(warp < FIRST_EPI_WARP + 4 ? 0 : C::HALF0, warp & 3, lane, rank, tmem_base, tfull_bar(0),
-                                 tempty_leader, stage, stage_u32, n_tiles, n_blocks, k_slabs, split_k, chunk_slabs, lead_chains, M, N, ep, dbg_epi, dbg_flags, smaps);
+                                 tempty_leader, stage, stage_u32, inbox_u32, n_tiles, n_blocks, k_slabs, split_k, chunk_slabs, lead_chains, M, N, ep, dbg_epi, dbg_flags, smaps);
     else if (warp < FIRST_EPI_WARP + 4)
-      epilogue_loop<C, C::HALF0>(0, warp & 3, lane, rank, tmem_base, tfull_bar(0), tempty_leader, stage, stage_u32, n_tiles,
+      epilogue_loop<C, C::HALF0>(0, warp & 3, lane, rank, tmem_base, tfull_bar(0), tempty_leader, stage, stage_u32, inbox_u32, n_tiles,
                                  n_blocks, k_slabs, split_k, chunk_slabs, lead_chains, M, N, ep, dbg_epi, dbg_flags, smaps);
     else
-      epilogue_loop<C, C::HALF1>(C::HALF0, warp & 3, lane, rank, tmem_base, tfull_bar(0), tempty_leader, stage, stage_u32,
+      epilogue_loop<C, C::HALF1>(C::HALF0, warp & 3, lane, rank, tmem_base, tfull_bar(0), tempty_leader, stage, stage_u32, inbox_u32,
                                  n_tiles, n_blocks, k_slabs, split_k, chunk_slabs, lead_chains, M, N, ep, nullptr, dbg_flags, smaps);
   }
 

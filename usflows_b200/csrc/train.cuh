@@ -262,31 +262,68 @@ base_backward_kernel(const float* __restrict__ z, long long ldz, long long rows,
 // weight-side matrix preparation:  out[i, j] = scale * src[ri(i), cj(j)]   (src read transposed when `transpose`)
 //   ri / cj: optional gather indices over the rows / columns of the (possibly transposed) source
 // ---------------------------------------------------------------------------------------------------------------------
+// 32 x 32 output tile per CTA (256 threads = 32 x 8), staged in shared memory so that the source is read along its
+// contiguous dimension (whichever of rows / columns that is under `transpose`) and every output -- the fp32 copy, the
+// operand planes and the TRANSPOSED operand planes -- is written along its own contiguous dimension.
 __global__ void __launch_bounds__(256)
 mat_prep_kernel(const float* __restrict__ src, long long ld_src, int rows, int cols, int transpose,
                 const int* __restrict__ row_idx, const int* __restrict__ col_idx, float scale, float* out_f32, long long ld_f32,
                 __half* out_h, __half* out_l, long long ld_16, __half* outT_h, __half* outT_l, long long ld_T, int* overflow_flag) {
-  const long long total = (long long)rows * cols;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int r = (int)(i / cols), c = (int)(i - (long long)r * cols);
-    const int sr = row_idx ? __ldg(row_idx + r) : r;
-    const int sc = col_idx ? __ldg(col_idx + c) : c;
-    const float v = scale * (transpose ? src[(long long)sc * ld_src + sr] : src[(long long)sr * ld_src + sc]);
-    if (out_f32) out_f32[(long long)r * ld_f32 + c] = v;
-    if (out_h || outT_h) {
-      __half h, l;
-      f16_split(v, h, l);
-      if (out_h) {
-        out_h[(long long)r * ld_16 + c] = h;
-        out_l[(long long)r * ld_16 + c] = l;
+  __shared__ float tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  // load: logical element (r, c) = scale * S[ri(r), cj(c)], S = src or src^T
+  if (!transpose) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int r = r0 + ty + 8 * k, c = c0 + tx;
+      if (r < rows && c < cols) {
+        const int sr = row_idx ? __ldg(row_idx + r) : r, sc = col_idx ? __ldg(col_idx + c) : c;
+        tile[ty + 8 * k][tx] = scale * src[(long long)sr * ld_src + sc];
       }
-      if (outT_h) {                      // the transposed operand planes of the same matrix (dX = dY . M reads M^T)
-        outT_h[(long long)c * ld_T + r] = h;
-        outT_l[(long long)c * ld_T + r] = l;
+    }
+  } else {       // S[a, b] = src[b, a]: walk the logical ROW index with tx (contiguous in src when no gather is given)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int r = r0 + tx, c = c0 + ty + 8 * k;
+      if (r < rows && c < cols) {
+        const int sr = row_idx ? __ldg(row_idx + r) : r, sc = col_idx ? __ldg(col_idx + c) : c;
+        tile[tx][ty + 8 * k] = scale * src[(long long)sc * ld_src + sr];
       }
-      if (!(fabsf(v) <= F16_GUARD) && overflow_flag) *overflow_flag = 1;
     }
   }
+  __syncthreads();
+  bool bad = false;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int r = r0 + ty + 8 * k, c = c0 + tx;
+    if (r < rows && c < cols) {
+      const float v = tile[ty + 8 * k][tx];
+      if (out_f32) out_f32[(long long)r * ld_f32 + c] = v;
+      if (out_h) {
+        __half h, l;
+        f16_split(v, h, l);
+        out_h[(long long)r * ld_16 + c] = h;
+        out_l[(long long)r * ld_16 + c] = l;
+        bad = bad || !(fabsf(v) <= F16_GUARD);
+      }
+    }
+  }
+  if (outT_h) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int c = c0 + ty + 8 * k, r = r0 + tx;     // transposed planes: row c, column r
+      if (r < rows && c < cols) {
+        const float v = tile[tx][ty + 8 * k];
+        __half h, l;
+        f16_split(v, h, l);
+        outT_h[(long long)c * ld_T + r] = h;
+        outT_l[(long long)c * ld_T + r] = l;
+        bad = bad || !(fabsf(v) <= F16_GUARD);
+      }
+    }
+  }
+  if (bad && overflow_flag) *overflow_flag = 1;
 }
 
 // ---- small vector / matrix products of the bias path (c = -W^-1 b and its derivative) -------------------------------
@@ -303,15 +340,19 @@ rowdot_kernel(const float* __restrict__ W, long long ld, int n_rows, int K, cons
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   if (lane == 0) out[warp] = alpha * s;
 }
-// out[j] += alpha * sum_i v[i] W[i, j]        (one thread per column, rows walked together: coalesced)
+// out[j] += alpha * sum_i v[i] W[i, j]        (thread = column, blockIdx.y = chunk of 32 rows: coalesced row reads, the
+// chunks meet in `out` through atomics)
+constexpr int CC_ROWS = 32;
 __global__ void __launch_bounds__(256)
 colcomb_kernel(const float* __restrict__ W, long long ld, int rows, int cols, const float* __restrict__ v, float alpha,
                float* __restrict__ out) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= cols) return;
+  const int i0 = blockIdx.y * CC_ROWS, i1 = min(rows, i0 + CC_ROWS);
   float s = 0.f;
-  for (int i = 0; i < rows; ++i) s = fmaf(__ldg(v + i), W[(long long)i * ld + j], s);
-  out[j] += alpha * s;
+#pragma unroll 8
+  for (int i = i0; i < i1; ++i) s = fmaf(__ldg(v + i), W[(long long)i * ld + j], s);
+  atomicAdd(out + j, alpha * s);
 }
 // A[i, j] += alpha * u[i] v[j]
 __global__ void __launch_bounds__(256)

@@ -253,6 +253,8 @@ class TrainEngine:
         self.cs2 = torch.zeros(d, device=dev)        # sum_r dy0 * x (scale gradient)
         pairs = max(1, _num_sms() // 2)
         self._pairs = pairs
+        self._side = [torch.cuda.Stream(device=dev) for _ in range(3)] if dev.type == "cuda" else []
+        self._side_used = set()
 
     # ------------------------------------------------------------------------------------------------------------
     def _split_k(self, n_out: int, k_out: int, rows: int) -> int:
@@ -283,22 +285,48 @@ class TrainEngine:
             lu, i = st.lu, st.index
             ops.lu_assemble(lu.L_raw.detach(), lu.U_raw.detach(), self.T[2 * i], self.T[2 * i + 1], transpose_u=True)
         ops.tri_inverse_batched(self.T, self.X, self.Ttmp, self.unit_mask)         # L^-1 and (U^T)^-1 = (U^-1)^T of every layer
-        for st in self.lus.values():
-            i = st.index
-            L, UT, Linv, UinvT = self.T[2 * i], self.T[2 * i + 1], self.X[2 * i], self.X[2 * i + 1]
-            ops.mat_prep(L, out=st.pL, out_t=st.pLT, overflow_flag=self.flag)
-            ops.mat_prep(UT, out=st.pUT, out_t=st.pU, overflow_flag=self.flag)
-            if st.need_w:                                                            # W = L U      (transforms.py:1281-1283)
-                ops.linear(ENGINE_TC_3XF16, st.pL, st.pUT.h16, st.pUT.l16, d, d, out=Act(d, d, f32=st.W), overflow_flag=self.flag)
-            if st.need_winv:                                                         # W^-1 = U^-1 L^-1   (transforms.py:1289-1293)
-                ops.mat_prep(UinvT, transpose=True, out=st.pUinv, overflow_flag=self.flag)
-                ops.mat_prep(Linv, transpose=True, out=st.pLinvT, overflow_flag=self.flag)
-                ops.linear(ENGINE_TC_3XF16, st.pUinv, st.pLinvT.h16, st.pLinvT.l16, d, d, out=Act(d, d, f32=st.Winv),
-                           overflow_flag=self.flag)
-                ops.mat_prep(st.Winv, out=st.pWinv, out_t=st.pWinvT, overflow_flag=self.flag)
+        # the chains of the layers are independent of each other (16 output tiles each on 74 CTA pairs): they run side by
+        # side on a few streams (parallel branches of the captured graph); the conditioner operands are prepared on the
+        # main stream meanwhile
+        for k, st in enumerate(self.lus.values()):
+            with self._on_side(k):
+                self._prepare_lu(st)
+        self._prepare_conditioners()
+        self._join_sides()
+
+    def _on_side(self, k: int):
+        """Context: a side stream that has waited for everything issued on the current stream so far (CUDA devices;
+        a no-op on the emulated backend)."""
+        if not self._side:
+            import contextlib
+            return contextlib.nullcontext()
+        s = self._side[k % len(self._side)]
+        s.wait_stream(torch.cuda.current_stream(self.dev))
+        self._side_used.add(k % len(self._side))
+        return torch.cuda.stream(s)
+
+    def _join_sides(self) -> None:
+        main = torch.cuda.current_stream(self.dev) if self._side else None
+        for k in sorted(self._side_used):
+            main.wait_stream(self._side[k])
+        self._side_used.clear()
+
+    def _prepare_lu(self, st: _LU) -> None:
+        d = self.d
+        i = st.index
+        L, UT, Linv, UinvT = self.T[2 * i], self.T[2 * i + 1], self.X[2 * i], self.X[2 * i + 1]
+        ops.mat_prep(L, out=st.pL, out_t=st.pLT, overflow_flag=self.flag)
+        ops.mat_prep(UT, out=st.pUT, out_t=st.pU, overflow_flag=self.flag)
+        if st.need_w:                                                            # W = L U      (transforms.py:1281-1283)
+            ops.linear(ENGINE_TC_3XF16, st.pL, st.pUT.h16, st.pUT.l16, d, d, out=Act(d, d, f32=st.W), overflow_flag=self.flag)
+        if st.need_winv:                                                         # W^-1 = U^-1 L^-1   (transforms.py:1289-1293)
+            ops.mat_prep(UinvT, transpose=True, out=st.pUinv, overflow_flag=self.flag)
+            ops.mat_prep(Linv, transpose=True, out=st.pLinvT, overflow_flag=self.flag)
+            ops.linear(ENGINE_TC_3XF16, st.pUinv, st.pLinvT.h16, st.pLinvT.l16, d, d, out=Act(d, d, f32=st.Winv),
+                       overflow_flag=self.flag)
+            ops.mat_prep(st.Winv, out=st.pWinv, out_t=st.pWinvT, overflow_flag=self.flag)
         for op in self.plan:
-            if op["kind"] == "aff":
-                st = op["lu"]
+            if op["kind"] == "aff" and op["lu"] is st:
                 P = st.W if op["fwd"] else st.Winv
                 r = self.order if op["perm_out"] else None
                 c = self.order if op["perm_in"] else None
@@ -308,7 +336,10 @@ class TrainEngine:
                     ops.mat_prep(b.reshape(1, d), col_idx=r, out_f32=op["c"].reshape(1, d))
                 else:                                                                # y = (x - b) W^-T = x W^-T - W^-1 b  (:936-962)
                     ops.rowdot(st.Winv, b, -1.0, op["c"], row_idx=r)
-            else:
+
+    def _prepare_conditioners(self) -> None:
+        for op in self.plan:
+            if op["kind"] == "coupling":
                 n_l = len(op["layers"])
                 for j, L in enumerate(op["layers"]):
                     w = L["lin"].weight.detach()
@@ -397,11 +428,12 @@ class TrainEngine:
                     gT_ready = False
                     self._scatter_affine_grads(op, inv_total)
                     st.n_uses -= 1
-                    if st.n_uses == 0:
-                        self._lu_backward(st, inv_total, share)
-                        if reducer is not None:
-                            for p in (st.lu.L_raw, st.lu.U_raw, st.lu.bias_vector):
-                                reducer.push(p)
+                    if st.n_uses == 0:               # weight-side derivative of this layer: beside the next block's batch work
+                        with self._on_side(st.index):
+                            self._lu_backward(st, inv_total, share)
+                            if reducer is not None:
+                                for p in (st.lu.L_raw, st.lu.U_raw, st.lu.bias_vector):
+                                    reducer.push(p)
                 else:
                     self._coupling_backward(op, g, inv_total)
                     gT_ready = False
@@ -416,6 +448,7 @@ class TrainEngine:
                 self._set_grad(self.scale_layer.scale, gs.reshape(self.scale_layer.scale.shape))
                 if reducer is not None:
                     reducer.push(self.scale_layer.scale)
+            self._join_sides()
         return loss
 
     # ------------------------------------------------------------------------------------------------------------
