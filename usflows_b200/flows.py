@@ -33,6 +33,19 @@ HOST_MAX_STAGE_SLICES = 8    # ... and when it needs at most this many chunks (o
 
 
 _capture_lock = threading.Lock()     # one graph capture at a time per process (the launch-mode switch below is global)
+_capture_streams: Dict[int, Any] = {}
+
+
+def capture_stream(device) -> "torch.cuda.Stream":
+    """The side stream graph captures of `device` run on.  torch.cuda.graph's default is ONE process-wide stream created on
+    whichever device captured first; a capture for another device would then launch on the wrong device (peer access, or an
+    illegal address), which is what the row-shard driver (parallel.py) hit with two GPUs in one process."""
+    device = torch.device(device)
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    s = _capture_streams.get(idx)
+    if s is None:
+        s = _capture_streams[idx] = torch.cuda.Stream(device=idx)
+    return s
 
 
 class _plain_stream_order:
@@ -204,7 +217,7 @@ class Flow(torch.nn.Module):
                 body()                                        # eager pass: sizes every workspace buffer before capture
                 torch.cuda.synchronize(dev)
                 graph = torch.cuda.CUDAGraph()
-                with _plain_stream_order(), torch.cuda.graph(graph, capture_error_mode="thread_local"):
+                with _plain_stream_order(), torch.cuda.graph(graph, stream=capture_stream(dev), capture_error_mode="thread_local"):
                     body()
             if len(cache) >= 8:                               # a few row counts per weight version; drop the oldest
                 cache.pop(next(iter(cache)))
@@ -232,7 +245,7 @@ class Flow(torch.nn.Module):
         prog._run_chunk(buf, fin, flag)                   # eager pass: sizes every workspace buffer before capture
         torch.cuda.synchronize(dev)
         graph = torch.cuda.CUDAGraph()
-        with _plain_stream_order(), torch.cuda.graph(graph, capture_error_mode="thread_local"):
+        with _plain_stream_order(), torch.cuda.graph(graph, stream=capture_stream(dev), capture_error_mode="thread_local"):
             prog._run_chunk(buf, fin, flag)
         ent = dict(graph=graph, fin=fin, flag=flag, gen=engine._workspace.generation)
         for k in [k for k in cache if k[0] == slot and (k[1] != key[1] or cache[k]["gen"] != ent["gen"])]:

@@ -542,9 +542,10 @@ class TrainStep:
         out = {}
         graph = torch.cuda.CUDAGraph()
         try:
-            from .flows import _plain_stream_order
+            from .flows import _plain_stream_order, capture_stream
             torch.cuda.synchronize(sample.device)
-            with _plain_stream_order(), torch.cuda.graph(graph, capture_error_mode="thread_local"):
+            with _plain_stream_order(), torch.cuda.graph(graph, stream=capture_stream(sample.device),
+                                                         capture_error_mode="thread_local"):
                 out["loss"] = self._eager_step(x_static, rows, total, zero_grad=False)
         except Exception as e:                                  # noqa: BLE001  (optimiser / collective not capturable)
             import warnings
