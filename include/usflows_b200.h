@@ -322,6 +322,45 @@ int usf_matmul_f64(const double* A, int64_t lda, const double* B, int64_t ldb, d
 int usf_softplus(const float* in, int64_t n, float* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Whole-stack evaluation (ABI 4).  A plan is the launch sequence of ONE direction of a layer stack whose steps are all
+ * contractions (every USFlow with DenseNN conditioners): ingest -> usf_linear chain -> base density.  Replaces the
+ * per-layer loops of Flow.log_prob (flows.py:225-245), Flow.backward (:57-67) and Flow._forward (:45-55) with one call
+ * per batch; the host that builds the plan passes prepared operands (the same ones usf_linear takes).  The plan owns
+ * its device workspaces (allocated by usf_plan_finalize for `max_rows` rows, freed by usf_plan_destroy) and keeps
+ * POINTERS to the operands, biases and base parameters it was given: they must stay alive and unchanged while it is used.
+ * One plan per device and stream at a time.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct usf_plan usf_plan;
+enum usf_mode { USF_MODE_FP32 = 0, USF_MODE_FP32_TF32 = 1, USF_MODE_FP32_SIMT = 2, USF_MODE_TF32 = 3, USF_MODE_BF16 = 4 };
+enum usf_plan_src { USF_PLAN_SRC_STREAM = 0, USF_PLAN_SRC_HIDDEN = 1 };
+enum usf_plan_dst { USF_PLAN_DST_STREAM = 0,   /* new stream activation (the LAST step writes the fp32 result instead) */
+                    USF_PLAN_DST_HIDDEN = 1,   /* conditioner hidden activation */
+                    USF_PLAN_DST_SEGMENT = 2   /* coupling output: stream[:, out_col0 : out_col0 + N] += resid_sign * value, in place */ };
+typedef struct usf_plan_linear {
+  int32_t N, K, engine, relu;
+  const void* w; const void* w_lo; int64_t ldw;     /* operand planes of the engine, [N, K] */
+  const float* bias;
+  int32_t src, dst;
+  int32_t in_col0, in_width;                         /* src = stream: columns read as A (in_width = 0: all) */
+  int32_t out_col0;
+  float resid_sign;
+} usf_plan_linear;
+int usf_plan_create(usf_plan** plan, int32_t d_in, int32_t mode, int64_t max_rows);
+int usf_plan_add_linear(usf_plan* plan, const usf_plan_linear* step);
+/* base density of the latent (Laplace / Normal, prepared loc / scale as for usf_base_logprob); add_const = -sum of the
+ * weight-only log-determinants */
+int usf_plan_set_base(usf_plan* plan, int32_t base_kind, const float* loc, const float* scale, float add_const);
+int usf_plan_finalize(usf_plan* plan);
+int64_t usf_plan_workspace_bytes(const usf_plan* plan);
+/* z[rows, width] (fp32) = the stack applied to x[rows, d_in] */
+int usf_flow_apply(const usf_plan* plan, const float* x, int64_t ldx, int64_t rows, float* z, int64_t ldz,
+                   int32_t* overflow_flag, void* stream);
+/* out[r] = log p(x[r, :]) = base.log_prob(stack(x[r, :])) + add_const   (Flow.log_prob, flows.py:225-245) */
+int usf_flow_logprob(const usf_plan* plan, const float* x, int64_t ldx, int64_t rows, float* out, int32_t* overflow_flag,
+                     void* stream);
+int usf_plan_destroy(usf_plan* plan);
+
+/* ------------------------------------------------------------------------------------------------
  * Training step (ABI 4).  Replaces what torch autograd does behind Flow.fit's loss.backward() (flows.py:199):
  * the batch-side products dX = dY . W and dW = dY^T . X are usf_linear calls (dW with split_k); these entries are the
  * passes between them and the weight-side algebra of LUTransform (transforms.py:1271-1293 and its derivative).

@@ -83,3 +83,26 @@ def test_sass_contains_blackwell_tensor_and_tma_instructions():
     for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM"):
         assert mnemonic in sass, mnemonic
     assert "sm_100a" in sass
+
+
+def test_plan_linear_layout_matches_header():
+    from usflows_b200 import _lib
+    with open(os.path.join(ROOT, "include", "usflows_b200.h")) as f:
+        text = f.read()
+    body = re.search(r"typedef struct usf_plan_linear \{(.*?)\} usf_plan_linear;", text, flags=re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    fields = [n for decl in body.split(";") for n in re.findall(r"([A-Za-z_0-9]+)\s*(?:,|$)", decl.strip().replace("\n", " "))
+              if n not in ("int32_t", "int64_t", "float", "const", "void")]
+    assert fields == [f[0] for f in _lib.PlanLinear._fields_], fields
+    assert ctypes.sizeof(_lib.PlanLinear) == 4 * 4 + 3 * 8 + 8 + 4 * 4 + 4 + 4
+
+
+def test_plan_entry_points_reject_bad_input_without_gpu():
+    from usflows_b200 import _lib
+    lib = _lib.load()
+    assert lib.usf_plan_create(None, 8, 0, 16) == -1 and b"bad input" in lib.usf_last_error()
+    h = ctypes.c_void_p()
+    assert lib.usf_plan_create(ctypes.byref(h), 8, 0, 16) == 0 and h.value
+    assert lib.usf_plan_finalize(h) == -1                       # no steps
+    assert lib.usf_flow_logprob(h, None, 0, 0, None, None, None) == -1
+    assert lib.usf_plan_destroy(h) == 0

@@ -399,3 +399,39 @@ def test_affine_coupling_extension_matches_its_restatement(name, mode, tol):
                                     if k.startswith("trainable_layers.1.conditioner.")}, len(spec["hidden_dims"]) + 1)
         want_ladj = ((1 - m) * st[:, :d].clamp(-5.0, 3.0)).sum(-1)
         assert rel_err(layer.log_abs_det_jacobian(x.cuda()), want_ladj) <= 3e-5
+
+
+@pytest.mark.parametrize("mode", ["fp32", "fp32_tf32", "fp32_simt", "tf32", "bf16"])
+@pytest.mark.parametrize("name", ["d32_h64", "c2_d784", "d5_noconj"])
+def test_whole_stack_c_entry_equals_the_launch_by_launch_route(name, mode):
+    """usf_flow_logprob / usf_flow_apply (the library owns the launch sequence: SURVEY 8b) against the Python-driven launch
+    program: same kernels in the same order, so the same bits -- every precision mode, ragged row counts, an unaligned
+    input view, the density and the sampling direction."""
+    import usflows_b200.flows as F
+    spec, params, arr = load_case(name)
+    flow = build_flow(spec, params, precision=mode)
+    prog, _ = flow._program("backward")
+    if not prog.plan_able():
+        pytest.skip("program outside the plan's scope (tiny events run as one fused launch)")
+    d = spec["in_dims"][0]
+    g = torch.Generator().manual_seed(17)
+    big = torch.rand(9001, d + 3, generator=g).cuda()
+    for x in (big[:5000, :d].contiguous(), big[:9001, 1:d + 1], big[:257, :d].contiguous()):
+        old = (F.USE_C_PLAN, F.SMALL_BATCH_GRAPH_ROWS)
+        try:
+            F.SMALL_BATCH_GRAPH_ROWS = 0
+            F.USE_C_PLAN = False
+            want_lp, want_z = flow.log_prob(x), flow.backward(x)
+            want_y = flow._forward(want_z)
+            F.USE_C_PLAN = True
+            got_lp, got_z = flow.log_prob(x), flow.backward(x)
+            got_y = flow._forward(want_z)
+        finally:
+            F.USE_C_PLAN, F.SMALL_BATCH_GRAPH_ROWS = old
+        assert torch.equal(got_lp, want_lp) and torch.equal(got_z, want_z) and torch.equal(got_y, want_y)
+    assert len(prog._c_plans) >= 1
+    # out-of-range activations: the plan reports the chunk, the tf32-split engine recomputes it
+    if mode == "fp32" and name == "d32_h64":
+        xs = (arr["x"] * 3.0e5).cuda()
+        tf = build_flow(spec, params, precision="fp32_tf32")
+        assert torch.equal(flow.log_prob(xs), tf.log_prob(xs))

@@ -14,12 +14,14 @@ for wl in ("c2", "c5"):
     for rows in (256, 1024, 4096, 16384):
         x = torch.rand(rows, d, device="cuda")
         res = {}
-        for graphs in (0, 16384):
-            flows.SMALL_BATCH_GRAPH_ROWS = graphs
+        ref = None
+        for tag, graphs, plan in (("python", 0, False), ("c_plan", 0, True), ("graph", 16384, True)):
+            flows.SMALL_BATCH_GRAPH_ROWS, flows.USE_C_PLAN = graphs, plan
             for _ in range(3): flow.log_prob(x)
             torch.cuda.synchronize(); t0 = time.perf_counter()
             for _ in range(20): lp = flow.log_prob(x)
-            torch.cuda.synchronize(); res[graphs] = (time.perf_counter() - t0) / 20 * 1e3
-            ref = lp if graphs == 0 else ref
-        same = bool(torch.equal(ref, lp))
-        print(f"{wl} rows {rows}: launch-by-launch {res[0]:.3f} ms, graph replay {res[16384]:.3f} ms, identical {same}")
+            torch.cuda.synchronize(); res[tag] = (time.perf_counter() - t0) / 20 * 1e3
+            same = True if ref is None else bool(torch.equal(ref, lp))
+            ref = lp if ref is None else ref
+        print(f"{wl} rows {rows}: launch-by-launch from Python {res['python']:.3f} ms, one C call (usf_flow_logprob) "
+              f"{res['c_plan']:.3f} ms, graph replay {res['graph']:.3f} ms, identical {same}")

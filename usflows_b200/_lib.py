@@ -56,6 +56,24 @@ class GlueArgs(C.Structure):
     ]
 
 
+class PlanLinear(C.Structure):
+    """Mirror of `usf_plan_linear` (include/usflows_b200.h)."""
+
+    _fields_ = [
+        ("N", C.c_int32), ("K", C.c_int32), ("engine", C.c_int32), ("relu", C.c_int32),
+        ("w", C.c_void_p), ("w_lo", C.c_void_p), ("ldw", C.c_int64),
+        ("bias", C.c_void_p),
+        ("src", C.c_int32), ("dst", C.c_int32),
+        ("in_col0", C.c_int32), ("in_width", C.c_int32),
+        ("out_col0", C.c_int32), ("resid_sign", C.c_float),
+    ]
+
+
+MODE_CODES = {"fp32": 0, "fp32_tf32": 1, "fp32_simt": 2, "tf32": 3, "bf16": 4}
+PLAN_SRC_STREAM, PLAN_SRC_HIDDEN = 0, 1
+PLAN_DST_STREAM, PLAN_DST_HIDDEN, PLAN_DST_SEGMENT = 0, 1, 2
+
+
 class Planes(C.Structure):
     """Mirror of `usf_planes` (include/usflows_b200.h)."""
 
@@ -110,6 +128,14 @@ SIGNATURES = {
     "usf_householder_right": (C.c_int, [_P, _I32, _I64, _P, _P, _P]),
     "usf_softplus": (C.c_int, [_P, _I64, _P, _P]),
     "usf_matmul_f64": (C.c_int, [_P, _I64, _P, _I64, _P, _I64, _I32, _I32, _I32, _P]),
+    "usf_plan_create": (C.c_int, [C.POINTER(_P), _I32, _I32, _I64]),
+    "usf_plan_add_linear": (C.c_int, [_P, C.POINTER(PlanLinear)]),
+    "usf_plan_set_base": (C.c_int, [_P, _I32, _P, _P, _F]),
+    "usf_plan_finalize": (C.c_int, [_P]),
+    "usf_plan_workspace_bytes": (C.c_int64, [_P]),
+    "usf_flow_apply": (C.c_int, [_P, _P, _I64, _I64, _P, _I64, _P, _P]),
+    "usf_flow_logprob": (C.c_int, [_P, _P, _I64, _I64, _P, _P, _P]),
+    "usf_plan_destroy": (C.c_int, [_P]),
     "usf_planes_glue": (C.c_int, [C.POINTER(GlueArgs), _P]),
     "usf_base_backward": (C.c_int, [_P, _I64, _I64, _I32, _P, _P, _I32, _P, _P, _I64, _P, _P, _I64, _P, _P, _P]),
     "usf_mat_prep": (C.c_int, [_P, _I64, _I32, _I32, _I32, _P, _P, _F, _P, _I64, _P, _P, _I64, _P, _P, _I64, _P, _P]),

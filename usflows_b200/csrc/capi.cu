@@ -10,6 +10,7 @@
 #include "prep.cuh"
 #include "radial.cuh"
 #include "train.cuh"
+#include "plan.cuh"
 
 namespace usf {
 
@@ -526,6 +527,90 @@ int usf_matmul_f64(const double* A, int64_t lda, const double* B, int64_t ldb, d
   USF_REQUIRE(grid.y <= 65535, "matmul_f64: too many row blocks");
   matmul_f64_kernel<<<grid, 256, 0, S(stream)>>>(A, lda, B, ldb, C, ldc, M, N, K);
   USF_CUDA_OK(cudaGetLastError());
+  return USF_OK;
+}
+
+int usf_plan_create(usf_plan** plan, int32_t d_in, int32_t mode, int64_t max_rows) {
+  USF_REQUIRE(plan && d_in > 0 && max_rows > 0 && mode >= USF_MODE_FP32 && mode <= USF_MODE_BF16, "bad input");
+  usf_plan* p = new (std::nothrow) usf_plan();
+  USF_REQUIRE(p != nullptr, "out of host memory");
+  p->d_in = d_in;
+  p->mode = mode;
+  p->max_rows = max_rows;
+  *plan = p;
+  return USF_OK;
+}
+
+int usf_plan_add_linear(usf_plan* p, const usf_plan_linear* st) {
+  USF_REQUIRE(p && st && !p->finalized, "bad input (plan null or already finalized)");
+  USF_REQUIRE(st->N > 0 && st->K > 0 && st->w, "bad step");
+  USF_REQUIRE(st->src == USF_PLAN_SRC_STREAM || st->src == USF_PLAN_SRC_HIDDEN, "bad step source");
+  USF_REQUIRE(st->dst >= USF_PLAN_DST_STREAM && st->dst <= USF_PLAN_DST_SEGMENT, "bad step destination");
+  USF_REQUIRE(st->src == USF_PLAN_SRC_STREAM || !p->steps.empty(), "the first step reads the stream");
+  p->steps.push_back(*st);
+  return USF_OK;
+}
+
+int usf_plan_set_base(usf_plan* p, int32_t base_kind, const float* loc, const float* scale, float add_const) {
+  USF_REQUIRE(p && loc && scale && (base_kind == USF_BASE_LAPLACE || base_kind == USF_BASE_NORMAL), "bad input");
+  p->base_kind = base_kind;
+  p->loc = loc;
+  p->scale = scale;
+  p->add_const = add_const;
+  return USF_OK;
+}
+
+int64_t usf_plan_workspace_bytes(const usf_plan* p) {
+  if (!p) return 0;
+  int64_t ws = p->d_in, wh = 8;
+  for (const auto& st : p->steps) {
+    if (st.dst == USF_PLAN_DST_HIDDEN) wh = st.N > wh ? st.N : wh;
+    if (st.dst == USF_PLAN_DST_STREAM) ws = st.N > ws ? st.N : ws;
+  }
+  // the ingest copy of the input may need the fp32 plane too (unaligned caller tensors in the tf32 / simt modes)
+  return 2 * (int64_t)planes_bytes(stream_planes(p->mode) | 1, p->max_rows, ws) +
+         2 * (int64_t)planes_bytes(hidden_planes(p->mode), p->max_rows, wh) + (int64_t)p->max_rows * pad_to(ws, 8) * 4 + 256;
+}
+
+int usf_plan_finalize(usf_plan* p) {
+  USF_REQUIRE(p && !p->finalized && !p->steps.empty(), "bad plan");
+  USF_REQUIRE(p->steps.back().dst == USF_PLAN_DST_STREAM, "the last step of a plan writes the stream");
+  int64_t ws = p->d_in, wh = 8;
+  int32_t width = p->d_in;
+  for (const auto& st : p->steps) {
+    if (st.dst == USF_PLAN_DST_HIDDEN) wh = st.N > wh ? st.N : wh;
+    if (st.dst == USF_PLAN_DST_STREAM) { ws = st.N > ws ? st.N : ws; width = st.N; }
+  }
+  p->out_width = width;
+  const size_t total = (size_t)usf_plan_workspace_bytes(p);
+  USF_CUDA_OK(cudaMalloc(&p->mem, total));
+  char* at = reinterpret_cast<char*>(p->mem);
+  for (int i = 0; i < 2; ++i) carve_planes(&p->x[i], stream_planes(p->mode) | 1, p->max_rows, ws, at);
+  for (int i = 0; i < 2; ++i) carve_planes(&p->h[i], hidden_planes(p->mode), p->max_rows, wh, at);
+  p->fin = reinterpret_cast<float*>(at);
+  p->ld_fin = pad_to(ws, 8);
+  p->finalized = true;
+  return USF_OK;
+}
+
+int usf_flow_apply(const usf_plan* p, const float* x, int64_t ldx, int64_t rows, float* z, int64_t ldz, int32_t* overflow_flag,
+                   void* stream) {
+  return plan_run(p, x, ldx, rows, z, ldz, overflow_flag, stream);
+}
+
+int usf_flow_logprob(const usf_plan* p, const float* x, int64_t ldx, int64_t rows, float* out, int32_t* overflow_flag,
+                     void* stream) {
+  USF_REQUIRE(p && p->finalized && p->base_kind >= 0 && out, "plan without a base density (usf_plan_set_base)");
+  int rc = plan_run(p, x, ldx, rows, p->fin, p->ld_fin, overflow_flag, stream);
+  if (rc) return rc;
+  return usf_base_logprob(p->fin, nullptr, p->ld_fin, rows, p->out_width, p->loc, p->scale, p->base_kind, p->add_const, out,
+                          stream);
+}
+
+int usf_plan_destroy(usf_plan* p) {
+  if (!p) return USF_OK;
+  if (p->mem) cudaFree(p->mem);
+  delete p;
   return USF_OK;
 }
 

@@ -729,6 +729,26 @@ class Program:
                     ops.permute(cur.f32, st.perm, out.f32)
                 cur = out
 
+    # -- whole-stack C entry (usf_plan_* / usf_flow_*): one call per chunk instead of one per launch --------------------
+    def plan_able(self) -> bool:
+        return (self.small is None and not self.force_fallback and not self.has_row_ladj and bool(self.steps)
+                and all(st.kind == "mm" and st.dst in ("x", "h") and st.src in ("x", "h")
+                        and (not st.resid or st.out_seg is not None) for st in self.steps)
+                and self.steps[-1].dst == "x" and self.steps[-1].out_seg is None)
+
+    def c_plan(self, d_in: int, max_rows: int, base=None, add_const: float = 0.0) -> "CPlan":
+        """The launch program as a library-owned plan (None when a step kind is outside its scope).  Cached per
+        (input width, rows capacity, base parameters)."""
+        if not self.plan_able():
+            return None
+        key = (d_in, max_rows, None if base is None else tuple(t.data_ptr() for t in base._prepared()), float(add_const))
+        cache = self.__dict__.setdefault("_c_plans", {})
+        if key not in cache:
+            if len(cache) >= 4:
+                cache.pop(next(iter(cache))).close()
+            cache[key] = CPlan(self, d_in, max_rows, base, add_const)
+        return cache[key]
+
     def _operand_planes(self) -> set:
         return {"fp32": {"h16", "l16"}, "fp32_tf32": {"hi", "lo"}, "bf16": {"bf16"}}.get(self.mode, {"f32"})
 
@@ -738,6 +758,74 @@ class Program:
         prog.mode, prog.items, prog.compress, prog.steps, prog.small, prog.has_row_ladj = mode, [], None, steps, None, False
         prog.layers, prog.direction, prog._fallback_prog, prog._wflag, prog.force_fallback = [], "forward", None, None, False
         return prog
+
+
+class CPlan:
+    """Owner of one `usf_plan` (include/usflows_b200.h, "Whole-stack evaluation"): keeps the Program (whose operand planes
+    the plan points into) and the base parameters alive, destroys the plan with itself."""
+
+    def __init__(self, prog: "Program", d_in: int, max_rows: int, base=None, add_const: float = 0.0):
+        import ctypes as C
+        from . import _lib
+        lib = _lib.load()
+        self._lib, self.prog, self.base, self.max_rows, self.d_in = lib, prog, base, int(max_rows), int(d_in)
+        handle = C.c_void_p()
+        _lib.check(lib.usf_plan_create(C.byref(handle), d_in, _lib.MODE_CODES[prog.mode], int(max_rows)))
+        self.handle = handle
+        self._keep = []
+        try:
+            for st in prog.steps:
+                s = _lib.PlanLinear()
+                s.N, s.K, s.engine, s.relu = st.N, st.K, st.engine, int(st.relu)
+                s.w, s.w_lo, s.ldw = st.w.data_ptr(), (None if st.w_lo is None else st.w_lo.data_ptr()), ops._ld(st.w)
+                s.bias = None if st.bias is None else st.bias.data_ptr()
+                s.src = _lib.PLAN_SRC_STREAM if st.src == "x" else _lib.PLAN_SRC_HIDDEN
+                if st.dst == "h":
+                    s.dst = _lib.PLAN_DST_HIDDEN
+                elif st.resid:
+                    if st.out_seg is None:
+                        raise NotImplementedError("coupling outputs on the whole stream are not in the plan's scope")
+                    s.dst, s.out_col0 = _lib.PLAN_DST_SEGMENT, st.out_seg[0]
+                else:
+                    s.dst = _lib.PLAN_DST_STREAM
+                if st.in_seg is not None:
+                    s.in_col0, s.in_width = st.in_seg
+                s.resid_sign = float(st.sign)
+                _lib.check(lib.usf_plan_add_linear(handle, C.byref(s)))
+            if base is not None:
+                loc, scale = base._prepared()
+                self._keep += [loc, scale]
+                _lib.check(lib.usf_plan_set_base(handle, base.base_kind, loc.data_ptr(), scale.data_ptr(), float(add_const)))
+            with ops.on_device(prog.steps[0].w):
+                _lib.check(lib.usf_plan_finalize(handle))
+        except Exception:
+            self.close()
+            raise
+        self.out_width = prog.out_width(d_in)
+
+    def close(self) -> None:
+        if getattr(self, "handle", None) is not None:
+            self._lib.usf_plan_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:                      # noqa: BLE001  (interpreter shutdown)
+            pass
+
+    def log_prob(self, x: torch.Tensor, out: torch.Tensor, flag: Optional[torch.Tensor] = None) -> None:
+        """out[r] = log p(x[r]) for r < rows <= max_rows on the current stream."""
+        ops.LAUNCHES += len(self.prog.steps) + 2
+        from . import _lib
+        _lib.check(self._lib.usf_flow_logprob(self.handle, x.data_ptr(), ops._ld(x), x.shape[0], out.data_ptr(),
+                                              None if flag is None else flag.data_ptr(), ops._stream()))
+
+    def apply(self, x: torch.Tensor, z: torch.Tensor, flag: Optional[torch.Tensor] = None) -> None:
+        ops.LAUNCHES += len(self.prog.steps) + 1
+        from . import _lib
+        _lib.check(self._lib.usf_flow_apply(self.handle, x.data_ptr(), ops._ld(x), x.shape[0], z.data_ptr(), ops._ld(z),
+                                            None if flag is None else flag.data_ptr(), ops._stream()))
 
 
 # --------------------------------------------------------------------------------------------------
@@ -907,13 +995,17 @@ def profile_step(fn) -> dict:
             records.append((label, e0, e1))
         return inner
 
+    from . import flows
+    use_plan = flows.USE_C_PLAN
     try:
+        flows.USE_C_PLAN = False               # launch by launch from Python, so that every launch can be bracketed
         for name, f in originals.items():
             setattr(ops, name, wrap(name, f))
         torch.cuda.synchronize()
         fn()
         torch.cuda.synchronize()
     finally:
+        flows.USE_C_PLAN = use_plan
         for name, f in originals.items():
             setattr(ops, name, f)
     out = {}

@@ -22,6 +22,8 @@ from .transforms import (BaseTransform, BlockAffineTransform, HouseholderTransfo
 
 
 SMALL_BATCH_GRAPH_ROWS = 4096   # `log_prob` on at most this many rows replays one captured CUDA graph (0 = off)
+USE_C_PLAN = True             # device-resident `log_prob` / `backward` / `_forward`: ONE C call per chunk (usf_flow_logprob /
+                              # usf_flow_apply on a library-owned plan) where the program is contractions only
 HOST_CUDA_GRAPHS = True       # `log_prob_host`: replay one captured CUDA graph per full-size chunk
 HOST_CHUNK_ROWS = 16384      # rows per H2D copy / kernel batch of `log_prob_host` (copy i+1 overlaps compute i)
 HOST_CHUNK_UNITS = (1, 1, 2, 3)   # `log_prob_host` chunk sizes in wave-aligned units (the last entry repeats).  Only the first
@@ -173,6 +175,9 @@ class Flow(torch.nn.Module):
             lp = self._log_prob_small_batch(prog, ladj, x2)
             if lp is not None:
                 return lp.reshape(batch_shape)
+        if USE_C_PLAN and x2.is_cuda and rows > 0 and prog.plan_able() and getattr(base, "base_kind", -1) >= 0 \
+                and not torch.cuda.is_current_stream_capturing():
+            return self._log_prob_plan(prog, base, ladj, x2).reshape(batch_shape)
         out = torch.empty(rows, dtype=torch.float32, device=x2.device)
 
         def sink(z_chunk, r0, r1):
@@ -187,6 +192,40 @@ class Flow(torch.nn.Module):
             else:
                 prog.run(x2, sink=sink)
         return out.reshape(batch_shape)
+
+    @staticmethod
+    def _plan_chunks(rows: int):
+        """(chunk rows, plan capacity) as `Program.run` would cut the batch; the capacity is rounded up so that a few plans
+        serve every batch size."""
+        cap = engine._default_chunk_rows
+        n_chunks = (rows + cap - 1) // cap
+        chunk = min(rows, ((rows + n_chunks - 1) // n_chunks + 255) // 256 * 256)
+        size = 4096
+        while size < chunk:
+            size *= 2
+        return chunk, min(size, max(cap, chunk))
+
+    def _log_prob_plan(self, prog, base, ladj: float, x2: torch.Tensor) -> torch.Tensor:
+        """`log_prob` through the whole-stack C entry: one `usf_flow_logprob` call per chunk (ingest, every contraction and
+        the base density are launched by the library).  Same kernels, same order, same bits as the launch-by-launch route."""
+        rows, d = x2.shape
+        x2 = x2.contiguous()
+        chunk, capacity = self._plan_chunks(rows)
+        with torch.no_grad():
+            plan = prog.c_plan(d, capacity, base, -ladj)
+            out = torch.empty(rows, dtype=torch.float32, device=x2.device)
+            starts = list(range(0, rows, chunk))
+            flags = torch.zeros(len(starts), dtype=torch.int32, device=x2.device) if prog.mode == "fp32" else None
+            for ci, r0 in enumerate(starts):
+                r1 = min(rows, r0 + chunk)
+                plan.log_prob(x2[r0:r1], out[r0:r1], None if flags is None else flags[ci:ci + 1])
+            if flags is not None:                       # chunks that left the fp16 range: tf32-split engine, launch by launch
+                for ci in torch.nonzero(flags).reshape(-1).tolist():
+                    r0 = starts[ci]
+                    r1 = min(rows, r0 + chunk)
+                    prog._fallback().run(x2[r0:r1], sink=lambda z, a, b, r0=r0: base._density_into(
+                        ops.Act(b - a, z.shape[1], f32=z), -ladj, out[r0 + a:r0 + b]))
+        return out
 
     def _log_prob_small_batch(self, prog, ladj: float, x2: torch.Tensor):
         """Small batches are bound by the host-side cost of ~23 kernel launches (~40 us each through ctypes + tensor-map
@@ -462,11 +501,34 @@ class Flow(torch.nn.Module):
             self._programs[direction] = hit
         return hit[1], hit[2]
 
+    def _apply_plan(self, prog, x2: torch.Tensor) -> torch.Tensor:
+        rows, d = x2.shape
+        x2 = x2.contiguous()
+        chunk, capacity = self._plan_chunks(rows)
+        plan = prog.c_plan(d, capacity)
+        width = prog.out_width(d)
+        y = torch.empty(rows, width, dtype=torch.float32, device=x2.device)
+        starts = list(range(0, rows, chunk))
+        flags = torch.zeros(len(starts), dtype=torch.int32, device=x2.device) if prog.mode == "fp32" else None
+        for ci, r0 in enumerate(starts):
+            r1 = min(rows, r0 + chunk)
+            plan.apply(x2[r0:r1], y[r0:r1], None if flags is None else flags[ci:ci + 1])
+        if flags is not None:
+            for ci in torch.nonzero(flags).reshape(-1).tolist():
+                r0 = starts[ci]
+                r1 = min(rows, r0 + chunk)
+                prog._fallback().run(x2[r0:r1], out=y[r0:r1])
+        return y
+
     def _run(self, direction: str, x: torch.Tensor) -> torch.Tensor:
         x2, batch_shape = engine._flatten_rows(x, len(self._event_shape()))
         with torch.no_grad(), ops.on_device(x2):
             prog, _ = self._program(direction)
-            y = prog.run(x2)
+            if USE_C_PLAN and x2.is_cuda and x2.shape[0] > 0 and prog.plan_able() \
+                    and not torch.cuda.is_current_stream_capturing():
+                y = self._apply_plan(prog, x2)
+            else:
+                y = prog.run(x2)
         return y.reshape(*batch_shape, *self._event_shape())
 
 
