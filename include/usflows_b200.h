@@ -115,7 +115,7 @@ typedef struct usf_linear_args {
   void* out_l16;
   int64_t ld_16;
   int32_t* overflow_flag; /* device int, set to 1 if a value written to out_h16 exceeds the fp16 range */
-  /* ABI 4.  split_k > 1 (CTA-pair tcgen05 engines only; ignored elsewhere): the contraction over K is cut into up to
+  /* ABI 4.  split_k > 1 (the fp16-split engine TC_3XF16 only; ignored elsewhere): the contraction over K is cut into up to
    * split_k pieces that run on different CTA pairs and are summed into out_f32 with vector reductions -- for products
    * with a small output and a long K, i.e. the weight gradients dW[N_w, K_w] = dY^T . X of the training pass
    * (reference: autograd of F.linear, flows.py:199).  Requires out_f32 (16-byte aligned, ld_f32 % 4 == 0, N % 8 == 0)

@@ -171,7 +171,7 @@ int usf_linear(const usf_linear_args* a, void* stream) {
     case USF_ENGINE_TC_TF32:
     case USF_ENGINE_TC_BF16:
     case USF_ENGINE_TC_3XF16:
-      if (a->split_k > 1 && (g_tc_impl == 2 || a->engine == USF_ENGINE_TC_3XF16) && a->M > 0 && a->N > 0)   // partial tiles are added: start from zero
+      if (a->split_k > 1 && a->engine == USF_ENGINE_TC_3XF16 && a->M > 0 && a->N > 0)   // partial tiles are added: start from zero
         USF_CUDA_OK(cudaMemset2DAsync(a->out_f32, (size_t)a->ld_f32 * 4, 0, (size_t)a->N * 4, (size_t)a->M, S(stream)));
       return launch_gemm_tc(a, ep, S(stream));
   }

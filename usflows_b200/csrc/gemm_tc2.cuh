@@ -83,8 +83,16 @@ __device__ __forceinline__ int chain_count(int k_slabs, int chunk, int lead) {
 // split_k > 1 (dW = dY^T . X of the training pass: a small output and a contraction over all batch rows) the K range of a
 // tile is cut into split_k pieces that run on different CTA pairs and meet in the fp32 output through red.global.add.
 struct TileCoord { long long m_blk; int n_blk; int ks_begin; int nks; };
+template <bool SPLITK>
 __device__ __forceinline__ TileCoord decode_tile(long long tile, int n_blocks, int split_k, int k_slabs) {
   TileCoord t;
+  if (!SPLITK) {
+    t.m_blk = tile / n_blocks;
+    t.n_blk = (int)(tile % n_blocks);
+    t.ks_begin = 0;
+    t.nks = k_slabs;
+    return t;
+  }
   const int sk = (int)(tile % split_k);
   const long long mn = tile / split_k;
   t.m_blk = mn / n_blocks;
@@ -620,10 +628,10 @@ __device__ __forceinline__ void async_piece(const Epilogue& ep, const EpiRegs& e
 }
 
 // One epilogue warp: TMEM lanes [32*quarter, +32) x columns [col0, col0+COLS) of every tile of this CTA.
-template <class C, int COLS>
+template <class C, int COLS, bool SPLITK>
 __device__ __forceinline__ void epilogue_loop(int col0, int quarter, int lane, uint32_t rank, uint32_t tmem_base,
                                               uint32_t tfull0, uint32_t tempty0_leader, uint8_t* stage_gen,
-                                              uint32_t stage, uint32_t inbox, long long n_tiles, int n_blocks, int k_slabs, int split_k, int chunk_slabs, int lead,
+                                              uint32_t stage, long long n_tiles, int n_blocks, int k_slabs, int split_k, int chunk_slabs, int lead,
                                               long long M, int N, const Epilogue& ep, unsigned long long* dbg, int dbg_flags,
                                               const StoreMaps& smaps) {
   constexpr int BLOCK_N = C::kBlockN;
@@ -634,9 +642,11 @@ __device__ __forceinline__ void epilogue_loop(int col0, int quarter, int lane, u
   float* patch = reinterpret_cast<float*>(stage_gen);
   // everything the tile loop needs lives in registers from here on (opaque to the compiler): re-deriving these from
   // special registers / the parameter bank inside the loop costs a dependent S2R / LDC per use
-  asm volatile("" : "+r"(stage), "+r"(tfull0), "+r"(tempty0_leader), "+r"(tmem_base), "+r"(inbox));
+  asm volatile("" : "+r"(stage), "+r"(tfull0), "+r"(tempty0_leader), "+r"(tmem_base));
+  // the warp's in-box sits right behind its staging boxes (no register of its own); debug flag 256 switches it off
+  const uint32_t inbox = (C::INBOX && !(dbg_flags & 256)) ? stage + STAGE_EPI_BYTES : 0u;
   asm volatile("" : "+l"(M), "+r"(N), "+r"(lane), "+r"(quarter), "+r"(col0), "+r"(rank), "+r"(n_blocks), "+l"(n_tiles),
-               "+r"(n_chunks), "+r"(dbg_flags), "+r"(split_k), "+r"(k_slabs));
+               "+r"(n_chunks), "+r"(dbg_flags));
   const EpiRegs er = load_epi_regs(ep);
   const bool fast_store = ep.fast_store != 0;
   const bool async_store = ep.async_store != 0;
@@ -644,8 +654,8 @@ __device__ __forceinline__ void epilogue_loop(int col0, int quarter, int lane, u
   for (long long tile = cluster_id_x(); tile < n_tiles; tile += num_clusters_x()) {
     long long m_blk = tile / n_blocks;
     int n_blk = (int)(tile % n_blocks);
-    if (split_k > 1) {
-      const TileCoord tc = decode_tile(tile, n_blocks, split_k, k_slabs);
+    if (SPLITK) {
+      const TileCoord tc = decode_tile<true>(tile, n_blocks, split_k, k_slabs);
       m_blk = tc.m_blk;
       n_blk = tc.n_blk;
       n_chunks = chain_count(tc.nks, chunk_slabs, lead);
@@ -777,7 +787,7 @@ __device__ __forceinline__ void epilogue_loop(int col0, int quarter, int lane, u
   __syncwarp();
 }
 
-template <int BLOCK_N, int NTERMS, int KIND>
+template <int BLOCK_N, int NTERMS, int KIND, bool SPLITK = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_a_lo,
                 const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_w_lo,
@@ -803,7 +813,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
   const int n_blocks = (N + BLOCK_N - 1) / BLOCK_N;
   const long long m_blocks = (M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
   const int k_slabs = (K + C::ELEMS_PER_SLAB - 1) / C::ELEMS_PER_SLAB;
-  if (split_k < 1) split_k = 1;
+  if (!SPLITK || split_k < 1) split_k = 1;
   const long long n_tiles = m_blocks * n_blocks * split_k;
   if (chunk_slabs <= 0 || chunk_slabs > k_slabs) chunk_slabs = k_slabs;
   if (KIND == KIND_F16 && NTERMS == 3) chunk_slabs = 1;   // the 2^-11 rescale happens once per accumulation chain
@@ -849,7 +859,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         int stage = 0;
         uint32_t phase = 0;
         for (long long tile = cluster_id_x(); tile < n_tiles; tile += num_clusters_x()) {
-          const TileCoord tc = decode_tile(tile, n_blocks, split_k, k_slabs);
+          const TileCoord tc = decode_tile<SPLITK>(tile, n_blocks, split_k, k_slabs);
           const int m_idx = (int)tc.m_blk * (2 * BLOCK_M) + (int)rank * BLOCK_M;
           const int n_tile = tc.n_blk * BLOCK_N;
           const int n_idx = n_tile + (int)rank * (tile_width(n_tile) >> 1);   // this CTA stages its half of the W rows
@@ -879,7 +889,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
       int dbg_chain = 0;
       unsigned long long* dbg_mma = (cluster_id_x() == 0 && lane == 0) ? dbg_buf : nullptr;
       for (long long tile = cluster_id_x(); tile < n_tiles; tile += num_clusters_x()) {
-        const TileCoord tc = decode_tile(tile, n_blocks, split_k, k_slabs);
+        const TileCoord tc = decode_tile<SPLITK>(tile, n_blocks, split_k, k_slabs);
         const uint32_t idesc = C::IDESC_NO_N | ((uint32_t)(tile_width(tc.n_blk * BLOCK_N) >> 3) << 17);
         const int lead = chain_lead(tc.nks, chunk_slabs, lead_chains);
         const int ks_last = k_slabs - 1 - tc.ks_begin;   // index (within this work item) of the K tail slab, if it is here
@@ -985,20 +995,19 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
   } else {
     // ===================== epilogue warps (TMEM lane quarter = warp % 4; column half = (warp-4)/4) ======
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_EPI));
-    const uint32_t stage_u32 = epi_base + (warp - FIRST_EPI_WARP) * STAGE_EPI_BYTES;
+    const uint32_t stage_u32 = epi_base + (warp - FIRST_EPI_WARP) * (STAGE_EPI_BYTES + (C::INBOX ? INBOX_BYTES : 0));
     uint8_t* stage = smem_gen + (stage_u32 - smem_base);
-    const uint32_t inbox_u32 = (C::INBOX && !(dbg_flags & 256))
-                                   ? epi_base + NUM_EPI_WARPS * STAGE_EPI_BYTES + (warp - FIRST_EPI_WARP) * INBOX_BYTES : 0u;
+
     const uint32_t tempty_leader = mapa(tempty_bar(0), 0);
     unsigned long long* dbg_epi = (cluster_id_x() == 0 && rank == 0 && warp == FIRST_EPI_WARP && lane == 0) ? dbg_buf : nullptr;
     if (C::HALF0 == C::HALF1)     // one copy of the epilogue code serves both column halves
-      epilogue_loop<C, C::HALF0>(warp < FIRST_EPI_WARP + 4 ? 0 : C::HALF0, warp & 3, lane, rank, tmem_base, tfull_bar(0),
-                                 tempty_leader, stage, stage_u32, inbox_u32, n_tiles, n_blocks, k_slabs, split_k, chunk_slabs, lead_chains, M, N, ep, dbg_epi, dbg_flags, smaps);
+      epilogue_loop<C, C::HALF0, SPLITK>(warp < FIRST_EPI_WARP + 4 ? 0 : C::HALF0, warp & 3, lane, rank, tmem_base, tfull_bar(0),
+                                 tempty_leader, stage, stage_u32, n_tiles, n_blocks, k_slabs, split_k, chunk_slabs, lead_chains, M, N, ep, dbg_epi, dbg_flags, smaps);
     else if (warp < FIRST_EPI_WARP + 4)
-      epilogue_loop<C, C::HALF0>(0, warp & 3, lane, rank, tmem_base, tfull_bar(0), tempty_leader, stage, stage_u32, inbox_u32, n_tiles,
+      epilogue_loop<C, C::HALF0, SPLITK>(0, warp & 3, lane, rank, tmem_base, tfull_bar(0), tempty_leader, stage, stage_u32, n_tiles,
                                  n_blocks, k_slabs, split_k, chunk_slabs, lead_chains, M, N, ep, dbg_epi, dbg_flags, smaps);
     else
-      epilogue_loop<C, C::HALF1>(C::HALF0, warp & 3, lane, rank, tmem_base, tfull_bar(0), tempty_leader, stage, stage_u32, inbox_u32,
+      epilogue_loop<C, C::HALF1, SPLITK>(C::HALF0, warp & 3, lane, rank, tmem_base, tfull_bar(0), tempty_leader, stage, stage_u32,
                                  n_tiles, n_blocks, k_slabs, split_k, chunk_slabs, lead_chains, M, N, ep, nullptr, dbg_flags, smaps);
   }
 
@@ -1040,12 +1049,15 @@ inline int make_store_map16(CUtensorMap* map, const void* ptr, long long rows, l
   return USF_OK;
 }
 
-template <int BLOCK_N, int NTERMS, int KIND>
+template <int BLOCK_N, int NTERMS, int KIND, bool SPLITK = false>
 int launch_gemm_tc2_cfg(const usf_linear_args* a, const Epilogue& ep_in, cudaStream_t st) {
   using C = tc2::Config<BLOCK_N, NTERMS, KIND>;
+  // split-K exists for the fp16-split engine (the training pass); every other engine runs the plain kernel
+  if (!SPLITK && NTERMS == 3 && KIND == tc2::KIND_F16 && a->split_k > 1)
+    return launch_gemm_tc2_cfg<BLOCK_N, NTERMS, KIND, NTERMS == 3 && KIND == tc2::KIND_F16>(a, ep_in, st);
   static bool attr_set_dev[MAX_DEVICES] = {false};
   bool& attr_set = attr_set_dev[current_device_slot()];
-  auto kern = tc2::gemm_tc2_kernel<BLOCK_N, NTERMS, KIND>;
+  auto kern = tc2::gemm_tc2_kernel<BLOCK_N, NTERMS, KIND, SPLITK>;
   const int dt = KIND == tc2::KIND_TF32 ? 0 : KIND == tc2::KIND_BF16 ? 1 : 2;
   if (!attr_set) {
     USF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
@@ -1079,7 +1091,7 @@ int launch_gemm_tc2_cfg(const usf_linear_args* a, const Epilogue& ep_in, cudaStr
   // split-K (training: dW = dY^T . X): the K-slabs of a tile are cut into `split_k` work items that add their partial tiles
   // into the fp32 output (red.global.add.v4.f32); the caller zeroes / pre-loads the output (usf_linear does, see capi.cu)
   int split_k = 1;
-  if (a->split_k > 1) {
+  if (SPLITK && a->split_k > 1) {
     const int k_slabs = (int)((a->K + C::ELEMS_PER_SLAB - 1) / C::ELEMS_PER_SLAB);
     const int per = (k_slabs + a->split_k - 1) / a->split_k;
     split_k = (k_slabs + per - 1) / per;                    // every work item gets at least one slab

@@ -524,7 +524,7 @@ class Flow(torch.nn.Module):
         x2, batch_shape = engine._flatten_rows(x, len(self._event_shape()))
         with torch.no_grad(), ops.on_device(x2):
             prog, _ = self._program(direction)
-            if USE_C_PLAN and x2.is_cuda and x2.shape[0] > 0 and prog.plan_able() \
+            if USE_C_PLAN and x2.is_cuda and x2.shape[0] > 0 and isinstance(prog, engine.Program) and prog.plan_able() \
                     and not torch.cuda.is_current_stream_capturing():
                 y = self._apply_plan(prog, x2)
             else:
