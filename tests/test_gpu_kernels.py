@@ -427,3 +427,54 @@ def test_mat_prep_and_tri_mask():
     ops.tri_mask(sq, 1, 0.5, o1, diag_src=diag_src, coef=2.0)
     assert torch.equal(o0, 0.5 * sq.tril(-1))
     assert rel_err(o1, 0.5 * sq.triu() + torch.diag(2.0 / diag_src.diagonal())) <= 1e-6
+
+
+@pytest.mark.parametrize("eng_name,eng,fmt", [("tf32", 2, "f32"), ("bf16", 3, "bf16"), ("3xf16", 4, "f16")])
+@pytest.mark.parametrize("planes", ["bf16", "bf16+f32+resid", "f32", "f32+resid"])
+@pytest.mark.parametrize("M,N,K", [(300, 784, 392), (70000, 1024, 64), (515, 392, 1024), (130, 600, 72), (64, 48, 40), (257, 112, 64)])
+def test_tma_store_path_for_bf16_and_fp32_planes(eng_name, eng, fmt, planes, M, N, K):
+    """Mode 2 of the asynchronous store path (bf16 plane and / or fp32 plane leave through TMA tensor stores: the bf16 and
+    tf32 precision modes, and every fp32 result of the fp16-split engine) == the epilogue warps storing themselves (flag 32)
+    == the generic register path (flag 4), including the in-place coupling form with an fp32 residual stream."""
+    from usflows_b200 import _lib, ops
+    from usflows_b200.ops import Act
+    g = torch.Generator().manual_seed(M + N + K)
+    a = torch.randn(M, K, generator=g)
+    w = torch.randn(N, K, generator=g) / K ** 0.5
+    bias = torch.randn(N, generator=g).cuda()
+    x0 = torch.randn(M, N, generator=g)
+    act, a_used = _f16_planes(a) if fmt == "f16" else _planes(a, fmt)
+    wact, w_used = _f16_planes(w) if fmt == "f16" else _planes(w, fmt)
+    w_hi = wact.h16 if fmt == "f16" else wact.bf16 if fmt == "bf16" else wact.f32
+    w_lo = wact.l16 if fmt == "f16" else None
+    lib = _lib.load()
+    results = []
+    for flags in (0, 32, 4):
+        out = Act(M, N)
+        if "f32" in planes:
+            out.f32 = torch.zeros(M, ops.pad4(N), device="cuda")[:, :N]
+            out.f32.copy_(x0)
+        if "bf16" in planes:
+            out.bf16 = torch.zeros(M, ops.pad4(N), device="cuda", dtype=torch.bfloat16)[:, :N]
+        resid = Act(M, N, f32=out.f32) if "resid" in planes else None           # in place on the fp32 stream
+        lib.usf_debug_gemm_timeline(None, flags)
+        try:
+            ops.linear(eng, act, w_hi, w_lo, N, K, bias=bias, relu="resid" not in planes, resid=resid, resid_sign=-1.0, out=out)
+            torch.cuda.synchronize()
+        finally:
+            lib.usf_debug_gemm_timeline(None, 0)
+        results.append(out)
+    p = results[0]
+    for q in results[1:]:
+        for name in ("f32", "bf16"):
+            if getattr(p, name) is not None:
+                assert torch.equal(getattr(p, name), getattr(q, name)), name
+    ref = a_used.double() @ w_used.double().T + bias.double().cpu()
+    ref = x0.double() - ref if "resid" in planes else torch.relu(ref)
+    tol = {"tf32": 3e-3, "bf16": 3e-6, "3xf16": 3e-6}[eng_name]
+    got = p.f32 if p.f32 is not None else p.bf16.float()
+    assert rel_err(got, ref) <= (tol if p.f32 is not None else 1e-2)
+    for name in ("f32", "bf16"):                      # padding columns beyond N stay untouched
+        t = getattr(p, name)
+        if t is not None and ops.pad4(N) != N and "f32" not in planes:
+            assert float(t._base[:, N:].abs().float().max()) == 0.0

@@ -452,6 +452,19 @@ class TrainEngine:
         return loss
 
     # ------------------------------------------------------------------------------------------------------------
+    def bind_grad_buffers(self, view_of) -> None:
+        """Let the large gradients (LU factors, conditioner weights) be written straight into caller-owned buffers
+        (`view_of(param)` -> tensor of the parameter's shape: the slices of the all-reduce buckets), so that the exchange
+        needs no copy in or out."""
+        for st in self.lus.values():
+            st.gL, st.gU, st.gb = view_of(st.lu.L_raw), view_of(st.lu.U_raw), view_of(st.lu.bias_vector)
+        for op in self.plan:
+            if op["kind"] == "coupling":
+                for L in op["layers"]:
+                    L["gw"], L["gb"] = view_of(L["lin"].weight), view_of(L["lin"].bias)
+                    L["gw"].zero_()                       # (only the gathered rows / columns are rewritten each step)
+                    L["gb"].zero_()
+
     def _set_grad(self, p: torch.nn.Parameter, g: torch.Tensor) -> None:
         if p.grad is None or p.grad.shape != g.shape:
             p.grad = g                    # persistent buffers of the engine: no copy

@@ -431,7 +431,8 @@ class GradReducer:
         b = self.buckets[bi]
         if b["filled"][vi]:
             return
-        b["views"][vi].copy_(p.grad)
+        if p.grad.data_ptr() != b["views"][vi].data_ptr():     # (the engine writes its gradients straight into the views)
+            b["views"][vi].copy_(p.grad)
         b["filled"][vi] = True
         b["ready"] += 1
         if b["ready"] == len(b["params"]):
@@ -446,7 +447,7 @@ class GradReducer:
                     if not b["filled"][vi]:
                         if p.grad is None:
                             b["views"][vi].zero_()
-                        else:
+                        elif p.grad.data_ptr() != b["views"][vi].data_ptr():
                             b["views"][vi].copy_(p.grad)
                 self._launch(b)
         for b in self.buckets:
@@ -454,9 +455,15 @@ class GradReducer:
             for p, v in zip(b["params"], b["views"]):
                 if p.grad is None:
                     p.grad = v.clone()
-                else:
+                elif p.grad.data_ptr() != v.data_ptr():
                     p.grad.copy_(v)
         return self.floats
+
+    def view_of(self, p) -> torch.Tensor:
+        """The slice of the bucket buffer that holds `p`'s gradient: a backward pass that writes there directly (and sets
+        `p.grad` to it) saves the copy into the bucket and the copy back."""
+        bi, vi = self._where[id(p)]
+        return self.buckets[bi]["views"][vi]
 
 
 class TrainStep:
@@ -570,6 +577,8 @@ class TrainStep:
                 if len(self._engines) >= 2:                    # full batches + one ragged last batch
                     self._engines.pop(next(iter(self._engines)))
                 eng = self._engines[rows] = train_engine.TrainEngine(flow, rows)
+                if self.reducer is not None:                   # gradients land in the all-reduce buckets directly
+                    eng.bind_grad_buffers(self.reducer.view_of)
             eng.flag.zero_()
             local = eng.step(sample.reshape(rows, -1), total, self.reducer)
             self.out_of_range += eng.flag[0]
