@@ -530,7 +530,12 @@ def main():
     if rank == 0:
         sampler.start()
     ops.LAUNCHES = 0
+    ranged = bool(os.environ.get("USF_PROFILE_RANGE"))          # ncu --profile-from-start off: the timed steps only
+    if ranged:
+        torch.cuda.profiler.start()
     ms_step = timed(step, args.steps)
+    if ranged:
+        torch.cuda.profiler.stop()
     launches = ops.LAUNCHES
     if args.only_logprob:
         if rank == 0:

@@ -313,11 +313,41 @@ class Flow(torch.nn.Module):
         rows, d = x2.shape
         if out_host is None:
             out_host = torch.empty(rows, dtype=torch.float32, pin_memory=True)
-        if isinstance(prog, image_engine.ImageProgram):      # image-shaped events: plain chunked copies (no overlap yet)
+        if isinstance(prog, image_engine.ImageProgram):
+            # image-shaped events: two staging buffers in turn, the H2D copy of chunk i + 1 on the copy stream under the
+            # kernels of chunk i, one D2H copy of all log-probs at the end
             step = max(1, chunk_rows or HOST_CHUNK_ROWS)
-            for r0 in range(0, rows, step):
-                lp = self.log_prob(x2[r0:r0 + step].to(dev, non_blocking=True).reshape(-1, *self._event_shape()))
-                out_host.reshape(-1)[r0:r0 + step].copy_(lp)
+            main = torch.cuda.current_stream(dev)
+            if getattr(self, "_img_stage", None) is None or self._img_stage.shape[1:] != (min(step, max(rows, 1)), d) \
+                    or self._img_stage.device != dev:
+                self._img_stage = torch.empty(2, min(step, max(rows, 1)), d, dtype=torch.float32, device=dev)
+                self._copy_stream = torch.cuda.Stream(device=dev)
+            out_dev = torch.empty(rows, dtype=torch.float32, device=dev)
+            starts = list(range(0, rows, step))
+            copied = [torch.cuda.Event() for _ in range(2)]
+            consumed = [torch.cuda.Event() for _ in range(2)]
+            self._copy_stream.wait_stream(main)
+
+            def issue_copy(i):
+                r0 = starts[i]
+                n = min(step, rows - r0)
+                with torch.cuda.stream(self._copy_stream):
+                    if i >= 2:
+                        self._copy_stream.wait_event(consumed[i % 2])
+                    self._img_stage[i % 2, :n].copy_(x2[r0:r0 + n], non_blocking=True)
+                    copied[i % 2].record(self._copy_stream)
+
+            if starts:
+                issue_copy(0)
+            for i, r0 in enumerate(starts):
+                n = min(step, rows - r0)
+                if i + 1 < len(starts):
+                    issue_copy(i + 1)
+                main.wait_event(copied[i % 2])
+                out_dev[r0:r0 + n] = self._log_prob(self._img_stage[i % 2, :n].reshape(n, *self._event_shape()))
+                consumed[i % 2].record(main)
+            out_host.reshape(-1)[:rows].copy_(out_dev, non_blocking=True)
+            main.synchronize()
             return out_host
         # Chunk schedule.  The H2D copy of chunk i+1 hides under the kernels of chunk i (a row copies faster than it
         # computes), so only the FIRST copy is exposed: start with the smallest wave-aligned chunk and let the later

@@ -26,7 +26,7 @@ import torch
 
 from . import engine
 
-_UNCOPIED = ("_programs", "_host_stage", "_host_out", "_copy_stream", "_cl_perm", "_cl_perm_key", "_sharded")
+_UNCOPIED = ("_programs", "_host_stage", "_host_out", "_img_stage", "_copy_stream", "_cl_perm", "_cl_perm_key", "_sharded")
 
 
 def shard_bounds(n: int, rank: int, world: int):
