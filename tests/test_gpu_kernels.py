@@ -478,3 +478,49 @@ def test_tma_store_path_for_bf16_and_fp32_planes(eng_name, eng, fmt, planes, M, 
         t = getattr(p, name)
         if t is not None and ops.pad4(N) != N and "f32" not in planes:
             assert float(t._base[:, N:].abs().float().max()) == 0.0
+
+
+@pytest.mark.parametrize("M,N,K", [(300, 784, 784), (1000, 1024, 392), (515, 392, 1024), (257, 208, 72), (70000, 256, 128),
+                                   (64, 48, 40)])
+def test_half_size_pipeline_stages_give_the_same_bits(M, N, K):
+    """fp16-split engine: six 64-byte-row stages (64B swizzle; default) == three 128-byte-row stages (128B swizzle): the same
+    sequence of 16-element K steps and the same 64-element accumulation chains, so bit-identical outputs -- plain, with the
+    in-place coupling residual, with an fp32 result, and split-K."""
+    from usflows_b200 import _lib, ops
+    from usflows_b200.ops import Act
+    g = torch.Generator().manual_seed(M + N + K)
+    a = torch.randn(M, K, generator=g)
+    w = torch.randn(N, K, generator=g) / K ** 0.5
+    bias = torch.randn(N, generator=g).cuda()
+    x0 = torch.randn(M, N, generator=g)
+    act, a_used = _f16_planes(a)
+    wact, w_used = _f16_planes(w)
+    lib = _lib.load()
+    res = {}
+    for slab in (64, 128):
+        lib.usf_debug_set_slab(slab)
+        try:
+            plain, _ = _f16_planes(torch.zeros(M, N))
+            ops.linear(ops.ENGINE_TC_3XF16, act, wact.h16, wact.l16, N, K, bias=bias, relu=True, out=plain)
+            stream, _ = _f16_planes(x0)
+            ops.linear(ops.ENGINE_TC_3XF16, act, wact.h16, wact.l16, N, K, bias=bias, resid=stream, resid_sign=-1.0,
+                       out=Act(M, N, h16=stream.h16, l16=stream.l16))
+            f32 = torch.zeros(M, ops.pad4(N, 4), device="cuda")[:, :N]
+            ops.linear(ops.ENGINE_TC_3XF16, act, wact.h16, wact.l16, N, K, bias=bias, out=Act(M, N, f32=f32))
+            aT, _ = _f16_planes(a.t().contiguous())
+            xT, _ = _f16_planes(x0.t().contiguous())
+            dw = torch.zeros(K, ops.pad4(N, 4), device="cuda")[:, :N]
+            ops.linear_splitk(ops.ENGINE_TC_3XF16, aT, xT, N, M, dw, 4)
+            torch.cuda.synchronize()
+        finally:
+            lib.usf_debug_set_slab(64)
+        res[slab] = (plain, stream, f32, dw)
+    for p, q in zip(res[64][:3], res[128][:3]):
+        if isinstance(p, torch.Tensor):
+            assert torch.equal(p, q)
+        else:
+            assert torch.equal(p.h16, q.h16) and torch.equal(p.l16, q.l16)
+    ref = a_used.double() @ w_used.double().T + bias.double().cpu()
+    assert rel_err(res[64][2], ref) <= 3e-6
+    dref = a_used.double().t() @ (x0.to(torch.float16).double() + ((x0 - x0.to(torch.float16).float()) * 2048).to(torch.float16).double() / 2048)
+    assert rel_err(res[64][3], dref) <= 3e-6 and rel_err(res[128][3], dref) <= 3e-6      # (atomic order differs: not bitwise)

@@ -25,6 +25,7 @@ int g_dbg_flags = 0;
 int g_no_fast_store = 0;
 int g_use_pdl = 1;
 int g_no_async_store = 0;
+int g_f16_slab = 64;
 
 int num_sms() {
   static int cached[64] = {0};
@@ -137,6 +138,12 @@ int usf_debug_gemm_timeline(unsigned long long* device_buf, int flags) {
   g_dbg_flags = flags & ~(4 | 32);
   g_no_fast_store = (flags & 4) ? 1 : 0;
   g_no_async_store = (flags & 32) ? 1 : 0;
+  return USF_OK;
+}
+
+int usf_debug_set_slab(int bytes) {  // test hook: K bytes per pipeline stage of the fp16-split engine (64 default, 128)
+  USF_REQUIRE(bytes == 64 || bytes == 128, "slab must be 64 or 128 bytes");
+  g_f16_slab = bytes;
   return USF_OK;
 }
 

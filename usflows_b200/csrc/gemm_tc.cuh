@@ -373,17 +373,17 @@ PFN_encodeTiled get_encode_tiled();
 // 2-D row-major [rows, cols] operand, box = 128 B of K x box_rows rows, 128B swizzle, zero OOB fill
 // dtype: 0 = fp32 / tf32, 1 = bf16, 2 = fp16
 inline int make_operand_map(CUtensorMap* map, const void* ptr, long long rows, long long cols, long long ld,
-                            int box_rows, int dtype) {
+                            int box_rows, int dtype, int slab_bytes = tc::SLAB_BYTES) {
   PFN_encodeTiled enc = get_encode_tiled();
   if (!enc) return fail(USF_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available%s%s");
   const int esz = dtype ? 2 : 4;
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)ld * esz};
-  cuuint32_t box[2] = {(cuuint32_t)(tc::SLAB_BYTES / esz), (cuuint32_t)box_rows};
+  cuuint32_t box[2] = {(cuuint32_t)(slab_bytes / esz), (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, dtype == 1 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : dtype == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
                    const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   slab_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     snprintf(g_err, sizeof(g_err), "cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld cols=%lld ld=%lld)",

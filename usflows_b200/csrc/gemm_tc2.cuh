@@ -84,7 +84,7 @@ __device__ __forceinline__ int chain_count(int k_slabs, int chunk, int lead) {
 // tile is cut into split_k pieces that run on different CTA pairs and meet in the fp32 output through red.global.add.
 struct TileCoord { long long m_blk; int n_blk; int ks_begin; int nks; };
 template <bool SPLITK>
-__device__ __forceinline__ TileCoord decode_tile(long long tile, int n_blocks, int split_k, int k_slabs) {
+__device__ __forceinline__ TileCoord decode_tile(long long tile, int n_blocks, int split_k, int k_slabs, int per) {
   TileCoord t;
   if (!SPLITK) {
     t.m_blk = tile / n_blocks;
@@ -97,8 +97,7 @@ __device__ __forceinline__ TileCoord decode_tile(long long tile, int n_blocks, i
   const long long mn = tile / split_k;
   t.m_blk = mn / n_blocks;
   t.n_blk = (int)(mn % n_blocks);
-  const int per = (k_slabs + split_k - 1) / split_k;
-  t.ks_begin = sk * per;
+  t.ks_begin = sk * per;               // `per` = K-slabs per piece (a whole number of accumulation chains; the launcher's)
   const int rest = k_slabs - t.ks_begin;
   t.nks = rest < per ? rest : per;     // > 0: the launcher keeps (split_k - 1) * per < k_slabs
   return t;
@@ -142,8 +141,25 @@ __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
       : "memory");
 }
 
-template <int BLOCK_N, int NTERMS, int KIND>
+// K-major operand tile with rows of SLAB bytes (128: SWIZZLE_128B, 64: SWIZZLE_64B), 8-row groups 8 * SLAB bytes apart
+template <int SLAB>
+__device__ __forceinline__ uint64_t make_smem_desc_s(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3ffff) >> 4);  // start address, bits [0,14)
+  d |= (uint64_t)1 << 16;                        // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)((8 * SLAB) >> 4) << 32;        // stride byte offset = 8 rows * SLAB B
+  d |= (uint64_t)1 << 46;                        // descriptor version (Blackwell)
+  d |= (uint64_t)(SLAB == 128 ? 2 : 4) << 61;    // SWIZZLE_128B = 2, SWIZZLE_64B = 4
+  return d;
+}
+
+// SLAB = bytes of K per pipeline stage and operand row.  The pipeline is bound by the operand bytes in flight
+// (TMA issue -> landing is ~3 000-3 500 cycles under load; measured: 1 044 of 1 900 cycles per chain the MMA issuer waits
+// for operands with 3 stages of 128-byte slabs, i.e. 2 of 3 stages = 116 KB in flight).  Half-size stages (64-byte rows,
+// 64B swizzle) keep 5 of 6 stages in flight out of the same shared memory.
+template <int BLOCK_N, int NTERMS, int KIND, int SLAB = 128>
 struct Config {
+  static constexpr int SLAB_BYTES = SLAB;       // (shadows tc::SLAB_BYTES inside this configuration)
   static_assert(BLOCK_N % 16 == 0 && BLOCK_N >= 32 && BLOCK_N <= 256, "UMMA N for M=256 (cta_group::2)");
   static_assert(NTERMS == 1 || NTERMS == 3, "1 = single pass, 3 = tf32 split");
   static constexpr int kBlockN = BLOCK_N;
@@ -707,7 +723,7 @@ __device__ __forceinline__ void async_piece2(const Epilogue& ep, const EpiRegs& 
 template <class C, int COLS, bool SPLITK>
 __device__ __forceinline__ void epilogue_loop(int col0, int quarter, int lane, uint32_t rank, uint32_t tmem_base,
                                               uint32_t tfull0, uint32_t tempty0_leader, uint8_t* stage_gen,
-                                              uint32_t stage, long long n_tiles, int n_blocks, int k_slabs, int split_k, int chunk_slabs, int lead,
+                                              uint32_t stage, long long n_tiles, int n_blocks, int k_slabs, int split_k, int split_per, int chunk_slabs, int lead,
                                               long long M, int N, const Epilogue& ep, unsigned long long* dbg, int dbg_flags,
                                               const StoreMaps& smaps) {
   constexpr int BLOCK_N = C::kBlockN;
@@ -732,7 +748,7 @@ __device__ __forceinline__ void epilogue_loop(int col0, int quarter, int lane, u
     long long m_blk = tile / n_blocks;
     int n_blk = (int)(tile % n_blocks);
     if (SPLITK) {
-      const TileCoord tc = decode_tile<true>(tile, n_blocks, split_k, k_slabs);
+      const TileCoord tc = decode_tile<true>(tile, n_blocks, split_k, k_slabs, split_per);
       m_blk = tc.m_blk;
       n_blk = tc.n_blk;
       n_chunks = chain_count(tc.nks, chunk_slabs, lead);
@@ -874,13 +890,15 @@ __device__ __forceinline__ void epilogue_loop(int col0, int quarter, int lane, u
   __syncwarp();
 }
 
-template <int BLOCK_N, int NTERMS, int KIND, bool SPLITK = false>
+template <int BLOCK_N, int NTERMS, int KIND, bool SPLITK = false, int SLAB = 128>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_a_lo,
                 const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_w_lo,
-                long long M, int N, int K, int chunk_slabs, int lead_chains, int split_k, const __grid_constant__ Epilogue ep,
-                const __grid_constant__ StoreMaps smaps, unsigned long long* dbg_buf, int dbg_flags) {
-  using C = Config<BLOCK_N, NTERMS, KIND>;
+                long long M, int N, int K, int chunk_slabs, int lead_chains, int split_k, int split_per,
+                const __grid_constant__ Epilogue ep, const __grid_constant__ StoreMaps smaps, unsigned long long* dbg_buf,
+                int dbg_flags) {
+  using C = Config<BLOCK_N, NTERMS, KIND, SLAB>;
+  constexpr int SLAB_BYTES = C::SLAB_BYTES;
   extern __shared__ uint8_t smem_raw[];
   uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // same offset in both CTAs of the pair
   asm volatile("" : "+r"(smem_base));   // opaque: otherwise every use re-derives it (S2UR SR_CgaCtaId + arithmetic)
@@ -903,7 +921,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
   if (!SPLITK || split_k < 1) split_k = 1;
   const long long n_tiles = m_blocks * n_blocks * split_k;
   if (chunk_slabs <= 0 || chunk_slabs > k_slabs) chunk_slabs = k_slabs;
-  if (KIND == KIND_F16 && NTERMS == 3) chunk_slabs = 1;   // the 2^-11 rescale happens once per accumulation chain
+  if (KIND == KIND_F16 && NTERMS == 3) chunk_slabs = 128 / SLAB_BYTES;   // 64 K-elements per accumulation chain (the 2^-11
+                                                                         // rescale happens once per chain)
   // the last tile of a tile row is only as wide as N needs (UMMA N is a run-time field of the instruction descriptor;
   // multiples of 16 for M = 256), and the last K-slab only issues the 32-byte K steps that hold data
   auto tile_width = [&](int n_idx) {
@@ -946,7 +965,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         int stage = 0;
         uint32_t phase = 0;
         for (long long tile = cluster_id_x(); tile < n_tiles; tile += num_clusters_x()) {
-          const TileCoord tc = decode_tile<SPLITK>(tile, n_blocks, split_k, k_slabs);
+          const TileCoord tc = decode_tile<SPLITK>(tile, n_blocks, split_k, k_slabs, split_per);
           const int m_idx = (int)tc.m_blk * (2 * BLOCK_M) + (int)rank * BLOCK_M;
           const int n_tile = tc.n_blk * BLOCK_N;
           const int n_idx = n_tile + (int)rank * (tile_width(n_tile) >> 1);   // this CTA stages its half of the W rows
@@ -976,7 +995,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
       int dbg_chain = 0;
       unsigned long long* dbg_mma = (cluster_id_x() == 0 && lane == 0) ? dbg_buf : nullptr;
       for (long long tile = cluster_id_x(); tile < n_tiles; tile += num_clusters_x()) {
-        const TileCoord tc = decode_tile<SPLITK>(tile, n_blocks, split_k, k_slabs);
+        const TileCoord tc = decode_tile<SPLITK>(tile, n_blocks, split_k, k_slabs, split_per);
         const uint32_t idesc = C::IDESC_NO_N | ((uint32_t)(tile_width(tc.n_blk * BLOCK_N) >> 3) << 17);
         const int lead = chain_lead(tc.nks, chunk_slabs, lead_chains);
         const int ks_last = k_slabs - 1 - tc.ks_begin;   // index (within this work item) of the K tail slab, if it is here
@@ -1001,8 +1020,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
               if (lane == 0) {
                 const uint32_t sa = smem_base + st * C::STAGE_BYTES;
                 const uint32_t sb = sa + C::NPLANES * C::A_TILE;
-                const uint64_t da_hi = make_smem_desc(sa), db_hi = make_smem_desc(sb);
-                const uint64_t da_lo = make_smem_desc(sa + C::A_TILE), db_lo = make_smem_desc(sb + C::B_TILE);
+                const uint64_t da_hi = make_smem_desc_s<SLAB_BYTES>(sa), db_hi = make_smem_desc_s<SLAB_BYTES>(sb);
+                const uint64_t da_lo = make_smem_desc_s<SLAB_BYTES>(sa + C::A_TILE), db_lo = make_smem_desc_s<SLAB_BYTES>(sb + C::B_TILE);
                 const int nk = ks == ks_last ? last_ksteps : KSTEPS;
 #pragma unroll
                 for (int k = 0; k < KSTEPS; ++k) {
@@ -1021,7 +1040,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
               if (lane == 0) {
                 const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
                 const uint32_t sb = sa + C::NPLANES * C::A_TILE;
-                const uint64_t da_hi = make_smem_desc(sa), db_hi = make_smem_desc(sb);
+                const uint64_t da_hi = make_smem_desc_s<SLAB_BYTES>(sa), db_hi = make_smem_desc_s<SLAB_BYTES>(sb);
                 const int nk = ks == ks_last ? last_ksteps : KSTEPS;
                 if (ks == ks0) umma_pair_f16_scale11(da_hi, db_hi, tmem_d, idesc);
 #pragma unroll
@@ -1045,10 +1064,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
               if (lane == 0) {
                 const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
                 const uint32_t sb = sa + C::NPLANES * C::A_TILE;
-                const uint64_t da_hi = make_smem_desc(sa), db_hi = make_smem_desc(sb);
+                const uint64_t da_hi = make_smem_desc_s<SLAB_BYTES>(sa), db_hi = make_smem_desc_s<SLAB_BYTES>(sb);
                 const int nk = ks == ks_last ? last_ksteps : KSTEPS;
                 if (NTERMS == 3) {  // small terms first: they meet the accumulator while it is smallest
-                  const uint64_t da_lo = make_smem_desc(sa + C::A_TILE), db_lo = make_smem_desc(sb + C::B_TILE);
+                  const uint64_t da_lo = make_smem_desc_s<SLAB_BYTES>(sa + C::A_TILE), db_lo = make_smem_desc_s<SLAB_BYTES>(sb + C::B_TILE);
 #pragma unroll
                   for (int k = 0; k < KSTEPS; ++k) {
                     if (k < nk) {
@@ -1089,13 +1108,13 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     unsigned long long* dbg_epi = (cluster_id_x() == 0 && rank == 0 && warp == FIRST_EPI_WARP && lane == 0) ? dbg_buf : nullptr;
     if (C::HALF0 == C::HALF1)     // one copy of the epilogue code serves both column halves
       epilogue_loop<C, C::HALF0, SPLITK>(warp < FIRST_EPI_WARP + 4 ? 0 : C::HALF0, warp & 3, lane, rank, tmem_base, tfull_bar(0),
-                                 tempty_leader, stage, stage_u32, n_tiles, n_blocks, k_slabs, split_k, chunk_slabs, lead_chains, M, N, ep, dbg_epi, dbg_flags, smaps);
+                                 tempty_leader, stage, stage_u32, n_tiles, n_blocks, k_slabs, split_k, split_per, chunk_slabs, lead_chains, M, N, ep, dbg_epi, dbg_flags, smaps);
     else if (warp < FIRST_EPI_WARP + 4)
       epilogue_loop<C, C::HALF0, SPLITK>(0, warp & 3, lane, rank, tmem_base, tfull_bar(0), tempty_leader, stage, stage_u32, n_tiles,
-                                 n_blocks, k_slabs, split_k, chunk_slabs, lead_chains, M, N, ep, dbg_epi, dbg_flags, smaps);
+                                 n_blocks, k_slabs, split_k, split_per, chunk_slabs, lead_chains, M, N, ep, dbg_epi, dbg_flags, smaps);
     else
       epilogue_loop<C, C::HALF1, SPLITK>(C::HALF0, warp & 3, lane, rank, tmem_base, tfull_bar(0), tempty_leader, stage, stage_u32,
-                                 n_tiles, n_blocks, k_slabs, split_k, chunk_slabs, lead_chains, M, N, ep, nullptr, dbg_flags, smaps);
+                                 n_tiles, n_blocks, k_slabs, split_k, split_per, chunk_slabs, lead_chains, M, N, ep, nullptr, dbg_flags, smaps);
   }
 
   tcgen05_fence_before();
@@ -1155,15 +1174,20 @@ inline int make_store_map32(CUtensorMap* map, const void* ptr, long long rows, l
   return USF_OK;
 }
 
-template <int BLOCK_N, int NTERMS, int KIND, bool SPLITK = false>
+extern int g_f16_slab;                  // K bytes per pipeline stage of the fp16-split engine: 64 (default) or 128 (usf_debug_set_slab)
+
+template <int BLOCK_N, int NTERMS, int KIND, bool SPLITK = false, int SLAB = 128>
 int launch_gemm_tc2_cfg(const usf_linear_args* a, const Epilogue& ep_in, cudaStream_t st) {
-  using C = tc2::Config<BLOCK_N, NTERMS, KIND>;
-  // split-K exists for the fp16-split engine (the training pass); every other engine runs the plain kernel
-  if (!SPLITK && NTERMS == 3 && KIND == tc2::KIND_F16 && a->split_k > 1)
-    return launch_gemm_tc2_cfg<BLOCK_N, NTERMS, KIND, NTERMS == 3 && KIND == tc2::KIND_F16>(a, ep_in, st);
+  using C = tc2::Config<BLOCK_N, NTERMS, KIND, SLAB>;
+  constexpr bool F16S = NTERMS == 3 && KIND == tc2::KIND_F16;
+  // split-K and the half-size pipeline stages exist for the fp16-split engine; every other engine runs the plain kernel
+  if (F16S && SLAB == 128 && g_f16_slab == 64)
+    return launch_gemm_tc2_cfg<BLOCK_N, NTERMS, KIND, SPLITK, F16S ? 64 : 128>(a, ep_in, st);
+  if (!SPLITK && F16S && a->split_k > 1)
+    return launch_gemm_tc2_cfg<BLOCK_N, NTERMS, KIND, F16S, SLAB>(a, ep_in, st);
   static bool attr_set_dev[MAX_DEVICES] = {false};
   bool& attr_set = attr_set_dev[current_device_slot()];
-  auto kern = tc2::gemm_tc2_kernel<BLOCK_N, NTERMS, KIND, SPLITK>;
+  auto kern = tc2::gemm_tc2_kernel<BLOCK_N, NTERMS, KIND, SPLITK, SLAB>;
   const int dt = KIND == tc2::KIND_TF32 ? 0 : KIND == tc2::KIND_BF16 ? 1 : 2;
   if (!attr_set) {
     USF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
@@ -1171,11 +1195,11 @@ int launch_gemm_tc2_cfg(const usf_linear_args* a, const Epilogue& ep_in, cudaStr
   }
   CUtensorMap ma, mal, mw, mwl;
   int rc;
-  if ((rc = make_operand_map(&ma, a->a, a->M, a->K, a->lda, tc::BLOCK_M, dt))) return rc;
-  if ((rc = make_operand_map(&mw, a->w, a->N, a->K, a->ldw, C::HALF_N, dt))) return rc;
+  if ((rc = make_operand_map(&ma, a->a, a->M, a->K, a->lda, tc::BLOCK_M, dt, SLAB))) return rc;
+  if ((rc = make_operand_map(&mw, a->w, a->N, a->K, a->ldw, C::HALF_N, dt, SLAB))) return rc;
   if (NTERMS == 3) {
-    if ((rc = make_operand_map(&mal, a->a_lo, a->M, a->K, a->lda, tc::BLOCK_M, dt))) return rc;
-    if ((rc = make_operand_map(&mwl, a->w_lo, a->N, a->K, a->ldw, C::HALF_N, dt))) return rc;
+    if ((rc = make_operand_map(&mal, a->a_lo, a->M, a->K, a->lda, tc::BLOCK_M, dt, SLAB))) return rc;
+    if ((rc = make_operand_map(&mwl, a->w_lo, a->N, a->K, a->ldw, C::HALF_N, dt, SLAB))) return rc;
   } else {
     mal = ma;
     mwl = mw;
@@ -1206,11 +1230,14 @@ int launch_gemm_tc2_cfg(const usf_linear_args* a, const Epilogue& ep_in, cudaStr
   }
   // split-K (training: dW = dY^T . X): the K-slabs of a tile are cut into `split_k` work items that add their partial tiles
   // into the fp32 output (red.global.add.v4.f32); the caller zeroes / pre-loads the output (usf_linear does, see capi.cu)
-  int split_k = 1;
+  int split_k = 1, split_per = 0;
   if (SPLITK && a->split_k > 1) {
     const int k_slabs = (int)((a->K + C::ELEMS_PER_SLAB - 1) / C::ELEMS_PER_SLAB);
-    const int per = (k_slabs + a->split_k - 1) / a->split_k;
+    constexpr int CH = F16S ? 128 / SLAB : 1;               // a piece is a whole number of accumulation chains
+    int per = (k_slabs + a->split_k - 1) / a->split_k;
+    per = (per + CH - 1) / CH * CH;
     split_k = (k_slabs + per - 1) / per;                    // every work item gets at least one slab
+    split_per = per;
     USF_REQUIRE(ep.fast_store && ep.out_f32 && !ep.out_h16 && !ep.out_hi && !ep.out_bf16 && !ep.bias && !ep.relu &&
                     !ep.resid_hi && !ep.resid_h16 && !ep.colscale && !ep.postsub,
                 "split_k > 1 accumulates plain partial products into an aligned fp32 output (no other epilogue feature)");
@@ -1221,7 +1248,8 @@ int launch_gemm_tc2_cfg(const usf_linear_args* a, const Epilogue& ep_in, cudaStr
   const int grid = 2 * (int)(tiles < pairs ? tiles : pairs);
   USF_CUDA_OK(launch_chain(kern, dim3(grid), dim3(tc::NUM_THREADS), (size_t)C::SMEM_BYTES, st, ma, mal, mw, mwl, (long long)a->M,
                            (int)a->N, (int)a->K, NTERMS == 3 ? g_chunk_slabs : 0,
-                           (NTERMS == 3 && KIND == tc2::KIND_F16) ? g_lead_chains : 0, split_k, ep, sm, g_dbg_buf, g_dbg_flags));
+                           (NTERMS == 3 && KIND == tc2::KIND_F16) ? g_lead_chains : 0, split_k, split_per, ep, sm, g_dbg_buf,
+                           g_dbg_flags));
   return USF_OK;
 }
 
