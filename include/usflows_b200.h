@@ -142,9 +142,9 @@ int usf_debug_set_impl(int impl);
 /* test hook: 1 (default) = the kernels of an evaluation are chained with programmatic dependent launch, 0 = plain
  * stream order */
 int usf_debug_set_pdl(int on);
-/* test hook: K bytes per pipeline stage (operand row) of the fp16-split CTA-pair kernel: 64 (default: six half-size stages
- * with the 64B swizzle, 5 of 6 in flight) or 128 (three stages with the 128B swizzle); same bits either way */
-int usf_debug_set_slab(int bytes);
+/* test hook: 1 = the hi / lo operand planes of a tile travel in ONE 3-D TMA operation (planes as the third tensor
+ * dimension, plane stride = distance of the two pointers), 0 (default) = one 2-D operation per plane; same bits, same speed */
+int usf_debug_set_planes3d(int on);
 /* profiling hook for the CTA-pair tcgen05 kernel: `device_buf` (512 x 8 uint64, or NULL to switch off) receives
  * clock64() stamps of the first 512 accumulation chains of cluster 0 (0 = accumulator free seen by the MMA issuer,
  * 1 = operands landed, 2 = chain issued, 3 = accumulator full seen by epilogue warp 4, 4 = drained, 5 = tile stored);

@@ -480,47 +480,39 @@ def test_tma_store_path_for_bf16_and_fp32_planes(eng_name, eng, fmt, planes, M, 
             assert float(t._base[:, N:].abs().float().max()) == 0.0
 
 
-@pytest.mark.parametrize("M,N,K", [(300, 784, 784), (1000, 1024, 392), (515, 392, 1024), (257, 208, 72), (70000, 256, 128),
-                                   (64, 48, 40)])
-def test_half_size_pipeline_stages_give_the_same_bits(M, N, K):
-    """fp16-split engine: six 64-byte-row stages (64B swizzle; default) == three 128-byte-row stages (128B swizzle): the same
-    sequence of 16-element K steps and the same 64-element accumulation chains, so bit-identical outputs -- plain, with the
-    in-place coupling residual, with an fp32 result, and split-K."""
+@pytest.mark.parametrize("eng_name,eng,fmt", [("3xtf32", 1, "split"), ("3xf16", 4, "f16")])
+@pytest.mark.parametrize("M,N,K", [(300, 784, 784), (1000, 1024, 392), (515, 392, 1024), (257, 208, 72), (64, 48, 40)])
+def test_both_operand_planes_in_one_tma_operation(eng_name, eng, fmt, M, N, K):
+    """Split engines: hi and lo planes of a tile fetched by ONE 3-D TMA operation (planes = third tensor dimension, possible
+    when lo - hi is a positive multiple of 16 bytes; a measured-neutral option) == one 2-D operation per plane (default); also
+    when the planes do not allow the 3-D form."""
     from usflows_b200 import _lib, ops
     from usflows_b200.ops import Act
     g = torch.Generator().manual_seed(M + N + K)
     a = torch.randn(M, K, generator=g)
     w = torch.randn(N, K, generator=g) / K ** 0.5
     bias = torch.randn(N, generator=g).cuda()
-    x0 = torch.randn(M, N, generator=g)
-    act, a_used = _f16_planes(a)
-    wact, w_used = _f16_planes(w)
+    act, a_used = _f16_planes(a) if fmt == "f16" else _planes(a, fmt)
+    wact, w_used = _f16_planes(w) if fmt == "f16" else _planes(w, fmt)
+    hi, lo = (act.h16, act.l16) if fmt == "f16" else (act.hi, act.lo)
+    w_hi, w_lo = (wact.h16, wact.l16) if fmt == "f16" else (wact.hi, wact.lo)
+    assert lo.data_ptr() > hi.data_ptr()
+    # the same activation with the planes the other way round in memory: the 3-D form is impossible, the kernel must notice
+    rev = torch.zeros(2, M, ops.pad4(K), dtype=hi.dtype, device="cuda")
+    rev[1, :, :K].copy_(hi)
+    rev[0, :, :K].copy_(lo)
+    act_rev = Act(M, K, h16=rev[1, :, :K], l16=rev[0, :, :K]) if fmt == "f16" else Act(M, K, hi=rev[1, :, :K], lo=rev[0, :, :K])
     lib = _lib.load()
-    res = {}
-    for slab in (64, 128):
-        lib.usf_debug_set_slab(slab)
+    outs = []
+    for on, A in ((1, act), (0, act), (1, act_rev)):
+        out = torch.zeros(M, ops.pad4(N, 4), device="cuda")[:, :N]
+        lib.usf_debug_set_planes3d(on)
         try:
-            plain, _ = _f16_planes(torch.zeros(M, N))
-            ops.linear(ops.ENGINE_TC_3XF16, act, wact.h16, wact.l16, N, K, bias=bias, relu=True, out=plain)
-            stream, _ = _f16_planes(x0)
-            ops.linear(ops.ENGINE_TC_3XF16, act, wact.h16, wact.l16, N, K, bias=bias, resid=stream, resid_sign=-1.0,
-                       out=Act(M, N, h16=stream.h16, l16=stream.l16))
-            f32 = torch.zeros(M, ops.pad4(N, 4), device="cuda")[:, :N]
-            ops.linear(ops.ENGINE_TC_3XF16, act, wact.h16, wact.l16, N, K, bias=bias, out=Act(M, N, f32=f32))
-            aT, _ = _f16_planes(a.t().contiguous())
-            xT, _ = _f16_planes(x0.t().contiguous())
-            dw = torch.zeros(K, ops.pad4(N, 4), device="cuda")[:, :N]
-            ops.linear_splitk(ops.ENGINE_TC_3XF16, aT, xT, N, M, dw, 4)
+            ops.linear(eng, A, w_hi, w_lo, N, K, bias=bias, relu=True, out=Act(M, N, f32=out))
             torch.cuda.synchronize()
         finally:
-            lib.usf_debug_set_slab(64)
-        res[slab] = (plain, stream, f32, dw)
-    for p, q in zip(res[64][:3], res[128][:3]):
-        if isinstance(p, torch.Tensor):
-            assert torch.equal(p, q)
-        else:
-            assert torch.equal(p.h16, q.h16) and torch.equal(p.l16, q.l16)
-    ref = a_used.double() @ w_used.double().T + bias.double().cpu()
-    assert rel_err(res[64][2], ref) <= 3e-6
-    dref = a_used.double().t() @ (x0.to(torch.float16).double() + ((x0 - x0.to(torch.float16).float()) * 2048).to(torch.float16).double() / 2048)
-    assert rel_err(res[64][3], dref) <= 3e-6 and rel_err(res[128][3], dref) <= 3e-6      # (atomic order differs: not bitwise)
+            lib.usf_debug_set_planes3d(0)
+        outs.append(out)
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    ref = torch.relu(a_used.double() @ w_used.double().T + bias.double().cpu())
+    assert rel_err(outs[0], ref) <= 3e-6

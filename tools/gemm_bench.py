@@ -71,7 +71,6 @@ def main():
     ap.add_argument("--check", action="store_true")
     ap.add_argument("--epi", action="store_true", help="bias + relu epilogue")
     ap.add_argument("--lead", type=int, default=-1)
-    ap.add_argument("--slab", type=int, default=0, help="fp16-split engine: K bytes per pipeline stage (64 | 128)")
     ap.add_argument("--resid", action="store_true", help="3xf16: in-place coupling residual (out = out - (a.w^T + bias))")
     ap.add_argument("--flags", type=int, default=0, help="usf_debug_gemm_timeline flags (256 = residual without the in-box)")
     args = ap.parse_args()
@@ -81,8 +80,6 @@ def main():
     lib.usf_debug_set_block_n(args.bn)
     if args.lead >= 0:
         lib.usf_set_accum_lead(args.lead)
-    if args.slab:
-        lib.usf_debug_set_slab(args.slab)
     print(torch.cuda.get_device_name(0), flush=True)
     for eng in args.engines.split(","):
         for shp in args.shapes.split(","):

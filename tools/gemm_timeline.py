@@ -34,7 +34,6 @@ def main():
     ap.add_argument("--flags", default="0,1,2,3")
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--lead", type=int, default=-1)
-    ap.add_argument("--slab", type=int, default=0, help="fp16-split engine: K bytes per pipeline stage (64 | 128)")
     args = ap.parse_args()
     lib = _lib.load()
     lib.usf_debug_set_block_n(args.bn)
@@ -42,8 +41,6 @@ def main():
         lib.usf_set_accum_chunk(args.chunk)
     if args.lead >= 0:
         lib.usf_set_accum_lead(args.lead)
-    if args.slab:
-        lib.usf_debug_set_slab(args.slab)
     M, N, K = (int(v) for v in args.shape.split("x"))
     eng = args.engine
     act, wt, wl, bias, out, _, _ = make_case(eng, M, N, K, 0, False)

@@ -149,7 +149,7 @@ SIGNATURES = {
     "usf_set_accum_lead": (C.c_int, [C.c_int]),
     "usf_debug_set_impl": (C.c_int, [C.c_int]),
     "usf_debug_set_pdl": (C.c_int, [C.c_int]),
-    "usf_debug_set_slab": (C.c_int, [C.c_int]),
+    "usf_debug_set_planes3d": (C.c_int, [C.c_int]),
     "usf_debug_gemm_timeline": (C.c_int, [_P, C.c_int]),
 }
 

@@ -25,7 +25,7 @@ int g_dbg_flags = 0;
 int g_no_fast_store = 0;
 int g_use_pdl = 1;
 int g_no_async_store = 0;
-int g_f16_slab = 64;
+int g_planes3d = 0;
 
 int num_sms() {
   static int cached[64] = {0};
@@ -141,9 +141,8 @@ int usf_debug_gemm_timeline(unsigned long long* device_buf, int flags) {
   return USF_OK;
 }
 
-int usf_debug_set_slab(int bytes) {  // test hook: K bytes per pipeline stage of the fp16-split engine (64 default, 128)
-  USF_REQUIRE(bytes == 64 || bytes == 128, "slab must be 64 or 128 bytes");
-  g_f16_slab = bytes;
+int usf_debug_set_planes3d(int on) {  // test hook: hi / lo operand planes in one 3-D TMA operation (default on)
+  g_planes3d = on ? 1 : 0;
   return USF_OK;
 }
 

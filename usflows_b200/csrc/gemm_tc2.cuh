@@ -64,6 +64,14 @@ __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap
       ::"r"(dst), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1)
       : "memory");
 }
+// both operand planes (hi, lo) of a tile in ONE TMA operation: the planes are the third dimension of the tensor map (any two
+// plane pointers are "a tensor with two planes" whose plane stride is their difference) and land back to back in shared memory
+__device__ __forceinline__ void tma_load_3d_pair(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1), "r"(0)
+      : "memory");
+}
 constexpr int STAGE_EPI_BYTES = 4096;          // per epilogue warp: one 32-row x (128 B | 2 x 64 B) staging box
 constexpr int INBOX_BYTES = 2048;              // per epilogue warp: one plane of a 32-row x 32-column residual piece
 
@@ -153,10 +161,12 @@ __device__ __forceinline__ uint64_t make_smem_desc_s(uint32_t smem_addr) {
   return d;
 }
 
-// SLAB = bytes of K per pipeline stage and operand row.  The pipeline is bound by the operand bytes in flight
-// (TMA issue -> landing is ~3 000-3 500 cycles under load; measured: 1 044 of 1 900 cycles per chain the MMA issuer waits
-// for operands with 3 stages of 128-byte slabs, i.e. 2 of 3 stages = 116 KB in flight).  Half-size stages (64-byte rows,
-// 64B swizzle) keep 5 of 6 stages in flight out of the same shared memory.
+// SLAB = bytes of K per pipeline stage and operand row (128: three stages; the kernel is written for either).  Measured
+// (tools/gemm_timeline.py --slab, B200): the MMA issuer waits ~1 050 of ~1 980 cycles per 64-element chain for operands with
+// three 128-byte stages; SIX half-size stages (64-byte rows, 64B swizzle: 5 of 6 stages in flight instead of 2 of 3) are
+// SLOWER -- chain period 2 506 vs 1 979 cycles, 784 x 784 over 65 536 rows 274 vs 246 us, 1024 x 1024 366 vs 331 us: twice
+// the TMA operations per K, each fetching 64-byte rows, cost more than the deeper pipeline gives.  So SLAB = 128 it is; the
+// 64-byte instantiation is not built.
 template <int BLOCK_N, int NTERMS, int KIND, int SLAB = 128>
 struct Config {
   static constexpr int SLAB_BYTES = SLAB;       // (shadows tc::SLAB_BYTES inside this configuration)
@@ -894,7 +904,7 @@ template <int BLOCK_N, int NTERMS, int KIND, bool SPLITK = false, int SLAB = 128
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_a_lo,
                 const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_w_lo,
-                long long M, int N, int K, int chunk_slabs, int lead_chains, int split_k, int split_per,
+                long long M, int N, int K, int chunk_slabs, int lead_chains, int split_k, int split_per, int planes3d,
                 const __grid_constant__ Epilogue ep, const __grid_constant__ StoreMaps smaps, unsigned long long* dbg_buf,
                 int dbg_flags) {
   using C = Config<BLOCK_N, NTERMS, KIND, SLAB>;
@@ -976,11 +986,16 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
             const int k_idx = (tc.ks_begin + ks) * C::ELEMS_PER_SLAB;
             const uint32_t fb = mapa(full_bar(stage), 0);
             if (rank == 0) mbar_expect_tx(full_bar(stage), 2 * C::STAGE_BYTES);
-            tma_load_2d_pair(sa, &tm_a, fb, k_idx, m_idx);
-            tma_load_2d_pair(sb, &tm_w, fb, k_idx, n_idx);
-            if (NTERMS == 3) {
-              tma_load_2d_pair(sa + C::A_TILE, &tm_a_lo, fb, k_idx, m_idx);
-              tma_load_2d_pair(sb + C::B_TILE, &tm_w_lo, fb, k_idx, n_idx);
+            if (NTERMS == 3 && planes3d) {          // hi + lo planes of A (and of W) in one operation each
+              tma_load_3d_pair(sa, &tm_a, fb, k_idx, m_idx);
+              tma_load_3d_pair(sb, &tm_w, fb, k_idx, n_idx);
+            } else {
+              tma_load_2d_pair(sa, &tm_a, fb, k_idx, m_idx);
+              tma_load_2d_pair(sb, &tm_w, fb, k_idx, n_idx);
+              if (NTERMS == 3) {
+                tma_load_2d_pair(sa + C::A_TILE, &tm_a_lo, fb, k_idx, m_idx);
+                tma_load_2d_pair(sb + C::B_TILE, &tm_w_lo, fb, k_idx, n_idx);
+              }
             }
             if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
           }
@@ -1174,15 +1189,31 @@ inline int make_store_map32(CUtensorMap* map, const void* ptr, long long rows, l
   return USF_OK;
 }
 
-extern int g_f16_slab;                  // K bytes per pipeline stage of the fp16-split engine: 64 (default) or 128 (usf_debug_set_slab)
+extern int g_planes3d;                  // 1: hi / lo operand planes travel in one 3-D TMA operation where possible (usf_debug_set_planes3d;
+                                        // measured neutral: 246.5 vs 247.3 us on 784 x 784, so the default stays one 2-D operation per plane)
+
+// [2 planes, rows, cols] operand map over two plane pointers (plane stride = their distance); false if they do not allow it
+inline bool make_operand_map3(CUtensorMap* map, const void* hi, const void* lo, long long rows, long long cols, long long ld,
+                              int box_rows, int dtype) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  const long long diff = (const char*)lo - (const char*)hi;
+  if (!enc || diff <= 0 || diff % 16 != 0 || diff >= (1LL << 40)) return false;
+  const int esz = dtype ? 2 : 4;
+  cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, 2};
+  cuuint64_t strides[2] = {(cuuint64_t)ld * esz, (cuuint64_t)diff};
+  cuuint32_t box[3] = {(cuuint32_t)(tc::SLAB_BYTES / esz), (cuuint32_t)box_rows, 2};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, dtype == 1 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : dtype == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
+                   const_cast<void*>(hi), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
 
 template <int BLOCK_N, int NTERMS, int KIND, bool SPLITK = false, int SLAB = 128>
 int launch_gemm_tc2_cfg(const usf_linear_args* a, const Epilogue& ep_in, cudaStream_t st) {
   using C = tc2::Config<BLOCK_N, NTERMS, KIND, SLAB>;
   constexpr bool F16S = NTERMS == 3 && KIND == tc2::KIND_F16;
-  // split-K and the half-size pipeline stages exist for the fp16-split engine; every other engine runs the plain kernel
-  if (F16S && SLAB == 128 && g_f16_slab == 64)
-    return launch_gemm_tc2_cfg<BLOCK_N, NTERMS, KIND, SPLITK, F16S ? 64 : 128>(a, ep_in, st);
+  // split-K exists for the fp16-split engine (the training pass); every other engine runs the plain kernel
   if (!SPLITK && F16S && a->split_k > 1)
     return launch_gemm_tc2_cfg<BLOCK_N, NTERMS, KIND, F16S, SLAB>(a, ep_in, st);
   static bool attr_set_dev[MAX_DEVICES] = {false};
@@ -1195,9 +1226,21 @@ int launch_gemm_tc2_cfg(const usf_linear_args* a, const Epilogue& ep_in, cudaStr
   }
   CUtensorMap ma, mal, mw, mwl;
   int rc;
-  if ((rc = make_operand_map(&ma, a->a, a->M, a->K, a->lda, tc::BLOCK_M, dt, SLAB))) return rc;
-  if ((rc = make_operand_map(&mw, a->w, a->N, a->K, a->ldw, C::HALF_N, dt, SLAB))) return rc;
-  if (NTERMS == 3) {
+  int planes3d = 0;
+  if (NTERMS == 3 && SLAB == 128 && g_planes3d) {
+    CUtensorMap ta, tw;
+    if (make_operand_map3(&ta, a->a, a->a_lo, a->M, a->K, a->lda, tc::BLOCK_M, dt) &&
+        make_operand_map3(&tw, a->w, a->w_lo, a->N, a->K, a->ldw, C::HALF_N, dt)) {
+      ma = ta; mw = tw; mal = ta; mwl = tw;
+      planes3d = 1;
+    }
+  }
+  if (planes3d) {
+  } else if ((rc = make_operand_map(&ma, a->a, a->M, a->K, a->lda, tc::BLOCK_M, dt, SLAB))) {
+    return rc;
+  } else if ((rc = make_operand_map(&mw, a->w, a->N, a->K, a->ldw, C::HALF_N, dt, SLAB))) {
+    return rc;
+  } else if (NTERMS == 3) {
     if ((rc = make_operand_map(&mal, a->a_lo, a->M, a->K, a->lda, tc::BLOCK_M, dt, SLAB))) return rc;
     if ((rc = make_operand_map(&mwl, a->w_lo, a->N, a->K, a->ldw, C::HALF_N, dt, SLAB))) return rc;
   } else {
@@ -1248,7 +1291,7 @@ int launch_gemm_tc2_cfg(const usf_linear_args* a, const Epilogue& ep_in, cudaStr
   const int grid = 2 * (int)(tiles < pairs ? tiles : pairs);
   USF_CUDA_OK(launch_chain(kern, dim3(grid), dim3(tc::NUM_THREADS), (size_t)C::SMEM_BYTES, st, ma, mal, mw, mwl, (long long)a->M,
                            (int)a->N, (int)a->K, NTERMS == 3 ? g_chunk_slabs : 0,
-                           (NTERMS == 3 && KIND == tc2::KIND_F16) ? g_lead_chains : 0, split_k, split_per, ep, sm, g_dbg_buf,
+                           (NTERMS == 3 && KIND == tc2::KIND_F16) ? g_lead_chains : 0, split_k, split_per, planes3d, ep, sm, g_dbg_buf,
                            g_dbg_flags));
   return USF_OK;
 }

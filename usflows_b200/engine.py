@@ -838,11 +838,24 @@ class _Workspace:
         self._bufs = {}
         self.generation = 0          # bumped whenever a buffer is (re)allocated: captured CUDA graphs go stale
 
+    _PAIR = {"h16": ("p16", 0), "l16": ("p16", 1), "hi": ("p32", 0), "lo": ("p32", 1)}
+
     def planes(self, device, name: str, rows: int, width: int, fmt: str) -> torch.Tensor:
         ld = pad4(width)
-        key = (device, name, fmt)
         need = rows * ld
         dtype = torch.bfloat16 if fmt == "bf16" else torch.float16 if fmt in ("h16", "l16") else torch.float32
+        pair = self._PAIR.get(fmt)
+        if pair is not None:
+            # the two planes of a split format live in ONE allocation, hi first: the contraction kernel then fetches both
+            # with one 3-D TMA operation per tile (plane = third tensor dimension; needs lo - hi > 0)
+            key = (device, name, pair[0])
+            buf = self._bufs.get(key)
+            if buf is None or buf.shape[1] < need:
+                buf = torch.empty(2, max(need, 8), dtype=dtype, device=device)
+                self._bufs[key] = buf
+                self.generation += 1
+            return buf[pair[1], :need].view(rows, ld)[:, :width]
+        key = (device, name, fmt)
         buf = self._bufs.get(key)
         if buf is None or buf.numel() < need:
             buf = torch.empty(max(need, 1), dtype=dtype, device=device)
