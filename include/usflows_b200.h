@@ -255,6 +255,49 @@ int usf_im2col(const float* in, int64_t ld_in, int64_t n_images, int32_t h, int3
  * 3 * 32 KB + ceil(K/32) * 2 * (N <= 32 ? 32 : 64) * 128 B exceeds 227 KB (use usf_im2col + usf_linear then). */
 int usf_conv2d_rows(const usf_linear_args* a, const float* act, int64_t ld_act, int64_t n_images, int32_t h, int32_t w,
                     int32_t c_in, int32_t k, int32_t dilation, const float* mask, int32_t relu_in, void* stream);
+/* ---- pixel planes: the ConvNet2D conditioner without gather threads (csrc/conv_pix.cuh) ----------------------------
+ * An activation with <= 32 channels as [n*h*w, 64] fp16: per pixel 32 high halves | 32 low halves' (x = hi + lo' 2^-11,
+ * missing channels zero) = one 128-byte operand row; a k x k tap of 256 pixels is ONE 4-D TMA box (zero padding 'same' by
+ * the hardware's out-of-bounds fill).
+ * usf_pix_encode: fp32 channels-last rows x [rows, c] (c <= 32) -> pixel planes, times mask[(r mod hw)*c + ch] when mask is
+ * given (the coupling's x * mask, transforms.py:286), then optional ReLU. */
+int usf_pix_encode(const float* x, int64_t ldx, int64_t rows, int32_t c, int32_t hw, const float* mask, int32_t relu,
+                   void* out16, int32_t* overflow_flag, void* stream);
+typedef struct usf_conv_pix_args {
+  const void* a16;       /* input pixel planes [n*h*w, 64] fp16 */
+  int64_t n_images;
+  int32_t h, w, ksize, dilation;   /* odd ksize, stride 1, padding 'same' */
+  const void* w1;        /* [32, k*k*64] fp16: row = output channel (rows >= n1 zero), per tap 32 hi | 32 lo' input channels */
+  const float* bias1;    /* [32], entries >= n1 zero */
+  int32_t n1;            /* output channels of the k x k convolution (<= 32, multiple of 4; gated: 32) */
+  int32_t relu1;         /* plain: ReLU on conv + bias */
+  int32_t gated;         /* 0 = plain, 1 = GatedConv block (networks.py:100-121) */
+  int32_t post_relu;     /* gated: ReLU after the gate (ConvNet2D applies its nonlinearity to the GatedConv output) */
+  const void* w2;        /* gated: [64, 64] fp16, rows = val (32) | gate (32) channels of the 1 x 1 convolution, 32 hi | 32 lo' */
+  const float* bias2;    /* gated: [64] */
+  const float* gamma;    /* LayerNormChannels over the n1 channels, after relu1 / post_relu (NULL: none; networks.py:40-58) */
+  const float* beta;
+  float eps;
+  float sign;            /* plain + x: sign of the coupling update */
+  float* out_f32;        /* plain: result rows [n*h*w, n1] (optional); gated: residual stream y [n*h*w, 32], updated in place */
+  int64_t ld_f32;
+  void* out16;           /* pixel planes of the result (optional) */
+  int32_t relu_planes;   /* the planes hold max(result, 0) (the ReLU in front of the next convolution) */
+  int32_t c_x;           /* plain + x: channels of x (<= n1) */
+  float* x;              /* plain: x[r, c] += sign * inv_mask[(r mod h*w)*c_x + c] * result[r, c] (transforms.py:284-290) */
+  int64_t ldx;
+  const float* inv_mask;
+  int32_t* overflow_flag;   /* set when a value written to fp16 planes leaves the fp16 range (may be NULL) */
+} usf_conv_pix_args;
+/* Plain: result = [LayerNorm]([ReLU](conv_kxk(a16) + bias1)) -> out_f32 / out16 / the coupling update of x.
+ * Gated: u = relu(conv_kxk(a16) + bias1); [val | gate] = w2 u + bias2 (same kernel, second TMEM accumulator);
+ *        y <- [LayerNorm]([ReLU](y + val * sigmoid(gate))) in place, + its pixel planes.  fp32-accurate (fp16 split, 3 products).
+ * Replaces nn.Conv2d, GatedConv.forward, the ReLU and LayerNormChannels of ConvNet2D (networks.py:40-121, 405-494) and, for the
+ * last convolution, MaskedCoupling's update.  USF_ERR_UNSUPPORTED when w > 256 or the k*k*4 KB weight leaves no room for two
+ * 32 KB pipeline stages in 227 KB of shared memory. */
+int usf_conv2d_pix(const usf_conv_pix_args* a, void* stream);
+int usf_set_pix_chain_taps(int32_t taps);   /* taps per TMEM accumulation chain (default 3 = 96 K-elements); tools only */
+
 /* x[r, c] += sign * g[(r mod hw)*c_dim + c] * t[r, c]: MaskedCoupling.forward/backward with a mask over [C, H, W]
  * (transforms.py:284-290, 301-306; g = 1 - mask in channels-last order). */
 int usf_masked_add(float* x, int64_t ldx, const float* t, int64_t ldt, int64_t rows, int32_t c, int32_t hw, const float* g,

@@ -9,6 +9,7 @@ from usflows_b200.ops import Act, ENGINE_SIMT, ENGINE_TC_3XF16, ENGINE_TC_3XTF32
 
 CALLS = []
 real_conv2d_rows_supported = real_ops.conv2d_rows_supported
+real_ops_conv2d_pix_supported = real_ops.conv2d_pix_supported
 
 
 def tf32_round(x: torch.Tensor) -> torch.Tensor:
@@ -264,6 +265,69 @@ def conv2d_rows_supported(N, K, c_in):
     return real_conv2d_rows_supported(N, K, c_in)
 
 
+def _pix_decode(p16):
+    return f16_join(p16[:, :32], p16[:, 32:64])
+
+
+def _pix_store(out16, v, relu, flag):
+    v = torch.relu(v) if relu else v
+    full = torch.zeros(v.shape[0], 32)
+    full[:, :v.shape[1]] = v
+    h, l = f16_split(full)
+    out16[:, :32].copy_(h)
+    out16[:, 32:64].copy_(l)
+    if flag is not None and bool((~(full.abs() <= 65000.0)).any()):
+        flag.fill_(1)
+
+
+def pix_encode(x, hw, out16, *, mask=None, relu=False, overflow_flag=None):
+    CALLS.append(("pix_encode", x.shape[1], mask is not None, bool(relu)))
+    v = x
+    if mask is not None:
+        v = v * mask.reshape(hw, x.shape[1]).repeat(x.shape[0] // hw, 1)
+    _pix_store(out16, v, relu, overflow_flag)
+
+
+def conv2d_pix_supported(h, w, k, gated=True):
+    return real_ops_conv2d_pix_supported(h, w, k, gated)
+
+
+def conv2d_pix(a16, n_images, h, w, k, dilation, w1, bias1, n1, *, relu1=False, gated=False, post_relu=False, w2=None,
+               bias2=None, gamma=None, beta=None, eps=0.0, out_f32=None, out16=None, relu_planes=False, x=None, inv_mask=None,
+               sign=1.0, overflow_flag=None):
+    CALLS.append(("conv2d_pix", k, n1, bool(gated), gamma is not None, out16 is not None, x is not None))
+    taps = k * k
+    a = _pix_decode(a16)                                           # [rows, 32]
+    cols = Act(a.shape[0], taps * 32, f32=torch.empty(a.shape[0], taps * 32))
+    im2col(a, n_images, h, w, 32, k, dilation, cols)
+    CALLS.pop()
+    wt = w1.reshape(32, taps, 64)
+    wf = f16_join(wt[:, :, :32], wt[:, :, 32:]).reshape(32, taps * 32)
+    v = cols.f32 @ wf.T + bias1
+    if gated:
+        u = torch.relu(v)
+        uh, ul = f16_split(u)
+        if overflow_flag is not None and bool((~(u.abs() <= 65000.0)).any()):
+            overflow_flag.fill_(1)
+        vg = f16_join(uh, ul) @ f16_join(w2[:, :32], w2[:, 32:]).T + bias2
+        v = out_f32[:, :32] + vg[:, :32] * torch.sigmoid(vg[:, 32:])
+        if post_relu:
+            v = torch.relu(v)
+    elif relu1:
+        v = torch.relu(v)
+    v = v[:, :n1]
+    if gamma is not None:
+        v = torch.nn.functional.layer_norm(v, (n1,), gamma, beta, eps)
+    v = v.clone()
+    if x is not None:
+        c = x.shape[1]
+        x += sign * inv_mask.reshape(h * w, c).repeat(x.shape[0] // (h * w), 1) * v[:, :c]
+    if out_f32 is not None:
+        out_f32[:, :n1].copy_(v)
+    if out16 is not None:
+        _pix_store(out16, v, relu_planes, overflow_flag)
+
+
 def masked_add(x, t, hw, g, sign):
     CALLS.append(("masked_add", sign))
     rows, c = x.shape
@@ -470,7 +534,7 @@ def require_cuda(t, name="tensor", dtype=torch.float32):
 
 def install(monkeypatch):
     CALLS.clear()
-    for name in ["conv2d_rows", "layout_transpose", "im2col", "masked_add", "radial_logprob", "radial_sample", "gate_norm", "affine_couple", "sub_rows", "flow_small", "linear", "ingest", "base_logprob", "base_sample", "leaky_relu", "permute", "lu_assemble",
+    for name in ["conv2d_rows", "pix_encode", "conv2d_pix", "conv2d_pix_supported", "layout_transpose", "im2col", "masked_add", "radial_logprob", "radial_sample", "gate_norm", "affine_couple", "sub_rows", "flow_small", "linear", "ingest", "base_logprob", "base_sample", "leaky_relu", "permute", "lu_assemble",
                  "lu_logabsdet", "vec_logabs", "tri_inverse", "transpose", "scale_rows_cols", "split_tf32", "split_f16", "to_bf16",
                  "householder_right", "softplus", "matmul_f32", "matmul_f64", "require_cuda", "linear_splitk", "planes_glue",
                  "base_backward", "mat_prep", "tri_mask", "tri_inverse_batched", "rowdot", "colcomb", "rank1"]:

@@ -29,13 +29,31 @@ def test_image_launch_plan(fake_ops):
     B, L = spec["coupling_blocks"], spec["num_layers"]
     assert names.count("layout_transpose") == 1                       # NCHW -> channels-last, fused with x / scale
     assert [c for c in fake_ops.CALLS if c[0] == "layout_transpose"][0][1:] == (16, 49, 2)
-    assert names.count("conv2d_rows") == B * (2 + L)                   # one implicit-GEMM launch per k x k convolution
-    assert names.count("im2col") == 0
-    assert names.count("gate_norm") == B * L
-    assert names.count("masked_add") == B
-    assert names.count("linear") == (2 * B + 1) + B * L               # 1x1-conv affine layers + the 1x1 gate convolutions
+    # the whole ConvNet2D on pixel planes: encode + first + one launch per gated block + last (which updates x itself)
+    assert names.count("pix_encode") == B and names.count("conv2d_pix") == B * (2 + L)
+    assert names.count("conv2d_rows") == 0 and names.count("im2col") == 0
+    assert names.count("gate_norm") == 0 and names.count("masked_add") == 0
+    assert names.count("linear") == 2 * B + 1                          # the 1x1-convolution affine layers
     assert names.count("radial_logprob") == 1                          # on the channels-last memory, loc permuted
-    first = [c for c in fake_ops.CALLS if c[0] == "conv2d_rows"][0]
+    pix = [c for c in fake_ops.CALLS if c[0] == "conv2d_pix"]
+    assert pix[0][1:] == (3, 32, False, False, True, False)            # first: planes out
+    assert pix[1][1:] == (3, 32, True, True, True, False)              # GatedConv + ReLU + LayerNormChannels in one launch
+    assert pix[1 + L][1:] == (3, 16, False, False, False, True)        # last: the coupling update
+    assert [c for c in fake_ops.CALLS if c[0] == "pix_encode"][0][1:] == (16, True, False)   # x * mask fused into the encoding
+    from usflows_b200 import image_engine
+    image_engine.PIX_CONV = False                                      # the implicit-GEMM route (one launch per k x k conv)
+    try:
+        fake_ops.CALLS.clear()
+        lp1 = build_flow(spec, params, device="cpu", precision="fp32").log_prob(arr["x"])
+        names1 = [c[0] for c in fake_ops.CALLS]
+        calls1 = list(fake_ops.CALLS)
+    finally:
+        image_engine.PIX_CONV = True
+    assert rel_err(lp1, lp) < 1e-5
+    assert names1.count("conv2d_rows") == B * (2 + L) and names1.count("im2col") == 0
+    assert names1.count("gate_norm") == B * L and names1.count("masked_add") == B
+    assert names1.count("linear") == (2 * B + 1) + B * L              # 1x1-conv affine layers + the 1x1 gate convolutions
+    first = [c for c in calls1 if c[0] == "conv2d_rows"][0]
     assert first[1:] == (16, 3, 32, True, False, False)                # coupling mask fused into the first gather
     from usflows_b200 import image_engine
     image_engine.IMPLICIT_CONV = False                                 # the gather + contraction route

@@ -45,3 +45,58 @@ for rr in (128 * 148, 128 * 148 * 4):
     nn = rr // 49
     us = timed(lambda: ops.conv2d_rows(x, nn, H, W, C, k, 1, w_hi, w_lo, N, bias=b, relu=True, out=out, relu_in=True))
     print(f"conv2d_rows {nn} images ({nn * 49 / 128 / 148:.2f} tiles per SM): {us:.1f} us")
+
+# ---- the pixel-plane route (usf_conv2d_pix): one 4-D TMA box per tap, no gather threads -------------------------------
+from usflows_b200 import image_engine
+a16 = torch.empty(rows, 64, dtype=torch.float16, device="cuda")
+b16 = torch.empty(rows, 64, dtype=torch.float16, device="cuda")
+y = torch.randn(rows, 32, generator=g).cuda()
+x16c = torch.randn(rows, 16, generator=g).cuda()
+mask = (torch.rand(49 * 16, generator=g) > 0.5).float().cuda()
+w16 = image_engine._pix_weight(w, k * k, C, 32, None)
+b32 = image_engine._pad_vec(b, 32)
+w2 = (torch.randn(64, 32, generator=g) / 6).cuda()
+w16_2 = image_engine._pix_weight(w2, 1, 32, 64, None)
+b64 = torch.randn(64, generator=g).cuda()
+gamma, beta = torch.ones(32, device="cuda"), torch.zeros(32, device="cuda")
+us = timed(lambda: ops.pix_encode(x16c, 49, a16, mask=mask))
+print(f"pix_encode (16 channels, mask): {us:.1f} us")
+ops.pix_encode(x, 49, a16, relu=True)
+for taps in (1, 2, 3):
+    _lib.load().usf_set_pix_chain_taps(taps)
+    us = timed(lambda: ops.conv2d_pix(a16, n, H, W, k, 1, w16, b32, 32, out_f32=out.f32, out16=b16, relu_planes=True))
+    print(f"conv2d_pix plain (fp32 rows + planes out), {taps} taps per chain: {us:.1f} us")
+    us = timed(lambda: ops.conv2d_pix(a16, n, H, W, k, 1, w16, b32, 32, gated=True, post_relu=True, w2=w16_2, bias2=b64,
+                                      gamma=gamma, beta=beta, eps=1e-5, out_f32=y, out16=b16, relu_planes=True))
+    print(f"conv2d_pix gated block (conv 3x3 + conv 1x1 + gate + ReLU + LayerNorm), {taps} taps per chain: {us:.1f} us")
+_lib.load().usf_set_pix_chain_taps(2)
+us = timed(lambda: ops.conv2d_pix(a16, n, H, W, k, 1, w16, b32, 16, x=x16c, inv_mask=mask, sign=1.0))
+print(f"conv2d_pix last (coupling update of 16 channels): {us:.1f} us")
+for nn in (5 * 148, 5 * 148 * 4):
+    us = timed(lambda: ops.conv2d_pix(a16, nn, H, W, k, 1, w16, b32, 32, out_f32=out.f32, out16=b16))
+    print(f"conv2d_pix plain {nn} images ({nn / 5 / 148:.0f} tiles per SM): {us:.1f} us")
+
+for flags, what in ((64, "no activation loads"), (128, "no MMAs"), (256, "no epilogue loads / stores"), (64 | 128, "no loads, no MMAs"),
+                    (64 | 256, "no loads, no epilogue traffic"), (64 | 128 | 256, "skeleton only")):
+    _lib.load().usf_debug_gemm_timeline(None, flags)
+    us = timed(lambda: ops.conv2d_pix(a16, n, H, W, k, 1, w16, b32, 32, out_f32=out.f32, out16=b16, relu_planes=True))
+    us2 = timed(lambda: ops.conv2d_pix(a16, n, H, W, k, 1, w16, b32, 32, gated=True, post_relu=True, w2=w16_2, bias2=b64,
+                                       gamma=gamma, beta=beta, eps=1e-5, out_f32=y, out16=b16, relu_planes=True))
+    print(f"conv2d_pix, {what}: plain {us:.1f} us, gated {us2:.1f} us")
+_lib.load().usf_debug_gemm_timeline(None, 0)
+us = timed(lambda: ops.conv2d_pix(a16, n, H, W, k, 1, w16, b32, 32, out16=b16, relu_planes=True))
+print(f"conv2d_pix plain, planes out only: {us:.1f} us")
+us = timed(lambda: ops.conv2d_pix(a16, n, H, W, k, 1, w16, b32, 32, out_f32=out.f32))
+print(f"conv2d_pix plain, fp32 rows out only: {us:.1f} us")
+
+
+# time against tiles per SM (5 images per tile, 148 SMs)
+for flags in (0, 64 | 256, 64 | 128 | 256):
+    _lib.load().usf_debug_gemm_timeline(None, flags)
+    line = []
+    for tps in (1, 2, 3, 4, 6, 8, 12, 16, 22):
+        nn = 5 * 148 * tps
+        us = timed(lambda: ops.conv2d_pix(a16, nn, H, W, k, 1, w16, b32, 32, out_f32=out.f32, out16=b16, relu_planes=True))
+        line.append(f"{tps}: {us:.1f}")
+    print(f"conv2d_pix plain, flags {flags}, us by tiles per SM: " + ", ".join(line))
+_lib.load().usf_debug_gemm_timeline(None, 0)

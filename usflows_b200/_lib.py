@@ -38,6 +38,22 @@ class LinearArgs(C.Structure):
     ]
 
 
+class ConvPixArgs(C.Structure):
+    """Mirror of `usf_conv_pix_args` (include/usflows_b200.h)."""
+
+    _fields_ = [
+        ("a16", C.c_void_p), ("n_images", C.c_int64),
+        ("h", C.c_int32), ("w", C.c_int32), ("ksize", C.c_int32), ("dilation", C.c_int32),
+        ("w1", C.c_void_p), ("bias1", C.c_void_p),
+        ("n1", C.c_int32), ("relu1", C.c_int32), ("gated", C.c_int32), ("post_relu", C.c_int32),
+        ("w2", C.c_void_p), ("bias2", C.c_void_p), ("gamma", C.c_void_p), ("beta", C.c_void_p),
+        ("eps", C.c_float), ("sign", C.c_float),
+        ("out_f32", C.c_void_p), ("ld_f32", C.c_int64), ("out16", C.c_void_p),
+        ("relu_planes", C.c_int32), ("c_x", C.c_int32),
+        ("x", C.c_void_p), ("ldx", C.c_int64), ("inv_mask", C.c_void_p), ("overflow_flag", C.c_void_p),
+    ]
+
+
 class GlueArgs(C.Structure):
     """Mirror of `usf_glue_args` (include/usflows_b200.h)."""
 
@@ -112,6 +128,9 @@ SIGNATURES = {
     "usf_im2col": (C.c_int, [_P, _I64, _I64, _I32, _I32, _I32, _I32, _I32, _P, _I32, C.POINTER(Planes), _P, _P]),
     "usf_conv2d_rows": (C.c_int, [C.POINTER(LinearArgs), _P, _I64, _I64, _I32, _I32, _I32, _I32, _I32, _P, _I32, _P]),
     "usf_masked_add": (C.c_int, [_P, _I64, _P, _I64, _I64, _I32, _I32, _P, _F, _P]),
+    "usf_pix_encode": (C.c_int, [_P, _I64, _I64, _I32, _I32, _P, _I32, _P, _P, _P]),
+    "usf_conv2d_pix": (C.c_int, [C.POINTER(ConvPixArgs), _P]),
+    "usf_set_pix_chain_taps": (C.c_int, [_I32]),
     "usf_gate_norm": (C.c_int, [_P, _I64, _P, _I64, _I64, _I32, _I32, _I32, _P, _P, _F, _P, _I64, C.POINTER(Planes), _I32,
                                 C.POINTER(Planes), _P, _P]),
     "usf_leaky_relu": (C.c_int, [_P, _I64, _I64, _I32, _F, _P, _I64, _P, _P]),

@@ -13,6 +13,14 @@
 #include "plan.cuh"
 
 namespace usf {
+// csrc/conv_pix.cuh (compiled in conv_pix_inst.cu only: the kernel is not a template)
+extern int g_pix_chain_taps;
+int launch_conv_pix(const usf_conv_pix_args* a, cudaStream_t st);
+int launch_pix_encode(const float* x, long long ldx, long long rows, int c, int hw, const float* mask, int relu, void* out16,
+                      int* overflow_flag, cudaStream_t st);
+}  // namespace usf
+
+namespace usf {
 
 thread_local char g_err[512] = "";
 int g_force_block_n = 0;
@@ -390,6 +398,41 @@ int usf_conv2d_rows(const usf_linear_args* a, const float* act, int64_t ld_act, 
   if (rc) return rc;
   ConvGeom g{act, ld_act, h, w, c_in, k, dilation, mask, relu_in ? 1 : 0};
   return launch_conv_tc(a, g, ep, S(stream));
+}
+
+int usf_pix_encode(const float* x, int64_t ldx, int64_t rows, int32_t c, int32_t hw, const float* mask, int32_t relu,
+                   void* out16, int32_t* overflow_flag, void* stream) {
+  USF_REQUIRE(x && out16 && rows >= 0 && c > 0 && c <= 32 && hw > 0 && ldx >= c, "bad input (c <= 32 channels)");
+  USF_REQUIRE(aligned16(out16), "unaligned pixel planes");
+  if (rows == 0) return USF_OK;
+  return launch_pix_encode(x, ldx, rows, c, hw, mask, relu ? 1 : 0, out16, overflow_flag, S(stream));
+}
+
+int usf_conv2d_pix(const usf_conv_pix_args* a, void* stream) {
+  USF_REQUIRE(a != nullptr, "null args");
+  USF_REQUIRE(a->a16 && a->w1 && a->bias1 && aligned16(a->a16) && aligned16(a->w1) && aligned16(a->bias1), "null / unaligned operand");
+  USF_REQUIRE(a->n_images >= 0 && a->n_images < (1ll << 31) && a->h > 0 && a->w > 0, "bad image extent");
+  USF_REQUIRE(a->ksize >= 1 && (a->ksize & 1) && a->dilation >= 1, "odd kernel size (padding 'same') and dilation >= 1");
+  USF_REQUIRE(a->n1 >= 4 && a->n1 <= 32 && a->n1 % 4 == 0, "n1: a multiple of 4, at most 32");
+  USF_REQUIRE((a->gamma == nullptr) == (a->beta == nullptr), "gamma and beta come as a pair");
+  if (a->gated) {
+    USF_REQUIRE(a->n1 == 32 && a->w2 && a->bias2 && aligned16(a->w2), "gated block: 32 channels, w2 and bias2");
+    USF_REQUIRE(a->out_f32 && a->ld_f32 >= 32 && a->ld_f32 % 4 == 0 && aligned16(a->out_f32), "gated block: fp32 residual stream [rows, 32]");
+    USF_REQUIRE(!a->x, "gated block: no coupling update");
+  } else {
+    USF_REQUIRE(a->out_f32 || a->out16 || a->x, "no output");
+    USF_REQUIRE(!a->out_f32 || (a->ld_f32 >= a->n1 && a->ld_f32 % 4 == 0 && aligned16(a->out_f32)), "out_f32: 16-byte aligned rows");
+    USF_REQUIRE(!a->x || (a->inv_mask && a->c_x >= 1 && a->c_x <= a->n1 && a->ldx >= a->c_x), "coupling update: x, inv_mask, c_x <= n1");
+  }
+  USF_REQUIRE(!a->out16 || aligned16(a->out16), "unaligned pixel planes");
+  if (a->n_images == 0) return USF_OK;
+  return launch_conv_pix(a, S(stream));
+}
+
+int usf_set_pix_chain_taps(int32_t taps) {
+  USF_REQUIRE(taps >= 1, "at least one tap per chain");
+  g_pix_chain_taps = taps;
+  return USF_OK;
 }
 
 int usf_masked_add(float* x, int64_t ldx, const float* t, int64_t ldt, int64_t rows, int32_t c, int32_t hw, const float* g,

@@ -60,7 +60,22 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  // fast path: the non-blocking test costs ~16 cycles on a completed phase, the (potentially suspending) try_wait ~180
+  // even when the phase is already complete (measured in-kernel, tools/conv_probe.py) -- and in a full pipeline most
+  // waits find their phase complete
+  if (mbar_test_wait(bar, parity)) return;
 #if USF_WATCHDOG
   unsigned long long t0 = 0;
   uint32_t spins = 0;

@@ -843,7 +843,7 @@ class _Workspace:
     def planes(self, device, name: str, rows: int, width: int, fmt: str) -> torch.Tensor:
         ld = pad4(width)
         need = rows * ld
-        dtype = torch.bfloat16 if fmt == "bf16" else torch.float16 if fmt in ("h16", "l16") else torch.float32
+        dtype = torch.bfloat16 if fmt == "bf16" else torch.float16 if fmt in ("h16", "l16", "pix") else torch.float32
         pair = self._PAIR.get(fmt)
         if pair is not None:
             # the two planes of a split format live in ONE allocation, hi first: the contraction kernel then fetches both

@@ -28,6 +28,8 @@ from .ops import Act, ENGINE_SIMT, ENGINE_TC_3XF16, ENGINE_TC_3XTF32, ENGINE_TC_
 _PLANES = {ENGINE_SIMT: ("f32",), ENGINE_TC_TF32: ("f32",), ENGINE_TC_3XF16: ("h16", "l16"), ENGINE_TC_3XTF32: ("hi", "lo"),
            ENGINE_TC_BF16: ("bf16",)}
 IMPLICIT_CONV = True                # k x k convolutions as implicit GEMMs (usf_conv2d_rows) where the shape allows it
+PIX_CONV = True                     # ... and the whole ConvNet2D on pixel planes (usf_conv2d_pix) where its widths allow it
+PIX_CH = 32                         # channels of a pixel-plane row
 IMAGE_CHUNK_ROWS = 1 << 19          # channels-last rows (N*H*W) per chunk: bounds the im2col workspace (rows x k*k*C)
 
 
@@ -70,6 +72,22 @@ class _Gemm:
                    overflow_flag=flag)
 
 
+def _pix_weight(w: torch.Tensor, taps: int, cin: int, n_pad: int, wflag) -> torch.Tensor:
+    """Contraction weight [N, taps * cin] (usf_im2col column order) -> [n_pad, taps * 64] fp16 for usf_conv2d_pix: per tap
+    32 high halves | 32 low halves' of the input channels, channels >= cin and rows >= N zero."""
+    n = w.shape[0]
+    w3 = torch.zeros(n_pad, taps, PIX_CH, dtype=torch.float32, device=w.device)
+    w3[:n, :, :cin] = w.to(torch.float32).reshape(n, taps, cin)
+    hi, lo = _operand(w3.reshape(n_pad, taps * PIX_CH), "fp32", ENGINE_TC_3XF16, wflag)
+    return torch.cat([hi.reshape(n_pad, taps, PIX_CH), lo.reshape(n_pad, taps, PIX_CH)], dim=2).reshape(n_pad, taps * 64).contiguous()
+
+
+def _pad_vec(b: torch.Tensor, n: int) -> torch.Tensor:
+    out = torch.zeros(n, dtype=torch.float32, device=b.device)
+    out[:b.shape[0]] = b.to(torch.float32)
+    return out
+
+
 def _conv_weight(conv) -> torch.Tensor:
     """nn.Conv2d weight [C_out, C_in, kh, kw] -> contraction weight [C_out, (kh, kw, C_in)] (the usf_im2col column order)."""
     w = conv.weight.detach()
@@ -97,9 +115,78 @@ class _ConvNet2DPlan:
             self.blocks.append((b["gated"], g1, g2, ln))
         self.last = _Gemm(mode, _conv_weight(d["last"]), d["last"].bias.detach(), wflag, pad_n=True, conv_cin=cin(d["last"]))
         self.gemms = [self.first, self.last] + [g for b in self.blocks for g in b[1:3] if g is not None]
+        self.pix = None
+        if self._pix_ok(mode, d, H, W):
+            self._prepare_pix(d, wflag)
+
+    # ---- the whole network on pixel planes (usf_conv2d_pix): 2 + num_layers launches + usf_pix_encode -------------------
+    def _pix_ok(self, mode: str, d: dict, H: int, W: int) -> bool:
+        if not (PIX_CONV and IMPLICIT_CONV and mode == "fp32" and self.k > 1):
+            return False
+        gated_any = any(b["gated"] for b in d["blocks"])
+        if not ops.conv2d_pix_supported(H, W, self.k, gated_any):
+            return False
+        widths = [d["first"].weight.shape[1] <= PIX_CH, d["first"].weight.shape[0] == PIX_CH,
+                  d["last"].weight.shape[1] == PIX_CH, d["last"].weight.shape[0] <= PIX_CH, d["last"].weight.shape[0] % 4 == 0]
+        for b in d["blocks"]:
+            widths += [tuple(b["conv1"].weight.shape[:2]) == (PIX_CH, PIX_CH)]
+            if b["gated"]:
+                widths += [tuple(b["conv2"].weight.shape[:2]) == (2 * PIX_CH, PIX_CH)]
+        return all(widths)
+
+    def _prepare_pix(self, d: dict, wflag) -> None:
+        taps = self.k * self.k
+        pw = lambda conv, n_pad, t: _pix_weight(_conv_weight(conv), t, conv.weight.shape[1], n_pad, wflag)   # noqa: E731
+        blocks = []
+        for b in d["blocks"]:
+            ln = None if b["ln"] is None else (b["ln"].gamma.detach().reshape(-1).float().contiguous(),
+                                               b["ln"].beta.detach().reshape(-1).float().contiguous(), float(b["ln"].eps))
+            blk = dict(gated=b["gated"], w1=pw(b["conv1"], PIX_CH, taps), b1=_pad_vec(b["conv1"].bias.detach(), PIX_CH), ln=ln)
+            if b["gated"]:
+                blk.update(w2=pw(b["conv2"], 2 * PIX_CH, 1), b2=_pad_vec(b["conv2"].bias.detach(), 2 * PIX_CH))
+            blocks.append(blk)
+        self.pix = dict(first=(pw(d["first"], PIX_CH, taps), _pad_vec(d["first"].bias.detach(), PIX_CH)), blocks=blocks,
+                        last=(pw(d["last"], PIX_CH, taps), _pad_vec(d["last"].bias.detach(), PIX_CH)),
+                        n_out=d["last"].weight.shape[0])
+
+    def run_pix(self, x_rows: torch.Tensor, n_images: int, mask_cl, flag, *, update=None) -> Optional[torch.Tensor]:
+        """t = net(x * mask) on pixel planes.  `update` = (x, inv_mask, sign): the last convolution applies the coupling
+        update x += sign * (1 - mask) * t itself and nothing is returned; else t comes back as fp32 rows [n*H*W, c_out]."""
+        dev, rows = x_rows.device, x_rows.shape[0]
+        H, W, k, dil, px = self.H, self.W, self.k, self.dil, self.pix
+        bufs = [_workspace.planes(dev, "pix_a", rows, 64, "pix"), _workspace.planes(dev, "pix_b", rows, 64, "pix")]
+        y = _workspace.planes(dev, "img_y", rows, PIX_CH, "f32")
+        blocks = px["blocks"]
+        relu_for = lambda i: i < len(blocks) and blocks[i]["gated"]     # noqa: E731  (GatedConv starts with a ReLU)
+        ops.pix_encode(x_rows, H * W, bufs[0], mask=mask_cl, overflow_flag=flag)
+        cur = 0
+        ops.conv2d_pix(bufs[cur], n_images, H, W, k, dil, px["first"][0], px["first"][1], PIX_CH, out_f32=y,
+                       out16=bufs[cur ^ 1], relu_planes=relu_for(0), overflow_flag=flag)
+        cur ^= 1
+        for i, b in enumerate(blocks):
+            gamma, beta, eps = b["ln"] if b["ln"] is not None else (None, None, 0.0)
+            if b["gated"]:      # GatedConv (networks.py:100-121) -> ReLU -> LayerNormChannels: one launch
+                ops.conv2d_pix(bufs[cur], n_images, H, W, k, dil, b["w1"], b["b1"], PIX_CH, gated=True, post_relu=True,
+                               w2=b["w2"], bias2=b["b2"], gamma=gamma, beta=beta, eps=eps, out_f32=y, out16=bufs[cur ^ 1],
+                               relu_planes=relu_for(i + 1), overflow_flag=flag)
+            else:               # Conv k x k -> ReLU -> LayerNormChannels
+                ops.conv2d_pix(bufs[cur], n_images, H, W, k, dil, b["w1"], b["b1"], PIX_CH, relu1=True, gamma=gamma, beta=beta,
+                               eps=eps, out_f32=y, out16=bufs[cur ^ 1], relu_planes=relu_for(i + 1), overflow_flag=flag)
+            cur ^= 1
+        if update is not None:
+            xs, inv_mask, sign = update
+            ops.conv2d_pix(bufs[cur], n_images, H, W, k, dil, px["last"][0], px["last"][1], px["n_out"], x=xs,
+                           inv_mask=inv_mask, sign=sign, overflow_flag=flag)
+            return None
+        t = _workspace.planes(dev, "img_t", rows, px["n_out"], "f32")
+        ops.conv2d_pix(bufs[cur], n_images, H, W, k, dil, px["last"][0], px["last"][1], px["n_out"], out_f32=t,
+                       overflow_flag=flag)
+        return t
 
     def run(self, x_rows: torch.Tensor, n_images: int, mask_cl: Optional[torch.Tensor], flag) -> torch.Tensor:
         """t = net(x * mask) as fp32 rows [n*H*W, c_out] (a workspace buffer)."""
+        if self.pix is not None:
+            return self.run_pix(x_rows, n_images, mask_cl, flag)
         dev, rows = x_rows.device, x_rows.shape[0]
         H, W, k, dil = self.H, self.W, self.k, self.dil
 
@@ -222,8 +309,11 @@ class ImageProgram:
                 cur = dst
             else:
                 _, plan, mask_cl, inv_cl, sign = op
-                t = plan.run(cur, n, mask_cl, flag)
-                ops.masked_add(cur, t, HW, inv_cl, sign)
+                if plan.pix is not None and plan.pix["n_out"] == C:     # the last convolution updates x itself
+                    plan.run_pix(cur, n, mask_cl, flag, update=(cur, inv_cl, sign))
+                else:
+                    t = plan.run(cur, n, mask_cl, flag)
+                    ops.masked_add(cur, t, HW, inv_cl, sign)
         if direct:
             if cur.data_ptr() != out.data_ptr():
                 out.view(rows, C).copy_(cur)

@@ -285,6 +285,48 @@ def conv2d_rows(x: torch.Tensor, n_images: int, h: int, w: int, c: int, k: int, 
                                       int(relu_in), _stream()))
 
 
+PIX_SMEM_LIMIT = 227 * 1024
+
+
+def conv2d_pix_supported(h: int, w: int, k: int, gated: bool = True) -> bool:
+    """Whether usf_conv2d_pix serves this image / kernel size (rows <= 256 pixels wide; the k*k*4 KB weight next to at least
+    two 32 KB pipeline stages -- and the gate's operand tile -- in shared memory)."""
+    fixed = k * k * 4096 + (8192 if gated else 0) + 32768 + 1280
+    return w <= 256 and k % 2 == 1 and (PIX_SMEM_LIMIT - fixed) // 32768 >= 2
+
+
+def pix_encode(x: torch.Tensor, hw: int, out16: torch.Tensor, *, mask=None, relu: bool = False,
+               overflow_flag: Optional[torch.Tensor] = None) -> None:
+    """fp32 channels-last rows [rows, c <= 32] -> pixel planes [rows, 64] fp16 (32 hi | 32 lo'); see usf_pix_encode."""
+    global LAUNCHES
+    LAUNCHES += 1
+    rows, c = x.shape
+    check(_lib.load().usf_pix_encode(_ptr(x), _ld(x), rows, c, hw, _ptr(mask), int(relu), _ptr(out16), _ptr(overflow_flag),
+                                     _stream()))
+
+
+def conv2d_pix(a16: torch.Tensor, n_images: int, h: int, w: int, k: int, dilation: int, w1: torch.Tensor, bias1: torch.Tensor,
+               n1: int, *, relu1: bool = False, gated: bool = False, post_relu: bool = False, w2=None, bias2=None, gamma=None,
+               beta=None, eps: float = 0.0, out_f32=None, out16=None, relu_planes: bool = False, x=None, inv_mask=None,
+               sign: float = 1.0, overflow_flag: Optional[torch.Tensor] = None) -> None:
+    """k x k 'same' convolution over pixel planes (one 4-D TMA box per tap), plain or as a whole GatedConv block; see
+    usf_conv2d_pix."""
+    global LAUNCHES
+    LAUNCHES += 1
+    a = _lib.ConvPixArgs()
+    a.a16, a.n_images, a.h, a.w, a.ksize, a.dilation = _ptr(a16), n_images, h, w, k, dilation
+    a.w1, a.bias1, a.n1, a.relu1 = _ptr(w1), _ptr(bias1), n1, int(relu1)
+    a.gated, a.post_relu, a.w2, a.bias2 = int(gated), int(post_relu), _ptr(w2), _ptr(bias2)
+    a.gamma, a.beta, a.eps, a.sign = _ptr(gamma), _ptr(beta), float(eps), float(sign)
+    if out_f32 is not None:
+        a.out_f32, a.ld_f32 = _ptr(out_f32), _ld(out_f32)
+    a.out16, a.relu_planes = _ptr(out16), int(relu_planes)
+    if x is not None:
+        a.x, a.ldx, a.inv_mask, a.c_x = _ptr(x), _ld(x), _ptr(inv_mask), x.shape[1]
+    a.overflow_flag = _ptr(overflow_flag)
+    check(_lib.load().usf_conv2d_pix(C.byref(a), _stream()))
+
+
 def masked_add(x: torch.Tensor, t: torch.Tensor, hw: int, g: torch.Tensor, sign: float) -> None:
     global LAUNCHES
     LAUNCHES += 1
