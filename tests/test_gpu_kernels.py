@@ -58,6 +58,33 @@ def test_linear_all_engines_full_epilogue(eng_name, eng, fmt, tol, M, N, K):
     assert rel_err(out.bf16.float(), out.f32) <= 1e-2
 
 
+@pytest.mark.parametrize("M,N,K", [(4096, 16, 16), (50000, 16, 16), (7001, 10, 7), (4100, 3, 16), (9000, 16, 5)])
+def test_narrow_rows_kernel_full_epilogue(M, N, K):
+    """The SIMT engine's narrow fast path (N, K <= 16, many rows: the 16 x 16 1x1-convolution affine layers of the image
+    flows): the same full epilogue as the tiled kernel, against fp64."""
+    from usflows_b200 import ops
+    from usflows_b200.ops import Act
+    g = torch.Generator().manual_seed(M + N + K)
+    a = torch.randn(M, K, generator=g)
+    w = torch.randn(N, K, generator=g) / K ** 0.5
+    bias, colscale, postsub = (torch.randn(N, generator=g) for _ in range(3))
+    resid = torch.randn(M, N, generator=g)
+    act, _ = _planes(a, "f32")
+    wact, _ = _planes(w, "f32")
+    racc, _ = _planes(resid, "f32")
+    out = Act(M, N, f32=torch.zeros(M, ops.pad4(N), device="cuda")[:, :N],
+              hi=torch.zeros(M, ops.pad4(N), device="cuda")[:, :N], lo=torch.zeros(M, ops.pad4(N), device="cuda")[:, :N])
+    ops.linear(0, act, wact.f32, None, N, K, bias=bias.cuda(), relu=True, resid=racc, resid_sign=-1.0,
+               colscale=colscale.cuda(), postsub=postsub.cuda(), out=out)
+    ref = torch.relu(a.double() @ w.double().T + bias.double())
+    ref = (resid.double() - ref) * colscale.double() - postsub.double()
+    assert rel_err(out.f32, ref) <= 3e-6
+    assert rel_err(out.hi.double() + out.lo.double(), out.f32) <= 1e-6
+    plain = torch.empty(M, N, device="cuda")                       # dense output, no epilogue terms
+    ops.linear(0, act, wact.f32, None, N, K, out=Act(M, N, f32=plain))
+    assert rel_err(plain, a.double() @ w.double().T) <= 3e-6
+
+
 @pytest.mark.parametrize("bn", [32, 64, 128, 208, 256])
 @pytest.mark.parametrize("chunk", [0, 1, 3])
 def test_tile_widths_and_accumulation_chunks(bn, chunk):

@@ -100,3 +100,15 @@ for flags in (0, 64 | 256, 64 | 128 | 256):
         line.append(f"{tps}: {us:.1f}")
     print(f"conv2d_pix plain, flags {flags}, us by tiles per SM: " + ", ".join(line))
 _lib.load().usf_debug_gemm_timeline(None, 0)
+
+for ga in (0, 1, 2, 3):
+    _lib.load().usf_set_pix_gate_at(ga)
+    line = []
+    for taps in (1, 2, 3):
+        _lib.load().usf_set_pix_chain_taps(taps)
+        us = timed(lambda: ops.conv2d_pix(a16, n, H, W, k, 1, w16, b32, 32, gated=True, post_relu=True, w2=w16_2, bias2=b64,
+                                          gamma=gamma, beta=beta, eps=1e-5, out_f32=y, out16=b16, relu_planes=True))
+        line.append(f"{taps} taps/chain {us:.1f} us")
+    print(f"conv2d_pix gated, gate contraction behind {ga} chains of the next tile: " + ", ".join(line))
+_lib.load().usf_set_pix_gate_at(0)
+_lib.load().usf_set_pix_chain_taps(3)

@@ -131,6 +131,7 @@ SIGNATURES = {
     "usf_pix_encode": (C.c_int, [_P, _I64, _I64, _I32, _I32, _P, _I32, _P, _P, _P]),
     "usf_conv2d_pix": (C.c_int, [C.POINTER(ConvPixArgs), _P]),
     "usf_set_pix_chain_taps": (C.c_int, [_I32]),
+    "usf_set_pix_gate_at": (C.c_int, [_I32]),
     "usf_gate_norm": (C.c_int, [_P, _I64, _P, _I64, _I64, _I32, _I32, _I32, _P, _P, _F, _P, _I64, C.POINTER(Planes), _I32,
                                 C.POINTER(Planes), _P, _P]),
     "usf_leaky_relu": (C.c_int, [_P, _I64, _I64, _I32, _F, _P, _I64, _P, _P]),

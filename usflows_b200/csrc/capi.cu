@@ -15,6 +15,7 @@
 namespace usf {
 // csrc/conv_pix.cuh (compiled in conv_pix_inst.cu only: the kernel is not a template)
 extern int g_pix_chain_taps;
+extern int g_pix_gate_at;
 int launch_conv_pix(const usf_conv_pix_args* a, cudaStream_t st);
 int launch_pix_encode(const float* x, long long ldx, long long rows, int c, int hw, const float* mask, int relu, void* out16,
                       int* overflow_flag, cudaStream_t st);
@@ -432,6 +433,12 @@ int usf_conv2d_pix(const usf_conv_pix_args* a, void* stream) {
 int usf_set_pix_chain_taps(int32_t taps) {
   USF_REQUIRE(taps >= 1, "at least one tap per chain");
   g_pix_chain_taps = taps;
+  return USF_OK;
+}
+
+int usf_set_pix_gate_at(int32_t chains) {
+  USF_REQUIRE(chains >= 0, "negative");
+  g_pix_gate_at = chains;
   return USF_OK;
 }
 

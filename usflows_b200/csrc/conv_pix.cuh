@@ -31,7 +31,7 @@ struct PixArgs {
   int n_images, H, W, HW;
   int ksize, dil, taps;
   int imgs, hr, tiles_per_img;          // tile geometry: imgs whole images (tiles_per_img == 1) or hr image rows
-  int chain_taps, stages;
+  int chain_taps, stages, gate_at;
   unsigned box_bytes;
   int gated;
   const float* bias1;                   // [32]
@@ -343,7 +343,8 @@ conv_pix_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
       int acc = 0;
       uint32_t acc_phase = 0, a2_phase = 0;
       bool pending = false;                              // the previous tile's 1 x 1 contraction has not been issued yet
-      const int gate_at = n_chains > NBUF ? NBUF : n_chains - 1;
+      const int gate_max = n_chains > NBUF ? NBUF : n_chains - 1;
+      const int gate_at = p.gate_at < gate_max ? p.gate_at : gate_max;
       const uint32_t a_lo0 = desc_lo(smem_base + (uint32_t)mt * A_MT), w_lo0 = desc_lo(w1_base);
       const uint32_t d_col = tmem_base + (uint32_t)mt * 32;
       auto gate_mma = [&]() {
@@ -599,6 +600,7 @@ inline size_t conv_pix_smem_bytes(int taps, int gated) {
          (gated ? convpix::W2_BYTES : 0) + convpix::A_STAGE + 1024 + 256;
 }
 
+extern int g_pix_gate_at;               // chains of the next tile issued in front of a tile's gate contraction
 extern int g_pix_chain_taps;            // taps per accumulation chain (3 = 96 K-elements; 2 = the flat engine's chain length)
 int launch_conv_pix(const usf_conv_pix_args* a, cudaStream_t st);
 int launch_pix_encode(const float* x, long long ldx, long long rows, int c, int hw, const float* mask, int relu, void* out16,

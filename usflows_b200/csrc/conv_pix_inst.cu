@@ -4,6 +4,7 @@
 namespace usf {
 
 int g_pix_chain_taps = 3;
+int g_pix_gate_at = 0;
 extern int g_dbg_flags;
 
 static int make_pix_map(CUtensorMap* map, const void* ptr, long long n_images, int H, int W, int hr, int imgs) {
@@ -44,6 +45,7 @@ int launch_conv_pix(const usf_conv_pix_args* a, cudaStream_t st) {
   p.chain_taps = g_pix_chain_taps < 1 ? 1 : g_pix_chain_taps;
   if (p.chain_taps > stages - 1) p.chain_taps = stages - 1;   // a chain holds its stages until its last product is issued
   if (p.chain_taps > taps) p.chain_taps = taps;
+  p.gate_at = g_pix_gate_at;
   p.box_bytes = (unsigned)(convpix::PIX_BYTES * a->w * hr * imgs);
   p.gated = a->gated ? 1 : 0;
   p.bias1 = a->bias1; p.n1 = a->n1; p.relu1 = a->relu1;

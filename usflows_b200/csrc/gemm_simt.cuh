@@ -113,8 +113,78 @@ gemm_simt_kernel(const float* __restrict__ A, const float* __restrict__ A_lo, lo
   }
 }
 
+// Narrow problems (N, K <= 16: the 16 x 16 1x1-convolution affine layers of the MNIST image flow, transforms.py:904-962,
+// over N*H*W channels-last rows): HBM-bound -- 64 B in, 64 B out per row -- and the 64 x 64 tiles above move them at
+// 1 TB/s.  Here four threads share a row: each keeps its 4 x 16 slice of the weight in registers for the whole grid-stride
+// loop, reads the row (the four reads of a row coalesce) and writes one 16-byte quarter of the output row, so a warp stores
+// 512 contiguous bytes.  Same summation order over k as the tiled kernel.
+constexpr int NR_K = 16;
+__global__ void __launch_bounds__(256)
+gemm_rows_narrow_kernel(const float* __restrict__ A, const float* __restrict__ A_lo, long long lda,
+                        const float* __restrict__ W, const float* __restrict__ W_lo, long long ldw,
+                        long long M, int N, int K, int vec_a, Epilogue ep) {
+  const int q = threadIdx.x & 3;
+  float w[4][NR_K];
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int k = 0; k < NR_K; ++k) {
+      const int n = 4 * q + j;
+      float v = 0.f;
+      if (n < N && k < K) {
+        v = W[(long long)n * ldw + k];
+        if (W_lo) v += W_lo[(long long)n * ldw + k];
+      }
+      w[j][k] = v;
+    }
+  const long long stride = (long long)gridDim.x * (blockDim.x >> 2);
+  for (long long r = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 2; r < M; r += stride) {
+    float a[NR_K];
+    const float* ar = A + r * lda;
+    if (vec_a) {                          // K % 4 == 0, 16-byte aligned rows
+#pragma unroll
+      for (int k = 0; k < NR_K; k += 4) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (k < K) {
+          v = *reinterpret_cast<const float4*>(ar + k);
+          if (A_lo) {
+            const float4 l = *reinterpret_cast<const float4*>(A_lo + r * lda + k);
+            v.x += l.x; v.y += l.y; v.z += l.z; v.w += l.w;
+          }
+        }
+        a[k] = v.x; a[k + 1] = v.y; a[k + 2] = v.z; a[k + 3] = v.w;
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < NR_K; ++k) {
+        float v = 0.f;
+        if (k < K) {
+          v = ar[k];
+          if (A_lo) v += A_lo[r * lda + k];
+        }
+        a[k] = v;
+      }
+    }
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < NR_K; ++k)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[j] = fmaf(a[k], w[j][k], acc[j]);
+    if (4 * q < N) epi_row_chunk<4>(ep, acc, r, 4 * q, N);
+  }
+}
+
 inline int launch_gemm_simt(const usf_linear_args* a, const Epilogue& ep, cudaStream_t st) {
   if (a->M == 0 || a->N == 0) return USF_OK;
+  if (!a->trans_w && a->N <= 16 && a->K <= NR_K && a->M >= 4096) {
+    const bool vec_a = a->K % 4 == 0 && a->lda % 4 == 0 && aligned16(a->a) && (!a->a_lo || aligned16(a->a_lo));
+    const long long blocks = (a->M * 4 + 255) / 256;
+    const int grid = (int)(blocks < (long long)num_sms() * 8 ? blocks : (long long)num_sms() * 8);
+    gemm_rows_narrow_kernel<<<grid, 256, 0, st>>>((const float*)a->a, (const float*)a->a_lo, a->lda, (const float*)a->w,
+                                                  (const float*)a->w_lo, a->ldw, a->M, a->N, a->K, vec_a ? 1 : 0, ep);
+    USF_CUDA_OK(cudaGetLastError());
+    return USF_OK;
+  }
   USF_REQUIRE((a->M + SG_BM - 1) / SG_BM <= 0x7fffffffLL && (a->N + SG_BN - 1) / SG_BN <= 65535,
               "SIMT engine: problem too large for one launch");
   dim3 grid((unsigned)((a->M + SG_BM - 1) / SG_BM), (a->N + SG_BN - 1) / SG_BN);
