@@ -97,17 +97,6 @@ __device__ __forceinline__ void umma_f16_scale11(uint64_t da, uint64_t db, uint3
       ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(1u), "r"(z)
       : "memory");
 }
-// one thread of the (converged) warp: elect.sync tells the compiler the branch is taken by exactly one lane, so the
-// uniform-datapath instructions inside (tcgen05.mma, tcgen05.commit, TMA) need no per-lane ELECT / BRA.U.ANY loop
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "elect.sync _|p, 0xffffffff;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(pred));
-  return pred != 0;
-}
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void st_shared_u4(uint32_t addr, uint4 v) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
@@ -169,7 +158,7 @@ __device__ __forceinline__ void layer_norm32(float (&v)[32], int n, const float*
   const float rstd = 1.f / sqrtf(sq / (float)n + eps);
 #pragma unroll
   for (int j = 0; j < 32; ++j)
-    if (j < n) v[j] = (v[j] - mean) * rstd * __ldg(gamma + j) + __ldg(beta + j);
+    if (j < n) v[j] = (v[j] - mean) * rstd * gamma[j] + beta[j];
 }
 
 // ---- per-warp staging block (32 rows x 128 B of shared memory, 16-byte chunks XOR-swizzled by row & 7 -- the operand
@@ -199,14 +188,12 @@ __device__ __forceinline__ void stage_store_rows(uint32_t stage, int lane, uint8
   }
   __syncwarp();
 }
-// global rows -> block (zeros outside)
-__device__ __forceinline__ void stage_load_rows(uint32_t stage, int lane, const uint8_t* g, long long pitch, int nch, int nrows) {
+// rows fetched in the coalesced pattern of stage_store_rows (row 4i + lane / 8, chunk lane % 8) -> block
+__device__ __forceinline__ void stage_put_rows(uint32_t stage, int lane, const uint4 (&v)[8]) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int row = 4 * i + (lane >> 3), ch = lane & 7;
-    uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (row < nrows && ch < nch) v = *reinterpret_cast<const uint4*>(g + row * pitch + ch * 16);
-    st_shared_u4(stage + (uint32_t)row * 128u + ((uint32_t)(ch ^ (row & 7)) << 4), v);
+    st_shared_u4(stage + (uint32_t)row * 128u + ((uint32_t)(ch ^ (row & 7)) << 4), v[i]);
   }
   __syncwarp();
 }
@@ -272,6 +259,9 @@ conv_pix_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
   const uint32_t acc2full_bar = bar_base + 8u * (2 * MAX_STAGES + 2 * NBUF + 2);
   const uint32_t tmem_slot = bar_base + 8u * (2 * MAX_STAGES + 2 * NBUF + 3);
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+  // per-channel constants of the epilogue (bias1[32] | bias2[64] | gamma[32] | beta[32]): broadcast shared-memory reads
+  // instead of ~200 uniform global loads per pixel thread and tile
+  float* s_par = reinterpret_cast<float*>(smem_raw + (bar_base + 256u - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_chains = (p.taps + p.chain_taps - 1) / p.chain_taps;
@@ -295,13 +285,23 @@ conv_pix_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  if (threadIdx.x >= 128 && threadIdx.x < 128 + 160) {
+    const int i = threadIdx.x - 128;
+    float v = 0.f;
+    if (i < 32) v = p.bias1[i];
+    else if (i < 96) v = p.gated ? p.bias2[i - 32] : 0.f;
+    else if (i < 128) v = (p.gamma && i - 96 < p.n1) ? p.gamma[i - 96] : 0.f;
+    else v = (p.beta && i - 128 < p.n1) ? p.beta[i - 128] : 0.f;
+    s_par[i] = v;
+  }
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   // What the measurements decided (tools/conv_probe.py, profiles/r02_conv_pix.md):
-  //  * no setmaxnreg: at 56 registers the issuer re-loaded its descriptors from local memory in front of every tcgen05.mma;
+  //  * setmaxnreg 96 / 200, not the 56 / 224 of the flat kernels: at 56 registers the issuer re-loaded its descriptors
+  //    from local memory in front of every tcgen05.mma;
   //  * the issuing threads are chosen with elect.sync, not `lane == 0`: the compiler then emits tcgen05.mma / TMA back to
   //    back instead of wrapping each one in an ELECT / BRA.U.ANY loop that waits for the instruction's scoreboard;
   //  * ONE thread per role runs the barrier protocol (32 lanes polling an mbarrier serialise), and a wait first tries the
@@ -309,6 +309,7 @@ conv_pix_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
   //  * the issuer's own instruction stream (~20 instructions per MMA of 16-44 tensor cycles at N = 32) is what bounds the
   //    kernel, so each of the two 128-row MMA tiles of a CTA tile has its own issuer warp.
   if (warp < FIRST_EPI_WARP) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(96));       // 128 x 96 + 256 x 200 = 63 488 registers
     if (warp == 0) {
       // ===================== TMA producer: the weights once, then one box per (tile, tap) =====================
       if (elect_one()) {
@@ -407,6 +408,7 @@ conv_pix_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     }
   } else {
     // ===================== epilogue warps: one thread per pixel of the tile =====================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(200));
     const int q = warp & 3, mt = (warp - FIRST_EPI_WARP) >> 2;
     const int wrow0 = mt * BLOCK_M + q * 32;                          // first tile row of this warp
     const int t = wrow0 + lane;                                       // row of the CTA tile
@@ -421,6 +423,19 @@ conv_pix_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
       int wrows = tl.nvalid - wrow0;                                  // valid rows of this warp's block
       wrows = no_traffic ? 0 : wrows < 0 ? 0 : wrows > 32 ? 32 : wrows;
       const long long r = tl.row0 + t, wr = tl.row0 + wrow0;
+      // the rows this tile's epilogue READS (gated: the residual stream; last convolution: x) are fetched now, 512 contiguous
+      // bytes per instruction, so their latency hides behind the waits for the accumulators
+      uint4 pre[8];
+      const uint8_t* pre_g = p.gated ? reinterpret_cast<const uint8_t*>(p.out_f32 + wr * p.ld_f32)
+                                     : x_vec ? reinterpret_cast<const uint8_t*>(p.x + wr * p.ldx) : nullptr;
+      const long long pre_pitch = p.gated ? p.ld_f32 * 4 : p.ldx * 4;
+      const int pre_nch = p.gated ? 8 : (p.c_x >> 2);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int row = 4 * i + (lane >> 3), ch = lane & 7;
+        pre[i] = make_uint4(0u, 0u, 0u, 0u);
+        if (pre_g && row < wrows && ch < pre_nch) pre[i] = *reinterpret_cast<const uint4*>(pre_g + row * pre_pitch + ch * 16);
+      }
       float m[32];
       for (int c = 0; c < n_chains; ++c) {
         if (lane == 0) mbar_wait(tfull_bar(acc), acc_phase);
@@ -443,7 +458,7 @@ conv_pix_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
       }
 #pragma unroll
       for (int j = 0; j < 32; j += 4) {
-        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias1 + j));
+        const float4 b = *reinterpret_cast<const float4*>(s_par + j);
         m[j] += b.x; m[j + 1] += b.y; m[j + 2] += b.z; m[j + 3] += b.w;
       }
       if (!p.gated) {
@@ -451,13 +466,13 @@ conv_pix_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
 #pragma unroll
           for (int j = 0; j < 32; ++j) m[j] = fmaxf(m[j], 0.f);
         }
-        if (p.gamma) layer_norm32(m, p.n1, p.gamma, p.beta, p.eps);
+        if (p.gamma) layer_norm32(m, p.n1, s_par + 96, s_par + 128, p.eps);
         if (p.x) {                                                    // x[r, c] += sign * (1 - mask)[pixel, c] * v[c]
           const int pix = (tl.h0 * p.W + t) % p.HW;
           const float* g = p.inv_mask + (long long)pix * p.c_x;
           if (x_vec) {
             uint8_t* xg = reinterpret_cast<uint8_t*>(p.x + wr * p.ldx);
-            stage_load_rows(stage, lane, xg, p.ldx * 4, p.c_x >> 2, wrows);
+            stage_put_rows(stage, lane, pre);
             float xr[32];
             stage_read_f32_row(stage, lane, xr);
             if (valid) {
@@ -489,7 +504,7 @@ conv_pix_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         // ended with a __syncwarp, its gate contraction has been consumed)
         uint8_t* yg = reinterpret_cast<uint8_t*>(p.out_f32 + wr * p.ld_f32);
         float y[32];
-        stage_load_rows(stage, lane, yg, p.ld_f32 * 4, 8, wrows);
+        stage_put_rows(stage, lane, pre);
         stage_read_f32_row(stage, lane, y);
         __syncwarp();
         // u = relu(conv + b) -> this warp's rows of the operand tile of the 1 x 1 convolution (= its staging block)
@@ -510,18 +525,18 @@ conv_pix_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
           tmem_ld32(lane_addr + ACC2_COL + mt * 64 + 32, g);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) m[j] = __fdividef(1.f, 1.f + __expf(-(g[j] + __ldg(p.bias2 + 32 + j))));
+          for (int j = 0; j < 32; ++j) m[j] = __fdividef(1.f, 1.f + __expf(-(g[j] + s_par[64 + j])));
           tmem_ld32(lane_addr + ACC2_COL + mt * 64, g);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) y[j] = y[j] + (g[j] + __ldg(p.bias2 + j)) * m[j];
+          for (int j = 0; j < 32; ++j) y[j] = y[j] + (g[j] + s_par[32 + j]) * m[j];
         }
         tcgen05_fence_before();
         if (p.post_relu) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) y[j] = fmaxf(y[j], 0.f);
         }
-        if (p.gamma) layer_norm32(y, p.n1, p.gamma, p.beta, p.eps);
+        if (p.gamma) layer_norm32(y, p.n1, s_par + 96, s_par + 128, p.eps);
         // (the gate contraction has completed -- acc2full -- so the tensor core is done reading the staging block)
         stage_write_f32_row(stage, lane, y);
         stage_store_rows(stage, lane, yg, p.ld_f32 * 4, 8, wrows);
@@ -590,14 +605,14 @@ inline bool conv_pix_geometry(int H, int W, int* imgs, int* hr, int* tiles_per_i
 }
 // pipeline stages that fit next to the resident weights (0: the shape does not fit)
 inline int conv_pix_stages(int taps, int gated) {
-  const long long fixed = (long long)taps * convpix::W1_TAP + (gated ? convpix::W2_BYTES : 0) + convpix::A_STAGE + 1024 + 256;
+  const long long fixed = (long long)taps * convpix::W1_TAP + (gated ? convpix::W2_BYTES : 0) + convpix::A_STAGE + 1024 + 1024;
   long long s = (227 * 1024 - fixed) / convpix::A_STAGE;
   if (s > convpix::MAX_STAGES) s = convpix::MAX_STAGES;
   return s >= 2 ? (int)s : 0;
 }
 inline size_t conv_pix_smem_bytes(int taps, int gated) {
   return (size_t)conv_pix_stages(taps, gated) * convpix::A_STAGE + (size_t)taps * convpix::W1_TAP +
-         (gated ? convpix::W2_BYTES : 0) + convpix::A_STAGE + 1024 + 256;
+         (gated ? convpix::W2_BYTES : 0) + convpix::A_STAGE + 1024 + 1024;
 }
 
 extern int g_pix_gate_at;               // chains of the next tile issued in front of a tile's gate contraction

@@ -96,6 +96,17 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 #endif
 }
 
+// one thread of the (converged) warp: elect.sync tells the compiler the branch is taken by exactly one lane, so the
+// uniform-datapath instructions inside (tcgen05.mma, tcgen05.commit, TMA) need no per-lane ELECT / BRA.U.ANY loop
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }

@@ -971,7 +971,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_NON_EPI));
     if (warp == 0) {
       // ===================== TMA producer (both CTAs) =====================
-      if (lane == 0) {
+      // (the issuing thread of each role is picked with elect.sync: the compiler then emits TMA / tcgen05.mma back to back
+      //  instead of wrapping each one in an ELECT / BRA.U.ANY loop that waits on the instruction's scoreboard; and ONE
+      //  thread runs the barrier protocol -- 32 lanes polling an mbarrier serialise; see csrc/conv_pix.cuh)
+      if (elect_one()) {
         int stage = 0;
         uint32_t phase = 0;
         for (long long tile = cluster_id_x(); tile < n_tiles; tile += num_clusters_x()) {
@@ -1001,14 +1004,14 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
           }
         }
       }
-    } else if (warp == 1 && rank == 0) {
+    } else if (warp == 1 && rank == 0 && elect_one()) {
       // ===================== MMA issuer (leader CTA only) =====================
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
       int dbg_chain = 0;
-      unsigned long long* dbg_mma = (cluster_id_x() == 0 && lane == 0) ? dbg_buf : nullptr;
+      unsigned long long* dbg_mma = cluster_id_x() == 0 ? dbg_buf : nullptr;
       for (long long tile = cluster_id_x(); tile < n_tiles; tile += num_clusters_x()) {
         const TileCoord tc = decode_tile<SPLITK>(tile, n_blocks, split_k, k_slabs, split_per);
         const uint32_t idesc = C::IDESC_NO_N | ((uint32_t)(tile_width(tc.n_blk * BLOCK_N) >> 3) << 17);
@@ -1032,7 +1035,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
             for (int ks = ks0; ks < ks1; ++ks) {
               mbar_wait(full_bar(st), ph);
               tcgen05_fence_after();
-              if (lane == 0) {
+              {
                 const uint32_t sa = smem_base + st * C::STAGE_BYTES;
                 const uint32_t sb = sa + C::NPLANES * C::A_TILE;
                 const uint64_t da_hi = make_smem_desc_s<SLAB_BYTES>(sa), db_hi = make_smem_desc_s<SLAB_BYTES>(sb);
@@ -1047,12 +1050,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
                   }
                 }
               }
-              __syncwarp();
               if (++st == C::STAGES) { st = 0; ph ^= 1; }
             }
             if (dbg_mma && dbg_chain < DBG_CHAINS) dbg_mma[dbg_chain * 8 + 1] = clock64();
             for (int ks = ks0; ks < ks1; ++ks) {
-              if (lane == 0) {
+              {
                 const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
                 const uint32_t sb = sa + C::NPLANES * C::A_TILE;
                 const uint64_t da_hi = make_smem_desc_s<SLAB_BYTES>(sa), db_hi = make_smem_desc_s<SLAB_BYTES>(sb);
@@ -1068,7 +1070,6 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
                 umma_commit_pair(empty_bar(stage));                  // slot free in both CTAs once these MMAs retire
                 if (ks == ks1 - 1) umma_commit_pair(tfull_bar(acc));  // accumulation chain complete (both CTAs)
               }
-              __syncwarp();
               if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
             }
           } else {
@@ -1076,7 +1077,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
               mbar_wait(full_bar(stage), phase);
               tcgen05_fence_after();
               if (dbg_mma && dbg_chain < DBG_CHAINS) dbg_mma[dbg_chain * 8 + 1] = clock64();
-              if (lane == 0) {
+              {
                 const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
                 const uint32_t sb = sa + C::NPLANES * C::A_TILE;
                 const uint64_t da_hi = make_smem_desc_s<SLAB_BYTES>(sa), db_hi = make_smem_desc_s<SLAB_BYTES>(sb);
@@ -1102,7 +1103,6 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
                 umma_commit_pair(empty_bar(stage));                  // slot free in both CTAs once these MMAs retire
                 if (ks == ks1 - 1) umma_commit_pair(tfull_bar(acc));  // accumulation chain complete (both CTAs)
               }
-              __syncwarp();
               if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
             }
           }
