@@ -159,7 +159,7 @@ def test_overflow_flag_and_chain_length():
         o = torch.empty(rows, 32, device="cuda")
         ops.conv2d_pix(a16, n, H, W, 3, 1, w16, b32, 32, out_f32=o)
         outs.append(o.cpu())
-    _lib.check(_lib.load().usf_set_pix_chain_taps(3))
+    _lib.check(_lib.load().usf_set_pix_chain_taps(0))
     for o in outs[1:]:
         assert rel_err(o, outs[0]) <= 2e-6
     # the gated block with several tiles per CTA (the gate contraction of tile i is issued among the chains of tile i + 1)
@@ -173,7 +173,7 @@ def test_overflow_flag_and_chain_length():
         yy = y0.clone()
         ops.conv2d_pix(a2, n2, H, W, 3, 1, w16, b32, 32, gated=True, post_relu=True, w2=w16_2, bias2=b32_2, out_f32=yy)
         ys.append(yy.cpu())
-    _lib.check(_lib.load().usf_set_pix_chain_taps(3))
+    _lib.check(_lib.load().usf_set_pix_chain_taps(0))
     for yy in ys[1:]:
         assert rel_err(yy, ys[0]) <= 2e-6
     flag = torch.zeros(1, dtype=torch.int32, device="cuda")

@@ -69,7 +69,7 @@ for taps in (1, 2, 3):
     us = timed(lambda: ops.conv2d_pix(a16, n, H, W, k, 1, w16, b32, 32, gated=True, post_relu=True, w2=w16_2, bias2=b64,
                                       gamma=gamma, beta=beta, eps=1e-5, out_f32=y, out16=b16, relu_planes=True))
     print(f"conv2d_pix gated block (conv 3x3 + conv 1x1 + gate + ReLU + LayerNorm), {taps} taps per chain: {us:.1f} us")
-_lib.load().usf_set_pix_chain_taps(2)
+_lib.load().usf_set_pix_chain_taps(0)
 us = timed(lambda: ops.conv2d_pix(a16, n, H, W, k, 1, w16, b32, 16, x=x16c, inv_mask=mask, sign=1.0))
 print(f"conv2d_pix last (coupling update of 16 channels): {us:.1f} us")
 for nn in (5 * 148, 5 * 148 * 4):
@@ -111,4 +111,4 @@ for ga in (0, 1, 2, 3):
         line.append(f"{taps} taps/chain {us:.1f} us")
     print(f"conv2d_pix gated, gate contraction behind {ga} chains of the next tile: " + ", ".join(line))
 _lib.load().usf_set_pix_gate_at(0)
-_lib.load().usf_set_pix_chain_taps(3)
+_lib.load().usf_set_pix_chain_taps(0)

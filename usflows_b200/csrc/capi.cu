@@ -431,7 +431,7 @@ int usf_conv2d_pix(const usf_conv_pix_args* a, void* stream) {
 }
 
 int usf_set_pix_chain_taps(int32_t taps) {
-  USF_REQUIRE(taps >= 1, "at least one tap per chain");
+  USF_REQUIRE(taps >= 0, "taps per chain (0 = default)");
   g_pix_chain_taps = taps;
   return USF_OK;
 }

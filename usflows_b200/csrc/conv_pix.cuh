@@ -616,7 +616,7 @@ inline size_t conv_pix_smem_bytes(int taps, int gated) {
 }
 
 extern int g_pix_gate_at;               // chains of the next tile issued in front of a tile's gate contraction
-extern int g_pix_chain_taps;            // taps per accumulation chain (3 = 96 K-elements; 2 = the flat engine's chain length)
+extern int g_pix_chain_taps;            // taps per accumulation chain (0 = auto; 3 = 96 K-elements; 2 = the flat engine's chain length)
 int launch_conv_pix(const usf_conv_pix_args* a, cudaStream_t st);
 int launch_pix_encode(const float* x, long long ldx, long long rows, int c, int hw, const float* mask, int relu, void* out16,
                       int* overflow_flag, cudaStream_t st);

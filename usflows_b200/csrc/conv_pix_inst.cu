@@ -3,7 +3,7 @@
 
 namespace usf {
 
-int g_pix_chain_taps = 3;
+int g_pix_chain_taps = 0;              // 0 = auto: 3 for the gated block, 2 for a plain convolution (measured, tools/conv_probe.py)
 int g_pix_gate_at = 0;
 extern int g_dbg_flags;
 
@@ -42,7 +42,7 @@ int launch_conv_pix(const usf_conv_pix_args* a, cudaStream_t st) {
   p.imgs = imgs; p.hr = hr; p.tiles_per_img = tpi;
   p.n_tiles = tpi == 1 ? (a->n_images + imgs - 1) / imgs : a->n_images * (long long)tpi;
   p.stages = stages;
-  p.chain_taps = g_pix_chain_taps < 1 ? 1 : g_pix_chain_taps;
+  p.chain_taps = g_pix_chain_taps < 1 ? (a->gated ? 3 : 2) : g_pix_chain_taps;
   if (p.chain_taps > stages - 1) p.chain_taps = stages - 1;   // a chain holds its stages until its last product is issued
   if (p.chain_taps > taps) p.chain_taps = taps;
   p.gate_at = g_pix_gate_at;

@@ -115,30 +115,28 @@ gemm_simt_kernel(const float* __restrict__ A, const float* __restrict__ A_lo, lo
 
 // Narrow problems (N, K <= 16: the 16 x 16 1x1-convolution affine layers of the MNIST image flow, transforms.py:904-962,
 // over N*H*W channels-last rows): HBM-bound -- 64 B in, 64 B out per row -- and the 64 x 64 tiles above move them at
-// 1 TB/s.  Here four threads share a row: each keeps its 4 x 16 slice of the weight in registers for the whole grid-stride
-// loop, reads the row (the four reads of a row coalesce) and writes one 16-byte quarter of the output row, so a warp stores
-// 512 contiguous bytes.  Same summation order over k as the tiled kernel.
+// 1 TB/s.  Here a thread owns a row: the zero-padded 16 x 16 weight sits in shared memory and is read as broadcast 128-bit
+// loads (every lane the same address), the row and its 16 sums stay in registers (~60 registers: full occupancy, 2 KB of
+// distinct loads in flight per warp -- a first version with four threads per row and the weight in registers kept only
+// 512 B per warp in flight and stopped at 1.5 TB/s).  Same summation order over k as the tiled kernel.
 constexpr int NR_K = 16;
 __global__ void __launch_bounds__(256)
 gemm_rows_narrow_kernel(const float* __restrict__ A, const float* __restrict__ A_lo, long long lda,
                         const float* __restrict__ W, const float* __restrict__ W_lo, long long ldw,
                         long long M, int N, int K, int vec_a, Epilogue ep) {
-  const int q = threadIdx.x & 3;
-  float w[4][NR_K];
-#pragma unroll
-  for (int j = 0; j < 4; ++j)
-#pragma unroll
-    for (int k = 0; k < NR_K; ++k) {
-      const int n = 4 * q + j;
-      float v = 0.f;
-      if (n < N && k < K) {
-        v = W[(long long)n * ldw + k];
-        if (W_lo) v += W_lo[(long long)n * ldw + k];
-      }
-      w[j][k] = v;
+  __shared__ __align__(16) float sW[NR_K][NR_K];
+  {
+    const int n = threadIdx.x >> 4, k = threadIdx.x & 15;
+    float v = 0.f;
+    if (n < N && k < K) {
+      v = W[(long long)n * ldw + k];
+      if (W_lo) v += W_lo[(long long)n * ldw + k];
     }
-  const long long stride = (long long)gridDim.x * (blockDim.x >> 2);
-  for (long long r = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 2; r < M; r += stride) {
+    sW[n][k] = v;
+  }
+  __syncthreads();
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < M; r += stride) {
     float a[NR_K];
     const float* ar = A + r * lda;
     if (vec_a) {                          // K % 4 == 0, 16-byte aligned rows
@@ -165,12 +163,21 @@ gemm_rows_narrow_kernel(const float* __restrict__ A, const float* __restrict__ A
         a[k] = v;
       }
     }
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int k = 0; k < NR_K; ++k)
+    for (int j = 0; j < NR_K; j += 4) {
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int j = 0; j < 4; ++j) acc[j] = fmaf(a[k], w[j][k], acc[j]);
-    if (4 * q < N) epi_row_chunk<4>(ep, acc, r, 4 * q, N);
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int k = 0; k < NR_K; k += 4) {
+          const float4 w = *reinterpret_cast<const float4*>(&sW[j + i][k]);
+          acc[i] = fmaf(a[k], w.x, acc[i]);
+          acc[i] = fmaf(a[k + 1], w.y, acc[i]);
+          acc[i] = fmaf(a[k + 2], w.z, acc[i]);
+          acc[i] = fmaf(a[k + 3], w.w, acc[i]);
+        }
+      if (j < N) epi_row_chunk<4>(ep, acc, r, j, N);
+    }
   }
 }
 
@@ -178,7 +185,7 @@ inline int launch_gemm_simt(const usf_linear_args* a, const Epilogue& ep, cudaSt
   if (a->M == 0 || a->N == 0) return USF_OK;
   if (!a->trans_w && a->N <= 16 && a->K <= NR_K && a->M >= 4096) {
     const bool vec_a = a->K % 4 == 0 && a->lda % 4 == 0 && aligned16(a->a) && (!a->a_lo || aligned16(a->a_lo));
-    const long long blocks = (a->M * 4 + 255) / 256;
+    const long long blocks = (a->M + 255) / 256;
     const int grid = (int)(blocks < (long long)num_sms() * 8 ? blocks : (long long)num_sms() * 8);
     gemm_rows_narrow_kernel<<<grid, 256, 0, st>>>((const float*)a->a, (const float*)a->a_lo, a->lda, (const float*)a->w,
                                                   (const float*)a->w_lo, a->ldw, a->M, a->N, a->K, vec_a ? 1 : 0, ep);
