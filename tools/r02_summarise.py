@@ -26,14 +26,16 @@ for src, dst in (("bench", "r02_bench_c2.json"), ("bench_ref", "r02_bench_c2_ref
     if os.path.exists(p) and os.path.getsize(p):
         shutil.copy(p, os.path.join(P, dst))
         print("copied", dst)
-for src, dst in (("small_batch.log", "r02_small_batch.log"), ("train_breakdown.log", "r02_train_breakdown.log")):
+for src, dst in (("small_batch.log", "r02_small_batch.log"), ("train_breakdown.log", "r02_train_breakdown.log"),
+                 ("conv_probe.log", "r02_conv_pix_probe.log")):
     p = os.path.join(G, f"{T}_{src}")
     if os.path.exists(p):
         shutil.copy(p, os.path.join(P, dst))
 
 # launch lists
 for src, dst, title in (("launches_c2.csv", "r02_launches_c2.md", "C2 log_prob: the two timed steps (cudaProfilerStart/Stop range), fp32 mode, through the whole-stack C entry"),
-                        ("launches_train.csv", "r02_launches_train.md", "C3 training step (8192 rows, hand-written pass + SophiaG), one step launch by launch")):
+                        ("launches_train.csv", "r02_launches_train.md", "C3 training step (8192 rows, hand-written pass + SophiaG), one step launch by launch"),
+                        ("launches_mnist_img.csv", "r02_launches_mnist_img.md", "image-shaped flow, the reference's live MNIST configuration ([16,7,7], B = 15, ConvNet2D 32 ch x 3 gated 3x3 blocks), ONE log_prob step over 16 384 images (two chunks), the conditioners on pixel planes (usf_conv2d_pix)")):
     p = os.path.join(G, f"{T}_{src}")
     if os.path.exists(p):
         body = run([sys.executable, os.path.join(ROOT, "tools", "ncu_summary.py"), "launches", p])
@@ -59,7 +61,9 @@ KEYS = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "la
 
 for src, dst, title in (("full_gemm_raw.csv", "r02_full_gemm_c2_fp32.md", "the 21 contraction launches of ONE C2 log_prob step, fp32 mode (fp16-split x3)"),
                         ("full_gemm_bf16_raw.csv", "r02_full_gemm_c2_bf16.md", "the 21 contraction launches of ONE C2 log_prob step, bf16 mode (TMA store path for bf16 / fp32 planes)"),
-                        ("full_train_raw.csv", "r02_full_train_kernels.md", "glue / weight-side kernels of the training step")):
+                        ("full_train_raw.csv", "r02_full_train_kernels.md", "glue / weight-side kernels of the training step"),
+                        ("pix_plain_raw.csv", "r02_full_conv_pix_plain.md", "usf_conv2d_pix, plain 3x3 convolution 32 -> 32 channels over 802 816 pixels (fp32 rows + pixel planes out), tools/pix_ncu.py"),
+                        ("pix_gated_raw.csv", "r02_full_conv_pix_gated.md", "usf_conv2d_pix, GatedConv block (3x3 conv + 1x1 conv + gate + ReLU + LayerNorm) over 802 816 pixels, tools/pix_ncu.py")):
     path = os.path.join(G, f"{T}_{src}")
     if not os.path.exists(path):
         continue
