@@ -58,14 +58,32 @@ def main():
     spec3 = dict(in_dims=[16, 7, 7], coupling_blocks=1, conditioner="convnet2d", c_hidden=32, num_layers=1, kernel_size=3,
                  gating=True, normalize_layers=True, affine_conjugation=True, lu_transform=1, householder=0, base="radial",
                  p=1, norm="lognormal")
-    for tag, sp in (("convnet + radial", spec2), ("image 16x7x7", spec3)):
+    from usflows_b200 import image_engine
+    for tag, sp, pix in (("convnet + radial", spec2, True), ("image 16x7x7, pixel planes (usf_conv2d_pix)", spec3, True),
+                         ("image 16x7x7, implicit-GEMM route (usf_conv2d_rows)", spec3, False)):
         p = O.random_params(sp, 9)
         xs = torch.rand(40, *sp["in_dims"], generator=g)
-        f = build_flow(sp, p, device="cuda:0", precision="fp32")
-        e = rel_err(f.log_prob(xs.cuda()), O.flow_log_prob(xs, sp, p))
-        f.sample([4])
+        image_engine.PIX_CONV = pix
+        try:
+            f = build_flow(sp, p, device="cuda:0", precision="fp32")
+            e = rel_err(f.log_prob(xs.cuda()), O.flow_log_prob(xs, sp, p))
+            f.sample([4])
+        finally:
+            image_engine.PIX_CONV = True
         print(f"[{tag}] log_prob err {e:.2e}", flush=True)
         assert e < 2e-5
+    # usf_conv2d_pix on an image cut into row tiles (H*W > 256), 5 x 5 taps, and the narrow SIMT path
+    from usflows_b200 import ops
+    from usflows_b200.ops import Act
+    a16 = torch.zeros(2 * 20 * 18, 64, dtype=torch.float16, device="cuda")
+    ops.pix_encode(torch.rand(2 * 20 * 18, 24, generator=g).cuda(), 20 * 18, a16)
+    w16 = image_engine._pix_weight((torch.randn(32, 25 * 24, generator=g) / 25).cuda(), 25, 24, 32, None)
+    o32 = torch.empty(2 * 20 * 18, 32, device="cuda")
+    ops.conv2d_pix(a16, 2, 20, 18, 5, 1, w16, torch.zeros(32, device="cuda"), 32, out_f32=o32, out16=torch.empty_like(a16))
+    ops.linear(0, Act(5000, 16, f32=torch.rand(5000, 16, generator=g).cuda()), torch.rand(16, 16, generator=g).cuda(), None, 16, 16,
+               out=Act(5000, 16, f32=torch.empty(5000, 16, device="cuda")))
+    torch.cuda.synchronize()
+    assert torch.isfinite(o32).all()
     # training step (autograd contractions incl. transposes) on a small flow
     from usflows_b200 import training
     import usflows_b200 as U
