@@ -106,3 +106,25 @@ def test_plan_entry_points_reject_bad_input_without_gpu():
     assert lib.usf_plan_finalize(h) == -1                       # no steps
     assert lib.usf_flow_logprob(h, None, 0, 0, None, None, None) == -1
     assert lib.usf_plan_destroy(h) == 0
+
+
+def test_conv_pix_args_layout_matches_header():
+    from usflows_b200 import _lib
+    with open(os.path.join(ROOT, "include", "usflows_b200.h")) as f:
+        text = f.read()
+    body = re.search(r"typedef struct usf_conv_pix_args \{(.*?)\} usf_conv_pix_args;", text, flags=re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    fields = [n for decl in body.split(";") for n in re.findall(r"([A-Za-z_0-9]+)\s*(?:,|$)", decl.strip().replace("\n", " "))
+              if n not in ("int32_t", "int64_t", "float", "const", "void")]
+    assert fields == [f[0] for f in _lib.ConvPixArgs._fields_], fields
+    assert ctypes.sizeof(_lib.ConvPixArgs) == 2 * 8 + 4 * 4 + 2 * 8 + 4 * 4 + 4 * 8 + 2 * 4 + 3 * 8 + 2 * 4 + 4 * 8
+
+
+def test_conv_pix_entry_points_reject_bad_input_without_gpu():
+    from usflows_b200 import _lib
+    lib = _lib.load()
+    assert lib.usf_conv2d_pix(None, None) == -1 and b"null args" in lib.usf_last_error()
+    a = _lib.ConvPixArgs()
+    assert lib.usf_conv2d_pix(ctypes.byref(a), None) == -1                  # null operands
+    assert lib.usf_pix_encode(None, 0, 0, 16, 49, None, 0, None, None, None) == -1
+    assert lib.usf_set_pix_chain_taps(0) == 0 and lib.usf_set_pix_gate_at(0) == 0
