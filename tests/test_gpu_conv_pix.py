@@ -198,3 +198,22 @@ def test_pixel_plane_route_equals_the_implicit_gemm_route_on_flows():
         assert rel_err(lp, arr["lp32"]) <= 1e-5 and rel_err(lp_rows, arr["lp32"]) <= 1e-5
         assert rel_err(lp, lp_rows) <= 3e-6 and rel_err(z, z_rows) <= 3e-6
         assert rel_err(flow._forward(z), x) <= 1e-4
+
+
+def test_image_flow_outside_the_fp16_range_falls_back_per_chunk():
+    """Pixel planes are fp16 split planes: a chunk whose activations leave the fp16 range raises the device flag and is re-run
+    by the tf32-split program (usf_conv2d_rows route), as in the flat path; the other chunks keep the fast route."""
+    from usflows_b200 import image_engine
+    spec, params, arr = load_case("img_mnist_16x7x7")
+    x = arr["x"].cuda().clone()
+    x[5] *= 1e6                                            # one image of the second chunk leaves the range
+    old = image_engine.IMAGE_CHUNK_ROWS
+    image_engine.IMAGE_CHUNK_ROWS = 49 * 4
+    try:
+        z = build_flow(spec, params, precision="fp32").backward(x)
+        z_ref = build_flow(spec, params, precision="fp32_tf32").backward(x)
+    finally:
+        image_engine.IMAGE_CHUNK_ROWS = old
+    assert bool(torch.isfinite(z).all())
+    assert torch.equal(z[4:8], z_ref[4:8])                 # the flagged chunk: exactly the fallback program's result
+    assert rel_err(z[:4], z_ref[:4]) <= 3e-6 and not torch.equal(z[:4], z_ref[:4])     # the others: the fp16-split engine

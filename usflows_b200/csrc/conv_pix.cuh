@@ -145,6 +145,29 @@ __device__ __forceinline__ Tile decode_tile(const PixArgs& p, long long tile) {
 // LayerNorm over the first n channels of a register row (biased variance, as nn.LayerNorm / gate_norm_kernel)
 __device__ __forceinline__ void layer_norm32(float (&v)[32], int n, const float* __restrict__ gamma, const float* __restrict__ beta,
                                              float eps) {
+  if (n == 32) {                        // all channels (the common case): no per-element predicates, 128-bit constant loads
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) sum += v[j];
+    const float mean = sum * (1.f / 32.f);
+    float sq = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float t = v[j] - mean;
+      sq = fmaf(t, t, sq);
+    }
+    const float rstd = 1.f / sqrtf(sq * (1.f / 32.f) + eps);
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      const float4 g = *reinterpret_cast<const float4*>(gamma + j);
+      const float4 b = *reinterpret_cast<const float4*>(beta + j);
+      v[j] = (v[j] - mean) * rstd * g.x + b.x;
+      v[j + 1] = (v[j + 1] - mean) * rstd * g.y + b.y;
+      v[j + 2] = (v[j + 2] - mean) * rstd * g.z + b.z;
+      v[j + 3] = (v[j + 3] - mean) * rstd * g.w + b.w;
+    }
+    return;
+  }
   float sum = 0.f;
 #pragma unroll
   for (int j = 0; j < 32; ++j) sum += j < n ? v[j] : 0.f;
@@ -212,19 +235,23 @@ __device__ __forceinline__ void stage_read_f32_row(uint32_t stage, int lane, flo
   }
 }
 // pixel planes of a register row (hi chunks 0-3, lo' chunks 4-7); returns whether a value left the fp16 range
-__device__ __forceinline__ bool stage_write_planes_row(uint32_t stage, int lane, const float (&v)[32], bool relu, bool zero) {
+template <bool RELU>
+__device__ __forceinline__ bool stage_write_planes_row_t(uint32_t stage, int lane, const float (&v)[32]) {
   bool bad = false;
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
     float t[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) t[i] = zero ? 0.f : relu ? fmaxf(v[8 * c + i], 0.f) : v[8 * c + i];
+    for (int i = 0; i < 8; ++i) t[i] = RELU ? fmaxf(v[8 * c + i], 0.f) : v[8 * c + i];
     uint4 hi, lo;
     bad |= split8(t, hi, lo);
     stage_write_chunk(stage, lane, c, hi);
     stage_write_chunk(stage, lane, c + 4, lo);
   }
   return bad;
+}
+__device__ __forceinline__ bool stage_write_planes_row(uint32_t stage, int lane, const float (&v)[32], bool relu) {
+  return relu ? stage_write_planes_row_t<true>(stage, lane, v) : stage_write_planes_row_t<false>(stage, lane, v);
 }
 
 // descriptor of a K-major 128B-swizzled operand tile from its low word (start address >> 4 | LBO): the high word (stride
@@ -495,7 +522,7 @@ conv_pix_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
           stage_store_rows(stage, lane, reinterpret_cast<uint8_t*>(p.out_f32 + wr * p.ld_f32), p.ld_f32 * 4, p.n1 >> 2, wrows);
         }
         if (p.out16) {
-          const bool bad = stage_write_planes_row(stage, lane, m, p.relu_planes != 0, false);
+          const bool bad = stage_write_planes_row(stage, lane, m, p.relu_planes != 0);
           if (bad && valid && p.overflow_flag) *p.overflow_flag = 1;
           stage_store_rows(stage, lane, reinterpret_cast<uint8_t*>(p.out16) + wr * PIX_BYTES, PIX_BYTES, 8, wrows);
         }
@@ -508,7 +535,11 @@ conv_pix_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         stage_read_f32_row(stage, lane, y);
         __syncwarp();
         // u = relu(conv + b) -> this warp's rows of the operand tile of the 1 x 1 convolution (= its staging block)
-        const bool bad = stage_write_planes_row(stage, lane, m, true, !valid);
+        if (!valid) {                                    // rows past the tile's pixels: a zero operand row
+#pragma unroll
+          for (int j = 0; j < 32; ++j) m[j] = 0.f;
+        }
+        const bool bad = stage_write_planes_row_t<true>(stage, lane, m);
         if (bad && p.overflow_flag) *p.overflow_flag = 1;
         fence_proxy_async_smem();
         tcgen05_fence_before();                          // (our reads of the gate accumulator for the previous tile are done)
@@ -525,11 +556,23 @@ conv_pix_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
           tmem_ld32(lane_addr + ACC2_COL + mt * 64 + 32, g);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) m[j] = __fdividef(1.f, 1.f + __expf(-(g[j] + s_par[64 + j])));
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b = *reinterpret_cast<const float4*>(s_par + 64 + j);
+            m[j] = __fdividef(1.f, 1.f + __expf(-(g[j] + b.x)));
+            m[j + 1] = __fdividef(1.f, 1.f + __expf(-(g[j + 1] + b.y)));
+            m[j + 2] = __fdividef(1.f, 1.f + __expf(-(g[j + 2] + b.z)));
+            m[j + 3] = __fdividef(1.f, 1.f + __expf(-(g[j + 3] + b.w)));
+          }
           tmem_ld32(lane_addr + ACC2_COL + mt * 64, g);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) y[j] = y[j] + (g[j] + s_par[32 + j]) * m[j];
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b = *reinterpret_cast<const float4*>(s_par + 32 + j);
+            y[j] = fmaf(g[j] + b.x, m[j], y[j]);
+            y[j + 1] = fmaf(g[j + 1] + b.y, m[j + 1], y[j + 1]);
+            y[j + 2] = fmaf(g[j + 2] + b.z, m[j + 2], y[j + 2]);
+            y[j + 3] = fmaf(g[j + 3] + b.w, m[j + 3], y[j + 3]);
+          }
         }
         tcgen05_fence_before();
         if (p.post_relu) {
@@ -541,7 +584,7 @@ conv_pix_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         stage_write_f32_row(stage, lane, y);
         stage_store_rows(stage, lane, yg, p.ld_f32 * 4, 8, wrows);
         if (p.out16) {
-          const bool bad2 = stage_write_planes_row(stage, lane, y, p.relu_planes != 0, false);
+          const bool bad2 = stage_write_planes_row(stage, lane, y, p.relu_planes != 0);
           if (bad2 && valid && p.overflow_flag) *p.overflow_flag = 1;
           stage_store_rows(stage, lane, reinterpret_cast<uint8_t*>(p.out16) + wr * PIX_BYTES, PIX_BYTES, 8, wrows);
         }
