@@ -296,7 +296,7 @@ typedef struct usf_conv_pix_args {
  * last convolution, MaskedCoupling's update.  USF_ERR_UNSUPPORTED when w > 256 or the k*k*4 KB weight leaves no room for two
  * 32 KB pipeline stages in 227 KB of shared memory. */
 int usf_conv2d_pix(const usf_conv_pix_args* a, void* stream);
-int usf_set_pix_gate_at(int32_t chains);     /* gated block: chains of the next tile issued in front of a tile's 1 x 1 contraction (default 0); tools only */
+int usf_set_pix_gate_at(int32_t chains);     /* gated block: chains of the next tile issued in front of a tile's 1 x 1 contraction (default 1); tools only */
 int usf_set_pix_chain_taps(int32_t taps);   /* taps per TMEM accumulation chain (0 = default: 3 = 96 K-elements in the gated block, 2 in a plain convolution); tools only */
 
 /* x[r, c] += sign * g[(r mod hw)*c_dim + c] * t[r, c]: MaskedCoupling.forward/backward with a mask over [C, H, W]

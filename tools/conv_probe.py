@@ -110,5 +110,5 @@ for ga in (0, 1, 2, 3):
                                           gamma=gamma, beta=beta, eps=1e-5, out_f32=y, out16=b16, relu_planes=True))
         line.append(f"{taps} taps/chain {us:.1f} us")
     print(f"conv2d_pix gated, gate contraction behind {ga} chains of the next tile: " + ", ".join(line))
-_lib.load().usf_set_pix_gate_at(0)
+_lib.load().usf_set_pix_gate_at(1)
 _lib.load().usf_set_pix_chain_taps(0)

@@ -66,6 +66,8 @@ constexpr int A_MT = BLOCK_M * PIX_BYTES;           // 16 KB: second MMA tile of
 constexpr int W1_TAP = 32 * PIX_BYTES;              // 4 KB per tap
 constexpr int W2_BYTES = 64 * PIX_BYTES;            // 8 KB
 constexpr int MAX_STAGES = 6;
+constexpr int PIX_EPI_WARPS = 16;                   // two warps per 32-row block: each thread owns 16 channels of one pixel
+constexpr int PIX_THREADS = (FIRST_EPI_WARP + PIX_EPI_WARPS) * 32;
 constexpr int NBUF = 4;                             // TMEM accumulators of the k x k convolution (chains in flight: the MMA
                                                     // issuer runs a whole tile ahead of the epilogue warps)
 constexpr int ACC2_COL = NBUF * 64;                 // gate accumulator: 2 MMA tiles x 64 columns
@@ -254,6 +256,88 @@ __device__ __forceinline__ bool stage_write_planes_row(uint32_t stage, int lane,
   return relu ? stage_write_planes_row_t<true>(stage, lane, v) : stage_write_planes_row_t<false>(stage, lane, v);
 }
 
+// ---- half rows: the two warps of a pair share one staging block; the thread of (row, half) owns channels 16*half .. +15
+__device__ __forceinline__ void pair_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+// 16 fp32 channels = chunks 4*half .. 4*half + 3 of the row
+__device__ __forceinline__ void stage_write_f32_half(uint32_t stage, int lane, int half, const float (&v)[16]) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+    stage_write_chunk(stage, lane, 4 * half + c, make_uint4(__float_as_uint(v[4 * c]), __float_as_uint(v[4 * c + 1]),
+                                                            __float_as_uint(v[4 * c + 2]), __float_as_uint(v[4 * c + 3])));
+}
+__device__ __forceinline__ void stage_read_f32_half(uint32_t stage, int lane, int half, float (&v)[16]) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const uint4 u = stage_read_chunk(stage, lane, 4 * half + c);
+    v[4 * c] = __uint_as_float(u.x); v[4 * c + 1] = __uint_as_float(u.y);
+    v[4 * c + 2] = __uint_as_float(u.z); v[4 * c + 3] = __uint_as_float(u.w);
+  }
+}
+// 16 channels as pixel planes: high halves = chunks 2*half, 2*half + 1; low halves' = chunks 4 + 2*half, 5 + 2*half
+template <bool RELU>
+__device__ __forceinline__ bool stage_write_planes_half(uint32_t stage, int lane, int half, const float (&v)[16]) {
+  bool bad = false;
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    float t[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t[i] = RELU ? fmaxf(v[8 * c + i], 0.f) : v[8 * c + i];
+    uint4 hi, lo;
+    bad |= split8(t, hi, lo);
+    stage_write_chunk(stage, lane, 2 * half + c, hi);
+    stage_write_chunk(stage, lane, 4 + 2 * half + c, lo);
+  }
+  return bad;
+}
+// rows 16*half .. 16*half + 15 of the block -> global (the other 16 rows are the partner warp's)
+__device__ __forceinline__ void stage_store_rows16(uint32_t stage, int lane, int half, uint8_t* g, long long pitch, int nch, int nrows) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int row = 16 * half + 4 * i + (lane >> 3), ch = lane & 7;
+    const uint4 v = ld_shared_u4(stage + (uint32_t)row * 128u + ((uint32_t)(ch ^ (row & 7)) << 4));
+    if (row < nrows && ch < nch) *reinterpret_cast<uint4*>(g + row * pitch + ch * 16) = v;
+  }
+}
+__device__ __forceinline__ void stage_put_rows16(uint32_t stage, int lane, int half, const uint4 (&v)[4]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int row = 16 * half + 4 * i + (lane >> 3), ch = lane & 7;
+    st_shared_u4(stage + (uint32_t)row * 128u + ((uint32_t)(ch ^ (row & 7)) << 4), v[i]);
+  }
+}
+// LayerNorm over the n channels of a pixel held by two threads (16 channels each) of different warps: partial sums meet in
+// shared memory (xs / xq: one float per (half, tile row)), two pair barriers; biased variance, as nn.LayerNorm
+__device__ __forceinline__ void layer_norm_pair(float (&v)[16], int half, int n, const float* gamma, const float* beta, float eps,
+                                                float* xs, float* xq, int t, int pair_id) {
+  const int c0 = 16 * half;
+  float sum = 0.f;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) sum += c0 + j < n ? v[j] : 0.f;
+  xs[half * TILE_ROWS + t] = sum;
+  pair_sync(pair_id);
+  const float mean = (sum + xs[(half ^ 1) * TILE_ROWS + t]) / (float)n;
+  float sq = 0.f;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const float d = c0 + j < n ? v[j] - mean : 0.f;
+    sq = fmaf(d, d, sq);
+  }
+  xq[half * TILE_ROWS + t] = sq;
+  pair_sync(pair_id);
+  const float rstd = 1.f / sqrtf((sq + xq[(half ^ 1) * TILE_ROWS + t]) / (float)n + eps);
+#pragma unroll
+  for (int j = 0; j < 16; j += 4) {
+    const float4 g = *reinterpret_cast<const float4*>(gamma + c0 + j);
+    const float4 b = *reinterpret_cast<const float4*>(beta + c0 + j);
+    if (c0 + j < n) {
+      v[j] = (v[j] - mean) * rstd * g.x + b.x;
+      v[j + 1] = (v[j + 1] - mean) * rstd * g.y + b.y;
+      v[j + 2] = (v[j + 2] - mean) * rstd * g.z + b.z;
+      v[j + 3] = (v[j + 3] - mean) * rstd * g.w + b.w;
+    }
+  }
+}
+
 // descriptor of a K-major 128B-swizzled operand tile from its low word (start address >> 4 | LBO): the high word (stride
 // 1024 B, version, swizzle mode) is a constant, so K offsets are 32-bit adds and the compiler keeps the high word in one
 // uniform register (the MMA issuers are single threads whose instruction stream bounds the kernel, see below)
@@ -268,7 +352,7 @@ __device__ __forceinline__ uint64_t desc64(uint32_t lo) {
 // DBG: the switches of tools/conv_probe.py (p.dbg: 64 = no activation loads, 128 = no MMAs, 256 = no global traffic in
 // the epilogue); the shipped instantiation has none of it.
 template <bool DBG>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(PIX_THREADS, 1)
 conv_pix_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w1,
                 const __grid_constant__ CUtensorMap tm_w2, const PixArgs p) {
   extern __shared__ uint8_t smem_raw[];
@@ -289,6 +373,8 @@ conv_pix_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
   // per-channel constants of the epilogue (bias1[32] | bias2[64] | gamma[32] | beta[32]): broadcast shared-memory reads
   // instead of ~200 uniform global loads per pixel thread and tile
   float* s_par = reinterpret_cast<float*>(smem_raw + (bar_base + 256u - smem_u32(smem_raw)));
+  float* s_xs = s_par + 192;                           // LayerNorm partial sums / squares of the two column halves: 2 x 2 x 256 floats
+  float* s_xq = s_xs + 2 * TILE_ROWS;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_chains = (p.taps + p.chain_taps - 1) / p.chain_taps;
@@ -302,9 +388,9 @@ conv_pix_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
   if (warp == 1) {
     if (lane == 0) {
       for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), MT); }
-      for (int s = 0; s < NBUF; ++s) { mbar_init(tfull_bar(s), MT); mbar_init(tempty_bar(s), NUM_EPI_WARPS); }
+      for (int s = 0; s < NBUF; ++s) { mbar_init(tfull_bar(s), MT); mbar_init(tempty_bar(s), PIX_EPI_WARPS); }
       mbar_init(wfull_bar, 1);
-      mbar_init(a2full_bar, NUM_EPI_WARPS);
+      mbar_init(a2full_bar, PIX_EPI_WARPS);
       mbar_init(acc2full_bar, MT);
       fence_barrier_init();
     }
@@ -327,8 +413,9 @@ conv_pix_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   // What the measurements decided (tools/conv_probe.py, profiles/r02_conv_pix.md):
-  //  * setmaxnreg 96 / 200, not the 56 / 224 of the flat kernels: at 56 registers the issuer re-loaded its descriptors
-  //    from local memory in front of every tcgen05.mma;
+  //  * no setmaxnreg (640 threads x 96 registers; the 56 / 224 split of the flat kernels made the issuer re-load its
+  //    descriptors from local memory in front of every tcgen05.mma; and setmaxnreg.inc can only take what .dec released
+  //    inside the CTA's launch allocation);
   //  * the issuing threads are chosen with elect.sync, not `lane == 0`: the compiler then emits tcgen05.mma / TMA back to
   //    back instead of wrapping each one in an ELECT / BRA.U.ANY loop that waits for the instruction's scoreboard;
   //  * ONE thread per role runs the barrier protocol (32 lanes polling an mbarrier serialise), and a wait first tries the
@@ -336,7 +423,6 @@ conv_pix_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
   //  * the issuer's own instruction stream (~20 instructions per MMA of 16-44 tensor cycles at N = 32) is what bounds the
   //    kernel, so each of the two 128-row MMA tiles of a CTA tile has its own issuer warp.
   if (warp < FIRST_EPI_WARP) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(96));       // 128 x 96 + 256 x 200 = 63 488 registers
     if (warp == 0) {
       // ===================== TMA producer: the weights once, then one box per (tile, tap) =====================
       if (elect_one()) {
@@ -434,49 +520,65 @@ conv_pix_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
       if (pending) gate_mma();
     }
   } else {
-    // ===================== epilogue warps: one thread per pixel of the tile =====================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(200));
-    const int q = warp & 3, mt = (warp - FIRST_EPI_WARP) >> 2;
-    const int wrow0 = mt * BLOCK_M + q * 32;                          // first tile row of this warp
+    // ===================== epilogue warps: two threads (of two warps) per pixel, 16 channels each =====================
+    // (one thread per pixel with all 32 channels was ~2 600 instructions per tile on two warps per scheduler and bound the
+    //  gated block; the pair meets in shared memory for the LayerNorm statistics and shares the 32-row staging block)
+    const int e = warp - FIRST_EPI_WARP;
+    const int q = e & 3, mt = (e >> 2) & 1, half = e >> 3;
+    const int pair_id = 1 + (e & 7);                                  // named barrier of the two warps of a block
+    const int c0 = 16 * half;                                         // first channel of this thread
+    const int wrow0 = mt * BLOCK_M + q * 32;                          // first tile row of the pair's block
     const int t = wrow0 + lane;                                       // row of the CTA tile
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-    const uint32_t stage = a2_base + (uint32_t)wrow0 * 128u;          // this warp's 4 KB block (rows wrow0 .. wrow0 + 31)
+    const uint32_t stage = a2_base + (uint32_t)wrow0 * 128u;          // the pair's 4 KB block (rows wrow0 .. wrow0 + 31)
     const bool x_vec = p.x && p.c_x % 4 == 0 && p.ldx % 4 == 0 && (reinterpret_cast<uintptr_t>(p.x) & 15) == 0;
     int acc = 0;
     uint32_t acc_phase = 0, acc2_phase = 0;
+    // The rows a tile's epilogue READS (gated: the residual stream; last convolution: x) are fetched ONE TILE AHEAD, as soon
+    // as the previous tile has moved its copy into the staging block (this warp: 16 of the block's 32 rows, 512 contiguous
+    // bytes per instruction): issued at the top of their own tile they queued behind the previous tile's stores and their
+    // latency showed (the gated block: 166 -> 15x us).
+    uint4 pre[4];
+    const bool pre_on = (p.gated || x_vec) && !no_traffic;
+    const uint8_t* pre_base = p.gated ? reinterpret_cast<const uint8_t*>(p.out_f32) : reinterpret_cast<const uint8_t*>(p.x);
+    const long long pre_pitch = p.gated ? p.ld_f32 * 4 : p.ldx * 4;
+    const int pre_nch = p.gated ? 8 : (p.c_x >> 2);
+    auto prefetch = [&](long long tile_) {
+      if (!pre_on || tile_ >= p.n_tiles) return;
+      const Tile tn = decode_tile(p, tile_);
+      int rows_ = tn.nvalid - wrow0;
+      rows_ = rows_ < 0 ? 0 : rows_ > 32 ? 32 : rows_;
+      const uint8_t* g_ = pre_base + (tn.row0 + wrow0) * pre_pitch;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int row = 16 * half + 4 * i + (lane >> 3), ch = lane & 7;
+        pre[i] = make_uint4(0u, 0u, 0u, 0u);
+        if (row < rows_ && ch < pre_nch) pre[i] = *reinterpret_cast<const uint4*>(g_ + row * pre_pitch + ch * 16);
+      }
+    };
+#pragma unroll
+    for (int i = 0; i < 4; ++i) pre[i] = make_uint4(0u, 0u, 0u, 0u);
+    prefetch(blockIdx.x);
     for (long long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
       const Tile tl = decode_tile(p, tile);
       const bool valid = t < tl.nvalid && !no_traffic;
-      int wrows = tl.nvalid - wrow0;                                  // valid rows of this warp's block
+      int wrows = tl.nvalid - wrow0;                                  // valid rows of the pair's block
       wrows = no_traffic ? 0 : wrows < 0 ? 0 : wrows > 32 ? 32 : wrows;
       const long long r = tl.row0 + t, wr = tl.row0 + wrow0;
-      // the rows this tile's epilogue READS (gated: the residual stream; last convolution: x) are fetched now, 512 contiguous
-      // bytes per instruction, so their latency hides behind the waits for the accumulators
-      uint4 pre[8];
-      const uint8_t* pre_g = p.gated ? reinterpret_cast<const uint8_t*>(p.out_f32 + wr * p.ld_f32)
-                                     : x_vec ? reinterpret_cast<const uint8_t*>(p.x + wr * p.ldx) : nullptr;
-      const long long pre_pitch = p.gated ? p.ld_f32 * 4 : p.ldx * 4;
-      const int pre_nch = p.gated ? 8 : (p.c_x >> 2);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int row = 4 * i + (lane >> 3), ch = lane & 7;
-        pre[i] = make_uint4(0u, 0u, 0u, 0u);
-        if (pre_g && row < wrows && ch < pre_nch) pre[i] = *reinterpret_cast<const uint4*>(pre_g + row * pre_pitch + ch * 16);
-      }
-      float m[32];
+      float m[16];
       for (int c = 0; c < n_chains; ++c) {
         if (lane == 0) mbar_wait(tfull_bar(acc), acc_phase);
         __syncwarp();
         tcgen05_fence_after();
-        float v[32];
-        tmem_ld32(lane_addr + acc * 64 + mt * 32, v);
+        float v[16];
+        tmem_ld16(lane_addr + acc * 64 + mt * 32 + c0, v);
         tmem_ld_wait();
         if (c == 0) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) m[j] = v[j];
+          for (int j = 0; j < 16; ++j) m[j] = v[j];
         } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) m[j] += v[j];
+          for (int j = 0; j < 16; ++j) m[j] += v[j];
         }
         tcgen05_fence_before();
         __syncwarp();
@@ -484,90 +586,99 @@ conv_pix_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         if (++acc == NBUF) { acc = 0; acc_phase ^= 1; }
       }
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        const float4 b = *reinterpret_cast<const float4*>(s_par + j);
+      for (int j = 0; j < 16; j += 4) {
+        const float4 b = *reinterpret_cast<const float4*>(s_par + c0 + j);
         m[j] += b.x; m[j + 1] += b.y; m[j + 2] += b.z; m[j + 3] += b.w;
       }
       if (!p.gated) {
         if (p.relu1) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) m[j] = fmaxf(m[j], 0.f);
+          for (int j = 0; j < 16; ++j) m[j] = fmaxf(m[j], 0.f);
         }
-        if (p.gamma) layer_norm32(m, p.n1, s_par + 96, s_par + 128, p.eps);
+        if (p.gamma) layer_norm_pair(m, half, p.n1, s_par + 96, s_par + 128, p.eps, s_xs, s_xq, t, pair_id);
         if (p.x) {                                                    // x[r, c] += sign * (1 - mask)[pixel, c] * v[c]
           const int pix = (tl.h0 * p.W + t) % p.HW;
           const float* g = p.inv_mask + (long long)pix * p.c_x;
           if (x_vec) {
             uint8_t* xg = reinterpret_cast<uint8_t*>(p.x + wr * p.ldx);
-            stage_put_rows(stage, lane, pre);
-            float xr[32];
-            stage_read_f32_row(stage, lane, xr);
+            stage_put_rows16(stage, lane, half, pre);
+            pair_sync(pair_id);
+            prefetch(tile + gridDim.x);
+            float xr[16];
+            stage_read_f32_half(stage, lane, half, xr);
             if (valid) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (j < p.c_x) xr[j] = fmaf(p.sign * __ldg(g + j), m[j], xr[j]);
+              for (int j = 0; j < 16; ++j)
+                if (c0 + j < p.c_x) xr[j] = fmaf(p.sign * __ldg(g + c0 + j), m[j], xr[j]);
             }
-            __syncwarp();
-            stage_write_f32_row(stage, lane, xr);
-            stage_store_rows(stage, lane, xg, p.ldx * 4, p.c_x >> 2, wrows);
+            stage_write_f32_half(stage, lane, half, xr);            // (own chunks only: read and written by this thread)
+            pair_sync(pair_id);
+            stage_store_rows16(stage, lane, half, xg, p.ldx * 4, p.c_x >> 2, wrows);
+            pair_sync(pair_id);
           } else if (valid) {
             float* xr = p.x + r * p.ldx;
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (j < p.c_x) xr[j] = fmaf(p.sign * __ldg(g + j), m[j], xr[j]);
+            for (int j = 0; j < 16; ++j)
+              if (c0 + j < p.c_x) xr[c0 + j] = fmaf(p.sign * __ldg(g + c0 + j), m[j], xr[c0 + j]);
           }
         }
         if (p.out_f32) {
-          stage_write_f32_row(stage, lane, m);
-          stage_store_rows(stage, lane, reinterpret_cast<uint8_t*>(p.out_f32 + wr * p.ld_f32), p.ld_f32 * 4, p.n1 >> 2, wrows);
+          stage_write_f32_half(stage, lane, half, m);
+          pair_sync(pair_id);
+          stage_store_rows16(stage, lane, half, reinterpret_cast<uint8_t*>(p.out_f32 + wr * p.ld_f32), p.ld_f32 * 4, p.n1 >> 2, wrows);
+          pair_sync(pair_id);
         }
         if (p.out16) {
-          const bool bad = stage_write_planes_row(stage, lane, m, p.relu_planes != 0);
+          const bool bad = p.relu_planes ? stage_write_planes_half<true>(stage, lane, half, m)
+                                         : stage_write_planes_half<false>(stage, lane, half, m);
           if (bad && valid && p.overflow_flag) *p.overflow_flag = 1;
-          stage_store_rows(stage, lane, reinterpret_cast<uint8_t*>(p.out16) + wr * PIX_BYTES, PIX_BYTES, 8, wrows);
+          pair_sync(pair_id);
+          stage_store_rows16(stage, lane, half, reinterpret_cast<uint8_t*>(p.out16) + wr * PIX_BYTES, PIX_BYTES, 8, wrows);
+          pair_sync(pair_id);
         }
       } else {
-        // the residual stream's rows of this warp, through the staging block (which is free: the previous tile's stores
-        // ended with a __syncwarp, its gate contraction has been consumed)
+        // the residual stream's rows of this block, through the staging block (free: the previous tile's stores ended with
+        // a pair barrier, its gate contraction has been consumed)
         uint8_t* yg = reinterpret_cast<uint8_t*>(p.out_f32 + wr * p.ld_f32);
-        float y[32];
-        stage_put_rows(stage, lane, pre);
-        stage_read_f32_row(stage, lane, y);
-        __syncwarp();
-        // u = relu(conv + b) -> this warp's rows of the operand tile of the 1 x 1 convolution (= its staging block)
+        float y[16];
+        stage_put_rows16(stage, lane, half, pre);
+        pair_sync(pair_id);
+        stage_read_f32_half(stage, lane, half, y);
+        pair_sync(pair_id);                              // both halves have read their channels: the block becomes the operand
+        // u = relu(conv + b) -> the pair's rows of the operand tile of the 1 x 1 convolution (= its staging block)
         if (!valid) {                                    // rows past the tile's pixels: a zero operand row
 #pragma unroll
-          for (int j = 0; j < 32; ++j) m[j] = 0.f;
+          for (int j = 0; j < 16; ++j) m[j] = 0.f;
         }
-        const bool bad = stage_write_planes_row_t<true>(stage, lane, m);
+        const bool bad = stage_write_planes_half<true>(stage, lane, half, m);
         if (bad && p.overflow_flag) *p.overflow_flag = 1;
         fence_proxy_async_smem();
         tcgen05_fence_before();                          // (our reads of the gate accumulator for the previous tile are done)
         __syncwarp();
         if (lane == 0) mbar_arrive(a2full_bar);
+        prefetch(tile + gridDim.x);                      // (its registers were emptied into the staging block above)
         if (lane == 0) mbar_wait(acc2full_bar, acc2_phase);
         __syncwarp();
         acc2_phase ^= 1;
         tcgen05_fence_after();
         {
-          // sigmoid with ex2.approx / rcp.approx (a few ulp; 32 of them per pixel: the full-precision expf + division were
-          // a third of the epilogue's instructions)
-          float g[32];
-          tmem_ld32(lane_addr + ACC2_COL + mt * 64 + 32, g);
+          // sigmoid with ex2.approx / rcp.approx (a few ulp)
+          float g[16];
+          tmem_ld16(lane_addr + ACC2_COL + mt * 64 + 32 + c0, g);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 b = *reinterpret_cast<const float4*>(s_par + 64 + j);
+          for (int j = 0; j < 16; j += 4) {
+            const float4 b = *reinterpret_cast<const float4*>(s_par + 64 + c0 + j);
             m[j] = __fdividef(1.f, 1.f + __expf(-(g[j] + b.x)));
             m[j + 1] = __fdividef(1.f, 1.f + __expf(-(g[j + 1] + b.y)));
             m[j + 2] = __fdividef(1.f, 1.f + __expf(-(g[j + 2] + b.z)));
             m[j + 3] = __fdividef(1.f, 1.f + __expf(-(g[j + 3] + b.w)));
           }
-          tmem_ld32(lane_addr + ACC2_COL + mt * 64, g);
+          tmem_ld16(lane_addr + ACC2_COL + mt * 64 + c0, g);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 b = *reinterpret_cast<const float4*>(s_par + 32 + j);
+          for (int j = 0; j < 16; j += 4) {
+            const float4 b = *reinterpret_cast<const float4*>(s_par + 32 + c0 + j);
             y[j] = fmaf(g[j] + b.x, m[j], y[j]);
             y[j + 1] = fmaf(g[j + 1] + b.y, m[j + 1], y[j + 1]);
             y[j + 2] = fmaf(g[j + 2] + b.z, m[j + 2], y[j + 2]);
@@ -577,16 +688,23 @@ conv_pix_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         tcgen05_fence_before();
         if (p.post_relu) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) y[j] = fmaxf(y[j], 0.f);
+          for (int j = 0; j < 16; ++j) y[j] = fmaxf(y[j], 0.f);
         }
-        if (p.gamma) layer_norm32(y, p.n1, s_par + 96, s_par + 128, p.eps);
-        // (the gate contraction has completed -- acc2full -- so the tensor core is done reading the staging block)
-        stage_write_f32_row(stage, lane, y);
-        stage_store_rows(stage, lane, yg, p.ld_f32 * 4, 8, wrows);
+        if (p.gamma) layer_norm_pair(y, half, p.n1, s_par + 96, s_par + 128, p.eps, s_xs, s_xq, t, pair_id);
+        // (the gate contraction has completed -- acc2full, observed by BOTH warps before the pair barriers of the LayerNorm
+        //  or the one below -- so the tensor core is done reading the staging block)
+        if (!p.gamma) pair_sync(pair_id);
+        stage_write_f32_half(stage, lane, half, y);
+        pair_sync(pair_id);
+        stage_store_rows16(stage, lane, half, yg, p.ld_f32 * 4, 8, wrows);
+        pair_sync(pair_id);
         if (p.out16) {
-          const bool bad2 = stage_write_planes_row(stage, lane, y, p.relu_planes != 0);
+          const bool bad2 = p.relu_planes ? stage_write_planes_half<true>(stage, lane, half, y)
+                                          : stage_write_planes_half<false>(stage, lane, half, y);
           if (bad2 && valid && p.overflow_flag) *p.overflow_flag = 1;
-          stage_store_rows(stage, lane, reinterpret_cast<uint8_t*>(p.out16) + wr * PIX_BYTES, PIX_BYTES, 8, wrows);
+          pair_sync(pair_id);
+          stage_store_rows16(stage, lane, half, reinterpret_cast<uint8_t*>(p.out16) + wr * PIX_BYTES, PIX_BYTES, 8, wrows);
+          pair_sync(pair_id);
         }
       }
     }
@@ -648,14 +766,14 @@ inline bool conv_pix_geometry(int H, int W, int* imgs, int* hr, int* tiles_per_i
 }
 // pipeline stages that fit next to the resident weights (0: the shape does not fit)
 inline int conv_pix_stages(int taps, int gated) {
-  const long long fixed = (long long)taps * convpix::W1_TAP + (gated ? convpix::W2_BYTES : 0) + convpix::A_STAGE + 1024 + 1024;
+  const long long fixed = (long long)taps * convpix::W1_TAP + (gated ? convpix::W2_BYTES : 0) + convpix::A_STAGE + 1024 + 6144;
   long long s = (227 * 1024 - fixed) / convpix::A_STAGE;
   if (s > convpix::MAX_STAGES) s = convpix::MAX_STAGES;
   return s >= 2 ? (int)s : 0;
 }
 inline size_t conv_pix_smem_bytes(int taps, int gated) {
   return (size_t)conv_pix_stages(taps, gated) * convpix::A_STAGE + (size_t)taps * convpix::W1_TAP +
-         (gated ? convpix::W2_BYTES : 0) + convpix::A_STAGE + 1024 + 1024;
+         (gated ? convpix::W2_BYTES : 0) + convpix::A_STAGE + 1024 + 6144;
 }
 
 extern int g_pix_gate_at;               // chains of the next tile issued in front of a tile's gate contraction

@@ -4,7 +4,7 @@
 namespace usf {
 
 int g_pix_chain_taps = 0;              // 0 = auto: 3 for the gated block, 2 for a plain convolution (measured, tools/conv_probe.py)
-int g_pix_gate_at = 0;
+int g_pix_gate_at = 1;
 extern int g_dbg_flags;
 
 static int make_pix_map(CUtensorMap* map, const void* ptr, long long n_images, int H, int W, int hr, int imgs) {
@@ -75,7 +75,7 @@ int launch_conv_pix(const usf_conv_pix_args* a, cudaStream_t st) {
     mw2 = mw1;
   }
   const int grid = (int)(p.n_tiles < num_sms() ? p.n_tiles : num_sms());
-  kern<<<grid, tc::NUM_THREADS, smem, st>>>(ma, mw1, mw2, p);
+  kern<<<grid, convpix::PIX_THREADS, smem, st>>>(ma, mw1, mw2, p);
   USF_CUDA_OK(cudaGetLastError());
   return USF_OK;
 }

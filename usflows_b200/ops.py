@@ -291,7 +291,7 @@ PIX_SMEM_LIMIT = 227 * 1024
 def conv2d_pix_supported(h: int, w: int, k: int, gated: bool = True) -> bool:
     """Whether usf_conv2d_pix serves this image / kernel size (rows <= 256 pixels wide; the k*k*4 KB weight next to at least
     two 32 KB pipeline stages -- and the gate's operand tile -- in shared memory)."""
-    fixed = k * k * 4096 + (8192 if gated else 0) + 32768 + 2048
+    fixed = k * k * 4096 + (8192 if gated else 0) + 32768 + 7168
     return w <= 256 and k % 2 == 1 and (PIX_SMEM_LIMIT - fixed) // 32768 >= 2
 
 
