@@ -70,6 +70,25 @@ def test_image_launch_plan(fake_ops):
     assert {c[2] for c in fake_ops.CALLS if c[0] == "linear"} == {arr["x"].shape[0] * 49}
 
 
+def test_image_program_merges_neighbouring_affine_maps_on_request(fake_ops):
+    """engine.MERGE_AFFINE (off by default, see engine.py): the inverse 1x1 convolution of one block's affine conjugation
+    and the next block's are one C x C map."""
+    from usflows_b200 import engine
+    spec, params, arr = load_case("img_mnist_16x7x7")
+    lp = build_flow(spec, params, device="cpu", precision="fp32").log_prob(arr["x"])
+    n_plain = [c[0] for c in fake_ops.CALLS].count("linear")
+    engine.MERGE_AFFINE = True
+    try:
+        fake_ops.CALLS.clear()
+        lp_m = build_flow(spec, params, device="cpu", precision="fp32").log_prob(arr["x"])
+        n_merged = [c[0] for c in fake_ops.CALLS].count("linear")
+    finally:
+        engine.MERGE_AFFINE = False
+    B = spec["coupling_blocks"]
+    assert n_merged == B + 1 and n_merged < n_plain
+    assert rel_err(lp_m, lp) < 1e-5
+
+
 def test_image_flow_api_shapes(fake_ops):
     spec, params, arr = load_case("img_c4_4x4")
     flow = build_flow(spec, params, device="cpu")

@@ -251,6 +251,14 @@ class ImageProgram:
         if prims and prims[-1].kind in ("mul", "div"):
             self.exit_scale = (prims[-1].v.contiguous(), 1 if prims[-1].kind == "mul" else 2)
             prims = prims[:-1]
+        if engine.MERGE_AFFINE:                              # consecutive 1x1 convolutions (the inverse of one block's affine
+            merged: List[Prim] = []                          # conjugation, the next block's) are ONE C x C map, composed in fp64
+            for p in prims:
+                if p.kind == "aff" and merged and merged[-1].kind == "aff":
+                    merged[-1] = engine._compose_run([merged[-1], p])
+                else:
+                    merged.append(p)
+            prims = merged
         self.ops = []
         for p in prims:
             if p.kind == "aff":                              # 1x1 convolution with the C x C matrix (transforms.py:904-962)
