@@ -561,13 +561,15 @@ def main():
     # kernel-class breakdown of one step (events around every launch; after the timed region)
     breakdown = engine.profile_step(lambda: flow.log_prob(x))
     gemm_ms = sum(v for k, v in breakdown.items() if k.startswith("linear"))
-    if len(spec["in_dims"]) > 1:            # image path: the convolutions (implicit GEMM, or gather + contraction)
-        gemm_ms += breakdown.get("im2col", 0.0) + breakdown.get("conv2d_rows", 0.0)
+    conv_names = ("im2col", "conv2d_rows", "pix_encode", "conv2d_pix")
+    if len(spec["in_dims"]) > 1:            # image path: the convolutions (pixel planes, implicit GEMM, or gather + contraction)
+        gemm_ms += sum(breakdown.get(k, 0.0) for k in conv_names)
     peaks, peak_kind = measured_peaks()
     traffic, traffic_step, traffic_src = committed_traffic(args.workload, args.precision)
     achieved_tf = rows * flops_per_sample / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
     peak_tf = peaks["bf16_tflops_sustained"]
-    n_gemm = sum(1 for k in breakdown.get("_names", []) if k.startswith("linear")) or 1
+    n_gemm = sum(1 for k in breakdown.get("_names", []) if k.startswith("linear") or
+                 (len(spec["in_dims"]) > 1 and k in conv_names)) or 1
 
     extra_modes = {}
     tf32_peak = None
@@ -628,8 +630,9 @@ def main():
                     f"`traffic` = mean PER LAUNCH of the dominant kernel, `traffic_per_step` = sum over its launches of one step",
                     peak_source=f"bf16_tflops_sustained, of {peak_kind}",
                     kernel="tc2::gemm_tc2_kernel (CTA-pair tcgen05, all launches of one step)" if len(spec["in_dims"]) == 1
-                    else "convtc::conv_tc_kernel (implicit-GEMM tcgen05 convolution) + tc2::gemm_tc2_kernel / SIMT 1x1 "
-                         "convolutions, all launches of one step",
+                    else "convpix::conv_pix_kernel (ConvNet2D conditioners on pixel planes: TMA-box taps, tcgen05 kind::f16 x3; "
+                         "convtc::conv_tc_kernel for other widths / modes) + pix_encode + the 1x1-convolution contractions, "
+                         "all launches of one step",
                     kernel_ms_per_step=gemm_ms,
                     launches_per_step=n_gemm,
                     algorithmic_bytes_per_step=rows * (4 * d + 4),

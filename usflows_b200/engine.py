@@ -993,7 +993,7 @@ def profile_step(fn) -> dict:
     records = []
     originals = {name: getattr(ops, name) for name in ("linear", "ingest", "base_logprob", "flow_small", "gate_norm", "radial_logprob",
                                                          "affine_couple", "im2col", "conv2d_rows", "layout_transpose",
-                                                         "masked_add")}
+                                                         "masked_add", "pix_encode", "conv2d_pix")}
 
     def wrap(name, f):
         def inner(*a, **k):
