@@ -217,3 +217,33 @@ def test_image_flow_outside_the_fp16_range_falls_back_per_chunk():
     assert bool(torch.isfinite(z).all())
     assert torch.equal(z[4:8], z_ref[4:8])                 # the flagged chunk: exactly the fallback program's result
     assert rel_err(z[:4], z_ref[:4]) <= 3e-6 and not torch.equal(z[:4], z_ref[:4])     # the others: the fp16-split engine
+
+
+def test_small_image_batches_replay_one_graph():
+    """`log_prob` of an image-shaped flow on a small batch: the ~100 launches of the step are captured once per batch size
+    and replayed; same bits as the launch-by-launch route, follows new inputs and new weights, and a batch outside the
+    fp16 range falls through to the launch-by-launch route (which re-runs the chunk on the tf32-split program)."""
+    from usflows_b200 import flows
+    spec, params, arr = load_case("img_mnist_16x7x7")
+    x = arr["x"].cuda()
+    flow = build_flow(spec, params)
+    old = flows.SMALL_BATCH_GRAPH_IMAGES
+    flows.SMALL_BATCH_GRAPH_IMAGES = 0
+    try:
+        want = flow.log_prob(x)
+        want2 = flow.log_prob(x.flip(0))
+    finally:
+        flows.SMALL_BATCH_GRAPH_IMAGES = old
+    prog, _ = flow._program("backward")
+    assert torch.equal(flow.log_prob(x), want) and len(prog.__dict__.get("_lp_graphs", {})) == 1
+    assert torch.equal(flow.log_prob(x.flip(0)), want2)                 # replay on new inputs
+    assert torch.equal(flow.log_prob(x[:7]), want[:7]) and len(prog.__dict__["_lp_graphs"]) == 2
+    big = x.clone()
+    big[3] *= 1e6
+    lp_big = flow.log_prob(big)
+    assert bool(torch.isfinite(lp_big[:3]).all()) and torch.equal(lp_big[:3], want[:3])
+    with torch.no_grad():
+        for p_ in flow.parameters():
+            p_.mul_(1.001)
+    lp_new = flow.log_prob(x)
+    assert not torch.equal(lp_new, want) and rel_err(lp_new, want) < 0.5    # the graph followed the new weight version

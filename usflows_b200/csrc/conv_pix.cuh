@@ -411,6 +411,10 @@ conv_pix_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  // Programmatic dependent launch (common.cuh): everything above -- and the weight load below -- touches only kernel
+  // parameters, per-weight-version constants and this CTA's shared / tensor memory, so it may run while the previous kernel
+  // of the chain drains; the threads that read or write activations (producer, epilogue warps) wait for it first.
+  griddep_launch_dependents();
 
   // What the measurements decided (tools/conv_probe.py, profiles/r02_conv_pix.md):
   //  * no setmaxnreg (640 threads x 96 registers; the 56 / 224 split of the flat kernels made the issuer re-load its
@@ -429,6 +433,7 @@ conv_pix_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         mbar_expect_tx(wfull_bar, (uint32_t)p.taps * W1_TAP + (p.gated ? W2_BYTES : 0));
         for (int tap = 0; tap < p.taps; ++tap) tma_load_2d(w1_base + (uint32_t)tap * W1_TAP, &tm_w1, wfull_bar, tap * 64, 0);
         if (p.gated) tma_load_2d(w2_base, &tm_w2, wfull_bar, 0, 0);
+        griddep_wait();
         const int half = p.ksize >> 1;
         int stage = 0;
         uint32_t phase = 0;
@@ -534,6 +539,7 @@ conv_pix_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     const bool x_vec = p.x && p.c_x % 4 == 0 && p.ldx % 4 == 0 && (reinterpret_cast<uintptr_t>(p.x) & 15) == 0;
     int acc = 0;
     uint32_t acc_phase = 0, acc2_phase = 0;
+    griddep_wait();
     // The rows a tile's epilogue READS (gated: the residual stream; last convolution: x) are fetched ONE TILE AHEAD, as soon
     // as the previous tile has moved its copy into the staging block (this warp: 16 of the block's 32 rows, 512 contiguous
     // bytes per instruction): issued at the top of their own tile they queued behind the previous tile's stores and their

@@ -75,7 +75,7 @@ int launch_conv_pix(const usf_conv_pix_args* a, cudaStream_t st) {
     mw2 = mw1;
   }
   const int grid = (int)(p.n_tiles < num_sms() ? p.n_tiles : num_sms());
-  kern<<<grid, convpix::PIX_THREADS, smem, st>>>(ma, mw1, mw2, p);
+  USF_CUDA_OK(launch_chain(kern, dim3(grid), dim3(convpix::PIX_THREADS), smem, st, ma, mw1, mw2, p));
   USF_CUDA_OK(cudaGetLastError());
   return USF_OK;
 }

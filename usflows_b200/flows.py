@@ -22,6 +22,7 @@ from .transforms import (BaseTransform, BlockAffineTransform, HouseholderTransfo
 
 
 SMALL_BATCH_GRAPH_ROWS = 4096   # `log_prob` on at most this many rows replays one captured CUDA graph (0 = off)
+SMALL_BATCH_GRAPH_IMAGES = 1024 # the same for image-shaped events (one chunk; ~15 us of host time per launch otherwise)
 USE_C_PLAN = True             # device-resident `log_prob` / `backward` / `_forward`: ONE C call per chunk (usf_flow_logprob /
                               # usf_flow_apply on a library-owned plan) where the program is contractions only
 HOST_CUDA_GRAPHS = True       # `log_prob_host`: replay one captured CUDA graph per full-size chunk
@@ -164,6 +165,11 @@ class Flow(torch.nn.Module):
         d = x2.shape[1]
         rows = x2.shape[0]
         if isinstance(prog, image_engine.ImageProgram):      # image-shaped event: the latent arrives channels-last
+            if x2.is_cuda and 0 < rows <= SMALL_BATCH_GRAPH_IMAGES and not prog.force_fallback \
+                    and not torch.cuda.is_current_stream_capturing():
+                lp = self._log_prob_small_batch(prog, ladj, x2)     # ~100 launches per step: one graph replay instead
+                if lp is not None:
+                    return lp.reshape(batch_shape)
             out = torch.empty(rows, dtype=torch.float32, device=x2.device)
             perm = self._channels_last_perm(x2.device)
             with torch.no_grad():
@@ -246,11 +252,19 @@ class Flow(torch.nn.Module):
             out = torch.empty(rows, dtype=torch.float32, device=dev)
             flag = torch.zeros(1, dtype=torch.int32, device=dev) if prog.mode == "fp32" else None
             width = prog.out_width(d)
-            fin = engine._workspace.planes(dev, "final_small", rows, width, "f32")
+            if isinstance(prog, image_engine.ImageProgram):
+                fin = image_engine._dense(dev, "img_final_small", rows, d)
+                perm = self._channels_last_perm(dev)
 
-            def body():
-                prog._run_chunk(xin, fin, flag)
-                base._density_into(ops.Act(rows, width, f32=fin), -ladj, out)
+                def body():
+                    prog._run_chunk(xin, fin, False, flag)
+                    base._density_into(ops.Act(rows, d, f32=fin), -ladj, out, perm=perm)
+            else:
+                fin = engine._workspace.planes(dev, "final_small", rows, width, "f32")
+
+                def body():
+                    prog._run_chunk(xin, fin, flag)
+                    base._density_into(ops.Act(rows, width, f32=fin), -ladj, out)
             with torch.no_grad():
                 xin.copy_(x2)
                 body()                                        # eager pass: sizes every workspace buffer before capture
