@@ -507,7 +507,7 @@ def main():
         U.set_chunk_rows(args.chunk_rows)
         if len(spec["in_dims"]) > 1:                 # image-shaped events: channels-last rows (N*H*W) per chunk
             from usflows_b200 import image_engine
-            image_engine.IMAGE_CHUNK_ROWS = args.chunk_rows
+            image_engine.IMAGE_CHUNK_ROWS = image_engine.IMAGE_CHUNK_ROWS_PIX = args.chunk_rows
     rows = args.rows or wl["rows"]
     params = O.random_params(spec, 0)
     flow = build_flow(spec, params, device=dev, precision=args.precision)
@@ -660,7 +660,10 @@ def main():
                "bf16": "bf16"}[args.precision],
         config=dict(workload=wl["name"], rows_per_gpu_per_step=rows, d=d, hidden=spec.get("hidden_dims", spec.get("c_hidden")),
                     coupling_blocks=spec["coupling_blocks"], precision=args.precision,
-                    chunk_rows=engine._default_chunk_rows, l2="inputs larger than L2, no flush",
+                    chunk_rows=engine._default_chunk_rows if len(spec["in_dims"]) == 1 else
+                    f"{__import__('usflows_b200.image_engine', fromlist=['x']).IMAGE_CHUNK_ROWS_PIX} channels-last rows "
+                    f"(pixel-plane route; {__import__('usflows_b200.image_engine', fromlist=['x']).IMAGE_CHUNK_ROWS} on the others)",
+                    l2="inputs larger than L2, no flush",
                     flops_per_sample=flops_per_sample, prep_ms_once_per_weight_version=prep_ms,
                     host_affinity=affinity),
         roofline=roofline,

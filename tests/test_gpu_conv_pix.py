@@ -207,13 +207,13 @@ def test_image_flow_outside_the_fp16_range_falls_back_per_chunk():
     spec, params, arr = load_case("img_mnist_16x7x7")
     x = arr["x"].cuda().clone()
     x[5] *= 1e6                                            # one image of the second chunk leaves the range
-    old = image_engine.IMAGE_CHUNK_ROWS
-    image_engine.IMAGE_CHUNK_ROWS = 49 * 4
+    old = image_engine.IMAGE_CHUNK_ROWS, image_engine.IMAGE_CHUNK_ROWS_PIX
+    image_engine.IMAGE_CHUNK_ROWS = image_engine.IMAGE_CHUNK_ROWS_PIX = 49 * 4
     try:
         z = build_flow(spec, params, precision="fp32").backward(x)
         z_ref = build_flow(spec, params, precision="fp32_tf32").backward(x)
     finally:
-        image_engine.IMAGE_CHUNK_ROWS = old
+        image_engine.IMAGE_CHUNK_ROWS, image_engine.IMAGE_CHUNK_ROWS_PIX = old
     assert bool(torch.isfinite(z).all())
     assert torch.equal(z[4:8], z_ref[4:8])                 # the flagged chunk: exactly the fallback program's result
     assert rel_err(z[:4], z_ref[:4]) <= 3e-6 and not torch.equal(z[:4], z_ref[:4])     # the others: the fp16-split engine

@@ -266,12 +266,12 @@ def test_mnist_config_against_oracle_on_fresh_inputs(mode):
     assert rel_err(flow._forward(z), x) <= 3 * e_rt + 1e-4
     # chunking over images does not change a bit; neither does the host-rows path
     from usflows_b200 import image_engine
-    old = image_engine.IMAGE_CHUNK_ROWS
-    image_engine.IMAGE_CHUNK_ROWS = 49 * 100
+    old = image_engine.IMAGE_CHUNK_ROWS, image_engine.IMAGE_CHUNK_ROWS_PIX
+    image_engine.IMAGE_CHUNK_ROWS = image_engine.IMAGE_CHUNK_ROWS_PIX = 49 * 100
     try:
         assert torch.equal(flow.log_prob(x.cuda()), lp)
     finally:
-        image_engine.IMAGE_CHUNK_ROWS = old
+        image_engine.IMAGE_CHUNK_ROWS, image_engine.IMAGE_CHUNK_ROWS_PIX = old
     assert torch.equal(flow.log_prob_host(x.pin_memory()).cuda(), lp)
     s = flow.sample([32])
     assert s.shape == (32, 16, 7, 7) and bool(torch.isfinite(s).all())

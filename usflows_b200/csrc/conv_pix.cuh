@@ -13,7 +13,8 @@
 // folds them in with scale-input-d 2^-11 at the first hi.hi product, as gemm_tc2.cuh; chains are summed in fp32
 // registers by the epilogue warps.
 //
-// Two epilogues, one thread per pixel (it holds the whole 32-channel row, so LayerNormChannels needs no exchange):
+// Two epilogues; two threads (of two warps) per pixel, 16 channels each -- the LayerNormChannels partial sums of a pixel
+// meet in shared memory -- moving their rows through a per-pair staging block so that global accesses are coalesced:
 //   plain : v = conv + b  [ReLU] [LayerNorm]  -> fp32 rows and / or pixel planes ([ReLU] on the planes), or the masked
 //           coupling update x[r, c] += sign * (1 - mask)[pixel, c] * v[c] of transforms.py:284-290 (last convolution)
 //   gated : u = relu(conv + b) is re-encoded into a shared-memory operand tile and contracted IN THE SAME KERNEL with the
@@ -144,49 +145,7 @@ __device__ __forceinline__ Tile decode_tile(const PixArgs& p, long long tile) {
   return t;
 }
 
-// LayerNorm over the first n channels of a register row (biased variance, as nn.LayerNorm / gate_norm_kernel)
-__device__ __forceinline__ void layer_norm32(float (&v)[32], int n, const float* __restrict__ gamma, const float* __restrict__ beta,
-                                             float eps) {
-  if (n == 32) {                        // all channels (the common case): no per-element predicates, 128-bit constant loads
-    float sum = 0.f;
-#pragma unroll
-    for (int j = 0; j < 32; ++j) sum += v[j];
-    const float mean = sum * (1.f / 32.f);
-    float sq = 0.f;
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const float t = v[j] - mean;
-      sq = fmaf(t, t, sq);
-    }
-    const float rstd = 1.f / sqrtf(sq * (1.f / 32.f) + eps);
-#pragma unroll
-    for (int j = 0; j < 32; j += 4) {
-      const float4 g = *reinterpret_cast<const float4*>(gamma + j);
-      const float4 b = *reinterpret_cast<const float4*>(beta + j);
-      v[j] = (v[j] - mean) * rstd * g.x + b.x;
-      v[j + 1] = (v[j + 1] - mean) * rstd * g.y + b.y;
-      v[j + 2] = (v[j + 2] - mean) * rstd * g.z + b.z;
-      v[j + 3] = (v[j + 3] - mean) * rstd * g.w + b.w;
-    }
-    return;
-  }
-  float sum = 0.f;
-#pragma unroll
-  for (int j = 0; j < 32; ++j) sum += j < n ? v[j] : 0.f;
-  const float mean = sum / (float)n;
-  float sq = 0.f;
-#pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    const float t = j < n ? v[j] - mean : 0.f;
-    sq = fmaf(t, t, sq);
-  }
-  const float rstd = 1.f / sqrtf(sq / (float)n + eps);
-#pragma unroll
-  for (int j = 0; j < 32; ++j)
-    if (j < n) v[j] = (v[j] - mean) * rstd * gamma[j] + beta[j];
-}
-
-// ---- per-warp staging block (32 rows x 128 B of shared memory, 16-byte chunks XOR-swizzled by row & 7 -- the operand
+// ---- staging block of a warp pair (32 rows x 128 B of shared memory, 16-byte chunks XOR-swizzled by row & 7 -- the operand
 // layout of the tensor core, so the same block is the warp's part of the gate's operand tile): the epilogue thread of
 // row `lane` writes / reads its 128 bytes there, and the warp moves the block to / from global memory with 512
 // contiguous bytes per instruction (a thread storing its own row directly touches 32 different 128-byte lines per
@@ -202,60 +161,6 @@ __device__ __forceinline__ void stage_write_chunk(uint32_t stage, int lane, int 
 __device__ __forceinline__ uint4 stage_read_chunk(uint32_t stage, int lane, int c) {
   return ld_shared_u4(stage + (uint32_t)lane * 128u + ((uint32_t)(c ^ (lane & 7)) << 4));
 }
-// block -> global rows at `pitch` bytes, `nch` 16-byte chunks per row, rows < nrows only
-__device__ __forceinline__ void stage_store_rows(uint32_t stage, int lane, uint8_t* g, long long pitch, int nch, int nrows) {
-  __syncwarp();
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int row = 4 * i + (lane >> 3), ch = lane & 7;
-    const uint4 v = ld_shared_u4(stage + (uint32_t)row * 128u + ((uint32_t)(ch ^ (row & 7)) << 4));
-    if (row < nrows && ch < nch) *reinterpret_cast<uint4*>(g + row * pitch + ch * 16) = v;
-  }
-  __syncwarp();
-}
-// rows fetched in the coalesced pattern of stage_store_rows (row 4i + lane / 8, chunk lane % 8) -> block
-__device__ __forceinline__ void stage_put_rows(uint32_t stage, int lane, const uint4 (&v)[8]) {
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int row = 4 * i + (lane >> 3), ch = lane & 7;
-    st_shared_u4(stage + (uint32_t)row * 128u + ((uint32_t)(ch ^ (row & 7)) << 4), v[i]);
-  }
-  __syncwarp();
-}
-__device__ __forceinline__ void stage_write_f32_row(uint32_t stage, int lane, const float (&v)[32]) {
-#pragma unroll
-  for (int c = 0; c < 8; ++c)
-    stage_write_chunk(stage, lane, c, make_uint4(__float_as_uint(v[4 * c]), __float_as_uint(v[4 * c + 1]),
-                                                 __float_as_uint(v[4 * c + 2]), __float_as_uint(v[4 * c + 3])));
-}
-__device__ __forceinline__ void stage_read_f32_row(uint32_t stage, int lane, float (&v)[32]) {
-#pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    const uint4 u = stage_read_chunk(stage, lane, c);
-    v[4 * c] = __uint_as_float(u.x); v[4 * c + 1] = __uint_as_float(u.y);
-    v[4 * c + 2] = __uint_as_float(u.z); v[4 * c + 3] = __uint_as_float(u.w);
-  }
-}
-// pixel planes of a register row (hi chunks 0-3, lo' chunks 4-7); returns whether a value left the fp16 range
-template <bool RELU>
-__device__ __forceinline__ bool stage_write_planes_row_t(uint32_t stage, int lane, const float (&v)[32]) {
-  bool bad = false;
-#pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    float t[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) t[i] = RELU ? fmaxf(v[8 * c + i], 0.f) : v[8 * c + i];
-    uint4 hi, lo;
-    bad |= split8(t, hi, lo);
-    stage_write_chunk(stage, lane, c, hi);
-    stage_write_chunk(stage, lane, c + 4, lo);
-  }
-  return bad;
-}
-__device__ __forceinline__ bool stage_write_planes_row(uint32_t stage, int lane, const float (&v)[32], bool relu) {
-  return relu ? stage_write_planes_row_t<true>(stage, lane, v) : stage_write_planes_row_t<false>(stage, lane, v);
-}
-
 // ---- half rows: the two warps of a pair share one staging block; the thread of (row, half) owns channels 16*half .. +15
 __device__ __forceinline__ void pair_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
 // 16 fp32 channels = chunks 4*half .. 4*half + 3 of the row
@@ -289,7 +194,8 @@ __device__ __forceinline__ bool stage_write_planes_half(uint32_t stage, int lane
   }
   return bad;
 }
-// rows 16*half .. 16*half + 15 of the block -> global (the other 16 rows are the partner warp's)
+// rows 16*half .. 16*half + 15 of the block -> global rows at `pitch` bytes, `nch` 16-byte chunks per row, rows < nrows
+// only (the other 16 rows are the partner warp's); lane l moves chunk l % 8 of row 4i + l / 8: 512 contiguous bytes
 __device__ __forceinline__ void stage_store_rows16(uint32_t stage, int lane, int half, uint8_t* g, long long pitch, int nch, int nrows) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) {

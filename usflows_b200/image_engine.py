@@ -31,6 +31,9 @@ IMPLICIT_CONV = True                # k x k convolutions as implicit GEMMs (usf_
 PIX_CONV = True                     # ... and the whole ConvNet2D on pixel planes (usf_conv2d_pix) where its widths allow it
 PIX_CH = 32                         # channels of a pixel-plane row
 IMAGE_CHUNK_ROWS = 1 << 19          # channels-last rows (N*H*W) per chunk: bounds the im2col workspace (rows x k*k*C)
+IMAGE_CHUNK_ROWS_PIX = 1 << 21      # ... when every conditioner runs on pixel planes (~0.6 KB of workspace per row): fewer,
+                                    # longer launches win over L2 residency (tools/img_chunk_probe.py: 16 384 images as
+                                    # 2^17 / 2^18 / 2^19 / 2^20-row chunks 16.9 / 15.2 / 13.1 / 12.3 ms)
 
 
 def _act(dev, name: str, rows: int, width: int, eng: int) -> Act:
@@ -347,7 +350,8 @@ class ImageProgram:
             return out
         if self.force_fallback:
             return self._fallback().run(x, nchw_out, sink, chunk_rows)
-        per = max(1, (chunk_rows or IMAGE_CHUNK_ROWS) // self.HW)
+        all_pix = all(op[0] != "coupling" or op[1].pix is not None for op in self.ops)
+        per = max(1, (chunk_rows or (IMAGE_CHUNK_ROWS_PIX if all_pix else IMAGE_CHUNK_ROWS)) // self.HW)
         starts = list(range(0, N, per))
         flags = torch.zeros(len(starts), dtype=torch.int32, device=x.device) if self.mode == "fp32" else None
 
