@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define USF_ABI_VERSION 4
+#define USF_ABI_VERSION 5
 
 #define USF_OK 0
 #define USF_ERR_INVALID (-1)     /* bad argument (shape, alignment, null pointer) */
@@ -255,7 +255,7 @@ int usf_im2col(const float* in, int64_t ld_in, int64_t n_images, int32_t h, int3
  * 3 * 32 KB + ceil(K/32) * 2 * (N <= 32 ? 32 : 64) * 128 B exceeds 227 KB (use usf_im2col + usf_linear then). */
 int usf_conv2d_rows(const usf_linear_args* a, const float* act, int64_t ld_act, int64_t n_images, int32_t h, int32_t w,
                     int32_t c_in, int32_t k, int32_t dilation, const float* mask, int32_t relu_in, void* stream);
-/* ---- pixel planes: the ConvNet2D conditioner without gather threads (csrc/conv_pix.cuh) ----------------------------
+/* ---- pixel planes (ABI 5): the ConvNet2D conditioner without gather threads (csrc/conv_pix.cuh) ------------------------
  * An activation with <= 32 channels as [n*h*w, 64] fp16: per pixel 32 high halves | 32 low halves' (x = hi + lo' 2^-11,
  * missing channels zero) = one 128-byte operand row; a k x k tap of 256 pixels is ONE 4-D TMA box (zero padding 'same' by
  * the hardware's out-of-bounds fill).

@@ -196,7 +196,7 @@ def load():
         fn = getattr(lib, name)  # AttributeError if the ABI and this table disagree
         fn.restype = res
         fn.argtypes = args
-    if lib.usf_abi_version() != 4:
+    if lib.usf_abi_version() != 5:
         raise RuntimeError("usflows_b200: ABI version mismatch between _lib.py and the shared library")
     _lib = lib
     return lib
