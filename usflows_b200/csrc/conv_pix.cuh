@@ -322,7 +322,7 @@ conv_pix_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
   // of the chain drains; the threads that read or write activations (producer, epilogue warps) wait for it first.
   griddep_launch_dependents();
 
-  // What the measurements decided (tools/conv_probe.py, profiles/r02_conv_pix.md):
+  // What the measurements decided (tools/conv_probe.py, DESIGN.md 4.3, profiles/r02_conv_pix_probe.log):
   //  * no setmaxnreg (640 threads x 96 registers; the 56 / 224 split of the flat kernels made the issuer re-load its
   //    descriptors from local memory in front of every tcgen05.mma; and setmaxnreg.inc can only take what .dec released
   //    inside the CTA's launch allocation);
