@@ -250,7 +250,7 @@ class Flow(torch.nn.Module):
             base._prepared()                  # parameter-side work happens here, outside any graph capture
             xin = torch.empty(rows, d, dtype=torch.float32, device=dev)
             out = torch.empty(rows, dtype=torch.float32, device=dev)
-            flag = torch.zeros(1, dtype=torch.int32, device=dev) if prog.mode == "fp32" else None
+            flag = torch.zeros(1, dtype=torch.int32, device=dev) if getattr(prog, "uses_range_flag", prog.mode == "fp32") else None
             width = prog.out_width(d)
             if isinstance(prog, image_engine.ImageProgram):
                 fin = image_engine._dense(dev, "img_final_small", rows, d)
