@@ -176,6 +176,18 @@ def test_overflow_flag_and_chain_length():
     _lib.check(_lib.load().usf_set_pix_chain_taps(0))
     for yy in ys[1:]:
         assert rel_err(yy, ys[0]) <= 2e-6
+    # ... and wherever the gate contraction of a tile is issued among the chains of the next one: the same bits
+    for taps in (1, 3):
+        _lib.check(_lib.load().usf_set_pix_chain_taps(taps))
+        base = None
+        for gate_at in (0, 1, 2, 3, 7):
+            _lib.check(_lib.load().usf_set_pix_gate_at(gate_at))
+            yy = y0.clone()
+            ops.conv2d_pix(a2, n2, H, W, 3, 1, w16, b32, 32, gated=True, post_relu=True, w2=w16_2, bias2=b32_2, out_f32=yy)
+            base = yy if base is None else base
+            assert torch.equal(yy, base)
+    _lib.check(_lib.load().usf_set_pix_gate_at(1))
+    _lib.check(_lib.load().usf_set_pix_chain_taps(0))
     flag = torch.zeros(1, dtype=torch.int32, device="cuda")
     p16 = torch.empty(rows, 64, dtype=torch.float16, device="cuda")
     ops.conv2d_pix(a16, n, H, W, 3, 1, w16, (b32 + 1e5).contiguous(), 32, out16=p16, overflow_flag=flag)

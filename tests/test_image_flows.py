@@ -89,6 +89,20 @@ def test_image_program_merges_neighbouring_affine_maps_on_request(fake_ops):
     assert rel_err(lp_m, lp) < 1e-5
 
 
+def test_pixel_plane_route_is_taken_only_where_the_widths_fit(fake_ops):
+    """<= 32 input channels and 32 hidden channels (usf_conv2d_pix's operand row); other conditioners keep the round-1 routes;
+    the tf32-split mode (the fp16-range fallback) never uses fp16 planes."""
+    for name, mode, want in (("img_mnist_16x7x7", "fp32", True), ("img_c32_4x4_noln", "fp32", True), ("img_c4_4x4", "fp32", False),
+                             ("img_c6_5x3_plain_channel", "fp32", False), ("img_mnist_16x7x7", "bf16", True),
+                             ("img_mnist_16x7x7", "fp32_tf32", False), ("img_mnist_16x7x7", "fp32_simt", False)):
+        spec, params, arr = load_case(name)
+        fake_ops.CALLS.clear()
+        build_flow(spec, params, device="cpu", precision=mode).log_prob(arr["x"][:4])
+        names = {c[0] for c in fake_ops.CALLS}
+        assert ("conv2d_pix" in names) == want, (name, mode)
+        assert ("pix_encode" in names) == want
+
+
 def test_image_flow_api_shapes(fake_ops):
     spec, params, arr = load_case("img_c4_4x4")
     flow = build_flow(spec, params, device="cpu")
