@@ -304,22 +304,13 @@ conv_pix_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  if (threadIdx.x >= 128 && threadIdx.x < 128 + 160) {
-    const int i = threadIdx.x - 128;
-    float v = 0.f;
-    if (i < 32) v = p.bias1[i];
-    else if (i < 96) v = p.gated ? p.bias2[i - 32] : 0.f;
-    else if (i < 128) v = (p.gamma && i - 96 < p.n1) ? p.gamma[i - 96] : 0.f;
-    else v = (p.beta && i - 128 < p.n1) ? p.beta[i - 128] : 0.f;
-    s_par[i] = v;
-  }
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
-  // Programmatic dependent launch (common.cuh): everything above -- and the weight load below -- touches only kernel
-  // parameters, per-weight-version constants and this CTA's shared / tensor memory, so it may run while the previous kernel
-  // of the chain drains; the threads that read or write activations (producer, epilogue warps) wait for it first.
+  // Programmatic dependent launch (common.cuh): everything above touches only kernel parameters and this CTA's shared /
+  // tensor memory, so it may run while the previous kernel of the chain drains; every thread that reads or writes global
+  // memory (the producer -- weights included: they may come from the kernel just before --, the epilogue warps) waits first.
   griddep_launch_dependents();
 
   // What the measurements decided (tools/conv_probe.py, DESIGN.md 4.3, profiles/r02_conv_pix_probe.log):
@@ -336,10 +327,10 @@ conv_pix_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     if (warp == 0) {
       // ===================== TMA producer: the weights once, then one box per (tile, tap) =====================
       if (elect_one()) {
+        griddep_wait();
         mbar_expect_tx(wfull_bar, (uint32_t)p.taps * W1_TAP + (p.gated ? W2_BYTES : 0));
         for (int tap = 0; tap < p.taps; ++tap) tma_load_2d(w1_base + (uint32_t)tap * W1_TAP, &tm_w1, wfull_bar, tap * 64, 0);
         if (p.gated) tma_load_2d(w2_base, &tm_w2, wfull_bar, 0, 0);
-        griddep_wait();
         const int half = p.ksize >> 1;
         int stage = 0;
         uint32_t phase = 0;
@@ -446,6 +437,18 @@ conv_pix_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     int acc = 0;
     uint32_t acc_phase = 0, acc2_phase = 0;
     griddep_wait();
+    {                                                    // per-channel constants -> shared memory (the 512 epilogue threads)
+      const int i = threadIdx.x - FIRST_EPI_WARP * 32;
+      if (i < 160) {
+        float v = 0.f;
+        if (i < 32) v = p.bias1[i];
+        else if (i < 96) v = p.gated ? p.bias2[i - 32] : 0.f;
+        else if (i < 128) v = (p.gamma && i - 96 < p.n1) ? p.gamma[i - 96] : 0.f;
+        else v = (p.beta && i - 128 < p.n1) ? p.beta[i - 128] : 0.f;
+        s_par[i] = v;
+      }
+      asm volatile("bar.sync 9, %0;" ::"n"(PIX_EPI_WARPS * 32) : "memory");
+    }
     // The rows a tile's epilogue READS (gated: the residual stream; last convolution: x) are fetched ONE TILE AHEAD, as soon
     // as the previous tile has moved its copy into the staging block (this warp: 16 of the block's 32 rows, 512 contiguous
     // bytes per instruction): issued at the top of their own tile they queued behind the previous tile's stores and their
