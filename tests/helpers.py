@@ -58,3 +58,20 @@ def record_parity(**row):
             f.write(json.dumps(row) + "\n")
     except OSError:
         pass
+
+
+SIMPLIFY_CASES = ["c1_d2_laplace", "d6_hh_normal", "d5_noconj", "d32_h64", "d100_h50_hh", "d64_convnet", "d32_radial_inf",
+                  "img_c4_4x4", "img_mnist_16x7x7", "img_c6_5x3_plain_channel"]
+
+
+def load_simplify_case(name):
+    """Outputs of the REFERENCE's `flow.simplify()` for a golden case (oracle/make_golden_simplify.py)."""
+    z = np.load(os.path.join(GOLDEN, "simplify.npz"))
+    meta = json.loads(bytes(z[name + ":meta"]).decode())
+    return meta, {k: torch.from_numpy(z[f"{name}:{k}"]) for k in ("lp", "z", "y")}
+
+
+def layer_kinds(flow):
+    """Class names of a flow's layers with the wrapped / block transform, as make_golden_simplify.py records them."""
+    return [type(l).__name__ + ("/" + type(l.transform).__name__ if hasattr(l, "transform") else "")
+            + ("/" + type(l.block_transform).__name__ if hasattr(l, "block_transform") else "") for l in flow.layers]

@@ -15,8 +15,8 @@ import math
 import pytest
 import torch
 
-from helpers import (EXT_CASES, IMG_CASES, LARGE_CASES, SMALL_CASES, build_flow, elementwise_err, load_case, record_parity,
-                     rel_err)
+from helpers import (EXT_CASES, IMG_CASES, LARGE_CASES, SIMPLIFY_CASES, SMALL_CASES, build_flow, elementwise_err, layer_kinds,
+                     load_case, load_simplify_case, record_parity, rel_err)
 from oracle import flow_oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -435,3 +435,53 @@ def test_whole_stack_c_entry_equals_the_launch_by_launch_route(name, mode):
         xs = (arr["x"] * 3.0e5).cuda()
         tf = build_flow(spec, params, precision="fp32_tf32")
         assert torch.equal(flow.log_prob(xs), tf.log_prob(xs))
+
+
+@pytest.mark.parametrize("mode", ["fp32", "fp32_simt", "bf16"])
+@pytest.mark.parametrize("name", SIMPLIFY_CASES)
+def test_simplify_matches_the_reference_simplify(name, mode):
+    """`Flow.simplify()` (flows.py:600-606) on the device: the simplified flow has the reference's layer classes and
+    state-dict keys and reproduces the outputs of the REFERENCE's simplified flow (tests/golden/simplify.npz)."""
+    spec, params, arr = load_case(name)
+    meta, want = load_simplify_case(name)
+    flow = build_flow(spec, params, precision=mode)
+    simple = flow.simplify()
+    assert layer_kinds(simple) == meta["layers"]
+    assert list(simple.state_dict().keys()) == meta["state_keys"]
+    assert all(p.is_cuda for p in simple.parameters())
+    x, z0 = arr["x"].cuda(), arr["z0"].cuda()
+    t_lp, t_z = TOL[mode]
+    assert rel_err(simple.log_prob(x), want["lp"]) <= t_lp
+    assert rel_err(simple.backward(x), want["z"]) <= t_z
+    assert rel_err(simple._forward(z0), want["y"]) <= t_z
+    assert rel_err(simple.log_prob(x), flow.log_prob(x)) <= t_lp        # and its own unsimplified flow
+    if len(spec["in_dims"]) == 1:
+        s = simple.sample(torch.Size([5]))
+        assert s.shape == (5, spec["in_dims"][0]) and bool(torch.isfinite(s).all())
+
+
+def test_plane_linear_and_1x1_conv_on_device():
+    """`PlaneBijectiveLinearTransform` / `Bijective1x1Conv2d` built from plain tensors (transforms.py:618-695, 1031-1176)."""
+    import usflows_b200 as U
+    g = torch.Generator().manual_seed(7)
+    d = 48
+    m = torch.randn(d, d, generator=g) / math.sqrt(d) + 2 * torch.eye(d)
+    b = torch.randn(d, generator=g)
+    t = U.PlaneBijectiveLinearTransform(d, m, b, torch.linalg.inv(m)).to("cuda")
+    x = torch.randn(300, d, generator=g)
+    y = t.forward(x.cuda())
+    assert rel_err(y, x.double() @ m.double().t() + b.double()) <= 1e-5
+    assert rel_err(t.backward(y), x) <= 1e-5
+    assert abs(float(t.log_abs_det_jacobian(x, y)) - float(torch.linalg.slogdet(m.double())[1])) <= 1e-4
+    C, H, W = 16, 7, 7
+    w = torch.randn(C, C, generator=g) / math.sqrt(C) + 2 * torch.eye(C)
+    cb = torch.randn(C, generator=g)
+    conv = U.Bijective1x1Conv2d(w.view(C, C, 1, 1), cb)
+    flow = U.Flow(U.Normal(torch.zeros(C, H, W), torch.ones(C, H, W)), [conv], device="cuda")
+    xi = torch.randn(33, C, H, W, generator=g)
+    z = flow.backward(xi.cuda())
+    want = torch.nn.functional.conv2d(xi.double() - cb.double().view(1, C, 1, 1), torch.linalg.inv(w.double()).view(C, C, 1, 1))
+    assert rel_err(z, want) <= 1e-5
+    assert rel_err(flow._forward(z), xi) <= 1e-5
+    lp = torch.distributions.Normal(0.0, 1.0).log_prob(want).sum((1, 2, 3)) - float(torch.linalg.slogdet(w.double())[1]) * H * W
+    assert rel_err(flow.log_prob(xi.cuda()), lp) <= 1e-5

@@ -4,7 +4,8 @@ import pytest
 import torch
 
 import fake_backend
-from helpers import EXT_CASES, IMG_CASES, LARGE_CASES, SMALL_CASES, build_flow, load_case, rel_err
+from helpers import (EXT_CASES, IMG_CASES, LARGE_CASES, SIMPLIFY_CASES, SMALL_CASES, build_flow, layer_kinds, load_case,
+                     load_simplify_case, rel_err)
 
 
 @pytest.mark.parametrize("mode", ["fp32_simt", "fp32", "fp32_tf32", "tf32"])
@@ -206,3 +207,61 @@ def test_replicas_of_the_row_shard_driver_are_independent_and_keep_the_aliasing(
     for n, world in ((10, 3), (7, 8), (0, 2), (65536, 8)):
         cuts = [parallel.shard_bounds(n, r, world) for r in range(world)]
         assert cuts[0][0] == 0 and cuts[-1][1] == n and all(a[1] == b[0] for a, b in zip(cuts, cuts[1:]))
+
+
+@pytest.mark.parametrize("name", SIMPLIFY_CASES)
+def test_simplify_matches_the_reference_simplify(fake_ops, name):
+    """`Flow.simplify()` (flows.py:600-606): same layer classes and state-dict keys as the reference's simplified flow,
+    same log_prob / latents / samples (golden outputs of the reference's simplified flow), and idempotent."""
+    spec, params, arr = load_case(name)
+    meta, want = load_simplify_case(name)
+    flow = build_flow(spec, params, device="cpu", precision="fp32")
+    simple = flow.simplify()
+    assert layer_kinds(simple) == meta["layers"]
+    assert list(simple.state_dict().keys()) == meta["state_keys"]
+    assert rel_err(simple.log_prob(arr["x"]), want["lp"]) < 2e-5
+    assert rel_err(simple.backward(arr["x"]), want["z"]) < 5e-5
+    assert rel_err(simple._forward(arr["z0"]), want["y"]) < 5e-5
+    again = simple.simplify()
+    assert layer_kinds(again) == meta["layers"]
+    assert torch.equal(again.log_prob(arr["x"]), simple.log_prob(arr["x"]))
+    assert simple.is_feasible()
+    assert rel_err(simple.reference_module("log_prob")(arr["x"]), want["lp"]) < 2e-5     # export of a simplified flow
+
+
+def test_plane_linear_and_1x1_conv_built_directly(fake_ops):
+    """`PlaneBijectiveLinearTransform(dim, m, bias, m_inv)` (transforms.py:618-695) and `Bijective1x1Conv2d(weight, bias)`
+    (transforms.py:1031-1176) from plain tensors: forward / backward invert each other, log|det| as the reference's."""
+    import usflows_b200 as U
+    g = torch.Generator().manual_seed(5)
+    d = 6
+    m = torch.randn(d, d, generator=g) + 3 * torch.eye(d)
+    b = torch.randn(d, generator=g)
+    t = U.PlaneBijectiveLinearTransform(d, m, b, torch.linalg.inv(m))
+    x = torch.randn(9, d, generator=g)
+    y = t.forward(x)
+    assert rel_err(y, x @ m.t() + b) < 1e-6
+    assert rel_err(t.backward(y), x) < 1e-5
+    assert abs(float(t.log_abs_det_jacobian(x, y)) - float(torch.linalg.slogdet(m)[1])) < 1e-5
+    assert list(t.state_dict().keys()) == ["forth.weight", "forth.bias", "back.weight", "back.bias"]
+    assert torch.equal(t.matrix(), m) and torch.equal(t.bias(), b)
+    t2 = U.PlaneBijectiveLinearTransform(d, m, b)                # inverse derived here (the reference requires it)
+    assert rel_err(t2.inverse_matrix(), torch.linalg.inv(m)) < 1e-6
+
+    C, H, W = 4, 3, 5
+    w = torch.randn(C, C, generator=g) + 2 * torch.eye(C)
+    cb = torch.randn(C, generator=g)
+    conv = U.Bijective1x1Conv2d(w.view(C, C, 1, 1), cb)
+    xi = torch.randn(7, C, H, W, generator=g)
+    ladj = conv.log_abs_det_jacobian(xi, xi)
+    assert ladj.shape == (7,) and rel_err(ladj, torch.full((7,), float(torch.linalg.slogdet(w)[1]) * H * W)) < 1e-6
+    flow = U.Flow(U.Normal(torch.zeros(C, H, W), torch.ones(C, H, W)), [conv], device="cpu")
+    assert conv.n_blocks == H * W                                # bound from the flow's event shape
+    z = flow.backward(xi)
+    want = torch.nn.functional.conv2d(xi - cb.view(1, C, 1, 1), torch.linalg.inv(w).view(C, C, 1, 1))
+    assert rel_err(z, want) < 1e-5
+    assert rel_err(flow._forward(z), xi) < 1e-5
+    base = torch.distributions.Normal(0.0, 1.0).log_prob(want).sum((1, 2, 3))
+    assert rel_err(flow.log_prob(xi), base - ladj) < 1e-5
+    with pytest.raises(ValueError):
+        U.Bijective1x1Conv2d(torch.zeros(3, 4, 1, 1))

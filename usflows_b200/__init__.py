@@ -13,7 +13,7 @@ from .engine import get_precision, set_chunk_rows, set_precision  # noqa: F401
 from .flows import Flow, USFlow  # noqa: F401
 from .nn import ConvNet, ConvNet2D, DenseNN, GatedConv, GatedMLP, LayerNormChannels, LayerNormVector  # noqa: F401
 from .optim import SophiaG  # noqa: F401
-from .transforms import MaskedAffineCoupling  # noqa: F401
+from .transforms import Bijective1x1Conv2d, MaskedAffineCoupling, PlaneBijectiveLinearTransform  # noqa: F401
 from .transforms import (AffineTransform, BaseTransform, BlockAffineTransform, HouseholderTransform,  # noqa: F401
                          InverseTransform, LeakyReLUTransform, LUTransform, MaskedCoupling, Permute, ScaleTransform,
                          SequentialAffineTransform)

@@ -88,7 +88,7 @@ def _lower_layer(layer, direction: str, out: List[Prim]) -> None:
         return
     if isinstance(layer, T.BlockAffineTransform):
         layer = layer.block_transform
-    if isinstance(layer, T.AffineTransform):
+    if isinstance(layer, (T.AffineTransform, T.Bijective1x1Conv2d)):    # Bijective1x1Conv2d: the C x C map of a 1x1 convolution
         p = layer._prepared()
         if fwd:    # x @ W^T + b                     (transforms.py:913-934)
             out.append(Prim("aff", W=p["matrix64"], c=p["bias"].double()))

@@ -50,8 +50,8 @@ class ReferenceSemantics(torch.nn.Module):
                 layer = layer.transform
             self.inverted.append(inv)
             start = count
-            if isinstance(layer, T.BlockAffineTransform):
-                W, Winv, b, ladj = _affine_tensors(layer.block_transform)
+            if isinstance(layer, (T.BlockAffineTransform, T.Bijective1x1Conv2d)):
+                W, Winv, b, ladj = _affine_tensors(getattr(layer, "block_transform", layer))
                 self.kinds.append("affine")
                 for t in (W, Winv, b, ladj * layer.n_blocks):
                     reg(t)

@@ -17,7 +17,7 @@ import torch
 from . import engine, image_engine, ops
 from .distributions import DistributionModule, Independent
 from .transforms import MaskedAffineCoupling
-from .transforms import (BaseTransform, BlockAffineTransform, HouseholderTransform, InverseTransform, LUTransform,
+from .transforms import (BaseTransform, Bijective1x1Conv2d, BlockAffineTransform, HouseholderTransform, InverseTransform, LUTransform,
                          MaskedCoupling, ScaleTransform, SequentialAffineTransform)
 
 
@@ -117,8 +117,22 @@ class Flow(torch.nn.Module):
         if len(batch_shape) > 0:                                   # flows.py:97-101
             self.base_distribution = Independent(self.base_distribution, len(batch_shape))
         self._programs: Dict[str, Any] = {}
+        ev = tuple(self._event_shape())
+        if len(ev) == 3:                    # a Bijective1x1Conv2d's log|det| counts the pixels of the event (its own
+            for l in layers:                # forward sees them on the tensor; the launch program needs them up front)
+                while isinstance(l, InverseTransform):
+                    l = l.transform
+                if isinstance(l, Bijective1x1Conv2d) and l.n_blocks is None:
+                    l.n_blocks = ev[1] * ev[2]
 
     # -- reference API ---------------------------------------------------------------------------
+    def simplify(self) -> "Flow":
+        """The same flow with every LU / Householder / sequential affine layer replaced by its plain matrix form
+        (`PlaneBijectiveLinearTransform`, `Bijective1x1Conv2d` for image-shaped events): flows.py:600-606.  The result
+        stays on this flow's device and keeps its precision mode (the reference's lands on its default device)."""
+        return Flow(self.base_distribution, [l.simplify() for l in self.layers], device=self.device,
+                    precision=self.precision)
+
     def forward(self, x: torch.Tensor):
         """Export-mode dispatch (flows.py:30-43)."""
         if self.export == "log_prob":

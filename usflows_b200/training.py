@@ -119,6 +119,12 @@ def affine_parts(t, cache: Optional[dict] = None):
         Linv = torch.linalg.solve_triangular(L, _eye(d, L), upper=False, unitriangular=True)
         Uinv = torch.linalg.solve_triangular(U, _eye(d, U), upper=True)
         return L @ U, Uinv @ Linv, t.bias_vector, t.U_raw.diagonal().abs().log().sum()
+    if isinstance(t, T.PlaneBijectiveLinearTransform):            # given tensors (transforms.py:618-695); not meant to be trained
+        return t.forth.weight, t.back.weight, t.forth.bias, t.ladj
+    if isinstance(t, T.Bijective1x1Conv2d):                       # transforms.py:1031-1176, per pixel
+        C = t.in_channels
+        b = t.forward_conv.bias if t.forward_conv.bias is not None else t.forward_conv.weight.new_zeros(C)
+        return t.forward_conv.weight.reshape(C, C), t.inverse_conv.weight.reshape(C, C), b, t.ladj
     if isinstance(t, T.HouseholderTransform):
         W = t.w_0
         for k in range(t.nvs):
@@ -146,8 +152,8 @@ def _layer_backward(layer, y: torch.Tensor, inverse: bool = False, cache: Option
     if isinstance(layer, T.InverseTransform):
         x, ladj = _layer_backward(layer.transform, y, not inverse, cache, geom)
         return x, -ladj
-    if isinstance(layer, T.BlockAffineTransform):
-        W, Winv, b, ladj = affine_parts(layer.block_transform, cache)
+    if isinstance(layer, (T.BlockAffineTransform, T.Bijective1x1Conv2d)):
+        W, Winv, b, ladj = affine_parts(getattr(layer, "block_transform", layer), cache)
         ladj = ladj * layer.n_blocks
         if inverse:                                     # the layer's forward: x W^T + b      (transforms.py:913-934)
             return linear(y, W, b), ladj

@@ -210,6 +210,79 @@ class AffineTransform(BaseTransform):
     def _ladj_device(self):
         return self._prepared()["ladj"]
 
+    def _to_plane_linear(self) -> "PlaneBijectiveLinearTransform":
+        """The same map as a plain (W, b, W^-1) layer (transforms.py:732-747).  The prepared log|det| of this layer
+        travels with it instead of being re-derived by a dense `slogdet` of W."""
+        p = self._prepared()
+        bias = p["bias"].clone()
+        if isinstance(self, LUTransform):                  # its bias() IS the `bias_vector` parameter (:1295-1297)
+            bias = nn.Parameter(bias)
+        return PlaneBijectiveLinearTransform(self.dim, p["matrix"].clone(), bias, p["inverse_matrix"].clone(),
+                                             ladj=p["ladj"][0].clone())
+
+    def simplify(self):
+        return self._to_plane_linear()                                         # transforms.py:749-750
+
+
+class PlaneBijectiveLinearTransform(AffineTransform):
+    """y = W x + b with W, b and W^-1 given as plain tensors (transforms.py:618-695): what `simplify()` turns every LU /
+    Householder / sequential affine layer into for verification back ends.  Holds the reference's modules (`forth`, `back`:
+    state-dict keys `forth.weight`, `forth.bias`, `back.weight`, `back.bias`); not meant to be trained, bijectivity is
+    not enforced.  `log|det W|` is a construction-time constant as in the reference (`slogdet` there, `:653-654`); pass
+    `ladj` when it is known (the LU layers know theirs exactly).  The reference requires `m_inv`; here a missing one is
+    computed once at construction."""
+
+    volume_preserving = False
+
+    def __init__(self, dim: int, m: torch.Tensor, bias: torch.Tensor, m_inv: Optional[torch.Tensor] = None, *,
+                 ladj: Optional[torch.Tensor] = None):
+        super().__init__(dim)
+        bias_is_parameter = isinstance(bias, nn.Parameter)
+        m, bias = m.detach(), bias.detach()
+        if tuple(m.shape) != (dim, dim) or tuple(bias.shape) != (dim,):
+            raise ValueError("m must be [dim, dim] and bias [dim]")
+        with torch.no_grad():
+            m_inv = torch.linalg.inv(m.double()).to(m.dtype) if m_inv is None else m_inv.detach()
+            if ladj is None:
+                ladj = torch.linalg.slogdet(m.double())[1].to(m.dtype)
+            back_bias = -(m_inv.double() @ bias.double()).to(m.dtype)          # :649
+        # `self.bias_vector = bias` (:639): a parameter (and a state-dict key) exactly when the caller hands one in, which
+        # the reference's LUTransform.bias() does and its SequentialAffineTransform.bias() does not
+        self.bias_vector = nn.Parameter(bias) if bias_is_parameter else bias
+        self.forth = nn.Linear(dim, dim, bias=True)
+        self.forth.weight = nn.Parameter(m)
+        self.forth.bias = nn.Parameter(bias)
+        self.back = nn.Linear(dim, dim, bias=True)
+        self.back.weight = nn.Parameter(m_inv)
+        self.back.bias = nn.Parameter(back_bias)
+        self.register_buffer("ladj", torch.as_tensor(ladj, dtype=m.dtype).detach().reshape(()).to(m.device),
+                             persistent=False)
+
+    @property
+    def m_inv(self) -> torch.Tensor:
+        return self.back.weight
+
+    def _prep_params(self) -> List[torch.Tensor]:
+        return [self.forth.weight, self.forth.bias, self.back.weight]
+
+    def _prepare(self) -> dict:
+        W, Winv = self.forth.weight.detach().contiguous(), self.back.weight.detach().contiguous()
+        ladj = torch.stack([self.ladj.to(W.device, torch.float32), torch.zeros((), dtype=torch.float32, device=W.device)])
+        return dict(matrix=W, inverse_matrix=Winv, bias=self.forth.bias.detach(), ladj=ladj,
+                    matrix64=W.double(), inverse64=Winv.double())
+
+    def log_abs_det_jacobian(self, x=None, y=None, context=None):
+        return self.ladj
+
+    def matrix(self) -> torch.Tensor:
+        return self.forth.weight
+
+    def inverse_matrix(self) -> torch.Tensor:
+        return self.back.weight
+
+    def bias(self) -> torch.Tensor:
+        return self.forth.bias
+
     def simplify(self):
         return self
 
@@ -419,6 +492,113 @@ class BlockAffineTransform(BaseTransform):
     def to(self, device):
         self.block_transform.to(device)
         return super().to(device)
+
+    def _to_block_plane_linear(self) -> "BlockAffineTransform":
+        return BlockAffineTransform(self.in_dims, self.block_transform._to_plane_linear())     # transforms.py:993-1002
+
+    def simplify(self):
+        """Plain-matrix form (transforms.py:1004-1020): a `Bijective1x1Conv2d` for `[C, H, W]` events, else a block of a
+        `PlaneBijectiveLinearTransform`."""
+        if len(self.in_dims) == 3:
+            p = self.block_transform._prepared()
+            C = self.block_size
+            return Bijective1x1Conv2d(p["matrix"].clone().view(C, C, 1, 1), p["bias"].clone().view(C),
+                                      inv_weight=p["inverse_matrix"].clone().view(C, C, 1, 1), ladj=p["ladj"][0].clone(),
+                                      n_blocks=self.n_blocks)
+        return self._to_block_plane_linear()
+
+
+class Bijective1x1Conv2d(BaseTransform):
+    """y = W * x + b as a 1x1 convolution with given weights (transforms.py:1031-1176): the `[C, H, W]` counterpart of
+    `PlaneBijectiveLinearTransform`.  Buffers `weight [C, C, 1, 1]`, `bias [C]`, `inv_weight`, and the reference's
+    `forward_conv` / `inverse_conv` modules as parameter holders (same state-dict keys); runs as the C x C contraction
+    over channels-last rows like `BlockAffineTransform`.  log|det J| = H * W * log|det W| (`:1128-1146`): `H * W` comes
+    from the tensor when `log_abs_det_jacobian` is called with one, from `n_blocks` (set by `simplify()` or by the
+    `Flow` that holds the layer, from its event shape) inside a flow.  `inv_weight` / `ladj` / `n_blocks` are
+    extensions: the reference re-derives the first two with `torch.inverse` / `slogdet` (the default here as well)."""
+
+    def __init__(self, weight: torch.Tensor, bias: Optional[torch.Tensor] = None, *,
+                 inv_weight: Optional[torch.Tensor] = None, ladj: Optional[torch.Tensor] = None,
+                 n_blocks: Optional[int] = None):
+        super().__init__()
+        weight = weight.detach()
+        if weight.dim() != 4 or weight.shape[2] != 1 or weight.shape[3] != 1:
+            raise ValueError("Weight must be 4D tensor with shape (C, C, 1, 1)")
+        self.in_channels, self.out_channels = weight.shape[1], weight.shape[0]
+        if self.in_channels != self.out_channels:
+            raise ValueError("Input and output channels must be equal for bijective 1x1 conv")
+        C = self.in_channels
+        self.dim = self.block_size = C
+        self.n_blocks = n_blocks
+        with torch.no_grad():
+            w2 = weight.reshape(C, C)
+            if inv_weight is None:
+                inv_weight = torch.linalg.inv(w2.double()).to(weight.dtype).view(C, C, 1, 1)       # :1092-1101
+            if ladj is None:
+                ladj = torch.linalg.slogdet(w2.double())[1].to(weight.dtype)                       # :1139-1140
+        self.register_buffer("weight", weight)
+        self.register_buffer("bias", None if bias is None else bias.detach())
+        self.register_buffer("inv_weight", inv_weight.detach())
+        self.forward_conv = nn.Conv2d(C, C, kernel_size=1, bias=False)
+        self.forward_conv.weight = nn.Parameter(self.weight)
+        if bias is not None:
+            self.forward_conv.bias = nn.Parameter(self.bias)
+        self.inverse_conv = nn.Conv2d(C, C, kernel_size=1, bias=False)
+        self.inverse_conv.weight = nn.Parameter(self.inv_weight)
+        self.register_buffer("ladj", torch.as_tensor(ladj, dtype=weight.dtype).detach().reshape(()).to(weight.device),
+                             persistent=False)
+
+    def _prepared(self) -> dict:
+        """Same contract as `AffineTransform._prepared` (per-pixel C x C map; `ladj` is per block).  Read from the
+        parameters the reference's forward / backward use (`forward_conv`, `inverse_conv`)."""
+        C = self.in_channels
+        fw, iw, fb = self.forward_conv.weight, self.inverse_conv.weight, self.forward_conv.bias
+        key = _versions([fw, iw] + ([] if fb is None else [fb]))
+        if getattr(self, "_prep_key", None) != key:
+            ops.require_cuda(fw, "Bijective1x1Conv2d.forward_conv.weight")
+            W, Winv = fw.detach().reshape(C, C).contiguous(), iw.detach().reshape(C, C).contiguous()
+            b = torch.zeros(C, dtype=W.dtype, device=W.device) if fb is None else fb.detach()
+            ladj = torch.stack([self.ladj.to(W.device, torch.float32), torch.zeros((), dtype=torch.float32, device=W.device)])
+            self._prep_cache = dict(matrix=W, inverse_matrix=Winv, bias=b, ladj=ladj, matrix64=W.double(),
+                                    inverse64=Winv.double())
+            self._prep_key = key
+        return self._prep_cache
+
+    def log_abs_det_jacobian(self, x=None, y=None, context=None):
+        if x is not None and x.dim() == 4:                       # per batch element, as the reference (:1142-1146)
+            return self.ladj * (x.shape[2] * x.shape[3]) * torch.ones(x.shape[0], device=x.device)
+        if self.n_blocks is None:
+            raise RuntimeError("Bijective1x1Conv2d: the spatial size is unknown (pass x, or set n_blocks)")
+        return self.ladj * self.n_blocks
+
+    def _ladj_device(self):
+        if self.n_blocks is None:
+            raise RuntimeError("Bijective1x1Conv2d: the spatial size is unknown (set n_blocks = H * W)")
+        ladj = self._prepared()["ladj"]
+        return ladj * torch.tensor([float(self.n_blocks), 1.0], device=ladj.device)
+
+    def sign(self):
+        return torch.linalg.slogdet(self.forward_conv.weight.detach().reshape(self.dim, self.dim).double())[0]
+
+    def is_feasible(self) -> bool:
+        return bool(torch.isfinite(self.ladj)) and float(self.ladj) > math.log(1e-6)               # |det W| > 1e-6 (:1148-1151)
+
+    def update_inverse_weight(self) -> None:
+        """Inverse and log|det| re-derived from the forward weight (:1092-1101)."""
+        C = self.in_channels
+        with torch.no_grad():
+            w2 = self.forward_conv.weight.detach().reshape(C, C).double()
+            inv = torch.linalg.inv(w2).to(self.weight.dtype).view(C, C, 1, 1)
+            self.inverse_conv.weight.copy_(inv)
+            self.inv_weight.copy_(inv)
+            self.ladj.copy_(torch.linalg.slogdet(w2)[1].to(self.weight.dtype))
+
+    def add_jitter(self, jitter: float = 1e-6) -> None:
+        """weight += jitter * I, inverse and log|det| re-derived (`jitter`, :1153-1168)."""
+        with torch.no_grad():
+            self.forward_conv.weight.reshape(self.in_channels, -1).diagonal().add_(jitter)
+            self.weight.copy_(self.forward_conv.weight)
+        self.update_inverse_weight()
 
 
 class InverseTransform(BaseTransform):
