@@ -304,9 +304,45 @@ def convnet2d(x: Tensor, prefix: str, params, spec: dict) -> Tensor:
     return F.conv2d(h, params[f"{prefix}nn.{idx}.weight"], params[f"{prefix}nn.{idx}.bias"], padding="same")
 
 
+def convnet_spatial(x: Tensor, prefix: str, params, spec: dict) -> Tensor:
+    """networks.ConvNet.forward for in_dims=[C, H, W] (networks.py:390-403) over the module list built at :308-377:
+    Conv k x k (C, h0) -> per hidden width [GatedConvND (:142-203; residual projected by a 1x1 convolution when the width
+    changes) | Conv k x k] -> nonlinearity -> [LayerNormChannelsND (:122-140)] -> Conv k x k (h_last, C); padding k // 2."""
+    c_hidden = list(spec["c_hidden"])
+    gating, normalize = spec.get("gating", True), spec.get("normalize_layers", True)
+    pad = int(spec.get("kernel_size", 3)) // 2
+    h = F.conv2d(x, params[f"{prefix}nn.0.weight"], params[f"{prefix}nn.0.bias"], padding=pad)
+    idx = 1
+    for i, out_ch in enumerate(c_hidden):
+        in_ch = c_hidden[i - 1] if i > 0 else c_hidden[0]
+        q = f"{prefix}nn.{idx}."
+        if gating:                                               # GatedConvND.forward, networks.py:196-203
+            out = F.conv2d(F.relu(h), params[q + "net.1.weight"], params[q + "net.1.bias"], padding=pad)
+            out = F.conv2d(F.relu(out), params[q + "net.3.weight"], params[q + "net.3.bias"])
+            val, gate = out.chunk(2, dim=1)
+            res = val * torch.sigmoid(gate)
+            if in_ch != out_ch:
+                h = F.conv2d(h, params[q + "proj.weight"], params[q + "proj.bias"])
+            h = h + res
+        else:
+            h = F.conv2d(h, params[q + "weight"], params[q + "bias"], padding=pad)
+        h = F.relu(h)
+        idx += 2
+        if normalize:                                            # LayerNormChannelsND.forward, networks.py:134-140
+            q = f"{prefix}nn.{idx}."
+            mean = h.mean(dim=1, keepdim=True)
+            var = h.var(dim=1, unbiased=False, keepdim=True)
+            h = (h - mean) / torch.sqrt(var + 1e-5)
+            h = h * params[q + "gamma"] + params[q + "beta"]
+            idx += 1
+    return F.conv2d(h, params[f"{prefix}nn.{idx}.weight"], params[f"{prefix}nn.{idx}.bias"], padding=pad)
+
+
 def conditioner(x: Tensor, layer: dict, params, n_layers: int, spec=None) -> Tensor:
     if spec is not None and spec.get("conditioner") == "convnet2d":
         return convnet2d(x, layer["prefix"], params, spec)
+    if spec is not None and spec.get("conditioner") == "convnet" and len(spec["in_dims"]) == 3:
+        return convnet_spatial(x, layer["prefix"], params, spec)
     if spec is not None and spec.get("conditioner") == "convnet":
         return convnet_vector(x, layer["prefix"], params, spec)
     return dense_nn(x, layer["prefix"], params, n_layers)
@@ -700,6 +736,30 @@ def random_params(spec: dict, seed: int = 0, min_abs_scale: float = 0.1) -> Dict
                     out[f"{p}nn.{idx}.beta"] = uni((1, ch, 1, 1), 0.2)
                     idx += 1
             conv(f"nn.{idx}", d0, ch, k)
+        elif layer["kind"] == "coupling" and spec.get("conditioner") == "convnet" and len(in_dims) == 3:
+            def conv(name, n_out, n_in, k):
+                bound = 1 / math.sqrt(n_in * k * k)
+                out[f"{p}{name}.weight"] = uni((n_out, n_in, k, k), bound)
+                out[f"{p}{name}.bias"] = uni((n_out,), bound)
+
+            ch, k = [int(c) for c in spec["c_hidden"]], int(spec.get("kernel_size", 3))
+            conv("nn.0", ch[0], d0, k)
+            idx = 1
+            for i, oc in enumerate(ch):
+                ic = ch[i - 1] if i > 0 else ch[0]
+                if spec.get("gating", True):
+                    conv(f"nn.{idx}.net.1", oc, ic, k)
+                    conv(f"nn.{idx}.net.3", 2 * oc, oc, 1)
+                    if ic != oc:
+                        conv(f"nn.{idx}.proj", oc, ic, 1)
+                else:
+                    conv(f"nn.{idx}", oc, ic, k)
+                idx += 2
+                if spec.get("normalize_layers", True):
+                    out[f"{p}nn.{idx}.gamma"] = 1 + uni((1, oc, 1, 1), 0.2)
+                    out[f"{p}nn.{idx}.beta"] = uni((1, oc, 1, 1), 0.2)
+                    idx += 1
+            conv(f"nn.{idx}", d0, ch[-1], k)
         elif layer["kind"] == "coupling" and spec.get("conditioner") == "convnet":
             def lin(name, n_out, n_in):
                 bound = 1 / math.sqrt(n_in)

@@ -15,7 +15,9 @@ LARGE_CASES = ["c2_d784", "c4_d3072_b2"]
 EXT_CASES = ["d64_convnet", "d64_convnet_proj_radial2", "d40_convnet_plain_gmm1", "d64_convnet_noln", "d32_radial_inf",
              "d784_radial1_lognormal"]
 # image-shaped events [C, H, W] (1x1-convolution BlockAffine, ConvNet2D conditioners, [C, H, W] masks)
-IMG_CASES = ["img_c4_4x4", "img_mnist_16x7x7", "img_c6_5x3_plain_channel", "img_c32_4x4_noln"]
+IMG_CASES = ["img_c4_4x4", "img_mnist_16x7x7", "img_c6_5x3_plain_channel", "img_c32_4x4_noln",
+             # networks.ConvNet's convolutional branch (networks.py:308-377) as the conditioner
+             "img_convnet_c4_4x4_proj", "img_convnet_c6_5x3_plain", "img_convnet_16x7x7"]
 
 
 def load_case(name):

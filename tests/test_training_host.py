@@ -27,7 +27,7 @@ def _oracle_grads(spec, params, x):
     return float(loss), {k: v.grad for k, v in p.items() if v.grad is not None}
 
 
-@pytest.mark.parametrize("name", ["d6_hh_normal", "d32_h64", "d100_h50_hh"])
+@pytest.mark.parametrize("name", ["d6_hh_normal", "d32_h64", "d100_h50_hh", "img_c4_4x4", "img_convnet_c4_4x4_proj"])
 def test_loss_and_gradients_match_the_oracle(fake_ops, name):
     from usflows_b200 import training
     spec, params, arr = load_case(name)

@@ -28,8 +28,8 @@ def build_flow(spec, params=None, device="cuda", precision=None):
                          gating=spec.get("gating", True))
     elif spec.get("conditioner") == "convnet":
         cond_cls = U.ConvNet
-        cond_args = dict(in_dims=[d], c_hidden=list(spec["c_hidden"]), gating=spec.get("gating", True),
-                         normalize_layers=spec.get("normalize_layers", True))
+        cond_args = dict(in_dims=list(spec["in_dims"]), c_hidden=list(spec["c_hidden"]), gating=spec.get("gating", True),
+                         normalize_layers=spec.get("normalize_layers", True), kernel_size=spec.get("kernel_size", 3))
     else:
         cond_cls = U.DenseNN
         cond_args = dict(input_dim=d, hidden_dims=list(spec["hidden_dims"]),

@@ -138,6 +138,11 @@ class ReferenceSemantics(torch.nn.Module):
                     lin(blk["conv1"], "conv")
                     plan.append(("relu", 0, 0))
                     lin(blk["conv2"], "conv")
+                    if blk.get("proj") is not None:          # GatedConvND whose width changes (networks.py:186-201)
+                        reg(blk["proj"].weight)
+                        reg(blk["proj"].bias)
+                        plan.append(("proj_conv", n[0], 0))
+                        n[0] += 2
                     plan.append(("gate", 0, 0))
                 else:
                     lin(blk["conv1"], "conv")
@@ -186,6 +191,8 @@ class ReferenceSemantics(torch.nn.Module):
                 saved = h
             elif op == "proj":
                 saved = F.linear(saved, ts[i], ts[i + 1])
+            elif op == "proj_conv":
+                saved = F.conv2d(saved, ts[i], ts[i + 1])
             elif op == "gate":
                 val, gate = h.chunk(2, dim=1)
                 h = saved + val * torch.sigmoid(gate)

@@ -117,9 +117,10 @@ class _ConvNet2DPlan:
                                                b["ln"].beta.detach().reshape(-1).contiguous(), float(b["ln"].eps))
             g1 = _Gemm(mode, _conv_weight(b["conv1"]), b["conv1"].bias.detach(), wflag, conv_cin=cin(b["conv1"]))
             g2 = None if not b["gated"] else _Gemm(mode, _conv_weight(b["conv2"]), b["conv2"].bias.detach(), wflag)
-            self.blocks.append((b["gated"], g1, g2, ln))
+            gp = None if b.get("proj") is None else _Gemm(mode, _conv_weight(b["proj"]), b["proj"].bias.detach(), wflag)
+            self.blocks.append((b["gated"], g1, g2, ln, gp))
         self.last = _Gemm(mode, _conv_weight(d["last"]), d["last"].bias.detach(), wflag, pad_n=True, conv_cin=cin(d["last"]))
-        self.gemms = [self.first, self.last] + [g for b in self.blocks for g in b[1:3] if g is not None]
+        self.gemms = [self.first, self.last] + [g for b in self.blocks for g in (b[1], b[2], b[4]) if g is not None]
         self.pix = None
         if self._pix_ok(mode, d, H, W):
             self._prepare_pix(d, wflag)
@@ -134,7 +135,7 @@ class _ConvNet2DPlan:
         widths = [d["first"].weight.shape[1] <= PIX_CH, d["first"].weight.shape[0] == PIX_CH,
                   d["last"].weight.shape[1] == PIX_CH, d["last"].weight.shape[0] <= PIX_CH, d["last"].weight.shape[0] % 4 == 0]
         for b in d["blocks"]:
-            widths += [tuple(b["conv1"].weight.shape[:2]) == (PIX_CH, PIX_CH)]
+            widths += [tuple(b["conv1"].weight.shape[:2]) == (PIX_CH, PIX_CH), b.get("proj") is None]
             if b["gated"]:
                 widths += [tuple(b["conv2"].weight.shape[:2]) == (2 * PIX_CH, PIX_CH)]
         return all(widths)
@@ -211,14 +212,24 @@ class _ConvNet2DPlan:
         f32 = lambda name, width: Act(rows, width, f32=_workspace.planes(dev, name, rows, width, "f32"))   # noqa: E731
         y = f32("img_y", self.first.N)                       # residual stream of the conditioner
         conv(x_rows, self.c_in, self.first, y, mask=mask_cl)
-        for gated, g1, g2, ln in self.blocks:
+        for gated, g1, g2, ln, gp in self.blocks:
             gamma, beta, eps = ln if ln is not None else (None, None, 0.0)
             if gated:                                        # GatedConv (networks.py:100-121) -> ReLU -> LayerNormChannels
                 hid = _act(dev, "img_h", rows, g1.N, g2.engine)
                 conv(y.f32, g1.K // (k * k), g1, hid, relu_in=True, relu_out=True)
                 vg = f32("img_st", g2.N)
                 g2(hid, vg, flag=flag)
-                ops.gate_norm(vg.f32, g1.K // (k * k), xres=y.f32, gated=True, pre_relu=True, gamma=gamma, beta=beta,
+                n = g2.n_true // 2                           # block width: c_in of a GatedConv, c_out of a GatedConvND
+                if gp is not None:                           # GatedConvND whose width changes: residual = proj(x), a 1x1
+                    cols = _act(dev, "img_cols", rows, gp.K, gp.engine)            # convolution (networks.py:186-201)
+                    ops.im2col(y.f32, n_images, H, W, gp.K, 1, 1, cols, overflow_flag=flag)
+                    res = f32("img_r", gp.N)
+                    gp(cols, res, flag=flag)
+                    y = f32("img_y", n)                      # the old residual stream has been consumed (conv1, proj)
+                    ops.gate_norm(vg.f32, n, xres=res.f32, gated=True, pre_relu=True, gamma=gamma, beta=beta, eps=eps,
+                                  y_f32=y.f32)
+                    continue
+                ops.gate_norm(vg.f32, n, xres=y.f32, gated=True, pre_relu=True, gamma=gamma, beta=beta,
                               eps=eps, y_f32=y.f32)
             else:                                            # Conv k x k -> ReLU -> LayerNormChannels
                 o = f32("img_st", g1.N)

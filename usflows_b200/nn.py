@@ -67,7 +67,8 @@ class ConvNet(torch.nn.Module):
     -> Linear(h_last, c_out), same constructor arguments and state-dict names (`nn.{i}. ...`) as the reference
     (networks.py:262-307).  A parameter container: inside a `MaskedCoupling` its contractions run on the tcgen05 /
     SIMT kernels and the gate / LayerNorm glue on `usf_gate_norm`; calling the module evaluates it through the same
-    kernels.  Spatial in_dims (the convolutional branch, networks.py:308-377) are not built."""
+    kernels.  `in_dims=[C, H, W]` builds the convolutional branch (networks.py:308-377; 2-D only), which runs like a
+    `ConvNet2D` (image_engine.py) with per-block widths and residual projections."""
 
     def __init__(self, in_dims, c_hidden, c_out: int = -1, nonlinearity=torch.nn.ReLU(), kernel_size: int = 3,
                  stride: int = 1, dilation: int = 1, padding=None, normalize_layers: bool = True, gating: bool = True):
@@ -77,12 +78,14 @@ class ConvNet(torch.nn.Module):
             in_dims = list(in_dims)
         except TypeError:
             raise ValueError("in_dims must be an iterable like [C, H, W] or [C] for vector")
-        if len(in_dims) != 1:
-            raise NotImplementedError("usflows_b200.nn.ConvNet: only the vector branch (in_dims=[d]) is built")
         c_in = int(in_dims[0])
         c_out = c_out if c_out > 0 else c_in
         assert len(c_hidden) > 0 and all(h > 0 for h in c_hidden), "c_hidden must be non-empty list of positive ints"
         hidden = [int(h) for h in c_hidden]
+        if len(in_dims) != 1:
+            self._build_spatial(in_dims, c_in, hidden, c_out, nonlinearity, kernel_size, stride, dilation, padding,
+                                normalize_layers, gating)
+            return
         layers = [torch.nn.Linear(c_in, hidden[0])]
         for i, out_ch in enumerate(hidden):
             in_ch = hidden[i - 1] if i > 0 else hidden[0]
@@ -97,8 +100,40 @@ class ConvNet(torch.nn.Module):
         self.is_vector = True
         self._vector_in_features = c_in
 
+    def _build_spatial(self, in_dims, c_in, hidden, c_out, nonlinearity, kernel_size, stride, dilation, padding,
+                       normalize_layers, gating) -> None:
+        """The convolutional branch (networks.py:308-377) for `in_dims=[C, H, W]`: Conv k x k (C, h0) -> [GatedConvND |
+        Conv k x k -> ReLU -> LayerNormChannelsND]* -> Conv k x k (h_last, c_out); a block whose width changes projects
+        its residual with a 1x1 convolution (networks.py:186-201).  Same state-dict names as the reference."""
+        if len(in_dims) != 3:
+            raise NotImplementedError("usflows_b200.nn.ConvNet: in_dims=[d] (vector) and [C, H, W] (2-D convolutions) are built")
+        if padding is None:
+            padding = kernel_size // 2
+        if stride != 1 or kernel_size % 2 != 1 or not (padding == "same" or padding == (kernel_size // 2) * dilation):
+            raise NotImplementedError("usflows_b200.nn.ConvNet: stride 1, odd kernel_size and 'same'-sized padding only")
+        conv = lambda i, o: torch.nn.Conv2d(i, o, kernel_size=kernel_size, padding=padding, stride=stride,   # noqa: E731
+                                            dilation=dilation)
+        layers = [conv(c_in, hidden[0])]
+        for i, out_ch in enumerate(hidden):
+            in_ch = hidden[i - 1] if i > 0 else hidden[0]
+            if gating:
+                layers += [GatedConvND(in_ch, out_ch, kernel_size=kernel_size, padding=padding, stride=stride,
+                                       dilation=dilation, nonlinearity=nonlinearity, input_rank=2), nonlinearity]
+            else:
+                layers += [conv(in_ch, out_ch), nonlinearity]
+            if normalize_layers:
+                layers += [LayerNormChannelsND(out_ch, num_spatial_dims=2)]
+        layers += [conv(hidden[-1], c_out)]
+        self.nn = torch.nn.Sequential(*layers)
+        self.is_vector = False
+        self._spatial_rank = 2
+        self.kernel_size, self.dilation = kernel_size, dilation
+
     def _describe(self) -> dict:
-        """Structure of the network as the engine's planner reads it: first / last Linear and the hidden blocks."""
+        """Structure of the network as the engine's planner reads it: first / last Linear and the hidden blocks (the
+        spatial branch answers in `ConvNet2D._describe`'s format, with `proj` per block)."""
+        if not self.is_vector:
+            return _describe_conv_stack(self.nn, self.kernel_size, self.dilation)
         mods = list(self.nn)
         blocks, i = [], 1
         while i < len(mods) - 1:
@@ -115,6 +150,9 @@ class ConvNet(torch.nn.Module):
         return dict(first=mods[0], blocks=blocks, last=mods[-1])
 
     def forward(self, x: torch.Tensor, context=None) -> torch.Tensor:
+        if not self.is_vector:
+            from . import image_engine
+            return image_engine.run_convnet2d(self, x)
         from . import engine
         if x.dim() == 3 and x.shape[-1] == 1:
             x = x.reshape(x.shape[0], x.shape[1])
@@ -147,6 +185,55 @@ class GatedConv(torch.nn.Module):
             nonlinearity, torch.nn.Conv2d(c_in, c_hidden, kernel_size=kernel_size, padding=padding, stride=stride,
                                           dilation=dilation),
             nonlinearity, torch.nn.Conv2d(c_hidden, 2 * c_in, kernel_size=1, padding=0))
+
+
+class LayerNormChannelsND(torch.nn.Module):
+    """Parameter container of the channel LayerNorm of `networks.ConvNet`'s spatial branch (networks.py:122-140): `gamma`,
+    `beta` of shape (1, C, 1, ..., 1)."""
+
+    def __init__(self, c_in: int, num_spatial_dims: int = 2, eps: float = 1e-5):
+        super().__init__()
+        shape = (1, c_in) + (1,) * num_spatial_dims
+        self.gamma = torch.nn.Parameter(torch.ones(*shape))
+        self.beta = torch.nn.Parameter(torch.zeros(*shape))
+        self.eps = eps
+
+
+class GatedConvND(torch.nn.Module):
+    """proj(x) + val * sigmoid(gate), [val | gate] = Conv1x1(c_out, 2 c_out)(relu(Conv k x k(c_in, c_out)(relu(x)))), `proj` a
+    1x1 convolution when c_in != c_out, else the identity (networks.py:142-203).  Parameter container: keys `net.1.*`,
+    `net.3.*`, `proj.*`.  2-D only here."""
+
+    def __init__(self, c_in: int, c_out: int, kernel_size: int = 3, padding=1, stride: int = 1, dilation: int = 1,
+                 nonlinearity=torch.nn.ReLU(), input_rank: int = 2):
+        super().__init__()
+        _require_relu(nonlinearity)
+        assert stride == 1, "Stride > 1 cannot be used to skip connection."
+        if input_rank != 2:
+            raise NotImplementedError("usflows_b200.nn.GatedConvND: 2-D convolutions only")
+        self.net = torch.nn.Sequential(
+            nonlinearity, torch.nn.Conv2d(c_in, c_out, kernel_size=kernel_size, padding=padding, stride=stride,
+                                          dilation=dilation),
+            nonlinearity, torch.nn.Conv2d(c_out, 2 * c_out, kernel_size=1, padding=0, stride=1))
+        self.proj = torch.nn.Conv2d(c_in, c_out, kernel_size=1, padding=0) if c_in != c_out else None
+
+
+def _describe_conv_stack(seq, kernel_size: int, dilation: int) -> dict:
+    """first / blocks / last of a convolutional conditioner stack (`ConvNet2D.nn`, the spatial `ConvNet.nn`)."""
+    mods = [m for m in seq if not isinstance(m, torch.nn.ReLU)]
+    blocks, i = [], 1
+    while i < len(mods) - 1:
+        m = mods[i]
+        if isinstance(m, (GatedConv, GatedConvND)):
+            blk = dict(gated=True, conv1=m.net[1], conv2=m.net[3], proj=getattr(m, "proj", None), ln=None)
+        else:
+            blk = dict(gated=False, conv1=m, conv2=None, proj=None, ln=None)
+        i += 1
+        if i < len(mods) - 1 and isinstance(mods[i], (LayerNormChannels, LayerNormChannelsND)):
+            blk["ln"] = mods[i]
+            i += 1
+        blocks.append(blk)
+    return dict(first=mods[0], blocks=blocks, last=mods[-1], k=kernel_size, dilation=dilation)
 
 
 class ConvNet2D(torch.nn.Module):
@@ -184,20 +271,7 @@ class ConvNet2D(torch.nn.Module):
         self.kernel_size, self.dilation = kernel_size, dilation
 
     def _describe(self) -> dict:
-        mods = [m for m in self.nn if not isinstance(m, torch.nn.ReLU)]
-        blocks, i = [], 1
-        while i < len(mods) - 1:
-            m = mods[i]
-            if isinstance(m, GatedConv):
-                blk = dict(gated=True, conv1=m.net[1], conv2=m.net[3], ln=None)
-            else:
-                blk = dict(gated=False, conv1=m, conv2=None, ln=None)
-            i += 1
-            if i < len(mods) - 1 and isinstance(mods[i], LayerNormChannels):
-                blk["ln"] = mods[i]
-                i += 1
-            blocks.append(blk)
-        return dict(first=mods[0], blocks=blocks, last=mods[-1], k=self.kernel_size, dilation=self.dilation)
+        return _describe_conv_stack(self.nn, self.kernel_size, self.dilation)
 
     def forward(self, x: torch.Tensor, context=None) -> torch.Tensor:
         from . import image_engine

@@ -265,6 +265,8 @@ def _convnet2d_rows(net, x: torch.Tensor, geom) -> torch.Tensor:
         if blk["gated"]:                                  # GatedConv.forward, networks.py:103-121
             o = _conv_rows(torch.relu(_conv_rows(torch.relu(h), blk["conv1"], geom)), blk["conv2"], geom)
             val, gate = o.chunk(2, dim=1)
+            if blk.get("proj") is not None:               # GatedConvND whose width changes (networks.py:186-201)
+                h = _conv_rows(h, blk["proj"], geom)
             h = h + val * torch.sigmoid(gate)
         else:
             h = _conv_rows(h, blk["conv1"], geom)

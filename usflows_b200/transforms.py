@@ -657,7 +657,8 @@ class MaskedCoupling(BaseTransform):
         """Conditioner weights / biases and the flat mask, for the engine's planner (which either folds the mask
         into the first / last Linear or re-orders the features so both halves are contiguous)."""
         from .nn import ConvNet, ConvNet2D
-        if isinstance(self.conditioner, ConvNet2D):        # image-shaped events (image_engine.py)
+        if isinstance(self.conditioner, ConvNet2D) or (isinstance(self.conditioner, ConvNet) and not self.conditioner.is_vector):
+            # image-shaped events (image_engine.py): ConvNet2D, or ConvNet's convolutional branch (networks.py:308-377)
             ws = [m.weight.detach().reshape(m.weight.shape[0], -1) for m in self.conditioner.modules()
                   if isinstance(m, nn.Conv2d)]
             dev = ws[0].device
