@@ -71,8 +71,15 @@ def test_convnet_state_dict_names_are_the_reference_names():
     plain = U.ConvNet(in_dims=[10], c_hidden=[12], gating=False, normalize_layers=False)
     assert sorted(plain.state_dict()) == sorted(["nn.0.weight", "nn.0.bias", "nn.1.1.weight", "nn.1.1.bias",
                                                  "nn.2.weight", "nn.2.bias"])
+    # the convolutional branch (networks.py:308-377): GatedConvND with a projected residual where the width changes
+    spatial = U.ConvNet(in_dims=[16, 7, 7], c_hidden=[32, 24], gating=True)
+    assert sorted(spatial.state_dict()) == sorted(
+        ["nn.0.weight", "nn.0.bias", "nn.1.net.1.weight", "nn.1.net.1.bias", "nn.1.net.3.weight", "nn.1.net.3.bias",
+         "nn.3.gamma", "nn.3.beta", "nn.4.net.1.weight", "nn.4.net.1.bias", "nn.4.net.3.weight", "nn.4.net.3.bias",
+         "nn.4.proj.weight", "nn.4.proj.bias", "nn.6.gamma", "nn.6.beta", "nn.7.weight", "nn.7.bias"])
+    assert tuple(spatial.nn[4].proj.weight.shape) == (24, 32, 1, 1) and tuple(spatial.nn[7].weight.shape) == (16, 24, 3, 3)
     with pytest.raises(NotImplementedError):
-        U.ConvNet(in_dims=[16, 7, 7], c_hidden=[32])
+        U.ConvNet(in_dims=[16, 7], c_hidden=[32])               # 1-D / 3-D convolutions are not built
 
 
 def test_radial_constructor_contract():
