@@ -451,6 +451,11 @@ def test_simplify_matches_the_reference_simplify(name, mode):
     assert all(p.is_cuda for p in simple.parameters())
     x, z0 = arr["x"].cuda(), arr["z0"].cuda()
     t_lp, t_z = TOL[mode]
+    # a simplified layer holds fp32 copies of W and W^-1 (the LU layers compose theirs in fp64), so on an ill-conditioned
+    # stack (d6_hh_normal: the reference's own fp32 log_prob is 1.5e-5 from its fp64 evaluation) two fp32 evaluations
+    # differ by a small multiple of the reference's own fp32 error
+    t_lp = max(t_lp, 3 * rel_err(arr["lp32"], arr["lp64"]))
+    t_z = max(t_z, 3 * rel_err(arr["z32"], arr["z64"]))
     assert rel_err(simple.log_prob(x), want["lp"]) <= t_lp
     assert rel_err(simple.backward(x), want["z"]) <= t_z
     assert rel_err(simple._forward(z0), want["y"]) <= t_z
