@@ -338,12 +338,29 @@ def convnet_spatial(x: Tensor, prefix: str, params, spec: dict) -> Tensor:
     return F.conv2d(h, params[f"{prefix}nn.{idx}.weight"], params[f"{prefix}nn.{idx}.bias"], padding=pad)
 
 
+COND_KINDS = {"condconvnet2d": "convnet2d", "condconvnet": "convnet"}
+
+
+def with_context(x: Tensor, context) -> Tensor:
+    """CondConvNet.forward / CondConvNet2D.forward (networks.py:560-600, 643-680): the context ([N, 1]; None = 0) is
+    expanded to (N, 1, *spatial) and appended to x as one more channel (feature, for vector inputs)."""
+    n = x.shape[0]
+    if context is None:
+        context = torch.zeros(1, dtype=x.dtype)
+    c = context.to(x.dtype).reshape(*context.shape, *([1] * (x.dim() - context.dim()))).expand(n, 1, *x.shape[2:])
+    return torch.cat([x, c], dim=1)
+
+
 def conditioner(x: Tensor, layer: dict, params, n_layers: int, spec=None) -> Tensor:
-    if spec is not None and spec.get("conditioner") == "convnet2d":
+    kind = spec.get("conditioner") if spec is not None else None
+    if kind in COND_KINDS:      # soft training (flows.py:172-193, 559-565): spec["_context"] is the context of this call
+        x = with_context(x, spec.get("_context"))
+        kind = COND_KINDS[kind]
+    if kind == "convnet2d":
         return convnet2d(x, layer["prefix"], params, spec)
-    if spec is not None and spec.get("conditioner") == "convnet" and len(spec["in_dims"]) == 3:
+    if kind == "convnet" and len(spec["in_dims"]) == 3:
         return convnet_spatial(x, layer["prefix"], params, spec)
-    if spec is not None and spec.get("conditioner") == "convnet":
+    if kind == "convnet":
         return convnet_vector(x, layer["prefix"], params, spec)
     return dense_nn(x, layer["prefix"], params, n_layers)
 
@@ -715,14 +732,14 @@ def random_params(spec: dict, seed: int = 0, min_abs_scale: float = 0.1) -> Dict
                     w = torch.zeros(d0, d0)
                     w[torch.arange(d0), torch.randperm(d0, generator=g)] = 1.0
                     out[q + "w_0"] = w
-        elif layer["kind"] == "coupling" and spec.get("conditioner") == "convnet2d":
+        elif layer["kind"] == "coupling" and spec.get("conditioner") in ("convnet2d", "condconvnet2d"):
             def conv(name, n_out, n_in, k):
                 bound = 1 / math.sqrt(n_in * k * k)
                 out[f"{p}{name}.weight"] = uni((n_out, n_in, k, k), bound)
                 out[f"{p}{name}.bias"] = uni((n_out,), bound)
 
             ch, k = int(spec["c_hidden"]), int(spec.get("kernel_size", 3))
-            conv("nn.0", ch, d0, k)
+            conv("nn.0", ch, d0 + (spec["conditioner"] == "condconvnet2d"), k)       # + the context channel
             idx = 1
             for _ in range(spec["num_layers"]):
                 if spec.get("gating", True):
@@ -736,14 +753,14 @@ def random_params(spec: dict, seed: int = 0, min_abs_scale: float = 0.1) -> Dict
                     out[f"{p}nn.{idx}.beta"] = uni((1, ch, 1, 1), 0.2)
                     idx += 1
             conv(f"nn.{idx}", d0, ch, k)
-        elif layer["kind"] == "coupling" and spec.get("conditioner") == "convnet" and len(in_dims) == 3:
+        elif layer["kind"] == "coupling" and spec.get("conditioner") in ("convnet", "condconvnet") and len(in_dims) == 3:
             def conv(name, n_out, n_in, k):
                 bound = 1 / math.sqrt(n_in * k * k)
                 out[f"{p}{name}.weight"] = uni((n_out, n_in, k, k), bound)
                 out[f"{p}{name}.bias"] = uni((n_out,), bound)
 
             ch, k = [int(c) for c in spec["c_hidden"]], int(spec.get("kernel_size", 3))
-            conv("nn.0", ch[0], d0, k)
+            conv("nn.0", ch[0], d0 + (spec["conditioner"] == "condconvnet"), k)
             idx = 1
             for i, oc in enumerate(ch):
                 ic = ch[i - 1] if i > 0 else ch[0]
@@ -760,14 +777,14 @@ def random_params(spec: dict, seed: int = 0, min_abs_scale: float = 0.1) -> Dict
                     out[f"{p}nn.{idx}.beta"] = uni((1, oc, 1, 1), 0.2)
                     idx += 1
             conv(f"nn.{idx}", d0, ch[-1], k)
-        elif layer["kind"] == "coupling" and spec.get("conditioner") == "convnet":
+        elif layer["kind"] == "coupling" and spec.get("conditioner") in ("convnet", "condconvnet"):
             def lin(name, n_out, n_in):
                 bound = 1 / math.sqrt(n_in)
                 out[f"{p}{name}.weight"] = uni((n_out, n_in), bound)
                 out[f"{p}{name}.bias"] = uni((n_out,), bound)
 
             ch = list(spec["c_hidden"])
-            lin("nn.0", ch[0], dtot)
+            lin("nn.0", ch[0], dtot + (spec["conditioner"] == "condconvnet"))
             idx = 1
             for i, oc in enumerate(ch):
                 ic = ch[i - 1] if i > 0 else ch[0]

@@ -18,6 +18,8 @@ EXT_CASES = ["d64_convnet", "d64_convnet_proj_radial2", "d40_convnet_plain_gmm1"
 IMG_CASES = ["img_c4_4x4", "img_mnist_16x7x7", "img_c6_5x3_plain_channel", "img_c32_4x4_noln",
              # networks.ConvNet's convolutional branch (networks.py:308-377) as the conditioner
              "img_convnet_c4_4x4_proj", "img_convnet_c6_5x3_plain", "img_convnet_16x7x7"]
+# soft training (flows.py:172-193, 559-565): context-conditioned conditioners; fixtures also hold `ctx`, `lp32_ctx`, `lp64_ctx`
+SOFT_CASES = ["soft_img_c4_4x4", "soft_img_mnist_16x7x7", "soft_img_convnet_c4_4x4", "soft_d24_convnet"]
 
 
 def load_case(name):

@@ -15,8 +15,8 @@ import math
 import pytest
 import torch
 
-from helpers import (EXT_CASES, IMG_CASES, LARGE_CASES, SIMPLIFY_CASES, SMALL_CASES, build_flow, elementwise_err, layer_kinds,
-                     load_case, load_simplify_case, record_parity, rel_err)
+from helpers import (EXT_CASES, IMG_CASES, LARGE_CASES, SIMPLIFY_CASES, SMALL_CASES, SOFT_CASES, build_flow, elementwise_err,
+                     layer_kinds, load_case, load_simplify_case, record_parity, rel_err)
 from oracle import flow_oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -31,7 +31,7 @@ TOL = {  # mode: (log_prob, latent/sample)
 
 
 @pytest.mark.parametrize("mode", list(TOL))
-@pytest.mark.parametrize("name", SMALL_CASES + LARGE_CASES + EXT_CASES + IMG_CASES)
+@pytest.mark.parametrize("name", SMALL_CASES + LARGE_CASES + EXT_CASES + IMG_CASES + SOFT_CASES)
 def test_flow_matches_reference_golden(name, mode):
     spec, params, arr = load_case(name)
     flow = build_flow(spec, params, precision=mode)
@@ -490,3 +490,31 @@ def test_plane_linear_and_1x1_conv_on_device():
     assert rel_err(flow._forward(z), xi) <= 1e-5
     lp = torch.distributions.Normal(0.0, 1.0).log_prob(want).sum((1, 2, 3)) - float(torch.linalg.slogdet(w.double())[1]) * H * W
     assert rel_err(flow.log_prob(xi.cuda()), lp) <= 1e-5
+
+
+@pytest.mark.parametrize("mode", ["fp32", "fp32_simt"])
+@pytest.mark.parametrize("name", SOFT_CASES)
+def test_soft_training_context_matches_the_reference(name, mode):
+    """`log_prob(x, context)` of a soft-training flow over CondConvNet2D / CondConvNet conditioners (flows.py:235-238,
+    559-565; networks.py:513-680) against the reference's output; context 0 is the kernels' launch program."""
+    spec, params, arr = load_case(name)
+    flow = build_flow(spec, params, precision=mode)
+    x, ctx = arr["x"].cuda(), arr["ctx"].cuda()
+    lp_ctx = flow.log_prob(x, context=ctx)
+    assert rel_err(lp_ctx, arr["lp32_ctx"]) <= 1e-5
+    assert rel_err(lp_ctx, arr["lp64_ctx"]) <= 3 * rel_err(arr["lp32_ctx"], arr["lp64_ctx"]) + 2e-6
+    assert rel_err(flow.log_prob(x, context=torch.zeros(x.shape[0], 1, device="cuda")), flow.log_prob(x)) <= 2e-6
+    y = flow.sample([6], context=torch.full((6, 1), 0.5, device="cuda"))
+    assert y.shape == (6, *spec["in_dims"]) and bool(torch.isfinite(y).all())
+
+
+def test_soft_training_fit_on_device():
+    """`fit` with soft_training (flows.py:172-193) on the B200: the perturbed batch and its context go through the
+    contraction kernels' autograd route; the loss falls and the evaluation kernels follow the updated weights."""
+    spec, params, arr = load_case("soft_img_mnist_16x7x7")
+    flow = build_flow(spec, params)
+    x = arr["x"].cuda()
+    before = float(-flow.log_prob(x).mean())
+    losses = flow.fit(x, optim=torch.optim.Adam, optim_params=dict(lr=1e-3), batch_size=24, epochs=8, shuffle=False)
+    assert all(math.isfinite(float(l)) for l in losses) and float(losses[-1]) < float(losses[0])
+    assert float(-flow.log_prob(x).mean()) < before

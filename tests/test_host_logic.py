@@ -4,12 +4,12 @@ import pytest
 import torch
 
 import fake_backend
-from helpers import (EXT_CASES, IMG_CASES, LARGE_CASES, SIMPLIFY_CASES, SMALL_CASES, build_flow, layer_kinds, load_case,
-                     load_simplify_case, rel_err)
+from helpers import (EXT_CASES, IMG_CASES, LARGE_CASES, SIMPLIFY_CASES, SMALL_CASES, SOFT_CASES, build_flow, layer_kinds,
+                     load_case, load_simplify_case, rel_err)
 
 
 @pytest.mark.parametrize("mode", ["fp32_simt", "fp32", "fp32_tf32", "tf32"])
-@pytest.mark.parametrize("name", SMALL_CASES + ["c2_d784"] + EXT_CASES + IMG_CASES)
+@pytest.mark.parametrize("name", SMALL_CASES + ["c2_d784"] + EXT_CASES + IMG_CASES + SOFT_CASES)
 def test_flow_program_matches_reference(fake_ops, name, mode):
     spec, params, arr = load_case(name)
     flow = build_flow(spec, params, device="cpu", precision=mode)
@@ -265,3 +265,30 @@ def test_plane_linear_and_1x1_conv_built_directly(fake_ops):
     assert rel_err(flow.log_prob(xi), base - ladj) < 1e-5
     with pytest.raises(ValueError):
         U.Bijective1x1Conv2d(torch.zeros(3, 4, 1, 1))
+
+
+@pytest.mark.parametrize("name", SOFT_CASES)
+def test_soft_training_context_matches_the_reference(fake_ops, name):
+    """USFlow(soft_training=True) over CondConvNet2D / CondConvNet conditioners (flows.py:559-565, networks.py:513-680):
+    `log_prob(x)` is the context-0 evaluation (covered by test_flow_program_matches_reference through the kernels'
+    launch program), `log_prob(x, context)` reproduces the reference's output for per-sample contexts."""
+    spec, params, arr = load_case(name)
+    flow = build_flow(spec, params, device="cpu", precision="fp32")
+    assert flow.soft_training and float(flow.training_noise_prior.high) == pytest.approx(0.01)
+    lp_ctx = flow.log_prob(arr["x"], context=arr["ctx"])
+    assert rel_err(lp_ctx, arr["lp32_ctx"]) < 2e-5
+    assert rel_err(lp_ctx, arr["lp32"]) > 1e-7                       # the context does reach the conditioners
+    zero = flow.log_prob(arr["x"], context=torch.zeros(arr["x"].shape[0], 1))
+    assert rel_err(zero, flow.log_prob(arr["x"])) < 2e-6              # explicit zeros = the implicit default
+    y0 = flow.sample([4], context=torch.zeros(4, 1))
+    assert y0.shape == (4, *spec["in_dims"]) and bool(torch.isfinite(y0).all())
+
+
+def test_soft_training_needs_a_conditional_conditioner(fake_ops):
+    """The reference hands the context to the conditioner, which pyro's DenseNN rejects with a TypeError."""
+    spec, params, arr = load_case("d32_h64")
+    flow = build_flow(dict(spec, soft_training=True), params, device="cpu")
+    with pytest.raises(TypeError):
+        flow.log_prob(arr["x"])
+    plain = build_flow(spec, params, device="cpu")                    # USFlow drops a context unless soft_training
+    assert torch.equal(plain.log_prob(arr["x"], context=torch.ones(arr["x"].shape[0], 1)), plain.log_prob(arr["x"]))

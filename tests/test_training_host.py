@@ -20,9 +20,9 @@ def fake_ops(monkeypatch):
     return fake_backend
 
 
-def _oracle_grads(spec, params, x):
+def _oracle_grads(spec, params, x, context=None):
     p = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in params.items()}
-    loss = -O.flow_log_prob(x, spec, p).mean()
+    loss = -O.flow_log_prob(x, spec if context is None else dict(spec, _context=context), p).mean()
     loss.backward()
     return float(loss), {k: v.grad for k, v in p.items() if v.grad is not None}
 
@@ -63,6 +63,50 @@ def test_loss_and_gradients_match_the_oracle(fake_ops, name):
         assert rel_err(got[key].grad, ref) <= 2e-4, key
         checked += 1
     assert checked >= 6
+
+
+@pytest.mark.parametrize("name", ["soft_img_c4_4x4", "soft_img_convnet_c4_4x4", "soft_d24_convnet"])
+def test_soft_training_gradients_match_the_oracle(fake_ops, name):
+    """The loss of a soft-training step (flows.py:195-198 with the context of :172-193) and its gradients, including
+    those of the context channel's weights, against autograd through the oracle."""
+    from usflows_b200 import training
+    spec, params, arr = load_case(name)
+    spec = dict(spec, base="normal")
+    flow = build_flow(spec, params, device="cpu")
+    x, ctx = arr["x"][:16], arr["ctx"][:16]
+    loss = -training.log_prob_autograd(flow, x, ctx).mean()
+    loss.backward()
+    want_loss, want = _oracle_grads(spec, params, x, ctx)
+    assert abs(float(loss) - want_loss) <= 2e-5 * max(1.0, abs(want_loss))
+    got = dict(flow.named_parameters())
+    checked = 0
+    for key, g in want.items():
+        if "conditioner" not in key:
+            continue
+        assert rel_err(got[key].grad, g) <= 2e-4, key
+        checked += 1
+    first = [k for k in want if k.endswith("conditioner.nn.0.weight")][0]
+    assert float(got[first].grad[:, -1].abs().max()) > 0              # the context input's weights do learn
+    assert checked >= 8
+
+
+def test_soft_training_fit_runs_and_perturbs_like_the_reference(fake_ops):
+    """`fit` with soft_training (flows.py:172-193): noise scales from the prior, one per sample, context = scale * 2 / high;
+    the shard of a data-parallel rank is a slice of the global batch's draws."""
+    from usflows_b200 import training
+    spec, params, arr = load_case("soft_d24_convnet")
+    flow = build_flow(spec, params, device="cpu")
+    torch.manual_seed(3)
+    noisy, ctx = training.soft_training_noise(flow, arr["x"])
+    assert ctx.shape == (arr["x"].shape[0], 1) and float(ctx.min()) >= 0 and float(ctx.max()) <= 2.0
+    sigma = ctx[:, 0] * float(flow.training_noise_prior.high) / 2
+    assert float(((noisy - arr["x"]).abs() / sigma[:, None]).max()) < 6.0          # |e| <= 6 sigma
+    torch.manual_seed(3)
+    part, cpart = training.soft_training_noise(flow, arr["x"], 8, 20)
+    assert torch.equal(part, noisy[8:20]) and torch.equal(cpart, ctx[8:20])
+    losses = flow.fit(arr["x"], optim=torch.optim.Adam, optim_params=dict(lr=1e-3), batch_size=16, epochs=3, shuffle=False,
+                      device="cpu")
+    assert len(losses) == 3 and all(np.isfinite(losses)) and losses[-1] < losses[0]
 
 
 def test_sophiag_is_sign_momentum_without_hessian_updates():

@@ -21,15 +21,17 @@ def build_flow(spec, params=None, device="cuda", precision=None):
         base = U.RadialDistribution(torch.zeros(*ev), nd, p=float("inf") if spec["p"] == "inf" else float(spec["p"]))
     else:
         base = (U.Laplace if spec.get("base", "laplace") == "laplace" else U.Normal)(torch.zeros(*ev), torch.ones(*ev))
-    if spec.get("conditioner") == "convnet2d":
-        cond_cls = U.ConvNet2D
+    if spec.get("conditioner") in ("convnet2d", "condconvnet2d"):
+        cond_cls = U.ConvNet2D if spec["conditioner"] == "convnet2d" else U.CondConvNet2D
         cond_args = dict(c_in=d, c_hidden=spec["c_hidden"], num_layers=spec["num_layers"], padding="same",
                          kernel_size=spec.get("kernel_size", 3), normalize_layers=spec.get("normalize_layers", True),
                          gating=spec.get("gating", True))
-    elif spec.get("conditioner") == "convnet":
-        cond_cls = U.ConvNet
+    elif spec.get("conditioner") in ("convnet", "condconvnet"):
+        cond_cls = U.ConvNet if spec["conditioner"] == "convnet" else U.CondConvNet
         cond_args = dict(in_dims=list(spec["in_dims"]), c_hidden=list(spec["c_hidden"]), gating=spec.get("gating", True),
                          normalize_layers=spec.get("normalize_layers", True), kernel_size=spec.get("kernel_size", 3))
+        if cond_cls is U.CondConvNet:
+            cond_args["c_out"] = d
     else:
         cond_cls = U.DenseNN
         cond_args = dict(input_dim=d, hidden_dims=list(spec["hidden_dims"]),
@@ -41,6 +43,8 @@ def build_flow(spec, params=None, device="cuda", precision=None):
         coupling=spec.get("coupling", "additive"),
         prior_scale=1.0, lu_transform=spec.get("lu_transform", 1), householder=spec.get("householder", 1),
         affine_conjugation=spec.get("affine_conjugation", False), masktype=spec.get("masktype", "checkerboard"),
+        soft_training=bool(spec.get("soft_training", False)),
+        training_noise_prior=torch.distributions.Uniform(1e-20, 0.01) if spec.get("soft_training") else None,
         precision=precision)
     if params is not None:
         res = flow.load_state_dict(params, strict=True)

@@ -98,13 +98,13 @@ class Flow(torch.nn.Module):
     export_modes = Literal["log_prob", "sample", "forward", "backward"]
     export: str = "log_prob"
     device = "cpu"
+    _context_needs_soft_training = False
 
     def __init__(self, base_distribution, layers, soft_training: bool = False, training_noise_prior=None,
                  device: str = "cpu", precision: Optional[str] = None, *args, **kwargs) -> None:
         super().__init__(*args, **kwargs)
-        if soft_training:
-            # reference flows.py:559-565 passes a context to the conditioner, which pyro's DenseNN rejects
-            raise NotImplementedError("usflows_b200: soft_training (context-conditioned conditioners) is not built")
+        if training_noise_prior is None:                           # flows.py:79-80
+            training_noise_prior = torch.distributions.Uniform(0, 1e-6)
         self.soft_training = soft_training
         self.training_noise_prior = training_noise_prior
         self.layers = layers
@@ -166,10 +166,39 @@ class Flow(torch.nn.Module):
 
     def log_prob(self, x: torch.Tensor, context: Optional[torch.Tensor] = None) -> torch.Tensor:
         """log p(x) = base.log_prob(z) - sum_k log|det J_k|  (flows.py:225-245)."""
+        if self.soft_training:
+            self._require_conditional()
+        elif self._context_needs_soft_training:
+            context = None                    # USFlow.log_prob drops the context unless soft_training (flows.py:559-567)
         if context is not None:
-            raise NotImplementedError("usflows_b200: context-conditioned evaluation is not built")
-        with ops.on_device(x):
-            return self._log_prob(x)
+            return self._with_context("log_prob", x, context)
+        with ops.on_device(x):                # no context = context 0 (flows.py:559-565): the conditional conditioners
+            return self._log_prob(x)          # are lowered without their context input, which is exact
+
+    def _require_conditional(self) -> None:
+        """Soft training hands a context to every coupling's conditioner (transforms.py:284-289), which only the
+        conditional networks accept: the reference fails with a TypeError on the first call otherwise."""
+        for l in self.layers:
+            while isinstance(l, InverseTransform):
+                l = l.transform
+            if isinstance(l, MaskedCoupling) and not getattr(l.conditioner, "context_channels", 0):
+                raise TypeError(f"soft_training passes a context to the conditioner; {type(l.conditioner).__name__} takes "
+                                "none (use CondConvNet / CondConvNet2D)")
+
+    def _with_context(self, what: str, x: torch.Tensor, context: torch.Tensor) -> torch.Tensor:
+        """Evaluation with an explicit context (flows.py:235-238, 257-263): the context channel of the conditional
+        conditioners is data, so this runs the layer-by-layer route of the training pass (training.py: every contraction
+        on the library's kernels, no gradient bookkeeping)."""
+        from . import training
+        ops.require_cuda(x, "input")
+        ev = len(self._event_shape())
+        batch_shape = x.shape[:x.dim() - ev]
+        x2 = x.reshape(-1, *x.shape[x.dim() - ev:])
+        context = torch.as_tensor(context, dtype=torch.float32, device=x.device)
+        with torch.no_grad(), ops.on_device(x):
+            if what == "log_prob":
+                return training.log_prob_autograd(self, x2, context).reshape(batch_shape)
+            return training.apply_autograd(self, x2, what, context).reshape(*batch_shape, *x2.shape[1:])
 
     def _log_prob(self, x: torch.Tensor) -> torch.Tensor:
         prog, ladj = self._program("backward")
@@ -478,15 +507,14 @@ class Flow(torch.nn.Module):
 
     def sample(self, sample_shape: Iterable[int] = None, context: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Draw from the base and push through the layers (flows.py:247-265)."""
-        if context is not None:
-            raise NotImplementedError("usflows_b200: context-conditioned evaluation is not built")
         if sample_shape is None:
             sample_shape = [1]
         shape = [int(s) for s in sample_shape]
         with ops.on_device(next(self.parameters())):
             z = self.base_distribution.sample(shape)
             ev = len(self._event_shape())
-            y = self._run("forward", z.reshape(-1, *z.shape[z.dim() - ev:]))
+            z = z.reshape(-1, *z.shape[z.dim() - ev:])
+            y = self._run("forward", z) if context is None else self._with_context("forward", z, context)
         return y.reshape(*shape, *y.shape[1:])
 
     def fit(self, data_train, optim=None, optim_params: Optional[Dict[str, Any]] = None, batch_size: int = 32,
@@ -595,6 +623,8 @@ class USFlow(Flow):
     [-> BlockAffine^-1]] x coupling_blocks -> BlockAffine(LU) -> Scale  (flows.py:380-491)."""
 
     MASKTYPE = Literal["checkerboard", "channel"]
+
+    _context_needs_soft_training = True
 
     def __init__(self, base_distribution, in_dims: List[int], coupling_blocks: int,
                  conditioner_cls: Type[torch.nn.Module], conditioner_args: Dict[str, Any], soft_training=False,

@@ -129,11 +129,15 @@ class ConvNet(torch.nn.Module):
         self._spatial_rank = 2
         self.kernel_size, self.dilation = kernel_size, dilation
 
-    def _describe(self) -> dict:
+    context_channels = 0          # CondConvNet: trailing input channels / features that carry the context
+
+    def _describe(self, with_context: bool = False) -> dict:
         """Structure of the network as the engine's planner reads it: first / last Linear and the hidden blocks (the
-        spatial branch answers in `ConvNet2D._describe`'s format, with `proj` per block)."""
+        spatial branch answers in `ConvNet2D._describe`'s format, with `proj` per block).  A conditional network
+        (`CondConvNet`) is described WITHOUT its context inputs unless `with_context`: context 0, which is what the
+        reference evaluates `log_prob` / `backward` / `sample` with when none is given (flows.py:559-565)."""
         if not self.is_vector:
-            return _describe_conv_stack(self.nn, self.kernel_size, self.dilation)
+            return _describe_conv_stack(self.nn, self.kernel_size, self.dilation, 0 if with_context else self.context_channels)
         mods = list(self.nn)
         blocks, i = [], 1
         while i < len(mods) - 1:
@@ -147,9 +151,13 @@ class ConvNet(torch.nn.Module):
                 blk["ln"] = mods[i].layernorm
                 i += 1
             blocks.append(blk)
-        return dict(first=mods[0], blocks=blocks, last=mods[-1])
+        first = mods[0] if with_context or not self.context_channels else _without_context(mods[0], self.context_channels)
+        return dict(first=first, blocks=blocks, last=mods[-1])
 
     def forward(self, x: torch.Tensor, context=None) -> torch.Tensor:
+        if context is not None and self.context_channels:
+            raise NotImplementedError("usflows_b200.nn: a conditional network is evaluated with a context inside a flow "
+                                      "(Flow.log_prob(x, context) / fit); called directly it uses context 0")
         if not self.is_vector:
             from . import image_engine
             return image_engine.run_convnet2d(self, x)
@@ -218,8 +226,23 @@ class GatedConvND(torch.nn.Module):
         self.proj = torch.nn.Conv2d(c_in, c_out, kernel_size=1, padding=0) if c_in != c_out else None
 
 
-def _describe_conv_stack(seq, kernel_size: int, dilation: int) -> dict:
-    """first / blocks / last of a convolutional conditioner stack (`ConvNet2D.nn`, the spatial `ConvNet.nn`)."""
+class _LayerView:
+    """A Linear / Conv2d seen without its trailing `n` context inputs: a zero context contributes nothing, so the layer
+    is the one with `weight[:, :-n]` (a differentiable view of the parameter)."""
+
+    def __init__(self, layer, n: int):
+        self.weight = layer.weight[:, :layer.weight.shape[1] - n].contiguous()
+        self.bias = layer.bias
+        self.dilation = getattr(layer, "dilation", (1, 1))
+
+
+def _without_context(layer, n: int):
+    return _LayerView(layer, n)
+
+
+def _describe_conv_stack(seq, kernel_size: int, dilation: int, drop_context: int = 0) -> dict:
+    """first / blocks / last of a convolutional conditioner stack (`ConvNet2D.nn`, the spatial `ConvNet.nn`);
+    `drop_context` trailing input channels of the first convolution are left out (context 0)."""
     mods = [m for m in seq if not isinstance(m, torch.nn.ReLU)]
     blocks, i = [], 1
     while i < len(mods) - 1:
@@ -233,7 +256,8 @@ def _describe_conv_stack(seq, kernel_size: int, dilation: int) -> dict:
             blk["ln"] = mods[i]
             i += 1
         blocks.append(blk)
-    return dict(first=mods[0], blocks=blocks, last=mods[-1], k=kernel_size, dilation=dilation)
+    first = _without_context(mods[0], drop_context) if drop_context else mods[0]
+    return dict(first=first, blocks=blocks, last=mods[-1], k=kernel_size, dilation=dilation)
 
 
 class ConvNet2D(torch.nn.Module):
@@ -270,9 +294,51 @@ class ConvNet2D(torch.nn.Module):
         self.nn = torch.nn.Sequential(*layers)
         self.kernel_size, self.dilation = kernel_size, dilation
 
-    def _describe(self) -> dict:
-        return _describe_conv_stack(self.nn, self.kernel_size, self.dilation)
+    context_channels = 0          # CondConvNet2D: 1
+
+    def _describe(self, with_context: bool = False) -> dict:
+        return _describe_conv_stack(self.nn, self.kernel_size, self.dilation, 0 if with_context else self.context_channels)
 
     def forward(self, x: torch.Tensor, context=None) -> torch.Tensor:
+        if context is not None and self.context_channels:
+            raise NotImplementedError("usflows_b200.nn: a conditional network is evaluated with a context inside a flow "
+                                      "(Flow.log_prob(x, context) / fit); called directly it uses context 0")
         from . import image_engine
         return image_engine.run_convnet2d(self, x)
+
+
+# --------------------------------------------------------------------------------------------------
+# Context-conditioned conditioners of soft training (flows.py:172-193, 559-565): `networks.CondConvNet` (networks.py:513-
+# 600) and `networks.CondConvNet2D` (networks.py:603-680) append the per-sample context (the noise scale) as ONE extra
+# input channel / feature, constant over the pixels of a sample.
+# --------------------------------------------------------------------------------------------------
+class CondConvNet(ConvNet):
+    """`networks.CondConvNet`: a `ConvNet` over `[in_dims[0] + 1, ...]` inputs.  As in the reference `c_out` defaults to
+    the widened input (pass `c_out=in_dims[0]` for a coupling)."""
+
+    context_channels = 1
+
+    def __init__(self, in_dims, c_hidden, c_out: int = -1, nonlinearity=torch.nn.ReLU(), kernel_size: int = 3,
+                 stride: int = 1, dilation: int = 1, padding=None, normalize_layers: bool = True, gating: bool = True,
+                 **kwargs):
+        try:
+            in_dims = list(in_dims)
+        except TypeError:
+            raise ValueError("in_dims must be an iterable like [C, H, W]")
+        super().__init__(in_dims=[in_dims[0] + 1] + in_dims[1:], c_hidden=c_hidden, c_out=c_out, nonlinearity=nonlinearity,
+                         kernel_size=kernel_size, stride=stride, dilation=dilation, padding=padding,
+                         normalize_layers=normalize_layers, gating=gating, **kwargs)
+        self._orig_in_dims = in_dims
+
+
+class CondConvNet2D(ConvNet2D):
+    """`networks.CondConvNet2D`: a `ConvNet2D` over `c_in + 1` input channels with `c_out = c_in` by default."""
+
+    context_channels = 1
+
+    def __init__(self, c_in: int, c_hidden: int = 3, c_out: int = -1, num_layers: int = 3, nonlinearity=torch.nn.ReLU(),
+                 kernel_size: int = 3, stride: int = 1, dilation: int = 1, padding=None, **kwargs):
+        if c_out < 0:
+            c_out = c_in
+        super().__init__(c_in=c_in + 1, c_hidden=c_hidden, c_out=c_out, num_layers=num_layers, nonlinearity=nonlinearity,
+                         kernel_size=kernel_size, stride=stride, dilation=dilation, padding=padding, **kwargs)

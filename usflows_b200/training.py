@@ -144,13 +144,14 @@ def affine_parts(t, cache: Optional[dict] = None):
     raise NotImplementedError(f"usflows_b200: training of {type(t).__name__} is not built")
 
 
-def _layer_backward(layer, y: torch.Tensor, inverse: bool = False, cache: Optional[dict] = None, geom=None):
+def _layer_backward(layer, y: torch.Tensor, inverse: bool = False, cache: Optional[dict] = None, geom=None,
+                    context: Optional[torch.Tensor] = None):
     """(density direction value, forward log|det J|) of one layer; `inverse` swaps the direction.  For image-shaped events
     `geom = (C, H, W)` and y holds channels-last rows [N*H*W, C] (the layout of image_engine.py): the 1x1 convolution of a
     BlockAffineTransform is then the same `linear` as the flat case, per-element vectors are indexed per pixel."""
     from . import transforms as T
     if isinstance(layer, T.InverseTransform):
-        x, ladj = _layer_backward(layer.transform, y, not inverse, cache, geom)
+        x, ladj = _layer_backward(layer.transform, y, not inverse, cache, geom, context)
         return x, -ladj
     if isinstance(layer, (T.BlockAffineTransform, T.Bijective1x1Conv2d)):
         W, Winv, b, ladj = affine_parts(getattr(layer, "block_transform", layer), cache)
@@ -186,21 +187,33 @@ def _layer_backward(layer, y: torch.Tensor, inverse: bool = False, cache: Option
         C, H, W = geom
         m = layer.mask.reshape(C, H * W).t().to(y.dtype)                # channels-last mask [H*W, C]
         y3 = y.reshape(-1, H * W, C)
-        t = _convnet2d_rows(layer.conditioner, (y3 * m).reshape(-1, C), geom).reshape(-1, H * W, C)
+        t = _convnet2d_rows(layer.conditioner, (y3 * m).reshape(-1, C), geom, context).reshape(-1, H * W, C)
         t = (1 - m) * t
         return ((y3 + t) if inverse else (y3 - t)).reshape(-1, C), y.new_zeros(())
     if isinstance(layer, T.MaskedCoupling):
         m = layer.mask.reshape(-1).to(y.dtype)
-        t = (1 - m) * _conditioner(layer.conditioner, y * m)
+        t = (1 - m) * _conditioner(layer.conditioner, y * m, context)
         return (y + t if inverse else y - t), y.new_zeros(())      # transforms.py:277-306, 316-326
     raise NotImplementedError(f"usflows_b200: training of {type(layer).__name__} is not built")
 
 
-def _conditioner(net, h: torch.Tensor) -> torch.Tensor:
+def _context_rows(context: torch.Tensor, rows: int, like: torch.Tensor) -> torch.Tensor:
+    """The per-sample context [N] / [N, 1] as one extra column for `rows` = N * (pixels per sample) rows: the channel a
+    conditional network appends, constant over a sample (networks.py:560-600, 643-680)."""
+    c = context.to(device=like.device, dtype=like.dtype).reshape(-1, 1)
+    if rows % c.shape[0]:
+        raise ValueError("context must hold one value per sample")
+    return c.repeat_interleave(rows // c.shape[0], dim=0)
+
+
+def _conditioner(net, h: torch.Tensor, context: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Conditioner network as an autograd graph: contractions on the library's kernels, element-wise glue in torch."""
     from .nn import ConvNet
     if isinstance(net, ConvNet):                      # networks.py:222-245 (GatedMLP), 205-219 (LayerNormVector), 287-307
-        d = net._describe()
+        with_ctx = context is not None and net.context_channels > 0
+        if with_ctx:                                  # CondConvNet, vector branch: [x | context] (networks.py:560-600)
+            h = torch.cat([h, _context_rows(context, h.shape[0], h)], dim=1)
+        d = net._describe(with_context=with_ctx)
         x = linear(h, d["first"].weight, d["first"].bias)
         for blk in d["blocks"]:
             a = linear(torch.relu(x), blk["lin1"].weight, blk["lin1"].bias)
@@ -257,9 +270,13 @@ def _conv_rows(x: torch.Tensor, conv, geom) -> torch.Tensor:
     return linear(cols, w, conv.bias)
 
 
-def _convnet2d_rows(net, x: torch.Tensor, geom) -> torch.Tensor:
-    """networks.ConvNet2D (networks.py:441-506) over channels-last rows as an autograd graph."""
-    d = net._describe()
+def _convnet2d_rows(net, x: torch.Tensor, geom, context: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """networks.ConvNet2D (networks.py:441-506) over channels-last rows as an autograd graph; a conditional network
+    (CondConvNet2D / CondConvNet) with a context gets it as one more input channel, else runs without (context 0)."""
+    with_ctx = context is not None and getattr(net, "context_channels", 0) > 0
+    if with_ctx:
+        x = torch.cat([x, _context_rows(context, x.shape[0], x)], dim=1)
+    d = net._describe(with_context=with_ctx)
     h = _conv_rows(x, d["first"], geom)
     for blk in d["blocks"]:
         if blk["gated"]:                                  # GatedConv.forward, networks.py:103-121
@@ -314,8 +331,27 @@ def base_log_prob(base, z: torch.Tensor) -> torch.Tensor:
     return lp.sum(-1)
 
 
-def log_prob_autograd(flow, x: torch.Tensor) -> torch.Tensor:
-    """`Flow.log_prob` (flows.py:225-245) as an autograd graph over the flow's parameters."""
+def apply_autograd(flow, x: torch.Tensor, direction: str, context: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """`Flow.backward` ("backward": data -> latent) / `Flow._forward` ("forward") on the autograd route -- the route that
+    takes a context (flows.py:45-67 with the `context` of :235-238, 257-263)."""
+    ev = tuple(flow._event_shape())
+    geom = ev if len(ev) == 3 else None
+    if geom is not None:
+        C, H, W = ev
+        z = x.reshape(-1, C, H * W).transpose(1, 2).reshape(-1, C)
+    else:
+        z = x.reshape(-1, ev[0])
+    cache: dict = {}
+    for layer in (reversed(flow.layers) if direction == "backward" else flow.layers):
+        z, _ = _layer_backward(layer, z, inverse=direction != "backward", cache=cache, geom=geom, context=context)
+    if geom is not None:
+        z = z.reshape(-1, H * W, C).transpose(1, 2).reshape(-1, C, H, W)
+    return z
+
+
+def log_prob_autograd(flow, x: torch.Tensor, context: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """`Flow.log_prob` (flows.py:225-245) as an autograd graph over the flow's parameters; `context` [N] / [N, 1] reaches
+    the conditional conditioners (soft training, flows.py:172-193)."""
     ev = tuple(flow._event_shape())
     geom = None
     if len(ev) == 3:                             # image-shaped event: channels-last rows [N*H*W, C] through the layers
@@ -327,7 +363,7 @@ def log_prob_autograd(flow, x: torch.Tensor) -> torch.Tensor:
     total = z.new_zeros(())                      # scalar, or [rows] once a data-dependent log-det joins
     cache: dict = {}
     for layer in reversed(flow.layers):
-        z, ladj = _layer_backward(layer, z, cache=cache, geom=geom)
+        z, ladj = _layer_backward(layer, z, cache=cache, geom=geom, context=context)
         total = total + ladj
     if geom is not None:                         # back to the NCHW element order the base parameters are stored in
         z = z.reshape(-1, H * W, C).transpose(1, 2).reshape(-1, C * H * W)
@@ -526,11 +562,14 @@ class TrainStep:
     # captured once per (rows, global batch) and replayed; the NCCL all-reduces of the buckets are captured with it
     # (on NCCL's stream, so they still overlap the remaining backward kernels).  Optimisers that cannot be captured
     # (host-side state reads) keep the eager route: `graph=False`, or automatically when the capture fails.
-    def step(self, sample: torch.Tensor, global_rows: Optional[int] = None) -> torch.Tensor:
+    def step(self, sample: torch.Tensor, global_rows: Optional[int] = None,
+             context: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Runs the step on this rank's shard `sample` [rows, ...]; returns this rank's share of the loss (a device
-        scalar: the sum over ranks is the global mean loss)."""
+        scalar: the sum over ranks is the global mean loss).  `context` [rows, 1]: the noise scales of soft training."""
         rows = sample.shape[0]
         total = global_rows if global_rows is not None else rows * self.world
+        if context is not None:
+            return self._eager_step(sample, rows, total, context=context)
         if self.graph and self.use_engine and rows > 0 and sample.is_cuda and float(self._lr_signature()) == self._lr_sig:
             key = (rows, total)
             if key in self._graphs:
@@ -572,7 +611,8 @@ class TrainStep:
         graph.replay()                                          # capturing does not execute: this is the step itself
         return out["loss"].clone()
 
-    def _eager_step(self, sample: torch.Tensor, rows: int, total: int, zero_grad: bool = True) -> torch.Tensor:
+    def _eager_step(self, sample: torch.Tensor, rows: int, total: int, zero_grad: bool = True,
+                    context: Optional[torch.Tensor] = None) -> torch.Tensor:
         flow = self.flow
         if zero_grad:
             self.opt.zero_grad()
@@ -591,7 +631,7 @@ class TrainStep:
             local = eng.step(sample.reshape(rows, -1), total, self.reducer)
             self.out_of_range += eng.flag[0]
         elif rows > 0:
-            loss = -log_prob_autograd(flow, sample).sum() / total
+            loss = -log_prob_autograd(flow, sample, context).sum() / total
             if self.rank == 0:                          # the prior is a function of the weights only: count it once
                 prior = flow.log_prior()
                 if isinstance(prior, torch.Tensor) or prior != 0:
@@ -607,6 +647,21 @@ class TrainStep:
         self.opt.step()
         self.infeasible += infeasible_count(flow)
         return local
+
+
+def soft_training_noise(flow, batch: torch.Tensor, lo: int = 0, hi: Optional[int] = None):
+    """SoftFlow perturbation of one GLOBAL batch (flows.py:172-193): one noise scale per sample from
+    `training_noise_prior`, `x + N(0, sigma)` with that scale on every element of the sample, and the context
+    `sigma * 2 / prior.high` the conditional conditioners see.  Drawn for the whole batch on every rank (same generator
+    state => same draws) and cut to this rank's rows [lo, hi), so a data-parallel run perturbs the batch exactly as a
+    single process would.  Returns (noisy rows, context [rows, 1])."""
+    prior = flow.training_noise_prior
+    n = batch.shape[0]
+    hi = n if hi is None else hi
+    sigma = prior.sample([n]).to(batch.device).reshape(n, *([1] * (batch.dim() - 1))).to(batch.dtype)
+    noisy = batch + torch.randn_like(batch) * sigma
+    context = (sigma.reshape(n, 1) * (2.0 / float(prior.high))).detach()
+    return noisy[lo:hi], context[lo:hi]
 
 
 def infeasible_count(flow) -> torch.Tensor:
@@ -652,8 +707,6 @@ def fit(flow, data_train, optim=None, optim_params: Optional[Dict[str, Any]] = N
     step); the losses stay on the device until the epoch ends."""
     import torch.distributed as dist
     from .optim import SophiaG
-    if flow.soft_training:
-        raise NotImplementedError("usflows_b200: soft_training is not built")
     if device is None:
         device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else flow.device
     model = flow.to(device)
@@ -695,7 +748,10 @@ def fit(flow, data_train, optim=None, optim_params: Optional[Dict[str, Any]] = N
                     end = min(idx + batch_size, N)
                     lo, hi = shard_bounds(end - idx, rank, world)
                     sample = data[idx + lo:idx + hi].to(device=device, dtype=torch.float32)
-                    losses.append(ts.step(sample, global_rows=end - idx))
+                    context = None
+                    if flow.soft_training:                       # flows.py:172-193
+                        sample, context = soft_training_noise(flow, data[idx:end].to(device=device, dtype=torch.float32), lo, hi)
+                    losses.append(ts.step(sample, global_rows=end - idx, context=context))
                     steps += 1
                     if steps % max(1, feasibility_every) == 0:
                         check_feasible()
