@@ -518,3 +518,28 @@ def test_soft_training_fit_on_device():
     losses = flow.fit(x, optim=torch.optim.Adam, optim_params=dict(lr=1e-3), batch_size=24, epochs=8, shuffle=False)
     assert all(math.isfinite(float(l)) for l in losses) and float(losses[-1]) < float(losses[0])
     assert float(-flow.log_prob(x).mean()) < before
+
+
+def test_graph_capture_survives_garbage_collection_of_old_programs():
+    """Flows of an earlier weight version that sit in reference cycles are finalised by the cyclic collector, whenever it
+    runs -- their CUDA graphs and C plans release device objects, which the capturing thread may not do while it captures.
+    With a collection forced at (almost) every allocation the small-batch capture of a fresh flow must still succeed."""
+    import gc
+    spec, params, arr = load_case("d32_h64")
+    x = arr["x"].cuda()
+    want = None
+    thresholds = gc.get_threshold()
+    try:
+        for _ in range(4):
+            flow = build_flow(spec, params)
+            want = flow.log_prob(x)              # builds a C plan and captures a small-batch graph
+            flow.__dict__["_cycle"] = flow       # only the cyclic collector can free it now
+            del flow
+        gc.set_threshold(1, 1, 1)
+        fresh = build_flow(spec, params)
+        got = fresh.log_prob(x)                  # captures while the collector finalises the four flows above
+        again = fresh.log_prob(x)                # replay
+    finally:
+        gc.set_threshold(*thresholds)
+    assert torch.equal(got, want) and torch.equal(again, want)
+    assert rel_err(got, arr["lp32"]) <= 1e-5

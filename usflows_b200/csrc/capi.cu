@@ -111,6 +111,14 @@ int make_epilogue(const usf_linear_args* a, Epilogue* ep) {
 
 static inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// Scope in which this thread's stream-capture interaction mode is "relaxed", so an allocation / release issued while the
+// thread happens to be capturing a CUDA graph neither fails nor invalidates the capture.
+struct RelaxedCaptureMode {
+  cudaStreamCaptureMode mode = cudaStreamCaptureModeRelaxed;
+  RelaxedCaptureMode() { cudaThreadExchangeStreamCaptureMode(&mode); }
+  ~RelaxedCaptureMode() { cudaThreadExchangeStreamCaptureMode(&mode); }
+};
+
 }  // namespace usf
 
 using namespace usf;
@@ -639,7 +647,10 @@ int usf_plan_finalize(usf_plan* p) {
   }
   p->out_width = width;
   const size_t total = (size_t)usf_plan_workspace_bytes(p);
-  USF_CUDA_OK(cudaMalloc(&p->mem, total));
+  {   // legal even if the calling thread is capturing a graph (thread-local / global capture modes forbid cudaMalloc)
+    RelaxedCaptureMode relaxed;
+    USF_CUDA_OK(cudaMalloc(&p->mem, total));
+  }
   char* at = reinterpret_cast<char*>(p->mem);
   for (int i = 0; i < 2; ++i) carve_planes(&p->x[i], stream_planes(p->mode) | 1, p->max_rows, ws, at);
   for (int i = 0; i < 2; ++i) carve_planes(&p->h[i], hidden_planes(p->mode), p->max_rows, wh, at);
@@ -665,7 +676,12 @@ int usf_flow_logprob(const usf_plan* p, const float* x, int64_t ldx, int64_t row
 
 int usf_plan_destroy(usf_plan* p) {
   if (!p) return USF_OK;
-  if (p->mem) cudaFree(p->mem);
+  if (p->mem) {
+    // a host may destroy a plan from a finaliser that runs while this thread captures a graph: cudaFree would invalidate
+    // the capture in the thread-local / global modes
+    RelaxedCaptureMode relaxed;
+    cudaFree(p->mem);
+  }
   delete p;
   return USF_OK;
 }

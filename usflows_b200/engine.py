@@ -770,6 +770,7 @@ class CPlan:
         lib = _lib.load()
         self._lib, self.prog, self.base, self.max_rows, self.d_in = lib, prog, base, int(max_rows), int(d_in)
         handle = C.c_void_p()
+        CPlan._drain_parked()
         _lib.check(lib.usf_plan_create(C.byref(handle), d_in, _lib.MODE_CODES[prog.mode], int(max_rows)))
         self.handle = handle
         self._keep = []
@@ -803,10 +804,33 @@ class CPlan:
             raise
         self.out_width = prog.out_width(d_in)
 
+    # A plan owns device memory that usf_plan_destroy releases with cudaFree, and the garbage collector may run a plan's
+    # __del__ at ANY point -- also while a CUDA graph is being captured on this thread, where cudaFree is not permitted
+    # and invalidates the capture (seen: a plan of an earlier weight version collected inside `_log_prob_small_batch`'s
+    # capture).  Destruction under a capture is therefore parked and carried out by the next close / create outside one.
+    _parked: List[tuple] = []
+
+    @staticmethod
+    def _capturing() -> bool:
+        try:
+            return torch.cuda.is_available() and torch.cuda.is_current_stream_capturing()
+        except Exception:                      # noqa: BLE001
+            return False
+
+    @classmethod
+    def _drain_parked(cls) -> None:
+        while cls._parked and not cls._capturing():
+            lib, handle = cls._parked.pop()
+            lib.usf_plan_destroy(handle)
+
     def close(self) -> None:
         if getattr(self, "handle", None) is not None:
-            self._lib.usf_plan_destroy(self.handle)
-            self.handle = None
+            handle, self.handle = self.handle, None
+            if self._capturing():
+                CPlan._parked.append((self._lib, handle))
+            else:
+                self._lib.usf_plan_destroy(handle)
+                CPlan._drain_parked()
 
     def __del__(self):
         try:

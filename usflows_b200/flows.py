@@ -55,18 +55,29 @@ class _plain_stream_order:
     """Kernels captured into a CUDA graph are launched without programmatic dependent launch: inside a graph the
     programmatic edges bought nothing and cost 4% on the chunked host path (measured); on a plain stream they hide the
     launch latency and the next kernel's prologue (-1.7% per step).  Holds the process-wide capture lock: the row-shard
-    driver (parallel.py) warms several devices up from several threads."""
+    driver (parallel.py) warms several devices up from several threads.
+
+    Also keeps the cyclic garbage collector off for the duration of the capture: a collection that starts inside it may
+    finalise CUDA graphs and plans of an earlier weight version, and `cudaGraphExecDestroy` / `cudaFree` issued by the
+    capturing thread invalidate a thread-local capture ("operation not permitted when stream is capturing"; torch >= 2.9
+    no longer collects before a capture by itself).  The garbage is collected after the capture instead."""
 
     def __enter__(self):
+        import gc
         from . import _lib
         _capture_lock.acquire()
+        self._gc_was_on = gc.isenabled()
+        gc.disable()
         _lib.check(_lib.load().usf_debug_set_pdl(0))
 
     def __exit__(self, *exc):
+        import gc
         from . import _lib
         try:
             _lib.check(_lib.load().usf_debug_set_pdl(1))
         finally:
+            if self._gc_was_on:
+                gc.enable()
             _capture_lock.release()
         return False
 
