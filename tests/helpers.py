@@ -79,3 +79,47 @@ def layer_kinds(flow):
     """Class names of a flow's layers with the wrapped / block transform, as make_golden_simplify.py records them."""
     return [type(l).__name__ + ("/" + type(l.transform).__name__ if hasattr(l, "transform") else "")
             + ("/" + type(l.block_transform).__name__ if hasattr(l, "block_transform") else "") for l in flow.layers]
+
+
+def load_layers_golden():
+    """Outputs of the reference's Rotation / CompositeRotation / BlockLUTransform (oracle/make_golden_layers.py)."""
+    z = np.load(os.path.join(GOLDEN, "layers.npz"))
+    return {k: (torch.from_numpy(np.asarray(z[k])) if z[k].shape else float(z[k])) for k in z.files}
+
+
+def check_standalone_layers(device, tol=1e-5):
+    """Rotation, CompositeRotation and BlockLUTransform against the reference's outputs; shared by the emulated-backend
+    test (CPU) and the GPU test."""
+    import usflows_b200 as U
+    G = load_layers_golden()
+    x = G["rot:x"].to(device)
+    rot = U.Rotation(5, (1, 3), 0.7).to(device)
+    y = rot.forward(x)
+    assert rel_err(y, G["rot:y"]) <= tol
+    assert torch.equal(rot.as_matrix(), G["rot:matrix"])
+    assert rel_err(rot.backward(y), G["rot:x"]) <= tol                 # the inverse (the reference's backward is not)
+    assert float(rot.log_abs_det_jacobian(x, y)) == 0.0
+    comp = U.CompositeRotation([U.Rotation(5, (0, 1), 0.3), U.Rotation(5, (1, 4), -1.1), U.Rotation(5, (2, 0), 2.0)]).to(device)
+    yc = comp.forward(x)
+    assert rel_err(yc, G["comp:y"]) <= tol
+    assert rel_err(comp.as_matrix(), G["comp:as_matrix"]) <= 1e-6      # the reference's (reversed-order) product, literally
+    assert rel_err(comp.backward(yc), G["rot:x"]) <= tol
+    assert rel_err(yc, G["rot:x"].double() @ comp.matrix().double().cpu().t()) <= tol
+    for tag, in_dims in (("blu_flat", [6]), ("blu_img", [4, 3, 5])):
+        t = U.BlockLUTransform(in_dims)
+        t.load_state_dict({k.split(":param:")[1]: v for k, v in G.items() if k.startswith(tag + ":param:")})
+        t = t.to(device)
+        xs = G[f"{tag}:x"].to(device)
+        assert sorted(t.state_dict()) == ["L_raw", "U_raw", "bias_vector"]
+        assert abs(float(t.log_abs_det_jacobian(xs, xs)) - G[f"{tag}:ladj"]) <= 1e-5 * max(1.0, abs(G[f"{tag}:ladj"]))
+        assert abs(float(t.log_prior()) - G[f"{tag}:log_prior"]) <= 1e-4 * max(1.0, abs(G[f"{tag}:log_prior"]))
+        base = U.Normal(torch.zeros(*in_dims), torch.ones(*in_dims))
+        flow = U.Flow(base, [t], device=device)
+        assert rel_err(flow._forward(xs), G[f"{tag}:y"]) <= tol
+        z = flow.backward(xs)
+        assert rel_err(z, G[f"{tag}:z"]) <= tol
+        want = torch.distributions.Normal(0.0, 1.0).log_prob(G[f"{tag}:z"].double()).reshape(xs.shape[0], -1).sum(1) \
+            - G[f"{tag}:ladj"]
+        assert rel_err(flow.log_prob(xs), want) <= tol
+        simple = flow.simplify()
+        assert rel_err(simple.log_prob(xs), want) <= tol

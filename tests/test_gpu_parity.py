@@ -543,3 +543,10 @@ def test_graph_capture_survives_garbage_collection_of_old_programs():
         gc.set_threshold(*thresholds)
     assert torch.equal(got, want) and torch.equal(again, want)
     assert rel_err(got, arr["lp32"]) <= 1e-5
+
+
+def test_rotation_and_block_lu_layers_match_the_reference():
+    """`Rotation`, `CompositeRotation` (transforms.py:476-616) and `BlockLUTransform` (transforms.py:1488-1622) on the
+    device against outputs of the reference (tests/golden/layers.npz)."""
+    from helpers import check_standalone_layers
+    check_standalone_layers("cuda")

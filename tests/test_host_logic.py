@@ -292,3 +292,10 @@ def test_soft_training_needs_a_conditional_conditioner(fake_ops):
         flow.log_prob(arr["x"])
     plain = build_flow(spec, params, device="cpu")                    # USFlow drops a context unless soft_training
     assert torch.equal(plain.log_prob(arr["x"], context=torch.ones(arr["x"].shape[0], 1)), plain.log_prob(arr["x"]))
+
+
+def test_rotation_and_block_lu_layers_match_the_reference(fake_ops):
+    """`Rotation`, `CompositeRotation` (transforms.py:476-616) and `BlockLUTransform` (transforms.py:1488-1622) against
+    outputs of the reference (tests/golden/layers.npz)."""
+    from helpers import check_standalone_layers
+    check_standalone_layers("cpu")

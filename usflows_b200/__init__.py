@@ -15,8 +15,8 @@ from .nn import (CondConvNet, CondConvNet2D, ConvNet, ConvNet2D, DenseNN, GatedC
                  LayerNormChannels, LayerNormChannelsND, LayerNormVector)
 from .optim import SophiaG  # noqa: F401
 from .transforms import Bijective1x1Conv2d, MaskedAffineCoupling, PlaneBijectiveLinearTransform  # noqa: F401
-from .transforms import (AffineTransform, BaseTransform, BlockAffineTransform, HouseholderTransform,  # noqa: F401
-                         InverseTransform, LeakyReLUTransform, LUTransform, MaskedCoupling, Permute, ScaleTransform,
-                         SequentialAffineTransform)
+from .transforms import (AffineTransform, BaseTransform, BlockAffineTransform, BlockLUTransform,  # noqa: F401
+                         CompositeRotation, HouseholderTransform, InverseTransform, LeakyReLUTransform, LUTransform,
+                         MaskedCoupling, Permute, Rotation, ScaleTransform, SequentialAffineTransform)
 
 __version__ = "0.1.0"

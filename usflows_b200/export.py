@@ -58,7 +58,7 @@ class ReferenceSemantics(torch.nn.Module):
             elif isinstance(layer, T.AffineTransform):
                 W, Winv, b, ladj = _affine_tensors(layer)
                 self.kinds.append("affine")
-                for t in (W, Winv, b, ladj):
+                for t in (W, Winv, b, ladj * getattr(layer, "n_blocks", 1)):     # BlockLUTransform: per block
                     reg(t)
             elif type(layer) is T.MaskedCoupling and not hasattr(layer.conditioner, "layers"):
                 # the reference's own conditioners: networks.ConvNet (vector branch) / networks.ConvNet2D

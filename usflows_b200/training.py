@@ -125,6 +125,9 @@ def affine_parts(t, cache: Optional[dict] = None):
         C = t.in_channels
         b = t.forward_conv.bias if t.forward_conv.bias is not None else t.forward_conv.weight.new_zeros(C)
         return t.forward_conv.weight.reshape(C, C), t.inverse_conv.weight.reshape(C, C), b, t.ladj
+    if isinstance(t, T.Rotation):                                 # fixed orthogonal maps (transforms.py:476-616)
+        R = t._prepared()["matrix"]
+        return R, R.t(), R.new_zeros(t.dim), R.new_zeros(())
     if isinstance(t, T.HouseholderTransform):
         W = t.w_0
         for k in range(t.nvs):
@@ -153,9 +156,9 @@ def _layer_backward(layer, y: torch.Tensor, inverse: bool = False, cache: Option
     if isinstance(layer, T.InverseTransform):
         x, ladj = _layer_backward(layer.transform, y, not inverse, cache, geom, context)
         return x, -ladj
-    if isinstance(layer, (T.BlockAffineTransform, T.Bijective1x1Conv2d)):
+    if isinstance(layer, (T.BlockAffineTransform, T.Bijective1x1Conv2d, T.AffineTransform)):
         W, Winv, b, ladj = affine_parts(getattr(layer, "block_transform", layer), cache)
-        ladj = ladj * layer.n_blocks
+        ladj = ladj * getattr(layer, "n_blocks", 1)    # BlockLUTransform carries its own; a bare affine layer is one block
         if inverse:                                     # the layer's forward: x W^T + b      (transforms.py:913-934)
             return linear(y, W, b), ladj
         return linear(y - b, Winv), ladj                # (y - b) Winv^T                       (transforms.py:936-962)

@@ -372,6 +372,130 @@ class LUTransform(AffineTransform):
         return -(x * x).sum() / (2 * self.prior_scale ** 2) - x.sum()
 
 
+class BlockLUTransform(LUTransform):
+    """An LU layer over the leading axis of `in_dims`, applied to every block of the remaining axes (a 1x1 convolution for
+    `[C, H, W]`): transforms.py:1488-1622.  The same map as `BlockAffineTransform(in_dims, LUTransform(in_dims[0]))` with
+    the parameters `L_raw`, `U_raw`, `bias_vector` at the top level; log|det| = sum log|U_kk| x prod(in_dims[1:]).
+    (`sign()` raises in the reference -- it reads a `block_transform` the class does not have; here it is the LU sign to
+    the power of the block count.)"""
+
+    def __init__(self, in_dims: Iterable[int], prior_scale: float = 1.0):
+        self.in_dims = list(in_dims)
+        self.block_size = self.in_dims[0]
+        self.input_rank = len(self.in_dims) - 1
+        self.n_blocks = math.prod(self.in_dims[1:])
+        if self.input_rank not in (0, 2):
+            raise NotImplementedError("usflows_b200: in_dims=[d] (flat) and [C, H, W] (1x1 convolution) are built")
+        super().__init__(self.block_size, prior_scale)
+
+    def log_abs_det_jacobian(self, x=None, y=None, context=None):
+        return super().log_abs_det_jacobian(x, y, context) * self.n_blocks
+
+    def _ladj_device(self):
+        ladj = self._prepared()["ladj"]
+        return ladj * torch.tensor([float(self.n_blocks), 1.0], device=ladj.device)
+
+    def sign(self):
+        return super().sign() ** self.n_blocks
+
+    def log_prior(self, correlated: bool = False):
+        """Log-normal prior on |diag U| (transforms.py:1565-1591): precision of the (optionally negatively correlated)
+        covariance `prior_scale^2 / d * I`."""
+        d = self.block_size
+        x = self.U_raw.diag().abs().log()
+        if correlated:
+            cov = (-1 / d * torch.ones(d, d, device=x.device) + (1 + 1 / d) * torch.eye(d, device=x.device)) * self.prior_scale ** 2
+        else:
+            cov = torch.eye(d, device=x.device) * (self.prior_scale ** 2 / d)
+        return -(x * (torch.linalg.inv(cov) @ x)).sum() - x.sum()
+
+    def simplify(self):
+        """Plain-matrix form, as `BlockAffineTransform.simplify` (the reference inherits `AffineTransform.simplify`, which
+        drops the block structure: transforms.py:749-750)."""
+        return BlockAffineTransform(self.in_dims, LUTransform._to_plane_linear(self)).simplify() \
+            if self.input_rank == 2 else BlockAffineTransform(self.in_dims, LUTransform._to_plane_linear(self))
+
+
+class Rotation(AffineTransform):
+    """Rotation by `angle` in the coordinate plane `plane` of R^dim (transforms.py:476-556); log|det| = 0.  `forward` is
+    the reference's map.  `backward` is its INVERSE: the reference's backward overwrites y[plane[0]] and then uses the
+    overwritten value for y[plane[1]] (transforms.py:521-524), which is not the inverse rotation (round-trip error of
+    order sin(angle)) -- a deviation of the same kind as SURVEY Q1."""
+
+    ladj = 0
+
+    def __init__(self, dim: int, plane, angle: float):
+        if dim < 2:
+            raise ValueError("dim must be at least 2")
+        if plane[0] == plane[1]:
+            raise ValueError("plane must be a tuple of different indices")
+        if dim <= max(plane):
+            raise ValueError("plane indices must be smaller than dim")
+        super().__init__(dim)
+        self.plane = tuple(plane)
+        self.angle = angle
+        self.register_buffer("_anchor", torch.zeros(1), persistent=False)      # follows .to(device): where the map lives
+
+    def as_matrix(self) -> torch.Tensor:
+        R = torch.eye(self.dim)
+        i, j = self.plane
+        c, s = math.cos(self.angle), math.sin(self.angle)
+        R[i, i], R[i, j], R[j, i], R[j, j] = c, -s, s, c
+        return R
+
+    def _matrix64(self) -> torch.Tensor:
+        R = torch.eye(self.dim, dtype=torch.float64)
+        i, j = self.plane
+        c, s = math.cos(self.angle), math.sin(self.angle)
+        R[i, i], R[i, j], R[j, i], R[j, j] = c, -s, s, c
+        return R
+
+    def _prep_params(self) -> List[torch.Tensor]:
+        return [self._anchor]
+
+    def _prepare(self) -> dict:
+        dev = self._anchor.device
+        R = self._matrix64().to(dev)
+        return dict(matrix=R.float(), inverse_matrix=R.t().contiguous().float(),
+                    bias=torch.zeros(self.dim, dtype=torch.float32, device=dev),
+                    ladj=torch.zeros(2, dtype=torch.float32, device=dev), matrix64=R, inverse64=R.t().contiguous())
+
+    def log_abs_det_jacobian(self, x=None, y=None, context=None):
+        return self.ladj
+
+    def sign(self):
+        return 1
+
+    def simplify(self):
+        return self
+
+
+class CompositeRotation(Rotation):
+    """Rotations applied one after the other, `y = R_n ... R_1 x` (transforms.py:558-616); `backward` is the inverse (see
+    `Rotation`).  `as_matrix()` returns the reference's product `R_1 R_2 ... R_n` literally -- which is the matrix of the
+    rotations applied in the OPPOSITE order (transforms.py:580-584), not of `forward`; `matrix()` is the map `forward`
+    applies."""
+
+    def __init__(self, rotations: List[Rotation]):
+        rotations = list(rotations)
+        AffineTransform.__init__(self, rotations[0].dim)
+        self.rotations = rotations
+        self.input_shape = rotations[0].dim
+        self.register_buffer("_anchor", torch.zeros(1), persistent=False)
+
+    def as_matrix(self) -> torch.Tensor:
+        R = torch.eye(self.input_shape)
+        for rot in self.rotations:
+            R = torch.matmul(R, rot.as_matrix())
+        return R
+
+    def _matrix64(self) -> torch.Tensor:
+        R = torch.eye(self.dim, dtype=torch.float64)
+        for rot in self.rotations:                     # forward applies rot_1 first: x -> R_n ... R_1 x
+            R = rot._matrix64() @ R
+        return R
+
+
 class HouseholderTransform(AffineTransform):
     """y = H x, H = w_0 prod_k (I - 2 v_k v_k^T / v_k.v_k)  (transforms.py:752-872); log|det| = 0."""
 
