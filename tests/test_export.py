@@ -3,7 +3,7 @@ agree with the outputs of the REAL reference (golden fixtures) -- and must not l
 import pytest
 import torch
 
-from helpers import EXT_CASES, IMG_CASES, SMALL_CASES, build_flow, load_case, rel_err
+from helpers import EXT_CASES, IMG_CASES, SMALL_CASES, SOFT_CASES, build_flow, load_case, rel_err
 
 
 def _flow(name):
@@ -25,7 +25,7 @@ def test_reference_module_reproduces_the_reference(name):
     assert s.shape == (7, arr["x"].shape[1]) and torch.isfinite(s).all()
 
 
-@pytest.mark.parametrize("name", EXT_CASES[:5] + IMG_CASES)
+@pytest.mark.parametrize("name", EXT_CASES[:5] + IMG_CASES + SOFT_CASES)
 def test_reference_module_covers_convnet_radial_and_image_flows(name):
     """ConvNet (vector) / ConvNet2D conditioners, Lp-radial bases, image-shaped events."""
     flow, arr = _flow(name)
