@@ -84,3 +84,76 @@ def test_random_configuration_matches_oracle_on_gpu(seed):
         assert rel_err(flow._forward(z0.cuda()), want_y) <= 3 * e_y + 3e-5, (spec, mode)
     s = flow.sample([5])
     assert s.shape == (5, *spec["in_dims"]) and bool(torch.isfinite(s).all())
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Second sweep: the families added late in round 2 -- networks.ConvNet's convolutional branch (varying widths, projected
+# residuals), the context-conditioned conditioners of soft training (with and without an explicit context), simplify().
+# ----------------------------------------------------------------------------------------------------------------------
+def _draw_wide(seed: int):
+    rng = random.Random(5000 + seed)
+    image = rng.random() < 0.6
+    soft = rng.random() < 0.5
+    spec = dict(coupling_blocks=rng.randint(1, 3), affine_conjugation=rng.random() < 0.6, lu_transform=rng.randint(1, 2),
+                householder=rng.choice([0, 0, 1, 2]), masktype=rng.choice(["checkerboard", "channel"]) if image else "checkerboard",
+                soft_training=soft, gating=rng.random() < 0.7, normalize_layers=rng.random() < 0.7)
+    if image:
+        spec["in_dims"] = [rng.choice([4, 6, 8, 16]), rng.randint(3, 6), rng.randint(3, 6)]
+        if rng.random() < 0.4:
+            spec.update(conditioner="condconvnet2d" if soft else "convnet2d", c_hidden=rng.choice([4, 8, 16]),
+                        num_layers=rng.randint(1, 3), kernel_size=rng.choice([1, 3, 3, 5]))
+        else:
+            spec.update(conditioner="condconvnet" if soft else "convnet", kernel_size=rng.choice([1, 3, 3]),
+                        c_hidden=[rng.choice([4, 8, 12, 16]) for _ in range(rng.randint(1, 3))])
+    else:
+        spec["in_dims"] = [rng.choice([8, 12, 16, 24, 40])]
+        spec.update(conditioner="condconvnet" if soft else "convnet",
+                    c_hidden=[rng.choice([8, 16, 24]) for _ in range(rng.randint(1, 3))])
+    base = rng.choice(["laplace", "normal", "radial"])
+    spec["base"] = base
+    if base == "radial":
+        spec.update(p=rng.choice([1, 2, "inf"]), norm=rng.choice(["lognormal", "gammamm"]), n_comp=rng.randint(2, 9))
+    return spec
+
+
+def _check_wide(seed: int, device: str, n: int, modes, slack_lp: float, slack_z: float):
+    spec = _draw_wide(seed)
+    params = O.random_params(spec, 7000 + seed)
+    g = torch.Generator().manual_seed(seed)
+    x = torch.rand(n, *spec["in_dims"], generator=g)
+    z0 = torch.randn(n, *spec["in_dims"], generator=g)
+    ctx = torch.rand(n, 1, generator=g) * 2
+    want_lp = O.flow_log_prob(x, spec, params, dtype=torch.float64)
+    want_z = O.flow_backward(x, spec, params, dtype=torch.float64)
+    want_y = O.flow_forward(z0, spec, params, dtype=torch.float64)
+    e_lp = rel_err(O.flow_log_prob(x, spec, params), want_lp)
+    e_z = rel_err(O.flow_backward(x, spec, params), want_z)
+    e_y = rel_err(O.flow_forward(z0, spec, params), want_y)
+    xd, zd = x.to(device), z0.to(device)
+    for mode in modes:
+        flow = build_flow(spec, params, device=device, precision=mode)
+        assert rel_err(flow.log_prob(xd), want_lp) <= 3 * e_lp + slack_lp, (spec, mode)
+        assert rel_err(flow.backward(xd), want_z) <= 3 * e_z + slack_z, (spec, mode)
+        assert rel_err(flow._forward(zd), want_y) <= 3 * e_y + slack_z, (spec, mode)
+        if spec["soft_training"]:
+            cspec = dict(spec, _context=ctx.double())
+            want_ctx = O.flow_log_prob(x, cspec, params, dtype=torch.float64)
+            e_ctx = rel_err(O.flow_log_prob(x, dict(spec, _context=ctx), params), want_ctx)
+            assert rel_err(flow.log_prob(xd, context=ctx.to(device)), want_ctx) <= 3 * e_ctx + slack_lp, (spec, mode)
+    simple = flow.simplify()
+    assert rel_err(simple.log_prob(xd), want_lp) <= 6 * e_lp + 2 * slack_lp, spec
+    return flow, spec, x, want_lp, e_lp
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_random_wide_configuration_matches_oracle(fake_ops, seed):
+    flow, spec, x, want_lp, e_lp = _check_wide(seed, "cpu", 9, ("fp32_simt", "fp32"), 2e-5, 5e-5)
+    assert rel_err(flow.reference_module("log_prob")(x), want_lp) <= 3 * e_lp + 2e-5, spec
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", range(16))
+def test_random_wide_configuration_matches_oracle_on_gpu(seed):
+    flow, spec, _, _, _ = _check_wide(seed, "cuda", 300, ("fp32", "fp32_tf32"), 1e-5, 3e-5)
+    s = flow.sample([5])
+    assert s.shape == (5, *spec["in_dims"]) and bool(torch.isfinite(s).all())
