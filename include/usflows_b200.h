@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define USF_ABI_VERSION 5
+#define USF_ABI_VERSION 6
 
 #define USF_OK 0
 #define USF_ERR_INVALID (-1)     /* bad argument (shape, alignment, null pointer) */
@@ -49,6 +49,9 @@ extern "C" {
 #define USF_LP_2 2
 #define USF_NORM_LOGNORMAL 0     /* params = [mu, sigma]                                  (distributions.py:181-197) */
 #define USF_NORM_GAMMA_MIXTURE 1 /* params = [logits (K) | concentration (K) | rate (K)]  (distributions.py:674-707) */
+#define USF_NORM_GAMMA_MIXTURE_SQ 2 /* R = scale * sqrt(S), S ~ the Gamma mixture: params = [logits | concentration | rate | scale];
+                                       log f_R(r) = log f_S((r/scale)^2) + log(2 r / scale) - log(scale) -- the reference's Chi(df, scale)
+                                       (distributions.py:55-116: Chi2 = Gamma(df/2, 1/2)) and torch's HalfNormal (ABI 6) */
 
 /* output planes of an activation in the operand format(s) of an engine mode; unused planes are NULL */
 typedef struct usf_planes {

@@ -506,21 +506,49 @@ def radial_norm_distribution(spec: dict, params):
     if spec["norm"] == "lognormal":
         d = torch.distributions.LogNormal(params[q + "loc"], F.softplus(params[q + "scale_unconstrained"]))
         return torch.distributions.Independent(d, len(d.batch_shape))
+    if spec["norm"] == "chi":           # distributions.py:55-115: scale * sqrt(Chi2(df)); log_prob as written at :88-97
+        return _Chi(torch.tensor(float(spec["df"]), dtype=params["base_distribution.loc"].dtype), spec.get("chi_scale", 1.0))
+    if spec["norm"] == "chi2":          # torch objects passed straight in (experiments/mnist/mnist_digits_minimal_radial_chi2.yaml:63)
+        return torch.distributions.Chi2(torch.tensor(float(spec["df"]), dtype=params["base_distribution.loc"].dtype))
+    if spec["norm"] == "halfnormal":    # experiments/mnist/mnist_digits_minimal_radialdists.yaml:95
+        return torch.distributions.HalfNormal(torch.tensor(float(spec["chi_scale"]), dtype=params["base_distribution.loc"].dtype))
     conc = F.softplus(params[q + "concentration_unconstrained"])
     rate = F.softplus(params[q + "rate_unconstrained"])
+    if spec["norm"] == "gamma":         # distributions.py:162-179, made Independent over its batch dim (:129-138)
+        d = torch.distributions.Gamma(conc, rate)
+        return torch.distributions.Independent(d, len(d.batch_shape))
     return torch.distributions.MixtureSameFamily(torch.distributions.Categorical(logits=params[q + "mixture_logits"]),
                                                  torch.distributions.Gamma(conc, rate), validate_args=False)
 
 
+class _Chi:
+    """distributions.py:55-115, `log_prob` term by term: chi2.log_prob((v / scale)^2) + log(2 v / scale) - log(scale)."""
+
+    def __init__(self, df, scale):
+        self.chi2, self.scale = torch.distributions.Chi2(df), scale
+
+    def log_prob(self, value):
+        value = value / self.scale
+        return self.chi2.log_prob(value ** 2) + torch.log(value * 2) - torch.log(torch.tensor(self.scale, dtype=value.dtype))
+
+    def sample(self, sample_shape=torch.Size()):
+        return self.scale * torch.sqrt(self.chi2.sample(sample_shape))
+
+
 def radial_log_delta_volume(p: float, r: Tensor, dim: int) -> Tensor:
-    """distributions.py:514-549, term by term in the reference's order."""
+    """distributions.py:514-549, term by term in the reference's order.  The reference's `self.dim` is a 0-dim int64 TENSOR
+    (`torch.prod(torch.tensor(loc.shape))`, :364), so `x * self.dim` / `self.dim / 2` are fp32 tensor operations under the
+    default dtype and `math.log(self.dim)` a Python float -- restated with the same operand types (the constants then
+    round where the reference's do; with a Python int the p = 2 value differed by one fp32 ulp)."""
+    dim = torch.tensor(int(dim))
+    dimf = dim.to(r.dtype)      # int tensor (*, /) Python float -> the default dtype, which is r's dtype when the reference runs
     if p == 1:
         log_denominator = sum([math.log(i) for i in range(1, dim)])
-        return math.log(2) * dim + torch.log(r) * (dim - 1) - log_denominator
+        return math.log(2) * dimf + torch.log(r) * (dim - 1) - log_denominator
     if p == 2:
-        log_numerator = math.log(dim) + (dim / 2) * math.log(math.pi) + (dim - 1) * torch.log(r)
-        return log_numerator - math.lgamma((dim / 2) + 1)
-    return math.log(dim) + dim * math.log(2) + (dim - 1) * torch.log(r)
+        log_numerator = math.log(dim) + (dimf / 2) * math.log(math.pi) + (dim - 1) * torch.log(r)
+        return log_numerator - math.lgamma((dimf / 2) + 1)
+    return math.log(dim) + dimf * math.log(2) + (dim - 1) * torch.log(r)
 
 
 def radial_log_prob(x: Tensor, spec: dict, params) -> Tensor:
@@ -822,6 +850,11 @@ def random_params(spec: dict, seed: int = 0, min_abs_scale: float = 0.1) -> Dict
         if spec["norm"] == "lognormal":                       # experiments/mnist/mnist.yaml:86-92 (loc 6, scale .35 at d=784)
             out[q + "loc"] = torch.full((1,), 0.5 * math.log(dtot))
             out[q + "scale_unconstrained"] = inv_softplus(torch.full((1,), 0.35))
+        elif spec["norm"] == "gamma":
+            out[q + "concentration_unconstrained"] = inv_softplus(0.5 + torch.rand(1, generator=g) * math.sqrt(dtot))
+            out[q + "rate_unconstrained"] = inv_softplus(0.5 + torch.rand(1, generator=g))
+        elif spec["norm"] in ("chi", "chi2", "halfnormal"):   # no learnable radius parameters (distributions.py:55-75)
+            pass
         else:                                                 # experiments/synthetic/gaussian_mixture.yaml:84-91
             K = int(spec.get("n_comp", 20))
             out[q + "concentration_unconstrained"] = inv_softplus(0.2 + torch.rand(K, generator=g) * math.sqrt(dtot))

@@ -13,11 +13,14 @@ SMALL_CASES = ["c1_d2_laplace", "d2_refinit", "d6_hh_normal", "d5_noconj", "d32_
 LARGE_CASES = ["c2_d784", "c4_d3072_b2"]
 # networks.ConvNet (vector branch) conditioners, Lp-radial bases (LogNormal / GammaMM radius)
 EXT_CASES = ["d64_convnet", "d64_convnet_proj_radial2", "d40_convnet_plain_gmm1", "d64_convnet_noln", "d32_radial_inf",
-             "d784_radial1_lognormal"]
+             "d784_radial1_lognormal",
+             # the other radius distributions of the reference's configurations: its Chi, torch's Chi2 / HalfNormal
+             "d32_radial2_chi", "d24_radial1_chi2", "d16_radialinf_halfnormal"]
 # image-shaped events [C, H, W] (1x1-convolution BlockAffine, ConvNet2D conditioners, [C, H, W] masks)
 IMG_CASES = ["img_c4_4x4", "img_mnist_16x7x7", "img_c6_5x3_plain_channel", "img_c32_4x4_noln",
              # networks.ConvNet's convolutional branch (networks.py:308-377) as the conditioner
-             "img_convnet_c4_4x4_proj", "img_convnet_c6_5x3_plain", "img_convnet_16x7x7"]
+             "img_convnet_c4_4x4_proj", "img_convnet_c6_5x3_plain", "img_convnet_16x7x7",
+             "img_c4_4x4_radial2_gamma"]      # single-Gamma radius (distributions.py:162-179)
 # soft training (flows.py:172-193, 559-565): context-conditioned conditioners; fixtures also hold `ctx`, `lp32_ctx`, `lp64_ctx`
 SOFT_CASES = ["soft_img_c4_4x4", "soft_img_mnist_16x7x7", "soft_img_convnet_c4_4x4", "soft_d24_convnet"]
 

@@ -96,6 +96,14 @@ def test_radial_constructor_contract():
     assert sorted(r.state_dict()) == ["loc", "norm_distribution.loc", "norm_distribution.scale_unconstrained"]
     g = U.GammaMM(torch.ones(5), torch.ones(5), torch.ones(5) / 5)
     assert sorted(g.state_dict()) == ["concentration_unconstrained", "mixture_logits", "rate_unconstrained"]
+    assert sorted(U.Gamma(torch.ones(1), torch.ones(1)).state_dict()) == ["concentration_unconstrained", "rate_unconstrained"]
+    # the reference's Chi and torch's Chi2 / HalfNormal carry no parameters: only `loc` is in the state dict
+    for nd0 in (U.Chi(6, 1.5), torch.distributions.Chi2(torch.tensor(6.0)), torch.distributions.HalfNormal(torch.tensor(2.0))):
+        assert sorted(U.RadialDistribution(torch.zeros(6), nd0, p=2.0).state_dict()) == ["loc"]
+    with pytest.raises(NotImplementedError):
+        U.RadialDistribution(torch.zeros(6), torch.distributions.Weibull(torch.tensor(1.0), torch.tensor(1.0)), p=2.0)
+    with pytest.raises(ValueError):
+        U.Chi(-1.0)
     # r-independent part of the differential volume against the oracle's formula at r = 1
     for p in (1.0, 2.0, math.inf):
         rd = U.RadialDistribution(torch.zeros(9), nd, p=p)
@@ -103,7 +111,8 @@ def test_radial_constructor_contract():
         assert abs(rd.log_delta_volume_const() - want) < 1e-12
 
 
-@pytest.mark.parametrize("name", ["d64_convnet_proj_radial2", "d40_convnet_plain_gmm1", "d64_convnet_noln"])
+@pytest.mark.parametrize("name", ["d64_convnet_proj_radial2", "d40_convnet_plain_gmm1", "d64_convnet_noln",
+                                  "d32_radial2_chi", "img_c4_4x4_radial2_gamma"])
 def test_training_pass_matches_oracle_gradients(fake_ops, name):
     from usflows_b200 import training
     spec, params, arr = load_case(name)
@@ -130,7 +139,9 @@ def test_training_pass_matches_oracle_gradients(fake_ops, name):
 # kernels through the C ABI
 # ---------------------------------------------------------------------------------------------------------------------
 def _radial_spec(p, norm, d, K=20):
-    return dict(in_dims=[d], coupling_blocks=1, hidden_dims=[8], base="radial", p=p, norm=norm, n_comp=K)
+    # df / chi_scale: the Chi-family radius distributions (a `chi_scale`-scaled standard normal in `df` dimensions)
+    return dict(in_dims=[d], coupling_blocks=1, hidden_dims=[8], base="radial", p=p, norm=norm, n_comp=K,
+                df=max(1, d // 2) + 0.5, chi_scale=1.75)
 
 
 def _radial_module(spec, params):
@@ -139,6 +150,14 @@ def _radial_module(spec, params):
     sp = torch.nn.functional.softplus
     if spec["norm"] == "lognormal":
         nd = U.LogNormal(params[q + "loc"].clone(), sp(params[q + "scale_unconstrained"]))
+    elif spec["norm"] == "gamma":
+        nd = U.Gamma(sp(params[q + "concentration_unconstrained"]), sp(params[q + "rate_unconstrained"]))
+    elif spec["norm"] == "chi":
+        nd = U.Chi(spec["df"], spec["chi_scale"])
+    elif spec["norm"] == "chi2":                  # torch objects go straight in, as in the reference's configurations
+        nd = torch.distributions.Chi2(torch.tensor(float(spec["df"])))
+    elif spec["norm"] == "halfnormal":
+        nd = torch.distributions.HalfNormal(torch.tensor(float(spec["chi_scale"])))
     else:
         nd = U.GammaMM(sp(params[q + "concentration_unconstrained"]), sp(params[q + "rate_unconstrained"]),
                        params[q + "mixture_logits"].clone())
@@ -148,7 +167,7 @@ def _radial_module(spec, params):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("d", [3, 32, 785, 3072])
-@pytest.mark.parametrize("norm", ["lognormal", "gammamm"])
+@pytest.mark.parametrize("norm", ["lognormal", "gammamm", "gamma", "chi", "chi2", "halfnormal"])
 @pytest.mark.parametrize("p", [1, 2, "inf"])
 def test_radial_logprob_kernel_matches_oracle(p, norm, d):
     spec = _radial_spec(p, norm, d)
@@ -179,7 +198,7 @@ def test_radial_logprob_full_size_rows_and_batch_shapes():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("norm", ["lognormal", "gammamm"])
+@pytest.mark.parametrize("norm", ["lognormal", "gammamm", "gamma", "chi", "chi2", "halfnormal"])
 @pytest.mark.parametrize("p", [1, 2, "inf"])
 def test_radial_sample_properties(p, norm):
     """x - loc = R u with ||u||_p = 1 exactly up to rounding, so the radius of a sample IS its Lp norm: its empirical
@@ -201,9 +220,16 @@ def test_radial_sample_properties(p, norm):
         mu, sg = float(params[q + "loc"]), float(sp(params[q + "scale_unconstrained"]))
         assert abs(float(r.log().mean()) - mu) < 5 * sg / math.sqrt(n) + 1e-4
         assert abs(float(r.log().std()) - sg) < 0.01 * sg
+    elif norm in ("chi", "chi2", "halfnormal"):      # moments of the torch / reference distribution object itself
+        nd = O.radial_norm_distribution(spec, O._cast(params, torch.float64))
+        rs = nd.sample((400000,)).double()
+        mean, second = float(rs.mean()), float((rs ** 2).mean())
+        sd = math.sqrt(max(second - mean ** 2, 0.0))
+        assert abs(float(r.mean()) - mean) < 8 * sd / math.sqrt(n)
+        assert abs(float((r ** 2).mean()) - second) < 0.02 * second
     else:
         a, b = sp(params[q + "concentration_unconstrained"]).double(), sp(params[q + "rate_unconstrained"]).double()
-        w = torch.softmax(params[q + "mixture_logits"].double(), 0)
+        w = torch.softmax(params[q + "mixture_logits"].double(), 0) if norm == "gammamm" else torch.ones(1, dtype=torch.float64)
         mean = float((w * a / b).sum())
         second = float((w * (a * (a + 1) / b ** 2)).sum())
         sd = math.sqrt(second - mean ** 2)

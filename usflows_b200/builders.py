@@ -15,6 +15,14 @@ def build_flow(spec, params=None, device="cuda", precision=None):
     if spec.get("base") == "radial":
         if spec["norm"] == "lognormal":
             nd = U.LogNormal(torch.ones(1), torch.ones(1))
+        elif spec["norm"] == "gamma":
+            nd = U.Gamma(torch.ones(1), torch.ones(1))
+        elif spec["norm"] == "chi":
+            nd = U.Chi(spec["df"], spec.get("chi_scale", 1.0))
+        elif spec["norm"] == "chi2":
+            nd = torch.distributions.Chi2(torch.tensor(float(spec["df"])))
+        elif spec["norm"] == "halfnormal":
+            nd = torch.distributions.HalfNormal(torch.tensor(float(spec["chi_scale"])))
         else:
             K = spec.get("n_comp", 20)
             nd = U.GammaMM(torch.ones(K), torch.ones(K), torch.ones(K) / K)

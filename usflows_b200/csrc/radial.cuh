@@ -61,6 +61,13 @@ __device__ __forceinline__ float radial_norm_logpdf(float radius, float logr, in
     const float u = logr - mu;
     return -(u * u) / (2.f * (sg * sg)) - logf(sg) - 0.91893853320467274178f - logr;
   }
+  float extra = 0.f;
+  if (norm_kind == USF_NORM_GAMMA_MIXTURE_SQ) {   // R = scale sqrt(S): f_R(r) = f_S((r / scale)^2) 2 r / scale^2
+    const float sc = __ldg(params + 3 * K), lsc = logf(sc), u = radius / sc;
+    extra = 0.69314718055994530942f + (logr - lsc) - lsc;
+    logr = 2.f * (logr - lsc);
+    radius = u * u;
+  }
   // Gamma mixture: logsumexp_k [log w_k + a_k log b_k + (a_k - 1) log r - b_k r - lgamma(a_k)]
   float m = -INFINITY;
   for (int k = lane; k < K; k += 32) {
@@ -73,7 +80,7 @@ __device__ __forceinline__ float radial_norm_logpdf(float radius, float logr, in
     const float t = s.c[k] + (s.am1[k] == 0.f ? 0.f : s.am1[k] * logr) - s.b[k] * radius;
     e += expf(t - m);
   }
-  return m + logf(warp_sum(e));
+  return m + logf(warp_sum(e)) + extra;
 }
 
 template <bool VEC>
@@ -82,7 +89,7 @@ radial_logprob_kernel(const float* __restrict__ z, const float* __restrict__ z_l
                       const float* __restrict__ loc, int p_kind, int norm_kind, const float* __restrict__ params, int n_comp,
                       float dv_const, float add_const, float* __restrict__ out) {
   __shared__ GammaMixSmem sm;
-  if (norm_kind == USF_NORM_GAMMA_MIXTURE) gamma_mix_prepare(sm, params, n_comp);
+  if (norm_kind != USF_NORM_LOGNORMAL) gamma_mix_prepare(sm, params, n_comp);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int wpb = RAD_THREADS / 32;
   for (long long r = (long long)blockIdx.x * wpb + warp; r < rows; r += (long long)gridDim.x * wpb) {
@@ -151,7 +158,7 @@ radial_sample_kernel(long long rows, int d, const float* __restrict__ loc, int p
                      const float* __restrict__ params, int n_comp, uint64_t seed, uint64_t offset,
                      float* __restrict__ out, long long ldo) {
   __shared__ GammaMixSmem sm;
-  if (norm_kind == USF_NORM_GAMMA_MIXTURE) gamma_mix_prepare(sm, params, n_comp);
+  if (norm_kind != USF_NORM_LOGNORMAL) gamma_mix_prepare(sm, params, n_comp);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int wpb = RAD_THREADS / 32;
   const int d4 = (d + 3) >> 2;
@@ -173,6 +180,7 @@ radial_sample_kernel(long long rows, int d, const float* __restrict__ loc, int p
         if (a >= 1.f) g = gamma_mt(a, seed, (uint64_t)r, (offset ^ RTAG) + 1);
         else g = gamma_mt(a + 1.f, seed, (uint64_t)r, (offset ^ RTAG) + 1) * powf(u01_open(rnd[1]), 1.f / a);   // boost
         radius = g / b;
+        if (norm_kind == USF_NORM_GAMMA_MIXTURE_SQ) radius = __ldg(params + 3 * n_comp) * sqrtf(radius);
       }
       if (p_kind == USF_LP_INF) {
         uint32_t rnd[4];

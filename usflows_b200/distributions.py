@@ -192,7 +192,28 @@ class LogNormal(_RadiusDistribution):
         return ops.NORM_LOGNORMAL, 1, buf
 
 
-class GammaMM(_RadiusDistribution):
+class _GammaFamily(_RadiusDistribution):
+    """Radius distributions that are a Gamma mixture, or `scale * sqrt` of one: `_mixture()` hands the constrained
+    values (logits [K], concentration [K], rate [K], scale or None) over as differentiable tensors -- the radial kernels
+    read them packed (USF_NORM_GAMMA_MIXTURE / _SQ), the training route and the exportable module evaluate them with torch."""
+
+    def _mixture(self):
+        raise NotImplementedError
+
+    def _pack(self):
+        logits, conc, rate, scale = self._mixture()
+        K = logits.numel()
+        buf = torch.empty(3 * K + (scale is not None), dtype=torch.float32, device=logits.device)
+        buf[:K].copy_(logits.detach().reshape(-1))
+        buf[K:2 * K].copy_(conc.detach().reshape(-1))
+        buf[2 * K:3 * K].copy_(rate.detach().reshape(-1))
+        if scale is None:
+            return ops.NORM_GAMMA_MIXTURE, K, buf
+        buf[3 * K:].copy_(scale.detach().reshape(-1))
+        return ops.NORM_GAMMA_MIXTURE_SQ, K, buf
+
+
+class GammaMM(_GammaFamily):
     """Mixture of K Gamma(concentration_k, rate_k) with weights softmax(mixture_logits)  (distributions.py:674-707)."""
 
     norm_kind = ops.NORM_GAMMA_MIXTURE
@@ -209,13 +230,93 @@ class GammaMM(_RadiusDistribution):
     def _params(self):
         return (self.mixture_logits, self.concentration_unconstrained, self.rate_unconstrained)
 
-    def _pack(self):
-        K = self.mixture_logits.numel()
-        buf = torch.empty(3 * K, dtype=torch.float32, device=self.mixture_logits.device)
-        buf[:K].copy_(self.mixture_logits.detach())
-        buf[K:2 * K].copy_(_softplus_vec(self.concentration_unconstrained))
-        buf[2 * K:].copy_(_softplus_vec(self.rate_unconstrained))
-        return ops.NORM_GAMMA_MIXTURE, K, buf
+    def _mixture(self):
+        sp = torch.nn.functional.softplus
+        return self.mixture_logits, sp(self.concentration_unconstrained), sp(self.rate_unconstrained), None
+
+
+class Gamma(_GammaFamily):
+    """Gamma(softplus(concentration_unconstrained), softplus(rate_unconstrained)) radius (distributions.py:162-179);
+    one-element concentration / rate -- a one-component mixture for the kernels."""
+
+    norm_kind = ops.NORM_GAMMA_MIXTURE
+
+    def __init__(self, concentration: torch.Tensor, rate: torch.Tensor, device: str = "cpu"):
+        super().__init__()
+        if concentration.numel() != 1 or rate.numel() != 1:
+            raise NotImplementedError("usflows_b200.Gamma: one radius distribution per flow (1-element concentration / rate)")
+        self.concentration_unconstrained = Parameter(inv_softplus(concentration))
+        self.rate_unconstrained = Parameter(inv_softplus(rate))
+        self.to(device)
+
+    def _params(self):
+        return (self.concentration_unconstrained, self.rate_unconstrained)
+
+    def _mixture(self):
+        sp = torch.nn.functional.softplus
+        conc = sp(self.concentration_unconstrained).reshape(1)
+        return torch.zeros_like(conc), conc, sp(self.rate_unconstrained).reshape(1), None
+
+
+class Chi(_GammaFamily):
+    """R = scale * sqrt(S), S ~ Chi2(df) = Gamma(df / 2, 1 / 2)  (distributions.py:55-115; the radius of a `scale`-scaled
+    standard normal in `df` dimensions).  No learnable parameters, as in the reference; `df` / `scale` are buffers so that
+    `.to(device)` moves them."""
+
+    norm_kind = ops.NORM_GAMMA_MIXTURE_SQ
+
+    def __init__(self, df, scale: float = 1.0, validate_args=None, device: str = "cpu"):
+        super().__init__()
+        df_t = torch.as_tensor(df, dtype=torch.float32).reshape(-1)
+        if df_t.numel() != 1:
+            raise NotImplementedError("usflows_b200.Chi: one radius distribution per flow (scalar df)")
+        if not (float(df_t) > 0 and float(scale) > 0):
+            raise ValueError("Chi: df and scale must be positive")
+        self.df, self.scale = df, scale
+        self.register_buffer("_df", df_t, persistent=False)
+        self.register_buffer("_scale", torch.full((1,), float(scale)), persistent=False)
+        self.to(device)
+
+    def _params(self):
+        return (self._df, self._scale)
+
+    def _mixture(self):
+        return torch.zeros_like(self._df), self._df / 2, torch.full_like(self._df, 0.5), self._scale
+
+
+class _TorchRadius(_GammaFamily):
+    """A frozen `torch.distributions` object as the radius distribution -- the reference's configurations pass `Chi2(df)`
+    and `HalfNormal(scale)` straight into `RadialDistribution` (experiments/mnist/mnist_digits_minimal_radial_chi2.yaml:63,
+    mnist_digits_minimal_radialdists.yaml:81-95).  Chi2(df) = Gamma(df / 2, 1 / 2); HalfNormal(s) = s * sqrt(Chi2(1));
+    `torch.distributions.Gamma` as is.  Values are read at construction (no parameters, as in the reference)."""
+
+    def __init__(self, dist):
+        super().__init__()
+        D = torch.distributions
+        f = lambda t: torch.as_tensor(t, dtype=torch.float32).detach().reshape(-1).clone()
+        if isinstance(dist, D.Chi2):                # before Gamma: Chi2 is a Gamma subclass
+            conc, rate, scale = f(dist.df) / 2, torch.full_like(f(dist.df), 0.5), None
+        elif isinstance(dist, D.Gamma):
+            conc, rate, scale = f(dist.concentration), f(dist.rate), None
+        elif isinstance(dist, D.HalfNormal):
+            scale = f(dist.scale)
+            conc, rate = torch.full_like(scale, 0.5), torch.full_like(scale, 0.5)
+        else:
+            raise NotImplementedError(f"usflows_b200.RadialDistribution: radius distribution {type(dist).__name__} is not built "
+                                      "(LogNormal, GammaMM, Gamma, Chi, torch Chi2 / Gamma / HalfNormal are)")
+        if conc.numel() != 1:
+            raise NotImplementedError("usflows_b200.RadialDistribution: one radius distribution per flow (scalar parameters)")
+        self.distribution = dist
+        self.norm_kind = ops.NORM_GAMMA_MIXTURE if scale is None else ops.NORM_GAMMA_MIXTURE_SQ
+        self.register_buffer("_conc", conc, persistent=False)
+        self.register_buffer("_rate", rate, persistent=False)
+        self.register_buffer("_scale", scale, persistent=False)
+
+    def _params(self):
+        return (self._conc, self._rate)
+
+    def _mixture(self):
+        return torch.zeros_like(self._conc), self._conc, self._rate, self._scale
 
 
 class RadialDistribution(Module):
@@ -233,6 +334,8 @@ class RadialDistribution(Module):
             raise ValueError(f"p={p} not implemented. Use p=1,2, or infinity")
         if n_batch_dims != 0:
             raise NotImplementedError("usflows_b200.RadialDistribution: n_batch_dims > 0 is not built")
+        if isinstance(norm_distribution, torch.distributions.Distribution):
+            norm_distribution = _TorchRadius(norm_distribution)
         self.norm_distribution = norm_distribution
         self.event_shape = loc.shape[n_batch_dims:]
         self.batch_shape = loc.shape[:n_batch_dims]

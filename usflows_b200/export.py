@@ -106,9 +106,11 @@ class ReferenceSemantics(torch.nn.Module):
                 self.register_buffer("r_sigma", sp(nd.scale_unconstrained.detach()).reshape(()))
             else:
                 self.norm_kind = "gammamm"
-                self.register_buffer("r_logw", torch.log_softmax(nd.mixture_logits.detach(), 0))
-                self.register_buffer("r_conc", sp(nd.concentration_unconstrained.detach()))
-                self.register_buffer("r_rate", sp(nd.rate_unconstrained.detach()))
+                logits, conc, rate, scale = (None if t is None else t.detach().clone() for t in nd._mixture())
+                self.register_buffer("r_logw", torch.log_softmax(logits, 0))
+                self.register_buffer("r_conc", conc)
+                self.register_buffer("r_rate", rate)
+                self.register_buffer("r_scale", scale)         # not None: R = scale sqrt(S)  (Chi / HalfNormal)
         else:
             self.base_kind = "laplace" if type(base).__name__ == "Laplace" else "normal"
             raw = base.scale_unconstrained.detach()
@@ -301,9 +303,13 @@ class ReferenceSemantics(torch.nn.Module):
                 lpr = -((logr - self.r_mu) ** 2) / (2 * self.r_sigma ** 2) - self.r_sigma.log() \
                     - 0.5 * math.log(2 * math.pi) - logr
             else:
+                sq, logsq, extra = r, logr, 0.0
+                if self.r_scale is not None:
+                    logu = logr - self.r_scale.log()
+                    sq, logsq, extra = torch.exp(2 * logu), 2 * logu, math.log(2.0) + logu - self.r_scale.log()
                 t = self.r_logw + self.r_conc * self.r_rate.log() - torch.lgamma(self.r_conc) \
-                    + (self.r_conc - 1) * logr[:, None] - self.r_rate * r[:, None]
-                lpr = torch.logsumexp(t, -1)
+                    + (self.r_conc - 1) * logsq[:, None] - self.r_rate * sq[:, None]
+                lpr = torch.logsumexp(t, -1) + extra
             return lpr - (self.dv_const + (self.loc.numel() - 1) * logr) - total
         if self.base_kind == "laplace":
             lp = -torch.log(2 * self.scale) - (z - self.loc).abs() / self.scale

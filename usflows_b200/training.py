@@ -298,8 +298,8 @@ def _convnet2d_rows(net, x: torch.Tensor, geom, context: Optional[torch.Tensor] 
 
 
 def _radial_log_prob(b, z: torch.Tensor) -> torch.Tensor:
-    """Differentiable Lp-radial log-density (distributions.py:501-549) with LogNormal / GammaMM radius distributions."""
-    from .distributions import GammaMM, LogNormal
+    """Differentiable Lp-radial log-density (distributions.py:501-549) with LogNormal / Gamma-family radius distributions."""
+    from .distributions import LogNormal, _GammaFamily
     v = z - b.loc.reshape(-1)
     r = v.abs().sum(-1) if b.p == 1.0 else v.pow(2).sum(-1).sqrt() if b.p == 2.0 else v.abs().max(-1).values
     logr = r.log()
@@ -308,11 +308,13 @@ def _radial_log_prob(b, z: torch.Tensor) -> torch.Tensor:
     if isinstance(nd, LogNormal):
         mu, sg = nd.loc.reshape(()), sp(nd.scale_unconstrained).reshape(())
         lp = -((logr - mu) ** 2) / (2 * sg ** 2) - sg.log() - 0.5 * math.log(2 * math.pi) - logr
-    elif isinstance(nd, GammaMM):
-        a, rate = sp(nd.concentration_unconstrained), sp(nd.rate_unconstrained)
-        t = torch.log_softmax(nd.mixture_logits, 0) + a * rate.log() - torch.lgamma(a) \
-            + torch.xlogy(a - 1, r[:, None]) - rate * r[:, None]
-        lp = torch.logsumexp(t, -1)
+    elif isinstance(nd, _GammaFamily):
+        logits, a, rate, scale = nd._mixture()
+        s, extra = r, 0.0
+        if scale is not None:                    # R = scale sqrt(S)  (Chi, distributions.py:88-97)
+            s, extra = (r / scale) ** 2, torch.log(2 * r / scale) - scale.log()
+        t = torch.log_softmax(logits, 0) + a * rate.log() - torch.lgamma(a) + torch.xlogy(a - 1, s[:, None]) - rate * s[:, None]
+        lp = torch.logsumexp(t, -1) + extra
     else:
         raise NotImplementedError(f"usflows_b200: training with radius distribution {type(nd).__name__} is not built")
     return lp - (b.log_delta_volume_const() + (b.dim - 1) * logr)
