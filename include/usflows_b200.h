@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define USF_ABI_VERSION 6
+#define USF_ABI_VERSION 7
 
 #define USF_OK 0
 #define USF_ERR_INVALID (-1)     /* bad argument (shape, alignment, null pointer) */
@@ -367,6 +367,16 @@ int usf_householder_right(float* W, int32_t d, int64_t ld, const float* v, float
  * and the products across Aff_i^-1 / Aff_{i+1} boundaries) in higher precision than the layers run in. */
 int usf_matmul_f64(const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc, int32_t M,
                    int32_t N, int32_t K, void* stream);
+
+/* The same product for the triangular factors of an LU layer (ABI 7): `USF_TRI_LOWER_UPPER` C = L . U (the layer's matrix,
+ * transforms.py:1281-1283), `USF_TRI_UPPER_LOWER` C = U^-1 . L^-1 (its inverse, :1291-1293).  A and B are dense d x d
+ * arrays WITH their zeros stored; the kind only lets a tile skip the k range in which one factor is zero (a third of
+ * the work of the dense product).  The result is the full dense d x d matrix. */
+#define USF_TRI_NONE 0
+#define USF_TRI_LOWER_UPPER 1
+#define USF_TRI_UPPER_LOWER 2
+int usf_matmul_f64_tri(const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc, int32_t d,
+                       int32_t tri, void* stream);
 
 /* out[j] = softplus(in[j])  (distributions.py:211-215, base scale parameterisation) */
 int usf_softplus(const float* in, int64_t n, float* out, void* stream);

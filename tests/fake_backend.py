@@ -425,7 +425,11 @@ def matmul_f32(a, b, out, bias=None):
     out.copy_(v if bias is None else v + bias)
 
 
-def matmul_f64(a, b, out):
+def matmul_f64(a, b, out, tri=0):
+    if tri == real_ops.TRI_LOWER_UPPER:           # the kind is a promise about the zeros of the factors
+        assert not a.triu(1).any() and not b.tril(-1).any()
+    elif tri == real_ops.TRI_UPPER_LOWER:
+        assert not a.tril(-1).any() and not b.triu(1).any()
     out.copy_(a @ b)
 
 

@@ -543,3 +543,50 @@ def test_both_operand_planes_in_one_tma_operation(eng_name, eng, fmt, M, N, K):
     assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
     ref = torch.relu(a_used.double() @ w_used.double().T + bias.double().cpu())
     assert rel_err(outs[0], ref) <= 3e-6
+
+
+@pytest.mark.parametrize("M,N,K", [(1, 1, 1), (5, 3, 7), (64, 64, 16), (130, 70, 33), (784, 784, 784), (100, 784, 50),
+                                   (1000, 1, 9), (2600, 2500, 130)])
+def test_matmul_f64_tensor_core_tiles(M, N, K):
+    """`usf_matmul_f64` (fp64 MMA tiles, 64 x 64 and -- once the grid fills the SMs twice -- 128 x 128) against torch's CPU
+    fp64 product: ragged edges in M, N and K, leading dimensions that are not the widths, exact small-integer products."""
+    from usflows_b200 import ops
+    g = torch.Generator().manual_seed(M * 7 + N * 3 + K)
+    a = torch.randn(M, K, generator=g, dtype=torch.float64)
+    b = torch.randn(K, N, generator=g, dtype=torch.float64)
+    ad = torch.zeros(M, K + 3, dtype=torch.float64, device="cuda")[:, 1:K + 1]
+    bd = torch.zeros(K, N + 5, dtype=torch.float64, device="cuda")[:, 2:N + 2]
+    ad.copy_(a)
+    bd.copy_(b)
+    out = torch.full((M, N + 1), float("nan"), dtype=torch.float64, device="cuda")[:, :N]
+    ops.matmul_f64(ad, bd, out)
+    want = a @ b
+    assert float((out.cpu() - want).abs().max()) <= 1e-13 * max(1.0, float(want.abs().max())) * max(1, K) ** 0.5
+    ai = torch.randint(-8, 9, (M, K), generator=g).double()
+    bi = torch.randint(-8, 9, (K, N), generator=g).double()
+    oi = torch.empty(M, N, dtype=torch.float64, device="cuda")
+    ops.matmul_f64(ai.cuda(), bi.cuda(), oi)
+    assert torch.equal(oi.cpu(), ai @ bi)               # integers: every product and partial sum is exact in fp64
+
+
+@pytest.mark.parametrize("d", [1, 17, 64, 200, 784, 2600])
+def test_matmul_f64_triangular_factors(d):
+    """`usf_matmul_f64_tri`: L . U and U^-1 . L^-1 shaped products (factors stored dense) equal the dense product bit for
+    bit on integer factors, and to fp64 rounding on random ones -- the skipped k ranges only ever held zeros."""
+    from usflows_b200 import ops
+    g = torch.Generator().manual_seed(d)
+    for exact in (True, False):
+        a = (torch.randint(-4, 5, (d, d), generator=g).double() if exact else torch.randn(d, d, generator=g, dtype=torch.float64))
+        b = (torch.randint(-4, 5, (d, d), generator=g).double() if exact else torch.randn(d, d, generator=g, dtype=torch.float64))
+        for tri, A, B in ((ops.TRI_LOWER_UPPER, a.tril(), b.triu()), (ops.TRI_UPPER_LOWER, a.triu(), b.tril())):
+            out = torch.full((d, d), float("nan"), dtype=torch.float64, device="cuda")
+            ops.matmul_f64(A.cuda(), B.cuda(), out, tri)
+            dense = torch.empty(d, d, dtype=torch.float64, device="cuda")
+            ops.matmul_f64(A.cuda(), B.cuda(), dense)
+            want = A @ B
+            if exact:
+                assert torch.equal(out.cpu(), want) and torch.equal(dense.cpu(), want)
+            else:
+                assert float((out.cpu() - want).abs().max()) <= 1e-13 * max(1.0, float(want.abs().max())) * d ** 0.5
+    with pytest.raises(RuntimeError):
+        ops.check(ops._lib.load().usf_matmul_f64_tri(1, 4, 1, 4, 1, 4, 4, 7, None))

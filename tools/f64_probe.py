@@ -1,0 +1,29 @@
+"""usf_matmul_f64 against cuBLAS DGEMM (torch.matmul) at the operator sizes of the C2 / C5 stacks -- what the fp64
+composition of neighbouring affine layers costs per weight version, and the rate the library DGEMM sets as the bar."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+from usflows_b200 import ops
+
+def timed(fn, n=10):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(n):
+        fn()
+    e.record()
+    torch.cuda.synchronize()
+    return s.elapsed_time(e) / n * 1e3
+
+for d in (784, 1024, 3072):
+    a = torch.randn(d, d, dtype=torch.float64, device="cuda")
+    b = torch.randn(d, d, dtype=torch.float64, device="cuda")
+    o = torch.empty_like(a)
+    t_own = timed(lambda: ops.matmul_f64(a, b, o))
+    t_lib = timed(lambda: torch.matmul(a, b, out=o))
+    fl = 2.0 * d ** 3
+    print(f"d={d}: usf_matmul_f64 {t_own:8.1f} us ({fl / t_own * 1e-6:6.2f} TFLOP/s)   cuBLAS DGEMM {t_lib:8.1f} us "
+          f"({fl / t_lib * 1e-6:6.2f} TFLOP/s)", flush=True)

@@ -105,6 +105,7 @@ ENGINE_SIMT, ENGINE_TC_3XTF32, ENGINE_TC_TF32, ENGINE_TC_BF16, ENGINE_TC_3XF16 =
 BASE_LAPLACE, BASE_NORMAL = 0, 1
 LP_INF, LP_1, LP_2 = 0, 1, 2
 NORM_LOGNORMAL, NORM_GAMMA_MIXTURE, NORM_GAMMA_MIXTURE_SQ = 0, 1, 2
+TRI_NONE, TRI_LOWER_UPPER, TRI_UPPER_LOWER = 0, 1, 2
 
 _P, _I64, _I32, _F, _U64 = C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_uint64
 
@@ -148,6 +149,7 @@ SIGNATURES = {
     "usf_householder_right": (C.c_int, [_P, _I32, _I64, _P, _P, _P]),
     "usf_softplus": (C.c_int, [_P, _I64, _P, _P]),
     "usf_matmul_f64": (C.c_int, [_P, _I64, _P, _I64, _P, _I64, _I32, _I32, _I32, _P]),
+    "usf_matmul_f64_tri": (C.c_int, [_P, _I64, _P, _I64, _P, _I64, _I32, _I32, _P]),
     "usf_plan_create": (C.c_int, [C.POINTER(_P), _I32, _I32, _I64]),
     "usf_plan_add_linear": (C.c_int, [_P, C.POINTER(PlanLinear)]),
     "usf_plan_set_base": (C.c_int, [_P, _I32, _P, _P, _F]),
@@ -196,7 +198,7 @@ def load():
         fn = getattr(lib, name)  # AttributeError if the ABI and this table disagree
         fn.restype = res
         fn.argtypes = args
-    if lib.usf_abi_version() != 6:
+    if lib.usf_abi_version() != 7:
         raise RuntimeError("usflows_b200: ABI version mismatch between _lib.py and the shared library")
     _lib = lib
     return lib

@@ -585,15 +585,31 @@ int usf_householder_right(float* W, int32_t d, int64_t ld, const float* v, float
   return USF_OK;
 }
 
-int usf_matmul_f64(const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc, int32_t M,
-                   int32_t N, int32_t K, void* stream) {
+static int matmul_f64_launch(const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc, int32_t M,
+                             int32_t N, int32_t K, int32_t tri, void* stream) {
   USF_REQUIRE(A && B && C && M > 0 && N > 0 && K > 0, "bad input");
   USF_REQUIRE(C != A && C != B, "matmul_f64 cannot run in place");
-  dim3 grid((N + 63) / 64, (M + 63) / 64);
-  USF_REQUIRE(grid.y <= 65535, "matmul_f64: too many row blocks");
-  matmul_f64_kernel<<<grid, 256, 0, S(stream)>>>(A, lda, B, ldb, C, ldc, M, N, K);
+  USF_REQUIRE(tri == USF_TRI_NONE || ((tri == USF_TRI_LOWER_UPPER || tri == USF_TRI_UPPER_LOWER) && M == K && N == K),
+              "matmul_f64: triangular products are square");
+  USF_REQUIRE((M + 63) / 64 <= 65535, "matmul_f64: too many row blocks");
+  // fp64 tensor-core tiles: 128 x 128 once they fill the SMs twice over, else 64 x 64 (more CTAs for the 784-wide operators)
+  const long long big = (long long)((N + 127) / 128) * ((M + 127) / 128);
+  if (big >= 2LL * num_sms())
+    matmul_f64_mma_kernel<128, 128, 64, 32><<<dim3((N + 127) / 128, (M + 127) / 128), 256, 0, S(stream)>>>(A, lda, B, ldb, C, ldc, M, N, K, tri);
+  else
+    matmul_f64_mma_kernel<64, 64, 32, 32><<<dim3((N + 63) / 64, (M + 63) / 64), 128, 0, S(stream)>>>(A, lda, B, ldb, C, ldc, M, N, K, tri);
   USF_CUDA_OK(cudaGetLastError());
   return USF_OK;
+}
+
+int usf_matmul_f64(const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc, int32_t M,
+                   int32_t N, int32_t K, void* stream) {
+  return matmul_f64_launch(A, lda, B, ldb, C, ldc, M, N, K, USF_TRI_NONE, stream);
+}
+
+int usf_matmul_f64_tri(const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc, int32_t d,
+                       int32_t tri, void* stream) {
+  return matmul_f64_launch(A, lda, B, ldb, C, ldc, d, d, d, tri, stream);
 }
 
 int usf_plan_create(usf_plan** plan, int32_t d_in, int32_t mode, int64_t max_rows) {

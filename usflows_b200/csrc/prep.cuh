@@ -322,4 +322,84 @@ matmul_f64_kernel(const double* __restrict__ A, long long lda, const double* __r
     }
 }
 
+// The same product on the fp64 tensor-core path: mma.sync.m8n8k4.f64 (tcgen05 has no fp64 kind; DMMA is the fp64 MMA that
+// sm_100a offers).  The SIMT kernel above reaches about 4.5 TFLOP/s; composing the nine 3072 x 3072 operators of the C5
+// stack (58 GFLOP each) took 13 ms a product, most of the 100 ms a weight update cost the inference path.
+// BM x BN x 16 tiles; warps hold WM x WN; A is staged k-major so that both fragments are read with stride LD = B* + 4
+// doubles (LD mod 16 = 4: the 16 lanes of a half warp hit 16 distinct 8-byte bank pairs); next tile prefetched into
+// registers while the current one is multiplied.
+template <int BM, int BN, int WM, int WN>
+__global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32)
+matmul_f64_mma_kernel(const double* __restrict__ A, long long lda, const double* __restrict__ B, long long ldb,
+                      double* __restrict__ C, long long ldc, int M, int N, int K, int tri) {
+  constexpr int BK = 16, T = (BM / WM) * (BN / WN) * 32, LDA = BM + 4, LDB = BN + 4;
+  constexpr int NA = BM * BK / T, NB = BN * BK / T, MT = WM / 8, NT = WN / 8;
+  static_assert(BM * BK % T == 0 && BN * BK % T == 0 && LDA % 16 == 4 && LDB % 16 == 4, "tile shape");
+  __shared__ double sA[BK * LDA];
+  __shared__ double sB[BK * LDB];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int wm = (warp / (BN / WN)) * WM, wn = (warp % (BN / WN)) * WN;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  double acc[MT][NT][2];
+#pragma unroll
+  for (int i = 0; i < MT; ++i)
+#pragma unroll
+    for (int j = 0; j < NT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+  double ra[NA], rb[NB];
+  auto fetch = [&](int k0) {
+#pragma unroll
+    for (int i = 0; i < NA; ++i) {              // A tile: BM rows x 16 k, 16 consecutive threads read one 128-byte row piece
+      const int e = tid + i * T, r = e >> 4, c = e & 15;
+      const int gm = m0 + r, gk = k0 + c;
+      ra[i] = (gm < M && gk < K) ? __ldg(A + (long long)gm * lda + gk) : 0.0;
+    }
+#pragma unroll
+    for (int i = 0; i < NB; ++i) {              // B tile: 16 k x BN columns
+      const int e = tid + i * T, kr = e / BN, nc = e % BN;
+      const int gk = k0 + kr, gn = n0 + nc;
+      rb[i] = (gk < K && gn < N) ? __ldg(B + (long long)gk * ldb + gn) : 0.0;
+    }
+  };
+  // triangular factors (stored dense, zeros included): a tile of lower x upper only has terms k < min(row, column) + 1,
+  // one of upper x lower only k >= max(row, column) -- a third of the work on average
+  int kb = 0, ke = K;
+  if (tri == USF_TRI_LOWER_UPPER) ke = min(K, min(m0 + BM, n0 + BN));
+  else if (tri == USF_TRI_UPPER_LOWER) kb = (max(m0, n0) / BK) * BK;
+  fetch(kb);
+  for (int k0 = kb; k0 < ke; k0 += BK) {
+#pragma unroll
+    for (int i = 0; i < NA; ++i) { const int e = tid + i * T; sA[(e & 15) * LDA + (e >> 4)] = ra[i]; }
+#pragma unroll
+    for (int i = 0; i < NB; ++i) { const int e = tid + i * T; sB[(e / BN) * LDB + (e % BN)] = rb[i]; }
+    __syncthreads();
+    if (k0 + BK < ke) fetch(k0 + BK);
+#pragma unroll
+    for (int kk = 0; kk < BK; kk += 4) {
+      double a[MT], b[NT];
+#pragma unroll
+      for (int i = 0; i < MT; ++i) a[i] = sA[(kk + t) * LDA + wm + i * 8 + g];
+#pragma unroll
+      for (int j = 0; j < NT; ++j) b[j] = sB[(kk + t) * LDB + wn + j * 8 + g];
+#pragma unroll
+      for (int i = 0; i < MT; ++i)
+#pragma unroll
+        for (int j = 0; j < NT; ++j)
+          asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                       : "+d"(acc[i][j][0]), "+d"(acc[i][j][1]) : "d"(a[i]), "d"(b[j]));
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < MT; ++i)
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+      const int gm = m0 + wm + i * 8 + g, gn = n0 + wn + j * 8 + 2 * t;
+      if (gm < M) {
+        if (gn < N) C[(long long)gm * ldc + gn] = acc[i][j][0];
+        if (gn + 1 < N) C[(long long)gm * ldc + gn + 1] = acc[i][j][1];
+      }
+    }
+}
+
+
 }  // namespace usf

@@ -13,8 +13,8 @@ import torch
 
 from . import _lib
 from ._lib import (BASE_LAPLACE, BASE_NORMAL, ENGINE_SIMT, ENGINE_TC_3XF16, ENGINE_TC_3XTF32,  # noqa: F401
-                   ENGINE_TC_BF16, ENGINE_TC_TF32, LP_1, LP_2, LP_INF, NORM_GAMMA_MIXTURE, NORM_GAMMA_MIXTURE_SQ, NORM_LOGNORMAL, LinearArgs,
-                   Planes, check)
+                   ENGINE_TC_BF16, ENGINE_TC_TF32, LP_1, LP_2, LP_INF, NORM_GAMMA_MIXTURE, NORM_GAMMA_MIXTURE_SQ,
+                   NORM_LOGNORMAL, TRI_LOWER_UPPER, TRI_NONE, TRI_UPPER_LOWER, LinearArgs, Planes, check)
 
 
 LAUNCHES = 0     # kernels launched through this module since the caller last reset it (bench.py `gpu_launches`)
@@ -407,12 +407,17 @@ def matmul_f32(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, bias=None) -
     linear(ENGINE_SIMT, Act(M, K, f32=a), b, None, N, K, bias=bias, out=Act(M, N, f32=out), trans_w=True)
 
 
-def matmul_f64(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor) -> None:
-    """out = a @ b in fp64 (weight composition, once per weight version)."""
+def matmul_f64(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, tri: int = 0) -> None:
+    """out = a @ b in fp64 (weight composition, once per weight version).  `tri`: TRI_LOWER_UPPER (a lower, b upper
+    triangular) / TRI_UPPER_LOWER -- square factors stored dense; the product skips the k range where one of them is zero."""
     M, K = a.shape
     N = b.shape[1]
     assert a.dtype == b.dtype == out.dtype == torch.float64 and b.shape[0] == K and out.shape == (M, N)
-    check(_lib.load().usf_matmul_f64(_ptr(a), _ld(a), _ptr(b), _ld(b), _ptr(out), _ld(out), M, N, K, _stream()))
+    if tri:
+        assert M == N == K
+        check(_lib.load().usf_matmul_f64_tri(_ptr(a), _ld(a), _ptr(b), _ld(b), _ptr(out), _ld(out), M, tri, _stream()))
+    else:
+        check(_lib.load().usf_matmul_f64(_ptr(a), _ld(a), _ptr(b), _ld(b), _ptr(out), _ld(out), M, N, K, _stream()))
 
 
 # ---- training step (see include/usflows_b200.h, "Training step") -------------------------------------------------------

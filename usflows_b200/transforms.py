@@ -26,9 +26,9 @@ def _versions(params) -> tuple:
     return tuple((p.data_ptr(), p._version) for p in params)
 
 
-def _mm64(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+def _mm64(a: torch.Tensor, b: torch.Tensor, tri: int = 0) -> torch.Tensor:
     out = torch.empty(a.shape[0], b.shape[1], dtype=torch.float64, device=a.device)
-    ops.matmul_f64(a.contiguous(), b.contiguous(), out)
+    ops.matmul_f64(a.contiguous(), b.contiguous(), out, tri)
     return out
 
 
@@ -327,19 +327,20 @@ class LUTransform(AffineTransform):
         L, U = T[0], new(d, d)
         ops.lu_assemble(self.L_raw.detach(), self.U_raw.detach(), L, T[1], transpose_u=True)   # L, U^T (:1271-1279)
         ops.transpose(T[1], U)
-        W = new(d, d)
-        ops.matmul_f32(L, U, W)                                                # matrix = L @ U (:1281-1283)
         # inverse(L), inverse(U) (:1291-1292): both lower-triangular inverses (L and U^T) in one batched recursive-doubling
         # pass (csrc/train.cuh; the per-matrix panel sweep took 0.5 ms at d = 784 and ~10 ms at d = 3072 per inverse)
         ops.tri_inverse_batched(T, X, tmp, 0b01)
         Linv, Uinv = X[0], new(d, d)
         ops.transpose(X[1], Uinv)
-        Winv = new(d, d)
-        ops.matmul_f32(Uinv, Linv, Winv)                                       # U^-1 @ L^-1 (:1293)
         ladj = new(2)
         ops.lu_logabsdet(self.U_raw.detach(), ladj)                            # sum log|diag U| (:1303-1320)
-        # fp64 products of the same factors: what the engine composes neighbouring affine layers from
-        W64, Winv64 = _mm64(L.double(), U.double()), _mm64(Uinv.double(), Linv.double())
+        # matrix = L @ U (:1281-1283), inverse = U^-1 @ L^-1 (:1293) as fp64 tensor-core products that skip the zero halves
+        # of the factors: what the engine composes neighbouring affine layers from.  The fp32 `matrix` / `inverse_matrix`
+        # are these rounded once (the fp32 CUDA-core products they used to be cost as much as everything else in the
+        # preparation at d = 3072, and carried the rounding of a K-term fp32 sum).
+        W64 = _mm64(L.double(), U.double(), ops.TRI_LOWER_UPPER)
+        Winv64 = _mm64(Uinv.double(), Linv.double(), ops.TRI_UPPER_LOWER)
+        W, Winv = W64.float(), Winv64.float()
         return dict(matrix=W, inverse_matrix=Winv, bias=self.bias_vector.detach(), ladj=ladj,
                     L=L, U=U, L_inv=Linv, U_inv=Uinv, matrix64=W64, inverse64=Winv64)
 
