@@ -84,6 +84,31 @@ def main():
                out=Act(5000, 16, f32=torch.empty(5000, 16, device="cuda")))
     torch.cuda.synchronize()
     assert torch.isfinite(o32).all()
+    # Chi-family radius (USF_NORM_GAMMA_MIXTURE_SQ): density and sampling
+    spec_chi = dict(in_dims=[32], coupling_blocks=1, hidden_dims=[32], affine_conjugation=True, lu_transform=1, householder=0,
+                    base="radial", p=2, norm="chi", df=32, chi_scale=1.5)
+    pc = O.random_params(spec_chi, 3)
+    xc = torch.rand(100, 32, generator=g)
+    fc = build_flow(spec_chi, pc, device="cuda:0", precision="fp32")
+    e = rel_err(fc.log_prob(xc.cuda()), O.flow_log_prob(xc, spec_chi, pc))
+    fc.sample([50])
+    print(f"[radial chi] log_prob err {e:.2e}", flush=True)
+    assert e < 2e-5
+    # fp64 tensor-core products of the weight preparation: 64 x 64 tiles with ragged edges (dense and both triangular
+    # kinds), 128 x 128 tiles (grid >= 2 x SMs) on a short K
+    for tri in (ops.TRI_NONE, ops.TRI_LOWER_UPPER, ops.TRI_UPPER_LOWER):
+        a = torch.randn(200, 200, generator=g, dtype=torch.float64)
+        b = torch.randn(200, 200, generator=g, dtype=torch.float64)
+        if tri:
+            a, b = (a.tril(), b.triu()) if tri == ops.TRI_LOWER_UPPER else (a.triu(), b.tril())
+        o = torch.empty(200, 200, dtype=torch.float64, device="cuda")
+        ops.matmul_f64(a.cuda(), b.cuda(), o, tri)
+        assert rel_err(o, a @ b) < 1e-13
+    a, b = torch.randn(2300, 20, generator=g, dtype=torch.float64), torch.randn(20, 2290, generator=g, dtype=torch.float64)
+    o = torch.empty(2300, 2290, dtype=torch.float64, device="cuda")
+    ops.matmul_f64(a.cuda(), b.cuda(), o)
+    assert rel_err(o, a @ b) < 1e-13
+    print("[matmul_f64] ok", flush=True)
     # training step (autograd contractions incl. transposes) on a small flow
     from usflows_b200 import training
     import usflows_b200 as U
