@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define USF_ABI_VERSION 7
+#define USF_ABI_VERSION 8
 
 #define USF_OK 0
 #define USF_ERR_INVALID (-1)     /* bad argument (shape, alignment, null pointer) */
@@ -49,9 +49,12 @@ extern "C" {
 #define USF_LP_2 2
 #define USF_NORM_LOGNORMAL 0     /* params = [mu, sigma]                                  (distributions.py:181-197) */
 #define USF_NORM_GAMMA_MIXTURE 1 /* params = [logits (K) | concentration (K) | rate (K)]  (distributions.py:674-707) */
-#define USF_NORM_GAMMA_MIXTURE_SQ 2 /* R = scale * sqrt(S), S ~ the Gamma mixture: params = [logits | concentration | rate | scale];
-                                       log f_R(r) = log f_S((r/scale)^2) + log(2 r / scale) - log(scale) -- the reference's Chi(df, scale)
-                                       (distributions.py:55-116: Chi2 = Gamma(df/2, 1/2)) and torch's HalfNormal (ABI 6) */
+#define USF_NORM_GENGAMMA_MIXTURE 2 /* R = scale_k * S^(1 / power_k), S ~ Gamma(concentration_k, rate_k), mixed with softmax(logits):
+                                       params = [logits (K) | concentration (K) | rate (K) | scale (K) | power (K)].  One kind for the
+                                       reference's Chi(df, scale) (distributions.py:55-116: a = df / 2, b = 1 / 2, power 2), torch's
+                                       HalfNormal, Weibull(scale, concentration) (a = b = 1, power = concentration) and WeibullMM
+                                       (distributions.py:835-848)  (ABI 6; the per-component scale / power layout is ABI 8) */
+#define USF_NORM_LOGNORMAL_MIXTURE 3 /* params = [logits (K) | mu (K) | sigma (K)]: LogNormalMM (distributions.py:821-833)  (ABI 8) */
 
 /* output planes of an activation in the operand format(s) of an engine mode; unused planes are NULL */
 typedef struct usf_planes {
@@ -212,8 +215,9 @@ int usf_base_sample(int64_t rows, int32_t d, const float* loc, const float* scal
                     float* out_lo, int64_t ld_split, void* out_bf16, int64_t ld_bf16, void* stream);
 
 /* Lp-radial base density:  out[r] = log f_R(r_r) - [dv_const + (d-1) log r_r] + add_const,  r_r = ||z[r,:] - loc||_p
- * (z = z [+ z_lo]); f_R is LogNormal(mu, sigma) or a K-component Gamma mixture (K <= 128), `norm_params` as listed at
- * USF_NORM_*, already constrained (sigma, concentration, rate > 0; logits raw).  dv_const = the r-independent part of
+ * (z = z [+ z_lo]); f_R is LogNormal(mu, sigma) or a K-component mixture (K <= 128) of Gammas, generalised Gammas or
+ * log-normals, `norm_params` as listed at USF_NORM_*, already constrained (sigma, concentration, rate, scale, power > 0;
+ * logits raw).  dv_const = the r-independent part of
  * log dV_p^d/dr.  Replaces RadialDistribution.log_prob + log_delta_volume (distributions.py:501-549), the norm
  * distributions' log_prob (torch LogNormal / MixtureSameFamily(Categorical, Gamma)) and the `+ log_det` of Flow.log_prob. */
 int usf_radial_logprob(const float* z, const float* z_lo, int64_t ldz, int64_t rows, int32_t d, const float* loc,

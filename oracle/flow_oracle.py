@@ -512,6 +512,18 @@ def radial_norm_distribution(spec: dict, params):
         return torch.distributions.Chi2(torch.tensor(float(spec["df"]), dtype=params["base_distribution.loc"].dtype))
     if spec["norm"] == "halfnormal":    # experiments/mnist/mnist_digits_minimal_radialdists.yaml:95
         return torch.distributions.HalfNormal(torch.tensor(float(spec["chi_scale"]), dtype=params["base_distribution.loc"].dtype))
+    dt = params["base_distribution.loc"].dtype
+    if spec["norm"] == "weibull":       # experiments/mnist/mnist_digits_minimal_radial_weilbul.yaml:63
+        return torch.distributions.Weibull(torch.tensor(float(spec["w_scale"]), dtype=dt), torch.tensor(float(spec["w_conc"]), dtype=dt))
+    if spec["norm"] == "exponential":   # experiments/mnist/mnist_digits_minimal_radial_exponential.yaml:63
+        return torch.distributions.Exponential(torch.tensor(float(spec["rate"]), dtype=dt))
+    if spec["norm"] == "torchlognormal":
+        return torch.distributions.LogNormal(torch.tensor(float(spec["ln_loc"]), dtype=dt), torch.tensor(float(spec["ln_scale"]), dtype=dt))
+    if spec["norm"] in ("weibullmm", "lognormalmm"):   # MixtureModel (distributions.py:730-795, 821-848)
+        p0, p1 = params[q + "unconstrained_params.0"], params[q + "unconstrained_params.1"]
+        comp = torch.distributions.Weibull(F.softplus(p0), F.softplus(p1)) if spec["norm"] == "weibullmm" \
+            else torch.distributions.LogNormal(p0, F.softplus(p1))
+        return torch.distributions.MixtureSameFamily(torch.distributions.Categorical(logits=params[q + "mixture_logits"]), comp)
     conc = F.softplus(params[q + "concentration_unconstrained"])
     rate = F.softplus(params[q + "rate_unconstrained"])
     if spec["norm"] == "gamma":         # distributions.py:162-179, made Independent over its batch dim (:129-138)
@@ -853,8 +865,17 @@ def random_params(spec: dict, seed: int = 0, min_abs_scale: float = 0.1) -> Dict
         elif spec["norm"] == "gamma":
             out[q + "concentration_unconstrained"] = inv_softplus(0.5 + torch.rand(1, generator=g) * math.sqrt(dtot))
             out[q + "rate_unconstrained"] = inv_softplus(0.5 + torch.rand(1, generator=g))
-        elif spec["norm"] in ("chi", "chi2", "halfnormal"):   # no learnable radius parameters (distributions.py:55-75)
-            pass
+        elif spec["norm"] in ("chi", "chi2", "halfnormal", "weibull", "exponential", "torchlognormal"):
+            pass                                              # no learnable radius parameters (distributions.py:55-75)
+        elif spec["norm"] in ("weibullmm", "lognormalmm"):
+            K = int(spec.get("n_comp", 4))
+            if spec["norm"] == "weibullmm":                   # scale around sqrt(d), shape 1.5 .. 3.5
+                out[q + "unconstrained_params.0"] = inv_softplus((0.5 + torch.rand(K, generator=g)) * math.sqrt(dtot))
+                out[q + "unconstrained_params.1"] = inv_softplus(1.5 + 2 * torch.rand(K, generator=g))
+            else:
+                out[q + "unconstrained_params.0"] = 0.5 * math.log(dtot) + 0.5 * torch.rand(K, generator=g)
+                out[q + "unconstrained_params.1"] = inv_softplus(0.2 + 0.3 * torch.rand(K, generator=g))
+            out[q + "mixture_logits"] = torch.rand(K, generator=g)
         else:                                                 # experiments/synthetic/gaussian_mixture.yaml:84-91
             K = int(spec.get("n_comp", 20))
             out[q + "concentration_unconstrained"] = inv_softplus(0.2 + torch.rand(K, generator=g) * math.sqrt(dtot))

@@ -168,14 +168,18 @@ def _radial_norm_logpdf(r, norm_kind, params, K):
     if norm_kind == real_ops.NORM_LOGNORMAL:
         mu, sg = params[0], params[1]
         return -((logr - mu) ** 2) / (2 * sg ** 2) - sg.log() - 0.9189385332046727 - logr
-    logits, a, b = params[:K], params[K:2 * K], params[2 * K:3 * K]
-    extra = 0.0
-    if norm_kind == real_ops.NORM_GAMMA_MIXTURE_SQ:       # R = scale sqrt(S)
-        sc = params[3 * K]
-        extra = torch.log(2 * r / sc) - sc.log()
-        r = (r / sc) ** 2
-    t = torch.log_softmax(logits, 0) + a * b.log() - torch.lgamma(a) + torch.xlogy(a - 1, r[:, None]) - b * r[:, None]
-    return torch.logsumexp(t, -1) + extra
+    logw, a, b = torch.log_softmax(params[:K], 0), params[K:2 * K], params[2 * K:3 * K]
+    if norm_kind == real_ops.NORM_LOGNORMAL_MIXTURE:      # a = mu, b = sigma
+        t = logw - ((logr[:, None] - a) ** 2) / (2 * b ** 2) - b.log() - 0.9189385332046727
+        return torch.logsumexp(t, -1) - logr
+    t = logw + a * b.log() - torch.lgamma(a)
+    if norm_kind == real_ops.NORM_GENGAMMA_MIXTURE:       # R = scale S^(1 / power)
+        sc, q = params[3 * K:4 * K], params[4 * K:5 * K]
+        lu = logr[:, None] - sc.log()
+        t = t + q.log() - sc.log() + (a * q - 1) * lu - b * torch.exp(q * lu)
+    else:
+        t = t + torch.xlogy(a - 1, r[:, None]) - b * r[:, None]
+    return torch.logsumexp(t, -1)
 
 
 def radial_logprob(z, loc, p_kind, norm_kind, norm_params, n_comp, dv_const, add_const, out):
@@ -195,9 +199,12 @@ def radial_sample(out, loc, p_kind, norm_kind, norm_params, n_comp, seed, offset
     else:
         K = n_comp
         k = torch.multinomial(torch.softmax(norm_params[:K], 0), rows, replacement=True, generator=g)
-        r = torch.distributions.Gamma(norm_params[K:2 * K][k], norm_params[2 * K:3 * K][k]).sample()
-        if norm_kind == real_ops.NORM_GAMMA_MIXTURE_SQ:
-            r = norm_params[3 * K] * r.sqrt()
+        if norm_kind == real_ops.NORM_LOGNORMAL_MIXTURE:
+            r = torch.exp(norm_params[K:2 * K][k] + norm_params[2 * K:3 * K][k] * torch.randn(rows, generator=g))
+        else:
+            r = torch.distributions.Gamma(norm_params[K:2 * K][k], norm_params[2 * K:3 * K][k]).sample()
+        if norm_kind == real_ops.NORM_GENGAMMA_MIXTURE:
+            r = norm_params[3 * K:4 * K][k] * r ** (1.0 / norm_params[4 * K:5 * K][k])
     if p_kind == real_ops.LP_2:
         u = torch.randn(rows, d, generator=g)
         u = u / u.norm(dim=-1, keepdim=True)

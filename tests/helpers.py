@@ -15,7 +15,10 @@ LARGE_CASES = ["c2_d784", "c4_d3072_b2"]
 EXT_CASES = ["d64_convnet", "d64_convnet_proj_radial2", "d40_convnet_plain_gmm1", "d64_convnet_noln", "d32_radial_inf",
              "d784_radial1_lognormal",
              # the other radius distributions of the reference's configurations: its Chi, torch's Chi2 / HalfNormal
-             "d32_radial2_chi", "d24_radial1_chi2", "d16_radialinf_halfnormal"]
+             "d32_radial2_chi", "d24_radial1_chi2", "d16_radialinf_halfnormal",
+             # torch's Weibull / Exponential / LogNormal objects, the reference's WeibullMM / LogNormalMM radius mixtures
+             "d20_radial1_weibull", "d12_radial1_exponential", "d18_radial2_torchlognormal", "d28_radialinf_weibullmm",
+             "d30_radial2_lognormalmm"]
 # image-shaped events [C, H, W] (1x1-convolution BlockAffine, ConvNet2D conditioners, [C, H, W] masks)
 IMG_CASES = ["img_c4_4x4", "img_mnist_16x7x7", "img_c6_5x3_plain_channel", "img_c32_4x4_noln",
              # networks.ConvNet's convolutional branch (networks.py:308-377) as the conditioner

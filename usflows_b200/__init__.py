@@ -8,7 +8,7 @@ CUDA (tcgen05 + TMEM + TMA contractions, fused elementwise kernels) through the 
 include/usflows_b200.h.  CUDA tensors only -- there is no CPU fallback.
 """
 from . import distributions, nn, transforms  # noqa: F401
-from .distributions import Chi, Gamma, GammaMM, Independent, Laplace, LogNormal, Normal, RadialDistribution  # noqa: F401
+from .distributions import Chi, Gamma, GammaMM, LogNormalMM, WeibullMM, Independent, Laplace, LogNormal, Normal, RadialDistribution  # noqa: F401
 from .engine import get_precision, set_chunk_rows, set_precision  # noqa: F401
 from .flows import Flow, USFlow  # noqa: F401
 from .nn import (CondConvNet, CondConvNet2D, ConvNet, ConvNet2D, DenseNN, GatedConv, GatedConvND, GatedMLP,  # noqa: F401

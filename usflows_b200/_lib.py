@@ -104,7 +104,7 @@ class Planes(C.Structure):
 ENGINE_SIMT, ENGINE_TC_3XTF32, ENGINE_TC_TF32, ENGINE_TC_BF16, ENGINE_TC_3XF16 = 0, 1, 2, 3, 4
 BASE_LAPLACE, BASE_NORMAL = 0, 1
 LP_INF, LP_1, LP_2 = 0, 1, 2
-NORM_LOGNORMAL, NORM_GAMMA_MIXTURE, NORM_GAMMA_MIXTURE_SQ = 0, 1, 2
+NORM_LOGNORMAL, NORM_GAMMA_MIXTURE, NORM_GENGAMMA_MIXTURE, NORM_LOGNORMAL_MIXTURE = 0, 1, 2, 3
 TRI_NONE, TRI_LOWER_UPPER, TRI_UPPER_LOWER = 0, 1, 2
 
 _P, _I64, _I32, _F, _U64 = C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_uint64
@@ -198,7 +198,7 @@ def load():
         fn = getattr(lib, name)  # AttributeError if the ABI and this table disagree
         fn.restype = res
         fn.argtypes = args
-    if lib.usf_abi_version() != 7:
+    if lib.usf_abi_version() != 8:
         raise RuntimeError("usflows_b200: ABI version mismatch between _lib.py and the shared library")
     _lib = lib
     return lib

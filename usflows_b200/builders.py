@@ -21,6 +21,18 @@ def build_flow(spec, params=None, device="cuda", precision=None):
             nd = U.Chi(spec["df"], spec.get("chi_scale", 1.0))
         elif spec["norm"] == "chi2":
             nd = torch.distributions.Chi2(torch.tensor(float(spec["df"])))
+        elif spec["norm"] == "weibull":
+            nd = torch.distributions.Weibull(torch.tensor(float(spec["w_scale"])), torch.tensor(float(spec["w_conc"])))
+        elif spec["norm"] == "exponential":
+            nd = torch.distributions.Exponential(torch.tensor(float(spec["rate"])))
+        elif spec["norm"] == "torchlognormal":
+            nd = torch.distributions.LogNormal(torch.tensor(float(spec["ln_loc"])), torch.tensor(float(spec["ln_scale"])))
+        elif spec["norm"] == "weibullmm":
+            K = spec.get("n_comp", 4)
+            nd = U.WeibullMM(torch.ones(K), torch.ones(K), torch.ones(K) / K)
+        elif spec["norm"] == "lognormalmm":
+            K = spec.get("n_comp", 4)
+            nd = U.LogNormalMM(torch.ones(K), torch.ones(K), torch.ones(K) / K)
         elif spec["norm"] == "halfnormal":
             nd = torch.distributions.HalfNormal(torch.tensor(float(spec["chi_scale"])))
         else:

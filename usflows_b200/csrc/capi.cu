@@ -293,7 +293,7 @@ int usf_radial_logprob(const float* z, const float* z_lo, int64_t ldz, int64_t r
   USF_REQUIRE(z && loc && norm_params && out && d > 0 && rows >= 0, "bad input");
   USF_REQUIRE(p_kind == USF_LP_INF || p_kind == USF_LP_1 || p_kind == USF_LP_2, "p must be 1, 2 or inf");
   USF_REQUIRE(norm_kind == USF_NORM_LOGNORMAL ||
-              ((norm_kind == USF_NORM_GAMMA_MIXTURE || norm_kind == USF_NORM_GAMMA_MIXTURE_SQ) && n_comp >= 1 && n_comp <= RAD_MAX_COMP),
+              (norm_kind >= USF_NORM_GAMMA_MIXTURE && norm_kind <= USF_NORM_LOGNORMAL_MIXTURE && n_comp >= 1 && n_comp <= RAD_MAX_COMP),
               "unknown norm distribution / too many mixture components");
   if (rows == 0) return USF_OK;
   const bool vec = aligned16(z) && (!z_lo || aligned16(z_lo)) && ldz % 4 == 0 && d % 4 == 0 && aligned16(loc);
@@ -312,7 +312,7 @@ int usf_radial_sample(int64_t rows, int32_t d, const float* loc, int32_t p_kind,
   USF_REQUIRE(loc && norm_params && out && d > 0 && rows >= 0 && ldo >= d, "bad input");
   USF_REQUIRE(p_kind == USF_LP_INF || p_kind == USF_LP_1 || p_kind == USF_LP_2, "p must be 1, 2 or inf");
   USF_REQUIRE(norm_kind == USF_NORM_LOGNORMAL ||
-              ((norm_kind == USF_NORM_GAMMA_MIXTURE || norm_kind == USF_NORM_GAMMA_MIXTURE_SQ) && n_comp >= 1 && n_comp <= RAD_MAX_COMP),
+              (norm_kind >= USF_NORM_GAMMA_MIXTURE && norm_kind <= USF_NORM_LOGNORMAL_MIXTURE && n_comp >= 1 && n_comp <= RAD_MAX_COMP),
               "unknown norm distribution / too many mixture components");
   if (rows == 0) return USF_OK;
   radial_sample_kernel<<<ew_grid(rows * 32, RAD_THREADS), RAD_THREADS, 0, S(stream)>>>(rows, d, loc, p_kind, norm_kind, norm_params, n_comp, seed, offset, out, ldo);

@@ -24,13 +24,20 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
-// Per-component constants of the Gamma mixture, computed once per block into shared memory:
-//   log w_k + a_k log b_k - lgamma(a_k)   (log w = log_softmax(logits)),   a_k - 1,   b_k
-// params = [logits (K) | concentration (K) | rate (K)], concentration / rate already constrained (softplus).
+// Per-component constants of the radius mixture, computed once per block into shared memory.
+//   USF_NORM_GAMMA_MIXTURE      params = [logits | concentration | rate]                      (K each, constrained values)
+//       c_k = log w_k + a_k log b_k - lgamma(a_k)   (log w = log_softmax(logits)),  coef_k = a_k - 1
+//       log f(r) = LSE_k [c_k + coef_k log r - b_k r]
+//   USF_NORM_GENGAMMA_MIXTURE   params = [logits | concentration | rate | scale | power]      R = s_k S^(1 / q_k), S ~ Gamma(a_k, b_k)
+//       with u = r / s_k:  log f(r) = LSE_k [c_k + log q_k - log s_k + (a_k q_k - 1) log u - b_k u^q_k]
+//       (Chi: a = df / 2, b = 1 / 2, q = 2;  Weibull(lambda, k): a = b = 1, s = lambda, q = k;  HalfNormal(s): a = b = 1 / 2, q = 2)
+//   USF_NORM_LOGNORMAL_MIXTURE  params = [logits | mu | sigma]
+//       log f(r) = LSE_k [log w_k - log sigma_k - log sqrt(2 pi) - (log r - mu_k)^2 / (2 sigma_k^2)] - log r
 struct GammaMixSmem {
   float c[RAD_MAX_COMP], am1[RAD_MAX_COMP], b[RAD_MAX_COMP], cdf[RAD_MAX_COMP];
+  float a[RAD_MAX_COMP], ls[RAD_MAX_COMP], q[RAD_MAX_COMP];      // concentration (mu for log-normals), log scale, power
 };
-__device__ __forceinline__ void gamma_mix_prepare(GammaMixSmem& s, const float* __restrict__ params, int K) {
+__device__ __forceinline__ void gamma_mix_prepare(GammaMixSmem& s, const float* __restrict__ params, int K, int kind) {
   if (threadIdx.x < 32) {
     const int lane = threadIdx.x;
     float m = -INFINITY;
@@ -41,9 +48,24 @@ __device__ __forceinline__ void gamma_mix_prepare(GammaMixSmem& s, const float* 
     const float lse = m + logf(warp_sum(e));
     for (int k = lane; k < K; k += 32) {
       const float a = params[K + k], b = params[2 * K + k];
+      s.a[k] = a;
+      s.b[k] = b;
+      if (kind == USF_NORM_LOGNORMAL_MIXTURE) {       // a = mu, b = sigma
+        s.c[k] = params[k] - lse - logf(b) - 0.91893853320467274178f;
+        s.am1[k] = 0.f; s.ls[k] = 0.f; s.q[k] = 1.f;
+        continue;
+      }
       s.c[k] = params[k] - lse + a * logf(b) - lgammaf(a);
       s.am1[k] = a - 1.f;
-      s.b[k] = b;
+      s.ls[k] = 0.f;
+      s.q[k] = 1.f;
+      if (kind == USF_NORM_GENGAMMA_MIXTURE) {
+        const float sc = params[3 * K + k], q = params[4 * K + k];
+        s.ls[k] = logf(sc);
+        s.q[k] = q;
+        s.c[k] += logf(q) - s.ls[k];
+        s.am1[k] = a * q - 1.f;
+      }
     }
     if (lane == 0) {                       // cumulative mixture weights for sampling (K is small)
       float acc = 0.f;
@@ -61,26 +83,24 @@ __device__ __forceinline__ float radial_norm_logpdf(float radius, float logr, in
     const float u = logr - mu;
     return -(u * u) / (2.f * (sg * sg)) - logf(sg) - 0.91893853320467274178f - logr;
   }
-  float extra = 0.f;
-  if (norm_kind == USF_NORM_GAMMA_MIXTURE_SQ) {   // R = scale sqrt(S): f_R(r) = f_S((r / scale)^2) 2 r / scale^2
-    const float sc = __ldg(params + 3 * K), lsc = logf(sc), u = radius / sc;
-    extra = 0.69314718055994530942f + (logr - lsc) - lsc;
-    logr = 2.f * (logr - lsc);
-    radius = u * u;
-  }
-  // Gamma mixture: logsumexp_k [log w_k + a_k log b_k + (a_k - 1) log r - b_k r - lgamma(a_k)]
+  // term of component k; the plain Gamma mixture keeps its own expression (xlogy(a - 1, r) - b r on the radius itself)
+  auto term = [&](int k) -> float {
+    if (norm_kind == USF_NORM_GAMMA_MIXTURE)
+      return s.c[k] + (s.am1[k] == 0.f ? 0.f : s.am1[k] * logr) - s.b[k] * radius;
+    if (norm_kind == USF_NORM_LOGNORMAL_MIXTURE) {
+      const float u = logr - s.a[k];
+      return s.c[k] - (u * u) / (2.f * (s.b[k] * s.b[k]));
+    }
+    const float lu = logr - s.ls[k];
+    return s.c[k] + (s.am1[k] == 0.f ? 0.f : s.am1[k] * lu) - s.b[k] * expf(s.q[k] * lu);
+  };
   float m = -INFINITY;
-  for (int k = lane; k < K; k += 32) {
-    const float t = s.c[k] + (s.am1[k] == 0.f ? 0.f : s.am1[k] * logr) - s.b[k] * radius;   // xlogy(a - 1, r)
-    m = fmaxf(m, t);
-  }
+  for (int k = lane; k < K; k += 32) m = fmaxf(m, term(k));
   m = warp_max(m);
   float e = 0.f;
-  for (int k = lane; k < K; k += 32) {
-    const float t = s.c[k] + (s.am1[k] == 0.f ? 0.f : s.am1[k] * logr) - s.b[k] * radius;
-    e += expf(t - m);
-  }
-  return m + logf(warp_sum(e)) + extra;
+  for (int k = lane; k < K; k += 32) e += expf(term(k) - m);
+  const float lp = m + logf(warp_sum(e));
+  return norm_kind == USF_NORM_LOGNORMAL_MIXTURE ? lp - logr : lp;
 }
 
 template <bool VEC>
@@ -89,7 +109,7 @@ radial_logprob_kernel(const float* __restrict__ z, const float* __restrict__ z_l
                       const float* __restrict__ loc, int p_kind, int norm_kind, const float* __restrict__ params, int n_comp,
                       float dv_const, float add_const, float* __restrict__ out) {
   __shared__ GammaMixSmem sm;
-  if (norm_kind != USF_NORM_LOGNORMAL) gamma_mix_prepare(sm, params, n_comp);
+  if (norm_kind != USF_NORM_LOGNORMAL) gamma_mix_prepare(sm, params, n_comp, norm_kind);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int wpb = RAD_THREADS / 32;
   for (long long r = (long long)blockIdx.x * wpb + warp; r < rows; r += (long long)gridDim.x * wpb) {
@@ -158,7 +178,7 @@ radial_sample_kernel(long long rows, int d, const float* __restrict__ loc, int p
                      const float* __restrict__ params, int n_comp, uint64_t seed, uint64_t offset,
                      float* __restrict__ out, long long ldo) {
   __shared__ GammaMixSmem sm;
-  if (norm_kind != USF_NORM_LOGNORMAL) gamma_mix_prepare(sm, params, n_comp);
+  if (norm_kind != USF_NORM_LOGNORMAL) gamma_mix_prepare(sm, params, n_comp, norm_kind);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int wpb = RAD_THREADS / 32;
   const int d4 = (d + 3) >> 2;
@@ -175,12 +195,17 @@ radial_sample_kernel(long long rows, int d, const float* __restrict__ loc, int p
         const float u = u01_open(rnd[0]);
         int k = 0;
         while (k + 1 < n_comp && u > sm.cdf[k]) ++k;
-        const float a = sm.am1[k] + 1.f, b = sm.b[k];
-        float g;
-        if (a >= 1.f) g = gamma_mt(a, seed, (uint64_t)r, (offset ^ RTAG) + 1);
-        else g = gamma_mt(a + 1.f, seed, (uint64_t)r, (offset ^ RTAG) + 1) * powf(u01_open(rnd[1]), 1.f / a);   // boost
-        radius = g / b;
-        if (norm_kind == USF_NORM_GAMMA_MIXTURE_SQ) radius = __ldg(params + 3 * n_comp) * sqrtf(radius);
+        const float a = sm.a[k], b = sm.b[k];
+        if (norm_kind == USF_NORM_LOGNORMAL_MIXTURE) {          // a = mu_k, b = sigma_k
+          radius = expf(fmaf(b, philox_normal(seed, (uint64_t)r, (offset ^ RTAG) + 1), a));
+        } else {
+          float g;
+          if (a >= 1.f) g = gamma_mt(a, seed, (uint64_t)r, (offset ^ RTAG) + 1);
+          else g = gamma_mt(a + 1.f, seed, (uint64_t)r, (offset ^ RTAG) + 1) * powf(u01_open(rnd[1]), 1.f / a);   // boost
+          radius = g / b;
+          if (norm_kind == USF_NORM_GENGAMMA_MIXTURE)           // R = s_k S^(1 / q_k)
+            radius = expf(sm.ls[k]) * (sm.q[k] == 2.f ? sqrtf(radius) : powf(radius, 1.f / sm.q[k]));
+        }
       }
       if (p_kind == USF_LP_INF) {
         uint32_t rnd[4];

@@ -191,26 +191,49 @@ class LogNormal(_RadiusDistribution):
         buf[1:2].copy_(_softplus_vec(self.scale_unconstrained))
         return ops.NORM_LOGNORMAL, 1, buf
 
+    def _lognormals(self):
+        mu = self.loc.reshape(1)
+        return torch.zeros_like(mu), mu, torch.nn.functional.softplus(self.scale_unconstrained).reshape(1)
+
 
 class _GammaFamily(_RadiusDistribution):
-    """Radius distributions that are a Gamma mixture, or `scale * sqrt` of one: `_mixture()` hands the constrained
-    values (logits [K], concentration [K], rate [K], scale or None) over as differentiable tensors -- the radial kernels
-    read them packed (USF_NORM_GAMMA_MIXTURE / _SQ), the training route and the exportable module evaluate them with torch."""
+    """Radius distributions that are a mixture of (generalised) Gammas: R = scale_k * S^(1 / power_k), S ~ Gamma(a_k, b_k).
+    `_mixture()` hands the constrained values (logits [K], concentration [K], rate [K], scale [K] or None, power [K] or
+    None) over as differentiable tensors -- the radial kernels read them packed (USF_NORM_GAMMA_MIXTURE without scale /
+    power, USF_NORM_GENGAMMA_MIXTURE with), the training route and the exportable module evaluate them with torch."""
 
     def _mixture(self):
         raise NotImplementedError
 
     def _pack(self):
-        logits, conc, rate, scale = self._mixture()
+        logits, conc, rate, scale, power = self._mixture()
         K = logits.numel()
-        buf = torch.empty(3 * K + (scale is not None), dtype=torch.float32, device=logits.device)
-        buf[:K].copy_(logits.detach().reshape(-1))
-        buf[K:2 * K].copy_(conc.detach().reshape(-1))
-        buf[2 * K:3 * K].copy_(rate.detach().reshape(-1))
-        if scale is None:
-            return ops.NORM_GAMMA_MIXTURE, K, buf
-        buf[3 * K:].copy_(scale.detach().reshape(-1))
-        return ops.NORM_GAMMA_MIXTURE_SQ, K, buf
+        parts = [logits, conc, rate] + ([] if scale is None else [scale, power])
+        buf = torch.empty(len(parts) * K, dtype=torch.float32, device=logits.device)
+        for i, t in enumerate(parts):
+            buf[i * K:(i + 1) * K].copy_(t.detach().reshape(-1))
+        return (ops.NORM_GAMMA_MIXTURE if scale is None else ops.NORM_GENGAMMA_MIXTURE), K, buf
+
+
+class _LogNormalFamily(_RadiusDistribution):
+    """Radius distributions that are a mixture of log-normals: `_lognormals()` -> (logits [K], mu [K], sigma [K])."""
+
+    def _lognormals(self):
+        raise NotImplementedError
+
+    def _pack(self):
+        logits, mu, sigma = self._lognormals()
+        K = logits.numel()
+        if K == 1:                                           # the single log-normal keeps its own kernel branch
+            buf = torch.cat([mu.detach().reshape(-1), sigma.detach().reshape(-1)]).to(torch.float32)
+            return ops.NORM_LOGNORMAL, 1, buf
+        buf = torch.cat([t.detach().reshape(-1) for t in (logits, mu, sigma)]).to(torch.float32)
+        return ops.NORM_LOGNORMAL_MIXTURE, K, buf
+
+
+def _mixture_args(*tensors):
+    if any(t.dim() != 1 or t.shape != tensors[0].shape for t in tensors):
+        raise NotImplementedError("usflows_b200: radius mixtures take 1-D [K] parameter tensors")
 
 
 class GammaMM(_GammaFamily):
@@ -232,7 +255,58 @@ class GammaMM(_GammaFamily):
 
     def _mixture(self):
         sp = torch.nn.functional.softplus
-        return self.mixture_logits, sp(self.concentration_unconstrained), sp(self.rate_unconstrained), None
+        return self.mixture_logits, sp(self.concentration_unconstrained), sp(self.rate_unconstrained), None, None
+
+
+class _MixtureModel:
+    """Parameter layout of the reference's `MixtureModel` (distributions.py:730-795): `unconstrained_params` (a
+    ParameterList in the order of the component's arguments, positive ones stored through inv_softplus) and
+    `mixture_logits` -- state-dict keys `unconstrained_params.0`, `unconstrained_params.1`, `mixture_logits`."""
+
+    def _init_mixture(self, params, positive, mixture_weights, device):
+        _mixture_args(*params, mixture_weights)
+        self.unconstrained_params = torch.nn.ParameterList(
+            [Parameter(inv_softplus(p) if pos else p) for p, pos in zip(params, positive)])
+        self._positive = tuple(positive)
+        self.mixture_logits = Parameter(mixture_weights)
+        self.to(device)
+
+    def _params(self):
+        return (self.mixture_logits, *self.unconstrained_params)
+
+    def _constrained(self):
+        sp = torch.nn.functional.softplus
+        return [sp(p) if pos else p for p, pos in zip(self.unconstrained_params, self._positive)]
+
+
+class WeibullMM(_MixtureModel, _GammaFamily):
+    """Mixture of K Weibull(scale_k, concentration_k) (distributions.py:835-848): R = scale * E^(1 / concentration),
+    E ~ Exponential(1) = Gamma(1, 1)."""
+
+    norm_kind = ops.NORM_GENGAMMA_MIXTURE
+
+    def __init__(self, scale: torch.Tensor, concentration: torch.Tensor, mixture_weights: torch.Tensor, device: str = "cpu"):
+        _GammaFamily.__init__(self)
+        self._init_mixture((scale, concentration), (True, True), mixture_weights, device)
+
+    def _mixture(self):
+        scale, conc = self._constrained()
+        one = torch.ones_like(scale)
+        return self.mixture_logits, one, one, scale, conc
+
+
+class LogNormalMM(_MixtureModel, _LogNormalFamily):
+    """Mixture of K LogNormal(loc_k, scale_k) (distributions.py:821-833)."""
+
+    norm_kind = ops.NORM_LOGNORMAL_MIXTURE
+
+    def __init__(self, loc: torch.Tensor, scale: torch.Tensor, mixture_weights: torch.Tensor, device: str = "cpu"):
+        _LogNormalFamily.__init__(self)
+        self._init_mixture((loc, scale), (False, True), mixture_weights, device)
+
+    def _lognormals(self):
+        loc, scale = self._constrained()
+        return self.mixture_logits, loc, scale
 
 
 class Gamma(_GammaFamily):
@@ -255,7 +329,7 @@ class Gamma(_GammaFamily):
     def _mixture(self):
         sp = torch.nn.functional.softplus
         conc = sp(self.concentration_unconstrained).reshape(1)
-        return torch.zeros_like(conc), conc, sp(self.rate_unconstrained).reshape(1), None
+        return torch.zeros_like(conc), conc, sp(self.rate_unconstrained).reshape(1), None, None
 
 
 class Chi(_GammaFamily):
@@ -263,7 +337,7 @@ class Chi(_GammaFamily):
     standard normal in `df` dimensions).  No learnable parameters, as in the reference; `df` / `scale` are buffers so that
     `.to(device)` moves them."""
 
-    norm_kind = ops.NORM_GAMMA_MIXTURE_SQ
+    norm_kind = ops.NORM_GENGAMMA_MIXTURE
 
     def __init__(self, df, scale: float = 1.0, validate_args=None, device: str = "cpu"):
         super().__init__()
@@ -281,42 +355,86 @@ class Chi(_GammaFamily):
         return (self._df, self._scale)
 
     def _mixture(self):
-        return torch.zeros_like(self._df), self._df / 2, torch.full_like(self._df, 0.5), self._scale
+        return (torch.zeros_like(self._df), self._df / 2, torch.full_like(self._df, 0.5), self._scale,
+                torch.full_like(self._df, 2.0))
 
 
-class _TorchRadius(_GammaFamily):
-    """A frozen `torch.distributions` object as the radius distribution -- the reference's configurations pass `Chi2(df)`
-    and `HalfNormal(scale)` straight into `RadialDistribution` (experiments/mnist/mnist_digits_minimal_radial_chi2.yaml:63,
-    mnist_digits_minimal_radialdists.yaml:81-95).  Chi2(df) = Gamma(df / 2, 1 / 2); HalfNormal(s) = s * sqrt(Chi2(1));
-    `torch.distributions.Gamma` as is.  Values are read at construction (no parameters, as in the reference)."""
+def _frozen(t) -> torch.Tensor:
+    return torch.as_tensor(t, dtype=torch.float32).detach().reshape(-1).clone()
+
+
+class _TorchGammaRadius(_GammaFamily):
+    """A frozen `torch.distributions` object as the radius distribution -- the reference's configurations pass them straight
+    into `RadialDistribution` (experiments/mnist/mnist_digits_minimal_radial_{chi2,weilbul,exponential}.yaml,
+    mnist_digits_minimal_radialdists.yaml:81-95).  Chi2(df) = Gamma(df / 2, 1 / 2); Exponential(rate) = Gamma(1, rate);
+    HalfNormal(s) = s sqrt(Chi2(1)); Weibull(scale, k) = scale Exponential(1)^(1 / k); `torch.distributions.Gamma` as is.
+    Values are read at construction (these objects carry no parameters in the reference either)."""
 
     def __init__(self, dist):
         super().__init__()
         D = torch.distributions
-        f = lambda t: torch.as_tensor(t, dtype=torch.float32).detach().reshape(-1).clone()
+        scale = power = None
         if isinstance(dist, D.Chi2):                # before Gamma: Chi2 is a Gamma subclass
-            conc, rate, scale = f(dist.df) / 2, torch.full_like(f(dist.df), 0.5), None
+            conc = _frozen(dist.df) / 2
+            rate = torch.full_like(conc, 0.5)
         elif isinstance(dist, D.Gamma):
-            conc, rate, scale = f(dist.concentration), f(dist.rate), None
+            conc, rate = _frozen(dist.concentration), _frozen(dist.rate)
+        elif isinstance(dist, D.Exponential):
+            rate = _frozen(dist.rate)
+            conc = torch.ones_like(rate)
         elif isinstance(dist, D.HalfNormal):
-            scale = f(dist.scale)
-            conc, rate = torch.full_like(scale, 0.5), torch.full_like(scale, 0.5)
+            scale = _frozen(dist.scale)
+            conc, rate, power = torch.full_like(scale, 0.5), torch.full_like(scale, 0.5), torch.full_like(scale, 2.0)
+        elif isinstance(dist, D.Weibull):
+            scale, power = _frozen(dist.scale), _frozen(dist.concentration)
+            conc, rate = torch.ones_like(scale), torch.ones_like(scale)
         else:
-            raise NotImplementedError(f"usflows_b200.RadialDistribution: radius distribution {type(dist).__name__} is not built "
-                                      "(LogNormal, GammaMM, Gamma, Chi, torch Chi2 / Gamma / HalfNormal are)")
+            raise NotImplementedError(type(dist).__name__)
         if conc.numel() != 1:
             raise NotImplementedError("usflows_b200.RadialDistribution: one radius distribution per flow (scalar parameters)")
         self.distribution = dist
-        self.norm_kind = ops.NORM_GAMMA_MIXTURE if scale is None else ops.NORM_GAMMA_MIXTURE_SQ
-        self.register_buffer("_conc", conc, persistent=False)
-        self.register_buffer("_rate", rate, persistent=False)
-        self.register_buffer("_scale", scale, persistent=False)
+        self.norm_kind = ops.NORM_GAMMA_MIXTURE if scale is None else ops.NORM_GENGAMMA_MIXTURE
+        for name, t in (("_conc", conc), ("_rate", rate), ("_scale", scale), ("_power", power)):
+            self.register_buffer(name, t, persistent=False)
 
     def _params(self):
         return (self._conc, self._rate)
 
     def _mixture(self):
-        return torch.zeros_like(self._conc), self._conc, self._rate, self._scale
+        return torch.zeros_like(self._conc), self._conc, self._rate, self._scale, self._power
+
+
+class _TorchLogNormalRadius(_LogNormalFamily):
+    """A frozen `torch.distributions.LogNormal` (pyro's is a subclass) as the radius distribution
+    (experiments/mnist/mnist_digits_minimal_radial_lognormal.yaml)."""
+
+    norm_kind = ops.NORM_LOGNORMAL
+
+    def __init__(self, dist):
+        super().__init__()
+        mu, sigma = _frozen(dist.loc), _frozen(dist.scale)
+        if mu.numel() != 1 or sigma.numel() != 1:
+            raise NotImplementedError("usflows_b200.RadialDistribution: one radius distribution per flow (scalar parameters)")
+        self.distribution = dist
+        self.register_buffer("_mu", mu, persistent=False)
+        self.register_buffer("_sigma", sigma, persistent=False)
+
+    def _params(self):
+        return (self._mu, self._sigma)
+
+    def _lognormals(self):
+        return torch.zeros_like(self._mu), self._mu, self._sigma
+
+
+def _wrap_torch_radius(dist):
+    D = torch.distributions
+    if isinstance(dist, D.LogNormal):
+        return _TorchLogNormalRadius(dist)
+    if isinstance(dist, (D.Gamma, D.Exponential, D.HalfNormal, D.Weibull)):
+        return _TorchGammaRadius(dist)
+    raise NotImplementedError(f"usflows_b200.RadialDistribution: radius distribution {type(dist).__name__} is not built "
+                              "(LogNormal, LogNormalMM, GammaMM, Gamma, WeibullMM, Chi, torch LogNormal / Gamma / Chi2 / "
+                              "Exponential / HalfNormal / Weibull are)")
 
 
 class RadialDistribution(Module):
@@ -335,7 +453,7 @@ class RadialDistribution(Module):
         if n_batch_dims != 0:
             raise NotImplementedError("usflows_b200.RadialDistribution: n_batch_dims > 0 is not built")
         if isinstance(norm_distribution, torch.distributions.Distribution):
-            norm_distribution = _TorchRadius(norm_distribution)
+            norm_distribution = _wrap_torch_radius(norm_distribution)
         self.norm_distribution = norm_distribution
         self.event_shape = loc.shape[n_batch_dims:]
         self.batch_shape = loc.shape[:n_batch_dims]

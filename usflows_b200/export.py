@@ -100,17 +100,20 @@ class ReferenceSemantics(torch.nn.Module):
         if type(base).__name__ == "RadialDistribution":            # distributions.py:501-549
             nd = base.norm_distribution
             self.base_kind, self.p, self.dv_const = "radial", base.p, base.log_delta_volume_const()
-            if type(nd).__name__ == "LogNormal":
+            if hasattr(nd, "_lognormals"):                         # log-normal family (single or mixture)
                 self.norm_kind = "lognormal"
-                self.register_buffer("r_mu", nd.loc.detach().clone().reshape(()))
-                self.register_buffer("r_sigma", sp(nd.scale_unconstrained.detach()).reshape(()))
-            else:
+                logits, mu, sg = (t.detach().clone() for t in nd._lognormals())
+                self.register_buffer("r_logw", torch.log_softmax(logits, 0))
+                self.register_buffer("r_mu", mu)
+                self.register_buffer("r_sigma", sg)
+            else:                                                  # (generalised) Gamma family
                 self.norm_kind = "gammamm"
-                logits, conc, rate, scale = (None if t is None else t.detach().clone() for t in nd._mixture())
+                logits, conc, rate, scale, power = (None if t is None else t.detach().clone() for t in nd._mixture())
                 self.register_buffer("r_logw", torch.log_softmax(logits, 0))
                 self.register_buffer("r_conc", conc)
                 self.register_buffer("r_rate", rate)
-                self.register_buffer("r_scale", scale)         # not None: R = scale sqrt(S)  (Chi / HalfNormal)
+                self.register_buffer("r_scale", scale)         # not None: R = scale S^(1 / power)  (Chi, Weibull, HalfNormal)
+                self.register_buffer("r_power", power)
         else:
             self.base_kind = "laplace" if type(base).__name__ == "Laplace" else "normal"
             raw = base.scale_unconstrained.detach()
@@ -300,16 +303,18 @@ class ReferenceSemantics(torch.nn.Module):
             r = v.abs().sum(ev) if self.p == 1.0 else v.pow(2).sum(ev).sqrt() if self.p == 2.0 else v.abs().amax(ev)
             logr = r.log()
             if self.norm_kind == "lognormal":
-                lpr = -((logr - self.r_mu) ** 2) / (2 * self.r_sigma ** 2) - self.r_sigma.log() \
-                    - 0.5 * math.log(2 * math.pi) - logr
+                t = self.r_logw - ((logr[:, None] - self.r_mu) ** 2) / (2 * self.r_sigma ** 2) - self.r_sigma.log() \
+                    - 0.5 * math.log(2 * math.pi)
+                lpr = torch.logsumexp(t, -1) - logr
             else:
-                sq, logsq, extra = r, logr, 0.0
-                if self.r_scale is not None:
-                    logu = logr - self.r_scale.log()
-                    sq, logsq, extra = torch.exp(2 * logu), 2 * logu, math.log(2.0) + logu - self.r_scale.log()
-                t = self.r_logw + self.r_conc * self.r_rate.log() - torch.lgamma(self.r_conc) \
-                    + (self.r_conc - 1) * logsq[:, None] - self.r_rate * sq[:, None]
-                lpr = torch.logsumexp(t, -1) + extra
+                t = self.r_logw + self.r_conc * self.r_rate.log() - torch.lgamma(self.r_conc)
+                if self.r_scale is None:
+                    t = t + (self.r_conc - 1) * logr[:, None] - self.r_rate * r[:, None]
+                else:
+                    lu = logr[:, None] - self.r_scale.log()
+                    t = t + self.r_power.log() - self.r_scale.log() + (self.r_conc * self.r_power - 1) * lu \
+                        - self.r_rate * torch.exp(self.r_power * lu)
+                lpr = torch.logsumexp(t, -1)
             return lpr - (self.dv_const + (self.loc.numel() - 1) * logr) - total
         if self.base_kind == "laplace":
             lp = -torch.log(2 * self.scale) - (z - self.loc).abs() / self.scale

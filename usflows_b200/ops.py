@@ -13,7 +13,7 @@ import torch
 
 from . import _lib
 from ._lib import (BASE_LAPLACE, BASE_NORMAL, ENGINE_SIMT, ENGINE_TC_3XF16, ENGINE_TC_3XTF32,  # noqa: F401
-                   ENGINE_TC_BF16, ENGINE_TC_TF32, LP_1, LP_2, LP_INF, NORM_GAMMA_MIXTURE, NORM_GAMMA_MIXTURE_SQ,
+                   ENGINE_TC_BF16, ENGINE_TC_TF32, LP_1, LP_2, LP_INF, NORM_GAMMA_MIXTURE, NORM_GENGAMMA_MIXTURE, NORM_LOGNORMAL_MIXTURE,
                    NORM_LOGNORMAL, TRI_LOWER_UPPER, TRI_NONE, TRI_UPPER_LOWER, LinearArgs, Planes, check)
 
 

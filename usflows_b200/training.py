@@ -298,26 +298,30 @@ def _convnet2d_rows(net, x: torch.Tensor, geom, context: Optional[torch.Tensor] 
 
 
 def _radial_log_prob(b, z: torch.Tensor) -> torch.Tensor:
-    """Differentiable Lp-radial log-density (distributions.py:501-549) with LogNormal / Gamma-family radius distributions."""
-    from .distributions import LogNormal, _GammaFamily
+    """Differentiable Lp-radial log-density (distributions.py:501-549) with the log-normal and (generalised) Gamma families
+    of radius distributions."""
     v = z - b.loc.reshape(-1)
     r = v.abs().sum(-1) if b.p == 1.0 else v.pow(2).sum(-1).sqrt() if b.p == 2.0 else v.abs().max(-1).values
     logr = r.log()
-    nd = b.norm_distribution
-    sp = torch.nn.functional.softplus
-    if isinstance(nd, LogNormal):
-        mu, sg = nd.loc.reshape(()), sp(nd.scale_unconstrained).reshape(())
-        lp = -((logr - mu) ** 2) / (2 * sg ** 2) - sg.log() - 0.5 * math.log(2 * math.pi) - logr
-    elif isinstance(nd, _GammaFamily):
-        logits, a, rate, scale = nd._mixture()
-        s, extra = r, 0.0
-        if scale is not None:                    # R = scale sqrt(S)  (Chi, distributions.py:88-97)
-            s, extra = (r / scale) ** 2, torch.log(2 * r / scale) - scale.log()
-        t = torch.log_softmax(logits, 0) + a * rate.log() - torch.lgamma(a) + torch.xlogy(a - 1, s[:, None]) - rate * s[:, None]
-        lp = torch.logsumexp(t, -1) + extra
-    else:
-        raise NotImplementedError(f"usflows_b200: training with radius distribution {type(nd).__name__} is not built")
-    return lp - (b.log_delta_volume_const() + (b.dim - 1) * logr)
+    return radius_log_prob(b.norm_distribution, r, logr) - (b.log_delta_volume_const() + (b.dim - 1) * logr)
+
+
+def radius_log_prob(nd, r: torch.Tensor, logr: torch.Tensor) -> torch.Tensor:
+    """log f_R(r) of a radius distribution of `usflows_b200.distributions`, as a torch expression of its parameters."""
+    if hasattr(nd, "_lognormals"):
+        logits, mu, sg = nd._lognormals()
+        t = torch.log_softmax(logits, 0) - ((logr[:, None] - mu) ** 2) / (2 * sg ** 2) - sg.log() - 0.5 * math.log(2 * math.pi)
+        return torch.logsumexp(t, -1) - logr
+    if hasattr(nd, "_mixture"):
+        logits, a, rate, scale, power = nd._mixture()
+        t = torch.log_softmax(logits, 0) + a * rate.log() - torch.lgamma(a)
+        if scale is None:
+            t = t + torch.xlogy(a - 1, r[:, None]) - rate * r[:, None]
+        else:                                    # R = scale S^(1 / power): Chi (distributions.py:88-97), Weibull, HalfNormal
+            lu = logr[:, None] - scale.log()
+            t = t + power.log() - scale.log() + (a * power - 1) * lu - rate * torch.exp(power * lu)
+        return torch.logsumexp(t, -1)
+    raise NotImplementedError(f"usflows_b200: training with radius distribution {type(nd).__name__} is not built")
 
 
 def base_log_prob(base, z: torch.Tensor) -> torch.Tensor:
