@@ -550,3 +550,26 @@ def test_rotation_and_block_lu_layers_match_the_reference():
     device against outputs of the reference (tests/golden/layers.npz)."""
     from helpers import check_standalone_layers
     check_standalone_layers("cuda")
+
+
+@pytest.mark.parametrize("name", ["d32_h64", "d6_hh_normal"])
+def test_plain_torch_distribution_object_as_the_base_on_gpu(name):
+    """A torch Laplace / Normal object as the base (flows.py:97-101): reference log-probs, trains without base gradients."""
+    import usflows_b200 as U
+    spec, params, arr = load_case(name)
+    flow = build_flow(spec, params, precision="fp32")
+    b = flow.base_distribution.base_dist if hasattr(flow.base_distribution, "base_dist") else flow.base_distribution
+    scale = torch.nn.functional.softplus(b.scale_unconstrained.detach())
+    cls = torch.distributions.Laplace if spec["base"] == "laplace" else torch.distributions.Normal
+    plain = U.Flow(cls(b.loc.detach(), scale), flow.layers, device="cuda", precision="fp32")
+    lp = plain.log_prob(arr["x"].cuda())
+    assert rel_err(lp, arr["lp64"]) <= TOL["fp32"][0] + 3 * rel_err(arr["lp32"], arr["lp64"])
+    assert torch.equal(lp, flow.log_prob(arr["x"].cuda())) or rel_err(lp, flow.log_prob(arr["x"].cuda())) < 1e-6
+    s = plain.sample([1000])
+    assert s.shape == (1000, *spec["in_dims"]) and bool(torch.isfinite(s).all())
+    assert not any(k.startswith("base_distribution") for k in plain.state_dict())
+    # one training step on the autograd route (the base has nothing to learn; the layers do)
+    from usflows_b200 import training
+    ts = training.TrainStep(plain, U.SophiaG(list(plain.parameters()), lr=1e-4, weight_decay=0.0), distributed=False)
+    l0 = float(ts.step(arr["x"].cuda()))
+    assert l0 == l0 and abs(l0 + float(arr["lp64"].mean())) < 1e-3 * max(1.0, abs(l0))

@@ -299,3 +299,24 @@ def test_rotation_and_block_lu_layers_match_the_reference(fake_ops):
     outputs of the reference (tests/golden/layers.npz)."""
     from helpers import check_standalone_layers
     check_standalone_layers("cpu")
+
+
+@pytest.mark.parametrize("name", ["d32_h64", "d6_hh_normal"])
+def test_plain_torch_distribution_object_as_the_base(fake_ops, name):
+    """`Flow` takes a plain torch Laplace / Normal object (the reference's older configurations pass
+    `pyro.distributions.Laplace(loc, scale)`; flows.py:97-101 turns its batch dims into event dims): same log-probs as the
+    module base, no parameters, no state-dict keys of the base."""
+    import usflows_b200 as U
+    spec, params, arr = load_case(name)
+    flow = build_flow(spec, params, device="cpu", precision="fp32")
+    b = flow.base_distribution.base_dist if hasattr(flow.base_distribution, "base_dist") else flow.base_distribution
+    scale = torch.nn.functional.softplus(b.scale_unconstrained.detach())
+    cls = torch.distributions.Laplace if spec["base"] == "laplace" else torch.distributions.Normal
+    for dist in (cls(b.loc.detach(), scale), torch.distributions.Independent(cls(b.loc.detach(), scale), 1)):
+        plain = U.Flow(dist, flow.layers, device="cpu", precision="fp32")
+        assert rel_err(plain.log_prob(arr["x"]), arr["lp32"]) < 2e-5
+        assert not any(k.startswith("base_distribution") for k in plain.state_dict())
+        assert not any(n.startswith("base_distribution") for n, _ in plain.named_parameters())
+        assert tuple(plain.sample([7]).shape) == (7, *spec["in_dims"])
+    with pytest.raises(NotImplementedError):
+        U.Flow(torch.distributions.Cauchy(torch.zeros(4), torch.ones(4)), flow.layers)

@@ -101,6 +101,31 @@ class Normal(DistributionModule):
         self.to(device)
 
 
+class _FrozenBase(DistributionModule):
+    """A plain `torch.distributions.Laplace` / `Normal` object (optionally inside `torch.distributions.Independent`) as
+    the base -- the reference's `Flow` takes any object with `log_prob` / `sample` / `batch_shape` and makes the batch dims
+    event dims (flows.py:97-101); its older configurations pass `pyro.distributions.Laplace(loc, scale)` this way.  The
+    values are read once into non-persistent buffers: no parameters and no state-dict keys, as in the reference."""
+
+    def __init__(self, dist):
+        super().__init__()
+        D = torch.distributions
+        while isinstance(dist, D.Independent):
+            dist = dist.base_dist
+        if isinstance(dist, D.Laplace):
+            self.base_kind = ops.BASE_LAPLACE
+        elif isinstance(dist, D.Normal):
+            self.base_kind = ops.BASE_NORMAL
+        else:
+            raise NotImplementedError(f"usflows_b200.Flow: base distribution {type(dist).__name__} is not built (Laplace, "
+                                      "Normal, RadialDistribution modules and torch Laplace / Normal objects are)")
+        loc, scale = torch.broadcast_tensors(torch.as_tensor(dist.loc, dtype=torch.float32),
+                                             torch.as_tensor(dist.scale, dtype=torch.float32))
+        self.distribution = dist
+        self.register_buffer("loc", loc.detach().clone(), persistent=False)
+        self.register_buffer("scale_unconstrained", inv_softplus(scale.detach().clone()), persistent=False)
+
+
 class Independent(Module):
     """Reinterprets batch dims of a DistributionModule as event dims (distributions.py:709-728).  The fused
     base-density kernel already sums over every non-batch dim, so this is bookkeeping only."""

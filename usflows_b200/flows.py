@@ -15,7 +15,7 @@ from typing import Any, Dict, Iterable, List, Literal, Optional, Type
 import torch
 
 from . import engine, image_engine, ops
-from .distributions import DistributionModule, Independent
+from .distributions import DistributionModule, Independent, _FrozenBase
 from .transforms import MaskedAffineCoupling
 from .transforms import (BaseTransform, Bijective1x1Conv2d, BlockAffineTransform, HouseholderTransform, InverseTransform, LUTransform,
                          MaskedCoupling, ScaleTransform, SequentialAffineTransform)
@@ -120,6 +120,8 @@ class Flow(torch.nn.Module):
         self.training_noise_prior = training_noise_prior
         self.layers = layers
         self.trainable_layers = torch.nn.ModuleList([l for l in layers if isinstance(l, torch.nn.Module)])
+        if isinstance(base_distribution, torch.distributions.Distribution):      # a plain torch Laplace / Normal object
+            base_distribution = _FrozenBase(base_distribution)
         self.base_distribution = base_distribution
         self.precision = precision
         self.to(device)

@@ -89,13 +89,13 @@ def _ops_of(flow) -> Optional[List[tuple]]:
 
 
 def supports(flow) -> bool:
-    from .distributions import DistributionModule, Independent, RadialDistribution
+    from .distributions import DistributionModule, Independent, RadialDistribution, _FrozenBase
     ev = tuple(flow._event_shape())
     if len(ev) != 1 or ev[0] % 8 or ev[0] < 32 or getattr(flow, "soft_training", False):
         return False
     base = flow.base_distribution.base_dist if isinstance(flow.base_distribution, Independent) else flow.base_distribution
-    if not isinstance(base, DistributionModule) or isinstance(base, RadialDistribution) or base.base_kind < 0:
-        return False
+    if not isinstance(base, DistributionModule) or isinstance(base, (RadialDistribution, _FrozenBase)) or base.base_kind < 0:
+        return False                  # (a frozen torch-object base has no gradients to write: autograd route)
     seq = _ops_of(flow)
     if not seq or any(k == "scale" for k, _ in seq[1:]):
         return False
