@@ -351,8 +351,26 @@ def with_context(x: Tensor, context) -> Tensor:
     return torch.cat([x, c], dim=1)
 
 
+def cond_dense_nn(x: Tensor, prefix: str, params, n_hidden: int, context) -> Tensor:
+    """networks.ConditionalDenseNN.forward (networks.py:733-749); layers = [input, context, hidden ..., output]
+    (:716-724): h = layers[0](x) (+ layers[1](context)); h = f(h); h = f(layer(h)) for the hidden ones; layers[-1](h)."""
+    lin = lambda j, h: F.linear(h, params[f"{prefix}layers.{j}.weight"], params[f"{prefix}layers.{j}.bias"])  # noqa: E731
+    h = lin(0, x)
+    if context is not None:
+        h = h + lin(1, context.to(x.dtype))
+    h = F.relu(h)
+    for j in range(2, n_hidden + 1):
+        h = F.relu(lin(j, h))
+    return lin(n_hidden + 1, h)
+
+
 def conditioner(x: Tensor, layer: dict, params, n_layers: int, spec=None) -> Tensor:
     kind = spec.get("conditioner") if spec is not None else None
+    if kind == "conddense":     # USFlow substitutes a zero context [N, 1] when soft_training and none is given (flows.py:559-565)
+        ctx = spec.get("_context")     # `backward` / `_forward` hand none over (flows.py:45-67): the context layer is skipped
+        if ctx is None and spec.get("_zero_context"):
+            ctx = torch.zeros(x.shape[0], 1, dtype=x.dtype)
+        return cond_dense_nn(x, layer["prefix"], params, len(spec["hidden_dims"]), ctx)
     if kind in COND_KINDS:      # soft training (flows.py:172-193, 559-565): spec["_context"] is the context of this call
         x = with_context(x, spec.get("_context"))
         kind = COND_KINDS[kind]
@@ -668,6 +686,8 @@ def flow_log_prob(x: Tensor, spec: dict, params, dtype=torch.float32) -> Tensor:
     return base.log_prob(y) + log_det."""
     params = _cast(params, dtype)
     x = x.to(dtype)
+    if spec.get("soft_training") and spec.get("_context") is None:    # USFlow.log_prob: implicit context 0 (flows.py:559-565)
+        spec = dict(spec, _zero_context=True)
     log_det = torch.zeros(x.shape[0], dtype=dtype)
     for layer in reversed(build_layers(spec)):
         y = layer_backward(x, layer, spec, params)
@@ -696,6 +716,8 @@ def flow_log_prob_amortised(x: Tensor, spec: dict, params, dtype=torch.float32, 
     ladj) are computed once and reused: the "amortised" CPU baseline of BASELINE.md section 4.
     Returns (log_prob, prepared)."""
     params = _cast(params, dtype)
+    if spec.get("soft_training") and spec.get("_context") is None:
+        spec = dict(spec, _zero_context=True)
     layers = build_layers(spec)
     in_dims = spec["in_dims"]
     rank = len(in_dims) - 1
@@ -841,6 +863,13 @@ def random_params(spec: dict, seed: int = 0, min_abs_scale: float = 0.1) -> Dict
                     out[f"{p}nn.{idx}.layernorm.bias"] = uni((oc,), 0.2)
                     idx += 1
             lin(f"nn.{idx}", dtot, ch[-1])
+        elif layer["kind"] == "coupling" and spec.get("conditioner") == "conddense":     # networks.py:716-724
+            shapes = [(hidden[0], dtot), (hidden[0], 1)] + [(hidden[i], hidden[i - 1]) for i in range(1, len(hidden))] \
+                + [(dtot, hidden[-1])]
+            for j, (o, i) in enumerate(shapes):
+                bound = 1 / math.sqrt(i) if j != 1 else 0.5
+                out[f"{p}layers.{j}.weight"] = uni((o, i), bound)
+                out[f"{p}layers.{j}.bias"] = uni((o,), bound)
         elif layer["kind"] == "coupling":
             dims = [dtot] + hidden + [2 * dtot if spec.get("coupling") == "affine" else dtot]
             for j in range(len(dims) - 1):

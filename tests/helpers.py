@@ -18,14 +18,16 @@ EXT_CASES = ["d64_convnet", "d64_convnet_proj_radial2", "d40_convnet_plain_gmm1"
              "d32_radial2_chi", "d24_radial1_chi2", "d16_radialinf_halfnormal",
              # torch's Weibull / Exponential / LogNormal objects, the reference's WeibullMM / LogNormalMM radius mixtures
              "d20_radial1_weibull", "d12_radial1_exponential", "d18_radial2_torchlognormal", "d28_radialinf_weibullmm",
-             "d30_radial2_lognormalmm"]
+             "d30_radial2_lognormalmm",
+             "d36_conddense_nocontext"]   # networks.ConditionalDenseNN outside soft training: its context layer is never used
 # image-shaped events [C, H, W] (1x1-convolution BlockAffine, ConvNet2D conditioners, [C, H, W] masks)
 IMG_CASES = ["img_c4_4x4", "img_mnist_16x7x7", "img_c6_5x3_plain_channel", "img_c32_4x4_noln",
              # networks.ConvNet's convolutional branch (networks.py:308-377) as the conditioner
              "img_convnet_c4_4x4_proj", "img_convnet_c6_5x3_plain", "img_convnet_16x7x7",
              "img_c4_4x4_radial2_gamma"]      # single-Gamma radius (distributions.py:162-179)
 # soft training (flows.py:172-193, 559-565): context-conditioned conditioners; fixtures also hold `ctx`, `lp32_ctx`, `lp64_ctx`
-SOFT_CASES = ["soft_img_c4_4x4", "soft_img_mnist_16x7x7", "soft_img_convnet_c4_4x4", "soft_d24_convnet"]
+SOFT_CASES = ["soft_img_c4_4x4", "soft_img_mnist_16x7x7", "soft_img_convnet_c4_4x4", "soft_d24_convnet",
+              "soft_d40_conddense"]      # networks.ConditionalDenseNN: zero context in log_prob, none in backward / _forward
 
 
 def load_case(name):

@@ -320,3 +320,32 @@ def test_plain_torch_distribution_object_as_the_base(fake_ops, name):
         assert tuple(plain.sample([7]).shape) == (7, *spec["in_dims"])
     with pytest.raises(NotImplementedError):
         U.Flow(torch.distributions.Cauchy(torch.zeros(4), torch.ones(4)), flow.layers)
+
+
+def test_conditional_dense_nn_contract(fake_ops):
+    """`ConditionalDenseNN` (networks.py:681-752): reference layer list / state-dict keys; no context skips the context
+    layer, a context adds `L1 c` before the first ReLU; a soft-training USFlow lowers `log_prob` with the zero context
+    (the context layer's bias stays) and `backward` without one -- two launch programs per direction."""
+    import usflows_b200 as U
+    torch.manual_seed(0)
+    net = U.ConditionalDenseNN(12, 1, [16, 8], 12)
+    assert list(net.state_dict()) == [f"layers.{i}.{n}" for i in range(4) for n in ("weight", "bias")]
+    assert net.layers[1].weight.shape == (16, 1) and net.context_channels == 1
+    x, c = torch.randn(9, 12), torch.rand(9, 1)
+    L = net.layers
+    def ref(ctx):
+        h = L[0](x) if ctx is None else L[0](x) + L[1](ctx)
+        return L[3](torch.relu(L[2](torch.relu(h))))
+    assert rel_err(net(x), ref(None).detach()) < 1e-6
+    assert rel_err(net(x, c), ref(c).detach()) < 1e-6
+    assert rel_err(net(x, torch.zeros(9, 1)), ref(torch.zeros(9, 1)).detach()) < 1e-6
+    with pytest.raises(NotImplementedError):
+        U.ConditionalDenseNN(12, 1, [16], 12, nonlinearity=torch.nn.Tanh())
+    spec, params, arr = load_case("soft_d40_conddense")
+    flow = build_flow(spec, params, device="cpu", precision="fp32")
+    flow.log_prob(arr["x"]); flow.backward(arr["x"]); flow._forward(arr["z0"]); flow.sample([3])
+    assert sorted(flow._programs, key=str) == [("backward", False), ("backward", True), ("forward", False), ("forward", True)]
+    assert rel_err(flow.log_prob(arr["x"], arr["ctx"]), arr["lp32_ctx"]) < 2e-5
+    hard = build_flow(dict(spec, soft_training=False), params, device="cpu", precision="fp32")
+    assert rel_err(hard.backward(arr["x"]), arr["z32"]) < 5e-5          # without soft training: never a context
+    assert rel_err(hard.log_prob(arr["x"]), arr["lp32"]) > 1e-4         # ... so log_prob lacks the context layer's bias

@@ -52,6 +52,9 @@ def build_flow(spec, params=None, device="cuda", precision=None):
                          normalize_layers=spec.get("normalize_layers", True), kernel_size=spec.get("kernel_size", 3))
         if cond_cls is U.CondConvNet:
             cond_args["c_out"] = d
+    elif spec.get("conditioner") == "conddense":
+        cond_cls = U.ConditionalDenseNN
+        cond_args = dict(input_dim=d, context_dim=1, hidden_dims=list(spec["hidden_dims"]), out_dim=d)
     else:
         cond_cls = U.DenseNN
         cond_args = dict(input_dim=d, hidden_dims=list(spec["hidden_dims"]),

@@ -917,7 +917,7 @@ def run_mlp(net, x: torch.Tensor, mode: Optional[str] = None) -> torch.Tensor:
 def _run_mlp(net, x, mode):
     x2, batch_shape = _flatten_rows(x)
     mode = mode or _default_precision
-    lin = list(net.layers)
+    lin = list(net.layers)                   # DenseNN, or an _MLPView of a ConditionalDenseNN without its context layer
     if min(min(l.weight.shape) for l in lin) < TC_MIN_DIM:
         mode = "fp32_simt"
     steps = []

@@ -28,6 +28,8 @@ class ReferenceSemantics(torch.nn.Module):
         super().__init__()
         from . import transforms as T
         from .distributions import Independent
+        for net in getattr(flow, "_cond_dense_nets", ()):      # zero context in log_prob / sample of a soft USFlow only
+            net.zero_context_default = bool(getattr(flow, "_zero_ctx", False)) and mode in ("log_prob", "sample")
         if mode not in ("log_prob", "backward", "forward", "sample"):
             raise ValueError(f"Unknown export mode {mode}")
         self.mode = mode
@@ -75,7 +77,8 @@ class ReferenceSemantics(torch.nn.Module):
             elif isinstance(layer, T.MaskedCoupling):
                 self.kinds.append("coupling")
                 reg(layer.mask.reshape(-1))
-                for lin in layer.conditioner.layers:
+                from .nn import mlp_layers
+                for lin in mlp_layers(layer.conditioner):            # ConditionalDenseNN: without / with zero context
                     reg(lin.weight)
                     reg(lin.bias)
             elif isinstance(layer, T.ScaleTransform):

@@ -123,6 +123,16 @@ class Flow(torch.nn.Module):
         if isinstance(base_distribution, torch.distributions.Distribution):      # a plain torch Laplace / Normal object
             base_distribution = _FrozenBase(base_distribution)
         self.base_distribution = base_distribution
+        # ConditionalDenseNN conditioners tell "no context" (its context layer is skipped: `backward` / `_forward`,
+        # flows.py:45-67) from the zero context that a soft-training USFlow substitutes in `log_prob` / `sample`
+        # (flows.py:559-565, 580-590: the context layer's bias stays) -- two launch programs per direction
+        self._cond_dense_nets = []
+        for l in layers:
+            while isinstance(l, InverseTransform):
+                l = l.transform
+            if isinstance(l, MaskedCoupling) and hasattr(l.conditioner, "zero_context_default"):
+                self._cond_dense_nets.append(l.conditioner)
+        self._zero_ctx = bool(soft_training and self._context_needs_soft_training)
         self.precision = precision
         self.to(device)
         self.device = device
@@ -196,7 +206,7 @@ class Flow(torch.nn.Module):
                 l = l.transform
             if isinstance(l, MaskedCoupling) and not getattr(l.conditioner, "context_channels", 0):
                 raise TypeError(f"soft_training passes a context to the conditioner; {type(l.conditioner).__name__} takes "
-                                "none (use CondConvNet / CondConvNet2D)")
+                                "none (use ConditionalDenseNN / CondConvNet / CondConvNet2D)")
 
     def _with_context(self, what: str, x: torch.Tensor, context: torch.Tensor) -> torch.Tensor:
         """Evaluation with an explicit context (flows.py:235-238, 257-263): the context channel of the conditional
@@ -214,7 +224,7 @@ class Flow(torch.nn.Module):
             return training.apply_autograd(self, x2, what, context).reshape(*batch_shape, *x2.shape[1:])
 
     def _log_prob(self, x: torch.Tensor) -> torch.Tensor:
-        prog, ladj = self._program("backward")
+        prog, ladj = self._program("backward", self._zero_ctx)
         base = self._base_module()
         base._prepared()                  # parameter-side work happens here, outside any graph capture
         x2, batch_shape = engine._flatten_rows(x, len(self._event_shape()))
@@ -376,7 +386,7 @@ class Flow(torch.nn.Module):
 
     def _log_prob_host(self, x_host, out_host, chunk_rows):
         dev = next(self.parameters()).device
-        prog, ladj = self._program("backward")
+        prog, ladj = self._program("backward", self._zero_ctx)
         base = self._base_module()
         base._prepared()                  # parameter-side work happens here, outside any graph capture
         x2 = x_host.reshape(-1, math.prod(self._event_shape()))
@@ -527,7 +537,7 @@ class Flow(torch.nn.Module):
             z = self.base_distribution.sample(shape)
             ev = len(self._event_shape())
             z = z.reshape(-1, *z.shape[z.dim() - ev:])
-            y = self._run("forward", z) if context is None else self._with_context("forward", z, context)
+            y = self._run("forward", z, self._zero_ctx) if context is None else self._with_context("forward", z, context)
         return y.reshape(*shape, *y.shape[1:])
 
     def fit(self, data_train, optim=None, optim_params: Optional[Dict[str, Any]] = None, batch_size: int = 32,
@@ -581,12 +591,18 @@ class Flow(torch.nn.Module):
     def _weights_key(self):
         return tuple((p.data_ptr(), p._version) for p in self.parameters())
 
-    def _program(self, direction: str):
-        """(Program, total forward log|det J|) for the current weight version."""
+    def _program(self, direction: str, zero_ctx: bool = False):
+        """(Program, total forward log|det J|) for the current weight version; `zero_ctx`: lowered for the zero context of a
+        soft-training `log_prob` / `sample` (only ConditionalDenseNN conditioners tell it from no context)."""
         mode = self.precision or engine.get_precision()
         key = (mode,) + self._weights_key()
-        hit = self._programs.get(direction)
+        slot = direction
+        if self._cond_dense_nets:
+            slot = (direction, bool(zero_ctx))
+        hit = self._programs.get(slot)
         if hit is None or hit[0] != key:
+            for net in self._cond_dense_nets:
+                net.zero_context_default = bool(zero_ctx)
             with torch.no_grad():
                 ev = tuple(self._event_shape())
                 if len(ev) == 3:
@@ -597,7 +613,7 @@ class Flow(torch.nn.Module):
                     raise NotImplementedError("usflows_b200: events of shape [d] and [C, H, W] are built")
             ladj, n_bad = engine.total_ladj(self.layers)
             hit = (key, prog, ladj, n_bad)
-            self._programs[direction] = hit
+            self._programs[slot] = hit
         return hit[1], hit[2]
 
     def _apply_plan(self, prog, x2: torch.Tensor) -> torch.Tensor:
@@ -619,10 +635,10 @@ class Flow(torch.nn.Module):
                 prog._fallback().run(x2[r0:r1], out=y[r0:r1])
         return y
 
-    def _run(self, direction: str, x: torch.Tensor) -> torch.Tensor:
+    def _run(self, direction: str, x: torch.Tensor, zero_ctx: bool = False) -> torch.Tensor:
         x2, batch_shape = engine._flatten_rows(x, len(self._event_shape()))
         with torch.no_grad(), ops.on_device(x2):
-            prog, _ = self._program(direction)
+            prog, _ = self._program(direction, zero_ctx)
             if USE_C_PLAN and x2.is_cuda and x2.shape[0] > 0 and isinstance(prog, engine.Program) and prog.plan_able() \
                     and not torch.cuda.is_current_stream_capturing():
                 y = self._apply_plan(prog, x2)

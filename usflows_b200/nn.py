@@ -34,6 +34,67 @@ class DenseNN(torch.nn.Module):
         return tuple(out.split(self.param_dims, dim=-1))       # pyro.nn.DenseNN returns one tensor per entry of param_dims
 
 
+class _DenseView:
+    """weight / bias of one Linear as the contraction kernels will see it (`bias` may be a sum of two parameters)."""
+
+    def __init__(self, weight, bias):
+        self.weight, self.bias = weight, bias
+
+
+class _MLPView:
+    def __init__(self, layers):
+        self.layers = layers
+
+
+def mlp_layers(net) -> list:
+    """The Linear / ReLU stack a coupling lowers for a `DenseNN` or a `ConditionalDenseNN` evaluated without an explicit
+    context (objects with `.weight` [out, in] and `.bias`)."""
+    return net._mlp_layers() if hasattr(net, "_mlp_layers") else list(net.layers)
+
+
+class ConditionalDenseNN(torch.nn.Module):
+    """`networks.ConditionalDenseNN` (networks.py:681-752): a Linear / ReLU stack whose first layer adds a Linear of the
+    context, `h = f(L0 x + L1 c)`; `layers = [L0 (input), L1 (context), hidden ..., output]` with the reference's state-dict
+    keys (`layers.<i>.weight / bias`).  The soft-training conditioner for flat events (flows.py:172-193 hands every
+    coupling the per-sample noise scale as `context` [N, 1]).
+
+    Without an explicit context the stack is a plain MLP and runs on the fused coupling launches: `context=None` leaves
+    `L1` out altogether (networks.py:739-741), the zero context a soft-training `USFlow` substitutes (flows.py:559-565)
+    contributes `L1`'s bias, which is folded into `L0`'s (`zero_context_default`, set by the flow).  With a context the
+    first layer gets the rank-`context_dim` term on the layer-by-layer route (training.py)."""
+
+    def __init__(self, input_dim, context_dim, hidden_dims, out_dim, nonlinearity=torch.nn.ReLU()):
+        super().__init__()
+        _require_relu(nonlinearity)
+        self.input_dim, self.context_dim, self.hidden_dims, self.out_dim = input_dim, context_dim, list(hidden_dims), out_dim
+        layers = [torch.nn.Linear(input_dim, self.hidden_dims[0]), torch.nn.Linear(context_dim, self.hidden_dims[0])]
+        for i in range(1, len(self.hidden_dims)):
+            layers.append(torch.nn.Linear(self.hidden_dims[i - 1], self.hidden_dims[i]))
+        layers.append(torch.nn.Linear(self.hidden_dims[-1], out_dim))
+        self.layers = torch.nn.ModuleList(layers)
+        self.f = nonlinearity
+        self.zero_context_default = False
+
+    @property
+    def context_channels(self) -> int:
+        return self.context_dim
+
+    def _mlp_layers(self, zero_context=None) -> list:
+        zero = self.zero_context_default if zero_context is None else zero_context
+        first = self.layers[0]
+        if zero:
+            first = _DenseView(first.weight, first.bias + self.layers[1].bias)
+        return [first] + list(self.layers[2:])
+
+    def forward(self, x: torch.Tensor, context=None) -> torch.Tensor:
+        if context is None:
+            from . import engine
+            return engine.run_mlp(_MLPView(self._mlp_layers(False)), x)
+        from . import training
+        with torch.no_grad():
+            return training._conditioner(self, x.reshape(-1, x.shape[-1]), context).reshape(*x.shape[:-1], self.out_dim)
+
+
 # --------------------------------------------------------------------------------------------------
 # The reference's own MLP-style conditioner: `networks.ConvNet` with 1-D in_dims (networks.py:205-245, 248-307, 379-389)
 # --------------------------------------------------------------------------------------------------

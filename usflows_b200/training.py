@@ -232,6 +232,19 @@ def _conditioner(net, h: torch.Tensor, context: Optional[torch.Tensor] = None) -
                 ln = blk["ln"]
                 x = torch.nn.functional.layer_norm(x, ln.normalized_shape, ln.weight, ln.bias, ln.eps)
         return linear(x, d["last"].weight, d["last"].bias)
+    if hasattr(net, "_mlp_layers"):                   # ConditionalDenseNN (networks.py:733-749): h = f(L0 x + L1 c), ...
+        lin = net._mlp_layers(False)
+        h = linear(h, lin[0].weight, lin[0].bias)
+        if context is not None:                       # rank-context_dim term: element-wise glue, not a contraction
+            c = context.to(device=h.device, dtype=h.dtype).reshape(-1, net.context_dim)
+            if c.shape[0] != h.shape[0]:
+                raise ValueError("context must hold one row per sample")
+            h = h + c @ net.layers[1].weight.t() + net.layers[1].bias
+        elif net.zero_context_default:                # the zero context of a soft-training flow (flows.py:559-565)
+            h = h + net.layers[1].bias
+        for l in lin[1:]:
+            h = linear(torch.relu(h), l.weight, l.bias)
+        return h
     lin = list(net.layers)
     for j, l in enumerate(lin):
         h = linear(h, l.weight, l.bias)
@@ -344,6 +357,8 @@ def apply_autograd(flow, x: torch.Tensor, direction: str, context: Optional[torc
     """`Flow.backward` ("backward": data -> latent) / `Flow._forward` ("forward") on the autograd route -- the route that
     takes a context (flows.py:45-67 with the `context` of :235-238, 257-263)."""
     ev = tuple(flow._event_shape())
+    for net in getattr(flow, "_cond_dense_nets", ()):      # `backward` / `_forward` without a context skip the context layer
+        net.zero_context_default = False
     geom = ev if len(ev) == 3 else None
     if geom is not None:
         C, H, W = ev
@@ -362,6 +377,8 @@ def log_prob_autograd(flow, x: torch.Tensor, context: Optional[torch.Tensor] = N
     """`Flow.log_prob` (flows.py:225-245) as an autograd graph over the flow's parameters; `context` [N] / [N, 1] reaches
     the conditional conditioners (soft training, flows.py:172-193)."""
     ev = tuple(flow._event_shape())
+    for net in getattr(flow, "_cond_dense_nets", ()):      # log_prob without a context: the zero context of a soft USFlow
+        net.zero_context_default = bool(getattr(flow, "_zero_ctx", False))
     geom = None
     if len(ev) == 3:                             # image-shaped event: channels-last rows [N*H*W, C] through the layers
         geom = ev

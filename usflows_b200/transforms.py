@@ -795,7 +795,8 @@ class MaskedCoupling(BaseTransform):
             dev = desc["first"][0].device
             return dict(net="convnet", desc=desc, weights=engine._convnet_weights(desc),
                         mask=self.mask.to(dev).reshape(-1).to(torch.float32))
-        lin = list(self.conditioner.layers)
+        from .nn import mlp_layers
+        lin = mlp_layers(self.conditioner)
         for l in lin:
             ops.require_cuda(l.weight, "conditioner parameter")
         dev = lin[0].weight.device
@@ -805,9 +806,10 @@ class MaskedCoupling(BaseTransform):
     def _prepared(self) -> dict:
         """Mask folded into the first / last Linear: (x*m) W1^T = x (W1 diag(m))^T and
         (1-m) * (h W3^T + b3) = h (diag(1-m) W3)^T + (1-m) b3 -- exact, multiplying by 0/1."""
-        lin = list(self.conditioner.layers)
-        params = [p for layer in lin for p in (layer.weight, layer.bias)]
-        key = _versions(params) + (self.mask.data_ptr(),)
+        from .nn import mlp_layers
+        params = list(self.conditioner.parameters())
+        key = _versions(params) + (self.mask.data_ptr(), bool(getattr(self.conditioner, "zero_context_default", False)))
+        lin = mlp_layers(self.conditioner)
         if getattr(self, "_prep_key", None) != key:
             for p in params:
                 ops.require_cuda(p, "conditioner parameter")
