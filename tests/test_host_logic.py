@@ -349,3 +349,16 @@ def test_conditional_dense_nn_contract(fake_ops):
     hard = build_flow(dict(spec, soft_training=False), params, device="cpu", precision="fp32")
     assert rel_err(hard.backward(arr["x"]), arr["z32"]) < 5e-5          # without soft training: never a context
     assert rel_err(hard.log_prob(arr["x"]), arr["lp32"]) > 1e-4         # ... so log_prob lacks the context layer's bias
+
+
+def test_additive_affine_nn(fake_ops):
+    """networks.AdditiveAffineNN (networks.py:14-38): [loc, 0] from a DenseNN under `loc_fnc`."""
+    import usflows_b200 as U
+    torch.manual_seed(1)
+    net = U.AdditiveAffineNN(10, [16, 16], 6)
+    assert list(net.state_dict()) == [f"loc_fnc.layers.{i}.{n}" for i in range(3) for n in ("weight", "bias")]
+    x = torch.randn(5, 10)
+    loc, log_scale = net(x)
+    L = net.loc_fnc.layers
+    want = L[2](torch.relu(L[1](torch.relu(L[0](x))))).detach()
+    assert rel_err(loc, want) < 1e-6 and log_scale.shape == loc.shape and not log_scale.any()

@@ -34,6 +34,20 @@ class DenseNN(torch.nn.Module):
         return tuple(out.split(self.param_dims, dim=-1))       # pyro.nn.DenseNN returns one tensor per entry of param_dims
 
 
+class AdditiveAffineNN(torch.nn.Module):
+    """`networks.AdditiveAffineNN` (networks.py:14-38): a DenseNN `loc_fnc` that yields `[loc, log_scale]` with
+    `log_scale = 0` -- the parameters of a purely additive affine transform (state-dict keys `loc_fnc.layers.<i>. ...`)."""
+
+    def __init__(self, input_dim: int, hidden_dims, output_dim: int, nonlinearity=None):
+        super().__init__()
+        self.loc_fnc = DenseNN(input_dim, hidden_dims, [output_dim],
+                               nonlinearity=torch.nn.ReLU() if nonlinearity is None else nonlinearity)
+
+    def forward(self, x: torch.Tensor):
+        loc = self.loc_fnc(x)
+        return [loc, torch.zeros_like(loc)]
+
+
 class _DenseView:
     """weight / bias of one Linear as the contraction kernels will see it (`bias` may be a sum of two parameters)."""
 
