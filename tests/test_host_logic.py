@@ -312,7 +312,8 @@ def test_plain_torch_distribution_object_as_the_base(fake_ops, name):
     b = flow.base_distribution.base_dist if hasattr(flow.base_distribution, "base_dist") else flow.base_distribution
     scale = torch.nn.functional.softplus(b.scale_unconstrained.detach())
     cls = torch.distributions.Laplace if spec["base"] == "laplace" else torch.distributions.Normal
-    for dist in (cls(b.loc.detach(), scale), torch.distributions.Independent(cls(b.loc.detach(), scale), 1)):
+    for dist in (cls(b.loc.detach(), scale), torch.distributions.Independent(cls(b.loc.detach(), scale), 1),
+                 U.Independent(cls(b.loc.detach(), scale), 1)):          # the reference's own wrapper (distributions.py:709-728)
         plain = U.Flow(dist, flow.layers, device="cpu", precision="fp32")
         assert rel_err(plain.log_prob(arr["x"]), arr["lp32"]) < 2e-5
         assert not any(k.startswith("base_distribution") for k in plain.state_dict())

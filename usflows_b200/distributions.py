@@ -132,6 +132,9 @@ class Independent(Module):
 
     def __init__(self, base_distribution: DistributionModule, reinterpreted_batch_ndims: int = 0):
         super().__init__()
+        if isinstance(base_distribution, torch.distributions.Distribution):   # the reference's wraps torch objects (:712-728)
+            # a torch Laplace / Normal [d] has batch_shape [d]; the frozen module treats those dims as the event already
+            base_distribution, reinterpreted_batch_ndims = _FrozenBase(base_distribution), 0
         self._base_distribution = base_distribution
         self.reinterpreted_batch_ndims = reinterpreted_batch_ndims
 
