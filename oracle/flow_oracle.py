@@ -364,8 +364,27 @@ def cond_dense_nn(x: Tensor, prefix: str, params, n_hidden: int, context) -> Ten
     return lin(n_hidden + 1, h)
 
 
+def bottleneck_conv(x: Tensor, prefix: str, params) -> Tensor:
+    """networks.BottleneckConv.forward (networks.py:802-824): conv / ReLU twice (down to one channel), view [N, H*W],
+    Linear / ReLU twice, view [N, 1, H, W], conv / ReLU twice (the output is rectified too)."""
+    spatial = x.shape[2:]
+    for j in range(2):
+        x = F.relu(F.conv2d(x, params[f"{prefix}in_convolutions.{j}.weight"], params[f"{prefix}in_convolutions.{j}.bias"],
+                            padding="same"))
+    x = x.view(x.shape[0], -1)
+    for j in range(2):
+        x = F.relu(F.linear(x, params[f"{prefix}linear_layers.{j}.weight"], params[f"{prefix}linear_layers.{j}.bias"]))
+    x = x.view(x.shape[0], 1, *spatial)
+    for j in range(2):
+        x = F.relu(F.conv2d(x, params[f"{prefix}out_convolutions.{j}.weight"], params[f"{prefix}out_convolutions.{j}.bias"],
+                            padding="same"))
+    return x
+
+
 def conditioner(x: Tensor, layer: dict, params, n_layers: int, spec=None) -> Tensor:
     kind = spec.get("conditioner") if spec is not None else None
+    if kind == "bottleneck":
+        return bottleneck_conv(x, layer["prefix"], params)
     if kind == "conddense":     # USFlow substitutes a zero context [N, 1] when soft_training and none is given (flows.py:559-565)
         ctx = spec.get("_context")     # `backward` / `_forward` hand none over (flows.py:45-67): the context layer is skipped
         if ctx is None and spec.get("_zero_context"):
@@ -794,6 +813,16 @@ def random_params(spec: dict, seed: int = 0, min_abs_scale: float = 0.1) -> Dict
                     w = torch.zeros(d0, d0)
                     w[torch.arange(d0), torch.randperm(d0, generator=g)] = 1.0
                     out[q + "w_0"] = w
+        elif layer["kind"] == "coupling" and spec.get("conditioner") == "bottleneck":      # networks.py:776-798
+            ch, k, npix = int(spec["c_hidden"]), int(spec.get("kernel_size", 3)), math.prod(in_dims[1:])
+            for name, o, i in (("in_convolutions.0", ch, d0), ("in_convolutions.1", 1, ch),
+                               ("out_convolutions.0", ch, 1), ("out_convolutions.1", d0, ch)):
+                bound = 1 / math.sqrt(i * k * k)
+                out[f"{p}{name}.weight"] = uni((o, i, k, k), bound)
+                out[f"{p}{name}.bias"] = uni((o,), bound).abs()       # keeps the rectified stack alive
+            for j in range(2):
+                out[f"{p}linear_layers.{j}.weight"] = uni((npix, npix), 1 / math.sqrt(npix))
+                out[f"{p}linear_layers.{j}.bias"] = uni((npix,), 1 / math.sqrt(npix)).abs()
         elif layer["kind"] == "coupling" and spec.get("conditioner") in ("convnet2d", "condconvnet2d"):
             def conv(name, n_out, n_in, k):
                 bound = 1 / math.sqrt(n_in * k * k)

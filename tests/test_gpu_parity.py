@@ -573,3 +573,23 @@ def test_plain_torch_distribution_object_as_the_base_on_gpu(name):
     ts = training.TrainStep(plain, U.SophiaG(list(plain.parameters()), lr=1e-4, weight_decay=0.0), distributed=False)
     l0 = float(ts.step(arr["x"].cuda()))
     assert l0 == l0 and abs(l0 + float(arr["lp64"].mean())) < 1e-3 * max(1.0, abs(l0))
+
+
+def test_bottleneck_conv_flow_on_gpu():
+    """networks.BottleneckConv conditioner (networks.py:754-824): reference outputs through the layer-by-layer route on the
+    device (gather + contraction kernels incl. the 1-channel convolutions), a training step, `log_prob_host`."""
+    import usflows_b200 as U
+    spec, params, arr = load_case("img_bottleneck_c4_5x4")
+    flow = build_flow(spec, params, precision="fp32")
+    x = arr["x"].cuda()
+    lp = flow.log_prob(x)
+    assert rel_err(lp, arr["lp64"]) <= TOL["fp32"][0] + 3 * rel_err(arr["lp32"], arr["lp64"])
+    assert rel_err(flow.backward(x), arr["z64"]) <= TOL["fp32"][1] + 4 * rel_err(arr["z32"], arr["z64"])
+    assert rel_err(flow._forward(arr["z0"].cuda()), arr["y64"]) <= TOL["fp32"][1] + 4 * rel_err(arr["y32"], arr["y64"])
+    assert rel_err(flow.log_prob_host(arr["x"]), lp) < 1e-6
+    s = flow.sample([64])
+    assert s.shape == (64, 4, 5, 4) and bool(torch.isfinite(s).all())
+    from usflows_b200 import training
+    ts = training.TrainStep(flow, U.SophiaG(list(flow.parameters()), lr=1e-4, weight_decay=0.0), distributed=False)
+    l0 = float(ts.step(x))
+    assert abs(l0 + float(arr["lp64"].mean())) < 1e-3 * max(1.0, abs(l0))

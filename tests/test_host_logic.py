@@ -363,3 +363,49 @@ def test_additive_affine_nn(fake_ops):
     L = net.loc_fnc.layers
     want = L[2](torch.relu(L[1](torch.relu(L[0](x))))).detach()
     assert rel_err(loc, want) < 1e-6 and log_scale.shape == loc.shape and not log_scale.any()
+
+
+def test_bottleneck_conv_conditioner_runs_layer_by_layer(fake_ops):
+    """networks.BottleneckConv (networks.py:754-824) as the coupling conditioner of an image-shaped USFlow: the reference's
+    outputs through the layer-by-layer route (no fused launch program exists for it), reference state-dict keys."""
+    import usflows_b200 as U
+    spec, params, arr = load_case("img_bottleneck_c4_5x4")
+    flow = build_flow(spec, params, device="cpu", precision="fp32")
+    assert flow._layer_route and not flow._programs
+    assert rel_err(flow.log_prob(arr["x"]), arr["lp32"]) < 2e-5
+    assert rel_err(flow.backward(arr["x"]), arr["z32"]) < 5e-5
+    assert rel_err(flow._forward(arr["z0"]), arr["y32"]) < 5e-5
+    assert tuple(flow.sample([3]).shape) == (3, 4, 5, 4) and not flow._programs
+    assert rel_err(flow.log_prob_host(arr["x"]), arr["lp32"]) < 2e-5
+    net = U.BottleneckConv(4, None, None, [4, 5, 4], c_hidden=6)
+    assert sorted(net.state_dict()) == sorted(f"{g}.{i}.{n}" for g in ("in_convolutions", "linear_layers", "out_convolutions")
+                                               for i in (0, 1) for n in ("weight", "bias"))
+    x = torch.rand(3, 4, 5, 4)
+    want = x
+    for conv in net.in_convolutions:
+        want = torch.relu(conv(want))
+    want = want.view(3, -1)
+    for lin in net.linear_layers:
+        want = torch.relu(lin(want))
+    want = want.view(3, 1, 5, 4)
+    for conv in net.out_convolutions:
+        want = torch.relu(conv(want))
+    assert net(x).shape == (3, 4, 5, 4) and rel_err(net(x), want.detach()) < 1e-5
+    # gradients of the training pass against autograd through the oracle
+    from usflows_b200 import training
+    from oracle import flow_oracle as O
+    loss = -training.log_prob_autograd(flow, arr["x"][:12]).mean()
+    loss.backward()
+    p = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in params.items()}
+    want_loss = -O.flow_log_prob(arr["x"][:12], spec, p).mean()
+    want_loss.backward()
+    assert abs(float(loss.detach()) - float(want_loss.detach())) <= 2e-5 * max(1.0, abs(float(want_loss.detach())))
+    got = dict(flow.named_parameters())
+    checked = 0
+    for key in got:
+        if "conditioner" in key:
+            g, w = got[key].grad, p[key].grad
+            assert g is not None and w is not None, key
+            assert float((g - w).abs().max()) <= 2e-4 * max(1.0, float(w.abs().max())), key
+            checked += 1
+    assert checked == 24

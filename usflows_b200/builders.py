@@ -52,6 +52,10 @@ def build_flow(spec, params=None, device="cuda", precision=None):
                          normalize_layers=spec.get("normalize_layers", True), kernel_size=spec.get("kernel_size", 3))
         if cond_cls is U.CondConvNet:
             cond_args["c_out"] = d
+    elif spec.get("conditioner") == "bottleneck":
+        cond_cls = U.BottleneckConv
+        cond_args = dict(c_in=d, c_hidden_in=None, c_hidden_out=None, in_dims=list(spec["in_dims"]),
+                         c_hidden=spec["c_hidden"], kernel_size=spec.get("kernel_size", 3))
     elif spec.get("conditioner") == "conddense":
         cond_cls = U.ConditionalDenseNN
         cond_args = dict(input_dim=d, context_dim=1, hidden_dims=list(spec["hidden_dims"]), out_dim=d)

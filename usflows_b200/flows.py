@@ -127,11 +127,14 @@ class Flow(torch.nn.Module):
         # flows.py:45-67) from the zero context that a soft-training USFlow substitutes in `log_prob` / `sample`
         # (flows.py:559-565, 580-590: the context layer's bias stays) -- two launch programs per direction
         self._cond_dense_nets = []
+        self._layer_route = False             # a conditioner without a fused lowering (networks.BottleneckConv)
         for l in layers:
             while isinstance(l, InverseTransform):
                 l = l.transform
             if isinstance(l, MaskedCoupling) and hasattr(l.conditioner, "zero_context_default"):
                 self._cond_dense_nets.append(l.conditioner)
+            if isinstance(l, MaskedCoupling) and getattr(l.conditioner, "layer_route_only", False):
+                self._layer_route = True
         self._zero_ctx = bool(soft_training and self._context_needs_soft_training)
         self.precision = precision
         self.to(device)
@@ -193,7 +196,7 @@ class Flow(torch.nn.Module):
             self._require_conditional()
         elif self._context_needs_soft_training:
             context = None                    # USFlow.log_prob drops the context unless soft_training (flows.py:559-567)
-        if context is not None:
+        if context is not None or self._layer_route:
             return self._with_context("log_prob", x, context)
         with ops.on_device(x):                # no context = context 0 (flows.py:559-565): the conditional conditioners
             return self._log_prob(x)          # are lowered without their context input, which is exact
@@ -217,7 +220,8 @@ class Flow(torch.nn.Module):
         ev = len(self._event_shape())
         batch_shape = x.shape[:x.dim() - ev]
         x2 = x.reshape(-1, *x.shape[x.dim() - ev:])
-        context = torch.as_tensor(context, dtype=torch.float32, device=x.device)
+        if context is not None:
+            context = torch.as_tensor(context, dtype=torch.float32, device=x.device)
         with torch.no_grad(), ops.on_device(x):
             if what == "log_prob":
                 return training.log_prob_autograd(self, x2, context).reshape(batch_shape)
@@ -386,6 +390,12 @@ class Flow(torch.nn.Module):
 
     def _log_prob_host(self, x_host, out_host, chunk_rows):
         dev = next(self.parameters()).device
+        if self._layer_route:                 # no launch program to overlap the copies with: plain chunks
+            out = torch.empty(x_host.shape[0], dtype=torch.float32) if out_host is None else out_host
+            step = max(1, chunk_rows or 8192)
+            for r0 in range(0, x_host.shape[0], step):
+                out[r0:r0 + step].copy_(self.log_prob(x_host[r0:r0 + step].to(dev)))
+            return out
         prog, ladj = self._program("backward", self._zero_ctx)
         base = self._base_module()
         base._prepared()                  # parameter-side work happens here, outside any graph capture
@@ -636,6 +646,8 @@ class Flow(torch.nn.Module):
         return y
 
     def _run(self, direction: str, x: torch.Tensor, zero_ctx: bool = False) -> torch.Tensor:
+        if self._layer_route:
+            return self._with_context(direction, x, None)
         x2, batch_shape = engine._flatten_rows(x, len(self._event_shape()))
         with torch.no_grad(), ops.on_device(x2):
             prog, _ = self._program(direction, zero_ctx)

@@ -417,3 +417,36 @@ class CondConvNet2D(ConvNet2D):
             c_out = c_in
         super().__init__(c_in=c_in + 1, c_hidden=c_hidden, c_out=c_out, num_layers=num_layers, nonlinearity=nonlinearity,
                          kernel_size=kernel_size, stride=stride, dilation=dilation, padding=padding, **kwargs)
+
+
+class BottleneckConv(torch.nn.Module):
+    """`networks.BottleneckConv` (networks.py:754-824): two 'same' convolutions down to ONE channel, two Linear layers over
+    the flattened pixels, two convolutions back up to `c_in` channels, a ReLU after every layer (the output included).
+    State-dict keys as the reference (`in_convolutions.<i>`, `linear_layers.<i>`, `out_convolutions.<i>`); `c_hidden_in` /
+    `c_hidden_out` are accepted and unused, as there.  No configuration of the reference uses it; a flow with this
+    conditioner is evaluated layer by layer (training.py: every convolution / Linear a contraction on the library's
+    kernels), not through a fused launch program."""
+
+    layer_route_only = True
+
+    def __init__(self, c_in, c_hidden_in, c_hidden_out, in_dims, c_hidden: int = 3, nonlinearity=torch.nn.ReLU(),
+                 kernel_size: int = 3):
+        super().__init__()
+        _require_relu(nonlinearity)
+        self.in_dims = list(in_dims)
+        self.n_pixels = 1
+        for n in self.in_dims[1:]:
+            self.n_pixels *= int(n)
+        conv = lambda i, o: torch.nn.Conv2d(i, o, kernel_size=kernel_size, padding="same")   # noqa: E731
+        self.in_convolutions = torch.nn.ModuleList([conv(c_in, c_hidden), conv(c_hidden, 1)])
+        self.linear_layers = torch.nn.ModuleList([torch.nn.Linear(self.n_pixels, self.n_pixels) for _ in range(2)])
+        self.out_convolutions = torch.nn.ModuleList([conv(1, c_hidden), conv(c_hidden, c_in)])
+        self.nonlinearity = nonlinearity
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        from . import training
+        C, H, W = x.shape[-3:]
+        rows = x.reshape(-1, C, H * W).transpose(1, 2).reshape(-1, C)              # channels-last rows
+        with torch.no_grad():
+            out = training._bottleneck_rows(self, rows, (C, H, W))
+        return out.reshape(-1, H * W, out.shape[1]).transpose(1, 2).reshape(*x.shape[:-3], out.shape[1], H, W)

@@ -190,7 +190,11 @@ def _layer_backward(layer, y: torch.Tensor, inverse: bool = False, cache: Option
         C, H, W = geom
         m = layer.mask.reshape(C, H * W).t().to(y.dtype)                # channels-last mask [H*W, C]
         y3 = y.reshape(-1, H * W, C)
-        t = _convnet2d_rows(layer.conditioner, (y3 * m).reshape(-1, C), geom, context).reshape(-1, H * W, C)
+        rows = (y3 * m).reshape(-1, C)
+        if getattr(layer.conditioner, "layer_route_only", False):      # networks.BottleneckConv
+            t = _bottleneck_rows(layer.conditioner, rows, geom).reshape(-1, H * W, C)
+        else:
+            t = _convnet2d_rows(layer.conditioner, rows, geom, context).reshape(-1, H * W, C)
         t = (1 - m) * t
         return ((y3 + t) if inverse else (y3 - t)).reshape(-1, C), y.new_zeros(())
     if isinstance(layer, T.MaskedCoupling):
@@ -308,6 +312,22 @@ def _convnet2d_rows(net, x: torch.Tensor, geom, context: Optional[torch.Tensor] 
             ln = blk["ln"]
             h = torch.nn.functional.layer_norm(h, (h.shape[1],), ln.gamma.reshape(-1), ln.beta.reshape(-1), ln.eps)
     return _conv_rows(h, d["last"], geom)
+
+
+def _bottleneck_rows(net, x: torch.Tensor, geom) -> torch.Tensor:
+    """networks.BottleneckConv.forward (networks.py:802-824) over channels-last rows [N*H*W, C]: convolutions down to one
+    channel, the flattened pixels [N, H*W] through two Linear layers, convolutions back up; a ReLU after every layer."""
+    C, H, W = geom
+    h = x
+    for conv in net.in_convolutions:
+        h = torch.relu(_conv_rows(h, conv, geom))
+    h = h.reshape(-1, H * W)                               # one channel left: a sample's rows are its flattened pixels
+    for lin in net.linear_layers:
+        h = torch.relu(linear(h, lin.weight, lin.bias))
+    h = h.reshape(-1, 1)
+    for conv in net.out_convolutions:
+        h = torch.relu(_conv_rows(h, conv, geom))
+    return h
 
 
 def _radial_log_prob(b, z: torch.Tensor) -> torch.Tensor:
