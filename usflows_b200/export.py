@@ -127,6 +127,9 @@ class ReferenceSemantics(torch.nn.Module):
     def _net_plan(net, reg, start):
         """Op list of a ConvNet (vector) / ConvNet2D conditioner; tensors are registered in order, ops refer to them by
         position (networks.py:222-245, 287-307 / 61-121, 441-494)."""
+        if not hasattr(net, "_describe"):
+            raise NotImplementedError(f"usflows_b200: the exportable reference semantics do not cover {type(net).__name__} "
+                                      "conditioners")
         d = net._describe()
         conv = "conv1" in (d["blocks"][0] if d["blocks"] else {}) or hasattr(net, "kernel_size")
         plan, n = [], [1]                            # tensor 0 of the layer is the mask
