@@ -27,7 +27,9 @@ MG = importlib.util.module_from_spec(_spec)
 _spec.loader.exec_module(MG)
 
 CASES = ["c1_d2_laplace", "d6_hh_normal", "d5_noconj", "d32_h64", "d100_h50_hh", "d64_convnet", "d32_radial_inf",
-         "img_c4_4x4", "img_mnist_16x7x7", "img_c6_5x3_plain_channel"]
+         "img_c4_4x4", "img_mnist_16x7x7", "img_c6_5x3_plain_channel",
+         # a soft-training flow over ConditionalDenseNN: the simplified flow is a plain `Flow`, which substitutes no zero context
+         "soft_d40_conddense"]
 
 
 def main():
