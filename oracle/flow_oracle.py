@@ -20,11 +20,15 @@ the reference has no test for it, so that single function is "parity unpinned" a
 
 The model is described by
   spec  : dict(in_dims, coupling_blocks, hidden_dims, affine_conjugation, lu_transform, householder,
-               base ("laplace"|"normal"|"radial" with p (1|2|"inf"), norm ("lognormal"|"gammamm"), n_comp),
+               base ("laplace"|"normal"|"radial" with p (1|2|"inf"), norm ("lognormal"|"gammamm"|"gamma"|"chi"|"chi2"|
+                     "halfnormal"|"weibull"|"exponential"|"torchlognormal"|"weibullmm"|"lognormalmm" with n_comp / df /
+                     chi_scale / w_scale / w_conc / rate / ln_loc / ln_scale)),
                masktype ("checkerboard"|"channel"),
                conditioner ("densenn" (default) | "convnet" with c_hidden, gating, normalize_layers
                             | "convnet2d" with c_hidden (int), num_layers, kernel_size, gating, normalize_layers: image-shaped
-                              in_dims = [C, H, W]))
+                              in_dims = [C, H, W]
+                            | "condconvnet" / "condconvnet2d" / "conddense" (context-conditioned; soft_training, `_context`)
+                            | "bottleneck" (networks.BottleneckConv)))
   params: dict name -> torch CPU tensor, keyed exactly like the reference `USFlow.state_dict()`.
 """
 from __future__ import annotations
