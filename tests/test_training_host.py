@@ -160,6 +160,7 @@ def _dp_worker(rank, world, port, name, tmp, rows=90):
     spec, params, arr = _dp_case(name, rows)
     flow = build_flow(spec, params, device="cpu")
     np.random.seed(7)
+    torch.manual_seed(11)                      # soft training: every rank draws the global batch's noise (same stream)
     data = torch.utils.data.TensorDataset(arr["x"][:rows])
     losses = flow.fit(data, optim=torch.optim.SGD, optim_params=dict(lr=1e-4), batch_size=rows // 3 if rows >= 30 else rows // 2,
                       gradient_clip=1.0, device="cpu", epochs=1)
@@ -171,7 +172,8 @@ def _dp_worker(rank, world, port, name, tmp, rows=90):
 
 @pytest.mark.parametrize("name,port,rows", [("d6_hh_normal", 29517, 90), ("img_c4_4x4", 29518, 24),
                                             ("d64_convnet_proj_radial2", 29519, 40),
-                                            ("engine:conj_laplace_3layer", 29520, 99)])
+                                            ("engine:conj_laplace_3layer", 29520, 99),
+                                            ("soft_d40_conddense", 29521, 32)])     # SoftFlow noise + context under DP
 def test_data_parallel_fit_matches_single_process(fake_ops, tmp_path, name, port, rows):
     """world_size 2 over gloo: sharded batches + one gradient all-reduce == the single-process mean-loss step (flat DenseNN
     flow, image-shaped ConvNet2D flow, ConvNet conditioner with a radial base)."""
@@ -181,6 +183,7 @@ def test_data_parallel_fit_matches_single_process(fake_ops, tmp_path, name, port
     spec, params, arr = _dp_case(name, rows)
     flow = build_flow(spec, params, device="cpu")
     np.random.seed(7)
+    torch.manual_seed(11)
     data = torch.utils.data.TensorDataset(arr["x"][:rows])
     losses = flow.fit(data, optim=torch.optim.SGD, optim_params=dict(lr=1e-4), batch_size=rows // 3 if rows >= 30 else rows // 2,
                       gradient_clip=1.0, device="cpu", epochs=1, distributed=False)
