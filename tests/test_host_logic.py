@@ -409,3 +409,55 @@ def test_bottleneck_conv_conditioner_runs_layer_by_layer(fake_ops):
             assert float((g - w).abs().max()) <= 2e-4 * max(1.0, float(w.abs().max())), key
             checked += 1
     assert checked == 24
+
+
+def test_reference_accessors(fake_ops):
+    """Small pieces of the reference's surface around the path: `LUTransform.to_linear` (transforms.py:1365-1369),
+    `HouseholderTransform._construct_householder_permutation` (:795-809), the Transform properties (:195-202, 247-251),
+    `DistributionModule.distribution` (distributions.py:129-138), `RadialDistribution.log_delta_volume` (:514-549), a
+    radius distribution's own `log_prob` / `sample`."""
+    import math
+    import usflows_b200 as U
+    from oracle import flow_oracle as O
+    torch.manual_seed(3)
+    lu = U.LUTransform(6, prior_scale=1.0)
+    lin = lu.to_linear()
+    W = (lu.L_raw.tril(-1) + torch.eye(6)) @ lu.U_raw.triu()
+    assert rel_err(lin.forth.weight.detach(), torch.linalg.inv(W.double())) < 1e-5
+    assert rel_err(lin.back.weight.detach(), W.detach()) < 1e-6
+    assert abs(float(lin.log_abs_det_jacobian(None, None)) + float(lu.log_abs_det_jacobian(None, None))) < 1e-5
+    hh = U.HouseholderTransform(5, nvs=2)
+    want = hh.w_0.detach().double()
+    for v in hh.vk_householder.detach().double():
+        want = want @ (torch.eye(5, dtype=torch.float64) - 2 * torch.outer(v, v) / v.dot(v))
+    assert rel_err(hh._construct_householder_permutation(), want) < 1e-6
+    perm = U.Permute(torch.randperm(6))
+    assert perm.with_cache(1) is perm and perm.domain.event_dim == 1 and perm.codomain.event_dim == 1
+    lap = U.Laplace(torch.zeros(4), 2 * torch.ones(4))
+    d = lap.distribution
+    assert isinstance(d, torch.distributions.Independent) and tuple(d.event_shape) == (4,)
+    x = torch.randn(7, 4)
+    assert rel_err(lap.log_prob(x), d.log_prob(x).detach()) < 1e-6
+    assert abs(float(U.Normal(torch.zeros(3), torch.ones(3)).distribution.entropy()) - 3 * 0.5 * math.log(2 * math.pi * math.e)) < 1e-5
+    rd = U.RadialDistribution(torch.zeros(9), U.LogNormal(torch.ones(1), torch.ones(1)), p=2.0)
+    r = torch.tensor([0.5, 1.0, 3.0], dtype=torch.float64)
+    for p in (1.0, 2.0, math.inf):
+        assert rel_err(rd.log_delta_volume(p, r), O.radial_log_delta_volume(p, r, 9)) < 1e-12
+    # a radius distribution on its own: log f_R(r) and draws of R
+    for nd, ref in ((U.Chi(5.0, 1.5), O._Chi(torch.tensor(5.0), 1.5)),
+                    (U.GammaMM(torch.tensor([2.0, 3.0]), torch.tensor([1.0, 0.5]), torch.tensor([0.2, -0.1])), None),
+                    (U.LogNormal(torch.tensor([0.3]), torch.tensor([0.4])), torch.distributions.LogNormal(0.3, 0.4))):
+        rr = torch.rand(11, 1) * 3 + 0.1
+        got = nd.log_prob(rr)
+        assert got.shape == (11,)
+        if ref is None:
+            sp = torch.nn.functional.softplus
+            ref = torch.distributions.MixtureSameFamily(torch.distributions.Categorical(logits=nd.mixture_logits.detach()),
+                                                        torch.distributions.Gamma(sp(nd.concentration_unconstrained.detach()),
+                                                                                  sp(nd.rate_unconstrained.detach())))
+            want = ref.log_prob(rr[:, 0])
+        else:
+            want = ref.log_prob(rr)[:, 0]
+        assert rel_err(got, want) < 1e-5
+        s = nd.sample([50])
+        assert s.shape == (50, 1) and bool((s > 0).all())

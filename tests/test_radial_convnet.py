@@ -401,3 +401,25 @@ def test_ext_cases_host_rows_path(name):
     flow = build_flow(spec, params)
     out = flow.log_prob_host(arr["x"].pin_memory())
     assert rel_err(out, arr["lp32"]) <= 1e-5
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("norm", ALL_NORMS)
+def test_radius_distribution_on_its_own(norm):
+    """`norm_distribution.log_prob(r)` / `.sample(shape)` outside a RadialDistribution (the reference's DistributionModule
+    surface, distributions.py:147-151): the radial kernels on a one-dimensional event."""
+    spec = _radial_spec(2, norm, 24, K=5)
+    params = O.random_params(spec, 17)
+    nd = _radial_module(spec, params).norm_distribution
+    ref = O.radial_norm_distribution(spec, O._cast(params, torch.float64))
+    r = (torch.rand(1000, 1, dtype=torch.float64) * 12 + 0.05)
+    want = ref.log_prob(r)
+    want = want[:, 0] if want.dim() == 2 else want
+    got = nd.log_prob(r.float().cuda())
+    assert got.shape == (1000,) and rel_err(got, want) <= 1e-5
+    torch.manual_seed(5)
+    s = nd.sample([100000])
+    assert s.shape == (100000, 1) and bool((s > 0).all()) and bool(torch.isfinite(s).all())
+    rs = ref.sample((200000,)).double().reshape(-1)
+    sd = float(rs.std())
+    assert abs(float(s.double().mean()) - float(rs.mean())) < 8 * sd / math.sqrt(100000)

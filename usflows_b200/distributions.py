@@ -68,6 +68,22 @@ class DistributionModule(Module):
     def batch_shape(self) -> torch.Size:
         return torch.Size(self.loc.shape[:self.n_batch_dims])
 
+    def _get_distribution_params(self):
+        """Current constrained parameters (distributions.py:141-143, 211-215, 234-238)."""
+        raw = self.scale_unconstrained
+        if raw.dim() == 0:
+            raw = raw.expand_as(self.loc)
+        return {"loc": self.loc, "scale": torch.nn.functional.softplus(raw)}
+
+    @property
+    def distribution(self) -> torch.distributions.Distribution:
+        """The `torch.distributions` object the reference rebuilds on every access (distributions.py:129-138), for callers
+        that want it (entropy, cdf, ...); `log_prob` / `sample` of this module run the fused kernels instead."""
+        cls = torch.distributions.Laplace if self.base_kind == ops.BASE_LAPLACE else torch.distributions.Normal
+        d = cls(**self._get_distribution_params())
+        extra = len(d.batch_shape) - self.n_batch_dims
+        return torch.distributions.Independent(d, extra) if extra > 0 else d
+
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         return self.log_prob(x)
 
@@ -121,9 +137,14 @@ class _FrozenBase(DistributionModule):
                                       "Normal, RadialDistribution modules and torch Laplace / Normal objects are)")
         loc, scale = torch.broadcast_tensors(torch.as_tensor(dist.loc, dtype=torch.float32),
                                              torch.as_tensor(dist.scale, dtype=torch.float32))
-        self.distribution = dist
+        self._torch_dist = dist
         self.register_buffer("loc", loc.detach().clone(), persistent=False)
         self.register_buffer("scale_unconstrained", inv_softplus(scale.detach().clone()), persistent=False)
+
+    @property
+    def distribution(self) -> torch.distributions.Distribution:
+        d = self._torch_dist
+        return torch.distributions.Independent(d, len(d.batch_shape)) if len(d.batch_shape) else d
 
 
 class Independent(Module):
@@ -183,10 +204,30 @@ class _RadiusDistribution(Module):
             self._prep_key = key
         return self._prep_cache
 
-    def log_prob(self, r):
-        raise NotImplementedError("usflows_b200: radius distributions are evaluated as part of a RadialDistribution")
+    def log_prob(self, r: torch.Tensor) -> torch.Tensor:
+        """log f_R(r) on its own (the reference's `DistributionModule.log_prob`, distributions.py:150-151): the radial
+        density kernel on a one-dimensional event -- ||r||_inf = |r|, volume term switched off."""
+        ops.require_cuda(r, "radius")
+        kind, K, params = self._norm_params()
+        flat = r.reshape(-1, 1).contiguous()
+        out = torch.empty(flat.shape[0], dtype=torch.float32, device=flat.device)
+        if flat.shape[0]:
+            with ops.on_device(flat):
+                ops.radial_logprob(ops.Act(flat.shape[0], 1, f32=flat), torch.zeros(1, device=flat.device), ops.LP_INF, kind,
+                                   params, K, 0.0, 0.0, out)
+        shape = r.shape[:-1] if r.dim() and r.shape[-1] == 1 else r.shape      # the radius arrives as [..., 1] (:508)
+        return out.reshape(shape)
 
-    sample = log_prob
+    def sample(self, sample_shape=None) -> torch.Tensor:
+        """Draws of R (the radial sampling kernel on a one-dimensional event: the Lp-sphere direction is +1)."""
+        from . import engine
+        kind, K, params = self._norm_params()
+        shape = [int(n) for n in (sample_shape if sample_shape is not None else [])]
+        out = torch.empty(max(1, math.prod(shape)), 1, dtype=torch.float32, device=params.device)
+        seed, offset = engine.philox_call_stream(out.device)
+        with ops.on_device(out):
+            ops.radial_sample(out, torch.zeros(1, device=out.device), ops.LP_INF, kind, params, K, seed, offset)
+        return out.reshape(*shape, 1)
 
 
 def _softplus_vec(raw: torch.Tensor) -> torch.Tensor:
@@ -497,14 +538,23 @@ class RadialDistribution(Module):
     def _p_kind(self) -> int:
         return ops.LP_1 if self.p == 1.0 else ops.LP_2 if self.p == 2.0 else ops.LP_INF
 
+    @staticmethod
+    def _dv_const(p: float, d: int) -> float:
+        if p == 1.0:             # (2r)^(d-1) 2 / (d-1)!   as written at :527-531
+            return math.log(2) * d - sum(math.log(i) for i in range(1, d))
+        if p == 2.0:             # d pi^(d/2) r^(d-1) / Gamma(d/2 + 1)
+            return math.log(d) + (d / 2) * math.log(math.pi) - math.lgamma(d / 2 + 1)
+        if p == math.inf:
+            return math.log(d) + d * math.log(2)
+        raise ValueError(f"p={p} not implemented. Use p=1,2, or infinity")
+
     def log_delta_volume_const(self) -> float:
         """r-independent part of log dV_p^d/dr (distributions.py:514-549): the full value is this + (d - 1) log r."""
-        d = self.dim
-        if self.p == 1.0:        # (2r)^(d-1) 2 / (d-1)!   as written at :527-531
-            return math.log(2) * d - sum(math.log(i) for i in range(1, d))
-        if self.p == 2.0:        # d pi^(d/2) r^(d-1) / Gamma(d/2 + 1)
-            return math.log(d) + (d / 2) * math.log(math.pi) - math.lgamma(d / 2 + 1)
-        return math.log(d) + d * math.log(2)
+        return self._dv_const(self.p, self.dim)
+
+    def log_delta_volume(self, p: float, r):
+        """log dV_p^d/dr at radius r (distributions.py:514-549): the constant above + (d - 1) log r."""
+        return self._dv_const(float(p), self.dim) + (self.dim - 1) * torch.log(torch.as_tensor(r))
 
     def _prepared(self):
         ops.require_cuda(self.loc, "base_distribution.loc")

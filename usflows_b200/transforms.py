@@ -73,6 +73,19 @@ class BaseTransform(nn.Module):
     def sign(self):
         return 1
 
+    # the pyro / torch `Transform` surface the reference's layers inherit (transforms.py:195-202, 247-251): every layer
+    # maps real vectors (one event dim) to real vectors and keeps no value cache
+    @property
+    def domain(self):
+        return torch.distributions.constraints.independent(torch.distributions.constraints.real, 1)
+
+    @property
+    def codomain(self):
+        return torch.distributions.constraints.independent(torch.distributions.constraints.real, 1)
+
+    def with_cache(self, cache_size: int = 1):
+        return self
+
     # engine hooks -------------------------------------------------------------------------------
     def _ladj_device(self) -> Optional[torch.Tensor]:
         """Device tensor [2] = (forward log|det J|, #infeasible entries), or None when identically 0."""
@@ -344,6 +357,14 @@ class LUTransform(AffineTransform):
         return dict(matrix=W, inverse_matrix=Winv, bias=self.bias_vector.detach(), ladj=ladj,
                     L=L, U=U, L_inv=Linv, U_inv=Uinv, matrix64=W64, inverse64=Winv64)
 
+    def to_linear(self) -> "PlaneBijectiveLinearTransform":
+        """transforms.py:1365-1369 as written there: `M_inv = L @ U`, `M = inverse(M_inv)`,
+        `PlaneBijectiveLinearTransform(dim, M, bias_vector, M_inv)` -- the plain layer whose `forth` weight is (L U)^-1
+        (`simplify()` / `_to_plane_linear` above is the one whose forward equals this layer's)."""
+        p = self._prepared()
+        return PlaneBijectiveLinearTransform(self.dim, p["inverse_matrix"].clone(), self.bias_vector,
+                                             p["matrix"].clone(), ladj=-p["ladj"][0].clone())
+
     @property
     def L(self) -> torch.Tensor:
         return self._prepared()["L"]
@@ -511,6 +532,10 @@ class HouseholderTransform(AffineTransform):
         self.vk_householder = nn.Parameter(0.2 * torch.randn(nvs, dim))
         self.w_0 = nn.Parameter(w, requires_grad=False)
         self.to(device)
+
+    def _construct_householder_permutation(self) -> torch.Tensor:
+        """w_0 prod_k (I - 2 v_k v_k^T / v_k.v_k)  (transforms.py:795-809): the prepared matrix."""
+        return self.matrix()
 
     def _prepare(self) -> dict:
         d, dev = self.dim, self.w_0.device
