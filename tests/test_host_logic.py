@@ -443,6 +443,11 @@ def test_reference_accessors(fake_ops):
     r = torch.tensor([0.5, 1.0, 3.0], dtype=torch.float64)
     for p in (1.0, 2.0, math.inf):
         assert rel_err(rd.log_delta_volume(p, r), O.radial_log_delta_volume(p, r, 9)) < 1e-12
+    chi = U.Chi(5.0, 1.5)                      # cdf / entropy as the reference's Chi states them (distributions.py:98-115)
+    v = torch.tensor([0.5, 2.0, 4.0])
+    ref_chi2 = torch.distributions.Chi2(torch.tensor(5.0))
+    assert torch.allclose(chi.cdf(v), ref_chi2.cdf((v / 1.5) ** 2))
+    assert abs(float(chi.entropy()) - float(ref_chi2.entropy() / 2 + math.log(2) + math.log(1.5))) < 1e-6
     # a radius distribution on its own: log f_R(r) and draws of R
     for nd, ref in ((U.Chi(5.0, 1.5), O._Chi(torch.tensor(5.0), 1.5)),
                     (U.GammaMM(torch.tensor([2.0, 3.0]), torch.tensor([1.0, 0.5]), torch.tensor([0.2, -0.1])), None),

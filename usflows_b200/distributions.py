@@ -427,6 +427,14 @@ class Chi(_GammaFamily):
         return (torch.zeros_like(self._df), self._df / 2, torch.full_like(self._df, 0.5), self._scale,
                 torch.full_like(self._df, 2.0))
 
+    # the two closed forms the reference's class adds to log_prob / sample (distributions.py:98-115); accessors, evaluated
+    # through torch's Chi2 like there
+    def cdf(self, value: torch.Tensor) -> torch.Tensor:
+        return torch.distributions.Chi2(self._df.to(value.device)).cdf((value / self.scale) ** 2)
+
+    def entropy(self) -> torch.Tensor:
+        return torch.distributions.Chi2(self._df).entropy() / 2 + math.log(2.0) + math.log(float(self.scale))
+
 
 def _frozen(t) -> torch.Tensor:
     return torch.as_tensor(t, dtype=torch.float32).detach().reshape(-1).clone()
