@@ -71,7 +71,8 @@ def test_invalid_arguments_fail_loudly_without_gpu():
 
 
 def test_sass_contains_blackwell_tensor_and_tma_instructions():
-    """tcgen05.mma -> UTC*MMA, TMA -> UTMALDG, tcgen05.ld -> LDTM (B200_PROFILING.md)."""
+    """tcgen05.mma -> UTC*MMA, TMA -> UTMALDG, tcgen05.ld -> LDTM (B200_PROFILING.md); the fp64 products of the weight
+    preparation -> DMMA (mma.sync.m8n8k4.f64: the fp64 tensor-core path of sm_100a)."""
     import shutil
     import subprocess
     from usflows_b200 import _lib
@@ -80,7 +81,7 @@ def test_sass_contains_blackwell_tensor_and_tma_instructions():
         pytest.skip("cuobjdump not available")
     _lib.load()
     sass = subprocess.run([cuobjdump, "-sass", _lib.library_path()], capture_output=True, text=True).stdout
-    for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM"):
+    for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM", "DMMA"):
         assert mnemonic in sass, mnemonic
     assert "sm_100a" in sass
 
